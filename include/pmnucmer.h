@@ -1,0 +1,123 @@
+/*
+ * pmnucmer.h — C ABI of libpmnucmer.so, the B200-native pairwise nucmer stage.
+ *
+ * What it replaces in the reference (orbitz/paramugsy):
+ *   the child process started by  lib/nucmer/mugsy_nucmer.ml:100
+ *       Shell.sh "nucmer %s %s -p %s %s" ref_file query_file obname options.nucmer_opts
+ *   which must leave  <obname>.delta  behind (lib/nucmer/mugsy_nucmer.ml:97-98).
+ * The reference has no FFI of its own (`grep -rn external lib` is empty);
+ * these entry points are what an OCaml `external` stub in lib/nucmer would bind
+ * (INTEGRATION.md shows the stub).  Plain C types only; no exception crosses the boundary.
+ *
+ * Error convention: 0 on success, negative on failure with a message in pmn_last_error().
+ * The reference's convention is "non-zero child exit => Shell.sh raises"
+ * (lib/nucmer/mugsy_nucmer.ml:100, lib/base/local_interface.ml:28-35 retries).
+ *
+ * There is NO CPU fallback: every entry point that computes fails with PMN_E_NOGPU when
+ * no CUDA device is usable.
+ */
+#ifndef PMNUCMER_H
+#define PMNUCMER_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PMN_OK          0
+#define PMN_E_ARG      (-1)   /* bad argument / malformed FASTA / unsupported option */
+#define PMN_E_CUDA     (-2)   /* a CUDA call failed */
+#define PMN_E_NOMEM    (-3)
+#define PMN_E_IO       (-4)
+#define PMN_E_NOGPU    (-5)
+#define PMN_E_INTERNAL (-6)
+
+typedef struct pmn_ctx pmn_ctx;       /* one per (process, GPU); owns a stream and all scratch memory */
+typedef struct pmn_seq pmn_seq;       /* a multi-FASTA file packed on the device (both strands)        */
+typedef struct pmn_index pmn_index;   /* suffix array + LCP + k-mer bucket table of a pmn_seq          */
+typedef struct pmn_result pmn_result; /* the .delta text of one pair plus counters                     */
+
+/* nucmer's command-line tunables (defaults = MUMmer 3.20 nucmer, which is what the
+ * reference always runs: lib/base/nucmer_task.ml:53 passes no -nucmer_opts). */
+typedef struct pmn_opts {
+    int32_t minmatch;      /* -l  20   */
+    int32_t mincluster;    /* -c  65   */
+    int32_t maxgap;        /* -g  90   */
+    int32_t diagdiff;      /* -D  5    */
+    double  diagfactor;    /* -d  0.12 */
+    int32_t breaklen;      /* -b  200  */
+    int32_t do_forward;    /* 0 with -r */
+    int32_t do_reverse;    /* 0 with -f */
+    int32_t do_extend;     /* --[no]extend   */
+    int32_t do_optimize;   /* --[no]optimize; only 1 is implemented */
+    int32_t do_simplify;   /* --[no]simplify */
+    int32_t keep_stages;   /* 1: keep anchors / clusters / alignments in the result (tests) */
+} pmn_opts;
+
+typedef struct pmn_stats {
+    int64_t ref_bases, qry_bases;
+    int64_t anchors, clusters, cluster_matches, alignments, aligned_ref_bases;
+    int64_t dp_cells;            /* cells evaluated by the extension engine            */
+    int64_t dp_jobs;             /* alignment-engine invocations                       */
+    int32_t sa_rounds;           /* prefix-doubling rounds after the 16-mer pass       */
+    int32_t kmer_bits;           /* 2*K of the bucket table                            */
+    float   ms_index, ms_seed, ms_cluster, ms_extend, ms_total;   /* CUDA-event times  */
+    int64_t kernel_launches;     /* kernels launched for this pair                     */
+} pmn_stats;
+
+void pmn_default_opts(pmn_opts *o);
+
+/* ---- context ---- */
+int  pmn_ctx_create(int device, pmn_ctx **out);
+void pmn_ctx_destroy(pmn_ctx *c);
+const char *pmn_last_error(const pmn_ctx *c);      /* c may be NULL: last error of the calling thread */
+int  pmn_device_count(void);
+
+/* ---- sequences: FASTA bytes in HOST memory -> packed text in HBM ---- */
+int  pmn_seq_from_fasta(pmn_ctx *c, const char *fasta, size_t bytes, pmn_seq **out);
+int  pmn_seq_from_file(pmn_ctx *c, const char *path, pmn_seq **out);
+void pmn_seq_free(pmn_seq *s);
+int64_t pmn_seq_bases(const pmn_seq *s);           /* concatenated, incl. one separator between records */
+int  pmn_seq_records(const pmn_seq *s);
+
+/* ---- index of a reference (kept by the caller while it aligns queries against it) ---- */
+int  pmn_index_build(pmn_ctx *c, const pmn_seq *ref, pmn_index **out);
+void pmn_index_free(pmn_index *ix);
+
+/* ---- one pair: seeding, clustering, extension, .delta text (host memory) ----
+ * ref_path / qry_path are only echoed on line 1 of the .delta
+ * (lib/profiles/m_delta.ml:56 splits it on the last space). */
+int  pmn_align(pmn_ctx *c, const pmn_index *ix, const pmn_seq *qry, const pmn_opts *o,
+               const char *ref_path, const char *qry_path, pmn_result **out);
+const char *pmn_result_delta(const pmn_result *r, size_t *len);
+void pmn_result_stats(const pmn_result *r, pmn_stats *out);
+void pmn_result_free(pmn_result *r);
+
+/* ---- file level: exactly the job of the `nucmer` child process ----
+ * Writes out_delta_path atomically (tmp + rename) so that a retry
+ * (lib/base/local_interface.ml:28-35) never sees a partial file. */
+int  pmn_align_pair(pmn_ctx *c, const char *ref_fasta_path, const char *qry_fasta_path,
+                    const pmn_opts *o, const char *out_delta_path);
+
+/* The batch unit of the reference is Nucmer_task.t.searches (lib/base/nucmer_task.ml:6):
+ * a list of (ref, query) paths.  Pairs that share a reference reuse its index. */
+int  pmn_align_batch(pmn_ctx *c, int n, const char *const *ref_fasta_paths, const char *const *qry_fasta_paths,
+                     const char *const *out_delta_paths, const pmn_opts *o);
+
+/* ---- stage dumps for the parity tests (sizes via the n_* calls; buffers are caller-owned) ---- */
+int64_t pmn_index_size(const pmn_index *ix);
+int  pmn_index_copy_sa(const pmn_index *ix, int32_t *sa_out, int32_t *lcp_out);
+int64_t pmn_result_n_anchors(const pmn_result *r);
+int  pmn_result_copy_anchors(const pmn_result *r, int32_t *out /* n x 4 */);
+int64_t pmn_result_n_clusters(const pmn_result *r);
+int64_t pmn_result_n_cluster_matches(const pmn_result *r);
+int  pmn_result_copy_clusters(const pmn_result *r, int32_t *matches /* m x 3 */, int32_t *off /* k+1 */, int32_t *tag /* k */);
+int64_t pmn_result_n_alignments(const pmn_result *r);
+int64_t pmn_result_n_deltas(const pmn_result *r);
+int  pmn_result_copy_alignments(const pmn_result *r, int64_t *rows /* a x 10 */, int64_t *doff /* a+1 */, int64_t *deltas);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -833,7 +833,7 @@ int pmo_stage_extend(pmo_run *r)
         uint8_t *br = (uint8_t *)xmalloc((size_t)lenB + 1); revcomp_codes(bf, lenB, br);
         /* postnuc input parsing: clusters of this query record (forward section, then
          * reverse), each split where consecutive matches fall into different reference
-         * records; one synteny per reference record, in order of first appearance */
+         * records; one synteny per reference record */
         int nsyn = 0; int *syn_ref = (int *)xmalloc(sizeof(int) * (size_t)r->ref.nrec);
         synteny_ctx *S = (synteny_ctx *)xmalloc(sizeof(synteny_ctx) * (size_t)r->ref.nrec);
         int *capC = (int *)xmalloc(sizeof(int) * (size_t)r->ref.nrec);
@@ -859,6 +859,13 @@ int pmo_stage_extend(pmo_run *r)
                 match_t m = { sA, sB, len }; cur->m[cur->nm++] = m;
             }
         }
+        /* syntenies of one query record are written in reference-record order (ORACLE_SPEC.md §6) */
+        for (int a = 1; a < nsyn; a++)
+            for (int b = a; b > 0 && syn_ref[b - 1] > syn_ref[b]; b--) {
+                int t = syn_ref[b]; syn_ref[b] = syn_ref[b - 1]; syn_ref[b - 1] = t;
+                synteny_ctx ts = S[b]; S[b] = S[b - 1]; S[b - 1] = ts;
+                int tc = capC[b]; capC[b] = capC[b - 1]; capC[b - 1] = tc;
+            }
         int rc = 0;
         for (int s = 0; s < nsyn && rc == 0; s++) {
             rc = extend_clusters(&S[s]);

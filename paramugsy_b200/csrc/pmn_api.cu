@@ -1,0 +1,381 @@
+// pmn_api.cu — the C ABI of include/pmnucmer.h: context, FASTA -> HBM, index, one pair,
+// batch, .delta text.  Replaces the `nucmer` child process of
+// /root/reference/lib/nucmer/mugsy_nucmer.ml:96-100 (see INTEGRATION.md for the OCaml stub).
+#include <algorithm>
+#include <cerrno>
+#include <cstdarg>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <unistd.h>
+#include <vector>
+
+#include "pmn_scratch.cuh"
+
+// ------------------------------------------------------------------------------------ errors
+
+static thread_local PmnError g_err;
+
+int pmn_set_error(int code, const char *fmt, ...)
+{
+    g_err.code = code;
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err.msg, sizeof g_err.msg, fmt, ap); va_end(ap);
+    return code;
+}
+
+extern "C" const char *pmn_last_error(const pmn_ctx *) { return g_err.msg; }
+
+extern "C" void pmn_default_opts(pmn_opts *o)
+{
+    o->minmatch = PMN_DEF_MINMATCH; o->mincluster = PMN_DEF_MINCLUSTER; o->maxgap = PMN_DEF_MAXGAP;
+    o->diagdiff = PMN_DEF_DIAGDIFF; o->diagfactor = PMN_DEF_DIAGFACTOR; o->breaklen = PMN_DEF_BREAKLEN;
+    o->do_forward = 1; o->do_reverse = 1; o->do_extend = 1; o->do_optimize = 1; o->do_simplify = 1; o->keep_stages = 0;
+}
+
+// ------------------------------------------------------------------------------------ context
+
+Scratch *pmn_scratch_new() { return new Scratch(); }
+void pmn_scratch_free(Scratch *s)
+{
+    if (!s) return;
+    DevBuf *bufs[] = { &s->rs.hist, &s->rs.spine, &s->k0, &s->k1, &s->v0, &s->v1, &s->scan_tmp, &s->codes, &s->gs, &s->rank, &s->flags,
+                       &s->list0, &s->list1, &s->gsn, &s->sections, &s->stage, &s->tile_cnt, &s->tile_off, &s->anchors,
+                       &s->cl_a, &s->cl_b, &s->cl_c, &s->cl_d, &s->cl_e, &s->cl_f, &s->cl_g, &s->cl_h, &s->cl_i, &s->cl_j, &s->cl_k, &s->cl_l,
+                       &s->cl_matches, &s->cl_recs, &s->cl_counters,
+                       &s->ex_a, &s->ex_b, &s->ex_c, &s->ex_d, &s->ex_e, &s->ex_f, &s->ex_g, &s->ex_h, &s->ex_i, &s->ex_j, &s->ex_k, &s->ex_l,
+                       &s->ex_scores, &s->ex_tb, &s->ex_tbidx, &s->ex_pool, &s->ex_counters, &s->ex_arena };
+    for (DevBuf *b : bufs) b->release();
+    if (s->pinned) cudaFreeHost(s->pinned);
+    delete s;
+}
+
+extern "C" int pmn_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int pmn_ctx_create(int device, pmn_ctx **out)
+{
+    if (!out) return pmn_set_error(PMN_E_ARG, "pmn_ctx_create: out is NULL");
+    *out = nullptr;
+    int n = pmn_device_count();
+    if (n <= 0) return pmn_set_error(PMN_E_NOGPU, "no CUDA device: libpmnucmer has no CPU path");
+    if (device < 0 || device >= n) return pmn_set_error(PMN_E_ARG, "device %d out of range (have %d)", device, n);
+    PMN_CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PMN_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return pmn_set_error(PMN_E_NOGPU, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    pmn_ctx *c = new pmn_ctx();
+    c->device = device; c->sm_count = prop.multiProcessorCount;
+    PMN_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto &e : c->ev) PMN_CUDA_OK(cudaEventCreate(&e));
+    c->scratch = pmn_scratch_new();
+    *out = c;
+    return 0;
+}
+
+extern "C" void pmn_ctx_destroy(pmn_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    pmn_scratch_free(c->scratch);
+    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+// ------------------------------------------------------------------------------------ FASTA
+
+// Like `mummer -n`: only a/c/g/t (either case) can match, everything else becomes code X.
+// Record ids = first token of the header (what the '>' line of a .delta carries; the
+// reference rewrites headers to species.accession, lib/base/m_rewrite_fasta.ml:5-59).
+static int parse_fasta_host(const char *txt, size_t nb, pmn_seq *s, std::vector<uint8_t> &codes)
+{
+    static uint8_t lut[256]; static bool init = false;
+    if (!init) {
+        memset(lut, PMN_CODE_X, sizeof lut);
+        lut['a'] = lut['A'] = PMN_CODE_A; lut['c'] = lut['C'] = PMN_CODE_C; lut['g'] = lut['G'] = PMN_CODE_G; lut['t'] = lut['T'] = PMN_CODE_T;
+        lut[' '] = lut['\t'] = lut['\r'] = lut['\n'] = lut['\v'] = lut['\f'] = 0xff;
+        init = true;
+    }
+    codes.clear(); codes.reserve(nb + 16);
+    size_t i = 0; int cur = -1; bool any_x = false;
+    while (i < nb) {
+        const char *nl = (const char *)memchr(txt + i, '\n', nb - i);
+        size_t e = nl ? (size_t)(nl - txt) : nb;
+        if (e > i && txt[i] == '>') {
+            size_t a = i + 1; while (a < e && (txt[a] == ' ' || txt[a] == '\t')) a++;
+            size_t b = a; while (b < e && lut[(unsigned char)txt[b]] != 0xff) b++;
+            if (cur >= 0) codes.push_back(PMN_CODE_X);
+            cur = s->nrec++;
+            s->ids.emplace_back(txt + a, b - a);
+            s->off.push_back((int64_t)codes.size()); s->len.push_back(0);
+        } else if (cur >= 0) {
+            size_t before = codes.size();
+            for (size_t k = i; k < e; k++) { uint8_t c = lut[(unsigned char)txt[k]]; if (c != 0xff) { codes.push_back(c); any_x |= c == PMN_CODE_X; } }
+            s->len[cur] += (int64_t)(codes.size() - before);
+        } else {
+            for (size_t k = i; k < e; k++) if (lut[(unsigned char)txt[k]] != 0xff) return pmn_set_error(PMN_E_ARG, "FASTA: sequence data before the first '>' header");
+        }
+        i = e + 1;
+    }
+    if (s->nrec == 0) return pmn_set_error(PMN_E_ARG, "FASTA: no records");
+    if (s->nrec > 32767) return pmn_set_error(PMN_E_ARG, "FASTA: more than 32767 records");
+    s->n = (int64_t)codes.size();
+    if (s->n > 0x7ffffff0ll) return pmn_set_error(PMN_E_ARG, "FASTA: more than 2^31 bases");
+    s->has_x = (any_x || s->nrec > 1) ? 1 : 0;
+    return 0;
+}
+
+extern "C" int pmn_seq_from_fasta(pmn_ctx *c, const char *fasta, size_t bytes, pmn_seq **out)
+{
+    if (!c || !out || (!fasta && bytes)) return pmn_set_error(PMN_E_ARG, "pmn_seq_from_fasta: NULL argument");
+    *out = nullptr;
+    PMN_CUDA_OK(cudaSetDevice(c->device));
+    std::unique_ptr<pmn_seq> s(new pmn_seq());
+    s->ctx = c;
+    std::vector<uint8_t> codes;
+    int rc = parse_fasta_host(fasta, bytes, s.get(), codes);
+    if (rc) return rc;
+    codes.resize(codes.size() + 64, PMN_CODE_X);
+    rc = pmn_pack_upload(c, s.get(), codes.data());
+    if (rc) return rc;
+    *out = s.release();
+    return 0;
+}
+
+static int read_file(const char *path, std::string &out)
+{
+    FILE *f = fopen(path, "rb");
+    if (!f) return pmn_set_error(PMN_E_IO, "cannot open %s: %s", path, strerror(errno));
+    char buf[1 << 16]; size_t k;
+    out.clear();
+    while ((k = fread(buf, 1, sizeof buf, f)) > 0) out.append(buf, k);
+    int bad = ferror(f); fclose(f);
+    if (bad) return pmn_set_error(PMN_E_IO, "read error on %s", path);
+    return 0;
+}
+
+extern "C" int pmn_seq_from_file(pmn_ctx *c, const char *path, pmn_seq **out)
+{
+    if (!path) return pmn_set_error(PMN_E_ARG, "pmn_seq_from_file: NULL path");
+    std::string txt;
+    int rc = read_file(path, txt);
+    if (rc) return rc;
+    return pmn_seq_from_fasta(c, txt.data(), txt.size(), out);
+}
+
+extern "C" void pmn_seq_free(pmn_seq *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    s->w_fwd.release(); s->xm_fwd.release(); s->w_rev.release(); s->xm_rev.release();
+    delete s;
+}
+extern "C" int64_t pmn_seq_bases(const pmn_seq *s) { return s ? s->n : 0; }
+extern "C" int pmn_seq_records(const pmn_seq *s) { return s ? s->nrec : 0; }
+
+// ------------------------------------------------------------------------------------ index
+
+extern "C" int pmn_index_build(pmn_ctx *c, const pmn_seq *ref, pmn_index **out)
+{
+    if (!c || !ref || !out) return pmn_set_error(PMN_E_ARG, "pmn_index_build: NULL argument");
+    *out = nullptr;
+    PMN_CUDA_OK(cudaSetDevice(c->device));
+    std::unique_ptr<pmn_index> ix(new pmn_index());
+    int rc = pmn_index_build_impl(c, ref, ix.get());
+    if (rc) { ix->sa.release(); ix->lcp.release(); ix->table.release(); return rc; }
+    *out = ix.release();
+    return 0;
+}
+
+extern "C" void pmn_index_free(pmn_index *ix)
+{
+    if (!ix) return;
+    cudaSetDevice(ix->ctx->device);
+    ix->sa.release(); ix->lcp.release(); ix->table.release();
+    delete ix;
+}
+
+extern "C" int64_t pmn_index_size(const pmn_index *ix) { return ix ? ix->n : 0; }
+
+extern "C" int pmn_index_copy_sa(const pmn_index *ix, int32_t *sa_out, int32_t *lcp_out)
+{
+    if (!ix) return pmn_set_error(PMN_E_ARG, "pmn_index_copy_sa: NULL index");
+    PMN_CUDA_OK(cudaSetDevice(ix->ctx->device));
+    if (sa_out) PMN_CUDA_OK(cudaMemcpy(sa_out, ix->sa.p, 4 * (size_t)ix->n, cudaMemcpyDeviceToHost));
+    if (lcp_out) PMN_CUDA_OK(cudaMemcpy(lcp_out, ix->lcp.p, 4 * (size_t)ix->n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ one pair
+
+// .delta grammar exactly as the reference parses it: lib/profiles_lib/m_delta.cc:72-92 (two
+// header lines), :154-162 ('>' line), :177-185 (seven ints), :187-196 (deltas up to "0");
+// lib/profiles/m_delta.ml:76-79,91 needs single spaces and no trailing blanks.
+static void write_delta_text(const pmn_seq *ref, const pmn_seq *qry, const char *ref_path, const char *qry_path, pmn_result *r)
+{
+    std::string &t = r->delta;
+    t.clear();
+    t += ref_path; t += ' '; t += qry_path; t += "\nNUCMER\n";
+    char buf[256];
+    size_t na = r->al_rows.size() / 10; int64_t prev_r = -1, prev_q = -1;
+    int64_t aligned = 0;
+    for (size_t k = 0; k < na; k++) {
+        const int64_t *a = &r->al_rows[k * 10];
+        if (a[0] != prev_r || a[1] != prev_q) {
+            t += '>'; t += ref->ids[(size_t)a[0]]; t += ' '; t += qry->ids[(size_t)a[1]];
+            snprintf(buf, sizeof buf, " %lld %lld\n", (long long)ref->len[(size_t)a[0]], (long long)qry->len[(size_t)a[1]]); t += buf;
+            prev_r = a[0]; prev_q = a[1];
+        }
+        int64_t sB = a[5], eB = a[6], lenB = qry->len[(size_t)a[1]];
+        if (a[2]) { sB = lenB - sB + 1; eB = lenB - eB + 1; }
+        snprintf(buf, sizeof buf, "%lld %lld %lld %lld %lld %lld %lld\n", (long long)a[3], (long long)a[4], (long long)sB, (long long)eB,
+                 (long long)a[7], (long long)a[8], (long long)a[9]);
+        t += buf;
+        for (int64_t d = r->al_doff[k]; d < r->al_doff[k + 1]; d++) { snprintf(buf, sizeof buf, "%lld\n", (long long)r->al_deltas[(size_t)d]); t += buf; }
+        t += "0\n";
+        aligned += a[4] - a[3] + 1;
+    }
+    r->stats.alignments = (int64_t)na;
+    r->stats.aligned_ref_bases = aligned;
+}
+
+extern "C" int pmn_align(pmn_ctx *c, const pmn_index *ix, const pmn_seq *qry, const pmn_opts *o_in,
+                         const char *ref_path, const char *qry_path, pmn_result **out)
+{
+    if (!c || !ix || !qry || !out) return pmn_set_error(PMN_E_ARG, "pmn_align: NULL argument");
+    *out = nullptr;
+    pmn_opts o; if (o_in) o = *o_in; else pmn_default_opts(&o);
+    if (!o.do_optimize) return pmn_set_error(PMN_E_ARG, "--nooptimize is not supported");
+    if (o.minmatch < 1 || o.maxgap < 0 || o.breaklen < 1 || o.mincluster < 0 || o.diagdiff < 0 || o.diagfactor < 0)
+        return pmn_set_error(PMN_E_ARG, "pmn_align: option out of range");
+    PMN_CUDA_OK(cudaSetDevice(c->device));
+    Scratch &S = *c->scratch;
+    cudaStream_t st = c->stream;
+    std::unique_ptr<pmn_result> r(new pmn_result());
+    long launches0 = c->launches;
+    r->stats.ref_bases = ix->n; r->stats.qry_bases = qry->n;
+    r->stats.sa_rounds = ix->rounds; r->stats.kmer_bits = 2 * ix->K; r->stats.ms_index = ix->ms_build;
+
+    PMN_CUDA_OK(cudaEventRecord(c->ev[2], st));
+    int64_t nanc = 0;
+    int rc = pmn_seed_impl(c, ix, qry, &o, &nanc);
+    if (rc) return rc;
+    PMN_CUDA_OK(cudaEventRecord(c->ev[3], st));
+    r->stats.anchors = nanc;
+    if (o.keep_stages && nanc > 0) {
+        r->anchors.resize((size_t)nanc * 4);
+        PMN_CUDA_OK(cudaMemcpyAsync(r->anchors.data(), S.anchors.p, 16 * (size_t)nanc, cudaMemcpyDeviceToHost, st));
+        PMN_CUDA_OK(cudaStreamSynchronize(st));
+    }
+    rc = pmn_cluster_impl(c, ix, qry, &o, nanc);
+    if (rc) return rc;
+    PMN_CUDA_OK(cudaEventRecord(c->ev[4], st));
+    rc = pmn_extend_impl(c, ix, qry, &o, r.get());
+    if (rc) return rc;
+    PMN_CUDA_OK(cudaEventRecord(c->ev[5], st));
+    PMN_CUDA_OK(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&r->stats.ms_seed, c->ev[2], c->ev[3]);
+    cudaEventElapsedTime(&r->stats.ms_cluster, c->ev[3], c->ev[4]);
+    cudaEventElapsedTime(&r->stats.ms_extend, c->ev[4], c->ev[5]);
+    cudaEventElapsedTime(&r->stats.ms_total, c->ev[2], c->ev[5]);
+    write_delta_text(ix->seq, qry, ref_path ? ref_path : "ref", qry_path ? qry_path : "qry", r.get());
+    r->stats.kernel_launches = c->launches - launches0;
+    *out = r.release();
+    return 0;
+}
+
+extern "C" const char *pmn_result_delta(const pmn_result *r, size_t *len) { if (len) *len = r ? r->delta.size() : 0; return r ? r->delta.c_str() : ""; }
+extern "C" void pmn_result_stats(const pmn_result *r, pmn_stats *out) { if (r && out) *out = r->stats; }
+extern "C" void pmn_result_free(pmn_result *r) { delete r; }
+
+extern "C" int64_t pmn_result_n_anchors(const pmn_result *r) { return r ? (int64_t)r->anchors.size() / 4 : 0; }
+extern "C" int pmn_result_copy_anchors(const pmn_result *r, int32_t *out)
+{
+    if (!r || !out) return pmn_set_error(PMN_E_ARG, "NULL argument");
+    memcpy(out, r->anchors.data(), r->anchors.size() * 4); return 0;
+}
+extern "C" int64_t pmn_result_n_clusters(const pmn_result *r) { return r ? (int64_t)r->cl_tag.size() : 0; }
+extern "C" int64_t pmn_result_n_cluster_matches(const pmn_result *r) { return r ? (int64_t)r->cl_matches.size() / 3 : 0; }
+extern "C" int pmn_result_copy_clusters(const pmn_result *r, int32_t *matches, int32_t *off, int32_t *tag)
+{
+    if (!r) return pmn_set_error(PMN_E_ARG, "NULL argument");
+    if (matches) memcpy(matches, r->cl_matches.data(), r->cl_matches.size() * 4);
+    if (off) memcpy(off, r->cl_off.data(), r->cl_off.size() * 4);
+    if (tag) memcpy(tag, r->cl_tag.data(), r->cl_tag.size() * 4);
+    return 0;
+}
+extern "C" int64_t pmn_result_n_alignments(const pmn_result *r) { return r ? (int64_t)r->al_rows.size() / 10 : 0; }
+extern "C" int64_t pmn_result_n_deltas(const pmn_result *r) { return r ? (int64_t)r->al_deltas.size() : 0; }
+extern "C" int pmn_result_copy_alignments(const pmn_result *r, int64_t *rows, int64_t *doff, int64_t *deltas)
+{
+    if (!r) return pmn_set_error(PMN_E_ARG, "NULL argument");
+    if (rows) memcpy(rows, r->al_rows.data(), r->al_rows.size() * 8);
+    if (doff) memcpy(doff, r->al_doff.data(), r->al_doff.size() * 8);
+    if (deltas) memcpy(deltas, r->al_deltas.data(), r->al_deltas.size() * 8);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ file level
+
+static int write_file_atomic(const char *path, const std::string &data)
+{
+    std::string tmp = std::string(path) + ".tmp." + std::to_string((long)getpid());
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f) return pmn_set_error(PMN_E_IO, "cannot create %s: %s", tmp.c_str(), strerror(errno));
+    size_t k = fwrite(data.data(), 1, data.size(), f);
+    int bad = (k != data.size()) | (fclose(f) != 0);
+    if (bad) { unlink(tmp.c_str()); return pmn_set_error(PMN_E_IO, "write error on %s", tmp.c_str()); }
+    if (rename(tmp.c_str(), path) != 0) { unlink(tmp.c_str()); return pmn_set_error(PMN_E_IO, "cannot rename to %s: %s", path, strerror(errno)); }
+    return 0;
+}
+
+extern "C" int pmn_align_batch(pmn_ctx *c, int n, const char *const *refs, const char *const *qrys, const char *const *outs, const pmn_opts *o)
+{
+    if (!c || n < 0 || (n && (!refs || !qrys || !outs))) return pmn_set_error(PMN_E_ARG, "pmn_align_batch: bad argument");
+    // pairs are processed grouped by reference so that every index is built once; sequences
+    // used several times are packed once
+    std::map<std::string, pmn_seq *> seqs;
+    std::map<std::string, pmn_index *> idx;
+    int rc = 0;
+    auto get_seq = [&](const char *p, pmn_seq **s) -> int {
+        auto it = seqs.find(p);
+        if (it != seqs.end()) { *s = it->second; return 0; }
+        int e = pmn_seq_from_file(c, p, s);
+        if (!e) seqs[p] = *s;
+        return e;
+    };
+    std::vector<int> order(n);
+    for (int i = 0; i < n; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return strcmp(refs[a], refs[b]) < 0; });
+    std::string cur_ref; pmn_index *cur_ix = nullptr;
+    for (int oi = 0; oi < n && !rc; oi++) {
+        int i = order[oi];
+        if (!refs[i] || !qrys[i] || !outs[i]) { rc = pmn_set_error(PMN_E_ARG, "pmn_align_batch: NULL path in pair %d", i); break; }
+        if (!cur_ix || cur_ref != refs[i]) {
+            if (cur_ix) { pmn_index_free(cur_ix); cur_ix = nullptr; }
+            pmn_seq *rs; rc = get_seq(refs[i], &rs); if (rc) break;
+            rc = pmn_index_build(c, rs, &cur_ix); if (rc) break;
+            cur_ref = refs[i];
+        }
+        pmn_seq *qs; rc = get_seq(qrys[i], &qs); if (rc) break;
+        pmn_result *res = nullptr;
+        rc = pmn_align(c, cur_ix, qs, o, refs[i], qrys[i], &res); if (rc) break;
+        rc = write_file_atomic(outs[i], res->delta);
+        pmn_result_free(res);
+    }
+    if (cur_ix) pmn_index_free(cur_ix);
+    for (auto &kv : seqs) pmn_seq_free(kv.second);
+    return rc;
+}
+
+extern "C" int pmn_align_pair(pmn_ctx *c, const char *ref_fasta_path, const char *qry_fasta_path, const pmn_opts *o, const char *out_delta_path)
+{
+    const char *r[1] = { ref_fasta_path }, *q[1] = { qry_fasta_path }, *d[1] = { out_delta_path };
+    return pmn_align_batch(c, 1, r, q, d, o);
+}

@@ -1,0 +1,111 @@
+// pmn_common.cuh — shared declarations of the B200 pairwise-nucmer path (sm_100a only).
+//
+// Data layout in HBM:
+//   packed text   uint64 words, 32 bases per word, base k of a word in bits [63-2k, 62-2k]
+//                 (MSB first, so unsigned integer order of a window == lexicographic order)
+//   x-mask        uint32 words, 32 bases per word, bit 31-k set when base k matches nothing
+//                 (non-acgt, record separator, and everything past the end of the text)
+//   both arrays carry PMN_PAD_WORDS words of padding on each side of nothing: the text is
+//   zero-padded and the mask one-padded behind the last base, so a 32-base window can be
+//   fetched at any position 0..n without a bounds test.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+
+#include "../../include/pmn_params.h"
+
+#define PMN_PAD_WORDS 96   /* >= seeding tile words + slack, see pmn_seed.cu */
+
+struct PmnError { int code; char msg[480]; };
+
+#define PMN_CUDA_OK(call)                                                                     \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            pmn_set_error(-2, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return -2;                                                                        \
+        }                                                                                     \
+    } while (0)
+
+int pmn_set_error(int code, const char *fmt, ...);
+
+// ---- a grow-only device buffer: no cudaMalloc at steady state -------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; cap = 0; return pmn_set_error(-3, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return (T *)p; }
+};
+
+// ---- device view of one packed sequence set ---------------------------------------------------
+struct PackedView {
+    const uint64_t *w;     // 2-bit text
+    const uint32_t *xm;    // x-mask
+    int64_t n;             // bases incl. separators
+    int has_x;             // 0: plain acgt, the mask is never read
+};
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint64_t pmn_window64(const uint64_t *__restrict__ w, int64_t p)
+{
+    int64_t k = p >> 5; int sh = (int)(p & 31) * 2;
+    uint64_t a = __ldg(w + k), b = __ldg(w + k + 1);
+    return sh ? (a << sh) | (b >> (64 - sh)) : a;
+}
+
+__device__ __forceinline__ uint32_t pmn_xwindow32(const uint32_t *__restrict__ xm, int64_t p)
+{
+    int64_t k = p >> 5; int sh = (int)(p & 31);
+    uint32_t a = __ldg(xm + k), b = __ldg(xm + k + 1);
+    return __funnelshift_l(b, a, sh);
+}
+
+// number of matchable bases among the 32 starting at p (stops at the first X or at the end)
+__device__ __forceinline__ int pmn_valid32(const PackedView &s, int64_t p)
+{
+    if (p >= s.n) return 0;
+    if (s.has_x) { uint32_t x = pmn_xwindow32(s.xm, p); return x ? __clz((int)x) : 32; }
+    int64_t r = s.n - p;
+    return r < 32 ? (int)r : 32;
+}
+
+__device__ __forceinline__ int pmn_base_at(const PackedView &s, int64_t p)   // 0..3, or 4
+{
+    if (p < 0 || p >= s.n) return PMN_CODE_X;
+    if (s.has_x && ((__ldg(s.xm + (p >> 5)) >> (31 - (int)(p & 31))) & 1u)) return PMN_CODE_X;
+    return (int)((__ldg(s.w + (p >> 5)) >> (62 - 2 * (int)(p & 31))) & 3ull);
+}
+
+// common prefix (in matchable bases) of a[pa..] and b[pb..], starting the comparison at
+// offset `from` (bases before it are known equal), capped at `cap`
+__device__ __forceinline__ int64_t pmn_lcp(const PackedView &a, int64_t pa, const PackedView &b, int64_t pb, int64_t from, int64_t cap)
+{
+    int64_t l = from;
+    while (l < cap) {
+        int va = pmn_valid32(a, pa + l), vb = pmn_valid32(b, pb + l);
+        int v = va < vb ? va : vb;
+        uint64_t x = pmn_window64(a.w, pa + l) ^ pmn_window64(b.w, pb + l);
+        int m = x ? (__clzll((long long)x) >> 1) : 32;
+        if (m > v) m = v;
+        l += m;
+        if (m < 32) break;
+    }
+    return l < cap ? l : cap;
+}
+
+__device__ __forceinline__ unsigned pmn_lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+
+#endif  // __CUDACC__

@@ -1,0 +1,841 @@
+// pmn_extend.cu — banded affine-gap extension between and beyond the anchors of each cluster,
+// alignment stitching, error counts.
+//
+// Stands in for `postnuc -b 200` (+ sw_align) inside the `nucmer` child process of
+// /root/reference/lib/nucmer/mugsy_nucmer.ml:100.  Oracle counterpart: oracle/pmn_oracle.c §6
+// (align_engine) and §7 (extend_clusters, extend_forward, extend_backward, parse_delta) —
+// alignment rows and delta lists must be identical.
+//
+// Organisation:
+//   E1  clusters are split per reference record, grouped into syntenies (query record x
+//       reference record) and sorted by (synteny, first reference start, mgaps order)
+//   E2  WAVE 1, fully parallel: every forward alignment of postnuc is a pure function of the
+//       cluster list (match -> next match inside a cluster; last match -> target cluster),
+//       so all of them run at once, one warp per job, persistent warps pulling jobs
+//   E3  STITCH, one warp per synteny: the sequential control flow of extendClusters
+//       (merging, shadow test, backward extension) consumes the wave-1 results; the few
+//       alignments that depend on earlier outcomes (backward searches, forced merges) run
+//       inline on the same warp with the same engine
+//   E4  flatten the delta lists, count errors (parseDelta), copy to the host
+//
+// The engine is an anti-diagonal DP: the cells of one anti-diagonal are striped over the 32
+// lanes, the two previous anti-diagonals live in a shared-memory ring (global memory when the
+// band outgrows it), high score / band trimming are warp reductions and ballots.  Integer
+// ALUs only.
+#include <algorithm>
+
+#include "pmn_scratch.cuh"
+
+#define EX_RW 256                      /* shared-memory ring width (cells) per score row          */
+#define EX_WCAP (PMN_MAX_ALIGNMENT_LENGTH + 8)   /* global score row capacity                    */
+#define EX_ROWS 12                     /* 3 anti-diagonals x (DEL, INS, MAT, cell max)            */
+#define EX_DMAX (2 * PMN_MAX_ALIGNMENT_LENGTH + 8)
+#define EX_TBW (1u << 20)              /* private traceback bytes per warp slot                   */
+#define EX_TB_HDR ((size_t)EX_DMAX * 16)   /* tboff (8) + tblo (4) + reversed deltas (4) per diagonal */
+#define EX_ARENA_CHUNK (256u << 10)
+#define EX_WARPS_PER_BLOCK 4
+
+#define EX_ERR_POOL 1
+#define EX_ERR_ARENA 2
+#define EX_ERR_LOGIC 4
+#define EX_ERR_NODES 8
+
+struct ExCluster { int32_t mfirst, nm, dir, syn, order, pad; };
+struct ExSynteny {
+    int32_t cfirst, nC, qrec, rrec;
+    int64_t Abase, lenA, BbaseF, BbaseR, lenB;     // *base: 0-based concat index of the record's first base
+    int32_t alfirst, alcap, nodefirst, nodecap;
+};
+struct ExJob { int32_t endA, endB, dcnt, target; uint32_t doff; int32_t reached, valid, pad; };
+struct ExAlign { int32_t dirB, sA, sB, eA, eB, deltaApos, head, tail, ndelta, live, pad0, pad1; };
+struct ExNode { uint32_t off; int32_t cnt, adjust, next; };
+
+struct ExShared {                       // everything the device code needs, passed by value
+    PackedView R, QF, QR;
+    const int32_t *mA, *mB, *mL;        // matches (local reference coordinate)
+    const ExCluster *cl; const ExSynteny *syn;
+    int nC, nS; int64_t nM;
+    ExJob *jobs; const int32_t *mcl;    // per match: result of its forward job, its cluster
+    ExAlign *al; ExNode *nodes;
+    int32_t *pool; uint32_t pool_cap;   // delta pool
+    uint8_t *arena; unsigned long long arena_cap;
+    int32_t *gscore; uint8_t *tbpriv;   // per warp slot: EX_ROWS*EX_WCAP ints, EX_TBW bytes
+    unsigned long long *counters;       // [0] pool cursor [1] arena cursor [2] cells [3] engine calls [4] error flags [5] job cursor A [6] job cursor B
+    int breaklen, do_extend, do_simplify;
+    int32_t *syn_nal;                   // alignments produced per synteny
+};
+
+// ------------------------------------------------------------------------------------ engine
+
+struct Eng {
+    const ExShared *X;
+    int32_t *ssc;          // shared-memory ring of this warp: EX_ROWS * EX_RW
+    int32_t *gsc;          // global rows of this warp
+    uint8_t *tbp;          // private traceback region
+    int lane;
+};
+
+__device__ __forceinline__ void score_edit(int del, int ins, int mat, int &val, int &used)
+{
+    if (del > ins) { if (del > mat) { val = del; used = PMN_ST_DEL; } else { val = mat; used = PMN_ST_MAT; } }
+    else if (ins > mat) { val = ins; used = PMN_ST_INS; }
+    else { val = mat; used = PMN_ST_MAT; }
+}
+__device__ __forceinline__ int max_state(int vD, int vI, int vM)
+{
+    if (vD > vI) return vD > vM ? PMN_ST_DEL : PMN_ST_MAT;
+    return vI > vM ? PMN_ST_INS : PMN_ST_MAT;
+}
+
+// One alignment.  All 32 lanes call with identical arguments and get identical results.
+// Returns reached (0/1); Aend/Bend become the finish cell.  Unless SEARCH, the deltas are
+// appended to the pool: *doff, *dcnt.
+__device__ int align_engine(const Eng &E, int64_t Abase, int64_t Astart, int64_t &Aend, const PackedView &Q, int64_t Bbase, int64_t Bstart, int64_t &Bend,
+                            unsigned m_o, uint32_t *doff, int32_t *dcnt)
+{
+    const ExShared &X = *E.X;
+    const int lane = E.lane;
+    const int dir = (m_o & PMN_DIRECTION_BIT) ? 1 : -1;
+    const int N = (int)(dir > 0 ? Aend - Astart + 1 : Astart - Aend + 1);
+    const int M = (int)(dir > 0 ? Bend - Bstart + 1 : Bstart - Bend + 1);
+    const bool forced = (m_o & PMN_FORCED_BIT) != 0, search = (m_o & PMN_SEARCH_BIT) != 0;
+    const int breaklen = X.breaklen;
+    const int max_diff = PMN_GOOD_SCORE * breaklen;
+    if (doff) { *doff = 0; *dcnt = 0; }
+    if (N < 1 || M < 1 || N > PMN_MAX_ALIGNMENT_LENGTH || M > PMN_MAX_ALIGNMENT_LENGTH) {
+        if (lane == 0) atomicOr(X.counters + 4, (unsigned long long)EX_ERR_LOGIC);
+        return 0;
+    }
+    if (lane == 0) atomicAdd(X.counters + 3, 1ull);
+
+    // score rows: ring in shared memory, or plain rows in global memory once the band is too wide
+    bool in_smem = true;
+    int32_t *base = E.ssc; int stride = EX_RW; int mask = EX_RW - 1;
+    int bpp = 0, bp = 1, bc = 2;
+#define SC(buf, st, j) base[((buf) * 4 + (st)) * stride + ((j) & mask)]
+
+    uint8_t **tboff = (uint8_t **)E.tbp;
+    int32_t *tblo = (int32_t *)(E.tbp + (size_t)EX_DMAX * 8);
+    int32_t *rev = (int32_t *)(E.tbp + (size_t)EX_DMAX * 12);
+    uint8_t *tcur = E.tbp + EX_TB_HDR, *tend = E.tbp + EX_TBW;     // current traceback chunk (warp-uniform)
+
+    int pplo = 1, pphi = 0, plo = 0, phi = 0, tlo = 0, thi = 0;
+    if (lane == 0) {
+        SC(bp, PMN_ST_DEL, 0) = PMN_NEG; SC(bp, PMN_ST_INS, 0) = PMN_NEG; SC(bp, PMN_ST_MAT, 0) = 0; SC(bp, 3, 0) = 0;
+        if (!search) { tboff[0] = tcur; tblo[0] = 0; tcur[0] = (uint8_t)(PMN_ST_NONE | PMN_ST_NONE << 2 | PMN_ST_NONE << 4 | PMN_ST_MAT << 6); }
+    }
+    if (!search) tcur += 1;
+    __syncwarp();
+
+    int high = 0, best_d = 0, best_j = 0, reached = 0;
+    unsigned long long cells = 0;
+    bool arena_fail = false;
+    for (int d = 1; d <= N + M; d++) {
+        if (!forced && d - best_d > breaklen) break;
+        const int clo = tlo > d - N ? tlo : d - N, chi = thi + 1 < M ? thi + 1 : M;
+        if (clo > chi) break;
+        const int width = chi - clo + 1;
+        if (in_smem && width > EX_RW) {
+            // move the two live anti-diagonals to global rows and carry on there
+            int32_t *g = E.gsc;
+            for (int st = 0; st < 4; st++) {
+                for (int j = plo + lane; j <= phi; j += 32) g[(bp * 4 + st) * EX_WCAP + j] = SC(bp, st, j);
+                for (int j = pplo + lane; j <= pphi; j += 32) g[(bpp * 4 + st) * EX_WCAP + j] = SC(bpp, st, j);
+            }
+            __syncwarp();
+            in_smem = false; base = g; stride = EX_WCAP; mask = -1;
+        }
+        uint8_t *trow = nullptr;
+        if (!search) {
+            if (tcur + width > tend) {
+                unsigned long long need = width > (int)EX_ARENA_CHUNK ? (unsigned long long)width : EX_ARENA_CHUNK, at = 0;
+                if (lane == 0) at = atomicAdd(X.counters + 1, need);
+                at = __shfl_sync(0xffffffffu, at, 0);
+                if (at + need > X.arena_cap) { arena_fail = true; break; }
+                tcur = X.arena + at; tend = tcur + need;
+            }
+            trow = tcur; tcur += width;
+            if (lane == 0) { tboff[d] = trow; tblo[d] = clo; }
+        }
+        long long dkey = LLONG_MIN;
+        for (int jb = clo; jb <= chi; jb += 32) {
+            const int j = jb + lane;
+            if (j <= chi) {
+                const int i = d - j;
+                int U0 = PMN_NEG, U1 = PMN_NEG, U2 = PMN_NEG, L0 = PMN_NEG, L1 = PMN_NEG, L2 = PMN_NEG, P0 = PMN_NEG, P1 = PMN_NEG, P2 = PMN_NEG;
+                if (j >= plo && j <= phi) { U0 = SC(bp, 0, j); U1 = SC(bp, 1, j); U2 = SC(bp, 2, j); }
+                if (j - 1 >= plo && j - 1 <= phi) { L0 = SC(bp, 0, j - 1); L1 = SC(bp, 1, j - 1); L2 = SC(bp, 2, j - 1); }
+                if (j - 1 >= pplo && j - 1 <= pphi) { P0 = SC(bpp, 0, j - 1); P1 = SC(bpp, 1, j - 1); P2 = SC(bpp, 2, j - 1); }
+                int s = PMN_BAD_SCORE;
+                if (i >= 1 && j >= 1) {
+                    int ca = pmn_base_at(X.R, Abase + Astart - 1 + (int64_t)dir * (i - 1));
+                    int cb = pmn_base_at(Q, Bbase + Bstart - 1 + (int64_t)dir * (j - 1));
+                    if (ca == cb && ca != PMN_CODE_X) s = PMN_GOOD_SCORE;
+                }
+                int vD, vI, vM, uD, uI, uM;
+                score_edit(L0 + PMN_CONT_GAP_SCORE, L1 + PMN_OPEN_GAP_SCORE, L2 + PMN_OPEN_GAP_SCORE, vD, uD);
+                score_edit(U0 + PMN_OPEN_GAP_SCORE, U1 + PMN_CONT_GAP_SCORE, U2 + PMN_OPEN_GAP_SCORE, vI, uI);
+                score_edit(P0 + s, P1 + s, P2 + s, vM, uM);
+                const int ms = max_state(vD, vI, vM);
+                const int cm = ms == PMN_ST_DEL ? vD : (ms == PMN_ST_INS ? vI : vM);
+                SC(bc, 0, j) = vD; SC(bc, 1, j) = vI; SC(bc, 2, j) = vM; SC(bc, 3, j) = cm;
+                if (!search) trow[j - clo] = (uint8_t)(uD | uI << 2 | uM << 4 | ms << 6);
+                long long key = (long long)cm * 4294967296ll + j;
+                if (key > dkey) dkey = key;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { long long k2 = __shfl_xor_sync(0xffffffffu, dkey, o); if (k2 > dkey) dkey = k2; }
+        cells += (unsigned long long)width;
+        __syncwarp();
+        {
+            // floor division by 2^32 recovers (cm, j) for negative cm as well
+            long long cmq = dkey >> 32; int dj = (int)(dkey - cmq * 4294967296ll);
+            int dmax = (int)cmq;
+            if (dmax >= high) { high = dmax; best_d = d; best_j = dj; }
+        }
+        if (d == N + M) { reached = 1; break; }
+        if (!forced) {
+            const int t = high - max_diff;
+            int nlo = chi + 1, nhi = clo - 1;
+            for (int jb = clo; jb <= chi; jb += 32) {
+                const int j = jb + lane;
+                unsigned bal = __ballot_sync(0xffffffffu, j <= chi && SC(bc, 3, j) >= t);
+                if (bal) { nlo = jb + __ffs(bal) - 1; break; }
+            }
+            if (nlo <= chi) {
+                for (int jt = chi; jt >= nlo; jt -= 32) {
+                    const int j = jt - lane;
+                    unsigned bal = __ballot_sync(0xffffffffu, j >= nlo && SC(bc, 3, j) >= t);
+                    if (bal) { nhi = jt - (__ffs(bal) - 1); break; }
+                }
+            }
+            tlo = nlo; thi = nhi;
+        } else { tlo = clo; thi = chi; }
+        { int x = bpp; bpp = bp; bp = bc; bc = x; }
+        pplo = plo; pphi = phi; plo = clo; phi = chi;
+    }
+#undef SC
+    if (lane == 0) atomicAdd(X.counters + 2, cells);
+    if (arena_fail) { if (lane == 0) atomicOr(X.counters + 4, (unsigned long long)EX_ERR_ARENA); return 0; }
+
+    int fd, fj;
+    if (reached && !(m_o & PMN_OPTIMAL_BIT)) { fd = N + M; fj = M; } else { fd = best_d; fj = best_j; }
+    const int fi = fd - fj;
+    Aend = Astart + (int64_t)dir * (fi - 1);
+    Bend = Bstart + (int64_t)dir * (fj - 1);
+
+    if (!search) {
+        __syncwarp();
+        int nrev = 0;
+        if (lane == 0) {
+            int cd = fd, cj = fj;
+            int st = tboff[cd][cj - tblo[cd]] >> 6;
+            int pending = 0, run = 0;
+            while (cd > 0) {
+                const uint8_t b = tboff[cd][cj - tblo[cd]];
+                if (st == PMN_ST_MAT) { run++; st = (b >> 4) & 3; cd -= 2; cj -= 1; }
+                else {
+                    if (pending) rev[nrev++] = pending * (run + 1);
+                    run = 0;
+                    if (st == PMN_ST_INS) { pending = 1; st = (b >> 2) & 3; cd -= 1; }
+                    else { pending = -1; st = b & 3; cd -= 1; cj -= 1; }
+                }
+            }
+            if (pending) rev[nrev++] = pending * (run + 1);
+        }
+        nrev = __shfl_sync(0xffffffffu, nrev, 0);
+        __syncwarp();
+        if (nrev > 0) {
+            unsigned long long at = 0;
+            if (lane == 0) at = atomicAdd(X.counters + 0, (unsigned long long)nrev);
+            at = __shfl_sync(0xffffffffu, at, 0);
+            if (at + (unsigned long long)nrev > X.pool_cap) { if (lane == 0) atomicOr(X.counters + 4, (unsigned long long)EX_ERR_POOL); return reached; }
+            for (int k = lane; k < nrev; k += 32) X.pool[at + k] = rev[nrev - 1 - k];
+            *doff = (uint32_t)at; *dcnt = nrev;
+        }
+        __syncwarp();
+    }
+    return reached;
+}
+
+// ------------------------------------------------------------------------------------ postnuc pieces shared by wave 1 and the stitcher
+
+// returns the cluster index (syn-relative indices are absolute here) or `end` when there is none
+__device__ int get_forward_target_cluster(const ExShared &X, int cp, int end, int64_t &targetA, int64_t &targetB)
+{
+    const ExCluster c = X.cl[cp];
+    const int last = c.mfirst + c.nm - 1;
+    const int64_t sA = (int64_t)X.mA[last] + X.mL[last] - 1, sB = (int64_t)X.mB[last] + X.mL[last] - 1;
+    int64_t dist = targetA - sA < targetB - sB ? targetA - sA : targetB - sB;
+    int best = end;
+    for (int ci = cp + 1; ci < end; ci++) {
+        const ExCluster t = X.cl[ci];
+        if (t.dir != c.dir) continue;
+        int64_t eA = X.mA[t.mfirst], eB = X.mB[t.mfirst];
+        const int tl = t.mfirst + t.nm - 1;
+        if ((eA < sA || eB < sB) && X.mA[tl] >= sA && X.mB[tl] >= sB)
+            for (int k = t.mfirst; k <= tl && (eA < sA || eB < sB); k++) { eA = X.mA[k]; eB = X.mB[k]; }
+        if (eA >= sA && eB >= sB) {
+            int64_t greater, lesser;
+            if (eA - sA > eB - sB) { greater = eA - sA; lesser = eB - sB; } else { lesser = eA - sA; greater = eB - sB; }
+            if (greater < X.breaklen || lesser * PMN_GOOD_SCORE + (greater - lesser) * PMN_CONT_GAP_SCORE >= 0) { best = ci; targetA = eA; targetB = eB; break; }
+            else if ((greater << 1) - lesser < dist) { best = ci; targetA = eA; targetB = eB; dist = (greater << 1) - lesser; }
+        }
+    }
+    return best;
+}
+
+// the alignment-engine part of extendForward, from (eA, eB) towards (targetA, targetB)
+__device__ int forward_job(const Eng &E, const ExSynteny &S, int dirB, int64_t eA, int64_t eB, int64_t targetA, int64_t targetB, unsigned m_o, ExJob &out)
+{
+    int overflow = 0;
+    if (targetA - eA + 1 > PMN_MAX_ALIGNMENT_LENGTH) { targetA = eA + PMN_MAX_ALIGNMENT_LENGTH - 1; overflow = 1; m_o |= PMN_OPTIMAL_BIT; }
+    if (targetB - eB + 1 > PMN_MAX_ALIGNMENT_LENGTH) { targetB = eB + PMN_MAX_ALIGNMENT_LENGTH - 1; overflow = 1; m_o |= PMN_OPTIMAL_BIT; }
+    uint32_t doff; int32_t dcnt;
+    int reached = align_engine(E, S.Abase, eA, targetA, dirB ? E.X->QR : E.X->QF, dirB ? S.BbaseR : S.BbaseF, eB, targetB, m_o, &doff, &dcnt);
+    if (reached && overflow) reached = 0;
+    out.endA = (int32_t)targetA; out.endB = (int32_t)targetB; out.dcnt = dcnt; out.doff = doff; out.reached = reached; out.valid = 1;
+    return reached;
+}
+
+// ------------------------------------------------------------------------------------ E2: wave 1
+
+__device__ __forceinline__ Eng make_eng(const ExShared &X, int32_t *smem_all)
+{
+    Eng E;
+    const int warp = threadIdx.x >> 5;
+    const size_t slot = (size_t)blockIdx.x * EX_WARPS_PER_BLOCK + warp;
+    E.X = &X; E.lane = threadIdx.x & 31;
+    E.ssc = smem_all + (size_t)warp * EX_ROWS * EX_RW;
+    E.gsc = X.gscore + slot * (size_t)EX_ROWS * EX_WCAP;
+    E.tbp = X.tbpriv + slot * (size_t)EX_TBW;
+    return E;
+}
+
+__global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32) k_ex_wave1(ExShared X)
+{
+    extern __shared__ int32_t smem_all[];
+    const Eng E = make_eng(X, smem_all);
+    const int lane = E.lane;
+    // pass A: cluster-end extensions (the long ones) first; pass B: match -> next match
+    if (X.do_extend) {
+        for (;;) {
+            unsigned long long k = 0;
+            if (lane == 0) k = atomicAdd(X.counters + 5, 1ull);
+            k = __shfl_sync(0xffffffffu, k, 0);
+            if (k >= (unsigned long long)X.nC) break;
+            const ExCluster c = X.cl[k];
+            const ExSynteny S = X.syn[c.syn];
+            const int g = c.mfirst + c.nm - 1;
+            int64_t targetA = S.lenA, targetB = S.lenB;
+            const int end = S.cfirst + S.nC;
+            int tc = get_forward_target_cluster(X, (int)k, end, targetA, targetB);
+            unsigned m_o = PMN_FORWARD_ALIGN; if (tc == end) m_o |= PMN_OPTIMAL_BIT;
+            ExJob r; r.pad = 0; r.target = tc;
+            forward_job(E, S, c.dir, (int64_t)X.mA[g] + X.mL[g] - 1, (int64_t)X.mB[g] + X.mL[g] - 1, targetA, targetB, m_o, r);
+            if (lane == 0) X.jobs[g] = r;
+        }
+    }
+    for (;;) {
+        unsigned long long g = 0;
+        if (lane == 0) g = atomicAdd(X.counters + 6, 1ull);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        if (g >= (unsigned long long)X.nM) break;
+        const ExCluster c = X.cl[X.mcl[g]];
+        if ((int)g == c.mfirst + c.nm - 1) continue;
+        const ExSynteny S = X.syn[c.syn];
+        ExJob r; r.pad = 0; r.target = -1;
+        forward_job(E, S, c.dir, (int64_t)X.mA[g] + X.mL[g] - 1, (int64_t)X.mB[g] + X.mL[g] - 1, X.mA[g + 1], X.mB[g + 1], PMN_FORWARD_ALIGN, r);
+        if (lane == 0) X.jobs[g] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------------ E3: stitch
+
+struct Stitch {
+    const Eng *E; const ExSynteny *S; ExAlign *al; ExNode *nodes; int nAl, nNodes; bool fail;
+};
+
+__device__ void al_append(Stitch &T, int ap, uint32_t doff, int dcnt, int adjust)
+{
+    if (dcnt <= 0) return;
+    if (T.nNodes >= T.S->nodecap) { T.fail = true; return; }
+    const int nd = T.nNodes++;
+    if (T.E->lane == 0) {
+        ExNode n; n.off = doff; n.cnt = dcnt; n.adjust = adjust; n.next = -1;
+        T.nodes[nd] = n;
+        ExAlign &a = T.al[ap];
+        if (a.head < 0) a.head = nd; else T.nodes[a.tail].next = nd;
+        a.tail = nd; a.ndelta += dcnt;
+    }
+    __syncwarp();
+}
+
+// sum over a delta segment of (d > 0 ? d : |d| - 1), the first value shifted by `adjust`
+__device__ int64_t seg_apos(const ExShared &X, uint32_t doff, int dcnt, int adjust, int lane)
+{
+    long long s = 0;
+    for (int k = lane; k < dcnt; k += 32) {
+        int d = X.pool[doff + k];
+        if (k == 0) d += d > 0 ? adjust : -adjust;
+        s += d > 0 ? d : -d - 1;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
+}
+
+// extendForward.  `g` >= 0 names the wave-1 job that computed exactly this extension.
+__device__ int st_extend_forward(Stitch &T, int ap, int dirB, int64_t targetA, int64_t targetB, unsigned m_o, int g)
+{
+    const ExShared &X = *T.E->X;
+    ExAlign a = T.al[ap];
+    ExJob r;
+    bool have = false;
+    if (g >= 0) {
+        r = X.jobs[g];
+        have = r.valid && a.eA == X.mA[g] + X.mL[g] - 1 && a.eB == X.mB[g] + X.mL[g] - 1;
+    }
+    if (!have) forward_job(*T.E, *T.S, dirB, a.eA, a.eB, targetA, targetB, m_o, r);
+    if (r.dcnt > 0) {
+        const int ValA = (a.eA - a.sA + 1) - a.deltaApos - 1;
+        al_append(T, ap, r.doff, r.dcnt, ValA);
+        a.deltaApos += (int32_t)seg_apos(X, r.doff, r.dcnt, ValA, T.E->lane);
+    }
+    a.eA = r.endA; a.eB = r.endB;
+    if (T.E->lane == 0) { ExAlign &w = T.al[ap]; w.eA = a.eA; w.eB = a.eB; w.deltaApos = a.deltaApos; }
+    __syncwarp();
+    return r.reached;
+}
+
+__device__ int st_get_reverse_target(const Stitch &T, int ap)
+{
+    const ExShared &X = *T.E->X;
+    const ExAlign c = T.al[ap];
+    const int64_t sA = c.sA, sB = c.sB;
+    int64_t dist = sA < sB ? sA : sB;
+    int best = -1;
+    for (int i = ap - 1; i >= 0; i--) {
+        const ExAlign a = T.al[i];
+        if (a.dirB != c.dirB) continue;
+        const int64_t eA = a.eA, eB = a.eB;
+        if (eA <= sA && eB <= sB) {
+            int64_t greater, lesser;
+            if (sA - eA > sB - eB) { greater = sA - eA; lesser = sB - eB; } else { lesser = sA - eA; greater = sB - eB; }
+            if (greater < X.breaklen || lesser * PMN_GOOD_SCORE + (greater - lesser) * PMN_CONT_GAP_SCORE >= 0) { best = i; break; }
+            else if ((greater << 1) - lesser < dist) { best = i; dist = (greater << 1) - lesser; }
+        }
+    }
+    return best;
+}
+
+// extendBackward; may drop the last alignment (merged into tp)
+__device__ int st_extend_backward(Stitch &T, int ap, int tp, int dirB)
+{
+    const ExShared &X = *T.E->X;
+    const ExSynteny &S = *T.S;
+    ExAlign a = T.al[ap];
+    int overflow = 0; unsigned m_o = PMN_BACKWARD_SEARCH;
+    int64_t targetA, targetB;
+    if (tp >= 0) { targetA = T.al[tp].eA; targetB = T.al[tp].eB; } else { targetA = 1; targetB = 1; m_o |= PMN_OPTIMAL_BIT; }
+    if (a.sA - targetA + 1 > PMN_MAX_ALIGNMENT_LENGTH) { targetA = a.sA - PMN_MAX_ALIGNMENT_LENGTH + 1; overflow = 1; m_o |= PMN_OPTIMAL_BIT; }
+    if (a.sB - targetB + 1 > PMN_MAX_ALIGNMENT_LENGTH) { targetB = a.sB - PMN_MAX_ALIGNMENT_LENGTH + 1; overflow = 1; m_o |= PMN_OPTIMAL_BIT; }
+    const PackedView &Q = dirB ? X.QR : X.QF; const int64_t Bbase = dirB ? S.BbaseR : S.BbaseF;
+    int reached = align_engine(*T.E, S.Abase, a.sA, targetA, Q, Bbase, a.sB, targetB, m_o, nullptr, nullptr);
+    if (overflow || tp < 0) reached = 0;
+    if (reached) {
+        st_extend_forward(T, tp, dirB, a.sA, a.sB, PMN_FORCED_FORWARD_ALIGN, -1);
+        if (T.E->lane == 0) { ExAlign &t = T.al[tp]; t.eA += a.eA - a.sA; t.eB += a.eB - a.sB; }
+        T.nAl--;
+        __syncwarp();
+    } else {
+        int64_t eA = a.sA, eB = a.sB; uint32_t doff; int32_t dcnt;
+        align_engine(*T.E, S.Abase, targetA, eA, Q, Bbase, targetB, eB, PMN_FORCED_FORWARD_ALIGN, &doff, &dcnt);
+        al_append(T, ap, doff, dcnt, 0);
+        int64_t ap_sum = dcnt > 0 ? seg_apos(X, doff, dcnt, 0, T.E->lane) : 0;
+        if (T.E->lane == 0) { ExAlign &w = T.al[ap]; w.sA = (int32_t)targetA; w.sB = (int32_t)targetB; w.deltaApos += (int32_t)ap_sum; }
+        __syncwarp();
+    }
+    return reached;
+}
+
+__device__ bool st_is_shadowed(const Stitch &T, int cp)
+{
+    const ExShared &X = *T.E->X;
+    const ExCluster c = X.cl[cp];
+    const int l = c.mfirst + c.nm - 1;
+    const int64_t sA = X.mA[c.mfirst], eA = (int64_t)X.mA[l] + X.mL[l] - 1, sB = X.mB[c.mfirst], eB = (int64_t)X.mB[l] + X.mL[l] - 1;
+    for (int i = T.nAl - 1; i >= 0; i--) {
+        const ExAlign a = T.al[i];
+        if (a.dirB == c.dir && a.eA >= eA && a.eB >= eB && a.sA <= sA && a.sB <= sB) return true;
+    }
+    return false;
+}
+
+// extendClusters for one synteny; every lane runs the same control flow on the same values
+__global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32) k_ex_stitch(ExShared X, uint8_t *fused)
+{
+    extern __shared__ int32_t smem_all[];
+    const Eng E = make_eng(X, smem_all);
+    const int lane = E.lane;
+    const int s = blockIdx.x * EX_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (s >= X.nS) return;
+    const ExSynteny S = X.syn[s];
+    Stitch T; T.E = &E; T.S = &S; T.al = X.al + S.alfirst; T.nodes = X.nodes + S.nodefirst; T.nAl = 0; T.nNodes = 0; T.fail = false;
+    const int c0 = S.cfirst, cend = S.cfirst + S.nC;
+    int target_reached = 0, CurrCp = c0, PrevCp = c0, TargetCp = cend, CurrAp = -1;
+    bool logic_err = false;
+    while (CurrCp < cend && !T.fail && !logic_err) {
+        const ExCluster c = X.cl[CurrCp];
+        if (X.do_extend && !target_reached && fused[CurrCp]) { CurrCp++; continue; }
+        if (!target_reached && X.do_simplify && st_is_shadowed(T, CurrCp)) {
+            if (lane == 0) fused[CurrCp] = 1;
+            __syncwarp();
+            CurrCp = ++PrevCp; continue;
+        }
+        int CurrMp = 0;
+        while (CurrMp < c.nm) {
+            const int g = c.mfirst + CurrMp;
+            if (target_reached) {
+                const ExAlign a = T.al[CurrAp];
+                if (a.eA != X.mA[g] || a.eB != X.mB[g]) {
+                    if (CurrMp >= c.nm - 1) { logic_err = true; break; }
+                    CurrMp++; continue;
+                }
+                if (lane == 0) { ExAlign &w = T.al[CurrAp]; w.eA += X.mL[g] - 1; w.eB += X.mL[g] - 1; }
+                __syncwarp();
+            } else {
+                if (T.nAl >= S.alcap) { logic_err = true; break; }
+                CurrAp = T.nAl++;
+                if (lane == 0) {
+                    ExAlign a; a.dirB = c.dir; a.sA = X.mA[g]; a.sB = X.mB[g]; a.eA = X.mA[g] + X.mL[g] - 1; a.eB = X.mB[g] + X.mL[g] - 1;
+                    a.deltaApos = 0; a.head = -1; a.tail = -1; a.ndelta = 0; a.live = 1; a.pad0 = a.pad1 = 0;
+                    T.al[CurrAp] = a;
+                }
+                __syncwarp();
+                if (X.do_extend || CurrMp != 0) {
+                    const int TargetAp = st_get_reverse_target(T, CurrAp);
+                    if (st_extend_backward(T, CurrAp, TargetAp, c.dir)) CurrAp = TargetAp;
+                }
+            }
+            unsigned m_o = PMN_FORWARD_ALIGN;
+            if (CurrMp < c.nm - 1) {
+                target_reached = st_extend_forward(T, CurrAp, c.dir, X.mA[g + 1], X.mB[g + 1], m_o, g);
+            } else if (X.do_extend) {
+                int64_t targetA = S.lenA, targetB = S.lenB;
+                TargetCp = get_forward_target_cluster(X, CurrCp, cend, targetA, targetB);
+                if (TargetCp == cend) m_o |= PMN_OPTIMAL_BIT;
+                target_reached = st_extend_forward(T, CurrAp, c.dir, targetA, targetB, m_o, g);
+            }
+            CurrMp++;
+        }
+        if (TargetCp == cend) target_reached = 0;
+        if (lane == 0) fused[CurrCp] = 1;
+        __syncwarp();
+        if (!target_reached) CurrCp = ++PrevCp; else CurrCp = TargetCp;
+    }
+    if (lane == 0) {
+        X.syn_nal[s] = T.nAl;
+        if (T.fail) atomicOr(X.counters + 4, (unsigned long long)EX_ERR_NODES);
+        if (logic_err) atomicOr(X.counters + 4, (unsigned long long)EX_ERR_LOGIC);
+    }
+}
+
+// ------------------------------------------------------------------------------------ E1 helpers
+
+// reference record of every match, local coordinate, piece starts
+__global__ void __launch_bounds__(256) k_ex_match_rec(const int32_t *__restrict__ m3, const int4 *__restrict__ recs, int64_t nc, const int64_t *__restrict__ roff,
+                                                     const int64_t *__restrict__ rlen, int nref, int32_t *__restrict__ mA, int32_t *__restrict__ mB,
+                                                     int32_t *__restrict__ mL, int32_t *__restrict__ mrec, uint32_t *__restrict__ pstart, int32_t *__restrict__ mtag)
+{
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nc) return;
+    const int4 r = recs[k];
+    int prev = -1;
+    for (int g = r.x; g < r.x + r.y; g++) {
+        int64_t sA = m3[g * 3];
+        int lo = 0, hi = nref - 1;
+        while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (roff[mid] + 1 <= sA) lo = mid; else hi = mid - 1; }
+        mA[g] = (int32_t)(sA - roff[lo]); mB[g] = m3[g * 3 + 1]; mL[g] = m3[g * 3 + 2]; mrec[g] = lo; mtag[g] = r.z;
+        pstart[g] = lo != prev ? 1u : 0u;
+        prev = lo;
+        (void)rlen;
+    }
+}
+
+// piece p (= cluster of postnuc): key for the sort and its first match
+__global__ void __launch_bounds__(256) k_ex_pieces(const uint32_t *__restrict__ pstart, const uint32_t *__restrict__ ppos, int64_t nm, const int32_t *__restrict__ mA,
+                                                  const int32_t *__restrict__ mrec, const int32_t *__restrict__ mtag, uint64_t *__restrict__ keys,
+                                                  uint32_t *__restrict__ vals, int32_t *__restrict__ pfirst)
+{
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nm || !pstart[g]) return;
+    uint32_t p = ppos[g];
+    keys[p] = ((uint64_t)(mtag[g] >> 1) << 47) | ((uint64_t)mrec[g] << 32) | (uint32_t)mA[g];
+    vals[p] = p; pfirst[p] = (int32_t)g;
+}
+
+// sorted pieces -> ExCluster records, per-match cluster index
+__global__ void __launch_bounds__(256) k_ex_clusters(const uint64_t *__restrict__ skeys, const uint32_t *__restrict__ svals, int64_t np, int64_t nm,
+                                                    const int32_t *__restrict__ pfirst, const uint32_t *__restrict__ pstart, const int32_t *__restrict__ mtag,
+                                                    ExCluster *__restrict__ cl, int32_t *__restrict__ mcl, uint32_t *__restrict__ sflag)
+{
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= np) return;
+    const uint32_t p = svals[k];
+    const int first = pfirst[p];
+    int g = first + 1;
+    while (g < nm && !pstart[g]) g++;
+    ExCluster c; c.mfirst = first; c.nm = g - first; c.dir = mtag[first] & 1; c.syn = 0; c.order = (int32_t)p; c.pad = 0;
+    cl[k] = c;
+    for (int t = first; t < g; t++) mcl[t] = (int32_t)k;
+    sflag[k] = (k == 0 || (skeys[k] >> 32) != (skeys[k - 1] >> 32)) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256) k_ex_syntenies(const uint64_t *__restrict__ skeys, const uint32_t *__restrict__ sflag, const uint32_t *__restrict__ spos, int64_t np,
+                                                     ExCluster *__restrict__ cl, ExSynteny *__restrict__ syn, const int64_t *__restrict__ roff, const int64_t *__restrict__ rlen,
+                                                     const int64_t *__restrict__ qoff, const int64_t *__restrict__ qlen, int64_t qn)
+{
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= np) return;
+    const uint32_t s = spos[k] + sflag[k] - 1;     // inclusive count of synteny starts up to k, minus one
+    cl[k].syn = (int32_t)s;
+    if (sflag[k]) {
+        int64_t e = k + 1; while (e < np && !sflag[e]) e++;
+        const int qrec = (int)(skeys[k] >> 47), rrec = (int)((skeys[k] >> 32) & 0x7fff);
+        ExSynteny S;
+        S.cfirst = (int32_t)k; S.nC = (int32_t)(e - k); S.qrec = qrec; S.rrec = rrec;
+        S.Abase = roff[rrec]; S.lenA = rlen[rrec]; S.BbaseF = qoff[qrec]; S.BbaseR = qn - qoff[qrec] - qlen[qrec]; S.lenB = qlen[qrec];
+        // capacity: one alignment per match at most; filled in below from the match counts
+        const int mbeg = cl[k].mfirst;
+        (void)mbeg;
+        S.alfirst = 0; S.alcap = 0; S.nodefirst = 0; S.nodecap = 0;
+        syn[s] = S;
+    }
+}
+
+// capacities per synteny from its clusters' match counts (clusters of a synteny are contiguous)
+__global__ void __launch_bounds__(128) k_ex_syn_caps(ExSynteny *__restrict__ syn, int nS, const ExCluster *__restrict__ cl)
+{
+    // single thread: nS is small and the prefix is sequential
+    if (blockIdx.x || threadIdx.x) return;
+    int al = 0, nd = 0;
+    for (int s = 0; s < nS; s++) {
+        int m = 0;
+        for (int k = syn[s].cfirst; k < syn[s].cfirst + syn[s].nC; k++) m += cl[k].nm;
+        syn[s].alfirst = al; syn[s].alcap = m; syn[s].nodefirst = nd; syn[s].nodecap = 3 * m + 8;
+        al += m; nd += 3 * m + 8;
+    }
+}
+
+// ------------------------------------------------------------------------------------ E4: flatten, parseDelta
+
+// one warp per alignment slot: copy its delta segments to out[doff..], then count errors
+__global__ void __launch_bounds__(128) k_ex_finish(ExShared X, const int32_t *__restrict__ al_syn, const uint32_t *__restrict__ al_slot, int64_t nal,
+                                                  const uint32_t *__restrict__ dstart, int32_t *__restrict__ dout, long long *__restrict__ rows)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t k = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (k >= nal) return;
+    const ExSynteny S = X.syn[al_syn[k]];
+    const ExAlign a = X.al[al_slot[k]];
+    const ExNode *nodes = X.nodes + S.nodefirst;
+    int32_t *out = dout + dstart[k];
+    int w = 0;
+    for (int nd = a.head; nd >= 0; nd = nodes[nd].next) {
+        const ExNode n = nodes[nd];
+        for (int t = lane; t < n.cnt; t += 32) {
+            int d = X.pool[n.off + t];
+            if (t == 0) d += d > 0 ? n.adjust : -n.adjust;
+            out[w + t] = d;
+        }
+        w += n.cnt;
+    }
+    __syncwarp();
+    // parseDelta: walk the alignment, count columns that are not an identical a/c/g/t pair
+    const PackedView &Q = a.dirB ? X.QR : X.QF;
+    const int64_t Ab = S.Abase - 1, Bb = (a.dirB ? S.BbaseR : S.BbaseF) - 1;
+    int64_t Apos = a.sA, Bpos = a.sB, Remain = (int64_t)a.eA - a.sA + 1;
+    long long errs = 0;
+    for (int t = 0; t <= a.ndelta; t++) {
+        int64_t run; int D = 0;
+        if (t < a.ndelta) { D = out[t]; run = (D < 0 ? -D : D) - 1; } else run = Remain;
+        long long e = 0;
+        for (int64_t x = lane; x < run; x += 32) {
+            int ca = pmn_base_at(X.R, Ab + Apos + x), cb = pmn_base_at(Q, Bb + Bpos + x);
+            if (ca != cb || ca == PMN_CODE_X) e++;
+        }
+        errs += e;
+        Apos += run; Bpos += run; Remain -= run;
+        if (t < a.ndelta) { if (lane == 0) errs++; if (D > 0) { Apos++; Remain--; } else Bpos++; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) errs += __shfl_xor_sync(0xffffffffu, errs, o);
+    if (lane == 0) {
+        long long *r = rows + k * 10;
+        r[0] = S.rrec; r[1] = S.qrec; r[2] = a.dirB; r[3] = a.sA; r[4] = a.eA; r[5] = a.sB; r[6] = a.eB; r[7] = errs; r[8] = errs; r[9] = 0;
+    }
+}
+
+// list the live alignments of all syntenies in order
+__global__ void __launch_bounds__(128) k_ex_list(const ExSynteny *__restrict__ syn, const int32_t *__restrict__ syn_nal, int nS, const ExAlign *__restrict__ al,
+                                                int32_t *__restrict__ al_syn, uint32_t *__restrict__ al_slot, uint32_t *__restrict__ dcount, unsigned long long *__restrict__ totals)
+{
+    if (blockIdx.x || threadIdx.x) return;
+    unsigned long long n = 0, nd = 0;
+    for (int s = 0; s < nS; s++)
+        for (int k = 0; k < syn_nal[s]; k++) {
+            const int slot = syn[s].alfirst + k;
+            al_syn[n] = s; al_slot[n] = (uint32_t)slot; dcount[n] = (uint32_t)al[slot].ndelta; nd += (unsigned long long)al[slot].ndelta; n++;
+        }
+    totals[0] = n; totals[1] = nd;
+}
+
+// ------------------------------------------------------------------------------------ driver
+
+static int small_or_radix_sort(Scratch &S, int64_t n, int nbits, cudaStream_t st, int *launches)
+{
+    return pmn_radix_sort(S.k0.as<uint64_t>(), S.v0.as<uint32_t>(), S.k1.as<uint64_t>(), S.v1.as<uint32_t>(), n, nbits, S.rs, st, launches);
+}
+
+int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_opts *o, pmn_result *res)
+{
+    Scratch &S = *c->scratch;
+    cudaStream_t st = c->stream;
+    const pmn_seq *ref = ix->seq;
+    const int64_t nc0 = S.n_clusters, nm = S.n_cl_matches;
+    res->stats.clusters = nc0; res->stats.cluster_matches = nm;
+    res->al_doff.assign(1, 0);
+    if (o->keep_stages && nc0 > 0) {
+        std::vector<int4> recs((size_t)nc0);
+        res->cl_matches.resize((size_t)nm * 3);
+        PMN_CUDA_OK(cudaMemcpyAsync(res->cl_matches.data(), S.cl_matches.p, 12 * (size_t)nm, cudaMemcpyDeviceToHost, st));
+        PMN_CUDA_OK(cudaMemcpyAsync(recs.data(), S.cl_recs.p, 16 * (size_t)nc0, cudaMemcpyDeviceToHost, st));
+        PMN_CUDA_OK(cudaStreamSynchronize(st));
+        res->cl_off.resize((size_t)nc0 + 1); res->cl_tag.resize((size_t)nc0);
+        for (int64_t k = 0; k < nc0; k++) { res->cl_off[(size_t)k] = recs[(size_t)k].x; res->cl_tag[(size_t)k] = recs[(size_t)k].z; }
+        res->cl_off[(size_t)nc0] = (int32_t)nm;
+    } else if (o->keep_stages) { res->cl_off.assign(1, 0); }
+    if (nc0 <= 0) return 0;
+    int launches = 0;
+
+    // ---- E1: record offsets to the device
+    const int nref = ref->nrec, nqry = q->nrec;
+    std::vector<int64_t> h((size_t)2 * nref + 2 * nqry);
+    for (int i = 0; i < nref; i++) { h[(size_t)i] = ref->off[(size_t)i]; h[(size_t)nref + i] = ref->len[(size_t)i]; }
+    for (int i = 0; i < nqry; i++) { h[(size_t)2 * nref + i] = q->off[(size_t)i]; h[(size_t)2 * nref + nqry + i] = q->len[(size_t)i]; }
+    if (S.ex_a.ensure(8 * h.size()) || S.ex_b.ensure(4 * 5 * (size_t)nm) || S.ex_c.ensure(4 * 2 * (size_t)nm) || S.scan_tmp.ensure(8 * pmn_scan_scratch_elems(nm)) ||
+        S.ensure_pinned(256)) return -3;
+    PMN_CUDA_OK(cudaMemcpyAsync(S.ex_a.p, h.data(), 8 * h.size(), cudaMemcpyHostToDevice, st));
+    const int64_t *roff = S.ex_a.as<int64_t>(), *rlen = roff + nref, *qoff = roff + 2 * nref, *qlen = qoff + nqry;
+    int32_t *mA = S.ex_b.as<int32_t>(), *mB = mA + nm, *mL = mA + 2 * nm, *mrec = mA + 3 * nm, *mtag = mA + 4 * nm;
+    uint32_t *pstart = S.ex_c.as<uint32_t>(), *ppos = pstart + nm;
+    k_ex_match_rec<<<(unsigned)((nc0 + 255) / 256), 256, 0, st>>>(S.cl_matches.as<int32_t>(), S.cl_recs.as<int4>(), nc0, roff, rlen, nref, mA, mB, mL, mrec, pstart, mtag);
+    pmn_scan<uint32_t, OpAddU32, false>(pstart, ppos, nm, S.scan_tmp.as<uint32_t>(), st);
+    launches += 4;
+    uint32_t *tail = (uint32_t *)S.pinned;
+    PMN_CUDA_OK(cudaMemcpyAsync(tail, ppos + (nm - 1), 4, cudaMemcpyDeviceToHost, st));
+    PMN_CUDA_OK(cudaMemcpyAsync(tail + 1, pstart + (nm - 1), 4, cudaMemcpyDeviceToHost, st));
+    PMN_CUDA_OK(cudaStreamSynchronize(st));       // also: h may go out of scope
+    const int64_t np = (int64_t)tail[0] + tail[1];
+
+    // pieces sorted by (query record, reference record, first reference start), stable
+    if (S.k0.ensure(8 * (size_t)np) || S.k1.ensure(8 * (size_t)np) || S.v0.ensure(4 * (size_t)np) || S.v1.ensure(4 * (size_t)np) ||
+        S.ex_d.ensure(4 * (size_t)np) || S.ex_e.ensure(sizeof(ExCluster) * (size_t)np) || S.ex_f.ensure(4 * (size_t)nm) ||
+        S.ex_g.ensure(4 * 2 * (size_t)np) || S.ex_h.ensure(sizeof(ExSynteny) * (size_t)np)) return -3;
+    int32_t *pfirst = S.ex_d.as<int32_t>();
+    k_ex_pieces<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(pstart, ppos, nm, mA, mrec, mtag, S.k0.as<uint64_t>(), S.v0.as<uint32_t>(), pfirst);
+    launches++;
+    int qb = 1; while ((1 << qb) < nqry) qb++;
+    int where = small_or_radix_sort(S, np, 47 + qb, st, &launches);
+    if (where < 0) return -3;
+    const uint64_t *skeys = where ? S.k1.as<uint64_t>() : S.k0.as<uint64_t>();
+    const uint32_t *svals = where ? S.v1.as<uint32_t>() : S.v0.as<uint32_t>();
+    ExCluster *cl = S.ex_e.as<ExCluster>(); int32_t *mcl = S.ex_f.as<int32_t>();
+    uint32_t *sflag = S.ex_g.as<uint32_t>(), *spos = sflag + np;
+    ExSynteny *syn = S.ex_h.as<ExSynteny>();
+    const unsigned gp = (unsigned)((np + 255) / 256);
+    k_ex_clusters<<<gp, 256, 0, st>>>(skeys, svals, np, nm, pfirst, pstart, mtag, cl, mcl, sflag);
+    pmn_scan<uint32_t, OpAddU32, false>(sflag, spos, np, S.scan_tmp.as<uint32_t>(), st);
+    k_ex_syntenies<<<gp, 256, 0, st>>>(skeys, sflag, spos, np, cl, syn, roff, rlen, qoff, qlen, q->n);
+    launches += 5;
+    PMN_CUDA_OK(cudaMemcpyAsync(tail, spos + (np - 1), 4, cudaMemcpyDeviceToHost, st));
+    PMN_CUDA_OK(cudaMemcpyAsync(tail + 1, sflag + (np - 1), 4, cudaMemcpyDeviceToHost, st));
+    PMN_CUDA_OK(cudaStreamSynchronize(st));
+    const int nS = (int)(tail[0] + tail[1]);
+    k_ex_syn_caps<<<1, 32, 0, st>>>(syn, nS, cl);
+    launches++;
+
+    // ---- E2/E3 storage
+    const int blocks1 = c->sm_count * 4;                      // 4 warps per block, 4 blocks per SM
+    const int blocks_st = (nS + EX_WARPS_PER_BLOCK - 1) / EX_WARPS_PER_BLOCK;
+    const int nslots = std::max(blocks1, blocks_st) * EX_WARPS_PER_BLOCK;
+    const size_t pool_cap = (size_t)std::max<int64_t>(1 << 20, 8 * nm + (ref->n + q->n) / 8);
+    const size_t arena_cap = (size_t)1 << 31;
+    const size_t ncap_al = (size_t)nm, ncap_nodes = 3 * (size_t)nm + 8 * (size_t)nS;
+    if (S.ex_i.ensure(sizeof(ExJob) * (size_t)nm) || S.ex_j.ensure(sizeof(ExAlign) * ncap_al) || S.ex_k.ensure(sizeof(ExNode) * ncap_nodes) ||
+        S.ex_pool.ensure(4 * pool_cap) || S.ex_arena.ensure(arena_cap) || S.ex_scores.ensure(4 * (size_t)EX_ROWS * EX_WCAP * (size_t)nslots) ||
+        S.ex_tb.ensure((size_t)EX_TBW * (size_t)nslots) || S.ex_counters.ensure(128) || S.ex_l.ensure((size_t)np + 4 * (size_t)nS + 64)) return -3;
+    PMN_CUDA_OK(cudaMemsetAsync(S.ex_i.p, 0, sizeof(ExJob) * (size_t)nm, st));
+    PMN_CUDA_OK(cudaMemsetAsync(S.ex_counters.p, 0, 128, st));
+    PMN_CUDA_OK(cudaMemsetAsync(S.ex_l.p, 0, (size_t)np + 4 * (size_t)nS + 64, st));
+    ExShared X;
+    X.R = ref->fwd(); X.QF = q->fwd(); X.QR = q->rev();
+    X.mA = mA; X.mB = mB; X.mL = mL; X.cl = cl; X.syn = syn; X.nC = (int)np; X.nS = nS; X.nM = nm;
+    X.jobs = S.ex_i.as<ExJob>(); X.mcl = mcl; X.al = S.ex_j.as<ExAlign>(); X.nodes = S.ex_k.as<ExNode>();
+    X.pool = S.ex_pool.as<int32_t>(); X.pool_cap = (uint32_t)std::min<size_t>(pool_cap, 0xfffffff0u);
+    X.arena = S.ex_arena.as<uint8_t>(); X.arena_cap = arena_cap;
+    X.gscore = S.ex_scores.as<int32_t>(); X.tbpriv = S.ex_tb.as<uint8_t>();
+    X.counters = S.ex_counters.as<unsigned long long>();
+    X.breaklen = o->breaklen; X.do_extend = o->do_extend; X.do_simplify = o->do_simplify;
+    uint8_t *fused = S.ex_l.as<uint8_t>();
+    X.syn_nal = (int32_t *)(fused + ((np + 63) / 64) * 64);
+
+    const size_t smem = (size_t)EX_WARPS_PER_BLOCK * EX_ROWS * EX_RW * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+        PMN_CUDA_OK(cudaFuncSetAttribute(k_ex_wave1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PMN_CUDA_OK(cudaFuncSetAttribute(k_ex_stitch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    int b1 = blocks1; { int64_t need = (nm + EX_WARPS_PER_BLOCK - 1) / EX_WARPS_PER_BLOCK; if (need < b1) b1 = (int)need; if (b1 < 1) b1 = 1; }
+    k_ex_wave1<<<b1, EX_WARPS_PER_BLOCK * 32, smem, st>>>(X);
+    k_ex_stitch<<<blocks_st, EX_WARPS_PER_BLOCK * 32, smem, st>>>(X, fused);
+    launches += 2;
+
+    // ---- E4
+    if (S.ex_c.ensure(4 * 4 * (size_t)nm + 64)) return -3;     // al_syn, al_slot, dcount, dstart
+    int32_t *al_syn = S.ex_c.as<int32_t>(); uint32_t *al_slot = (uint32_t *)al_syn + nm, *dcount = al_slot + nm, *dstart = dcount + nm;
+    k_ex_list<<<1, 32, 0, st>>>(syn, X.syn_nal, nS, X.al, al_syn, al_slot, dcount, X.counters + 8);
+    launches++;
+    unsigned long long *hc = (unsigned long long *)S.pinned;
+    PMN_CUDA_OK(cudaMemcpyAsync(hc, X.counters, 128, cudaMemcpyDeviceToHost, st));
+    PMN_CUDA_OK(cudaStreamSynchronize(st));
+    const unsigned long long errflags = hc[4];
+    res->stats.dp_cells = (int64_t)hc[2]; res->stats.dp_jobs = (int64_t)hc[3];
+    c->launches += launches; launches = 0;
+    if (errflags & EX_ERR_POOL) return pmn_set_error(PMN_E_NOMEM, "extend: delta pool exhausted (%zu entries)", pool_cap);
+    if (errflags & EX_ERR_ARENA) return pmn_set_error(PMN_E_NOMEM, "extend: traceback arena exhausted (%zu bytes)", arena_cap);
+    if (errflags & EX_ERR_NODES) return pmn_set_error(PMN_E_INTERNAL, "extend: delta segment list overflow");
+    if (errflags & EX_ERR_LOGIC) return pmn_set_error(PMN_E_INTERNAL, "extend: inconsistent cluster chain (target match does not exist)");
+    const int64_t nal = (int64_t)hc[8], nd = (int64_t)hc[9];
+    if (nal > 0) {
+        if (S.ex_d.ensure(4 * (size_t)(nd + 1)) || S.ex_g.ensure(80 * (size_t)nal)) return -3;
+        pmn_scan<uint32_t, OpAddU32, false>(dcount, dstart, nal, S.scan_tmp.as<uint32_t>(), st);
+        k_ex_finish<<<(unsigned)((nal + 3) / 4), 128, 0, st>>>(X, al_syn, al_slot, nal, dstart, S.ex_d.as<int32_t>(), S.ex_g.as<long long>());
+        launches += 4;
+        res->al_rows.resize((size_t)nal * 10);
+        std::vector<int32_t> d32((size_t)nd), dc((size_t)nal);
+        PMN_CUDA_OK(cudaMemcpyAsync(res->al_rows.data(), S.ex_g.p, 80 * (size_t)nal, cudaMemcpyDeviceToHost, st));
+        if (nd) PMN_CUDA_OK(cudaMemcpyAsync(d32.data(), S.ex_d.p, 4 * (size_t)nd, cudaMemcpyDeviceToHost, st));
+        PMN_CUDA_OK(cudaMemcpyAsync(dc.data(), dcount, 4 * (size_t)nal, cudaMemcpyDeviceToHost, st));
+        PMN_CUDA_OK(cudaStreamSynchronize(st));
+        res->al_deltas.assign(d32.begin(), d32.end());
+        res->al_doff.resize((size_t)nal + 1);
+        for (int64_t k = 0; k < nal; k++) res->al_doff[(size_t)k + 1] = res->al_doff[(size_t)k] + dc[(size_t)k];
+    }
+    PMN_CUDA_OK(cudaGetLastError());
+    c->launches += launches;
+    return 0;
+}

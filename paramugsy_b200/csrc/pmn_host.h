@@ -1,0 +1,64 @@
+// pmn_host.h — host-side objects behind the C ABI of include/pmnucmer.h.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "../../include/pmnucmer.h"
+#include "pmn_common.cuh"
+
+struct pmn_seq {
+    pmn_ctx *ctx = nullptr;
+    int nrec = 0;
+    std::vector<std::string> ids;
+    std::vector<int64_t> len, off;      // per record: bases, 0-based offset in the concatenation
+    int64_t n = 0;                      // concatenated bases incl. separators
+    int has_x = 0;
+    int64_t nwords = 0;                 // words in each packed array (incl. padding)
+    DevBuf w_fwd, xm_fwd;               // forward text
+    DevBuf w_rev, xm_rev;               // reverse complement of the whole concatenation
+    PackedView fwd() const { return PackedView{ w_fwd.as<uint64_t>(), xm_fwd.as<uint32_t>(), n, has_x }; }
+    PackedView rev() const { return PackedView{ w_rev.as<uint64_t>(), xm_rev.as<uint32_t>(), n, has_x }; }
+};
+
+struct pmn_index {
+    pmn_ctx *ctx = nullptr;
+    const pmn_seq *seq = nullptr;       // borrowed: the caller keeps the sequence alive
+    int64_t n = 0;
+    DevBuf sa, lcp, table;              // int32[n], int32[n], uint32[4^K + 1]
+    int K = 0;
+    int rounds = 0;                     // prefix-doubling rounds after the 16-mer pass
+    float ms_build = 0;
+};
+
+struct StageTimes { float pack = 0, index = 0, seed = 0, cluster = 0, extend = 0, total = 0; };
+
+struct pmn_result {
+    std::string delta;
+    pmn_stats stats{};
+    // stage dumps kept for parity tests
+    std::vector<int32_t> anchors;             // n x 4
+    std::vector<int32_t> cl_matches, cl_off, cl_tag;
+    std::vector<int64_t> al_rows, al_doff, al_deltas;
+};
+
+// per-context scratch, all grow-only
+struct Scratch;
+
+struct pmn_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    PmnError err{};
+    Scratch *scratch = nullptr;
+    long launches = 0;                  // kernels launched by this library (bench.py's gpu_launches)
+};
+
+// stage entry points (defined in the .cu files)
+int pmn_pack_upload(pmn_ctx *c, pmn_seq *s, const uint8_t *codes_host);
+int pmn_index_build_impl(pmn_ctx *c, const pmn_seq *ref, pmn_index *ix);
+int pmn_seed_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_opts *o, int64_t *n_anchors);
+int pmn_cluster_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_opts *o, int64_t n_anchors);
+int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_opts *o, pmn_result *res);
+Scratch *pmn_scratch_new();
+void pmn_scratch_free(Scratch *s);

@@ -1,0 +1,36 @@
+// pmn_scratch.cuh — every grow-only device buffer a context owns.  One pair is in flight
+// per context at a time, so stages simply reuse these between pairs (no cudaMalloc at
+// steady state).
+#pragma once
+#include "pmn_host.h"
+#include "pmn_prims.cuh"
+
+struct Scratch {
+    RadixScratch rs;
+    DevBuf k0, k1, v0, v1;            // radix sort ping-pong (uint64 keys, uint32 values)
+    DevBuf scan_tmp;                  // spine of pmn_scan
+    DevBuf codes;                     // uint8 staging of parsed FASTA
+    // index build
+    DevBuf gs, rank, flags, list0, list1, gsn;
+    // seeding
+    DevBuf sections, stage, tile_cnt, tile_off, anchors;   // anchors: int4 (r, q, len, tag)
+    // clustering
+    DevBuf cl_a, cl_b, cl_c, cl_d, cl_e, cl_f, cl_g, cl_h, cl_i, cl_j, cl_k, cl_l;
+    DevBuf cl_matches, cl_recs, cl_counters;
+    // extension
+    DevBuf ex_a, ex_b, ex_c, ex_d, ex_e, ex_f, ex_g, ex_h, ex_i, ex_j, ex_k, ex_l;
+    DevBuf ex_scores, ex_tb, ex_tbidx, ex_pool, ex_counters, ex_arena;
+    // host-side counts handed from one stage to the next (one pair in flight per context)
+    int64_t n_anchors = 0, n_clusters = 0, n_cl_matches = 0;
+    // pinned host staging
+    void *pinned = nullptr; size_t pinned_cap = 0;
+    int ensure_pinned(size_t bytes)
+    {
+        if (bytes <= pinned_cap) return 0;
+        if (pinned) cudaFreeHost(pinned);
+        size_t want = bytes + bytes / 4 + 4096;
+        if (cudaMallocHost(&pinned, want) != cudaSuccess) { pinned = nullptr; pinned_cap = 0; return pmn_set_error(-3, "cudaMallocHost(%zu) failed", want); }
+        pinned_cap = want;
+        return 0;
+    }
+};

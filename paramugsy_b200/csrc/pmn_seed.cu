@@ -1,0 +1,220 @@
+// pmn_seed.cu — MUM-reference seeding of every query position, both strands.
+//
+// Stands in for `mummer -mumreference -b -l 20 -n` inside the `nucmer` child process of
+// /root/reference/lib/nucmer/mugsy_nucmer.ml:100.  Oracle counterpart: oracle/pmn_oracle.c §4
+// (seed_strand) — the anchor list must be identical, in (tag, query pos) order.
+//
+// Per query position i of a (record, strand) section:
+//   1. 32-base window of the query from shared memory (the tile of packed query text and
+//      its x-mask is staged by one TMA bulk copy per block, cp.async.bulk + mbarrier)
+//   2. bucket [lo,hi) of the window's first K bases from the K-mer table
+//   3. lower bound of Q[i..] among the bucket's suffixes (binary search on packed text,
+//      32 bases per probe)
+//   4. longest match = better of the two neighbours of the insertion point; unique iff the
+//      other neighbour is shorter and the LCP entry on the far side is shorter too
+//   5. left-maximality, then ordered compaction of the tile's anchors
+// Output order equals the oracle's sort order, so no sort follows.
+#include "pmn_scratch.cuh"
+
+#define SEED_THREADS 256
+#define SEED_ITERS 8
+#define SEED_TILE (SEED_THREADS * SEED_ITERS)      /* query positions per block */
+#define SEED_WORDS (SEED_TILE / 32 + 8)            /* staged words: tile + alignment slack + one window */
+
+struct SeedSection {
+    int64_t start;      // offset of the record inside the strand's concatenated text
+    int64_t len;        // bases of the record
+    int64_t npos;       // positions to try = len - minmatch + 1 (>= 1)
+    int64_t tile0;      // first tile of this section
+    int32_t tag;        // record*2 + strand
+    int32_t strand;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+
+// true iff the reference suffix at s sorts before Q[g..] (order of pmn_index.cu; a query X or
+// the query end compares greater than every reference symbol)
+__device__ __forceinline__ bool ref_lt_query(const PackedView &R, int64_t s, const PackedView &Q, int64_t g, uint64_t qw0, int vq0)
+{
+    int64_t off = 0;
+    uint64_t qw = qw0; int vq = vq0;
+    for (;;) {
+        int vr = pmn_valid32(R, s + off);
+        uint64_t rw = pmn_window64(R.w, s + off);
+        uint64_t x = rw ^ qw;
+        int m = x ? (__clzll((long long)x) >> 1) : 32;
+        int v = vr < vq ? vr : vq;
+        if (m < v) return ((rw >> (62 - 2 * m)) & 3ull) < ((qw >> (62 - 2 * m)) & 3ull);
+        if (v == 32) { off += 32; vq = pmn_valid32(Q, g + off); qw = pmn_window64(Q.w, g + off); continue; }
+        if (vr < vq) return s + off + vr >= R.n;     // reference ran out (END, smallest) or hit an X (greater)
+        return true;                                 // the query hit X/END first, or both did: query is greater
+    }
+}
+
+__global__ void __launch_bounds__(SEED_THREADS) k_seed(PackedView R, const uint32_t *__restrict__ sa, const int32_t *__restrict__ lcp,
+                                                      const uint32_t *__restrict__ table, int K, PackedView QF, PackedView QR,
+                                                      const SeedSection *__restrict__ secs, int nsec, int minmatch,
+                                                      int4 *__restrict__ stage, uint32_t *__restrict__ tile_cnt)
+{
+    __shared__ __align__(16) uint64_t s_w[SEED_WORDS];
+    __shared__ __align__(16) uint32_t s_x[SEED_WORDS];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_wc[SEED_THREADS / 32];
+    __shared__ uint32_t s_count;
+
+    // which section does this tile belong to
+    int lo_s = 0, hi_s = nsec - 1;
+    while (lo_s < hi_s) { int mid = (lo_s + hi_s + 1) >> 1; if (secs[mid].tile0 <= (int64_t)blockIdx.x) lo_s = mid; else hi_s = mid - 1; }
+    const SeedSection sec = secs[lo_s];
+    const PackedView Q = sec.strand ? QR : QF;
+    const int64_t off0 = ((int64_t)blockIdx.x - sec.tile0) * SEED_TILE;    // first position of the tile inside the record
+    const int64_t g0 = sec.start + off0;
+    const int64_t w0 = (g0 >> 5) & ~3ll;                                   // 16-byte aligned for text and mask
+
+    if (threadIdx.x == 0) { mbar_init(&s_bar, 1); s_count = 0; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t bytes = SEED_WORDS * 8 + (Q.has_x ? SEED_WORDS * 4 : 0);
+        mbar_expect_tx(&s_bar, bytes);
+        tma_bulk_g2s(s_w, Q.w + w0, SEED_WORDS * 8, &s_bar);
+        if (Q.has_x) tma_bulk_g2s(s_x, Q.xm + w0, SEED_WORDS * 4, &s_bar);
+    }
+    mbar_wait(&s_bar, 0);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt = pmn_lanemask_lt();
+    const int first_need = minmatch < 32 ? minmatch : 32;
+
+    for (int it = 0; it < SEED_ITERS; it++) {
+        const int64_t off = off0 + it * SEED_THREADS + threadIdx.x;   // position inside the record
+        bool found = false; int4 out = make_int4(0, 0, 0, 0);
+        if (off < sec.npos) {
+            const int64_t g = sec.start + off;
+            // first window from the staged tile
+            int64_t rel = g - (w0 << 5); int k = (int)(rel >> 5), sh = (int)(rel & 31);
+            uint64_t a = s_w[k], b = s_w[k + 1];
+            uint64_t qw = sh ? (a << (2 * sh)) | (b >> (64 - 2 * sh)) : a;
+            int vq;
+            if (Q.has_x) { uint32_t xw = __funnelshift_l(s_x[k + 1], s_x[k], sh); vq = xw ? __clz((int)xw) : 32; }
+            else { int64_t r = Q.n - g; vq = r < 32 ? (int)r : 32; }
+            if (vq >= first_need) {
+                uint32_t lo, hi;
+                if (minmatch >= K) { uint32_t km = (uint32_t)(qw >> (64 - 2 * K)); lo = __ldg(table + km); hi = __ldg(table + km + 1); }
+                else { lo = 0; hi = (uint32_t)R.n; }
+                if (lo < hi) {
+                    while (lo < hi) {
+                        uint32_t mid = (lo + hi) >> 1;
+                        if (ref_lt_query(R, __ldg(sa + mid), Q, g, qw, vq)) lo = mid + 1; else hi = mid;
+                    }
+                    const int64_t p = lo;
+                    int64_t L1 = p > 0 ? pmn_lcp(Q, g, R, __ldg(sa + p - 1), 0, Q.n) : -1;
+                    int64_t L2 = p < R.n ? pmn_lcp(Q, g, R, __ldg(sa + p), 0, Q.n) : -1;
+                    int64_t L = L1 > L2 ? L1 : L2;
+                    if (L >= minmatch && L1 != L2) {
+                        bool unique; int64_t r;
+                        if (L2 > L1) { r = __ldg(sa + p); unique = !(p + 1 < R.n && __ldg(lcp + p + 1) >= L); }
+                        else { r = __ldg(sa + p - 1); unique = !(__ldg(lcp + p - 1) >= L); }
+                        if (unique) {
+                            int qb = pmn_base_at(Q, g - 1), rb = pmn_base_at(R, r - 1);
+                            if (!(qb == rb && qb < 4)) { found = true; out = make_int4((int)(r + 1), (int)(off + 1), (int)L, sec.tag); }
+                        }
+                    }
+                }
+            }
+        }
+        // ordered compaction of this iteration's 256 positions
+        unsigned bal = __ballot_sync(0xffffffffu, found);
+        if (lane == 0) s_wc[warp] = __popc(bal);
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < SEED_THREADS / 32; w++) { uint32_t cw = s_wc[w]; if (w < warp) before += cw; total += cw; }
+        uint32_t base = s_count;
+        if (found) stage[(size_t)blockIdx.x * SEED_TILE + base + before + __popc(bal & lt)] = out;
+        __syncthreads();
+        if (threadIdx.x == 0) s_count = base + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tile_cnt[blockIdx.x] = s_count;
+}
+
+// gather the per-tile runs into one contiguous, ordered anchor array
+__global__ void __launch_bounds__(256) k_seed_gather(const int4 *__restrict__ stage, const uint32_t *__restrict__ tile_cnt,
+                                                    const uint32_t *__restrict__ tile_off, int4 *__restrict__ anchors)
+{
+    uint32_t cnt = tile_cnt[blockIdx.x], off = tile_off[blockIdx.x];
+    for (uint32_t k = threadIdx.x; k < cnt; k += blockDim.x) anchors[off + k] = stage[(size_t)blockIdx.x * SEED_TILE + k];
+}
+
+int pmn_seed_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_opts *o, int64_t *n_anchors)
+{
+    Scratch &S = *c->scratch;
+    cudaStream_t st = c->stream;
+    *n_anchors = 0;
+    if (o->minmatch < 1) return pmn_set_error(PMN_E_ARG, "minmatch must be positive");
+    std::vector<SeedSection> secs;
+    int64_t tiles = 0;
+    for (int rec = 0; rec < q->nrec; rec++) {
+        for (int strand = 0; strand < 2; strand++) {
+            if (strand == 0 && !o->do_forward) continue;
+            if (strand == 1 && !o->do_reverse) continue;
+            int64_t npos = q->len[rec] - o->minmatch + 1;
+            if (npos < 1) continue;
+            SeedSection s;
+            s.start = strand ? q->n - q->off[rec] - q->len[rec] : q->off[rec];
+            s.len = q->len[rec]; s.npos = npos; s.tile0 = tiles; s.tag = rec * 2 + strand; s.strand = strand;
+            secs.push_back(s);
+            tiles += (npos + SEED_TILE - 1) / SEED_TILE;
+        }
+    }
+    if (tiles == 0) return 0;
+    if (tiles > 0x7fffffffll) return pmn_set_error(PMN_E_ARG, "seed: query too large");
+    if (S.sections.ensure(sizeof(SeedSection) * secs.size()) || S.stage.ensure(sizeof(int4) * (size_t)tiles * SEED_TILE) ||
+        S.tile_cnt.ensure(4 * (size_t)tiles) || S.tile_off.ensure(4 * (size_t)tiles) ||
+        S.scan_tmp.ensure(8 * pmn_scan_scratch_elems(tiles)) || S.ensure_pinned(64)) return -3;
+    PMN_CUDA_OK(cudaMemcpyAsync(S.sections.p, secs.data(), sizeof(SeedSection) * secs.size(), cudaMemcpyHostToDevice, st));
+    k_seed<<<(unsigned)tiles, SEED_THREADS, 0, st>>>(ix->seq->fwd(), ix->sa.as<uint32_t>(), ix->lcp.as<int32_t>(), ix->table.as<uint32_t>(), ix->K,
+                                                     q->fwd(), q->rev(), S.sections.as<SeedSection>(), (int)secs.size(), o->minmatch,
+                                                     S.stage.as<int4>(), S.tile_cnt.as<uint32_t>());
+    pmn_scan<uint32_t, OpAddU32, false>(S.tile_cnt.as<uint32_t>(), S.tile_off.as<uint32_t>(), tiles, S.scan_tmp.as<uint32_t>(), st);
+    uint32_t *tail = (uint32_t *)S.pinned;
+    PMN_CUDA_OK(cudaMemcpyAsync(tail, S.tile_off.as<uint32_t>() + (tiles - 1), 4, cudaMemcpyDeviceToHost, st));
+    PMN_CUDA_OK(cudaMemcpyAsync(tail + 1, S.tile_cnt.as<uint32_t>() + (tiles - 1), 4, cudaMemcpyDeviceToHost, st));
+    PMN_CUDA_OK(cudaStreamSynchronize(st));   // the secs vector is also safe to drop after this
+    int64_t total = (int64_t)tail[0] + tail[1];
+    c->launches += 4;
+    if (total > 0) {
+        if (S.anchors.ensure(sizeof(int4) * (size_t)total)) return -3;
+        k_seed_gather<<<(unsigned)tiles, 256, 0, st>>>(S.stage.as<int4>(), S.tile_cnt.as<uint32_t>(), S.tile_off.as<uint32_t>(), S.anchors.as<int4>());
+        c->launches += 1;
+    }
+    PMN_CUDA_OK(cudaGetLastError());
+    *n_anchors = total;
+    return 0;
+}

@@ -1,0 +1,228 @@
+"""ctypes binding of libpmnucmer.so (include/pmnucmer.h).
+
+The extension is built in-tree by paramugsy_b200/build.py (nvcc, sm_100a).  There is no
+CPU fallback anywhere: if the library is missing it is built, if it cannot be loaded or no
+B200 is visible every computing call raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class PmnError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libpmnucmer error {code}: {msg}")
+        self.code = code
+
+
+class Opts(C.Structure):
+    _fields_ = [("minmatch", C.c_int32), ("mincluster", C.c_int32), ("maxgap", C.c_int32),
+                ("diagdiff", C.c_int32), ("diagfactor", C.c_double), ("breaklen", C.c_int32),
+                ("do_forward", C.c_int32), ("do_reverse", C.c_int32), ("do_extend", C.c_int32),
+                ("do_optimize", C.c_int32), ("do_simplify", C.c_int32), ("keep_stages", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("ref_bases", C.c_int64), ("qry_bases", C.c_int64), ("anchors", C.c_int64),
+                ("clusters", C.c_int64), ("cluster_matches", C.c_int64), ("alignments", C.c_int64),
+                ("aligned_ref_bases", C.c_int64), ("dp_cells", C.c_int64), ("dp_jobs", C.c_int64),
+                ("sa_rounds", C.c_int32), ("kmer_bits", C.c_int32),
+                ("ms_index", C.c_float), ("ms_seed", C.c_float), ("ms_cluster", C.c_float),
+                ("ms_extend", C.c_float), ("ms_total", C.c_float), ("kernel_launches", C.c_int64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# every symbol include/pmnucmer.h declares (tests check the .so exports all of them)
+SYMBOLS = [
+    "pmn_default_opts", "pmn_ctx_create", "pmn_ctx_destroy", "pmn_last_error", "pmn_device_count",
+    "pmn_seq_from_fasta", "pmn_seq_from_file", "pmn_seq_free", "pmn_seq_bases", "pmn_seq_records",
+    "pmn_index_build", "pmn_index_free", "pmn_align", "pmn_result_delta", "pmn_result_stats",
+    "pmn_result_free", "pmn_align_pair", "pmn_align_batch", "pmn_index_size", "pmn_index_copy_sa",
+    "pmn_result_n_anchors", "pmn_result_copy_anchors", "pmn_result_n_clusters",
+    "pmn_result_n_cluster_matches", "pmn_result_copy_clusters", "pmn_result_n_alignments",
+    "pmn_result_n_deltas", "pmn_result_copy_alignments",
+]
+
+
+def lib_path():
+    return os.path.join(_HERE, "_lib", "libpmnucmer.so")
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(lib_path()):
+            from . import build
+            build.build()
+        L = C.CDLL(lib_path())
+        vp, cp, i64, i32p, i64p = C.c_void_p, C.c_char_p, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+        L.pmn_default_opts.argtypes = [C.POINTER(Opts)]
+        L.pmn_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+        L.pmn_ctx_destroy.argtypes = [vp]
+        L.pmn_last_error.argtypes = [vp]; L.pmn_last_error.restype = cp
+        L.pmn_seq_from_fasta.argtypes = [vp, cp, C.c_size_t, C.POINTER(vp)]
+        L.pmn_seq_from_file.argtypes = [vp, cp, C.POINTER(vp)]
+        L.pmn_seq_free.argtypes = [vp]
+        L.pmn_seq_bases.argtypes = [vp]; L.pmn_seq_bases.restype = i64
+        L.pmn_seq_records.argtypes = [vp]
+        L.pmn_index_build.argtypes = [vp, vp, C.POINTER(vp)]
+        L.pmn_index_free.argtypes = [vp]
+        L.pmn_align.argtypes = [vp, vp, vp, C.POINTER(Opts), cp, cp, C.POINTER(vp)]
+        L.pmn_result_delta.argtypes = [vp, C.POINTER(C.c_size_t)]; L.pmn_result_delta.restype = vp
+        L.pmn_result_stats.argtypes = [vp, C.POINTER(Stats)]
+        L.pmn_result_free.argtypes = [vp]
+        L.pmn_align_pair.argtypes = [vp, cp, cp, C.POINTER(Opts), cp]
+        L.pmn_align_batch.argtypes = [vp, C.c_int, C.POINTER(cp), C.POINTER(cp), C.POINTER(cp), C.POINTER(Opts)]
+        L.pmn_index_size.argtypes = [vp]; L.pmn_index_size.restype = i64
+        L.pmn_index_copy_sa.argtypes = [vp, vp, vp]
+        for name in ("pmn_result_n_anchors", "pmn_result_n_clusters", "pmn_result_n_cluster_matches",
+                     "pmn_result_n_alignments", "pmn_result_n_deltas"):
+            f = getattr(L, name); f.argtypes = [vp]; f.restype = i64
+        L.pmn_result_copy_anchors.argtypes = [vp, vp]
+        L.pmn_result_copy_clusters.argtypes = [vp, vp, vp, vp]
+        L.pmn_result_copy_alignments.argtypes = [vp, vp, vp, vp]
+        _LIB = L
+    return _LIB
+
+
+def default_opts(**kw):
+    o = Opts()
+    lib().pmn_default_opts(C.byref(o))
+    for k, v in kw.items():
+        if not hasattr(o, k):
+            raise TypeError(f"unknown nucmer option {k!r}")
+        setattr(o, k, v)
+    return o
+
+
+def _check(rc):
+    if rc != 0:
+        raise PmnError(rc, lib().pmn_last_error(None).decode(errors="replace"))
+
+
+class Context:
+    """One per (process, GPU): owns the stream and all scratch memory."""
+
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        _check(lib().pmn_ctx_create(device, C.byref(self.h)))
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().pmn_ctx_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def sequence(self, fasta: bytes):
+        return Sequence(self, fasta=fasta)
+
+    def sequence_from_file(self, path: str):
+        return Sequence(self, path=path)
+
+
+class Sequence:
+    def __init__(self, ctx, fasta=None, path=None):
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        if fasta is not None:
+            _check(lib().pmn_seq_from_fasta(ctx.h, fasta, len(fasta), C.byref(self.h)))
+        else:
+            _check(lib().pmn_seq_from_file(ctx.h, os.fsencode(path), C.byref(self.h)))
+
+    @property
+    def bases(self):
+        return lib().pmn_seq_bases(self.h)
+
+    @property
+    def records(self):
+        return lib().pmn_seq_records(self.h)
+
+    def close(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            lib().pmn_seq_free(self.h)
+        self.h = None
+
+    def index(self):
+        return Index(self)
+
+
+class Index:
+    def __init__(self, seq):
+        self.seq = seq           # keeps the sequence alive
+        self.ctx = seq.ctx
+        self.h = C.c_void_p()
+        _check(lib().pmn_index_build(self.ctx.h, seq.h, C.byref(self.h)))
+
+    def close(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            lib().pmn_index_free(self.h)
+        self.h = None
+
+    def suffix_array(self):
+        n = lib().pmn_index_size(self.h)
+        sa = np.empty(n, np.int32); lcp = np.empty(n, np.int32)
+        _check(lib().pmn_index_copy_sa(self.h, sa.ctypes.data, lcp.ctypes.data))
+        return sa, lcp
+
+    def align(self, qry, opts=None, ref_path="ref.fa", qry_path="qry.fa", **kw):
+        o = opts if opts is not None else default_opts(**kw)
+        r = C.c_void_p()
+        _check(lib().pmn_align(self.ctx.h, self.h, qry.h, C.byref(o), os.fsencode(ref_path), os.fsencode(qry_path), C.byref(r)))
+        return Result(r)
+
+
+class Result:
+    def __init__(self, h):
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().pmn_result_free(self.h)
+        self.h = None
+
+    __del__ = close
+
+    @property
+    def delta(self) -> bytes:
+        n = C.c_size_t()
+        p = lib().pmn_result_delta(self.h, C.byref(n))
+        return C.string_at(p, n.value)
+
+    @property
+    def stats(self):
+        s = Stats()
+        lib().pmn_result_stats(self.h, C.byref(s))
+        return s.as_dict()
+
+    def anchors(self):
+        n = lib().pmn_result_n_anchors(self.h)
+        a = np.empty((n, 4), np.int32)
+        if n:
+            _check(lib().pmn_result_copy_anchors(self.h, a.ctypes.data))
+        return a
+
+    def clusters(self):
+        k = lib().pmn_result_n_clusters(self.h); m = lib().pmn_result_n_cluster_matches(self.h)
+        ms = np.empty((m, 3), np.int32); off = np.zeros(k + 1, np.int32); tag = np.empty(k, np.int32)
+        if k:
+            _check(lib().pmn_result_copy_clusters(self.h, ms.ctypes.data, off.ctypes.data, tag.ctypes.data))
+        return ms, off, tag
+
+    def alignments(self):
+        a = lib().pmn_result_n_alignments(self.h); d = lib().pmn_result_n_deltas(self.h)
+        rows = np.empty((a, 10), np.int64); doff = np.zeros(a + 1, np.int64); dl = np.empty(d, np.int64)
+        if a:
+            _check(lib().pmn_result_copy_alignments(self.h, rows.ctypes.data, doff.ctypes.data, dl.ctypes.data))
+        return rows, doff, dl
