@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py — the pairwise nucmer stage on N B200s, one JSON line.
+
+    python bench.py --gpus 1 --steps K --warmup W
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...          # the CPU path (oracle port) on the host cores
+
+Workload (BASELINE.json configs[1]): 8 synthetic 5 Mbp genomes (2 % divergence from a common
+ancestor, two 50 kbp inversions each), all-vs-all = 28 (reference, query) pairs, the earlier
+genome being the reference (lib/base/pm_job.ml:43-51).  One STEP = one pass of the hot path
+over that batch: 7 index builds + 28 x (seeding, clustering, extension, .delta text).
+
+  value   pairs/s with the packed genomes already resident in HBM (index build is inside).
+  e2e     the same through the C ABI from FASTA bytes in HOST memory to .delta bytes in HOST
+          memory: parse + H2D + pack of all 8 genomes and D2H of every result are inside.
+  N > 1   weak scaling: every rank runs the same 28-pair batch on its own GPU (the path is
+          embarrassingly parallel by pair; `--mode strong` shards the 28 pairs over the ranks
+          with the reference indexes built once and broadcast over NCCL instead).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from paramugsy_b200 import synth  # noqa: E402
+
+METRIC = "nucmer_pair_alignments_per_s"
+UNIT = "pairs/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def workload(args):
+    genomes = synth.config_c2(n=args.genome_bp, count=args.genomes, inv_len=max(1000, args.genome_bp // 100))
+    fastas = [(name, synth.fasta(name, seq)) for name, seq in genomes]
+    pairs = [(i, j) for i in range(len(genomes)) for j in range(i + 1, len(genomes))]
+    return genomes, fastas, pairs
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.device)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from paramugsy_b200 import lib
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = lib.Context(local)
+    ext = torch.cuda.ExternalStream(ctx.stream, device=local)
+
+    genomes, fastas, pairs = workload(args)
+    my_pairs = pairs
+    if args.mode == "strong" and world > 1:
+        # group by reference, deal the references to the ranks largest-first
+        by_ref = {}
+        for p in pairs:
+            by_ref.setdefault(p[0], []).append(p)
+        load = [0] * world; mine = []
+        for r, ps in sorted(by_ref.items(), key=lambda kv: -len(kv[1])):
+            k = load.index(min(load)); load[k] += len(ps)
+            if k == rank:
+                mine += ps
+        my_pairs = mine
+    refs = sorted({i for i, _ in my_pairs})
+    total_bp_in = sum(len(genomes[i][1]) + len(genomes[j][1]) for i, j in my_pairs)
+
+    def step_resident(seqs, collect=None):
+        for i in refs:
+            ix = seqs[i].index()
+            for (a, b) in my_pairs:
+                if a != i:
+                    continue
+                res = ix.align(seqs[b], ref_path=genomes[a][0], qry_path=genomes[b][0])
+                if collect is not None:
+                    collect.append((a, b, res.stats, len(res.delta)))
+                res.close()
+            ix.close()
+
+    def step_e2e(collect=None):
+        need = sorted({g for p in my_pairs for g in p})
+        seqs = {g: ctx.sequence(fastas[g][1]) for g in need}
+        step_resident(seqs, collect)
+        for s in seqs.values():
+            s.close()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        c0 = ctx.counters()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        for _ in range(steps):
+            fn()
+        e1.record(ext)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        c1 = ctx.counters()
+        return ms, {k: c1[k] - c0[k] for k in c0}
+
+    # ---- resident arm
+    resident = {g: ctx.sequence(fastas[g][1]) for g in sorted({g for p in my_pairs for g in p})}
+    for _ in range(args.warmup):
+        step_resident(resident)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_res, cnt_res = timed(lambda: step_resident(resident), args.steps)
+    # ---- end-to-end arm (host FASTA bytes -> host .delta bytes)
+    step_e2e()
+    ms_e2e, cnt_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- one instrumented pass for the per-kernel figures
+    detail = []
+    step_resident(resident, detail)
+    int32_gops, _ = ctx.int32_peak()
+
+    npairs_rank = len(my_pairs)
+    if world > 1:
+        t = torch.tensor([npairs_rank, total_bp_in], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        npairs_all, bp_all = float(t[0].item()), float(t[1].item())
+    else:
+        npairs_all, bp_all = float(npairs_rank), float(total_bp_in)
+
+    if rank == 0:
+        hbm_peak, peak_src = peaks()
+        S = lambda k: sum(d[2][k] for d in detail)
+        aligned_bp = S("aligned_ref_bases")
+        stage_ms = {"index": 0.0, "seed": S("ms_seed"), "cluster": S("ms_cluster"), "extend": S("ms_extend")}
+        # every reference index is built once per step: take ms_index once per distinct reference
+        seen = {}
+        for a, b, st, _ in detail:
+            seen.setdefault(a, st["ms_index"])
+        stage_ms["index"] = sum(seen.values())
+        step_ms = ms_res / args.steps
+        # algorithmic bytes (SURVEY.md §8d / DESIGN.md §6)
+        import math
+        b_seed = sum(2 * st["qry_bases"] * (12 * math.ceil(math.log2(max(2, st["ref_bases"]))) + 8.25) + 12 * st["anchors"] for _, _, st, _ in detail)
+        b_index = sum(len(genomes[a][1]) * (4.25 + 16 * max(1, rounds) + 12.5)
+                      for a, rounds in {a: st["sa_rounds"] for a, _, st, _ in detail}.items())
+        seed_kernel_ms = S("ms_seed_kernel")
+        wave1_ms, wave1_cells = S("ms_wave1"), S("wave1_cells")
+        roof_seed = {"kernel": "k_seed", "bound": "hbm", "achieved": b_seed / (seed_kernel_ms * 1e-3) / 1e9 if seed_kernel_ms else None,
+                     "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src, "traffic": None,
+                     "algorithmic_bytes_per_launch": b_seed / max(1, len(detail)), "launch_ms": seed_kernel_ms / max(1, len(detail)),
+                     "share_of_step": seed_kernel_ms / (sum(stage_ms.values()) or 1)}
+        roof_seed["frac"] = roof_seed["achieved"] / hbm_peak if roof_seed["achieved"] else None
+        gcups = wave1_cells / (wave1_ms * 1e-3) / 1e9 if wave1_ms else None
+        roof_ext = {"kernel": "k_ex_wave1", "bound": "int32", "achieved": gcups * 16 if gcups else None, "peak": int32_gops, "unit": "Gop/s",
+                    "peak_source": "measured (pmn_measure_int32_peak, add+max chains)", "gcups": gcups, "ops_per_cell": 16,
+                    "cells_per_step": wave1_cells, "launch_ms": wave1_ms / max(1, len(detail)),
+                    "share_of_step": wave1_ms / (sum(stage_ms.values()) or 1)}
+        roof_ext["frac"] = roof_ext["achieved"] / int32_gops if roof_ext["achieved"] else None
+        roof_idx = {"kernel": "index build (sort + doubling + lcp + table)", "bound": "hbm", "achieved": b_index / (stage_ms["index"] * 1e-3) / 1e9 if stage_ms["index"] else None,
+                    "peak": hbm_peak, "unit": "GB/s"}
+        roof_idx["frac"] = roof_idx["achieved"] / hbm_peak if roof_idx["achieved"] else None
+        dominant = roof_ext if wave1_ms >= seed_kernel_ms else roof_seed
+        out = {
+            "metric": METRIC, "value": npairs_all * args.steps / (ms_res * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
+            "higher_is_better": True, "scaling": "weak" if args.mode == "weak" else "strong", "vs_baseline": None,
+            "dtype": "int32 (2-bit packed text, u8 traceback)", "data": "synthetic",
+            "config": {"workload": f"{args.genomes} synthetic {args.genome_bp / 1e6:g} Mbp genomes, all-vs-all {len(pairs)} pairs "
+                                   f"(BASELINE.json configs[1]); per rank: {npairs_rank} pairs, {len(refs)} index builds per step",
+                       "mode": args.mode, "pairs_per_step_all_ranks": npairs_all,
+                       "l2": "no explicit flush: one step streams > 1 GB of index, staging and score data per pair through a 126 MB L2"},
+            "aligned_mbp_per_s": aligned_bp * world / 1e6 / (step_ms * 1e-3) if args.mode == "weak" else aligned_bp / 1e6 / (step_ms * 1e-3),
+            "input_mbp_per_s": bp_all / 1e6 / (step_ms * 1e-3),
+            "extension_gcups": gcups,
+            "e2e": {"value": npairs_all * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": cnt_e2e["h2d_bytes"] // args.steps, "d2h_bytes_per_step": cnt_e2e["d2h_bytes"] // args.steps,
+                    "delta_bytes_per_step": sum(d[3] for d in detail)},
+            "gpu_launches": cnt_res["launches"],
+            "clocks": clocks,
+            "stage_ms_per_step": stage_ms,
+            "roofline": dominant, "roofline_seed": roof_seed, "roofline_extend": roof_ext, "roofline_index": roof_idx,
+            "counts_per_step": {"anchors": S("anchors"), "clusters": S("clusters"), "alignments": S("alignments"), "dp_cells": S("dp_cells"),
+                                "dp_jobs": S("dp_jobs"), "aligned_ref_bases": aligned_bp},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(args, genomes, fastas, pairs, budget_s=args.cpu_budget)
+        print(json.dumps(out))
+    for s in resident.values():
+        s.close()
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+
+def _cpu_one(job):
+    ref, qry = job
+    from oracle import pmn_oracle
+    t = time.time()
+    r = pmn_oracle.Run(ref, qry, fast_chain=1)
+    d = r.delta("ref", "qry")
+    rows = r.alignments()[0]
+    aligned = int((rows[:, 4] - rows[:, 3] + 1).sum()) if len(rows) else 0
+    cells = r.dp_cells()
+    r.close()
+    return time.time() - t, len(d), aligned, cells
+
+
+def cpu_sample(args, fastas, pairs, nproc, sample_bp):
+    """`nproc` pairs of the workload, each truncated to sample_bp bases, one process per pair."""
+    import multiprocessing as mp
+    jobs = []
+    for (i, j) in pairs[:nproc]:
+        def cut(name, fa):
+            seq = b"".join(fa.split(b"\n")[1:])[:sample_bp]
+            return synth.fasta(name, seq)
+        jobs.append((cut(*fastas[i]), cut(*fastas[j])))
+    t = time.time()
+    with mp.get_context("fork").Pool(nproc) as pool:
+        res = pool.map(_cpu_one, jobs)
+    wall = time.time() - t
+    return wall, res, len(jobs)
+
+
+def cpu_baseline(args, genomes, fastas, pairs, budget_s=25.0):
+    from oracle import pmn_oracle
+    pmn_oracle.build()
+    ncores = os.cpu_count() or 1
+    nproc = max(1, min(ncores, len(pairs), 8))
+    # the oracle needs ~3.5 s per Mbp of pair length on one core; bound the sample to the budget
+    sample_bp = int(min(args.genome_bp, max(100_000, budget_s / 4.0 * 1e6)))
+    wall, res, n = cpu_sample(args, fastas, pairs, nproc, sample_bp)
+    # pairs/s at FULL pair size, scaled linearly in sequence length from the sample
+    scale = sample_bp / args.genome_bp
+    return {"value": n / wall * scale, "unit": UNIT, "cores": nproc, "kind": "port",
+            "sample": f"{n} pairs of the workload truncated to {sample_bp} bp each, {nproc} processes, one pair per process, "
+                      f"wall {wall:.1f} s; scaled linearly to {args.genome_bp} bp pairs (oracle with fast_chain=1, identical output)",
+            "aligned_mbp_per_s": sum(r[2] for r in res) / 1e6 / wall, "what": "CPU restatement oracle/pmn_oracle.c, not MUMmer"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import pmn_oracle
+    pmn_oracle.build()
+    genomes, fastas, pairs = workload(args)
+    ncores = os.cpu_count() or 1
+    nproc = max(1, min(ncores, len(pairs)))
+    sample_bp = int(min(args.genome_bp, args.ref_sample_bp))
+    for _ in range(args.warmup):
+        cpu_sample(args, fastas, pairs, nproc, min(sample_bp, 100_000))
+    t0 = time.time(); n = 0
+    for _ in range(args.steps):
+        wall, res, k = cpu_sample(args, fastas, pairs, nproc, sample_bp)
+        n += k
+    tot = time.time() - t0
+    scale = sample_bp / args.genome_bp
+    v = n / tot * scale
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": tot / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64 (CPU)",
+           "data": "synthetic",
+           "config": {"workload": f"{args.genomes} synthetic {args.genome_bp / 1e6:g} Mbp genomes, all-vs-all {len(pairs)} pairs (BASELINE.json configs[1])"},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": nproc, "kind": "port",
+                            "sample": f"each step: {nproc} pairs truncated to {sample_bp} bp, one process per pair; scaled linearly to full-size pairs"},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "note": "the reference's own CPU path is MUMmer 3.20 (not vendored, absent here); this times the in-repo CPU restatement"}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--genomes", type=int, default=8)
+    ap.add_argument("--genome-bp", type=int, default=5_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=25.0)
+    ap.add_argument("--ref-sample-bp", type=int, default=1_000_000)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -63,7 +63,10 @@ typedef struct pmn_stats {
     int32_t sa_rounds;           /* prefix-doubling rounds after the 16-mer pass       */
     int32_t kmer_bits;           /* 2*K of the bucket table                            */
     float   ms_index, ms_seed, ms_cluster, ms_extend, ms_total;   /* CUDA-event times  */
+    float   ms_seed_kernel;      /* k_seed alone                                       */
+    float   ms_wave1, ms_stitch; /* k_ex_wave1 / k_ex_stitch alone                     */
     int64_t kernel_launches;     /* kernels launched for this pair                     */
+    int64_t wave1_cells;         /* DP cells evaluated inside k_ex_wave1               */
 } pmn_stats;
 
 void pmn_default_opts(pmn_opts *o);
@@ -73,6 +76,15 @@ int  pmn_ctx_create(int device, pmn_ctx **out);
 void pmn_ctx_destroy(pmn_ctx *c);
 const char *pmn_last_error(const pmn_ctx *c);      /* c may be NULL: last error of the calling thread */
 int  pmn_device_count(void);
+/* the CUDA stream (cudaStream_t) every kernel of this context is launched on, so that a caller
+ * can bracket calls with its own CUDA events */
+void *pmn_ctx_stream(const pmn_ctx *c);
+/* running totals since pmn_ctx_create: out[0] kernels launched, out[1] host->device bytes,
+ * out[2] device->host bytes, out[3] pairs aligned */
+void pmn_ctx_counters(const pmn_ctx *c, int64_t out[4]);
+/* INT32 ALU issue rate of this GPU in 10^9 ops/s (dependent-free IADD3/VIMNMX chains on every SM):
+ * the roofline denominator of the extension DP, which MEASURED_PEAKS.json does not hold */
+int  pmn_measure_int32_peak(pmn_ctx *c, double *gops_per_s, double *sm_mhz_effective);
 
 /* ---- sequences: FASTA bytes in HOST memory -> packed text in HBM ---- */
 int  pmn_seq_from_fasta(pmn_ctx *c, const char *fasta, size_t bytes, pmn_seq **out);

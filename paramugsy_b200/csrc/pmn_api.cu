@@ -77,6 +77,55 @@ extern "C" int pmn_ctx_create(int device, pmn_ctx **out)
     return 0;
 }
 
+extern "C" void *pmn_ctx_stream(const pmn_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+extern "C" void pmn_ctx_counters(const pmn_ctx *c, int64_t out[4])
+{
+    if (!c || !out) return;
+    out[0] = c->launches; out[1] = c->h2d_bytes; out[2] = c->d2h_bytes; out[3] = c->pairs;
+}
+
+// dependent-free chains of (add, max) on 8 accumulators per thread: the instruction mix of the
+// DP inner loop (IADD3 / VIMNMX on the integer pipe)
+__global__ void __launch_bounds__(1024) k_int32_peak(int *out, int seed, int iters)
+{
+    int a0 = seed + threadIdx.x, a1 = a0 ^ 0x55, a2 = a0 + 7, a3 = a0 - 9, a4 = a0 * 3, a5 = a0 + 11, a6 = a0 - 13, a7 = a0 ^ 0x33;
+    const int x = seed | 1, y = seed - 3;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            a0 = max(a0 + x, y); a1 = max(a1 + x, y); a2 = max(a2 + x, y); a3 = max(a3 + x, y);
+            a4 = max(a4 + x, y); a5 = max(a5 + x, y); a6 = max(a6 + x, y); a7 = max(a7 + x, y);
+        }
+    }
+    int r = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+    if (r == 0x7fffffff) out[0] = r;      // never true in practice; keeps the chains alive
+}
+
+extern "C" int pmn_measure_int32_peak(pmn_ctx *c, double *gops_per_s, double *sm_mhz_effective)
+{
+    if (!c || !gops_per_s) return pmn_set_error(PMN_E_ARG, "pmn_measure_int32_peak: NULL argument");
+    PMN_CUDA_OK(cudaSetDevice(c->device));
+    Scratch &S = *c->scratch;
+    if (S.ex_counters.ensure(128)) return -3;
+    const int iters = 2048, blocks = c->sm_count * 2;
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        PMN_CUDA_OK(cudaEventRecord(c->ev[11], c->stream));
+        k_int32_peak<<<blocks, 1024, 0, c->stream>>>(S.ex_counters.as<int>(), rep + 1, iters);
+        PMN_CUDA_OK(cudaEventRecord(c->ev[12], c->stream));
+        PMN_CUDA_OK(cudaStreamSynchronize(c->stream));
+        float ms; cudaEventElapsedTime(&ms, c->ev[11], c->ev[12]);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    c->launches += 5;
+    const double ops = (double)blocks * 1024.0 * iters * 8.0 * 8.0 * 2.0;
+    *gops_per_s = ops / (best * 1e-3) / 1e9;
+    if (sm_mhz_effective) *sm_mhz_effective = *gops_per_s * 1e9 / ((double)c->sm_count * 128.0) / 1e6;   // if 128 lanes/SM/clk
+    return 0;
+}
+
 extern "C" void pmn_ctx_destroy(pmn_ctx *c)
 {
     if (!c) return;
@@ -270,7 +319,7 @@ extern "C" int pmn_align(pmn_ctx *c, const pmn_index *ix, const pmn_seq *qry, co
     r->stats.anchors = nanc;
     if (o.keep_stages && nanc > 0) {
         r->anchors.resize((size_t)nanc * 4);
-        PMN_CUDA_OK(cudaMemcpyAsync(r->anchors.data(), S.anchors.p, 16 * (size_t)nanc, cudaMemcpyDeviceToHost, st));
+        PMN_D2H(c, r->anchors.data(), S.anchors.p, 16 * (size_t)nanc);
         PMN_CUDA_OK(cudaStreamSynchronize(st));
     }
     rc = pmn_cluster_impl(c, ix, qry, &o, nanc);
@@ -284,6 +333,8 @@ extern "C" int pmn_align(pmn_ctx *c, const pmn_index *ix, const pmn_seq *qry, co
     cudaEventElapsedTime(&r->stats.ms_cluster, c->ev[3], c->ev[4]);
     cudaEventElapsedTime(&r->stats.ms_extend, c->ev[4], c->ev[5]);
     cudaEventElapsedTime(&r->stats.ms_total, c->ev[2], c->ev[5]);
+    if (nanc >= 0 && qry->n >= o.minmatch) { if (cudaEventElapsedTime(&r->stats.ms_seed_kernel, c->ev[6], c->ev[7]) != cudaSuccess) { cudaGetLastError(); r->stats.ms_seed_kernel = 0; } }
+    c->pairs++;
     write_delta_text(ix->seq, qry, ref_path ? ref_path : "ref", qry_path ? qry_path : "qry", r.get());
     r->stats.kernel_launches = c->launches - launches0;
     *out = r.release();

@@ -320,8 +320,8 @@ int pmn_cluster_impl(pmn_ctx *c, const pmn_index *, const pmn_seq *, const pmn_o
     pmn_scan<uint32_t, OpAddU32, false>(good, pos, n, S.scan_tmp.as<uint32_t>(), st);
     k_cl_compact_anchors<<<g, 256, 0, st>>>(anc, good, pos, n, filt);
     launches += 10;
-    PMN_CUDA_OK(cudaMemcpyAsync(tail, pos + (n - 1), 4, cudaMemcpyDeviceToHost, st));
-    PMN_CUDA_OK(cudaMemcpyAsync(tail + 1, good + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+    PMN_D2H(c, tail, pos + (n - 1), 4);
+    PMN_D2H(c, tail + 1, good + (n - 1), 4);
     PMN_CUDA_OK(cudaStreamSynchronize(st));
     const int64_t nf = (int64_t)tail[0] + tail[1];
     if (nf <= 0) return pmn_set_error(PMN_E_INTERNAL, "cluster: filter removed every anchor");
@@ -332,7 +332,7 @@ int pmn_cluster_impl(pmn_ctx *c, const pmn_index *, const pmn_seq *, const pmn_o
     for (int s = 0; s <= o->maxgap; s++) { long l = (long)(o->diagfactor * (double)s); lim[(size_t)s] = (int32_t)(l > o->diagdiff ? l : o->diagdiff); }
     if (S.cl_g.ensure(4 * lim.size()) || S.cl_h.ensure(4 * (size_t)nf) || S.k0.ensure(8 * (size_t)nf) || S.k1.ensure(8 * (size_t)nf) ||
         S.v0.ensure(4 * (size_t)nf) || S.v1.ensure(4 * (size_t)nf)) return -3;
-    PMN_CUDA_OK(cudaMemcpyAsync(S.cl_g.p, lim.data(), 4 * lim.size(), cudaMemcpyHostToDevice, st));
+    PMN_H2D(c, S.cl_g.p, lim.data(), 4 * lim.size());
     uint32_t *parent = S.cl_h.as<uint32_t>();
     k_cl_init_parent<<<gf, 256, 0, st>>>(parent, nf);
     k_cl_union<<<gf, 256, 0, st>>>(filt, nf, o->maxgap, o->diagdiff, S.cl_g.as<int32_t>(), parent);
@@ -375,10 +375,10 @@ int pmn_cluster_impl(pmn_ctx *c, const pmn_index *, const pmn_seq *, const pmn_o
     uint32_t *mpos = cflag, *kpos = cpos;      // reuse
     pmn_scan<uint32_t, OpAddU32, false>(C.om_valid, mpos, nf, S.scan_tmp.as<uint32_t>(), st);
     pmn_scan<uint32_t, OpAddU32, false>(C.oc_valid, kpos, nf, S.scan_tmp.as<uint32_t>(), st);
-    PMN_CUDA_OK(cudaMemcpyAsync(tail, mpos + (nf - 1), 4, cudaMemcpyDeviceToHost, st));
-    PMN_CUDA_OK(cudaMemcpyAsync(tail + 1, C.om_valid + (nf - 1), 4, cudaMemcpyDeviceToHost, st));
-    PMN_CUDA_OK(cudaMemcpyAsync(tail + 2, kpos + (nf - 1), 4, cudaMemcpyDeviceToHost, st));
-    PMN_CUDA_OK(cudaMemcpyAsync(tail + 3, C.oc_valid + (nf - 1), 4, cudaMemcpyDeviceToHost, st));
+    PMN_D2H(c, tail, mpos + (nf - 1), 4);
+    PMN_D2H(c, tail + 1, C.om_valid + (nf - 1), 4);
+    PMN_D2H(c, tail + 2, kpos + (nf - 1), 4);
+    PMN_D2H(c, tail + 3, C.oc_valid + (nf - 1), 4);
     PMN_CUDA_OK(cudaStreamSynchronize(st));
     const int64_t nm = (int64_t)tail[0] + tail[1], nc = (int64_t)tail[2] + tail[3];
     launches += 6;

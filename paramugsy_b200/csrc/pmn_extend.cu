@@ -710,8 +710,8 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     if (o->keep_stages && nc0 > 0) {
         std::vector<int4> recs((size_t)nc0);
         res->cl_matches.resize((size_t)nm * 3);
-        PMN_CUDA_OK(cudaMemcpyAsync(res->cl_matches.data(), S.cl_matches.p, 12 * (size_t)nm, cudaMemcpyDeviceToHost, st));
-        PMN_CUDA_OK(cudaMemcpyAsync(recs.data(), S.cl_recs.p, 16 * (size_t)nc0, cudaMemcpyDeviceToHost, st));
+        PMN_D2H(c, res->cl_matches.data(), S.cl_matches.p, 12 * (size_t)nm);
+        PMN_D2H(c, recs.data(), S.cl_recs.p, 16 * (size_t)nc0);
         PMN_CUDA_OK(cudaStreamSynchronize(st));
         res->cl_off.resize((size_t)nc0 + 1); res->cl_tag.resize((size_t)nc0);
         for (int64_t k = 0; k < nc0; k++) { res->cl_off[(size_t)k] = recs[(size_t)k].x; res->cl_tag[(size_t)k] = recs[(size_t)k].z; }
@@ -726,8 +726,8 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     for (int i = 0; i < nref; i++) { h[(size_t)i] = ref->off[(size_t)i]; h[(size_t)nref + i] = ref->len[(size_t)i]; }
     for (int i = 0; i < nqry; i++) { h[(size_t)2 * nref + i] = q->off[(size_t)i]; h[(size_t)2 * nref + nqry + i] = q->len[(size_t)i]; }
     if (S.ex_a.ensure(8 * h.size()) || S.ex_b.ensure(4 * 5 * (size_t)nm) || S.ex_c.ensure(4 * 2 * (size_t)nm) || S.scan_tmp.ensure(8 * pmn_scan_scratch_elems(nm)) ||
-        S.ensure_pinned(256)) return -3;
-    PMN_CUDA_OK(cudaMemcpyAsync(S.ex_a.p, h.data(), 8 * h.size(), cudaMemcpyHostToDevice, st));
+        S.ensure_pinned(512)) return -3;
+    PMN_H2D(c, S.ex_a.p, h.data(), 8 * h.size());
     const int64_t *roff = S.ex_a.as<int64_t>(), *rlen = roff + nref, *qoff = roff + 2 * nref, *qlen = qoff + nqry;
     int32_t *mA = S.ex_b.as<int32_t>(), *mB = mA + nm, *mL = mA + 2 * nm, *mrec = mA + 3 * nm, *mtag = mA + 4 * nm;
     uint32_t *pstart = S.ex_c.as<uint32_t>(), *ppos = pstart + nm;
@@ -735,8 +735,8 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     pmn_scan<uint32_t, OpAddU32, false>(pstart, ppos, nm, S.scan_tmp.as<uint32_t>(), st);
     launches += 4;
     uint32_t *tail = (uint32_t *)S.pinned;
-    PMN_CUDA_OK(cudaMemcpyAsync(tail, ppos + (nm - 1), 4, cudaMemcpyDeviceToHost, st));
-    PMN_CUDA_OK(cudaMemcpyAsync(tail + 1, pstart + (nm - 1), 4, cudaMemcpyDeviceToHost, st));
+    PMN_D2H(c, tail, ppos + (nm - 1), 4);
+    PMN_D2H(c, tail + 1, pstart + (nm - 1), 4);
     PMN_CUDA_OK(cudaStreamSynchronize(st));       // also: h may go out of scope
     const int64_t np = (int64_t)tail[0] + tail[1];
 
@@ -760,8 +760,8 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     pmn_scan<uint32_t, OpAddU32, false>(sflag, spos, np, S.scan_tmp.as<uint32_t>(), st);
     k_ex_syntenies<<<gp, 256, 0, st>>>(skeys, sflag, spos, np, cl, syn, roff, rlen, qoff, qlen, q->n);
     launches += 5;
-    PMN_CUDA_OK(cudaMemcpyAsync(tail, spos + (np - 1), 4, cudaMemcpyDeviceToHost, st));
-    PMN_CUDA_OK(cudaMemcpyAsync(tail + 1, sflag + (np - 1), 4, cudaMemcpyDeviceToHost, st));
+    PMN_D2H(c, tail, spos + (np - 1), 4);
+    PMN_D2H(c, tail + 1, sflag + (np - 1), 4);
     PMN_CUDA_OK(cudaStreamSynchronize(st));
     const int nS = (int)(tail[0] + tail[1]);
     k_ex_syn_caps<<<1, 32, 0, st>>>(syn, nS, cl);
@@ -800,8 +800,12 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
         attr_set = true;
     }
     int b1 = blocks1; { int64_t need = (nm + EX_WARPS_PER_BLOCK - 1) / EX_WARPS_PER_BLOCK; if (need < b1) b1 = (int)need; if (b1 < 1) b1 = 1; }
+    PMN_CUDA_OK(cudaEventRecord(c->ev[8], st));
     k_ex_wave1<<<b1, EX_WARPS_PER_BLOCK * 32, smem, st>>>(X);
+    PMN_CUDA_OK(cudaEventRecord(c->ev[9], st));
+    PMN_D2H(c, (unsigned long long *)S.pinned + 24, X.counters + 2, 8);      // cells evaluated by wave 1
     k_ex_stitch<<<blocks_st, EX_WARPS_PER_BLOCK * 32, smem, st>>>(X, fused);
+    PMN_CUDA_OK(cudaEventRecord(c->ev[10], st));
     launches += 2;
 
     // ---- E4
@@ -810,10 +814,13 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     k_ex_list<<<1, 32, 0, st>>>(syn, X.syn_nal, nS, X.al, al_syn, al_slot, dcount, X.counters + 8);
     launches++;
     unsigned long long *hc = (unsigned long long *)S.pinned;
-    PMN_CUDA_OK(cudaMemcpyAsync(hc, X.counters, 128, cudaMemcpyDeviceToHost, st));
+    PMN_D2H(c, hc, X.counters, 128);
     PMN_CUDA_OK(cudaStreamSynchronize(st));
     const unsigned long long errflags = hc[4];
     res->stats.dp_cells = (int64_t)hc[2]; res->stats.dp_jobs = (int64_t)hc[3];
+    res->stats.wave1_cells = (int64_t)hc[24];
+    cudaEventElapsedTime(&res->stats.ms_wave1, c->ev[8], c->ev[9]);
+    cudaEventElapsedTime(&res->stats.ms_stitch, c->ev[9], c->ev[10]);
     c->launches += launches; launches = 0;
     if (errflags & EX_ERR_POOL) return pmn_set_error(PMN_E_NOMEM, "extend: delta pool exhausted (%zu entries)", pool_cap);
     if (errflags & EX_ERR_ARENA) return pmn_set_error(PMN_E_NOMEM, "extend: traceback arena exhausted (%zu bytes)", arena_cap);
@@ -827,9 +834,9 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
         launches += 4;
         res->al_rows.resize((size_t)nal * 10);
         std::vector<int32_t> d32((size_t)nd), dc((size_t)nal);
-        PMN_CUDA_OK(cudaMemcpyAsync(res->al_rows.data(), S.ex_g.p, 80 * (size_t)nal, cudaMemcpyDeviceToHost, st));
-        if (nd) PMN_CUDA_OK(cudaMemcpyAsync(d32.data(), S.ex_d.p, 4 * (size_t)nd, cudaMemcpyDeviceToHost, st));
-        PMN_CUDA_OK(cudaMemcpyAsync(dc.data(), dcount, 4 * (size_t)nal, cudaMemcpyDeviceToHost, st));
+        PMN_D2H(c, res->al_rows.data(), S.ex_g.p, 80 * (size_t)nal);
+        if (nd) PMN_D2H(c, d32.data(), S.ex_d.p, 4 * (size_t)nd);
+        PMN_D2H(c, dc.data(), dcount, 4 * (size_t)nal);
         PMN_CUDA_OK(cudaStreamSynchronize(st));
         res->al_deltas.assign(d32.begin(), d32.end());
         res->al_doff.resize((size_t)nal + 1);

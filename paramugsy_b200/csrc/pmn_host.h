@@ -48,11 +48,16 @@ struct pmn_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[8] = {};
+    cudaEvent_t ev[16] = {};
     PmnError err{};
     Scratch *scratch = nullptr;
     long launches = 0;                  // kernels launched by this library (bench.py's gpu_launches)
+    int64_t h2d_bytes = 0, d2h_bytes = 0, pairs = 0;
 };
+
+// host<->device copies on the context's stream, counted for bench.py's e2e byte figures
+#define PMN_H2D(c, dst, src, bytes) do { (c)->h2d_bytes += (int64_t)(bytes); PMN_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (c)->stream)); } while (0)
+#define PMN_D2H(c, dst, src, bytes) do { (c)->d2h_bytes += (int64_t)(bytes); PMN_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (c)->stream)); } while (0)
 
 // stage entry points (defined in the .cu files)
 int pmn_pack_upload(pmn_ctx *c, pmn_seq *s, const uint8_t *codes_host);

@@ -67,7 +67,7 @@ int pmn_pack_upload(pmn_ctx *c, pmn_seq *s, const uint8_t *codes_host)
     if (S.codes.ensure((size_t)n + 64)) return -3;
     if (s->w_fwd.ensure(8 * (size_t)s->nwords) || s->xm_fwd.ensure(4 * (size_t)s->nwords) ||
         s->w_rev.ensure(8 * (size_t)s->nwords) || s->xm_rev.ensure(4 * (size_t)s->nwords)) return -3;
-    PMN_CUDA_OK(cudaMemcpyAsync(S.codes.p, codes_host, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    PMN_H2D(c, S.codes.p, codes_host, (size_t)n);
     unsigned g = (unsigned)((s->nwords + 255) / 256);
     k_pack<<<g, 256, 0, c->stream>>>(S.codes.as<uint8_t>(), n, s->w_fwd.as<uint64_t>(), s->xm_fwd.as<uint32_t>(), s->nwords);
     k_revcomp<<<g, 256, 0, c->stream>>>(s->w_fwd.as<uint64_t>(), s->xm_fwd.as<uint32_t>(), n, s->w_rev.as<uint64_t>(), s->xm_rev.as<uint32_t>(), s->nwords);
@@ -261,8 +261,8 @@ int pmn_index_build_impl(pmn_ctx *c, const pmn_seq *ref, pmn_index *ix)
         // compact the flagged entries of the current list (round 0: of all slots)
         pmn_scan<uint32_t, OpAddU32, false>(flags, pos, m, S.scan_tmp.as<uint32_t>(), st); launches += 3;
         k_compact<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(flags, pos, m, src, list_next); launches++;
-        PMN_CUDA_OK(cudaMemcpyAsync(tail, pos + (m - 1), 4, cudaMemcpyDeviceToHost, st));
-        PMN_CUDA_OK(cudaMemcpyAsync(tail + 1, flags + (m - 1), 4, cudaMemcpyDeviceToHost, st));
+        PMN_D2H(c, tail, pos + (m - 1), 4);
+        PMN_D2H(c, tail + 1, flags + (m - 1), 4);
         PMN_CUDA_OK(cudaStreamSynchronize(st));
         int64_t m2 = (int64_t)tail[0] + tail[1];
         { uint32_t *t = list; list = list_next; list_next = t; }

@@ -198,14 +198,16 @@ int pmn_seed_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_o
     if (S.sections.ensure(sizeof(SeedSection) * secs.size()) || S.stage.ensure(sizeof(int4) * (size_t)tiles * SEED_TILE) ||
         S.tile_cnt.ensure(4 * (size_t)tiles) || S.tile_off.ensure(4 * (size_t)tiles) ||
         S.scan_tmp.ensure(8 * pmn_scan_scratch_elems(tiles)) || S.ensure_pinned(64)) return -3;
-    PMN_CUDA_OK(cudaMemcpyAsync(S.sections.p, secs.data(), sizeof(SeedSection) * secs.size(), cudaMemcpyHostToDevice, st));
+    PMN_H2D(c, S.sections.p, secs.data(), sizeof(SeedSection) * secs.size());
+    PMN_CUDA_OK(cudaEventRecord(c->ev[6], st));
     k_seed<<<(unsigned)tiles, SEED_THREADS, 0, st>>>(ix->seq->fwd(), ix->sa.as<uint32_t>(), ix->lcp.as<int32_t>(), ix->table.as<uint32_t>(), ix->K,
                                                      q->fwd(), q->rev(), S.sections.as<SeedSection>(), (int)secs.size(), o->minmatch,
                                                      S.stage.as<int4>(), S.tile_cnt.as<uint32_t>());
+    PMN_CUDA_OK(cudaEventRecord(c->ev[7], st));
     pmn_scan<uint32_t, OpAddU32, false>(S.tile_cnt.as<uint32_t>(), S.tile_off.as<uint32_t>(), tiles, S.scan_tmp.as<uint32_t>(), st);
     uint32_t *tail = (uint32_t *)S.pinned;
-    PMN_CUDA_OK(cudaMemcpyAsync(tail, S.tile_off.as<uint32_t>() + (tiles - 1), 4, cudaMemcpyDeviceToHost, st));
-    PMN_CUDA_OK(cudaMemcpyAsync(tail + 1, S.tile_cnt.as<uint32_t>() + (tiles - 1), 4, cudaMemcpyDeviceToHost, st));
+    PMN_D2H(c, tail, S.tile_off.as<uint32_t>() + (tiles - 1), 4);
+    PMN_D2H(c, tail + 1, S.tile_cnt.as<uint32_t>() + (tiles - 1), 4);
     PMN_CUDA_OK(cudaStreamSynchronize(st));   // the secs vector is also safe to drop after this
     int64_t total = (int64_t)tail[0] + tail[1];
     c->launches += 4;

@@ -32,7 +32,9 @@ class Stats(C.Structure):
                 ("aligned_ref_bases", C.c_int64), ("dp_cells", C.c_int64), ("dp_jobs", C.c_int64),
                 ("sa_rounds", C.c_int32), ("kmer_bits", C.c_int32),
                 ("ms_index", C.c_float), ("ms_seed", C.c_float), ("ms_cluster", C.c_float),
-                ("ms_extend", C.c_float), ("ms_total", C.c_float), ("kernel_launches", C.c_int64)]
+                ("ms_extend", C.c_float), ("ms_total", C.c_float), ("ms_seed_kernel", C.c_float),
+                ("ms_wave1", C.c_float), ("ms_stitch", C.c_float), ("kernel_launches", C.c_int64),
+                ("wave1_cells", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -41,6 +43,7 @@ class Stats(C.Structure):
 # every symbol include/pmnucmer.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "pmn_default_opts", "pmn_ctx_create", "pmn_ctx_destroy", "pmn_last_error", "pmn_device_count",
+    "pmn_ctx_stream", "pmn_ctx_counters", "pmn_measure_int32_peak",
     "pmn_seq_from_fasta", "pmn_seq_from_file", "pmn_seq_free", "pmn_seq_bases", "pmn_seq_records",
     "pmn_index_build", "pmn_index_free", "pmn_align", "pmn_result_delta", "pmn_result_stats",
     "pmn_result_free", "pmn_align_pair", "pmn_align_batch", "pmn_index_size", "pmn_index_copy_sa",
@@ -66,6 +69,9 @@ def lib():
         L.pmn_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
         L.pmn_ctx_destroy.argtypes = [vp]
         L.pmn_last_error.argtypes = [vp]; L.pmn_last_error.restype = cp
+        L.pmn_ctx_stream.argtypes = [vp]; L.pmn_ctx_stream.restype = vp
+        L.pmn_ctx_counters.argtypes = [vp, i64p]
+        L.pmn_measure_int32_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.pmn_seq_from_fasta.argtypes = [vp, cp, C.c_size_t, C.POINTER(vp)]
         L.pmn_seq_from_file.argtypes = [vp, cp, C.POINTER(vp)]
         L.pmn_seq_free.argtypes = [vp]
@@ -124,6 +130,21 @@ class Context:
 
     def __exit__(self, *a):
         self.close()
+
+    @property
+    def stream(self) -> int:
+        """cudaStream_t of this context as an integer (wrap with torch.cuda.ExternalStream)."""
+        return lib().pmn_ctx_stream(self.h) or 0
+
+    def counters(self):
+        out = (C.c_int64 * 4)()
+        lib().pmn_ctx_counters(self.h, out)
+        return {"launches": out[0], "h2d_bytes": out[1], "d2h_bytes": out[2], "pairs": out[3]}
+
+    def int32_peak(self):
+        g, mhz = C.c_double(), C.c_double()
+        _check(lib().pmn_measure_int32_peak(self.h, C.byref(g), C.byref(mhz)))
+        return g.value, mhz.value
 
     def sequence(self, fasta: bytes):
         return Sequence(self, fasta=fasta)
