@@ -46,9 +46,11 @@ struct ExSynteny {
     int64_t Abase, lenA, BbaseF, BbaseR, lenB;     // *base: 0-based concat index of the record's first base
     int32_t alfirst, alcap, nodefirst, nodecap;
 };
-struct ExJob { int32_t endA, endB, dcnt, target; uint32_t doff; int32_t reached, valid, pad; };
-struct ExAlign { int32_t dirB, sA, sB, eA, eB, deltaApos, head, tail, ndelta, live, pad0, pad1; };
-struct ExNode { uint32_t off; int32_t cnt, adjust, next; };
+struct ExJob { int32_t endA, endB, dcnt, target; uint32_t doff; int32_t reached, valid, asum; };   // asum: sum of (d>0 ? d : |d|-1) over the job's deltas
+struct ExAlign { int32_t dirB, sA, sB, eA, eB, P, head, tail, ndelta, live, pad0, pad1; };   // P: reference position consumed through the last indel (sA-1 when none)
+// a piece of an alignment's delta list: type 0 = `cnt` pool entries at `a` whose first value gets +-`b` added;
+// type 1 = the deltas of the wave-1 jobs [a, cnt) (all reached their targets), `b` = P before the range
+struct ExNode { int32_t type; uint32_t a; int32_t cnt, b, outoff, next, alslot, pad; };
 
 struct ExShared {                       // everything the device code needs, passed by value
     PackedView R, QF, QR;
@@ -63,6 +65,10 @@ struct ExShared {                       // everything the device code needs, pas
     unsigned long long *counters;       // [0] pool cursor [1] arena cursor [2] cells [3] engine calls [4] error flags [5] job cursor A [6] job cursor B
     int breaklen, do_extend, do_simplify;
     int32_t *syn_nal;                   // alignments produced per synteny
+    const uint32_t *dcnt_ex;            // exclusive prefix of jobs[].dcnt, nM + 1 entries
+    const long long *lastP;             // per job g: (piece << 32 | j+1), j = latest job <= g of the same cluster that has deltas
+    const uint8_t *anyfail;             // per cluster: some match -> next match job did not reach its target
+    unsigned long long *markkey;        // per job: set at the first job of a claimed range
 };
 
 // ------------------------------------------------------------------------------------ engine
@@ -91,7 +97,7 @@ __device__ __forceinline__ int max_state(int vD, int vI, int vM)
 // Returns reached (0/1); Aend/Bend become the finish cell.  Unless SEARCH, the deltas are
 // appended to the pool: *doff, *dcnt.
 __device__ int align_engine(const Eng &E, int64_t Abase, int64_t Astart, int64_t &Aend, const PackedView &Q, int64_t Bbase, int64_t Bstart, int64_t &Bend,
-                            unsigned m_o, uint32_t *doff, int32_t *dcnt)
+                            unsigned m_o, uint32_t *doff, int32_t *dcnt, int32_t *dasum)
 {
     const ExShared &X = *E.X;
     const int lane = E.lane;
@@ -101,7 +107,7 @@ __device__ int align_engine(const Eng &E, int64_t Abase, int64_t Astart, int64_t
     const bool forced = (m_o & PMN_FORCED_BIT) != 0, search = (m_o & PMN_SEARCH_BIT) != 0;
     const int breaklen = X.breaklen;
     const int max_diff = PMN_GOOD_SCORE * breaklen;
-    if (doff) { *doff = 0; *dcnt = 0; }
+    if (doff) { *doff = 0; *dcnt = 0; *dasum = 0; }
     if (N < 1 || M < 1 || N > PMN_MAX_ALIGNMENT_LENGTH || M > PMN_MAX_ALIGNMENT_LENGTH) {
         if (lane == 0) atomicOr(X.counters + 4, (unsigned long long)EX_ERR_LOGIC);
         return 0;
@@ -251,8 +257,11 @@ __device__ int align_engine(const Eng &E, int64_t Abase, int64_t Astart, int64_t
             if (lane == 0) at = atomicAdd(X.counters + 0, (unsigned long long)nrev);
             at = __shfl_sync(0xffffffffu, at, 0);
             if (at + (unsigned long long)nrev > X.pool_cap) { if (lane == 0) atomicOr(X.counters + 4, (unsigned long long)EX_ERR_POOL); return reached; }
-            for (int k = lane; k < nrev; k += 32) X.pool[at + k] = rev[nrev - 1 - k];
-            *doff = (uint32_t)at; *dcnt = nrev;
+            int asum = 0;
+            for (int k = lane; k < nrev; k += 32) { const int d = rev[nrev - 1 - k]; X.pool[at + k] = d; asum += d > 0 ? d : -d - 1; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) asum += __shfl_xor_sync(0xffffffffu, asum, o);
+            *doff = (uint32_t)at; *dcnt = nrev; *dasum = asum;
         }
         __syncwarp();
     }
@@ -292,10 +301,10 @@ __device__ int forward_job(const Eng &E, const ExSynteny &S, int dirB, int64_t e
     int overflow = 0;
     if (targetA - eA + 1 > PMN_MAX_ALIGNMENT_LENGTH) { targetA = eA + PMN_MAX_ALIGNMENT_LENGTH - 1; overflow = 1; m_o |= PMN_OPTIMAL_BIT; }
     if (targetB - eB + 1 > PMN_MAX_ALIGNMENT_LENGTH) { targetB = eB + PMN_MAX_ALIGNMENT_LENGTH - 1; overflow = 1; m_o |= PMN_OPTIMAL_BIT; }
-    uint32_t doff; int32_t dcnt;
-    int reached = align_engine(E, S.Abase, eA, targetA, dirB ? E.X->QR : E.X->QF, dirB ? S.BbaseR : S.BbaseF, eB, targetB, m_o, &doff, &dcnt);
+    uint32_t doff; int32_t dcnt, dasum;
+    int reached = align_engine(E, S.Abase, eA, targetA, dirB ? E.X->QR : E.X->QF, dirB ? S.BbaseR : S.BbaseF, eB, targetB, m_o, &doff, &dcnt, &dasum);
     if (reached && overflow) reached = 0;
-    out.endA = (int32_t)targetA; out.endB = (int32_t)targetB; out.dcnt = dcnt; out.doff = doff; out.reached = reached; out.valid = 1;
+    out.endA = (int32_t)targetA; out.endB = (int32_t)targetB; out.dcnt = dcnt; out.doff = doff; out.reached = reached; out.valid = 1; out.asum = dasum;
     return reached;
 }
 
@@ -332,7 +341,7 @@ __global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32) k_ex_wave1(ExShared X
             const int end = S.cfirst + S.nC;
             int tc = get_forward_target_cluster(X, (int)k, end, targetA, targetB);
             unsigned m_o = PMN_FORWARD_ALIGN; if (tc == end) m_o |= PMN_OPTIMAL_BIT;
-            ExJob r; r.pad = 0; r.target = tc;
+            ExJob r; r.target = tc;
             forward_job(E, S, c.dir, (int64_t)X.mA[g] + X.mL[g] - 1, (int64_t)X.mB[g] + X.mL[g] - 1, targetA, targetB, m_o, r);
             if (lane == 0) X.jobs[g] = r;
         }
@@ -345,10 +354,32 @@ __global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32) k_ex_wave1(ExShared X
         const ExCluster c = X.cl[X.mcl[g]];
         if ((int)g == c.mfirst + c.nm - 1) continue;
         const ExSynteny S = X.syn[c.syn];
-        ExJob r; r.pad = 0; r.target = -1;
+        ExJob r; r.target = -1;
         forward_job(E, S, c.dir, (int64_t)X.mA[g] + X.mL[g] - 1, (int64_t)X.mB[g] + X.mL[g] - 1, X.mA[g + 1], X.mB[g + 1], PMN_FORWARD_ALIGN, r);
         if (lane == 0) X.jobs[g] = r;
     }
+}
+
+// ------------------------------------------------------------------------------------ between wave 1 and the stitcher
+
+// per job: delta count (for the prefix that places range deltas), the key of the lastP scan,
+// and the per-cluster "some inner job failed" flag
+__global__ void __launch_bounds__(256) k_ex_jobmeta(const ExJob *__restrict__ jobs, const int32_t *__restrict__ mcl, const ExCluster *__restrict__ cl,
+                                                   const uint32_t *__restrict__ pstart, const uint32_t *__restrict__ ppos, int64_t nm, uint32_t *__restrict__ dcnt, long long *__restrict__ pkey,
+                                                   uint8_t *__restrict__ anyfail)
+{
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > nm) return;
+    if (g == nm) { dcnt[g] = 0; return; }
+    const ExJob j = jobs[g];
+    const int k = mcl[g];
+    const ExCluster c = cl[k];
+    const bool inner = (int)g != c.mfirst + c.nm - 1;
+    dcnt[g] = j.valid ? (uint32_t)j.dcnt : 0u;
+    const long long piece = (long long)(ppos[g] + pstart[g]) - 1;
+    const long long low = (inner && j.valid && j.dcnt > 0) ? g + 1 : 0;      // job index + 1 of a job that has deltas
+    pkey[g] = (piece << 32) | low;
+    if (inner && j.valid && !j.reached) anyfail[k] = 1;
 }
 
 // ------------------------------------------------------------------------------------ E3: stitch
@@ -357,33 +388,26 @@ struct Stitch {
     const Eng *E; const ExSynteny *S; ExAlign *al; ExNode *nodes; int nAl, nNodes; bool fail;
 };
 
+__device__ int new_node(Stitch &T, int ap)
+{
+    if (T.nNodes >= T.S->nodecap) { T.fail = true; return -1; }
+    return T.nNodes++;
+}
+
+// explicit segment: `dcnt` pool entries at doff, first value shifted by `adjust`
 __device__ void al_append(Stitch &T, int ap, uint32_t doff, int dcnt, int adjust)
 {
     if (dcnt <= 0) return;
-    if (T.nNodes >= T.S->nodecap) { T.fail = true; return; }
-    const int nd = T.nNodes++;
+    const int nd = new_node(T, ap);
+    if (nd < 0) return;
     if (T.E->lane == 0) {
-        ExNode n; n.off = doff; n.cnt = dcnt; n.adjust = adjust; n.next = -1;
-        T.nodes[nd] = n;
         ExAlign &a = T.al[ap];
+        ExNode n; n.type = 0; n.a = doff; n.cnt = dcnt; n.b = adjust; n.outoff = a.ndelta; n.next = -1; n.alslot = T.S->alfirst + ap; n.pad = 0;
+        T.nodes[nd] = n;
         if (a.head < 0) a.head = nd; else T.nodes[a.tail].next = nd;
         a.tail = nd; a.ndelta += dcnt;
     }
     __syncwarp();
-}
-
-// sum over a delta segment of (d > 0 ? d : |d| - 1), the first value shifted by `adjust`
-__device__ int64_t seg_apos(const ExShared &X, uint32_t doff, int dcnt, int adjust, int lane)
-{
-    long long s = 0;
-    for (int k = lane; k < dcnt; k += 32) {
-        int d = X.pool[doff + k];
-        if (k == 0) d += d > 0 ? adjust : -adjust;
-        s += d > 0 ? d : -d - 1;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    return s;
 }
 
 // extendForward.  `g` >= 0 names the wave-1 job that computed exactly this extension.
@@ -399,14 +423,57 @@ __device__ int st_extend_forward(Stitch &T, int ap, int dirB, int64_t targetA, i
     }
     if (!have) forward_job(*T.E, *T.S, dirB, a.eA, a.eB, targetA, targetB, m_o, r);
     if (r.dcnt > 0) {
-        const int ValA = (a.eA - a.sA + 1) - a.deltaApos - 1;
-        al_append(T, ap, r.doff, r.dcnt, ValA);
-        a.deltaApos += (int32_t)seg_apos(X, r.doff, r.dcnt, ValA, T.E->lane);
+        // the first new delta counts from the engine's start column: add the bases the alignment
+        // already holds since its last indel; afterwards P = (start - 1) + asum
+        al_append(T, ap, r.doff, r.dcnt, a.eA - a.P - 1);
+        a.P = a.eA - 1 + r.asum;
     }
     a.eA = r.endA; a.eB = r.endB;
-    if (T.E->lane == 0) { ExAlign &w = T.al[ap]; w.eA = a.eA; w.eB = a.eB; w.deltaApos = a.deltaApos; }
+    if (T.E->lane == 0) { ExAlign &w = T.al[ap]; w.eA = a.eA; w.eB = a.eB; w.P = a.P; }
     __syncwarp();
     return r.reached;
+}
+
+// P (reference position consumed through the last indel) left behind by the latest job in
+// [g0, g] that has deltas; `fallback` when there is none
+__device__ __forceinline__ int range_last_P(const ExShared &X, int g0, int g, int fallback)
+{
+    const int j = (int)(X.lastP[g] & 0xffffffffll) - 1;
+    if (j < g0) return fallback;
+    return X.mA[j] + X.mL[j] - 2 + X.jobs[j].asum;
+}
+
+// All jobs [g0, ge) of one cluster reached their targets: absorb matches g0+1 .. ge at once.
+__device__ void st_bulk_forward(Stitch &T, int ap, int dirB, int g0, int ge)
+{
+    const ExShared &X = *T.E->X;
+    const int cnt = (int)(X.dcnt_ex[ge] - X.dcnt_ex[g0]);
+    if (cnt > 0) {
+        const int nd = new_node(T, ap);
+        if (nd < 0) return;
+        if (T.E->lane == 0) {
+            ExAlign &a = T.al[ap];
+            ExNode n; n.type = 1; n.a = (uint32_t)g0; n.cnt = ge; n.b = a.P; n.outoff = a.ndelta; n.next = -1; n.alslot = T.S->alfirst + ap; n.pad = 0;
+            T.nodes[nd] = n;
+            if (a.head < 0) a.head = nd; else T.nodes[a.tail].next = nd;
+            a.tail = nd; a.ndelta += cnt;
+            a.P = range_last_P(X, g0, ge - 1, a.P);
+            X.markkey[g0] = ((unsigned long long)(g0 + 1) << 32) | (unsigned)(T.S->nodefirst + nd + 1);
+        }
+    }
+    if (T.E->lane == 0) { ExAlign &a = T.al[ap]; a.eA = X.mA[ge] + X.mL[ge] - 1; a.eB = X.mB[ge] + X.mL[ge] - 1; }
+    __syncwarp();
+}
+
+// first job in [g, last) that did not reach its target, or `last`
+__device__ int st_next_fail(const ExShared &X, int g, int last, int lane)
+{
+    for (int b = g; b < last; b += 32) {
+        const int k = b + lane;
+        unsigned bal = __ballot_sync(0xffffffffu, k < last && !X.jobs[k].reached);
+        if (bal) return b + __ffs(bal) - 1;
+    }
+    return last;
 }
 
 __device__ int st_get_reverse_target(const Stitch &T, int ap)
@@ -442,7 +509,7 @@ __device__ int st_extend_backward(Stitch &T, int ap, int tp, int dirB)
     if (a.sA - targetA + 1 > PMN_MAX_ALIGNMENT_LENGTH) { targetA = a.sA - PMN_MAX_ALIGNMENT_LENGTH + 1; overflow = 1; m_o |= PMN_OPTIMAL_BIT; }
     if (a.sB - targetB + 1 > PMN_MAX_ALIGNMENT_LENGTH) { targetB = a.sB - PMN_MAX_ALIGNMENT_LENGTH + 1; overflow = 1; m_o |= PMN_OPTIMAL_BIT; }
     const PackedView &Q = dirB ? X.QR : X.QF; const int64_t Bbase = dirB ? S.BbaseR : S.BbaseF;
-    int reached = align_engine(*T.E, S.Abase, a.sA, targetA, Q, Bbase, a.sB, targetB, m_o, nullptr, nullptr);
+    int reached = align_engine(*T.E, S.Abase, a.sA, targetA, Q, Bbase, a.sB, targetB, m_o, nullptr, nullptr, nullptr);
     if (overflow || tp < 0) reached = 0;
     if (reached) {
         st_extend_forward(T, tp, dirB, a.sA, a.sB, PMN_FORCED_FORWARD_ALIGN, -1);
@@ -450,11 +517,10 @@ __device__ int st_extend_backward(Stitch &T, int ap, int tp, int dirB)
         T.nAl--;
         __syncwarp();
     } else {
-        int64_t eA = a.sA, eB = a.sB; uint32_t doff; int32_t dcnt;
-        align_engine(*T.E, S.Abase, targetA, eA, Q, Bbase, targetB, eB, PMN_FORCED_FORWARD_ALIGN, &doff, &dcnt);
+        int64_t eA = a.sA, eB = a.sB; uint32_t doff; int32_t dcnt, dasum;
+        align_engine(*T.E, S.Abase, targetA, eA, Q, Bbase, targetB, eB, PMN_FORCED_FORWARD_ALIGN, &doff, &dcnt, &dasum);
         al_append(T, ap, doff, dcnt, 0);
-        int64_t ap_sum = dcnt > 0 ? seg_apos(X, doff, dcnt, 0, T.E->lane) : 0;
-        if (T.E->lane == 0) { ExAlign &w = T.al[ap]; w.sA = (int32_t)targetA; w.sB = (int32_t)targetB; w.deltaApos += (int32_t)ap_sum; }
+        if (T.E->lane == 0) { ExAlign &w = T.al[ap]; w.sA = (int32_t)targetA; w.sB = (int32_t)targetB; w.P = (int32_t)targetA - 1 + dasum; }
         __syncwarp();
     }
     return reached;
@@ -494,33 +560,49 @@ __global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32) k_ex_stitch(ExShared 
             __syncwarp();
             CurrCp = ++PrevCp; continue;
         }
-        int CurrMp = 0;
-        while (CurrMp < c.nm) {
+        const int last = c.mfirst + c.nm - 1;
+        // a cluster that is being merged a second time (reached as a target after it was fused) goes
+        // job by job, so that every wave-1 job belongs to at most one range node
+        const bool allow_bulk = !fused[CurrCp];
+        int CurrMp = 0; bool positioned = false;       // positioned: CurrAp already ends on the last base of match CurrMp
+        while (CurrMp < c.nm && !T.fail) {
             const int g = c.mfirst + CurrMp;
-            if (target_reached) {
-                const ExAlign a = T.al[CurrAp];
-                if (a.eA != X.mA[g] || a.eB != X.mB[g]) {
-                    if (CurrMp >= c.nm - 1) { logic_err = true; break; }
-                    CurrMp++; continue;
-                }
-                if (lane == 0) { ExAlign &w = T.al[CurrAp]; w.eA += X.mL[g] - 1; w.eB += X.mL[g] - 1; }
-                __syncwarp();
-            } else {
-                if (T.nAl >= S.alcap) { logic_err = true; break; }
-                CurrAp = T.nAl++;
-                if (lane == 0) {
-                    ExAlign a; a.dirB = c.dir; a.sA = X.mA[g]; a.sB = X.mB[g]; a.eA = X.mA[g] + X.mL[g] - 1; a.eB = X.mB[g] + X.mL[g] - 1;
-                    a.deltaApos = 0; a.head = -1; a.tail = -1; a.ndelta = 0; a.live = 1; a.pad0 = a.pad1 = 0;
-                    T.al[CurrAp] = a;
-                }
-                __syncwarp();
-                if (X.do_extend || CurrMp != 0) {
-                    const int TargetAp = st_get_reverse_target(T, CurrAp);
-                    if (st_extend_backward(T, CurrAp, TargetAp, c.dir)) CurrAp = TargetAp;
+            if (!positioned) {
+                if (target_reached) {
+                    const ExAlign a = T.al[CurrAp];
+                    if (a.eA != X.mA[g] || a.eB != X.mB[g]) {
+                        if (CurrMp >= c.nm - 1) { logic_err = true; break; }
+                        CurrMp++; continue;
+                    }
+                    if (lane == 0) { ExAlign &w = T.al[CurrAp]; w.eA += X.mL[g] - 1; w.eB += X.mL[g] - 1; }
+                    __syncwarp();
+                } else {
+                    if (T.nAl >= S.alcap) { logic_err = true; break; }
+                    CurrAp = T.nAl++;
+                    if (lane == 0) {
+                        ExAlign a; a.dirB = c.dir; a.sA = X.mA[g]; a.sB = X.mB[g]; a.eA = X.mA[g] + X.mL[g] - 1; a.eB = X.mB[g] + X.mL[g] - 1;
+                        a.P = a.sA - 1; a.head = -1; a.tail = -1; a.ndelta = 0; a.live = 1; a.pad0 = a.pad1 = 0;
+                        T.al[CurrAp] = a;
+                    }
+                    __syncwarp();
+                    if (X.do_extend || CurrMp != 0) {
+                        const int TargetAp = st_get_reverse_target(T, CurrAp);
+                        if (st_extend_backward(T, CurrAp, TargetAp, c.dir)) CurrAp = TargetAp;
+                    }
                 }
             }
+            positioned = false;
             unsigned m_o = PMN_FORWARD_ALIGN;
             if (CurrMp < c.nm - 1) {
+                const ExAlign a = T.al[CurrAp];
+                if (allow_bulk && a.eA == X.mA[g] + X.mL[g] - 1 && a.eB == X.mB[g] + X.mL[g] - 1) {
+                    const int f = X.anyfail[CurrCp] ? st_next_fail(X, g, last, lane) : last;
+                    if (f > g) {
+                        st_bulk_forward(T, CurrAp, c.dir, g, f);
+                        CurrMp = f - c.mfirst; positioned = true; target_reached = 1;
+                        continue;
+                    }
+                }
                 target_reached = st_extend_forward(T, CurrAp, c.dir, X.mA[g + 1], X.mB[g + 1], m_o, g);
             } else if (X.do_extend) {
                 int64_t targetA = S.lenA, targetB = S.lenB;
@@ -546,7 +628,7 @@ __global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32) k_ex_stitch(ExShared 
 
 // reference record of every match, local coordinate, piece starts
 __global__ void __launch_bounds__(256) k_ex_match_rec(const int32_t *__restrict__ m3, const int4 *__restrict__ recs, int64_t nc, const int64_t *__restrict__ roff,
-                                                     const int64_t *__restrict__ rlen, int nref, int32_t *__restrict__ mA, int32_t *__restrict__ mB,
+                                                     int nref, int32_t *__restrict__ mA, int32_t *__restrict__ mB,
                                                      int32_t *__restrict__ mL, int32_t *__restrict__ mrec, uint32_t *__restrict__ pstart, int32_t *__restrict__ mtag)
 {
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -560,7 +642,6 @@ __global__ void __launch_bounds__(256) k_ex_match_rec(const int32_t *__restrict_
         mA[g] = (int32_t)(sA - roff[lo]); mB[g] = m3[g * 3 + 1]; mL[g] = m3[g * 3 + 2]; mrec[g] = lo; mtag[g] = r.z;
         pstart[g] = lo != prev ? 1u : 0u;
         prev = lo;
-        (void)rlen;
     }
 }
 
@@ -607,18 +688,14 @@ __global__ void __launch_bounds__(256) k_ex_syntenies(const uint64_t *__restrict
         ExSynteny S;
         S.cfirst = (int32_t)k; S.nC = (int32_t)(e - k); S.qrec = qrec; S.rrec = rrec;
         S.Abase = roff[rrec]; S.lenA = rlen[rrec]; S.BbaseF = qoff[qrec]; S.BbaseR = qn - qoff[qrec] - qlen[qrec]; S.lenB = qlen[qrec];
-        // capacity: one alignment per match at most; filled in below from the match counts
-        const int mbeg = cl[k].mfirst;
-        (void)mbeg;
         S.alfirst = 0; S.alcap = 0; S.nodefirst = 0; S.nodecap = 0;
         syn[s] = S;
     }
 }
 
-// capacities per synteny from its clusters' match counts (clusters of a synteny are contiguous)
-__global__ void __launch_bounds__(128) k_ex_syn_caps(ExSynteny *__restrict__ syn, int nS, const ExCluster *__restrict__ cl)
+// capacities per synteny from its clusters' match counts (one thread: nS is small, the prefix sequential)
+__global__ void k_ex_syn_caps(ExSynteny *__restrict__ syn, int nS, const ExCluster *__restrict__ cl)
 {
-    // single thread: nS is small and the prefix is sequential
     if (blockIdx.x || threadIdx.x) return;
     int al = 0, nd = 0;
     for (int s = 0; s < nS; s++) {
@@ -631,9 +708,26 @@ __global__ void __launch_bounds__(128) k_ex_syn_caps(ExSynteny *__restrict__ syn
 
 // ------------------------------------------------------------------------------------ E4: flatten, parseDelta
 
-// one warp per alignment slot: copy its delta segments to out[doff..], then count errors
-__global__ void __launch_bounds__(128) k_ex_finish(ExShared X, const int32_t *__restrict__ al_syn, const uint32_t *__restrict__ al_slot, int64_t nal,
-                                                  const uint32_t *__restrict__ dstart, int32_t *__restrict__ dout, long long *__restrict__ rows)
+// the live alignments of all syntenies in output order (one thread: they are few)
+__global__ void k_ex_list(const ExSynteny *__restrict__ syn, const int32_t *__restrict__ syn_nal, int nS, const ExAlign *__restrict__ al,
+                          int32_t *__restrict__ al_syn, uint32_t *__restrict__ al_slot, uint32_t *__restrict__ dcount, int32_t *__restrict__ slot2out,
+                          unsigned long long *__restrict__ totals)
+{
+    if (blockIdx.x || threadIdx.x) return;
+    unsigned long long n = 0, nd = 0;
+    for (int s = 0; s < nS; s++)
+        for (int k = 0; k < syn_nal[s]; k++) {
+            const int slot = syn[s].alfirst + k;
+            al_syn[n] = s; al_slot[n] = (uint32_t)slot; dcount[n] = (uint32_t)al[slot].ndelta; slot2out[slot] = (int32_t)n;
+            nd += (unsigned long long)al[slot].ndelta; n++;
+        }
+    dcount[n] = 0;
+    totals[0] = n; totals[1] = nd;
+}
+
+// explicit nodes: one warp per alignment walks its list
+__global__ void __launch_bounds__(128) k_ex_flat_nodes(ExShared X, const int32_t *__restrict__ al_syn, const uint32_t *__restrict__ al_slot, int64_t nal,
+                                                      const uint32_t *__restrict__ dstart, int32_t *__restrict__ dout)
 {
     const int lane = threadIdx.x & 31;
     const int64_t k = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -641,63 +735,123 @@ __global__ void __launch_bounds__(128) k_ex_finish(ExShared X, const int32_t *__
     const ExSynteny S = X.syn[al_syn[k]];
     const ExAlign a = X.al[al_slot[k]];
     const ExNode *nodes = X.nodes + S.nodefirst;
-    int32_t *out = dout + dstart[k];
-    int w = 0;
     for (int nd = a.head; nd >= 0; nd = nodes[nd].next) {
         const ExNode n = nodes[nd];
+        if (n.type != 0) continue;
+        int32_t *out = dout + dstart[k] + n.outoff;
         for (int t = lane; t < n.cnt; t += 32) {
-            int d = X.pool[n.off + t];
-            if (t == 0) d += d > 0 ? n.adjust : -n.adjust;
-            out[w + t] = d;
+            int d = X.pool[n.a + t];
+            if (t == 0) d += d > 0 ? n.b : -n.b;
+            out[t] = d;
         }
-        w += n.cnt;
-    }
-    __syncwarp();
-    // parseDelta: walk the alignment, count columns that are not an identical a/c/g/t pair
-    const PackedView &Q = a.dirB ? X.QR : X.QF;
-    const int64_t Ab = S.Abase - 1, Bb = (a.dirB ? S.BbaseR : S.BbaseF) - 1;
-    int64_t Apos = a.sA, Bpos = a.sB, Remain = (int64_t)a.eA - a.sA + 1;
-    long long errs = 0;
-    for (int t = 0; t <= a.ndelta; t++) {
-        int64_t run; int D = 0;
-        if (t < a.ndelta) { D = out[t]; run = (D < 0 ? -D : D) - 1; } else run = Remain;
-        long long e = 0;
-        for (int64_t x = lane; x < run; x += 32) {
-            int ca = pmn_base_at(X.R, Ab + Apos + x), cb = pmn_base_at(Q, Bb + Bpos + x);
-            if (ca != cb || ca == PMN_CODE_X) e++;
-        }
-        errs += e;
-        Apos += run; Bpos += run; Remain -= run;
-        if (t < a.ndelta) { if (lane == 0) errs++; if (D > 0) { Apos++; Remain--; } else Bpos++; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) errs += __shfl_xor_sync(0xffffffffu, errs, o);
-    if (lane == 0) {
-        long long *r = rows + k * 10;
-        r[0] = S.rrec; r[1] = S.qrec; r[2] = a.dirB; r[3] = a.sA; r[4] = a.eA; r[5] = a.sB; r[6] = a.eB; r[7] = errs; r[8] = errs; r[9] = 0;
     }
 }
 
-// list the live alignments of all syntenies in order
-__global__ void __launch_bounds__(128) k_ex_list(const ExSynteny *__restrict__ syn, const int32_t *__restrict__ syn_nal, int nS, const ExAlign *__restrict__ al,
-                                                int32_t *__restrict__ al_syn, uint32_t *__restrict__ al_slot, uint32_t *__restrict__ dcount, unsigned long long *__restrict__ totals)
+// range nodes: one thread per wave-1 job; `mk` is the inclusive max-scan of markkey
+__global__ void __launch_bounds__(256) k_ex_flat_ranges(ExShared X, const unsigned long long *__restrict__ mk, const int32_t *__restrict__ slot2out,
+                                                       const uint32_t *__restrict__ dstart, int32_t *__restrict__ dout)
 {
-    if (blockIdx.x || threadIdx.x) return;
-    unsigned long long n = 0, nd = 0;
-    for (int s = 0; s < nS; s++)
-        for (int k = 0; k < syn_nal[s]; k++) {
-            const int slot = syn[s].alfirst + k;
-            al_syn[n] = s; al_slot[n] = (uint32_t)slot; dcount[n] = (uint32_t)al[slot].ndelta; nd += (unsigned long long)al[slot].ndelta; n++;
-        }
-    totals[0] = n; totals[1] = nd;
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= X.nM) return;
+    const unsigned long long key = mk[g];
+    if (!key) return;
+    const ExNode n = X.nodes[(uint32_t)(key & 0xffffffffull) - 1];
+    const int g0 = (int)n.a;
+    if (n.type != 1 || g < g0 || g >= n.cnt) return;
+    const ExJob j = X.jobs[g];
+    if (j.dcnt <= 0) return;
+    const int k = slot2out[n.alslot];
+    if (k < 0) return;
+    const int Pprev = g > g0 ? range_last_P(X, g0, (int)g - 1, n.b) : n.b;
+    const int adjust = (X.mA[g] + X.mL[g] - 1) - Pprev - 1;
+    int32_t *out = dout + dstart[k] + n.outoff + (X.dcnt_ex[g] - X.dcnt_ex[g0]);
+    for (int t = 0; t < j.dcnt; t++) {
+        int d = X.pool[j.doff + t];
+        if (t == 0) d += d > 0 ? adjust : -adjust;
+        out[t] = d;
+    }
+}
+
+// reference / query bases consumed by each delta (for the position prefix sums)
+__global__ void __launch_bounds__(256) k_ex_consumed(const int32_t *__restrict__ d, int64_t nd, uint32_t *__restrict__ fa, uint32_t *__restrict__ fb)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > nd) return;
+    if (t == nd) { fa[t] = 0; fb[t] = 0; return; }
+    const int v = d[t];
+    fa[t] = v > 0 ? (uint32_t)v : (uint32_t)(-v - 1);
+    fb[t] = v > 0 ? (uint32_t)(v - 1) : (uint32_t)(-v);
+}
+
+__device__ __forceinline__ uint64_t spread32(uint32_t x)     // bit 31-j of x -> bit 62-2j of the result
+{
+    uint64_t v = x;
+    v = (v | (v << 16)) & 0x0000ffff0000ffffull;
+    v = (v | (v << 8)) & 0x00ff00ff00ff00ffull;
+    v = (v | (v << 4)) & 0x0f0f0f0f0f0f0f0full;
+    v = (v | (v << 2)) & 0x3333333333333333ull;
+    v = (v | (v << 1)) & 0x5555555555555555ull;
+    return v;
+}
+
+// columns of a gap-free run that are not an identical a/c/g/t pair
+__device__ __forceinline__ int run_mismatches(const PackedView &R, int64_t a, const PackedView &Q, int64_t b, int64_t run)
+{
+    int cnt = 0;
+    for (int64_t off = 0; off < run; off += 32) {
+        uint64_t x = pmn_window64(R.w, a + off) ^ pmn_window64(Q.w, b + off);
+        uint64_t m = (x | (x >> 1)) & 0x5555555555555555ull;
+        if (R.has_x) m |= spread32(pmn_xwindow32(R.xm, a + off));
+        if (Q.has_x) m |= spread32(pmn_xwindow32(Q.xm, b + off));
+        const int64_t len = run - off;
+        if (len < 32) m &= ~0ull << (64 - 2 * (int)len);
+        cnt += __popcll(m);
+    }
+    return cnt;
+}
+
+// parseDelta in parallel: item t < nd = the run before delta t plus the indel itself;
+// item nd + k = the run behind the last delta of alignment k
+__global__ void __launch_bounds__(256) k_ex_errors(ExShared X, const int32_t *__restrict__ al_syn, const uint32_t *__restrict__ al_slot, int64_t nal,
+                                                  const uint32_t *__restrict__ dstart, const int32_t *__restrict__ d, int64_t nd,
+                                                  const uint32_t *__restrict__ sa_, const uint32_t *__restrict__ sb_, unsigned long long *__restrict__ errs)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nd + nal) return;
+    int64_t k;
+    if (t < nd) {
+        int64_t lo = 0, hi = nal - 1;      // last alignment whose first delta is <= t
+        while (lo < hi) { int64_t mid = (lo + hi + 1) >> 1; if ((int64_t)dstart[mid] <= t) lo = mid; else hi = mid - 1; }
+        k = lo;
+    } else k = t - nd;
+    const ExSynteny S = X.syn[al_syn[k]];
+    const ExAlign a = X.al[al_slot[k]];
+    const PackedView &Q = a.dirB ? X.QR : X.QF;
+    const int64_t Ab = S.Abase - 1, Bb = (a.dirB ? S.BbaseR : S.BbaseF) - 1;
+    const uint32_t first = dstart[k];
+    const int64_t idx = t < nd ? t : (int64_t)dstart[k + 1];
+    const int64_t Apos = a.sA + (int64_t)(uint32_t)(sa_[idx] - sa_[first]), Bpos = a.sB + (int64_t)(uint32_t)(sb_[idx] - sb_[first]);
+    int64_t run; unsigned long long e = 0;
+    if (t < nd) { const int v = d[t]; run = (v < 0 ? -v : v) - 1; e = 1; } else run = (int64_t)a.eA - Apos + 1;
+    if (run > 0) e += (unsigned long long)run_mismatches(X.R, Ab + Apos, Q, Bb + Bpos, run);
+    if (e) atomicAdd(errs + k, e);
+}
+
+__global__ void __launch_bounds__(256) k_ex_rows(ExShared X, const int32_t *__restrict__ al_syn, const uint32_t *__restrict__ al_slot, int64_t nal,
+                                                const unsigned long long *__restrict__ errs, long long *__restrict__ rows)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nal) return;
+    const ExSynteny S = X.syn[al_syn[k]];
+    const ExAlign a = X.al[al_slot[k]];
+    long long *r = rows + k * 10;
+    r[0] = S.rrec; r[1] = S.qrec; r[2] = a.dirB; r[3] = a.sA; r[4] = a.eA; r[5] = a.sB; r[6] = a.eB; r[7] = (long long)errs[k]; r[8] = r[7]; r[9] = 0;
 }
 
 // ------------------------------------------------------------------------------------ driver
 
-static int small_or_radix_sort(Scratch &S, int64_t n, int nbits, cudaStream_t st, int *launches)
-{
-    return pmn_radix_sort(S.k0.as<uint64_t>(), S.v0.as<uint32_t>(), S.k1.as<uint64_t>(), S.v1.as<uint32_t>(), n, nbits, S.rs, st, launches);
-}
+struct OpMaxI64x { __device__ __forceinline__ long long operator()(long long a, long long b) const { return a > b ? a : b; } static __device__ __forceinline__ long long identity() { return LLONG_MIN; } };
+struct OpMaxU64 { __device__ __forceinline__ unsigned long long operator()(unsigned long long a, unsigned long long b) const { return a > b ? a : b; } static __device__ __forceinline__ unsigned long long identity() { return 0ull; } };
 
 int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_opts *o, pmn_result *res)
 {
@@ -725,13 +879,13 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     std::vector<int64_t> h((size_t)2 * nref + 2 * nqry);
     for (int i = 0; i < nref; i++) { h[(size_t)i] = ref->off[(size_t)i]; h[(size_t)nref + i] = ref->len[(size_t)i]; }
     for (int i = 0; i < nqry; i++) { h[(size_t)2 * nref + i] = q->off[(size_t)i]; h[(size_t)2 * nref + nqry + i] = q->len[(size_t)i]; }
-    if (S.ex_a.ensure(8 * h.size()) || S.ex_b.ensure(4 * 5 * (size_t)nm) || S.ex_c.ensure(4 * 2 * (size_t)nm) || S.scan_tmp.ensure(8 * pmn_scan_scratch_elems(nm)) ||
+    if (S.ex_a.ensure(8 * h.size()) || S.ex_b.ensure(4 * 5 * (size_t)nm) || S.ex_c.ensure(4 * 2 * (size_t)nm) || S.scan_tmp.ensure(8 * pmn_scan_scratch_elems(nm + 1)) ||
         S.ensure_pinned(512)) return -3;
     PMN_H2D(c, S.ex_a.p, h.data(), 8 * h.size());
     const int64_t *roff = S.ex_a.as<int64_t>(), *rlen = roff + nref, *qoff = roff + 2 * nref, *qlen = qoff + nqry;
     int32_t *mA = S.ex_b.as<int32_t>(), *mB = mA + nm, *mL = mA + 2 * nm, *mrec = mA + 3 * nm, *mtag = mA + 4 * nm;
     uint32_t *pstart = S.ex_c.as<uint32_t>(), *ppos = pstart + nm;
-    k_ex_match_rec<<<(unsigned)((nc0 + 255) / 256), 256, 0, st>>>(S.cl_matches.as<int32_t>(), S.cl_recs.as<int4>(), nc0, roff, rlen, nref, mA, mB, mL, mrec, pstart, mtag);
+    k_ex_match_rec<<<(unsigned)((nc0 + 255) / 256), 256, 0, st>>>(S.cl_matches.as<int32_t>(), S.cl_recs.as<int4>(), nc0, roff, nref, mA, mB, mL, mrec, pstart, mtag);
     pmn_scan<uint32_t, OpAddU32, false>(pstart, ppos, nm, S.scan_tmp.as<uint32_t>(), st);
     launches += 4;
     uint32_t *tail = (uint32_t *)S.pinned;
@@ -747,8 +901,10 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     int32_t *pfirst = S.ex_d.as<int32_t>();
     k_ex_pieces<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(pstart, ppos, nm, mA, mrec, mtag, S.k0.as<uint64_t>(), S.v0.as<uint32_t>(), pfirst);
     launches++;
-    int qb = 1; while ((1 << qb) < nqry) qb++;
-    int where = small_or_radix_sort(S, np, 47 + qb, st, &launches);
+    // only the key bits in use are sorted: reference start, then the record fields if there are several records
+    int nbits = 1; { int64_t mx = 1; for (int i = 0; i < nref; i++) mx = std::max(mx, ref->len[(size_t)i]); while ((1ll << nbits) <= mx) nbits++; }
+    if (nref > 1 || nqry > 1) { int qb = 1; while ((1 << qb) < nqry) qb++; nbits = 47 + qb; }
+    int where = pmn_radix_sort(S.k0.as<uint64_t>(), S.v0.as<uint32_t>(), S.k1.as<uint64_t>(), S.v1.as<uint32_t>(), np, nbits, S.rs, st, &launches);
     if (where < 0) return -3;
     const uint64_t *skeys = where ? S.k1.as<uint64_t>() : S.k0.as<uint64_t>();
     const uint32_t *svals = where ? S.v1.as<uint32_t>() : S.v0.as<uint32_t>();
@@ -774,12 +930,14 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     const size_t pool_cap = (size_t)std::max<int64_t>(1 << 20, 8 * nm + (ref->n + q->n) / 8);
     const size_t arena_cap = (size_t)1 << 31;
     const size_t ncap_al = (size_t)nm, ncap_nodes = 3 * (size_t)nm + 8 * (size_t)nS;
+    const size_t l_bytes = ((size_t)np + 63) / 64 * 64 * 2 + 4 * (size_t)nS + 64;      // fused, anyfail, syn_nal
     if (S.ex_i.ensure(sizeof(ExJob) * (size_t)nm) || S.ex_j.ensure(sizeof(ExAlign) * ncap_al) || S.ex_k.ensure(sizeof(ExNode) * ncap_nodes) ||
         S.ex_pool.ensure(4 * pool_cap) || S.ex_arena.ensure(arena_cap) || S.ex_scores.ensure(4 * (size_t)EX_ROWS * EX_WCAP * (size_t)nslots) ||
-        S.ex_tb.ensure((size_t)EX_TBW * (size_t)nslots) || S.ex_counters.ensure(128) || S.ex_l.ensure((size_t)np + 4 * (size_t)nS + 64)) return -3;
+        S.ex_tb.ensure((size_t)EX_TBW * (size_t)nslots) || S.ex_counters.ensure(128) || S.ex_l.ensure(l_bytes) ||
+        S.ex_tbidx.ensure(8 * 3 * (size_t)(nm + 1))) return -3;
     PMN_CUDA_OK(cudaMemsetAsync(S.ex_i.p, 0, sizeof(ExJob) * (size_t)nm, st));
     PMN_CUDA_OK(cudaMemsetAsync(S.ex_counters.p, 0, 128, st));
-    PMN_CUDA_OK(cudaMemsetAsync(S.ex_l.p, 0, (size_t)np + 4 * (size_t)nS + 64, st));
+    PMN_CUDA_OK(cudaMemsetAsync(S.ex_l.p, 0, l_bytes, st));
     ExShared X;
     X.R = ref->fwd(); X.QF = q->fwd(); X.QR = q->rev();
     X.mA = mA; X.mB = mB; X.mL = mL; X.cl = cl; X.syn = syn; X.nC = (int)np; X.nS = nS; X.nM = nm;
@@ -790,7 +948,14 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     X.counters = S.ex_counters.as<unsigned long long>();
     X.breaklen = o->breaklen; X.do_extend = o->do_extend; X.do_simplify = o->do_simplify;
     uint8_t *fused = S.ex_l.as<uint8_t>();
-    X.syn_nal = (int32_t *)(fused + ((np + 63) / 64) * 64);
+    uint8_t *anyfail = fused + ((size_t)np + 63) / 64 * 64;
+    X.syn_nal = (int32_t *)(anyfail + ((size_t)np + 63) / 64 * 64);
+    long long *pkey = S.ex_tbidx.as<long long>();                          // nm+1
+    unsigned long long *markkey = (unsigned long long *)(pkey + (nm + 1));  // nm+1
+    uint32_t *dcnt = (uint32_t *)(markkey + (nm + 1));                      // nm+1, then dcnt_ex nm+1
+    uint32_t *dcnt_ex = dcnt + (nm + 1);
+    X.dcnt_ex = dcnt_ex; X.lastP = pkey; X.anyfail = anyfail; X.markkey = markkey;
+    PMN_CUDA_OK(cudaMemsetAsync(markkey, 0, 8 * (size_t)(nm + 1), st));
 
     const size_t smem = (size_t)EX_WARPS_PER_BLOCK * EX_ROWS * EX_RW * 4;
     static bool attr_set = false;
@@ -804,14 +969,19 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     k_ex_wave1<<<b1, EX_WARPS_PER_BLOCK * 32, smem, st>>>(X);
     PMN_CUDA_OK(cudaEventRecord(c->ev[9], st));
     PMN_D2H(c, (unsigned long long *)S.pinned + 24, X.counters + 2, 8);      // cells evaluated by wave 1
+    k_ex_jobmeta<<<(unsigned)((nm + 1 + 255) / 256), 256, 0, st>>>(X.jobs, mcl, cl, pstart, ppos, nm, dcnt, pkey, anyfail);
+    pmn_scan<uint32_t, OpAddU32, false>(dcnt, dcnt_ex, nm + 1, S.scan_tmp.as<uint32_t>(), st);
+    pmn_scan<long long, OpMaxI64x, true>(pkey, pkey, nm, S.scan_tmp.as<long long>(), st);
     k_ex_stitch<<<blocks_st, EX_WARPS_PER_BLOCK * 32, smem, st>>>(X, fused);
     PMN_CUDA_OK(cudaEventRecord(c->ev[10], st));
-    launches += 2;
+    launches += 9;
 
     // ---- E4
-    if (S.ex_c.ensure(4 * 4 * (size_t)nm + 64)) return -3;     // al_syn, al_slot, dcount, dstart
-    int32_t *al_syn = S.ex_c.as<int32_t>(); uint32_t *al_slot = (uint32_t *)al_syn + nm, *dcount = al_slot + nm, *dstart = dcount + nm;
-    k_ex_list<<<1, 32, 0, st>>>(syn, X.syn_nal, nS, X.al, al_syn, al_slot, dcount, X.counters + 8);
+    if (S.ex_c.ensure(4 * 5 * (size_t)(nm + 1) + 64)) return -3;     // al_syn, al_slot, dcount, dstart, slot2out  (pstart/ppos are dead now)
+    int32_t *al_syn = S.ex_c.as<int32_t>(); uint32_t *al_slot = (uint32_t *)al_syn + (nm + 1), *dcount = al_slot + (nm + 1), *dstart = dcount + (nm + 1);
+    int32_t *slot2out = (int32_t *)(dstart + (nm + 1));
+    PMN_CUDA_OK(cudaMemsetAsync(slot2out, 0xff, 4 * (size_t)(nm + 1), st));
+    k_ex_list<<<1, 32, 0, st>>>(syn, X.syn_nal, nS, X.al, al_syn, al_slot, dcount, slot2out, X.counters + 8);
     launches++;
     unsigned long long *hc = (unsigned long long *)S.pinned;
     PMN_D2H(c, hc, X.counters, 128);
@@ -828,14 +998,28 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     if (errflags & EX_ERR_LOGIC) return pmn_set_error(PMN_E_INTERNAL, "extend: inconsistent cluster chain (target match does not exist)");
     const int64_t nal = (int64_t)hc[8], nd = (int64_t)hc[9];
     if (nal > 0) {
-        if (S.ex_d.ensure(4 * (size_t)(nd + 1)) || S.ex_g.ensure(80 * (size_t)nal)) return -3;
-        pmn_scan<uint32_t, OpAddU32, false>(dcount, dstart, nal, S.scan_tmp.as<uint32_t>(), st);
-        k_ex_finish<<<(unsigned)((nal + 3) / 4), 128, 0, st>>>(X, al_syn, al_slot, nal, dstart, S.ex_d.as<int32_t>(), S.ex_g.as<long long>());
-        launches += 4;
+        if (S.ex_d.ensure(4 * 5 * (size_t)(nd + 1) + 64) || S.ex_g.ensure(88 * (size_t)nal + 64) || S.scan_tmp.ensure(8 * pmn_scan_scratch_elems(std::max(nd + 1, nm + 1)))) return -3;
+        int32_t *dflat = S.ex_d.as<int32_t>(); uint32_t *fa = (uint32_t *)dflat + (nd + 1), *fb = fa + (nd + 1), *sa_ = fb + (nd + 1), *sb_ = sa_ + (nd + 1);
+        long long *rows = S.ex_g.as<long long>(); unsigned long long *errs = (unsigned long long *)(rows + 10 * nal);
+        PMN_CUDA_OK(cudaMemsetAsync(errs, 0, 8 * (size_t)nal, st));
+        pmn_scan<uint32_t, OpAddU32, false>(dcount, dstart, nal + 1, S.scan_tmp.as<uint32_t>(), st);
+        launches += 3;
+        if (nd > 0) {
+            pmn_scan<unsigned long long, OpMaxU64, true>(markkey, markkey, nm, S.scan_tmp.as<unsigned long long>(), st);
+            k_ex_flat_nodes<<<(unsigned)((nal + 3) / 4), 128, 0, st>>>(X, al_syn, al_slot, nal, dstart, dflat);
+            k_ex_flat_ranges<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(X, markkey, slot2out, dstart, dflat);
+            launches += 5;
+        }
+        k_ex_consumed<<<(unsigned)((nd + 1 + 255) / 256), 256, 0, st>>>(dflat, nd, fa, fb);
+        pmn_scan<uint32_t, OpAddU32, false>(fa, sa_, nd + 1, S.scan_tmp.as<uint32_t>(), st);
+        pmn_scan<uint32_t, OpAddU32, false>(fb, sb_, nd + 1, S.scan_tmp.as<uint32_t>(), st);
+        k_ex_errors<<<(unsigned)((nd + nal + 255) / 256), 256, 0, st>>>(X, al_syn, al_slot, nal, dstart, dflat, nd, sa_, sb_, errs);
+        k_ex_rows<<<(unsigned)((nal + 255) / 256), 256, 0, st>>>(X, al_syn, al_slot, nal, errs, rows);
+        launches += 9;
         res->al_rows.resize((size_t)nal * 10);
         std::vector<int32_t> d32((size_t)nd), dc((size_t)nal);
-        PMN_D2H(c, res->al_rows.data(), S.ex_g.p, 80 * (size_t)nal);
-        if (nd) PMN_D2H(c, d32.data(), S.ex_d.p, 4 * (size_t)nd);
+        PMN_D2H(c, res->al_rows.data(), rows, 80 * (size_t)nal);
+        if (nd) PMN_D2H(c, d32.data(), dflat, 4 * (size_t)nd);
         PMN_D2H(c, dc.data(), dcount, 4 * (size_t)nal);
         PMN_CUDA_OK(cudaStreamSynchronize(st));
         res->al_deltas.assign(d32.begin(), d32.end());
