@@ -67,6 +67,7 @@ typedef struct pmn_stats {
     float   ms_wave1, ms_stitch; /* k_ex_wave1 / k_ex_stitch alone                     */
     int64_t kernel_launches;     /* kernels launched for this pair                     */
     int64_t wave1_cells;         /* DP cells evaluated inside k_ex_wave1               */
+    float   wall_ms_index, wall_ms_align, wall_ms_text;   /* host wall clock: index build, pmn_align, .delta formatting */
 } pmn_stats;
 
 void pmn_default_opts(pmn_opts *o);

@@ -3,6 +3,7 @@
 // /root/reference/lib/nucmer/mugsy_nucmer.ml:96-100 (see INTEGRATION.md for the OCaml stub).
 #include <algorithm>
 #include <cerrno>
+#include <chrono>
 #include <cstdarg>
 #include <cstring>
 #include <map>
@@ -77,6 +78,31 @@ extern "C" int pmn_ctx_create(int device, pmn_ctx **out)
     return 0;
 }
 
+int pmn_pool_get(pmn_ctx *c, DevBuf &b, size_t bytes)
+{
+    if (b.cap >= bytes) return 0;
+    if (b.p) pmn_pool_put(c, b);
+    int best = -1;
+    for (size_t i = 0; i < c->pool.size(); i++)
+        if (c->pool[i].cap >= bytes && (best < 0 || c->pool[i].cap < c->pool[(size_t)best].cap)) best = (int)i;
+    if (best >= 0 && c->pool[(size_t)best].cap <= 2 * bytes + (1u << 20)) {
+        b = c->pool[(size_t)best];
+        c->pool.erase(c->pool.begin() + best);
+        return 0;
+    }
+    return b.ensure(bytes);
+}
+
+void pmn_pool_put(pmn_ctx *c, DevBuf &b)
+{
+    if (!b.p) return;
+    if (c->pool.size() >= 64) { b.release(); return; }
+    c->pool.push_back(b);
+    b.p = nullptr; b.cap = 0;
+}
+
+static inline double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 extern "C" void *pmn_ctx_stream(const pmn_ctx *c) { return c ? (void *)c->stream : nullptr; }
 
 extern "C" void pmn_ctx_counters(const pmn_ctx *c, int64_t out[4])
@@ -132,6 +158,7 @@ extern "C" void pmn_ctx_destroy(pmn_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     pmn_scratch_free(c->scratch);
+    for (auto &b : c->pool) b.release();
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -142,41 +169,30 @@ extern "C" void pmn_ctx_destroy(pmn_ctx *c)
 // Like `mummer -n`: only a/c/g/t (either case) can match, everything else becomes code X.
 // Record ids = first token of the header (what the '>' line of a .delta carries; the
 // reference rewrites headers to species.accession, lib/base/m_rewrite_fasta.ml:5-59).
-static int parse_fasta_host(const char *txt, size_t nb, pmn_seq *s, std::vector<uint8_t> &codes)
+// The host only finds the header lines; bases are translated and packed on the device.
+static int find_headers(const char *txt, size_t nb, pmn_seq *s, std::vector<int64_t> &hp)
 {
-    static uint8_t lut[256]; static bool init = false;
-    if (!init) {
-        memset(lut, PMN_CODE_X, sizeof lut);
-        lut['a'] = lut['A'] = PMN_CODE_A; lut['c'] = lut['C'] = PMN_CODE_C; lut['g'] = lut['G'] = PMN_CODE_G; lut['t'] = lut['T'] = PMN_CODE_T;
-        lut[' '] = lut['\t'] = lut['\r'] = lut['\n'] = lut['\v'] = lut['\f'] = 0xff;
-        init = true;
-    }
-    codes.clear(); codes.reserve(nb + 16);
-    size_t i = 0; int cur = -1; bool any_x = false;
-    while (i < nb) {
-        const char *nl = (const char *)memchr(txt + i, '\n', nb - i);
-        size_t e = nl ? (size_t)(nl - txt) : nb;
-        if (e > i && txt[i] == '>') {
-            size_t a = i + 1; while (a < e && (txt[a] == ' ' || txt[a] == '\t')) a++;
-            size_t b = a; while (b < e && lut[(unsigned char)txt[b]] != 0xff) b++;
-            if (cur >= 0) codes.push_back(PMN_CODE_X);
-            cur = s->nrec++;
+    hp.clear();
+    // anything but white space before the first header is an error
+    size_t i = 0;
+    while (i < nb && (txt[i] == ' ' || txt[i] == '\t' || txt[i] == '\r' || txt[i] == '\n' || txt[i] == '\v' || txt[i] == '\f')) i++;
+    if (i == nb) return pmn_set_error(PMN_E_ARG, "FASTA: no records");
+    if (txt[i] != '>' || (i > 0 && txt[i - 1] != '\n')) return pmn_set_error(PMN_E_ARG, "FASTA: sequence data before the first '>' header");
+    const char *p = txt + i;
+    while (p) {
+        size_t at = (size_t)(p - txt);
+        if (at == 0 || txt[at - 1] == '\n') {
+            size_t e = at + 1; while (e < nb && txt[e] != '\n') e++;
+            size_t a = at + 1; while (a < e && (txt[a] == ' ' || txt[a] == '\t')) a++;
+            size_t b = a; while (b < e && !(txt[b] == ' ' || txt[b] == '\t' || txt[b] == '\r' || txt[b] == '\v' || txt[b] == '\f')) b++;
+            hp.push_back((int64_t)at);
             s->ids.emplace_back(txt + a, b - a);
-            s->off.push_back((int64_t)codes.size()); s->len.push_back(0);
-        } else if (cur >= 0) {
-            size_t before = codes.size();
-            for (size_t k = i; k < e; k++) { uint8_t c = lut[(unsigned char)txt[k]]; if (c != 0xff) { codes.push_back(c); any_x |= c == PMN_CODE_X; } }
-            s->len[cur] += (int64_t)(codes.size() - before);
-        } else {
-            for (size_t k = i; k < e; k++) if (lut[(unsigned char)txt[k]] != 0xff) return pmn_set_error(PMN_E_ARG, "FASTA: sequence data before the first '>' header");
-        }
-        i = e + 1;
+            at = e;
+        } else at++;
+        p = at < nb ? (const char *)memchr(txt + at, '>', nb - at) : nullptr;
     }
-    if (s->nrec == 0) return pmn_set_error(PMN_E_ARG, "FASTA: no records");
+    s->nrec = (int)hp.size();
     if (s->nrec > 32767) return pmn_set_error(PMN_E_ARG, "FASTA: more than 32767 records");
-    s->n = (int64_t)codes.size();
-    if (s->n > 0x7ffffff0ll) return pmn_set_error(PMN_E_ARG, "FASTA: more than 2^31 bases");
-    s->has_x = (any_x || s->nrec > 1) ? 1 : 0;
     return 0;
 }
 
@@ -187,12 +203,11 @@ extern "C" int pmn_seq_from_fasta(pmn_ctx *c, const char *fasta, size_t bytes, p
     PMN_CUDA_OK(cudaSetDevice(c->device));
     std::unique_ptr<pmn_seq> s(new pmn_seq());
     s->ctx = c;
-    std::vector<uint8_t> codes;
-    int rc = parse_fasta_host(fasta, bytes, s.get(), codes);
+    std::vector<int64_t> hp;
+    int rc = find_headers(fasta, bytes, s.get(), hp);
     if (rc) return rc;
-    codes.resize(codes.size() + 64, PMN_CODE_X);
-    rc = pmn_pack_upload(c, s.get(), codes.data());
-    if (rc) return rc;
+    rc = pmn_fasta_to_device(c, s.get(), fasta, bytes, hp);
+    if (rc) { s->w_fwd.release(); s->xm_fwd.release(); s->w_rev.release(); s->xm_rev.release(); return rc; }
     *out = s.release();
     return 0;
 }
@@ -222,7 +237,7 @@ extern "C" void pmn_seq_free(pmn_seq *s)
 {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
-    s->w_fwd.release(); s->xm_fwd.release(); s->w_rev.release(); s->xm_rev.release();
+    pmn_pool_put(s->ctx, s->w_fwd); pmn_pool_put(s->ctx, s->xm_fwd); pmn_pool_put(s->ctx, s->w_rev); pmn_pool_put(s->ctx, s->xm_rev);
     delete s;
 }
 extern "C" int64_t pmn_seq_bases(const pmn_seq *s) { return s ? s->n : 0; }
@@ -236,7 +251,9 @@ extern "C" int pmn_index_build(pmn_ctx *c, const pmn_seq *ref, pmn_index **out)
     *out = nullptr;
     PMN_CUDA_OK(cudaSetDevice(c->device));
     std::unique_ptr<pmn_index> ix(new pmn_index());
+    const double t0 = now_ms();
     int rc = pmn_index_build_impl(c, ref, ix.get());
+    ix->wall_ms_build = (float)(now_ms() - t0);
     if (rc) { ix->sa.release(); ix->lcp.release(); ix->table.release(); return rc; }
     *out = ix.release();
     return 0;
@@ -246,7 +263,7 @@ extern "C" void pmn_index_free(pmn_index *ix)
 {
     if (!ix) return;
     cudaSetDevice(ix->ctx->device);
-    ix->sa.release(); ix->lcp.release(); ix->table.release();
+    pmn_pool_put(ix->ctx, ix->sa); pmn_pool_put(ix->ctx, ix->lcp); pmn_pool_put(ix->ctx, ix->table);
     delete ix;
 }
 
@@ -266,30 +283,46 @@ extern "C" int pmn_index_copy_sa(const pmn_index *ix, int32_t *sa_out, int32_t *
 // .delta grammar exactly as the reference parses it: lib/profiles_lib/m_delta.cc:72-92 (two
 // header lines), :154-162 ('>' line), :177-185 (seven ints), :187-196 (deltas up to "0");
 // lib/profiles/m_delta.ml:76-79,91 needs single spaces and no trailing blanks.
+static inline char *fmt_int(char *p, long long v)
+{
+    if (v < 0) { *p++ = '-'; v = -v; }
+    char tmp[24]; int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+
 static void write_delta_text(const pmn_seq *ref, const pmn_seq *qry, const char *ref_path, const char *qry_path, pmn_result *r)
 {
     std::string &t = r->delta;
-    t.clear();
-    t += ref_path; t += ' '; t += qry_path; t += "\nNUCMER\n";
-    char buf[256];
-    size_t na = r->al_rows.size() / 10; int64_t prev_r = -1, prev_q = -1;
-    int64_t aligned = 0;
+    const size_t na = r->al_rows.size() / 10;
+    size_t idlen = 0;
+    for (auto &x : ref->ids) idlen = std::max(idlen, x.size());
+    for (auto &x : qry->ids) idlen = std::max(idlen, x.size());
+    const size_t head = strlen(ref_path) + strlen(qry_path) + 16;
+    t.resize(head + na * (2 * idlen + 64 + 7 * 21 + 4) + r->al_deltas.size() * 12 + 16);
+    char *p = &t[0];
+    p += sprintf(p, "%s %s\nNUCMER\n", ref_path, qry_path);
+    int64_t prev_r = -1, prev_q = -1, aligned = 0;
     for (size_t k = 0; k < na; k++) {
         const int64_t *a = &r->al_rows[k * 10];
         if (a[0] != prev_r || a[1] != prev_q) {
-            t += '>'; t += ref->ids[(size_t)a[0]]; t += ' '; t += qry->ids[(size_t)a[1]];
-            snprintf(buf, sizeof buf, " %lld %lld\n", (long long)ref->len[(size_t)a[0]], (long long)qry->len[(size_t)a[1]]); t += buf;
+            *p++ = '>';
+            const std::string &ri = ref->ids[(size_t)a[0]], &qi = qry->ids[(size_t)a[1]];
+            memcpy(p, ri.data(), ri.size()); p += ri.size(); *p++ = ' ';
+            memcpy(p, qi.data(), qi.size()); p += qi.size(); *p++ = ' ';
+            p = fmt_int(p, ref->len[(size_t)a[0]]); *p++ = ' '; p = fmt_int(p, qry->len[(size_t)a[1]]); *p++ = '\n';
             prev_r = a[0]; prev_q = a[1];
         }
-        int64_t sB = a[5], eB = a[6], lenB = qry->len[(size_t)a[1]];
+        int64_t sB = a[5], eB = a[6]; const int64_t lenB = qry->len[(size_t)a[1]];
         if (a[2]) { sB = lenB - sB + 1; eB = lenB - eB + 1; }
-        snprintf(buf, sizeof buf, "%lld %lld %lld %lld %lld %lld %lld\n", (long long)a[3], (long long)a[4], (long long)sB, (long long)eB,
-                 (long long)a[7], (long long)a[8], (long long)a[9]);
-        t += buf;
-        for (int64_t d = r->al_doff[k]; d < r->al_doff[k + 1]; d++) { snprintf(buf, sizeof buf, "%lld\n", (long long)r->al_deltas[(size_t)d]); t += buf; }
-        t += "0\n";
+        p = fmt_int(p, a[3]); *p++ = ' '; p = fmt_int(p, a[4]); *p++ = ' '; p = fmt_int(p, sB); *p++ = ' '; p = fmt_int(p, eB); *p++ = ' ';
+        p = fmt_int(p, a[7]); *p++ = ' '; p = fmt_int(p, a[8]); *p++ = ' '; p = fmt_int(p, a[9]); *p++ = '\n';
+        for (int64_t d = r->al_doff[k]; d < r->al_doff[k + 1]; d++) { p = fmt_int(p, r->al_deltas[(size_t)d]); *p++ = '\n'; }
+        *p++ = '0'; *p++ = '\n';
         aligned += a[4] - a[3] + 1;
     }
+    t.resize((size_t)(p - &t[0]));
     r->stats.alignments = (int64_t)na;
     r->stats.aligned_ref_bases = aligned;
 }
@@ -307,6 +340,7 @@ extern "C" int pmn_align(pmn_ctx *c, const pmn_index *ix, const pmn_seq *qry, co
     Scratch &S = *c->scratch;
     cudaStream_t st = c->stream;
     std::unique_ptr<pmn_result> r(new pmn_result());
+    const double t0 = now_ms();
     long launches0 = c->launches;
     r->stats.ref_bases = ix->n; r->stats.qry_bases = qry->n;
     r->stats.sa_rounds = ix->rounds; r->stats.kmer_bits = 2 * ix->K; r->stats.ms_index = ix->ms_build;
@@ -335,8 +369,12 @@ extern "C" int pmn_align(pmn_ctx *c, const pmn_index *ix, const pmn_seq *qry, co
     cudaEventElapsedTime(&r->stats.ms_total, c->ev[2], c->ev[5]);
     if (nanc >= 0 && qry->n >= o.minmatch) { if (cudaEventElapsedTime(&r->stats.ms_seed_kernel, c->ev[6], c->ev[7]) != cudaSuccess) { cudaGetLastError(); r->stats.ms_seed_kernel = 0; } }
     c->pairs++;
+    const double t1 = now_ms();
     write_delta_text(ix->seq, qry, ref_path ? ref_path : "ref", qry_path ? qry_path : "qry", r.get());
     r->stats.kernel_launches = c->launches - launches0;
+    r->stats.wall_ms_text = (float)(now_ms() - t1);
+    r->stats.wall_ms_align = (float)(now_ms() - t0);
+    r->stats.wall_ms_index = ix->wall_ms_build;
     *out = r.release();
     return 0;
 }
@@ -368,7 +406,7 @@ extern "C" int pmn_result_copy_alignments(const pmn_result *r, int64_t *rows, in
     if (!r) return pmn_set_error(PMN_E_ARG, "NULL argument");
     if (rows) memcpy(rows, r->al_rows.data(), r->al_rows.size() * 8);
     if (doff) memcpy(doff, r->al_doff.data(), r->al_doff.size() * 8);
-    if (deltas) memcpy(deltas, r->al_deltas.data(), r->al_deltas.size() * 8);
+    if (deltas) for (size_t k = 0; k < r->al_deltas.size(); k++) deltas[k] = r->al_deltas[k];
     return 0;
 }
 

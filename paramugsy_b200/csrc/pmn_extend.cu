@@ -52,6 +52,15 @@ struct ExAlign { int32_t dirB, sA, sB, eA, eB, P, head, tail, ndelta, live, pad0
 // type 1 = the deltas of the wave-1 jobs [a, cnt) (all reached their targets), `b` = P before the range
 struct ExNode { int32_t type; uint32_t a; int32_t cnt, b, outoff, next, alslot, pad; };
 
+// everything the stitcher needs to know about a cluster in one 80-byte record
+struct ExCSum {
+    int32_t sA0, sB0, len0;            // first match
+    int32_t sAl, sBl, eAl, eBl;        // last match: start and end
+    int32_t mfirst, nm, dir, anyfail;
+    int32_t endA, endB, e_reached, e_dcnt, e_asum, target; uint32_t e_doff;    // the cluster-end job of wave 1
+    int32_t bulk_cnt, bulk_P;          // deltas / last P of the inner jobs [mfirst, last) taken together
+};
+
 struct ExShared {                       // everything the device code needs, passed by value
     PackedView R, QF, QR;
     const int32_t *mA, *mB, *mL;        // matches (local reference coordinate)
@@ -64,7 +73,8 @@ struct ExShared {                       // everything the device code needs, pas
     int32_t *gscore; uint8_t *tbpriv;   // per warp slot: EX_ROWS*EX_WCAP ints, EX_TBW bytes
     unsigned long long *counters;       // [0] pool cursor [1] arena cursor [2] cells [3] engine calls [4] error flags [5] job cursor A [6] job cursor B
     int breaklen, do_extend, do_simplify;
-    int32_t *syn_nal;                   // alignments produced per synteny
+    int32_t *syn_nal;                   // alignments produced per synteny (then: nodes used per synteny at [nS + s])
+    const struct ExCSum *cs;            // per cluster summary for the stitcher
     const uint32_t *dcnt_ex;            // exclusive prefix of jobs[].dcnt, nM + 1 entries
     const long long *lastP;             // per job g: (piece << 32 | j+1), j = latest job <= g of the same cluster that has deltas
     const uint8_t *anyfail;             // per cluster: some match -> next match job did not reach its target
@@ -365,8 +375,8 @@ __global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32) k_ex_wave1(ExShared X
 // per job: delta count (for the prefix that places range deltas), the key of the lastP scan,
 // and the per-cluster "some inner job failed" flag
 __global__ void __launch_bounds__(256) k_ex_jobmeta(const ExJob *__restrict__ jobs, const int32_t *__restrict__ mcl, const ExCluster *__restrict__ cl,
-                                                   const uint32_t *__restrict__ pstart, const uint32_t *__restrict__ ppos, int64_t nm, uint32_t *__restrict__ dcnt, long long *__restrict__ pkey,
-                                                   uint8_t *__restrict__ anyfail)
+                                                   const uint32_t *__restrict__ pstart, const uint32_t *__restrict__ ppos, int64_t nm,
+                                                   uint32_t *__restrict__ dcnt, long long *__restrict__ pkey, uint8_t *__restrict__ anyfail)
 {
     int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g > nm) return;
@@ -382,58 +392,6 @@ __global__ void __launch_bounds__(256) k_ex_jobmeta(const ExJob *__restrict__ jo
     if (inner && j.valid && !j.reached) anyfail[k] = 1;
 }
 
-// ------------------------------------------------------------------------------------ E3: stitch
-
-struct Stitch {
-    const Eng *E; const ExSynteny *S; ExAlign *al; ExNode *nodes; int nAl, nNodes; bool fail;
-};
-
-__device__ int new_node(Stitch &T, int ap)
-{
-    if (T.nNodes >= T.S->nodecap) { T.fail = true; return -1; }
-    return T.nNodes++;
-}
-
-// explicit segment: `dcnt` pool entries at doff, first value shifted by `adjust`
-__device__ void al_append(Stitch &T, int ap, uint32_t doff, int dcnt, int adjust)
-{
-    if (dcnt <= 0) return;
-    const int nd = new_node(T, ap);
-    if (nd < 0) return;
-    if (T.E->lane == 0) {
-        ExAlign &a = T.al[ap];
-        ExNode n; n.type = 0; n.a = doff; n.cnt = dcnt; n.b = adjust; n.outoff = a.ndelta; n.next = -1; n.alslot = T.S->alfirst + ap; n.pad = 0;
-        T.nodes[nd] = n;
-        if (a.head < 0) a.head = nd; else T.nodes[a.tail].next = nd;
-        a.tail = nd; a.ndelta += dcnt;
-    }
-    __syncwarp();
-}
-
-// extendForward.  `g` >= 0 names the wave-1 job that computed exactly this extension.
-__device__ int st_extend_forward(Stitch &T, int ap, int dirB, int64_t targetA, int64_t targetB, unsigned m_o, int g)
-{
-    const ExShared &X = *T.E->X;
-    ExAlign a = T.al[ap];
-    ExJob r;
-    bool have = false;
-    if (g >= 0) {
-        r = X.jobs[g];
-        have = r.valid && a.eA == X.mA[g] + X.mL[g] - 1 && a.eB == X.mB[g] + X.mL[g] - 1;
-    }
-    if (!have) forward_job(*T.E, *T.S, dirB, a.eA, a.eB, targetA, targetB, m_o, r);
-    if (r.dcnt > 0) {
-        // the first new delta counts from the engine's start column: add the bases the alignment
-        // already holds since its last indel; afterwards P = (start - 1) + asum
-        al_append(T, ap, r.doff, r.dcnt, a.eA - a.P - 1);
-        a.P = a.eA - 1 + r.asum;
-    }
-    a.eA = r.endA; a.eB = r.endB;
-    if (T.E->lane == 0) { ExAlign &w = T.al[ap]; w.eA = a.eA; w.eB = a.eB; w.P = a.P; }
-    __syncwarp();
-    return r.reached;
-}
-
 // P (reference position consumed through the last indel) left behind by the latest job in
 // [g0, g] that has deltas; `fallback` when there is none
 __device__ __forceinline__ int range_last_P(const ExShared &X, int g0, int g, int fallback)
@@ -443,26 +401,72 @@ __device__ __forceinline__ int range_last_P(const ExShared &X, int g0, int g, in
     return X.mA[j] + X.mL[j] - 2 + X.jobs[j].asum;
 }
 
-// All jobs [g0, ge) of one cluster reached their targets: absorb matches g0+1 .. ge at once.
-__device__ void st_bulk_forward(Stitch &T, int ap, int dirB, int g0, int ge)
+__global__ void __launch_bounds__(256) k_ex_csum(ExShared X, ExCSum *__restrict__ out)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= X.nC) return;
+    const ExCluster c = X.cl[k];
+    const int f = c.mfirst, l = c.mfirst + c.nm - 1;
+    ExCSum s;
+    s.sA0 = X.mA[f]; s.sB0 = X.mB[f]; s.len0 = X.mL[f];
+    s.sAl = X.mA[l]; s.sBl = X.mB[l]; s.eAl = X.mA[l] + X.mL[l] - 1; s.eBl = X.mB[l] + X.mL[l] - 1;
+    s.mfirst = f; s.nm = c.nm; s.dir = c.dir; s.anyfail = X.anyfail[k];
+    const ExJob j = X.jobs[l];
+    s.endA = j.endA; s.endB = j.endB; s.e_reached = j.reached; s.e_dcnt = j.valid ? j.dcnt : -1; s.e_asum = j.asum; s.target = j.target; s.e_doff = j.doff;
+    s.bulk_cnt = (int32_t)(X.dcnt_ex[l] - X.dcnt_ex[f]);
+    s.bulk_P = c.nm > 1 ? range_last_P(X, f, l - 1, -1) : -1;
+    out[k] = s;
+}
+
+// ------------------------------------------------------------------------------------ E3: stitch
+
+struct Stitch {
+    const Eng *E; const ExSynteny *S; ExAlign *al; ExNode *nodes; int nAl, nNodes; bool fail;
+    ExAlign cur; int cur_slot;          // the alignment being grown lives in registers (identical on all lanes)
+};
+
+__device__ __forceinline__ void st_flush(Stitch &T)
+{
+    if (T.cur_slot >= 0 && T.E->lane == 0) T.al[T.cur_slot] = T.cur;
+    __syncwarp();
+}
+__device__ __forceinline__ void st_load(Stitch &T, int slot) { T.cur = T.al[slot]; T.cur_slot = slot; }
+
+// append a node to the alignment held in registers
+__device__ void cur_append(Stitch &T, int type, uint32_t a, int cnt_field, int b, int ndeltas)
+{
+    if (T.nNodes >= T.S->nodecap) { T.fail = true; return; }
+    const int nd = T.nNodes++;
+    if (T.E->lane == 0) {
+        ExNode n; n.type = type; n.a = a; n.cnt = cnt_field; n.b = b; n.outoff = T.cur.ndelta; n.next = -1; n.alslot = T.S->alfirst + T.cur_slot; n.pad = 0;
+        T.nodes[nd] = n;
+        if (T.cur.head >= 0) T.nodes[T.cur.tail].next = nd;
+    }
+    if (T.cur.head < 0) T.cur.head = nd;
+    T.cur.tail = nd; T.cur.ndelta += ndeltas;
+}
+
+// extendForward on the alignment in registers from a known result `r`
+__device__ __forceinline__ int cur_apply_job(Stitch &T, uint32_t doff, int dcnt, int asum, int endA, int endB, int reached)
+{
+    if (dcnt > 0) {
+        // the first new delta counts from the engine's start column: add the bases the alignment
+        // already holds since its last indel; afterwards P = (start - 1) + asum
+        cur_append(T, 0, doff, dcnt, T.cur.eA - T.cur.P - 1, dcnt);
+        T.cur.P = T.cur.eA - 1 + asum;
+    }
+    T.cur.eA = endA; T.cur.eB = endB;
+    return reached;
+}
+
+// extendForward, general: uses wave-1 job g when it computed exactly this extension, else runs the engine
+__device__ int cur_extend_forward(Stitch &T, int dirB, int64_t targetA, int64_t targetB, unsigned m_o, int g)
 {
     const ExShared &X = *T.E->X;
-    const int cnt = (int)(X.dcnt_ex[ge] - X.dcnt_ex[g0]);
-    if (cnt > 0) {
-        const int nd = new_node(T, ap);
-        if (nd < 0) return;
-        if (T.E->lane == 0) {
-            ExAlign &a = T.al[ap];
-            ExNode n; n.type = 1; n.a = (uint32_t)g0; n.cnt = ge; n.b = a.P; n.outoff = a.ndelta; n.next = -1; n.alslot = T.S->alfirst + ap; n.pad = 0;
-            T.nodes[nd] = n;
-            if (a.head < 0) a.head = nd; else T.nodes[a.tail].next = nd;
-            a.tail = nd; a.ndelta += cnt;
-            a.P = range_last_P(X, g0, ge - 1, a.P);
-            X.markkey[g0] = ((unsigned long long)(g0 + 1) << 32) | (unsigned)(T.S->nodefirst + nd + 1);
-        }
-    }
-    if (T.E->lane == 0) { ExAlign &a = T.al[ap]; a.eA = X.mA[ge] + X.mL[ge] - 1; a.eB = X.mB[ge] + X.mL[ge] - 1; }
-    __syncwarp();
+    ExJob r; bool have = false;
+    if (g >= 0) { r = X.jobs[g]; have = r.valid && T.cur.eA == X.mA[g] + X.mL[g] - 1 && T.cur.eB == X.mB[g] + X.mL[g] - 1; }
+    if (!have) forward_job(*T.E, *T.S, dirB, T.cur.eA, T.cur.eB, targetA, targetB, m_o, r);
+    return cur_apply_job(T, r.doff, r.dcnt, r.asum, r.endA, r.endB, r.reached);
 }
 
 // first job in [g, last) that did not reach its target, or `last`
@@ -476,67 +480,79 @@ __device__ int st_next_fail(const ExShared &X, int g, int last, int lane)
     return last;
 }
 
-__device__ int st_get_reverse_target(const Stitch &T, int ap)
+// getReverseTargetAlignment, 32 candidates per step.  The sequential original walks i = ap-1 .. 0,
+// stops at the first "close enough" alignment and otherwise keeps the first strict improvement
+// of dist = 2*greater - lesser.
+__device__ int st_get_reverse_target(const Stitch &T, int ap, int dirB, int64_t sA, int64_t sB)
 {
     const ExShared &X = *T.E->X;
-    const ExAlign c = T.al[ap];
-    const int64_t sA = c.sA, sB = c.sB;
-    int64_t dist = sA < sB ? sA : sB;
+    const int lane = T.E->lane;
+    long long dist = sA < sB ? sA : sB;
     int best = -1;
-    for (int i = ap - 1; i >= 0; i--) {
-        const ExAlign a = T.al[i];
-        if (a.dirB != c.dirB) continue;
-        const int64_t eA = a.eA, eB = a.eB;
-        if (eA <= sA && eB <= sB) {
-            int64_t greater, lesser;
-            if (sA - eA > sB - eB) { greater = sA - eA; lesser = sB - eB; } else { lesser = sA - eA; greater = sB - eB; }
-            if (greater < X.breaklen || lesser * PMN_GOOD_SCORE + (greater - lesser) * PMN_CONT_GAP_SCORE >= 0) { best = i; break; }
-            else if ((greater << 1) - lesser < dist) { best = i; dist = (greater << 1) - lesser; }
+    for (int top = ap - 1; top >= 0; top -= 32) {
+        const int i = top - lane;
+        bool valid = false, close = false; long long score = 0;
+        if (i >= 0) {
+            const ExAlign a = T.al[i];
+            if (a.dirB == dirB && a.eA <= sA && a.eB <= sB) {
+                valid = true;
+                long long greater, lesser;
+                if (sA - a.eA > sB - a.eB) { greater = sA - a.eA; lesser = sB - a.eB; } else { lesser = sA - a.eA; greater = sB - a.eB; }
+                close = greater < X.breaklen || lesser * PMN_GOOD_SCORE + (greater - lesser) * PMN_CONT_GAP_SCORE >= 0;
+                score = (greater << 1) - lesser;
+            }
         }
+        const unsigned cb = __ballot_sync(0xffffffffu, close);
+        const int F = cb ? __ffs(cb) - 1 : 32;
+        long long key = (valid && !close && lane < F) ? score * 32 + lane : LLONG_MAX;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { long long k2 = __shfl_xor_sync(0xffffffffu, key, o); if (k2 < key) key = k2; }
+        if (key != LLONG_MAX) { const long long sc = key >> 5; if (sc < dist) { dist = sc; best = top - (int)(key & 31); } }
+        if (cb) return top - F;
     }
     return best;
 }
 
-// extendBackward; may drop the last alignment (merged into tp)
-__device__ int st_extend_backward(Stitch &T, int ap, int tp, int dirB)
+__device__ bool st_is_shadowed(const Stitch &T, const ExCSum &c)
+{
+    const int lane = T.E->lane;
+    for (int top = T.nAl - 1; top >= 0; top -= 32) {
+        const int i = top - lane;
+        bool hit = false;
+        if (i >= 0) { const ExAlign a = T.al[i]; hit = a.dirB == c.dir && a.eA >= c.eAl && a.eB >= c.eBl && a.sA <= c.sA0 && a.sB <= c.sB0; }
+        if (__ballot_sync(0xffffffffu, hit)) return true;
+    }
+    return false;
+}
+
+// extendBackward for the freshly created alignment in registers; returns true when it was merged
+// into alignment tp (which then becomes the current one)
+__device__ int st_extend_backward(Stitch &T, int tp, int dirB)
 {
     const ExShared &X = *T.E->X;
     const ExSynteny &S = *T.S;
-    ExAlign a = T.al[ap];
+    const ExAlign a = T.cur;
     int overflow = 0; unsigned m_o = PMN_BACKWARD_SEARCH;
     int64_t targetA, targetB;
-    if (tp >= 0) { targetA = T.al[tp].eA; targetB = T.al[tp].eB; } else { targetA = 1; targetB = 1; m_o |= PMN_OPTIMAL_BIT; }
+    if (tp >= 0) { const ExAlign t = T.al[tp]; targetA = t.eA; targetB = t.eB; } else { targetA = 1; targetB = 1; m_o |= PMN_OPTIMAL_BIT; }
     if (a.sA - targetA + 1 > PMN_MAX_ALIGNMENT_LENGTH) { targetA = a.sA - PMN_MAX_ALIGNMENT_LENGTH + 1; overflow = 1; m_o |= PMN_OPTIMAL_BIT; }
     if (a.sB - targetB + 1 > PMN_MAX_ALIGNMENT_LENGTH) { targetB = a.sB - PMN_MAX_ALIGNMENT_LENGTH + 1; overflow = 1; m_o |= PMN_OPTIMAL_BIT; }
     const PackedView &Q = dirB ? X.QR : X.QF; const int64_t Bbase = dirB ? S.BbaseR : S.BbaseF;
     int reached = align_engine(*T.E, S.Abase, a.sA, targetA, Q, Bbase, a.sB, targetB, m_o, nullptr, nullptr, nullptr);
     if (overflow || tp < 0) reached = 0;
     if (reached) {
-        st_extend_forward(T, tp, dirB, a.sA, a.sB, PMN_FORCED_FORWARD_ALIGN, -1);
-        if (T.E->lane == 0) { ExAlign &t = T.al[tp]; t.eA += a.eA - a.sA; t.eB += a.eB - a.sB; }
-        T.nAl--;
-        __syncwarp();
+        // merge: the target alignment is extended (forced) up to this one's start and absorbs it
+        T.nAl--;                        // the new alignment was the last one; it held no deltas yet
+        st_load(T, tp);
+        cur_extend_forward(T, dirB, a.sA, a.sB, PMN_FORCED_FORWARD_ALIGN, -1);
+        T.cur.eA += a.eA - a.sA; T.cur.eB += a.eB - a.sB;
     } else {
         int64_t eA = a.sA, eB = a.sB; uint32_t doff; int32_t dcnt, dasum;
         align_engine(*T.E, S.Abase, targetA, eA, Q, Bbase, targetB, eB, PMN_FORCED_FORWARD_ALIGN, &doff, &dcnt, &dasum);
-        al_append(T, ap, doff, dcnt, 0);
-        if (T.E->lane == 0) { ExAlign &w = T.al[ap]; w.sA = (int32_t)targetA; w.sB = (int32_t)targetB; w.P = (int32_t)targetA - 1 + dasum; }
-        __syncwarp();
+        if (dcnt > 0) cur_append(T, 0, doff, dcnt, 0, dcnt);
+        T.cur.sA = (int32_t)targetA; T.cur.sB = (int32_t)targetB; T.cur.P = (int32_t)targetA - 1 + dasum;
     }
     return reached;
-}
-
-__device__ bool st_is_shadowed(const Stitch &T, int cp)
-{
-    const ExShared &X = *T.E->X;
-    const ExCluster c = X.cl[cp];
-    const int l = c.mfirst + c.nm - 1;
-    const int64_t sA = X.mA[c.mfirst], eA = (int64_t)X.mA[l] + X.mL[l] - 1, sB = X.mB[c.mfirst], eB = (int64_t)X.mB[l] + X.mL[l] - 1;
-    for (int i = T.nAl - 1; i >= 0; i--) {
-        const ExAlign a = T.al[i];
-        if (a.dirB == c.dir && a.eA >= eA && a.eB >= eB && a.sA <= sA && a.sB <= sB) return true;
-    }
-    return false;
 }
 
 // extendClusters for one synteny; every lane runs the same control flow on the same values
@@ -548,67 +564,85 @@ __global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32) k_ex_stitch(ExShared 
     const int s = blockIdx.x * EX_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     if (s >= X.nS) return;
     const ExSynteny S = X.syn[s];
-    Stitch T; T.E = &E; T.S = &S; T.al = X.al + S.alfirst; T.nodes = X.nodes + S.nodefirst; T.nAl = 0; T.nNodes = 0; T.fail = false;
+    Stitch T; T.E = &E; T.S = &S; T.al = X.al + S.alfirst; T.nodes = X.nodes + S.nodefirst; T.nAl = 0; T.nNodes = 0; T.fail = false; T.cur_slot = -1;
     const int c0 = S.cfirst, cend = S.cfirst + S.nC;
-    int target_reached = 0, CurrCp = c0, PrevCp = c0, TargetCp = cend, CurrAp = -1;
+    int target_reached = 0, CurrCp = c0, PrevCp = c0, TargetCp = cend;
     bool logic_err = false;
     while (CurrCp < cend && !T.fail && !logic_err) {
-        const ExCluster c = X.cl[CurrCp];
-        if (X.do_extend && !target_reached && fused[CurrCp]) { CurrCp++; continue; }
-        if (!target_reached && X.do_simplify && st_is_shadowed(T, CurrCp)) {
-            if (lane == 0) fused[CurrCp] = 1;
-            __syncwarp();
-            CurrCp = ++PrevCp; continue;
+        const ExCSum c = X.cs[CurrCp];
+        const int was_fused = fused[CurrCp];
+        if (X.do_extend && !target_reached && was_fused) { CurrCp++; continue; }
+        if (!target_reached && X.do_simplify) {
+            st_flush(T);
+            if (st_is_shadowed(T, c)) {
+                if (lane == 0) fused[CurrCp] = 1;
+                __syncwarp();
+                CurrCp = ++PrevCp; continue;
+            }
         }
         const int last = c.mfirst + c.nm - 1;
-        // a cluster that is being merged a second time (reached as a target after it was fused) goes
-        // job by job, so that every wave-1 job belongs to at most one range node
-        const bool allow_bulk = !fused[CurrCp];
-        int CurrMp = 0; bool positioned = false;       // positioned: CurrAp already ends on the last base of match CurrMp
+        // a cluster that is merged a second time (reached as a target after it was fused) goes job by
+        // job, so that every wave-1 job belongs to at most one range node
+        const bool allow_bulk = !was_fused;
+        int CurrMp = 0; bool positioned = false;       // positioned: the alignment already ends on the last base of match CurrMp
         while (CurrMp < c.nm && !T.fail) {
             const int g = c.mfirst + CurrMp;
+            int gA, gB, gL;                            // match g
+            if (CurrMp == 0) { gA = c.sA0; gB = c.sB0; gL = c.len0; } else { gA = X.mA[g]; gB = X.mB[g]; gL = X.mL[g]; }
             if (!positioned) {
                 if (target_reached) {
-                    const ExAlign a = T.al[CurrAp];
-                    if (a.eA != X.mA[g] || a.eB != X.mB[g]) {
+                    if (T.cur.eA != gA || T.cur.eB != gB) {
                         if (CurrMp >= c.nm - 1) { logic_err = true; break; }
                         CurrMp++; continue;
                     }
-                    if (lane == 0) { ExAlign &w = T.al[CurrAp]; w.eA += X.mL[g] - 1; w.eB += X.mL[g] - 1; }
-                    __syncwarp();
+                    T.cur.eA += gL - 1; T.cur.eB += gL - 1;
                 } else {
                     if (T.nAl >= S.alcap) { logic_err = true; break; }
-                    CurrAp = T.nAl++;
-                    if (lane == 0) {
-                        ExAlign a; a.dirB = c.dir; a.sA = X.mA[g]; a.sB = X.mB[g]; a.eA = X.mA[g] + X.mL[g] - 1; a.eB = X.mB[g] + X.mL[g] - 1;
-                        a.P = a.sA - 1; a.head = -1; a.tail = -1; a.ndelta = 0; a.live = 1; a.pad0 = a.pad1 = 0;
-                        T.al[CurrAp] = a;
-                    }
-                    __syncwarp();
+                    st_flush(T);
+                    T.cur_slot = T.nAl++;
+                    T.cur.dirB = c.dir; T.cur.sA = gA; T.cur.sB = gB; T.cur.eA = gA + gL - 1; T.cur.eB = gB + gL - 1;
+                    T.cur.P = gA - 1; T.cur.head = -1; T.cur.tail = -1; T.cur.ndelta = 0; T.cur.live = 1; T.cur.pad0 = T.cur.pad1 = 0;
                     if (X.do_extend || CurrMp != 0) {
-                        const int TargetAp = st_get_reverse_target(T, CurrAp);
-                        if (st_extend_backward(T, CurrAp, TargetAp, c.dir)) CurrAp = TargetAp;
+                        const int TargetAp = st_get_reverse_target(T, T.cur_slot, c.dir, gA, gB);
+                        st_extend_backward(T, TargetAp, c.dir);
                     }
                 }
             }
             positioned = false;
-            unsigned m_o = PMN_FORWARD_ALIGN;
             if (CurrMp < c.nm - 1) {
-                const ExAlign a = T.al[CurrAp];
-                if (allow_bulk && a.eA == X.mA[g] + X.mL[g] - 1 && a.eB == X.mB[g] + X.mL[g] - 1) {
-                    const int f = X.anyfail[CurrCp] ? st_next_fail(X, g, last, lane) : last;
+                if (allow_bulk && T.cur.eA == gA + gL - 1 && T.cur.eB == gB + gL - 1) {
+                    int f, cnt, Pn;
+                    if (CurrMp == 0 && !c.anyfail) { f = last; cnt = c.bulk_cnt; Pn = c.bulk_P; }
+                    else {
+                        f = c.anyfail ? st_next_fail(X, g, last, lane) : last;
+                        cnt = f > g ? (int)(X.dcnt_ex[f] - X.dcnt_ex[g]) : 0;
+                        Pn = f > g ? range_last_P(X, g, f - 1, -1) : -1;
+                    }
                     if (f > g) {
-                        st_bulk_forward(T, CurrAp, c.dir, g, f);
+                        // all jobs [g, f) reached their targets: absorb matches g+1 .. f at once
+                        if (cnt > 0) {
+                            const int nd_before = T.nNodes;
+                            cur_append(T, 1, (uint32_t)g, f, T.cur.P, cnt);
+                            if (lane == 0 && !T.fail) X.markkey[g] = ((unsigned long long)(g + 1) << 32) | (unsigned)(S.nodefirst + nd_before + 1);
+                            if (Pn >= 0) T.cur.P = Pn;
+                        }
+                        if (f == last) { T.cur.eA = c.eAl; T.cur.eB = c.eBl; }
+                        else { T.cur.eA = X.mA[f] + X.mL[f] - 1; T.cur.eB = X.mB[f] + X.mL[f] - 1; }
                         CurrMp = f - c.mfirst; positioned = true; target_reached = 1;
                         continue;
                     }
                 }
-                target_reached = st_extend_forward(T, CurrAp, c.dir, X.mA[g + 1], X.mB[g + 1], m_o, g);
+                target_reached = cur_extend_forward(T, c.dir, X.mA[g + 1], X.mB[g + 1], PMN_FORWARD_ALIGN, g);
             } else if (X.do_extend) {
-                int64_t targetA = S.lenA, targetB = S.lenB;
-                TargetCp = get_forward_target_cluster(X, CurrCp, cend, targetA, targetB);
-                if (TargetCp == cend) m_o |= PMN_OPTIMAL_BIT;
-                target_reached = st_extend_forward(T, CurrAp, c.dir, targetA, targetB, m_o, g);
+                if (c.e_dcnt >= 0 && T.cur.eA == c.eAl && T.cur.eB == c.eBl) {
+                    TargetCp = c.target;
+                    target_reached = cur_apply_job(T, c.e_doff, c.e_dcnt, c.e_asum, c.endA, c.endB, c.e_reached);
+                } else {
+                    int64_t targetA = S.lenA, targetB = S.lenB; unsigned m_o = PMN_FORWARD_ALIGN;
+                    TargetCp = get_forward_target_cluster(X, CurrCp, cend, targetA, targetB);
+                    if (TargetCp == cend) m_o |= PMN_OPTIMAL_BIT;
+                    target_reached = cur_extend_forward(T, c.dir, targetA, targetB, m_o, -1);
+                }
             }
             CurrMp++;
         }
@@ -617,8 +651,9 @@ __global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32) k_ex_stitch(ExShared 
         __syncwarp();
         if (!target_reached) CurrCp = ++PrevCp; else CurrCp = TargetCp;
     }
+    st_flush(T);
     if (lane == 0) {
-        X.syn_nal[s] = T.nAl;
+        X.syn_nal[s] = T.nAl; X.syn_nal[X.nS + s] = T.nNodes;
         if (T.fail) atomicOr(X.counters + 4, (unsigned long long)EX_ERR_NODES);
         if (logic_err) atomicOr(X.counters + 4, (unsigned long long)EX_ERR_LOGIC);
     }
@@ -626,26 +661,30 @@ __global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32) k_ex_stitch(ExShared 
 
 // ------------------------------------------------------------------------------------ E1 helpers
 
-// reference record of every match, local coordinate, piece starts
-__global__ void __launch_bounds__(256) k_ex_match_rec(const int32_t *__restrict__ m3, const int4 *__restrict__ recs, int64_t nc, const int64_t *__restrict__ roff,
-                                                     int nref, int32_t *__restrict__ mA, int32_t *__restrict__ mB,
-                                                     int32_t *__restrict__ mL, int32_t *__restrict__ mrec, uint32_t *__restrict__ pstart, int32_t *__restrict__ mtag)
+__device__ __forceinline__ int ref_record_of(const int64_t *__restrict__ roff, int nref, int64_t sA)
 {
-    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= nc) return;
-    const int4 r = recs[k];
-    int prev = -1;
-    for (int g = r.x; g < r.x + r.y; g++) {
-        int64_t sA = m3[g * 3];
-        int lo = 0, hi = nref - 1;
-        while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (roff[mid] + 1 <= sA) lo = mid; else hi = mid - 1; }
-        mA[g] = (int32_t)(sA - roff[lo]); mB[g] = m3[g * 3 + 1]; mL[g] = m3[g * 3 + 2]; mrec[g] = lo; mtag[g] = r.z;
-        pstart[g] = lo != prev ? 1u : 0u;
-        prev = lo;
-    }
+    int lo = 0, hi = nref - 1;
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (roff[mid] + 1 <= sA) lo = mid; else hi = mid - 1; }
+    return lo;
 }
 
-// piece p (= cluster of postnuc): key for the sort and its first match
+// per match: reference record, local coordinate, tag, "starts a piece" (= cluster of postnuc:
+// an mgaps cluster, split where consecutive matches lie in different reference records)
+__global__ void __launch_bounds__(256) k_ex_match_rec(const int32_t *__restrict__ m3, const int4 *__restrict__ recs, int64_t nc, int64_t nm,
+                                                     const int64_t *__restrict__ roff, int nref, int32_t *__restrict__ mA, int32_t *__restrict__ mB,
+                                                     int32_t *__restrict__ mL, int32_t *__restrict__ mrec, uint32_t *__restrict__ pstart, int32_t *__restrict__ mtag)
+{
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nm) return;
+    int64_t lo = 0, hi = nc - 1;        // the mgaps cluster holding match g
+    while (lo < hi) { int64_t mid = (lo + hi + 1) >> 1; if (recs[mid].x <= g) lo = mid; else hi = mid - 1; }
+    const int4 r = recs[lo];
+    const int64_t sA = m3[g * 3];
+    const int rec = ref_record_of(roff, nref, sA);
+    mA[g] = (int32_t)(sA - roff[rec]); mB[g] = m3[g * 3 + 1]; mL[g] = m3[g * 3 + 2]; mrec[g] = rec; mtag[g] = r.z;
+    pstart[g] = (g == r.x || ref_record_of(roff, nref, m3[(g - 1) * 3]) != rec) ? 1u : 0u;
+}
+
 __global__ void __launch_bounds__(256) k_ex_pieces(const uint32_t *__restrict__ pstart, const uint32_t *__restrict__ ppos, int64_t nm, const int32_t *__restrict__ mA,
                                                   const int32_t *__restrict__ mrec, const int32_t *__restrict__ mtag, uint64_t *__restrict__ keys,
                                                   uint32_t *__restrict__ vals, int32_t *__restrict__ pfirst)
@@ -657,21 +696,26 @@ __global__ void __launch_bounds__(256) k_ex_pieces(const uint32_t *__restrict__ 
     vals[p] = p; pfirst[p] = (int32_t)g;
 }
 
-// sorted pieces -> ExCluster records, per-match cluster index
+// sorted pieces -> ExCluster records and the inverse permutation
 __global__ void __launch_bounds__(256) k_ex_clusters(const uint64_t *__restrict__ skeys, const uint32_t *__restrict__ svals, int64_t np, int64_t nm,
-                                                    const int32_t *__restrict__ pfirst, const uint32_t *__restrict__ pstart, const int32_t *__restrict__ mtag,
-                                                    ExCluster *__restrict__ cl, int32_t *__restrict__ mcl, uint32_t *__restrict__ sflag)
+                                                    const int32_t *__restrict__ pfirst, const int32_t *__restrict__ mtag,
+                                                    ExCluster *__restrict__ cl, int32_t *__restrict__ inv, uint32_t *__restrict__ sflag)
 {
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= np) return;
     const uint32_t p = svals[k];
     const int first = pfirst[p];
-    int g = first + 1;
-    while (g < nm && !pstart[g]) g++;
-    ExCluster c; c.mfirst = first; c.nm = g - first; c.dir = mtag[first] & 1; c.syn = 0; c.order = (int32_t)p; c.pad = 0;
+    const int end = p + 1 < np ? pfirst[p + 1] : (int)nm;
+    ExCluster c; c.mfirst = first; c.nm = end - first; c.dir = mtag[first] & 1; c.syn = 0; c.order = (int32_t)p; c.pad = 0;
     cl[k] = c;
-    for (int t = first; t < g; t++) mcl[t] = (int32_t)k;
+    inv[p] = (int32_t)k;
     sflag[k] = (k == 0 || (skeys[k] >> 32) != (skeys[k - 1] >> 32)) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256) k_ex_mcl(const uint32_t *__restrict__ pstart, const uint32_t *__restrict__ ppos, const int32_t *__restrict__ inv, int64_t nm, int32_t *__restrict__ mcl)
+{
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < nm) mcl[g] = inv[ppos[g] + pstart[g] - 1];
 }
 
 __global__ void __launch_bounds__(256) k_ex_syntenies(const uint64_t *__restrict__ skeys, const uint32_t *__restrict__ sflag, const uint32_t *__restrict__ spos, int64_t np,
@@ -693,7 +737,8 @@ __global__ void __launch_bounds__(256) k_ex_syntenies(const uint64_t *__restrict
     }
 }
 
-// capacities per synteny from its clusters' match counts (one thread: nS is small, the prefix sequential)
+// capacities per synteny: its clusters are contiguous in the sorted order and so are the prefix
+// sums of their match counts (one thread: nS is small)
 __global__ void k_ex_syn_caps(ExSynteny *__restrict__ syn, int nS, const ExCluster *__restrict__ cl)
 {
     if (blockIdx.x || threadIdx.x) return;
@@ -725,25 +770,24 @@ __global__ void k_ex_list(const ExSynteny *__restrict__ syn, const int32_t *__re
     totals[0] = n; totals[1] = nd;
 }
 
-// explicit nodes: one warp per alignment walks its list
-__global__ void __launch_bounds__(128) k_ex_flat_nodes(ExShared X, const int32_t *__restrict__ al_syn, const uint32_t *__restrict__ al_slot, int64_t nal,
-                                                      const uint32_t *__restrict__ dstart, int32_t *__restrict__ dout)
+// explicit nodes: one thread per node slot (every node knows its alignment and its offset)
+__global__ void __launch_bounds__(256) k_ex_flat_nodes(ExShared X, int64_t ncap, const int32_t *__restrict__ slot2out, const uint32_t *__restrict__ dstart,
+                                                      int32_t *__restrict__ dout)
 {
-    const int lane = threadIdx.x & 31;
-    const int64_t k = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (k >= nal) return;
-    const ExSynteny S = X.syn[al_syn[k]];
-    const ExAlign a = X.al[al_slot[k]];
-    const ExNode *nodes = X.nodes + S.nodefirst;
-    for (int nd = a.head; nd >= 0; nd = nodes[nd].next) {
-        const ExNode n = nodes[nd];
-        if (n.type != 0) continue;
-        int32_t *out = dout + dstart[k] + n.outoff;
-        for (int t = lane; t < n.cnt; t += 32) {
-            int d = X.pool[n.a + t];
-            if (t == 0) d += d > 0 ? n.b : -n.b;
-            out[t] = d;
-        }
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ncap) return;
+    int lo = 0, hi = X.nS - 1;
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (X.syn[mid].nodefirst <= t) lo = mid; else hi = mid - 1; }
+    if (t - X.syn[lo].nodefirst >= X.syn_nal[X.nS + lo]) return;
+    const ExNode n = X.nodes[t];
+    if (n.type != 0) return;
+    const int k = slot2out[n.alslot];
+    if (k < 0) return;
+    int32_t *out = dout + dstart[k] + n.outoff;
+    for (int i = 0; i < n.cnt; i++) {
+        int d = X.pool[n.a + i];
+        if (i == 0) d += d > 0 ? n.b : -n.b;
+        out[i] = d;
     }
 }
 
@@ -885,7 +929,8 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     const int64_t *roff = S.ex_a.as<int64_t>(), *rlen = roff + nref, *qoff = roff + 2 * nref, *qlen = qoff + nqry;
     int32_t *mA = S.ex_b.as<int32_t>(), *mB = mA + nm, *mL = mA + 2 * nm, *mrec = mA + 3 * nm, *mtag = mA + 4 * nm;
     uint32_t *pstart = S.ex_c.as<uint32_t>(), *ppos = pstart + nm;
-    k_ex_match_rec<<<(unsigned)((nc0 + 255) / 256), 256, 0, st>>>(S.cl_matches.as<int32_t>(), S.cl_recs.as<int4>(), nc0, roff, nref, mA, mB, mL, mrec, pstart, mtag);
+    const unsigned gm = (unsigned)((nm + 255) / 256);
+    k_ex_match_rec<<<gm, 256, 0, st>>>(S.cl_matches.as<int32_t>(), S.cl_recs.as<int4>(), nc0, nm, roff, nref, mA, mB, mL, mrec, pstart, mtag);
     pmn_scan<uint32_t, OpAddU32, false>(pstart, ppos, nm, S.scan_tmp.as<uint32_t>(), st);
     launches += 4;
     uint32_t *tail = (uint32_t *)S.pinned;
@@ -896,10 +941,10 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
 
     // pieces sorted by (query record, reference record, first reference start), stable
     if (S.k0.ensure(8 * (size_t)np) || S.k1.ensure(8 * (size_t)np) || S.v0.ensure(4 * (size_t)np) || S.v1.ensure(4 * (size_t)np) ||
-        S.ex_d.ensure(4 * (size_t)np) || S.ex_e.ensure(sizeof(ExCluster) * (size_t)np) || S.ex_f.ensure(4 * (size_t)nm) ||
+        S.ex_d.ensure(4 * 2 * (size_t)np) || S.ex_e.ensure(sizeof(ExCluster) * (size_t)np) || S.ex_f.ensure(4 * (size_t)nm) ||
         S.ex_g.ensure(4 * 2 * (size_t)np) || S.ex_h.ensure(sizeof(ExSynteny) * (size_t)np)) return -3;
-    int32_t *pfirst = S.ex_d.as<int32_t>();
-    k_ex_pieces<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(pstart, ppos, nm, mA, mrec, mtag, S.k0.as<uint64_t>(), S.v0.as<uint32_t>(), pfirst);
+    int32_t *pfirst = S.ex_d.as<int32_t>(), *inv = pfirst + np;
+    k_ex_pieces<<<gm, 256, 0, st>>>(pstart, ppos, nm, mA, mrec, mtag, S.k0.as<uint64_t>(), S.v0.as<uint32_t>(), pfirst);
     launches++;
     // only the key bits in use are sorted: reference start, then the record fields if there are several records
     int nbits = 1; { int64_t mx = 1; for (int i = 0; i < nref; i++) mx = std::max(mx, ref->len[(size_t)i]); while ((1ll << nbits) <= mx) nbits++; }
@@ -912,10 +957,11 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     uint32_t *sflag = S.ex_g.as<uint32_t>(), *spos = sflag + np;
     ExSynteny *syn = S.ex_h.as<ExSynteny>();
     const unsigned gp = (unsigned)((np + 255) / 256);
-    k_ex_clusters<<<gp, 256, 0, st>>>(skeys, svals, np, nm, pfirst, pstart, mtag, cl, mcl, sflag);
+    k_ex_clusters<<<gp, 256, 0, st>>>(skeys, svals, np, nm, pfirst, mtag, cl, inv, sflag);
+    k_ex_mcl<<<gm, 256, 0, st>>>(pstart, ppos, inv, nm, mcl);
     pmn_scan<uint32_t, OpAddU32, false>(sflag, spos, np, S.scan_tmp.as<uint32_t>(), st);
     k_ex_syntenies<<<gp, 256, 0, st>>>(skeys, sflag, spos, np, cl, syn, roff, rlen, qoff, qlen, q->n);
-    launches += 5;
+    launches += 6;
     PMN_D2H(c, tail, spos + (np - 1), 4);
     PMN_D2H(c, tail + 1, sflag + (np - 1), 4);
     PMN_CUDA_OK(cudaStreamSynchronize(st));
@@ -930,11 +976,12 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     const size_t pool_cap = (size_t)std::max<int64_t>(1 << 20, 8 * nm + (ref->n + q->n) / 8);
     const size_t arena_cap = (size_t)1 << 31;
     const size_t ncap_al = (size_t)nm, ncap_nodes = 3 * (size_t)nm + 8 * (size_t)nS;
-    const size_t l_bytes = ((size_t)np + 63) / 64 * 64 * 2 + 4 * (size_t)nS + 64;      // fused, anyfail, syn_nal
+    const size_t npad = ((size_t)np + 63) / 64 * 64;
+    const size_t l_bytes = npad * 2 + 8 * (size_t)nS + 64;      // fused, anyfail, syn_nal (2 x nS)
     if (S.ex_i.ensure(sizeof(ExJob) * (size_t)nm) || S.ex_j.ensure(sizeof(ExAlign) * ncap_al) || S.ex_k.ensure(sizeof(ExNode) * ncap_nodes) ||
         S.ex_pool.ensure(4 * pool_cap) || S.ex_arena.ensure(arena_cap) || S.ex_scores.ensure(4 * (size_t)EX_ROWS * EX_WCAP * (size_t)nslots) ||
         S.ex_tb.ensure((size_t)EX_TBW * (size_t)nslots) || S.ex_counters.ensure(128) || S.ex_l.ensure(l_bytes) ||
-        S.ex_tbidx.ensure(8 * 3 * (size_t)(nm + 1))) return -3;
+        S.ex_tbidx.ensure(8 * 3 * (size_t)(nm + 1)) || S.ex_a.ensure(8 * h.size() + 0) || S.cl_l.ensure(sizeof(ExCSum) * (size_t)np)) return -3;
     PMN_CUDA_OK(cudaMemsetAsync(S.ex_i.p, 0, sizeof(ExJob) * (size_t)nm, st));
     PMN_CUDA_OK(cudaMemsetAsync(S.ex_counters.p, 0, 128, st));
     PMN_CUDA_OK(cudaMemsetAsync(S.ex_l.p, 0, l_bytes, st));
@@ -948,13 +995,15 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     X.counters = S.ex_counters.as<unsigned long long>();
     X.breaklen = o->breaklen; X.do_extend = o->do_extend; X.do_simplify = o->do_simplify;
     uint8_t *fused = S.ex_l.as<uint8_t>();
-    uint8_t *anyfail = fused + ((size_t)np + 63) / 64 * 64;
-    X.syn_nal = (int32_t *)(anyfail + ((size_t)np + 63) / 64 * 64);
+    uint8_t *anyfail = fused + npad;
+    X.syn_nal = (int32_t *)(anyfail + npad);
     long long *pkey = S.ex_tbidx.as<long long>();                          // nm+1
     unsigned long long *markkey = (unsigned long long *)(pkey + (nm + 1));  // nm+1
     uint32_t *dcnt = (uint32_t *)(markkey + (nm + 1));                      // nm+1, then dcnt_ex nm+1
     uint32_t *dcnt_ex = dcnt + (nm + 1);
     X.dcnt_ex = dcnt_ex; X.lastP = pkey; X.anyfail = anyfail; X.markkey = markkey;
+    ExCSum *cs = S.cl_l.as<ExCSum>();      // the clustering scratch is free by now
+    X.cs = cs;
     PMN_CUDA_OK(cudaMemsetAsync(markkey, 0, 8 * (size_t)(nm + 1), st));
 
     const size_t smem = (size_t)EX_WARPS_PER_BLOCK * EX_ROWS * EX_RW * 4;
@@ -972,9 +1021,10 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     k_ex_jobmeta<<<(unsigned)((nm + 1 + 255) / 256), 256, 0, st>>>(X.jobs, mcl, cl, pstart, ppos, nm, dcnt, pkey, anyfail);
     pmn_scan<uint32_t, OpAddU32, false>(dcnt, dcnt_ex, nm + 1, S.scan_tmp.as<uint32_t>(), st);
     pmn_scan<long long, OpMaxI64x, true>(pkey, pkey, nm, S.scan_tmp.as<long long>(), st);
+    k_ex_csum<<<gp, 256, 0, st>>>(X, cs);
     k_ex_stitch<<<blocks_st, EX_WARPS_PER_BLOCK * 32, smem, st>>>(X, fused);
     PMN_CUDA_OK(cudaEventRecord(c->ev[10], st));
-    launches += 9;
+    launches += 10;
 
     // ---- E4
     if (S.ex_c.ensure(4 * 5 * (size_t)(nm + 1) + 64)) return -3;     // al_syn, al_slot, dcount, dstart, slot2out  (pstart/ppos are dead now)
@@ -1006,8 +1056,8 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
         launches += 3;
         if (nd > 0) {
             pmn_scan<unsigned long long, OpMaxU64, true>(markkey, markkey, nm, S.scan_tmp.as<unsigned long long>(), st);
-            k_ex_flat_nodes<<<(unsigned)((nal + 3) / 4), 128, 0, st>>>(X, al_syn, al_slot, nal, dstart, dflat);
-            k_ex_flat_ranges<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(X, markkey, slot2out, dstart, dflat);
+            k_ex_flat_nodes<<<(unsigned)((ncap_nodes + 255) / 256), 256, 0, st>>>(X, (int64_t)ncap_nodes, slot2out, dstart, dflat);
+            k_ex_flat_ranges<<<gm, 256, 0, st>>>(X, markkey, slot2out, dstart, dflat);
             launches += 5;
         }
         k_ex_consumed<<<(unsigned)((nd + 1 + 255) / 256), 256, 0, st>>>(dflat, nd, fa, fb);
@@ -1017,14 +1067,13 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
         k_ex_rows<<<(unsigned)((nal + 255) / 256), 256, 0, st>>>(X, al_syn, al_slot, nal, errs, rows);
         launches += 9;
         res->al_rows.resize((size_t)nal * 10);
-        std::vector<int32_t> d32((size_t)nd), dc((size_t)nal);
+        res->al_deltas.resize((size_t)nd);
+        std::vector<uint32_t> ds((size_t)nal + 1);
         PMN_D2H(c, res->al_rows.data(), rows, 80 * (size_t)nal);
-        if (nd) PMN_D2H(c, d32.data(), dflat, 4 * (size_t)nd);
-        PMN_D2H(c, dc.data(), dcount, 4 * (size_t)nal);
+        if (nd) PMN_D2H(c, res->al_deltas.data(), dflat, 4 * (size_t)nd);
+        PMN_D2H(c, ds.data(), dstart, 4 * (size_t)(nal + 1));
         PMN_CUDA_OK(cudaStreamSynchronize(st));
-        res->al_deltas.assign(d32.begin(), d32.end());
-        res->al_doff.resize((size_t)nal + 1);
-        for (int64_t k = 0; k < nal; k++) res->al_doff[(size_t)k + 1] = res->al_doff[(size_t)k] + dc[(size_t)k];
+        res->al_doff.assign(ds.begin(), ds.end());
     }
     PMN_CUDA_OK(cudaGetLastError());
     c->launches += launches;

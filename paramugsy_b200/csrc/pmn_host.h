@@ -27,7 +27,7 @@ struct pmn_index {
     DevBuf sa, lcp, table;              // int32[n], int32[n], uint32[4^K + 1]
     int K = 0;
     int rounds = 0;                     // prefix-doubling rounds after the 16-mer pass
-    float ms_build = 0;
+    float ms_build = 0, wall_ms_build = 0;
 };
 
 struct StageTimes { float pack = 0, index = 0, seed = 0, cluster = 0, extend = 0, total = 0; };
@@ -38,7 +38,8 @@ struct pmn_result {
     // stage dumps kept for parity tests
     std::vector<int32_t> anchors;             // n x 4
     std::vector<int32_t> cl_matches, cl_off, cl_tag;
-    std::vector<int64_t> al_rows, al_doff, al_deltas;
+    std::vector<int64_t> al_rows, al_doff;      // 10 columns per alignment; delta offsets (a+1)
+    std::vector<int32_t> al_deltas;
 };
 
 // per-context scratch, all grow-only
@@ -53,14 +54,19 @@ struct pmn_ctx {
     Scratch *scratch = nullptr;
     long launches = 0;                  // kernels launched by this library (bench.py's gpu_launches)
     int64_t h2d_bytes = 0, d2h_bytes = 0, pairs = 0;
+    std::vector<DevBuf> pool;           // device buffers handed back by freed sequences / indexes, reused by the next ones
 };
 
 // host<->device copies on the context's stream, counted for bench.py's e2e byte figures
 #define PMN_H2D(c, dst, src, bytes) do { (c)->h2d_bytes += (int64_t)(bytes); PMN_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (c)->stream)); } while (0)
 #define PMN_D2H(c, dst, src, bytes) do { (c)->d2h_bytes += (int64_t)(bytes); PMN_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (c)->stream)); } while (0)
 
+// take a buffer of at least `bytes` from the context's pool (smallest that fits), else allocate
+int pmn_pool_get(pmn_ctx *c, DevBuf &b, size_t bytes);
+void pmn_pool_put(pmn_ctx *c, DevBuf &b);
+
 // stage entry points (defined in the .cu files)
-int pmn_pack_upload(pmn_ctx *c, pmn_seq *s, const uint8_t *codes_host);
+int pmn_fasta_to_device(pmn_ctx *c, pmn_seq *s, const char *txt, size_t nb, const std::vector<int64_t> &header_pos);
 int pmn_index_build_impl(pmn_ctx *c, const pmn_seq *ref, pmn_index *ix);
 int pmn_seed_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_opts *o, int64_t *n_anchors);
 int pmn_cluster_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_opts *o, int64_t n_anchors);

@@ -9,7 +9,11 @@
 //
 // Suffix order (same as the oracle): END < a < c < g < t < X_p, every X (non-acgt base or
 // record separator) being its own symbol ordered by text position.
+#include <vector>
+
 #include "pmn_scratch.cuh"
+
+struct OpMaxU32 { __device__ __forceinline__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; } static __device__ __forceinline__ uint32_t identity() { return 0u; } };
 
 // ------------------------------------------------------------------------------------ pack
 
@@ -59,21 +63,112 @@ __global__ void __launch_bounds__(256) k_revcomp(const uint64_t *__restrict__ fw
     rw[k] = ~r & ~spread; rx[k] = xr;
 }
 
-int pmn_pack_upload(pmn_ctx *c, pmn_seq *s, const uint8_t *codes_host)
+// ------------------------------------------------------------------------------------ FASTA on the device
+
+// v[i] = 2i+1 where a header starts ('>' first on its line), 2i at a newline, 0 elsewhere; the
+// inclusive max-scan tells every byte whether the latest such event was a header start, i.e.
+// whether it lies inside a header line
+__global__ void __launch_bounds__(256) k_fa_events(const uint8_t *__restrict__ txt, int64_t nb, uint32_t *__restrict__ ev)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nb) return;
+    const uint8_t ch = txt[i];
+    uint32_t v = 0;
+    if (ch == '\n') v = (uint32_t)(2 * i + 2);
+    else if (ch == '>' && (i == 0 || txt[i - 1] == '\n')) v = (uint32_t)(2 * i + 3);
+    ev[i] = v;
+}
+
+__device__ __forceinline__ uint32_t fa_code(uint8_t ch)      // 0..3 acgt, 4 other base, 255 white space
+{
+    switch (ch) {
+        case 'a': case 'A': return PMN_CODE_A;
+        case 'c': case 'C': return PMN_CODE_C;
+        case 'g': case 'G': return PMN_CODE_G;
+        case 't': case 'T': return PMN_CODE_T;
+        case ' ': case '\t': case '\r': case '\n': case '\v': case '\f': return 255u;
+        default: return PMN_CODE_X;
+    }
+}
+
+// keep[i] = byte i yields a code: a base outside header lines, or the '>' of every header but the
+// first (it becomes the one-base separator between records)
+__global__ void __launch_bounds__(256) k_fa_keep(const uint8_t *__restrict__ txt, const uint32_t *__restrict__ evmax, int64_t nb, int64_t first_header,
+                                                uint32_t *__restrict__ keep)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > nb) return;
+    if (i == nb) { keep[i] = 0; return; }
+    const uint32_t m = evmax[i];
+    uint32_t k;
+    if (m & 1u) k = ((int64_t)((m - 3) >> 1) == i && i != first_header) ? 1u : 0u;     // inside a header: only a later '>' itself
+    else k = (i > first_header && fa_code(txt[i]) != 255u) ? 1u : 0u;
+    keep[i] = k;
+}
+
+__global__ void __launch_bounds__(256) k_fa_emit(const uint8_t *__restrict__ txt, const uint32_t *__restrict__ keep, const uint32_t *__restrict__ pos, int64_t nb,
+                                                uint8_t *__restrict__ codes, uint32_t *__restrict__ any_x)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nb || !keep[i]) return;
+    const uint8_t ch = txt[i];
+    uint32_t cd = ch == '>' ? (uint32_t)PMN_CODE_X : fa_code(ch);
+    if (ch == '>') cd = PMN_CODE_X;       // a '>' is only kept as a record separator ('>' inside a sequence line is a plain non-acgt base)
+    codes[pos[i]] = (uint8_t)cd;
+    if (cd == PMN_CODE_X) *any_x = 1u;
+}
+
+__global__ void k_fa_gather(const uint32_t *__restrict__ pos, const int64_t *__restrict__ hp, int nrec, int64_t nb, uint32_t *__restrict__ out)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < nrec) out[r] = pos[hp[r]];
+    if (r == nrec) out[r] = pos[nb];
+}
+
+// FASTA bytes in host memory -> base codes in HBM -> packed text of both strands.  The host only
+// locates the header lines (for the record ids); everything per base happens on the device.
+int pmn_fasta_to_device(pmn_ctx *c, pmn_seq *s, const char *txt, size_t nb, const std::vector<int64_t> &header_pos)
 {
     Scratch &S = *c->scratch;
-    int64_t n = s->n;
+    cudaStream_t st = c->stream;
+    const int nrec = (int)header_pos.size();
+    if (nb >= 0x7ffffff0ull) return pmn_set_error(PMN_E_ARG, "FASTA: file larger than 2 GiB");
+    if (S.k0.ensure(nb + 64) || S.v0.ensure(4 * (nb + 1)) || S.v1.ensure(4 * (nb + 1)) || S.k1.ensure(4 * (nb + 1)) ||
+        S.codes.ensure(nb + 128) || S.scan_tmp.ensure(8 * pmn_scan_scratch_elems((int64_t)nb + 1)) || S.flags.ensure(16 * (size_t)(nrec + 8)) ||
+        S.ensure_pinned(8 * (size_t)(nrec + 2) + 64)) return -3;
+    uint8_t *dtxt = S.k0.as<uint8_t>(); uint32_t *ev = S.v0.as<uint32_t>(), *keep = S.v1.as<uint32_t>(), *pos = S.k1.as<uint32_t>();
+    int64_t *dhp = S.flags.as<int64_t>(); uint32_t *dout = (uint32_t *)(dhp + nrec + 1); uint32_t *anyx = dout + nrec + 2;
+    PMN_H2D(c, dtxt, txt, nb);
+    PMN_H2D(c, dhp, header_pos.data(), 8 * (size_t)nrec);
+    PMN_CUDA_OK(cudaMemsetAsync(anyx, 0, 4, st));
+    PMN_CUDA_OK(cudaMemsetAsync(S.codes.p, PMN_CODE_X, nb + 128, st));
+    const unsigned g = (unsigned)((nb + 1 + 255) / 256);
+    k_fa_events<<<g, 256, 0, st>>>(dtxt, (int64_t)nb, ev);
+    pmn_scan<uint32_t, OpMaxU32, true>(ev, ev, (int64_t)nb, S.scan_tmp.as<uint32_t>(), st);
+    k_fa_keep<<<g, 256, 0, st>>>(dtxt, ev, (int64_t)nb, header_pos[0], keep);
+    pmn_scan<uint32_t, OpAddU32, false>(keep, pos, (int64_t)nb + 1, S.scan_tmp.as<uint32_t>(), st);
+    k_fa_emit<<<g, 256, 0, st>>>(dtxt, keep, pos, (int64_t)nb, S.codes.as<uint8_t>(), anyx);
+    k_fa_gather<<<(nrec + 1 + 255) / 256, 256, 0, st>>>(pos, dhp, nrec, (int64_t)nb, dout);
+    c->launches += 10;
+    uint32_t *h = (uint32_t *)S.pinned;
+    PMN_D2H(c, h, dout, 4 * (size_t)(nrec + 3));
+    PMN_CUDA_OK(cudaStreamSynchronize(st));
+    const int64_t n = h[nrec];
+    s->n = n;
+    s->off.resize((size_t)nrec); s->len.resize((size_t)nrec);
+    for (int r = 0; r < nrec; r++) s->off[(size_t)r] = (int64_t)h[r] + (r > 0 ? 1 : 0);
+    for (int r = 0; r < nrec; r++) s->len[(size_t)r] = (r + 1 < nrec ? (int64_t)h[r + 1] : n) - s->off[(size_t)r];
+    s->has_x = (h[nrec + 2] || nrec > 1) ? 1 : 0;
+    if (n > 0x7ffffff0ll) return pmn_set_error(PMN_E_ARG, "FASTA: more than 2^31 bases");
     s->nwords = ((n + 31) / 32 + 3) / 4 * 4 + PMN_PAD_WORDS;
-    if (S.codes.ensure((size_t)n + 64)) return -3;
-    if (s->w_fwd.ensure(8 * (size_t)s->nwords) || s->xm_fwd.ensure(4 * (size_t)s->nwords) ||
-        s->w_rev.ensure(8 * (size_t)s->nwords) || s->xm_rev.ensure(4 * (size_t)s->nwords)) return -3;
-    PMN_H2D(c, S.codes.p, codes_host, (size_t)n);
-    unsigned g = (unsigned)((s->nwords + 255) / 256);
-    k_pack<<<g, 256, 0, c->stream>>>(S.codes.as<uint8_t>(), n, s->w_fwd.as<uint64_t>(), s->xm_fwd.as<uint32_t>(), s->nwords);
-    k_revcomp<<<g, 256, 0, c->stream>>>(s->w_fwd.as<uint64_t>(), s->xm_fwd.as<uint32_t>(), n, s->w_rev.as<uint64_t>(), s->xm_rev.as<uint32_t>(), s->nwords);
+    if (pmn_pool_get(c, s->w_fwd, 8 * (size_t)s->nwords) || pmn_pool_get(c, s->xm_fwd, 4 * (size_t)s->nwords) ||
+        pmn_pool_get(c, s->w_rev, 8 * (size_t)s->nwords) || pmn_pool_get(c, s->xm_rev, 4 * (size_t)s->nwords)) return -3;
+    const unsigned gw = (unsigned)((s->nwords + 255) / 256);
+    k_pack<<<gw, 256, 0, st>>>(S.codes.as<uint8_t>(), n, s->w_fwd.as<uint64_t>(), s->xm_fwd.as<uint32_t>(), s->nwords);
+    k_revcomp<<<gw, 256, 0, st>>>(s->w_fwd.as<uint64_t>(), s->xm_fwd.as<uint32_t>(), n, s->w_rev.as<uint64_t>(), s->xm_rev.as<uint32_t>(), s->nwords);
     c->launches += 2;
     PMN_CUDA_OK(cudaGetLastError());
-    PMN_CUDA_OK(cudaStreamSynchronize(c->stream));   // codes_host may be reused by the caller
+    PMN_CUDA_OK(cudaStreamSynchronize(st));   // txt may be reused by the caller
     return 0;
 }
 
@@ -228,7 +323,7 @@ int pmn_index_build_impl(pmn_ctx *c, const pmn_seq *ref, pmn_index *ix)
     if (S.gs.ensure(4 * (size_t)n) || S.rank.ensure(4 * (size_t)(n + 1)) || S.flags.ensure(4 * (size_t)n) ||
         S.list0.ensure(4 * (size_t)n) || S.list1.ensure(4 * (size_t)n) || S.gsn.ensure(4 * (size_t)n)) return -3;
     if (S.scan_tmp.ensure(8 * pmn_scan_scratch_elems(n))) return -3;
-    if (ix->sa.ensure(4 * (size_t)n) || ix->lcp.ensure(4 * (size_t)n)) return -3;
+    if (pmn_pool_get(c, ix->sa, 4 * (size_t)n) || pmn_pool_get(c, ix->lcp, 4 * (size_t)n)) return -3;
     if (S.ensure_pinned(64)) return -3;
 
     PMN_CUDA_OK(cudaEventRecord(c->ev[0], st));
@@ -289,7 +384,7 @@ int pmn_index_build_impl(pmn_ctx *c, const pmn_seq *ref, pmn_index *ix)
     // 4. bucket table over the first K bases
     int K = 8; while (K < 13 && (1ll << (2 * K)) < n) K++;
     ix->K = K;
-    if (ix->table.ensure(4 * ((size_t)1 << (2 * K)) + 16)) return -3;
+    if (pmn_pool_get(c, ix->table, 4 * ((size_t)1 << (2 * K)) + 16)) return -3;
     k_bucket_fill<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(T, sa, K, ix->table.as<uint32_t>()); launches++;
 
     PMN_CUDA_OK(cudaEventRecord(c->ev[1], st));

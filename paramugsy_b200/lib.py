@@ -34,7 +34,8 @@ class Stats(C.Structure):
                 ("ms_index", C.c_float), ("ms_seed", C.c_float), ("ms_cluster", C.c_float),
                 ("ms_extend", C.c_float), ("ms_total", C.c_float), ("ms_seed_kernel", C.c_float),
                 ("ms_wave1", C.c_float), ("ms_stitch", C.c_float), ("kernel_launches", C.c_int64),
-                ("wave1_cells", C.c_int64)]
+                ("wave1_cells", C.c_int64), ("wall_ms_index", C.c_float), ("wall_ms_align", C.c_float),
+                ("wall_ms_text", C.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
