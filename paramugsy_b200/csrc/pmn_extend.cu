@@ -27,6 +27,8 @@
 #include "pmn_scratch.cuh"
 
 #define EX_RW 256                      /* shared-memory ring width (cells) per score row          */
+#define EX_BAND_SMEM 224                /* widest band kept in shared memory (ring and base caches)  */
+#define EX_SMEM_WARP (EX_ROWS * EX_RW * 4 + 512)   /* bytes per warp: score ring + two 256-base caches */
 #define EX_WCAP (PMN_MAX_ALIGNMENT_LENGTH + 8)   /* global score row capacity                    */
 #define EX_ROWS 12                     /* 3 anti-diagonals x (DEL, INS, MAT, cell max)            */
 #define EX_DMAX (2 * PMN_MAX_ALIGNMENT_LENGTH + 8)
@@ -136,22 +138,111 @@ __device__ int align_engine(const Eng &E, int64_t Abase, int64_t Astart, int64_t
     uint8_t *tcur = E.tbp + EX_TB_HDR, *tend = E.tbp + EX_TBW;     // current traceback chunk (warp-uniform)
 
     int pplo = 1, pphi = 0, plo = 0, phi = 0, tlo = 0, thi = 0;
-    if (lane == 0) {
-        SC(bp, PMN_ST_DEL, 0) = PMN_NEG; SC(bp, PMN_ST_INS, 0) = PMN_NEG; SC(bp, PMN_ST_MAT, 0) = 0; SC(bp, 3, 0) = 0;
-        if (!search) { tboff[0] = tcur; tblo[0] = 0; tcur[0] = (uint8_t)(PMN_ST_NONE | PMN_ST_NONE << 2 | PMN_ST_NONE << 4 | PMN_ST_MAT << 6); }
-    }
-    if (!search) tcur += 1;
+    if (lane == 0 && !search) { tboff[0] = tcur; tblo[0] = 0; tcur[0] = (uint8_t)(PMN_ST_NONE | PMN_ST_NONE << 2 | PMN_ST_NONE << 4 | PMN_ST_MAT << 6); }
+    if (!search) tcur += 32;
     __syncwarp();
+
+    // base caches in shared memory: A'[i] at ca[i & 255], B'[j] at cb[j & 255], filled 32 bases at a
+    // time as the band advances (one global fetch per lane every 32 anti-diagonals)
+    uint8_t *ca = (uint8_t *)(E.ssc + EX_ROWS * EX_RW), *cb = ca + 256;
+    int ca_hi = 1, cb_hi = 1;                       // next window index to load
+    const int64_t Apos0 = Abase + Astart - 1, Bpos0 = Bbase + Bstart - 1;
 
     int high = 0, best_d = 0, best_j = 0, reached = 0;
     unsigned long long cells = 0;
     bool arena_fail = false;
-    for (int d = 1; d <= N + M; d++) {
+    int d = 1;
+    bool general = false;
+
+    // ===== register-band path: while the band is at most 31 columns wide, lane l owns column
+    // J0 + l; the previous anti-diagonal lives in registers (p*), the one before it shifted by one
+    // column (q* = row d-2 at column j-1, which is exactly what was shuffled in as L one step ago)
+    {
+        int J0 = 0;
+        int pD = PMN_NEG, pI = PMN_NEG, pM = lane == 0 ? 0 : PMN_NEG;
+        int qD = PMN_NEG, qI = PMN_NEG, qM = PMN_NEG;
+        int bq = PMN_CODE_X;
+        { const int j = J0 + lane; if (j >= 1 && j <= M) bq = pmn_base_at(Q, Bpos0 + (int64_t)dir * (j - 1)); }
+        for (; d <= N + M; d++) {
+            if (!forced && d - best_d > breaklen) break;
+            const int clo = tlo > d - N ? tlo : d - N, chi = thi + 1 < M ? thi + 1 : M;
+            if (clo > chi) break;
+            const int width = chi - clo + 1;
+            if (width > 31) { general = true; break; }
+            if (chi > J0 + 31) {
+                // slide the window: column clo-1 (still readable as a predecessor) becomes lane 0
+                const int sft = clo - 1 - J0;
+                pD = __shfl_down_sync(0xffffffffu, pD, sft); pI = __shfl_down_sync(0xffffffffu, pI, sft); pM = __shfl_down_sync(0xffffffffu, pM, sft);
+                qD = __shfl_down_sync(0xffffffffu, qD, sft); qI = __shfl_down_sync(0xffffffffu, qI, sft); qM = __shfl_down_sync(0xffffffffu, qM, sft);
+                if (lane + sft > 31) { pD = pI = pM = qD = qI = qM = PMN_NEG; }
+                J0 += sft;
+                const int j = J0 + lane;
+                bq = (j >= 1 && j <= M) ? pmn_base_at(Q, Bpos0 + (int64_t)dir * (j - 1)) : PMN_CODE_X;
+            }
+            {
+                const int need_i = d - clo < N ? d - clo : N;
+                bool filled = false;
+                while (ca_hi <= need_i) { const int i = ca_hi + lane; if (i <= N) ca[i & 255] = (uint8_t)pmn_base_at(X.R, Apos0 + (int64_t)dir * (i - 1)); ca_hi += 32; filled = true; }
+                if (filled) __syncwarp();
+            }
+            uint8_t *trow = nullptr;
+            if (!search) {
+                if (tcur + 32 > tend) {
+                    unsigned long long at = 0;
+                    if (lane == 0) at = atomicAdd(X.counters + 1, (unsigned long long)EX_ARENA_CHUNK);
+                    at = __shfl_sync(0xffffffffu, at, 0);
+                    if (at + EX_ARENA_CHUNK > X.arena_cap) { arena_fail = true; break; }
+                    tcur = X.arena + at; tend = tcur + EX_ARENA_CHUNK;
+                }
+                trow = tcur; tcur += 32;
+                if (lane == 0) { tboff[d] = trow; tblo[d] = J0; }
+            }
+            const int j = J0 + lane, i = d - j;
+            const bool act = j >= clo && j <= chi;
+            int LD = __shfl_up_sync(0xffffffffu, pD, 1), LI = __shfl_up_sync(0xffffffffu, pI, 1), LM = __shfl_up_sync(0xffffffffu, pM, 1);
+            if (lane == 0) { LD = PMN_NEG; LI = PMN_NEG; LM = PMN_NEG; }
+            int sc = PMN_BAD_SCORE;
+            if (act && i >= 1 && j >= 1) { const int a_ = ca[i & 255]; if (a_ == bq && a_ != PMN_CODE_X) sc = PMN_GOOD_SCORE; }
+            int vD, vI, vM, uD, uI, uM;
+            score_edit(LD + PMN_CONT_GAP_SCORE, LI + PMN_OPEN_GAP_SCORE, LM + PMN_OPEN_GAP_SCORE, vD, uD);
+            score_edit(pD + PMN_OPEN_GAP_SCORE, pI + PMN_CONT_GAP_SCORE, pM + PMN_OPEN_GAP_SCORE, vI, uI);
+            score_edit(qD + sc, qI + sc, qM + sc, vM, uM);
+            const int ms = max_state(vD, vI, vM);
+            const int cm = act ? (ms == PMN_ST_DEL ? vD : (ms == PMN_ST_INS ? vI : vM)) : INT32_MIN;
+            if (act && !search) trow[lane] = (uint8_t)(uD | uI << 2 | uM << 4 | ms << 6);
+            qD = LD; qI = LI; qM = LM;
+            pD = act ? vD : PMN_NEG; pI = act ? vI : PMN_NEG; pM = act ? vM : PMN_NEG;
+            const int cmax = __reduce_max_sync(0xffffffffu, cm);
+            const unsigned eq = __ballot_sync(0xffffffffu, cm == cmax);
+            cells += (unsigned long long)width;
+            if (cmax >= high) { high = cmax; best_d = d; best_j = J0 + 31 - __clz((int)eq); }
+            pplo = plo; pphi = phi; plo = clo; phi = chi;
+            if (d == N + M) { reached = 1; break; }
+            if (!forced) {
+                const unsigned bal = __ballot_sync(0xffffffffu, cm >= high - max_diff);
+                if (bal) { tlo = J0 + __ffs(bal) - 1; thi = J0 + 31 - __clz((int)bal); } else { tlo = chi + 1; thi = clo - 1; }
+            } else { tlo = clo; thi = chi; }
+        }
+        if (general) {
+            // the band outgrew the warp: park both rows in the shared-memory ring and continue below
+            const int j = J0 + lane;
+            if (j >= plo && j <= phi) { SC(bp, 0, j) = pD; SC(bp, 1, j) = pI; SC(bp, 2, j) = pM; }
+            if (j - 1 >= pplo && j - 1 <= pphi && j - 1 >= 0) { SC(bpp, 0, j - 1) = qD; SC(bpp, 1, j - 1) = qI; SC(bpp, 2, j - 1) = qM; }
+            if (plo < J0) plo = J0;
+            if (pplo < J0 - 1) pplo = J0 - 1;
+            const int cstart = (tlo > d - N ? tlo : d - N);
+            cb_hi = cstart > 32 ? ((cstart - 32) | 1) : 1;
+            __syncwarp();
+        }
+    }
+
+    // ===== general path: any band width, rows in the shared-memory ring (or global memory)
+    for (; general && d <= N + M; d++) {
         if (!forced && d - best_d > breaklen) break;
         const int clo = tlo > d - N ? tlo : d - N, chi = thi + 1 < M ? thi + 1 : M;
         if (clo > chi) break;
         const int width = chi - clo + 1;
-        if (in_smem && width > EX_RW) {
+        if (in_smem && width > EX_BAND_SMEM) {
             // move the two live anti-diagonals to global rows and carry on there
             int32_t *g = E.gsc;
             for (int st = 0; st < 4; st++) {
@@ -160,6 +251,13 @@ __device__ int align_engine(const Eng &E, int64_t Abase, int64_t Astart, int64_t
             }
             __syncwarp();
             in_smem = false; base = g; stride = EX_WCAP; mask = -1;
+        }
+        if (in_smem) {
+            const int need_i = d - clo < N ? d - clo : N;
+            bool filled = false;
+            while (ca_hi <= need_i) { const int i = ca_hi + lane; if (i <= N) ca[i & 255] = (uint8_t)pmn_base_at(X.R, Apos0 + (int64_t)dir * (i - 1)); ca_hi += 32; filled = true; }
+            while (cb_hi <= chi) { const int j = cb_hi + lane; if (j <= M) cb[j & 255] = (uint8_t)pmn_base_at(Q, Bpos0 + (int64_t)dir * (j - 1)); cb_hi += 32; filled = true; }
+            if (filled) __syncwarp();
         }
         uint8_t *trow = nullptr;
         if (!search) {
@@ -173,10 +271,14 @@ __device__ int align_engine(const Eng &E, int64_t Abase, int64_t Astart, int64_t
             trow = tcur; tcur += width;
             if (lane == 0) { tboff[d] = trow; tblo[d] = clo; }
         }
-        long long dkey = LLONG_MIN;
+        int dmax = INT32_MIN, dmaxj = -1;
+        int cm_f = INT32_MIN, cm_l = INT32_MIN;         // this lane's cell maxima in the first / last chunk
+        const int jb_last = clo + ((chi - clo) & ~31);
         for (int jb = clo; jb <= chi; jb += 32) {
             const int j = jb + lane;
-            if (j <= chi) {
+            const bool act = j <= chi;
+            int cm = INT32_MIN;
+            if (act) {
                 const int i = d - j;
                 int U0 = PMN_NEG, U1 = PMN_NEG, U2 = PMN_NEG, L0 = PMN_NEG, L1 = PMN_NEG, L2 = PMN_NEG, P0 = PMN_NEG, P1 = PMN_NEG, P2 = PMN_NEG;
                 if (j >= plo && j <= phi) { U0 = SC(bp, 0, j); U1 = SC(bp, 1, j); U2 = SC(bp, 2, j); }
@@ -184,46 +286,48 @@ __device__ int align_engine(const Eng &E, int64_t Abase, int64_t Astart, int64_t
                 if (j - 1 >= pplo && j - 1 <= pphi) { P0 = SC(bpp, 0, j - 1); P1 = SC(bpp, 1, j - 1); P2 = SC(bpp, 2, j - 1); }
                 int s = PMN_BAD_SCORE;
                 if (i >= 1 && j >= 1) {
-                    int ca = pmn_base_at(X.R, Abase + Astart - 1 + (int64_t)dir * (i - 1));
-                    int cb = pmn_base_at(Q, Bbase + Bstart - 1 + (int64_t)dir * (j - 1));
-                    if (ca == cb && ca != PMN_CODE_X) s = PMN_GOOD_SCORE;
+                    int a_, b_;
+                    if (in_smem) { a_ = ca[i & 255]; b_ = cb[j & 255]; }
+                    else { a_ = pmn_base_at(X.R, Apos0 + (int64_t)dir * (i - 1)); b_ = pmn_base_at(Q, Bpos0 + (int64_t)dir * (j - 1)); }
+                    if (a_ == b_ && a_ != PMN_CODE_X) s = PMN_GOOD_SCORE;
                 }
                 int vD, vI, vM, uD, uI, uM;
                 score_edit(L0 + PMN_CONT_GAP_SCORE, L1 + PMN_OPEN_GAP_SCORE, L2 + PMN_OPEN_GAP_SCORE, vD, uD);
                 score_edit(U0 + PMN_OPEN_GAP_SCORE, U1 + PMN_CONT_GAP_SCORE, U2 + PMN_OPEN_GAP_SCORE, vI, uI);
                 score_edit(P0 + s, P1 + s, P2 + s, vM, uM);
                 const int ms = max_state(vD, vI, vM);
-                const int cm = ms == PMN_ST_DEL ? vD : (ms == PMN_ST_INS ? vI : vM);
+                cm = ms == PMN_ST_DEL ? vD : (ms == PMN_ST_INS ? vI : vM);
                 SC(bc, 0, j) = vD; SC(bc, 1, j) = vI; SC(bc, 2, j) = vM; SC(bc, 3, j) = cm;
                 if (!search) trow[j - clo] = (uint8_t)(uD | uI << 2 | uM << 4 | ms << 6);
-                long long key = (long long)cm * 4294967296ll + j;
-                if (key > dkey) dkey = key;
             }
+            if (jb == clo) cm_f = cm;
+            if (jb == jb_last) cm_l = cm;
+            // chunk maximum; among equal cells the largest j wins, and a later chunk wins ties too
+            const int cmax = __reduce_max_sync(0xffffffffu, cm);
+            const unsigned eq = __ballot_sync(0xffffffffu, act && cm == cmax);
+            if (cmax >= dmax) { dmax = cmax; dmaxj = jb + 31 - __clz((int)eq); }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { long long k2 = __shfl_xor_sync(0xffffffffu, dkey, o); if (k2 > dkey) dkey = k2; }
         cells += (unsigned long long)width;
         __syncwarp();
-        {
-            // floor division by 2^32 recovers (cm, j) for negative cm as well
-            long long cmq = dkey >> 32; int dj = (int)(dkey - cmq * 4294967296ll);
-            int dmax = (int)cmq;
-            if (dmax >= high) { high = dmax; best_d = d; best_j = dj; }
-        }
+        if (dmax >= high) { high = dmax; best_d = d; best_j = dmaxj; }
         if (d == N + M) { reached = 1; break; }
         if (!forced) {
             const int t = high - max_diff;
             int nlo = chi + 1, nhi = clo - 1;
             for (int jb = clo; jb <= chi; jb += 32) {
                 const int j = jb + lane;
-                unsigned bal = __ballot_sync(0xffffffffu, j <= chi && SC(bc, 3, j) >= t);
+                int v = INT32_MIN;
+                if (j <= chi) v = jb == clo ? cm_f : (jb == jb_last ? cm_l : SC(bc, 3, j));
+                const unsigned bal = __ballot_sync(0xffffffffu, v >= t);
                 if (bal) { nlo = jb + __ffs(bal) - 1; break; }
             }
             if (nlo <= chi) {
-                for (int jt = chi; jt >= nlo; jt -= 32) {
-                    const int j = jt - lane;
-                    unsigned bal = __ballot_sync(0xffffffffu, j >= nlo && SC(bc, 3, j) >= t);
-                    if (bal) { nhi = jt - (__ffs(bal) - 1); break; }
+                for (int jb = jb_last; jb >= clo; jb -= 32) {
+                    const int j = jb + lane;
+                    int v = INT32_MIN;
+                    if (j <= chi && j >= nlo) v = jb == clo ? cm_f : (jb == jb_last ? cm_l : SC(bc, 3, j));
+                    const unsigned bal = __ballot_sync(0xffffffffu, v >= t);
+                    if (bal) { nhi = jb + 31 - __clz((int)bal); break; }
                 }
             }
             tlo = nlo; thi = nhi;
@@ -326,7 +430,7 @@ __device__ __forceinline__ Eng make_eng(const ExShared &X, int32_t *smem_all)
     const int warp = threadIdx.x >> 5;
     const size_t slot = (size_t)blockIdx.x * EX_WARPS_PER_BLOCK + warp;
     E.X = &X; E.lane = threadIdx.x & 31;
-    E.ssc = smem_all + (size_t)warp * EX_ROWS * EX_RW;
+    E.ssc = smem_all + (size_t)warp * (EX_SMEM_WARP / 4);
     E.gsc = X.gscore + slot * (size_t)EX_ROWS * EX_WCAP;
     E.tbp = X.tbpriv + slot * (size_t)EX_TBW;
     return E;
@@ -1006,7 +1110,7 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     X.cs = cs;
     PMN_CUDA_OK(cudaMemsetAsync(markkey, 0, 8 * (size_t)(nm + 1), st));
 
-    const size_t smem = (size_t)EX_WARPS_PER_BLOCK * EX_ROWS * EX_RW * 4;
+    const size_t smem = (size_t)EX_WARPS_PER_BLOCK * EX_SMEM_WARP;
     static bool attr_set = false;
     if (!attr_set) {
         PMN_CUDA_OK(cudaFuncSetAttribute(k_ex_wave1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
