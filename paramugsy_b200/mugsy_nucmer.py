@@ -1,0 +1,231 @@
+"""Host-side mirror of the reference's worker executable lib/nucmer/mugsy_nucmer.ml.
+
+Same option record, same flags, same file contract, same error behaviour; the one line that
+differs is the reference's
+    Shell.sh "nucmer %s %s -p %s %s" ref_file query_file obname options.nucmer_opts   (mugsy_nucmer.ml:100)
+which here calls the B200 library through its C ABI instead of forking MUMmer.
+
+`delta-filter` (mugsy_nucmer.ml:102-105) and `delta2maf` (:118-124) are external programs in the
+reference too and are rows "next" of SURVEY.md §8f: they are run from $PATH exactly as the
+reference does, and a missing program raises Failure like Shell.sh would.
+"""
+import os
+import shlex
+import shutil
+import subprocess
+import sys
+from dataclasses import dataclass
+from typing import Optional
+
+from . import lib
+
+
+class Failure(Exception):
+    """OCaml's `Failure` (mugsy_nucmer.ml:78-81) / a failing Shell.sh."""
+
+
+@dataclass
+class Options:                      # mugsy_nucmer.ml:30-41
+    ref_seq: str
+    query_seq: str
+    maf_out: str
+    delta_out: str
+    delta_pp: Optional[str] = None
+    nucmer_opts: str = ""
+    out_dir: str = "/tmp"
+    filter: bool = True
+    colinear: bool = False
+    debug: bool = False
+    tmp_dir: str = "/tmp"
+
+
+def parse_argv(argv) -> Options:
+    """mugsy_nucmer.ml:46-94.  Flags: -out_dir -ref_seq -query_seq -maf_out -delta_out -delta_pp
+    -nucmer_opts -nofilter -colinear -debug -tmp_dir."""
+    v = dict(out_dir="/tmp", ref_seq="", query_seq="", delta_pp=None, nucmer_opts="", filter=True, colinear=False,
+             debug=False, maf_out="", delta_out="", tmp_dir="/tmp")
+    takes = {"-out_dir": "out_dir", "-ref_seq": "ref_seq", "-query_seq": "query_seq", "-maf_out": "maf_out",
+             "-delta_out": "delta_out", "-delta_pp": "delta_pp", "-nucmer_opts": "nucmer_opts", "-tmp_dir": "tmp_dir"}
+    i = 0
+    while i < len(argv):
+        a = argv[i]
+        if a in takes:
+            if i + 1 >= len(argv):
+                raise Failure(f"option '{a}' needs an argument")
+            v[takes[a]] = argv[i + 1]; i += 2
+        elif a == "-nofilter":
+            v["filter"] = False; i += 1
+        elif a == "-colinear":
+            v["colinear"] = True; i += 1
+        elif a == "-debug":
+            v["debug"] = True; i += 1
+        elif a.startswith("-"):
+            raise Failure(f"unknown option '{a}'")
+        else:
+            i += 1                      # anonymous arguments are collected and ignored (mugsy_nucmer.ml:60)
+    if v["ref_seq"] == "" or v["query_seq"] == "":
+        raise Failure("Must specify -ref_seq and -query_seq")
+    if v["maf_out"] == "" or v["delta_out"] == "":
+        raise Failure("Must specify -maf_out and -delta_out")
+    v["maf_out"] = v["out_dir"] + "/" + v["maf_out"]          # mugsy_nucmer.ml:85-86
+    v["delta_out"] = v["out_dir"] + "/" + v["delta_out"]
+    return Options(**v)
+
+
+def nucmer_opts_to_pmn(opts: str) -> lib.Opts:
+    """The string the reference hands to nucmer verbatim (mugsy_nucmer.ml:100), as pmn_opts."""
+    o = lib.default_opts()
+    toks = shlex.split(opts)
+    i = 0
+    ints = {"-l": "minmatch", "--minmatch": "minmatch", "-c": "mincluster", "--mincluster": "mincluster", "-g": "maxgap",
+            "--maxgap": "maxgap", "-D": "diagdiff", "--diagdiff": "diagdiff", "-b": "breaklen", "--breaklen": "breaklen"}
+    while i < len(toks):
+        t = toks[i]
+        if t in ints:
+            setattr(o, ints[t], int(toks[i + 1])); i += 2
+        elif t in ("-d", "--diagfactor"):
+            o.diagfactor = float(toks[i + 1]); i += 2
+        elif t in ("-f", "--forward"):
+            o.do_reverse = 0; i += 1
+        elif t in ("-r", "--reverse"):
+            o.do_forward = 0; i += 1
+        elif t in ("--mumreference", "--delta", "--extend", "--simplify", "--optimize"):
+            i += 1
+        elif t == "--noextend":
+            o.do_extend = 0; i += 1
+        elif t == "--nosimplify":
+            o.do_simplify = 0; i += 1
+        else:
+            raise Failure(f"nucmer option {t!r} is not implemented on the B200 path")
+    return o
+
+
+def _sh(options: Options, cmd: str):
+    if options.debug:
+        print(cmd, file=sys.stderr)
+    prog = shlex.split(cmd)[0]
+    if shutil.which(prog) is None:
+        raise Failure(f"{prog}: command not found (external program of the reference, SURVEY.md §8f)")
+    rc = subprocess.call(cmd, shell=True)
+    if rc != 0:
+        raise Failure(f"command failed with status {rc}: {cmd}")
+
+
+def nucmer(options: Options, ref_file: str, query_file: str, ctx: Optional[lib.Context] = None) -> str:
+    """mugsy_nucmer.ml:96-116: <tmp>/nucmer.delta, optional delta-filter, optional post-processor."""
+    obname = f"{options.tmp_dir}/nucmer"
+    delta_file = f"{obname}.delta"
+    delta_filt_file = f"{obname}.filt.delta"
+    own = ctx is None
+    c = ctx or lib.Context(int(os.environ.get("PMN_DEVICE", "0")))
+    try:
+        o = nucmer_opts_to_pmn(options.nucmer_opts)
+        rc = lib.lib().pmn_align_pair(c.h, os.fsencode(ref_file), os.fsencode(query_file), o, os.fsencode(delta_file))
+        if rc != 0:
+            raise Failure(lib.lib().pmn_last_error(None).decode(errors="replace"))
+    finally:
+        if own:
+            c.close()
+    if options.filter:
+        chaining_opt = "-m" if options.colinear else "-1"
+        _sh(options, f"delta-filter {chaining_opt} {shlex.quote(delta_file)} > {shlex.quote(delta_filt_file)}")
+        delta_file = delta_filt_file
+    if options.delta_pp is not None:
+        delta_pp_file = f"{obname}.pp.delta"
+        _sh(options, f"{options.delta_pp} < {shlex.quote(delta_file)} > {shlex.quote(delta_pp_file)}")
+        delta_file = delta_pp_file
+    return delta_file
+
+
+def generate_maf(options: Options):
+    """mugsy_nucmer.ml:118-124."""
+    _sh(options, f"delta2maf {shlex.quote(options.delta_out)} > {shlex.quote(options.maf_out)}")
+
+
+def run_search(options: Options, ctx=None, maf=True):
+    """mugsy_nucmer.ml:127-131."""
+    delta_file = nucmer(options, options.ref_seq, options.query_seq, ctx)
+    shutil.copyfile(delta_file, options.delta_out)
+    if maf:
+        generate_maf(options)
+
+
+def main(argv=None):
+    """mugsy_nucmer.ml:134-140 (including the rm -rf of tmp_dir)."""
+    options = parse_argv(sys.argv[1:] if argv is None else argv)
+    os.makedirs(options.out_dir, exist_ok=True)
+    os.makedirs(options.tmp_dir, exist_ok=True)
+    run_search(options)
+    shutil.rmtree(options.tmp_dir, ignore_errors=True)
+
+
+# ---- the callers either side (lib/base/nucmer_task.ml, lib/base/pm_job.ml) ------------------------
+
+def basename(ref_seq: str, query_seq: str) -> str:
+    """nucmer_task.ml:10-11."""
+    return os.path.basename(ref_seq) + "-" + os.path.basename(query_seq)
+
+
+def out_paths(tmp_dir: str, sequences):
+    """nucmer_task.ml:13-23: keys <bname>-maf / <bname>-delta."""
+    m = {}
+    for ref_seq, query_seq in sequences:
+        b = basename(ref_seq, query_seq)
+        m[b + "-maf"] = os.path.join(tmp_dir, b + ".maf")
+        m[b + "-delta"] = os.path.join(tmp_dir, b + ".delta")
+    return m
+
+
+def make_commands(searches, tmp_dir: str):
+    """nucmer_task.ml:48-59: one mugsy_nucmer command line per pair (note -out_dir gets tmp_dir and
+    -tmp_dir gets tmp_dir/<bname>, Appendix A of SURVEY.md)."""
+    cmds = []
+    for ref_seq, query_seq in searches:
+        b = basename(ref_seq, query_seq)
+        cmds.append(f"mugsy_nucmer -ref_seq {ref_seq} -query_seq {query_seq} -out_dir {tmp_dir} -tmp_dir {os.path.join(tmp_dir, b)} "
+                    f"-maf_out {b}.maf -delta_out {b}.delta")
+    return cmds
+
+
+def searches(genomes):
+    """pm_job.ml:43-51: upper-triangle ordered pairs, the earlier genome is the reference."""
+    return [(genomes[i], g) for i in range(len(genomes)) for g in genomes[i + 1:]]
+
+
+def cross(left, right):
+    """pm_job.ml:53-57."""
+    return [(a, b) for a in left for b in right]
+
+
+def chunk(n: int, items):
+    """job_processor.ml:33-34."""
+    return [items[i:i + n] for i in range(0, len(items), n)]
+
+
+def run_nucmers(searches_, tmp_dir: str, nucmer_chunk: int = 10, ctx=None, filter=False):
+    """job_processor.ml:128-154 without the script/queue machinery: every chunk of pairs goes to the
+    library's batch entry point (the batch unit of the reference, nucmer_task.ml:6); returns the
+    out_paths map.  Any failing pair raises Failure (job_processor.ml:72-73 fails the whole node)."""
+    import ctypes as C
+    os.makedirs(tmp_dir, exist_ok=True)
+    own = ctx is None
+    c = ctx or lib.Context(int(os.environ.get("PMN_DEVICE", "0")))
+    try:
+        for part in chunk(nucmer_chunk, list(searches_)):
+            outs = [os.path.join(tmp_dir, basename(a, b) + ".delta") for a, b in part]
+            arr = lambda xs: (C.c_char_p * len(xs))(*[os.fsencode(x) for x in xs])
+            rc = lib.lib().pmn_align_batch(c.h, len(part), arr([a for a, _ in part]), arr([b for _, b in part]), arr(outs), None)
+            if rc != 0:
+                raise Failure(lib.lib().pmn_last_error(None).decode(errors="replace"))
+    finally:
+        if own:
+            c.close()
+    return out_paths(tmp_dir, searches_)
+
+
+if __name__ == "__main__":
+    try:
+        main()
+    except Failure as e:
+        print(f"Fatal error: exception Failure(\"{e}\")", file=sys.stderr)
+        sys.exit(2)
