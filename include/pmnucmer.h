@@ -118,6 +118,31 @@ int  pmn_align_pair(pmn_ctx *c, const char *ref_fasta_path, const char *qry_fast
 int  pmn_align_batch(pmn_ctx *c, int n, const char *const *ref_fasta_paths, const char *const *qry_fasta_paths,
                      const char *const *out_delta_paths, const pmn_opts *o);
 
+/* ---- in-process batch scheduler ----
+ * Replaces the reference's fan-out of one `mugsy_nucmer` process per pair: run_nucmers
+ * (lib/base/job_processor.ml:128-154) cuts the pair list into Nucmer_task.t.searches
+ * (lib/base/nucmer_task.ml:6) and runs `-cores N` scripts at a time
+ * (lib/base/queued_task_server.ml:57-64).  Here `workers` threads share one GPU, one
+ * context (stream + scratch) each; every genome is packed once and every reference index
+ * is built once and shared.  Pairs are (ref[k], qry[k]) indexes into the genome list;
+ * names[g] is echoed on line 1 of the .delta files.  out[k] is owned by the caller
+ * (pmn_result_free).  Results do not depend on `workers`. */
+typedef struct pmn_sched pmn_sched;
+int  pmn_sched_create(int device, int workers, pmn_sched **out);
+void pmn_sched_destroy(pmn_sched *s);
+int  pmn_sched_workers(const pmn_sched *s);
+pmn_ctx *pmn_sched_ctx(const pmn_sched *s, int k);          /* worker k's context (borrowed) */
+void pmn_sched_counters(const pmn_sched *s, int64_t out[4]); /* pmn_ctx_counters summed over the workers */
+/* genomes as FASTA bytes in HOST memory */
+int  pmn_sched_align_fasta(pmn_sched *s, int n_genomes, const char *const *fasta, const size_t *bytes, const char *const *names,
+                           int n_pairs, const int32_t *ref, const int32_t *qry, const pmn_opts *o, pmn_result **out);
+/* genomes already packed in HBM (any context of the scheduler's device) */
+int  pmn_sched_align_seqs(pmn_sched *s, int n_genomes, const pmn_seq *const *seqs, const char *const *names,
+                          int n_pairs, const int32_t *ref, const int32_t *qry, const pmn_opts *o, pmn_result **out);
+/* genomes and results as files: one call per Nucmer_task.t.searches */
+int  pmn_sched_align_files(pmn_sched *s, int n, const char *const *ref_fasta_paths, const char *const *qry_fasta_paths,
+                           const char *const *out_delta_paths, const pmn_opts *o);
+
 /* ---- stage dumps for the parity tests (sizes via the n_* calls; buffers are caller-owned) ---- */
 int64_t pmn_index_size(const pmn_index *ix);
 int  pmn_index_copy_sa(const pmn_index *ix, int32_t *sa_out, int32_t *lcp_out);

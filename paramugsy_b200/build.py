@@ -40,7 +40,7 @@ def build(force=False, verbose=False):
                 subprocess.check_call(cmd)
             objs.append(obj)
         cuda_lib = os.path.join(os.path.dirname(os.path.dirname(NVCC)), "lib64")
-        subprocess.check_call(["g++", "-shared", "-o", so] + objs + ["-L", cuda_lib, "-lcudart", "-Wl,-rpath," + cuda_lib])
+        subprocess.check_call(["g++", "-shared", "-o", so] + objs + ["-L", cuda_lib, "-lcudart", "-lpthread", "-Wl,-rpath," + cuda_lib])
     synth = os.path.join(LIB, "libpmn_synth.so")
     src = os.path.join(CSRC, "pmn_synth.c")
     if force or _stale(synth, [src]):

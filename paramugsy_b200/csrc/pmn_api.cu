@@ -45,7 +45,7 @@ void pmn_scratch_free(Scratch *s)
                        &s->cl_a, &s->cl_b, &s->cl_c, &s->cl_d, &s->cl_e, &s->cl_f, &s->cl_g, &s->cl_h, &s->cl_i, &s->cl_j, &s->cl_k, &s->cl_l,
                        &s->cl_matches, &s->cl_recs, &s->cl_counters,
                        &s->ex_a, &s->ex_b, &s->ex_c, &s->ex_d, &s->ex_e, &s->ex_f, &s->ex_g, &s->ex_h, &s->ex_i, &s->ex_j, &s->ex_k, &s->ex_l,
-                       &s->ex_scores, &s->ex_tb, &s->ex_tbidx, &s->ex_pool, &s->ex_counters, &s->ex_arena };
+                       &s->ex_scores, &s->ex_tb, &s->ex_tbidx, &s->ex_pool, &s->ex_counters, &s->ex_arena, &s->ex_dbg };
     for (DevBuf *b : bufs) b->release();
     if (s->pinned) cudaFreeHost(s->pinned);
     delete s;
@@ -74,6 +74,7 @@ extern "C" int pmn_ctx_create(int device, pmn_ctx **out)
     PMN_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto &e : c->ev) PMN_CUDA_OK(cudaEventCreate(&e));
     c->scratch = pmn_scratch_new();
+    c->pool = std::make_shared<DevPool>();
     *out = c;
     return 0;
 }
@@ -81,13 +82,15 @@ extern "C" int pmn_ctx_create(int device, pmn_ctx **out)
 int pmn_pool_get(pmn_ctx *c, DevBuf &b, size_t bytes)
 {
     if (b.cap >= bytes) return 0;
-    if (b.p) pmn_pool_put(c, b);
+    DevPool &P = *c->pool;
+    std::lock_guard<std::mutex> lk(P.mu);
+    if (b.p) { if (P.bufs.size() >= 256) b.release(); else { P.bufs.push_back(b); b.p = nullptr; b.cap = 0; } }
     int best = -1;
-    for (size_t i = 0; i < c->pool.size(); i++)
-        if (c->pool[i].cap >= bytes && (best < 0 || c->pool[i].cap < c->pool[(size_t)best].cap)) best = (int)i;
-    if (best >= 0 && c->pool[(size_t)best].cap <= 2 * bytes + (1u << 20)) {
-        b = c->pool[(size_t)best];
-        c->pool.erase(c->pool.begin() + best);
+    for (size_t i = 0; i < P.bufs.size(); i++)
+        if (P.bufs[i].cap >= bytes && (best < 0 || P.bufs[i].cap < P.bufs[(size_t)best].cap)) best = (int)i;
+    if (best >= 0 && P.bufs[(size_t)best].cap <= 2 * bytes + (1u << 20)) {
+        b = P.bufs[(size_t)best];
+        P.bufs.erase(P.bufs.begin() + best);
         return 0;
     }
     return b.ensure(bytes);
@@ -96,8 +99,10 @@ int pmn_pool_get(pmn_ctx *c, DevBuf &b, size_t bytes)
 void pmn_pool_put(pmn_ctx *c, DevBuf &b)
 {
     if (!b.p) return;
-    if (c->pool.size() >= 64) { b.release(); return; }
-    c->pool.push_back(b);
+    DevPool &P = *c->pool;
+    std::lock_guard<std::mutex> lk(P.mu);
+    if (P.bufs.size() >= 256) { b.release(); return; }
+    P.bufs.push_back(b);
     b.p = nullptr; b.cap = 0;
 }
 
@@ -158,7 +163,7 @@ extern "C" void pmn_ctx_destroy(pmn_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     pmn_scratch_free(c->scratch);
-    for (auto &b : c->pool) b.release();
+    c->pool.reset();
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -212,7 +217,7 @@ extern "C" int pmn_seq_from_fasta(pmn_ctx *c, const char *fasta, size_t bytes, p
     return 0;
 }
 
-static int read_file(const char *path, std::string &out)
+int pmn_read_file(const char *path, std::string &out)
 {
     FILE *f = fopen(path, "rb");
     if (!f) return pmn_set_error(PMN_E_IO, "cannot open %s: %s", path, strerror(errno));
@@ -228,7 +233,7 @@ extern "C" int pmn_seq_from_file(pmn_ctx *c, const char *path, pmn_seq **out)
 {
     if (!path) return pmn_set_error(PMN_E_ARG, "pmn_seq_from_file: NULL path");
     std::string txt;
-    int rc = read_file(path, txt);
+    int rc = pmn_read_file(path, txt);
     if (rc) return rc;
     return pmn_seq_from_fasta(c, txt.data(), txt.size(), out);
 }
@@ -412,13 +417,13 @@ extern "C" int pmn_result_copy_alignments(const pmn_result *r, int64_t *rows, in
 
 // ------------------------------------------------------------------------------------ file level
 
-static int write_file_atomic(const char *path, const std::string &data)
+int pmn_write_file_atomic(const char *path, const char *data, size_t len)
 {
     std::string tmp = std::string(path) + ".tmp." + std::to_string((long)getpid());
     FILE *f = fopen(tmp.c_str(), "wb");
     if (!f) return pmn_set_error(PMN_E_IO, "cannot create %s: %s", tmp.c_str(), strerror(errno));
-    size_t k = fwrite(data.data(), 1, data.size(), f);
-    int bad = (k != data.size()) | (fclose(f) != 0);
+    size_t k = fwrite(data, 1, len, f);
+    int bad = (k != len) | (fclose(f) != 0);
     if (bad) { unlink(tmp.c_str()); return pmn_set_error(PMN_E_IO, "write error on %s", tmp.c_str()); }
     if (rename(tmp.c_str(), path) != 0) { unlink(tmp.c_str()); return pmn_set_error(PMN_E_IO, "cannot rename to %s: %s", path, strerror(errno)); }
     return 0;
@@ -455,7 +460,7 @@ extern "C" int pmn_align_batch(pmn_ctx *c, int n, const char *const *refs, const
         pmn_seq *qs; rc = get_seq(qrys[i], &qs); if (rc) break;
         pmn_result *res = nullptr;
         rc = pmn_align(c, cur_ix, qs, o, refs[i], qrys[i], &res); if (rc) break;
-        rc = write_file_atomic(outs[i], res->delta);
+        rc = pmn_write_file_atomic(outs[i], res->delta.data(), res->delta.size());
         pmn_result_free(res);
     }
     if (cur_ix) pmn_index_free(cur_ix);

@@ -23,12 +23,13 @@
 // band outgrows it), high score / band trimming are warp reductions and ballots.  Integer
 // ALUs only.
 #include <algorithm>
+#include <vector>
 
 #include "pmn_scratch.cuh"
 
 #define EX_RW 256                      /* shared-memory ring width (cells) per score row          */
 #define EX_BAND_SMEM 224                /* widest band kept in shared memory (ring and base caches)  */
-#define EX_SMEM_WARP (EX_ROWS * EX_RW * 4 + 512)   /* bytes per warp: score ring + two 256-base caches */
+#define EX_SMEM_WARP (EX_ROWS * EX_RW * 4 + 512 + 256)   /* bytes per warp: score ring + reference base ring (512 B) + query nibble ring (256 B) */
 #define EX_WCAP (PMN_MAX_ALIGNMENT_LENGTH + 8)   /* global score row capacity                    */
 #define EX_ROWS 12                     /* 3 anti-diagonals x (DEL, INS, MAT, cell max)            */
 #define EX_DMAX (2 * PMN_MAX_ALIGNMENT_LENGTH + 8)
@@ -81,6 +82,7 @@ struct ExShared {                       // everything the device code needs, pas
     const long long *lastP;             // per job g: (piece << 32 | j+1), j = latest job <= g of the same cluster that has deltas
     const uint8_t *anyfail;             // per cluster: some match -> next match job did not reach its target
     unsigned long long *markkey;        // per job: set at the first job of a claimed range
+    int4 *dbg; unsigned dbg_cap;        // PMN_JOBLOG: two int4 per engine call (cursor = counters[15])
 };
 
 // ------------------------------------------------------------------------------------ engine
@@ -91,6 +93,7 @@ struct Eng {
     int32_t *gsc;          // global rows of this warp
     uint8_t *tbp;          // private traceback region
     int lane;
+    int kid;               // 1 = wave 1, 2 = stitcher (job log only)
 };
 
 __device__ __forceinline__ void score_edit(int del, int ins, int mat, int &val, int &used)
@@ -105,170 +108,271 @@ __device__ __forceinline__ int max_state(int vD, int vI, int vM)
     return vI > vM ? PMN_ST_INS : PMN_ST_MAT;
 }
 
-// One alignment.  All 32 lanes call with identical arguments and get identical results.
-// Returns reached (0/1); Aend/Bend become the finish cell.  Unless SEARCH, the deltas are
-// appended to the pool: *doff, *dcnt.
-__device__ int align_engine(const Eng &E, int64_t Abase, int64_t Astart, int64_t &Aend, const PackedView &Q, int64_t Bbase, int64_t Bstart, int64_t &Bend,
-                            unsigned m_o, uint32_t *doff, int32_t *dcnt, int32_t *dasum)
+// ------------------------------------------------------------------------------------ the DP engine
+//
+// Scores are kept multiplied by 4 inside the register path.  The two free low bits carry the
+// state a candidate comes from (DEL 0 < INS 1 < MAT 2), so that one integer maximum yields both
+// the best score and scoreEdit's tie rule (MAT over INS over DEL); each three-way maximum is one
+// IADD + two VIADDMNMX.
+//
+// Register band: column j of the DP belongs to lane (j / K) % 32, register slot j % K, K = 1, 2, 4
+// or 8 consecutive columns per lane.  The 32*K columns form a ring that the band travels along, so
+// nothing is ever shifted between lanes; the only lane-to-lane traffic per anti-diagonal is the
+// rotation of slot K-1 (the left neighbour of slot 0).  Per column the registers hold the previous
+// anti-diagonal (p*) and the one before it at column j-1 (q*, which is simply last step's left
+// neighbour).  K follows the band width; a change of K goes through the shared-memory ring, which
+// is also the hand-over format to the wide fallback (rows in shared / global memory).
+//
+// Bases: one nibble per base (reference: code | 8 when it matches nothing, query: code | 4), so
+// that the XOR of a reference and a query nibble is zero exactly for an identical a/c/g/t pair.
+// The reference nibbles of the K cells of a lane sit in a shift register fed from a shared-memory
+// ring (one LDS per anti-diagonal); the query nibbles of its K columns come from a nibble-packed
+// ring (one LDS).  Both rings are filled 32 bases at a time, one batch ahead of their use.
+
+#define EX_CR 512                       /* base ring entries (reference: bytes, query: nibbles) */
+
+struct EngCtx {                          // warp-uniform progress of one alignment
+    int N, M, dir, breaklen;
+    bool forced, search;
+    int d, tlo, thi, plo, phi, pplo, pphi;
+    int high, best_d, best_j, reached;   // high: plain (unscaled) score
+    unsigned long long cells;
+    uint8_t *tcur, *tend; bool arena_fail;
+    int ca_hi, cb_hi;                    // first unfilled index of the reference / query ring
+    int pa, pb;                          // this lane's nibble of the batch fetched ahead
+    int64_t Apos0, Bpos0;
+};
+
+#define SCR(buf, st, j) ring[((buf) * 4 + (st)) * EX_RW + ((j) & (EX_RW - 1))]
+
+__device__ __forceinline__ int eng_ref_nibble(const ExShared &X, const EngCtx &c, int i)
+{
+    if (i < 1 || i > c.N) return 8;
+    const int b = pmn_base_at(X.R, c.Apos0 + (int64_t)c.dir * (i - 1));
+    return b < 4 ? b : 8;
+}
+__device__ __forceinline__ int eng_qry_nibble(const PackedView &Q, const EngCtx &c, int j)
+{
+    if (j < 1 || j > c.M) return 4;
+    const int b = pmn_base_at(Q, c.Bpos0 + (int64_t)c.dir * (j - 1));
+    return b < 4 ? b : 4;
+}
+
+// write the batch fetched ahead into the ring, fetch the next one
+__device__ __forceinline__ void eng_fill_ref(const ExShared &X, EngCtx &c, uint8_t *ca, int lane)
+{
+    ca[(c.ca_hi + lane) & (EX_CR - 1)] = (uint8_t)c.pa;
+    c.ca_hi += 32;
+    c.pa = eng_ref_nibble(X, c, c.ca_hi + lane);
+    __syncwarp();
+}
+__device__ __forceinline__ void eng_fill_qry(const PackedView &Q, EngCtx &c, uint32_t *cbw, int lane)
+{
+    unsigned v = (unsigned)c.pb << (4 * (lane & 7));
+    v |= __shfl_xor_sync(0xffffffffu, v, 1); v |= __shfl_xor_sync(0xffffffffu, v, 2); v |= __shfl_xor_sync(0xffffffffu, v, 4);
+    if ((lane & 7) == 0) cbw[((c.cb_hi >> 3) + (lane >> 3)) & (EX_CR / 8 - 1)] = v;
+    c.cb_hi += 32;
+    c.pb = eng_qry_nibble(Q, c, c.cb_hi + lane);
+    __syncwarp();
+}
+
+#define ENG_DONE 0
+#define ENG_GROW 1
+#define ENG_SHRINK 2
+
+// Runs anti-diagonals from c.d on with K columns per lane until the alignment ends (ENG_DONE), the
+// band needs more columns (ENG_GROW) or fits half as many (ENG_SHRINK).  Enters and leaves with
+// the two live anti-diagonals in the shared-memory ring (plain scores; rows 0-2 = diagonal d-2,
+// rows 4-6 = diagonal d-1).
+template <int K>
+__device__ __forceinline__ int eng_run_reg(const Eng &E, EngCtx &c, const PackedView &Q, uint8_t **tboff, int32_t *tblo)
+{
+    constexpr int LOGK = K == 1 ? 0 : (K == 2 ? 1 : (K == 4 ? 2 : 3));
+    constexpr int W = 32 * K;
+    constexpr unsigned QMASK = K == 8 ? 0xffffffffu : ((1u << (4 * K)) - 1u);
+    const ExShared &X = *E.X;
+    const int lane = E.lane;
+    extern __shared__ int32_t smem_all[];
+    int32_t *ring = smem_all + (threadIdx.x >> 5) * (EX_SMEM_WARP / 4);
+    uint8_t *ca = (uint8_t *)(ring + EX_ROWS * EX_RW);
+    uint32_t *cbw = (uint32_t *)(ca + EX_CR);
+    const int N = c.N, M = c.M;
+    const int NEG4 = PMN_NEG * 4;
+    const int max_diff4 = 4 * PMN_GOOD_SCORE * c.breaklen;
+    int high4 = c.high * 4;
+
+    int pD[K], pI[K], pM[K], qD[K], qI[K], qM[K], cm[K];
+    int b_cur; unsigned aw = 0;
+    int Bb_last;
+    {   // load the live anti-diagonals into the window of the first anti-diagonal to run
+        const int clo = c.tlo > c.d - N ? c.tlo : c.d - N;
+        const int Bb = (clo - 1) >> LOGK;
+        const int b = Bb + ((lane - Bb) & 31), jbase = b << LOGK;
+#pragma unroll
+        for (int s = 0; s < K; s++) {
+            const int j = jbase + s;
+            const bool pv = j >= c.plo && j <= c.phi, qv = j - 1 >= c.pplo && j - 1 <= c.pphi;
+            pD[s] = pv ? SCR(1, 0, j) * 4 : NEG4; pI[s] = pv ? SCR(1, 1, j) * 4 : NEG4; pM[s] = pv ? SCR(1, 2, j) * 4 : NEG4;
+            qD[s] = qv ? SCR(0, 0, j - 1) * 4 : NEG4; qI[s] = qv ? SCR(0, 1, j - 1) * 4 : NEG4; qM[s] = qv ? SCR(0, 2, j - 1) * 4 : NEG4;
+        }
+        b_cur = b - 64;                 // forces the reference shift register to be primed
+        Bb_last = Bb;
+        __syncwarp();
+    }
+
+    int rc = ENG_DONE;
+    for (;; c.d++) {
+        const int d = c.d;
+        if (!c.forced && d - c.best_d > c.breaklen) break;
+        const int clo = c.tlo > d - N ? c.tlo : d - N, chi = c.thi + 1 < M ? c.thi + 1 : M;
+        if (clo > chi) break;
+        const int span = chi - c.plo + K + 4;
+        if (span > W) { rc = ENG_GROW; break; }
+        if (K > 1 && span + 8 <= W / 2) { rc = ENG_SHRINK; break; }
+        const int width = chi - clo + 1;
+        const int Bb = (clo - 1) >> LOGK;
+        const int b = Bb + ((lane - Bb) & 31), jbase = b << LOGK;
+        Bb_last = Bb;
+        // base rings
+        { const int need_i = d - clo < N ? d - clo : N; while (c.ca_hi <= need_i) eng_fill_ref(X, c, ca, lane); }
+        while (c.cb_hi <= chi + 7) eng_fill_qry(Q, c, cbw, lane);
+        const int i0 = d - jbase;       // reference index of slot 0
+        if (K > 1 && b != b_cur) {
+#pragma unroll
+            for (int s = K - 1; s >= 1; s--) aw = (aw << 4) | ca[(i0 - s) & (EX_CR - 1)];
+        }
+        b_cur = b;
+        aw = (aw << 4) | ca[i0 & (EX_CR - 1)];
+        const unsigned qw = (cbw[(jbase >> 3) & (EX_CR / 8 - 1)] >> (4 * (jbase & 7))) & QMASK;
+        const unsigned x = aw ^ qw;
+        // traceback row
+        uint8_t *trow = nullptr;
+        if (!c.search) {
+            if (c.tcur + W > c.tend) {
+                unsigned long long at = 0;
+                if (lane == 0) at = atomicAdd(X.counters + 1, (unsigned long long)EX_ARENA_CHUNK);
+                at = __shfl_sync(0xffffffffu, at, 0);
+                if (at + EX_ARENA_CHUNK > X.arena_cap) { c.arena_fail = true; break; }
+                c.tcur = X.arena + at; c.tend = c.tcur + EX_ARENA_CHUNK;
+            }
+            trow = c.tcur; c.tcur += W;
+            if (lane == 0) { tboff[d] = trow; tblo[d] = Bb << LOGK; }
+        }
+        // left neighbour of slot 0: slot K-1 of the lane below (ring rotation)
+        int LD = __shfl_sync(0xffffffffu, pD[K - 1], (lane + 31) & 31);
+        int LI = __shfl_sync(0xffffffffu, pI[K - 1], (lane + 31) & 31);
+        int LM = __shfl_sync(0xffffffffu, pM[K - 1], (lane + 31) & 31);
+        unsigned tbw[(K + 3) / 4];
+#pragma unroll
+        for (int w = 0; w < (K + 3) / 4; w++) tbw[w] = 0;
+        const unsigned range = (unsigned)(chi - clo);
+#pragma unroll
+        for (int s = K - 1; s >= 0; s--) {
+            const int j = jbase + s;
+            const bool act = (unsigned)(j - clo) <= range;
+            int lD, lI, lM;
+            if (s > 0) { lD = pD[s - 1]; lI = pI[s - 1]; lM = pM[s - 1]; } else { lD = LD; lI = LI; lM = LM; }
+            const int sc = ((x >> (4 * s)) & 0xfu) ? 4 * PMN_BAD_SCORE : 4 * PMN_GOOD_SCORE;
+            const int mD = __vimax3_s32(lD + (4 * PMN_CONT_GAP_SCORE + PMN_ST_DEL), lI + (4 * PMN_OPEN_GAP_SCORE + PMN_ST_INS), lM + (4 * PMN_OPEN_GAP_SCORE + PMN_ST_MAT));
+            const int mI = __vimax3_s32(pD[s] + (4 * PMN_OPEN_GAP_SCORE + PMN_ST_DEL), pI[s] + (4 * PMN_CONT_GAP_SCORE + PMN_ST_INS), pM[s] + (4 * PMN_OPEN_GAP_SCORE + PMN_ST_MAT));
+            const int mM = __vimax3_s32(qD[s] + sc + PMN_ST_DEL, qI[s] + sc + PMN_ST_INS, qM[s] + sc + PMN_ST_MAT);
+            const int vD = mD & ~3, vI = mI & ~3, vM = mM & ~3;
+            const int mc = __vimax3_s32(vD + PMN_ST_DEL, vI + PMN_ST_INS, vM + PMN_ST_MAT);
+            const unsigned tb = ((unsigned)mD & 3u) | (((unsigned)mI & 3u) << 2) | (((unsigned)mM & 3u) << 4) | (((unsigned)mc & 3u) << 6);
+            tbw[s >> 2] |= tb << (8 * (s & 3));
+            qD[s] = lD; qI[s] = lI; qM[s] = lM;
+            pD[s] = act ? vD : NEG4; pI[s] = act ? vI : NEG4; pM[s] = act ? vM : NEG4;
+            cm[s] = act ? (mc & ~3) : INT32_MIN;
+        }
+        if (!c.search) {
+            uint8_t *dst = trow + (((lane - Bb) & 31) << LOGK);
+            if (K == 1) *dst = (uint8_t)tbw[0];
+            else if (K == 2) *(uint16_t *)dst = (uint16_t)tbw[0];
+            else if (K == 4) *(uint32_t *)dst = tbw[0];
+            else *(uint2 *)dst = make_uint2(tbw[0], tbw[(K + 3) / 4 - 1]);
+        }
+        int lmax = cm[0];
+#pragma unroll
+        for (int s = 1; s < K; s++) lmax = max(lmax, cm[s]);
+        const int cmax = __reduce_max_sync(0xffffffffu, lmax);
+        c.cells += (unsigned long long)width;
+        if (cmax >= high4) {
+            int jm = -1;
+#pragma unroll
+            for (int s = 0; s < K; s++) if (cm[s] == cmax) jm = jbase + s;
+            high4 = cmax; c.best_d = d; c.best_j = __reduce_max_sync(0xffffffffu, jm);
+        }
+        c.pplo = c.plo; c.pphi = c.phi; c.plo = clo; c.phi = chi;
+        if (d == N + M) { c.reached = 1; break; }
+        if (!c.forced) {
+            const int t4 = high4 - max_diff4;
+            bool below = false;
+#pragma unroll
+            for (int s = 0; s < K; s++) below |= (cm[s] < t4) & (cm[s] != INT32_MIN);
+            if (__any_sync(0xffffffffu, below)) {
+                int lo = INT32_MAX, hi = INT32_MIN;
+#pragma unroll
+                for (int s = 0; s < K; s++) if (cm[s] >= t4) { lo = min(lo, jbase + s); hi = jbase + s; }
+                lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
+                if (lo == INT32_MAX) { c.tlo = chi + 1; c.thi = chi; }     // nothing survives: the oracle's loops leave (chi+1, chi)
+                else { c.tlo = lo; c.thi = hi; }
+            } else { c.tlo = clo; c.thi = chi; }
+        } else { c.tlo = clo; c.thi = chi; }
+    }
+    c.high = high4 >> 2;
+    if (rc != ENG_DONE) {
+        // park the two live anti-diagonals in the ring for the next layout
+        const int b = Bb_last + ((lane - Bb_last) & 31), jbase = b << LOGK;
+#pragma unroll
+        for (int s = 0; s < K; s++) {
+            const int j = jbase + s;
+            if (j >= c.plo && j <= c.phi) { SCR(1, 0, j) = pD[s] >> 2; SCR(1, 1, j) = pI[s] >> 2; SCR(1, 2, j) = pM[s] >> 2; }
+            if (j - 1 >= c.pplo && j - 1 <= c.pphi) { SCR(0, 0, j - 1) = qD[s] >> 2; SCR(0, 1, j - 1) = qI[s] >> 2; SCR(0, 2, j - 1) = qM[s] >> 2; }
+        }
+        __syncwarp();
+    }
+    return rc;
+}
+
+// The wide fallback: any band width, rows in the shared-memory ring, then in global memory.
+// Enters with the two live anti-diagonals in the ring.
+__device__ __noinline__ EngCtx eng_run_wide(const Eng &E, EngCtx c, const PackedView &Q, uint8_t **tboff, int32_t *tblo)
 {
     const ExShared &X = *E.X;
     const int lane = E.lane;
-    const int dir = (m_o & PMN_DIRECTION_BIT) ? 1 : -1;
-    const int N = (int)(dir > 0 ? Aend - Astart + 1 : Astart - Aend + 1);
-    const int M = (int)(dir > 0 ? Bend - Bstart + 1 : Bstart - Bend + 1);
-    const bool forced = (m_o & PMN_FORCED_BIT) != 0, search = (m_o & PMN_SEARCH_BIT) != 0;
-    const int breaklen = X.breaklen;
-    const int max_diff = PMN_GOOD_SCORE * breaklen;
-    if (doff) { *doff = 0; *dcnt = 0; *dasum = 0; }
-    if (N < 1 || M < 1 || N > PMN_MAX_ALIGNMENT_LENGTH || M > PMN_MAX_ALIGNMENT_LENGTH) {
-        if (lane == 0) atomicOr(X.counters + 4, (unsigned long long)EX_ERR_LOGIC);
-        return 0;
-    }
-    if (lane == 0) atomicAdd(X.counters + 3, 1ull);
-
-    // score rows: ring in shared memory, or plain rows in global memory once the band is too wide
+    const int N = c.N, M = c.M, dir = c.dir;
+    const int max_diff = PMN_GOOD_SCORE * c.breaklen;
     bool in_smem = true;
-    int32_t *base = E.ssc; int stride = EX_RW; int mask = EX_RW - 1;
+    extern __shared__ int32_t smem_all[];
+    int32_t *base = smem_all + (threadIdx.x >> 5) * (EX_SMEM_WARP / 4); int stride = EX_RW; int mask = EX_RW - 1;
     int bpp = 0, bp = 1, bc = 2;
 #define SC(buf, st, j) base[((buf) * 4 + (st)) * stride + ((j) & mask)]
-
-    uint8_t **tboff = (uint8_t **)E.tbp;
-    int32_t *tblo = (int32_t *)(E.tbp + (size_t)EX_DMAX * 8);
-    int32_t *rev = (int32_t *)(E.tbp + (size_t)EX_DMAX * 12);
-    uint8_t *tcur = E.tbp + EX_TB_HDR, *tend = E.tbp + EX_TBW;     // current traceback chunk (warp-uniform)
-
-    int pplo = 1, pphi = 0, plo = 0, phi = 0, tlo = 0, thi = 0;
-    if (lane == 0 && !search) { tboff[0] = tcur; tblo[0] = 0; tcur[0] = (uint8_t)(PMN_ST_NONE | PMN_ST_NONE << 2 | PMN_ST_NONE << 4 | PMN_ST_MAT << 6); }
-    if (!search) tcur += 32;
-    __syncwarp();
-
-    // base caches in shared memory: A'[i] at ca[i & 255], B'[j] at cb[j & 255], filled 32 bases at a
-    // time as the band advances (one global fetch per lane every 32 anti-diagonals)
-    uint8_t *ca = (uint8_t *)(E.ssc + EX_ROWS * EX_RW), *cb = ca + 256;
-    int ca_hi = 1, cb_hi = 1;                       // next window index to load
-    const int64_t Apos0 = Abase + Astart - 1, Bpos0 = Bbase + Bstart - 1;
-
-    int high = 0, best_d = 0, best_j = 0, reached = 0;
-    unsigned long long cells = 0;
-    bool arena_fail = false;
-    int d = 1;
-    bool general = false;
-
-    // ===== register-band path: while the band is at most 31 columns wide, lane l owns column
-    // J0 + l; the previous anti-diagonal lives in registers (p*), the one before it shifted by one
-    // column (q* = row d-2 at column j-1, which is exactly what was shuffled in as L one step ago)
-    {
-        int J0 = 0;
-        int pD = PMN_NEG, pI = PMN_NEG, pM = lane == 0 ? 0 : PMN_NEG;
-        int qD = PMN_NEG, qI = PMN_NEG, qM = PMN_NEG;
-        int bq = PMN_CODE_X;
-        { const int j = J0 + lane; if (j >= 1 && j <= M) bq = pmn_base_at(Q, Bpos0 + (int64_t)dir * (j - 1)); }
-        for (; d <= N + M; d++) {
-            if (!forced && d - best_d > breaklen) break;
-            const int clo = tlo > d - N ? tlo : d - N, chi = thi + 1 < M ? thi + 1 : M;
-            if (clo > chi) break;
-            const int width = chi - clo + 1;
-            if (width > 31) { general = true; break; }
-            if (chi > J0 + 31) {
-                // slide the window: column clo-1 (still readable as a predecessor) becomes lane 0
-                const int sft = clo - 1 - J0;
-                pD = __shfl_down_sync(0xffffffffu, pD, sft); pI = __shfl_down_sync(0xffffffffu, pI, sft); pM = __shfl_down_sync(0xffffffffu, pM, sft);
-                qD = __shfl_down_sync(0xffffffffu, qD, sft); qI = __shfl_down_sync(0xffffffffu, qI, sft); qM = __shfl_down_sync(0xffffffffu, qM, sft);
-                if (lane + sft > 31) { pD = pI = pM = qD = qI = qM = PMN_NEG; }
-                J0 += sft;
-                const int j = J0 + lane;
-                bq = (j >= 1 && j <= M) ? pmn_base_at(Q, Bpos0 + (int64_t)dir * (j - 1)) : PMN_CODE_X;
-            }
-            {
-                const int need_i = d - clo < N ? d - clo : N;
-                bool filled = false;
-                while (ca_hi <= need_i) { const int i = ca_hi + lane; if (i <= N) ca[i & 255] = (uint8_t)pmn_base_at(X.R, Apos0 + (int64_t)dir * (i - 1)); ca_hi += 32; filled = true; }
-                if (filled) __syncwarp();
-            }
-            uint8_t *trow = nullptr;
-            if (!search) {
-                if (tcur + 32 > tend) {
-                    unsigned long long at = 0;
-                    if (lane == 0) at = atomicAdd(X.counters + 1, (unsigned long long)EX_ARENA_CHUNK);
-                    at = __shfl_sync(0xffffffffu, at, 0);
-                    if (at + EX_ARENA_CHUNK > X.arena_cap) { arena_fail = true; break; }
-                    tcur = X.arena + at; tend = tcur + EX_ARENA_CHUNK;
-                }
-                trow = tcur; tcur += 32;
-                if (lane == 0) { tboff[d] = trow; tblo[d] = J0; }
-            }
-            const int j = J0 + lane, i = d - j;
-            const bool act = j >= clo && j <= chi;
-            int LD = __shfl_up_sync(0xffffffffu, pD, 1), LI = __shfl_up_sync(0xffffffffu, pI, 1), LM = __shfl_up_sync(0xffffffffu, pM, 1);
-            if (lane == 0) { LD = PMN_NEG; LI = PMN_NEG; LM = PMN_NEG; }
-            int sc = PMN_BAD_SCORE;
-            if (act && i >= 1 && j >= 1) { const int a_ = ca[i & 255]; if (a_ == bq && a_ != PMN_CODE_X) sc = PMN_GOOD_SCORE; }
-            int vD, vI, vM, uD, uI, uM;
-            score_edit(LD + PMN_CONT_GAP_SCORE, LI + PMN_OPEN_GAP_SCORE, LM + PMN_OPEN_GAP_SCORE, vD, uD);
-            score_edit(pD + PMN_OPEN_GAP_SCORE, pI + PMN_CONT_GAP_SCORE, pM + PMN_OPEN_GAP_SCORE, vI, uI);
-            score_edit(qD + sc, qI + sc, qM + sc, vM, uM);
-            const int ms = max_state(vD, vI, vM);
-            const int cm = act ? (ms == PMN_ST_DEL ? vD : (ms == PMN_ST_INS ? vI : vM)) : INT32_MIN;
-            if (act && !search) trow[lane] = (uint8_t)(uD | uI << 2 | uM << 4 | ms << 6);
-            qD = LD; qI = LI; qM = LM;
-            pD = act ? vD : PMN_NEG; pI = act ? vI : PMN_NEG; pM = act ? vM : PMN_NEG;
-            const int cmax = __reduce_max_sync(0xffffffffu, cm);
-            const unsigned eq = __ballot_sync(0xffffffffu, cm == cmax);
-            cells += (unsigned long long)width;
-            if (cmax >= high) { high = cmax; best_d = d; best_j = J0 + 31 - __clz((int)eq); }
-            pplo = plo; pphi = phi; plo = clo; phi = chi;
-            if (d == N + M) { reached = 1; break; }
-            if (!forced) {
-                const unsigned bal = __ballot_sync(0xffffffffu, cm >= high - max_diff);
-                if (bal) { tlo = J0 + __ffs(bal) - 1; thi = J0 + 31 - __clz((int)bal); } else { tlo = chi + 1; thi = clo - 1; }
-            } else { tlo = clo; thi = chi; }
-        }
-        if (general) {
-            // the band outgrew the warp: park both rows in the shared-memory ring and continue below
-            const int j = J0 + lane;
-            if (j >= plo && j <= phi) { SC(bp, 0, j) = pD; SC(bp, 1, j) = pI; SC(bp, 2, j) = pM; }
-            if (j - 1 >= pplo && j - 1 <= pphi && j - 1 >= 0) { SC(bpp, 0, j - 1) = qD; SC(bpp, 1, j - 1) = qI; SC(bpp, 2, j - 1) = qM; }
-            if (plo < J0) plo = J0;
-            if (pplo < J0 - 1) pplo = J0 - 1;
-            const int cstart = (tlo > d - N ? tlo : d - N);
-            cb_hi = cstart > 32 ? ((cstart - 32) | 1) : 1;
-            __syncwarp();
-        }
-    }
-
-    // ===== general path: any band width, rows in the shared-memory ring (or global memory)
-    for (; general && d <= N + M; d++) {
-        if (!forced && d - best_d > breaklen) break;
-        const int clo = tlo > d - N ? tlo : d - N, chi = thi + 1 < M ? thi + 1 : M;
+    for (; c.d <= N + M; c.d++) {
+        const int d = c.d;
+        if (!c.forced && d - c.best_d > c.breaklen) break;
+        const int clo = c.tlo > d - N ? c.tlo : d - N, chi = c.thi + 1 < M ? c.thi + 1 : M;
         if (clo > chi) break;
         const int width = chi - clo + 1;
         if (in_smem && width > EX_BAND_SMEM) {
             // move the two live anti-diagonals to global rows and carry on there
             int32_t *g = E.gsc;
-            for (int st = 0; st < 4; st++) {
-                for (int j = plo + lane; j <= phi; j += 32) g[(bp * 4 + st) * EX_WCAP + j] = SC(bp, st, j);
-                for (int j = pplo + lane; j <= pphi; j += 32) g[(bpp * 4 + st) * EX_WCAP + j] = SC(bpp, st, j);
+            for (int st = 0; st < 3; st++) {
+                for (int j = c.plo + lane; j <= c.phi; j += 32) g[(bp * 4 + st) * EX_WCAP + j] = SC(bp, st, j);
+                for (int j = c.pplo + lane; j <= c.pphi; j += 32) g[(bpp * 4 + st) * EX_WCAP + j] = SC(bpp, st, j);
             }
             __syncwarp();
             in_smem = false; base = g; stride = EX_WCAP; mask = -1;
         }
-        if (in_smem) {
-            const int need_i = d - clo < N ? d - clo : N;
-            bool filled = false;
-            while (ca_hi <= need_i) { const int i = ca_hi + lane; if (i <= N) ca[i & 255] = (uint8_t)pmn_base_at(X.R, Apos0 + (int64_t)dir * (i - 1)); ca_hi += 32; filled = true; }
-            while (cb_hi <= chi) { const int j = cb_hi + lane; if (j <= M) cb[j & 255] = (uint8_t)pmn_base_at(Q, Bpos0 + (int64_t)dir * (j - 1)); cb_hi += 32; filled = true; }
-            if (filled) __syncwarp();
-        }
         uint8_t *trow = nullptr;
-        if (!search) {
-            if (tcur + width > tend) {
+        if (!c.search) {
+            if (c.tcur + width > c.tend) {
                 unsigned long long need = width > (int)EX_ARENA_CHUNK ? (unsigned long long)width : EX_ARENA_CHUNK, at = 0;
                 if (lane == 0) at = atomicAdd(X.counters + 1, need);
                 at = __shfl_sync(0xffffffffu, at, 0);
-                if (at + need > X.arena_cap) { arena_fail = true; break; }
-                tcur = X.arena + at; tend = tcur + need;
+                if (at + need > X.arena_cap) { c.arena_fail = true; break; }
+                c.tcur = X.arena + at; c.tend = c.tcur + need;
             }
-            trow = tcur; tcur += width;
+            trow = c.tcur; c.tcur += width;
             if (lane == 0) { tboff[d] = trow; tblo[d] = clo; }
         }
         int dmax = INT32_MIN, dmaxj = -1;
@@ -281,14 +385,12 @@ __device__ int align_engine(const Eng &E, int64_t Abase, int64_t Astart, int64_t
             if (act) {
                 const int i = d - j;
                 int U0 = PMN_NEG, U1 = PMN_NEG, U2 = PMN_NEG, L0 = PMN_NEG, L1 = PMN_NEG, L2 = PMN_NEG, P0 = PMN_NEG, P1 = PMN_NEG, P2 = PMN_NEG;
-                if (j >= plo && j <= phi) { U0 = SC(bp, 0, j); U1 = SC(bp, 1, j); U2 = SC(bp, 2, j); }
-                if (j - 1 >= plo && j - 1 <= phi) { L0 = SC(bp, 0, j - 1); L1 = SC(bp, 1, j - 1); L2 = SC(bp, 2, j - 1); }
-                if (j - 1 >= pplo && j - 1 <= pphi) { P0 = SC(bpp, 0, j - 1); P1 = SC(bpp, 1, j - 1); P2 = SC(bpp, 2, j - 1); }
+                if (j >= c.plo && j <= c.phi) { U0 = SC(bp, 0, j); U1 = SC(bp, 1, j); U2 = SC(bp, 2, j); }
+                if (j - 1 >= c.plo && j - 1 <= c.phi) { L0 = SC(bp, 0, j - 1); L1 = SC(bp, 1, j - 1); L2 = SC(bp, 2, j - 1); }
+                if (j - 1 >= c.pplo && j - 1 <= c.pphi) { P0 = SC(bpp, 0, j - 1); P1 = SC(bpp, 1, j - 1); P2 = SC(bpp, 2, j - 1); }
                 int s = PMN_BAD_SCORE;
                 if (i >= 1 && j >= 1) {
-                    int a_, b_;
-                    if (in_smem) { a_ = ca[i & 255]; b_ = cb[j & 255]; }
-                    else { a_ = pmn_base_at(X.R, Apos0 + (int64_t)dir * (i - 1)); b_ = pmn_base_at(Q, Bpos0 + (int64_t)dir * (j - 1)); }
+                    const int a_ = pmn_base_at(X.R, c.Apos0 + (int64_t)dir * (i - 1)), b_ = pmn_base_at(Q, c.Bpos0 + (int64_t)dir * (j - 1));
                     if (a_ == b_ && a_ != PMN_CODE_X) s = PMN_GOOD_SCORE;
                 }
                 int vD, vI, vM, uD, uI, uM;
@@ -298,7 +400,7 @@ __device__ int align_engine(const Eng &E, int64_t Abase, int64_t Astart, int64_t
                 const int ms = max_state(vD, vI, vM);
                 cm = ms == PMN_ST_DEL ? vD : (ms == PMN_ST_INS ? vI : vM);
                 SC(bc, 0, j) = vD; SC(bc, 1, j) = vI; SC(bc, 2, j) = vM; SC(bc, 3, j) = cm;
-                if (!search) trow[j - clo] = (uint8_t)(uD | uI << 2 | uM << 4 | ms << 6);
+                if (!c.search) trow[j - clo] = (uint8_t)(uD | uI << 2 | uM << 4 | ms << 6);
             }
             if (jb == clo) cm_f = cm;
             if (jb == jb_last) cm_l = cm;
@@ -307,13 +409,14 @@ __device__ int align_engine(const Eng &E, int64_t Abase, int64_t Astart, int64_t
             const unsigned eq = __ballot_sync(0xffffffffu, act && cm == cmax);
             if (cmax >= dmax) { dmax = cmax; dmaxj = jb + 31 - __clz((int)eq); }
         }
-        cells += (unsigned long long)width;
+        c.cells += (unsigned long long)width;
         __syncwarp();
-        if (dmax >= high) { high = dmax; best_d = d; best_j = dmaxj; }
-        if (d == N + M) { reached = 1; break; }
-        if (!forced) {
-            const int t = high - max_diff;
-            int nlo = chi + 1, nhi = clo - 1;
+        if (dmax >= c.high) { c.high = dmax; c.best_d = d; c.best_j = dmaxj; }
+        c.pplo = c.plo; c.pphi = c.phi; c.plo = clo; c.phi = chi;
+        if (d == N + M) { c.reached = 1; break; }
+        if (!c.forced) {
+            const int t = c.high - max_diff;
+            int nlo = chi + 1, nhi = chi;               // nothing survives: the oracle's loops leave (chi+1, chi)
             for (int jb = clo; jb <= chi; jb += 32) {
                 const int j = jb + lane;
                 int v = INT32_MIN;
@@ -330,22 +433,92 @@ __device__ int align_engine(const Eng &E, int64_t Abase, int64_t Astart, int64_t
                     if (bal) { nhi = jb + 31 - __clz((int)bal); break; }
                 }
             }
-            tlo = nlo; thi = nhi;
-        } else { tlo = clo; thi = chi; }
+            c.tlo = nlo; c.thi = nhi;
+        } else { c.tlo = clo; c.thi = chi; }
         { int x = bpp; bpp = bp; bp = bc; bc = x; }
-        pplo = plo; pphi = phi; plo = clo; phi = chi;
     }
 #undef SC
-    if (lane == 0) atomicAdd(X.counters + 2, cells);
-    if (arena_fail) { if (lane == 0) atomicOr(X.counters + 4, (unsigned long long)EX_ERR_ARENA); return 0; }
+    return c;
+}
+
+// One alignment.  All 32 lanes call with identical arguments and get identical results.
+// Returns reached (0/1); Aend/Bend become the finish cell.  Unless SEARCH, the deltas are
+// appended to the pool: *doff, *dcnt.
+__device__ __noinline__ int align_engine(const Eng &E, int64_t Abase, int64_t Astart, int64_t &Aend, const PackedView &Q, int64_t Bbase, int64_t Bstart, int64_t &Bend,
+                                         unsigned m_o, uint32_t *doff, int32_t *dcnt, int32_t *dasum)
+{
+    const ExShared &X = *E.X;
+    const int lane = E.lane;
+    EngCtx c;
+    c.dir = (m_o & PMN_DIRECTION_BIT) ? 1 : -1;
+    const int N = c.N = (int)(c.dir > 0 ? Aend - Astart + 1 : Astart - Aend + 1);
+    const int M = c.M = (int)(c.dir > 0 ? Bend - Bstart + 1 : Bstart - Bend + 1);
+    c.forced = (m_o & PMN_FORCED_BIT) != 0; c.search = (m_o & PMN_SEARCH_BIT) != 0;
+    c.breaklen = X.breaklen;
+    if (doff) { *doff = 0; *dcnt = 0; *dasum = 0; }
+    if (N < 1 || M < 1 || N > PMN_MAX_ALIGNMENT_LENGTH || M > PMN_MAX_ALIGNMENT_LENGTH) {
+        if (lane == 0) atomicOr(X.counters + 4, (unsigned long long)EX_ERR_LOGIC);
+        return 0;
+    }
+    if (lane == 0) atomicAdd(X.counters + 3, 1ull);
+    const long long dbg_t0 = X.dbg ? clock64() : 0;
+
+    uint8_t **tboff = (uint8_t **)E.tbp;
+    int32_t *tblo = (int32_t *)(E.tbp + (size_t)EX_DMAX * 8);
+    int32_t *rev = (int32_t *)(E.tbp + (size_t)EX_DMAX * 12);
+    c.tcur = E.tbp + EX_TB_HDR; c.tend = E.tbp + EX_TBW; c.arena_fail = false;
+    if (lane == 0 && !c.search) { tboff[0] = c.tcur; tblo[0] = 0; c.tcur[0] = (uint8_t)(PMN_ST_NONE | PMN_ST_NONE << 2 | PMN_ST_NONE << 4 | PMN_ST_MAT << 6); }
+    if (!c.search) c.tcur += 32;
+
+    c.Apos0 = Abase + Astart - 1; c.Bpos0 = Bbase + Bstart - 1;
+    c.d = 1; c.tlo = 0; c.thi = 0; c.plo = 0; c.phi = 0; c.pplo = 1; c.pphi = 0;
+    c.high = 0; c.best_d = 0; c.best_j = 0; c.reached = 0; c.cells = 0;
+    {   // cell (0,0) into the ring; base rings: everything in front of the window matches nothing
+        extern __shared__ int32_t smem_all[];
+        int32_t *ring = smem_all + (threadIdx.x >> 5) * (EX_SMEM_WARP / 4);
+        uint8_t *ca = (uint8_t *)(ring + EX_ROWS * EX_RW);
+        uint32_t *cbw = (uint32_t *)(ca + EX_CR);
+        if (lane == 0) { SCR(1, 0, 0) = PMN_NEG; SCR(1, 1, 0) = PMN_NEG; SCR(1, 2, 0) = 0; }
+#pragma unroll
+        for (int k = 0; k < EX_CR / 128; k++) ((uint32_t *)ca)[k * 32 + lane] = 0x08080808u;
+        c.ca_hi = 1; c.pa = eng_ref_nibble(X, c, 1 + lane);
+        c.cb_hi = 0; c.pb = eng_qry_nibble(Q, c, lane);
+        __syncwarp();
+        eng_fill_ref(X, c, ca, lane);
+        eng_fill_qry(Q, c, cbw, lane);
+    }
+
+    int mode = 1, path = 0;
+    for (;;) {
+        int rc;
+        if (mode == 1) rc = eng_run_reg<1>(E, c, Q, tboff, tblo);
+        else if (mode == 2) rc = eng_run_reg<2>(E, c, Q, tboff, tblo);
+        else if (mode == 4) rc = eng_run_reg<4>(E, c, Q, tboff, tblo);
+        else if (mode == 8) rc = eng_run_reg<8>(E, c, Q, tboff, tblo);
+        else { c = eng_run_wide(E, c, Q, tboff, tblo); rc = ENG_DONE; }
+        if (rc == ENG_DONE) break;
+        mode = rc == ENG_GROW ? mode * 2 : mode / 2;
+        if (mode > path) path = mode;
+    }
+    const int d = c.d;
+    if (lane == 0) atomicAdd(X.counters + 2, c.cells);
+    if (X.dbg && lane == 0) {
+        const unsigned long long at = atomicAdd(X.counters + 15, 1ull);
+        if (at < X.dbg_cap) {
+            X.dbg[2 * at] = make_int4((int)m_o, N, M, d);
+            X.dbg[2 * at + 1] = make_int4((int)c.cells, (int)(clock64() - dbg_t0), E.kid, path);
+        }
+    }
+    if (c.arena_fail) { if (lane == 0) atomicOr(X.counters + 4, (unsigned long long)EX_ERR_ARENA); return 0; }
+    const int reached = c.reached;
 
     int fd, fj;
-    if (reached && !(m_o & PMN_OPTIMAL_BIT)) { fd = N + M; fj = M; } else { fd = best_d; fj = best_j; }
+    if (reached && !(m_o & PMN_OPTIMAL_BIT)) { fd = N + M; fj = M; } else { fd = c.best_d; fj = c.best_j; }
     const int fi = fd - fj;
-    Aend = Astart + (int64_t)dir * (fi - 1);
-    Bend = Bstart + (int64_t)dir * (fj - 1);
+    Aend = Astart + (int64_t)c.dir * (fi - 1);
+    Bend = Bstart + (int64_t)c.dir * (fj - 1);
 
-    if (!search) {
+    if (!c.search) {
         __syncwarp();
         int nrev = 0;
         if (lane == 0) {
@@ -372,7 +545,7 @@ __device__ int align_engine(const Eng &E, int64_t Abase, int64_t Astart, int64_t
             at = __shfl_sync(0xffffffffu, at, 0);
             if (at + (unsigned long long)nrev > X.pool_cap) { if (lane == 0) atomicOr(X.counters + 4, (unsigned long long)EX_ERR_POOL); return reached; }
             int asum = 0;
-            for (int k = lane; k < nrev; k += 32) { const int d = rev[nrev - 1 - k]; X.pool[at + k] = d; asum += d > 0 ? d : -d - 1; }
+            for (int k = lane; k < nrev; k += 32) { const int dv = rev[nrev - 1 - k]; X.pool[at + k] = dv; asum += dv > 0 ? dv : -dv - 1; }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) asum += __shfl_xor_sync(0xffffffffu, asum, o);
             *doff = (uint32_t)at; *dcnt = nrev; *dasum = asum;
@@ -381,6 +554,7 @@ __device__ int align_engine(const Eng &E, int64_t Abase, int64_t Astart, int64_t
     }
     return reached;
 }
+
 
 // ------------------------------------------------------------------------------------ postnuc pieces shared by wave 1 and the stitcher
 
@@ -433,13 +607,14 @@ __device__ __forceinline__ Eng make_eng(const ExShared &X, int32_t *smem_all)
     E.ssc = smem_all + (size_t)warp * (EX_SMEM_WARP / 4);
     E.gsc = X.gscore + slot * (size_t)EX_ROWS * EX_WCAP;
     E.tbp = X.tbpriv + slot * (size_t)EX_TBW;
+    E.kid = 0;
     return E;
 }
 
 __global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32) k_ex_wave1(ExShared X)
 {
     extern __shared__ int32_t smem_all[];
-    const Eng E = make_eng(X, smem_all);
+    Eng E = make_eng(X, smem_all); E.kid = 1;
     const int lane = E.lane;
     // pass A: cluster-end extensions (the long ones) first; pass B: match -> next match
     if (X.do_extend) {
@@ -663,7 +838,7 @@ __device__ int st_extend_backward(Stitch &T, int tp, int dirB)
 __global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32) k_ex_stitch(ExShared X, uint8_t *fused)
 {
     extern __shared__ int32_t smem_all[];
-    const Eng E = make_eng(X, smem_all);
+    Eng E = make_eng(X, smem_all); E.kid = 2;
     const int lane = E.lane;
     const int s = blockIdx.x * EX_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     if (s >= X.nS) return;
@@ -1109,13 +1284,19 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     ExCSum *cs = S.cl_l.as<ExCSum>();      // the clustering scratch is free by now
     X.cs = cs;
     PMN_CUDA_OK(cudaMemsetAsync(markkey, 0, 8 * (size_t)(nm + 1), st));
+    const char *joblog = getenv("PMN_JOBLOG");
+    X.dbg = nullptr; X.dbg_cap = 0;
+    if (joblog) {
+        X.dbg_cap = (unsigned)(nm + 4096);
+        if (S.ex_dbg.ensure(32 * (size_t)X.dbg_cap)) return -3;
+        X.dbg = S.ex_dbg.as<int4>();
+    }
 
     const size_t smem = (size_t)EX_WARPS_PER_BLOCK * EX_SMEM_WARP;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!c->smem_attr_set) {
         PMN_CUDA_OK(cudaFuncSetAttribute(k_ex_wave1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PMN_CUDA_OK(cudaFuncSetAttribute(k_ex_stitch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        c->smem_attr_set = true;
     }
     int b1 = blocks1; { int64_t need = (nm + EX_WARPS_PER_BLOCK - 1) / EX_WARPS_PER_BLOCK; if (need < b1) b1 = (int)need; if (b1 < 1) b1 = 1; }
     PMN_CUDA_OK(cudaEventRecord(c->ev[8], st));
@@ -1141,6 +1322,17 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     PMN_D2H(c, hc, X.counters, 128);
     PMN_CUDA_OK(cudaStreamSynchronize(st));
     const unsigned long long errflags = hc[4];
+    if (joblog) {
+        const size_t nrec = (size_t)std::min<unsigned long long>(hc[15], X.dbg_cap);
+        std::vector<int4> rec(2 * nrec);
+        PMN_CUDA_OK(cudaMemcpy(rec.data(), X.dbg, 32 * nrec, cudaMemcpyDeviceToHost));
+        if (FILE *f = fopen(joblog, "a")) {
+            fprintf(f, "# pair nm=%lld nC=%lld  columns: m_o N M d_end cells cycles kernel path\n", (long long)nm, (long long)np);
+            for (size_t k = 0; k < nrec; k++)
+                fprintf(f, "%d %d %d %d %d %d %d %d\n", rec[2 * k].x, rec[2 * k].y, rec[2 * k].z, rec[2 * k].w, rec[2 * k + 1].x, rec[2 * k + 1].y, rec[2 * k + 1].z, rec[2 * k + 1].w);
+            fclose(f);
+        }
+    }
     res->stats.dp_cells = (int64_t)hc[2]; res->stats.dp_jobs = (int64_t)hc[3];
     res->stats.wave1_cells = (int64_t)hc[24];
     cudaEventElapsedTime(&res->stats.ms_wave1, c->ev[8], c->ev[9]);

@@ -1,5 +1,7 @@
 // pmn_host.h — host-side objects behind the C ABI of include/pmnucmer.h.
 #pragma once
+#include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -42,6 +44,12 @@ struct pmn_result {
     std::vector<int32_t> al_deltas;
 };
 
+struct DevPool {
+    std::mutex mu;
+    std::vector<DevBuf> bufs;
+    ~DevPool() { for (auto &b : bufs) b.release(); }
+};
+
 // per-context scratch, all grow-only
 struct Scratch;
 
@@ -54,7 +62,10 @@ struct pmn_ctx {
     Scratch *scratch = nullptr;
     long launches = 0;                  // kernels launched by this library (bench.py's gpu_launches)
     int64_t h2d_bytes = 0, d2h_bytes = 0, pairs = 0;
-    std::vector<DevBuf> pool;           // device buffers handed back by freed sequences / indexes, reused by the next ones
+    std::shared_ptr<DevPool> pool;      // device buffers handed back by freed sequences / indexes, reused by the next ones;
+                                        // the worker contexts of one pmn_sched share one pool (a genome packed or an index
+                                        // built by one worker is freed by whichever worker finishes its last pair)
+    bool smem_attr_set = false;         // opt-in dynamic shared memory of the extension kernels (per device)
 };
 
 // host<->device copies on the context's stream, counted for bench.py's e2e byte figures
@@ -71,5 +82,7 @@ int pmn_index_build_impl(pmn_ctx *c, const pmn_seq *ref, pmn_index *ix);
 int pmn_seed_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_opts *o, int64_t *n_anchors);
 int pmn_cluster_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_opts *o, int64_t n_anchors);
 int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_opts *o, pmn_result *res);
+int pmn_read_file(const char *path, std::string &out);
+int pmn_write_file_atomic(const char *path, const char *data, size_t len);
 Scratch *pmn_scratch_new();
 void pmn_scratch_free(Scratch *s);

@@ -1,0 +1,201 @@
+// pmn_sched.cu — in-process batch scheduler: the unit of work of the reference's fan-out
+// (Nucmer_task.t.searches, /root/reference/lib/base/nucmer_task.ml:6, batched by
+// run_nucmers, lib/base/job_processor.ml:128-154, `-cores N` workers at a time,
+// lib/base/queued_task_server.ml:57-64) run by W worker threads that share one GPU.
+//
+// Every worker owns a context (stream + scratch), so the serial phases of one pair (host
+// round trips between stages, the single-warp stitcher, the tail of the extension wave)
+// overlap with the wide kernels of other pairs.  Genomes are packed once, every reference
+// index is built once by whichever worker needs it first and is shared read-only.
+#include <algorithm>
+#include <atomic>
+#include <map>
+#include <condition_variable>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "pmn_host.h"
+
+namespace {
+
+enum { ST_NONE = 0, ST_BUSY = 1, ST_READY = 2, ST_FAILED = 3 };
+
+struct Slot {                       // a lazily built shared object (packed genome or index)
+    int state = ST_NONE;
+    void *obj = nullptr;
+    int users = 0;                  // pairs that still need it
+};
+
+}  // namespace
+
+struct pmn_sched {
+    int device = 0;
+    std::vector<pmn_ctx *> ctx;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::string err; int err_code = 0;
+};
+
+extern "C" int pmn_sched_create(int device, int workers, pmn_sched **out)
+{
+    if (!out || workers < 1 || workers > 64) return pmn_set_error(PMN_E_ARG, "pmn_sched_create: bad argument");
+    *out = nullptr;
+    pmn_sched *s = new pmn_sched();
+    s->device = device;
+    for (int k = 0; k < workers; k++) {
+        pmn_ctx *c = nullptr;
+        int rc = pmn_ctx_create(device, &c);
+        if (rc) { for (pmn_ctx *x : s->ctx) pmn_ctx_destroy(x); delete s; return rc; }
+        if (!s->ctx.empty()) c->pool = s->ctx[0]->pool;
+        s->ctx.push_back(c);
+    }
+    *out = s;
+    return 0;
+}
+
+extern "C" void pmn_sched_destroy(pmn_sched *s)
+{
+    if (!s) return;
+    for (pmn_ctx *c : s->ctx) pmn_ctx_destroy(c);
+    delete s;
+}
+
+extern "C" int pmn_sched_workers(const pmn_sched *s) { return s ? (int)s->ctx.size() : 0; }
+extern "C" pmn_ctx *pmn_sched_ctx(const pmn_sched *s, int k) { return (s && k >= 0 && k < (int)s->ctx.size()) ? s->ctx[(size_t)k] : nullptr; }
+
+extern "C" void pmn_sched_counters(const pmn_sched *s, int64_t out[4])
+{
+    if (!s || !out) return;
+    out[0] = out[1] = out[2] = out[3] = 0;
+    for (pmn_ctx *c : s->ctx) { int64_t t[4]; pmn_ctx_counters(c, t); for (int k = 0; k < 4; k++) out[k] += t[k]; }
+}
+
+// The common engine: genomes either as host FASTA buffers (packed on demand) or as resident
+// pmn_seq handles; pairs as index pairs into the genome list.
+static int sched_run(pmn_sched *s, int ng, const char *const *fasta, const size_t *bytes, const pmn_seq *const *resident,
+                     const char *const *names, int np, const int32_t *ref, const int32_t *qry, const pmn_opts *opts, pmn_result **out)
+{
+    if (!s || ng < 0 || np < 0 || (np && (!ref || !qry || !out)) || (!fasta && !resident && ng)) return pmn_set_error(PMN_E_ARG, "pmn_sched: bad argument");
+    for (int p = 0; p < np; p++) {
+        out[p] = nullptr;
+        if (ref[p] < 0 || ref[p] >= ng || qry[p] < 0 || qry[p] >= ng) return pmn_set_error(PMN_E_ARG, "pmn_sched: pair %d names a genome out of range", p);
+    }
+    std::vector<Slot> seqs((size_t)ng), idx((size_t)ng);
+    for (int p = 0; p < np; p++) { seqs[(size_t)ref[p]].users++; seqs[(size_t)qry[p]].users++; idx[(size_t)ref[p]].users++; }
+    if (resident) for (int g = 0; g < ng; g++) { seqs[(size_t)g].state = ST_READY; seqs[(size_t)g].obj = (void *)resident[g]; }
+    // pairs in reference order, so that at most a few indexes are alive at a time
+    std::vector<int> order((size_t)np);
+    for (int p = 0; p < np; p++) order[(size_t)p] = p;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ref[a] < ref[b]; });
+    std::atomic<int> next{0};
+    s->err.clear(); s->err_code = 0;
+
+    // get a shared object: build it if nobody has, wait if somebody is
+    auto acquire = [&](std::vector<Slot> &v, int g, auto &&build) -> void * {
+        std::unique_lock<std::mutex> lk(s->mu);
+        Slot &sl = v[(size_t)g];
+        for (;;) {
+            if (sl.state == ST_READY) return sl.obj;
+            if (sl.state == ST_FAILED) return nullptr;
+            if (sl.state == ST_NONE) {
+                sl.state = ST_BUSY;
+                lk.unlock();
+                void *o = build();
+                lk.lock();
+                sl.obj = o; sl.state = o ? ST_READY : ST_FAILED;
+                if (!o && !s->err_code) { s->err_code = PMN_E_INTERNAL; s->err = pmn_last_error(nullptr); }
+                s->cv.notify_all();
+                return o;
+            }
+            s->cv.wait(lk);
+        }
+    };
+
+    auto worker = [&](int w) {
+        pmn_ctx *c = s->ctx[(size_t)w];
+        cudaSetDevice(c->device);
+        for (;;) {
+            { std::lock_guard<std::mutex> lk(s->mu); if (s->err_code) return; }
+            const int k = next.fetch_add(1);
+            if (k >= np) return;
+            const int p = order[(size_t)k], r = ref[p], q = qry[p];
+            auto pack = [&](int g) { return acquire(seqs, g, [&]() -> void * { pmn_seq *x = nullptr; return pmn_seq_from_fasta(c, fasta[g], bytes[g], &x) ? nullptr : (void *)x; }); };
+            pmn_seq *rs = (pmn_seq *)pack(r); if (!rs) return;
+            pmn_seq *qs = (pmn_seq *)pack(q); if (!qs) return;
+            pmn_index *ix = (pmn_index *)acquire(idx, r, [&]() -> void * { pmn_index *x = nullptr; return pmn_index_build(c, rs, &x) ? nullptr : (void *)x; });
+            if (!ix) return;
+            pmn_result *res = nullptr;
+            int rc = pmn_align(c, ix, qs, opts, names ? names[r] : nullptr, names ? names[q] : nullptr, &res);
+            std::lock_guard<std::mutex> lk(s->mu);
+            if (rc) { if (!s->err_code) { s->err_code = rc; s->err = pmn_last_error(nullptr); } return; }
+            out[p] = res;
+            // the last user of an index / of a genome packed by this run frees it
+            if (--idx[(size_t)r].users == 0) { pmn_index_free(ix); idx[(size_t)r].obj = nullptr; idx[(size_t)r].state = ST_NONE; }
+            if (!resident) for (int g : { r, q }) if (--seqs[(size_t)g].users == 0) { pmn_seq_free((pmn_seq *)seqs[(size_t)g].obj); seqs[(size_t)g].obj = nullptr; seqs[(size_t)g].state = ST_NONE; }
+        }
+    };
+
+    const int W = (int)std::min<size_t>(s->ctx.size(), (size_t)std::max(1, np));
+    std::vector<std::thread> th;
+    for (int w = 1; w < W; w++) th.emplace_back(worker, w);
+    worker(0);
+    for (auto &t : th) t.join();
+
+    if (s->err_code) {
+        for (int p = 0; p < np; p++) { pmn_result_free(out[p]); out[p] = nullptr; }
+        for (auto &sl : idx) if (sl.obj) pmn_index_free((pmn_index *)sl.obj);
+        if (!resident) for (auto &sl : seqs) if (sl.obj) pmn_seq_free((pmn_seq *)sl.obj);
+        return pmn_set_error(s->err_code, "%s", s->err.c_str());
+    }
+    return 0;
+}
+
+extern "C" int pmn_sched_align_fasta(pmn_sched *s, int n_genomes, const char *const *fasta, const size_t *bytes, const char *const *names,
+                                     int n_pairs, const int32_t *ref, const int32_t *qry, const pmn_opts *o, pmn_result **out)
+{
+    if (n_genomes && (!fasta || !bytes)) return pmn_set_error(PMN_E_ARG, "pmn_sched_align_fasta: NULL genome list");
+    return sched_run(s, n_genomes, fasta, bytes, nullptr, names, n_pairs, ref, qry, o, out);
+}
+
+extern "C" int pmn_sched_align_seqs(pmn_sched *s, int n_genomes, const pmn_seq *const *seqs, const char *const *names,
+                                    int n_pairs, const int32_t *ref, const int32_t *qry, const pmn_opts *o, pmn_result **out)
+{
+    if (!s || (n_genomes && !seqs)) return pmn_set_error(PMN_E_ARG, "pmn_sched_align_seqs: NULL argument");
+    for (int g = 0; g < n_genomes; g++) if (!seqs[g] || seqs[g]->ctx->device != s->device) return pmn_set_error(PMN_E_ARG, "pmn_sched_align_seqs: genome %d is not resident on device %d", g, s->device);
+    return sched_run(s, n_genomes, nullptr, nullptr, seqs, names, n_pairs, ref, qry, o, out);
+}
+
+// File level, one call per Nucmer_task.t.searches (lib/base/nucmer_task.ml:6,48-59): every distinct
+// FASTA is read and packed once, every .delta is written atomically (tmp + rename).
+extern "C" int pmn_sched_align_files(pmn_sched *s, int n, const char *const *ref_fasta_paths, const char *const *qry_fasta_paths,
+                                     const char *const *out_delta_paths, const pmn_opts *o)
+{
+    if (!s || n < 0 || (n && (!ref_fasta_paths || !qry_fasta_paths || !out_delta_paths))) return pmn_set_error(PMN_E_ARG, "pmn_sched_align_files: bad argument");
+    std::map<std::string, int> id;
+    std::vector<std::string> text; std::vector<const char *> names;
+    std::vector<int32_t> ref((size_t)n), qry((size_t)n);
+    auto genome = [&](const char *path, int32_t *g) -> int {
+        if (!path) return pmn_set_error(PMN_E_ARG, "pmn_sched_align_files: NULL path");
+        auto it = id.find(path);
+        if (it == id.end()) {
+            std::string t; int rc = pmn_read_file(path, t); if (rc) return rc;
+            it = id.emplace(path, (int)text.size()).first; text.push_back(std::move(t)); names.push_back(path);
+        }
+        *g = it->second; return 0;
+    };
+    for (int i = 0; i < n; i++) {
+        int rc = genome(ref_fasta_paths[i], &ref[(size_t)i]); if (rc) return rc;
+        rc = genome(qry_fasta_paths[i], &qry[(size_t)i]); if (rc) return rc;
+        if (!out_delta_paths[i]) return pmn_set_error(PMN_E_ARG, "pmn_sched_align_files: NULL output path");
+    }
+    std::vector<const char *> fa(text.size()); std::vector<size_t> nb(text.size());
+    for (size_t g = 0; g < text.size(); g++) { fa[g] = text[g].data(); nb[g] = text[g].size(); }
+    std::vector<pmn_result *> res((size_t)n, nullptr);
+    int rc = sched_run(s, (int)text.size(), fa.data(), nb.data(), nullptr, names.data(), n, ref.data(), qry.data(), o, res.data());
+    for (int i = 0; i < n && !rc; i++) { size_t len; const char *d = pmn_result_delta(res[(size_t)i], &len); rc = pmn_write_file_atomic(out_delta_paths[i], d, len); }
+    for (pmn_result *r : res) pmn_result_free(r);
+    return rc;
+}

@@ -51,6 +51,8 @@ SYMBOLS = [
     "pmn_result_n_anchors", "pmn_result_copy_anchors", "pmn_result_n_clusters",
     "pmn_result_n_cluster_matches", "pmn_result_copy_clusters", "pmn_result_n_alignments",
     "pmn_result_n_deltas", "pmn_result_copy_alignments",
+    "pmn_sched_create", "pmn_sched_destroy", "pmn_sched_workers", "pmn_sched_ctx", "pmn_sched_counters",
+    "pmn_sched_align_fasta", "pmn_sched_align_seqs", "pmn_sched_align_files",
 ]
 
 
@@ -94,6 +96,15 @@ def lib():
         L.pmn_result_copy_anchors.argtypes = [vp, vp]
         L.pmn_result_copy_clusters.argtypes = [vp, vp, vp, vp]
         L.pmn_result_copy_alignments.argtypes = [vp, vp, vp, vp]
+        i32a = C.POINTER(C.c_int32)
+        L.pmn_sched_create.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]
+        L.pmn_sched_destroy.argtypes = [vp]
+        L.pmn_sched_workers.argtypes = [vp]
+        L.pmn_sched_ctx.argtypes = [vp, C.c_int]; L.pmn_sched_ctx.restype = vp
+        L.pmn_sched_counters.argtypes = [vp, i64p]
+        L.pmn_sched_align_fasta.argtypes = [vp, C.c_int, C.POINTER(cp), C.POINTER(C.c_size_t), C.POINTER(cp), C.c_int, i32a, i32a, C.POINTER(Opts), C.POINTER(vp)]
+        L.pmn_sched_align_seqs.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(cp), C.c_int, i32a, i32a, C.POINTER(Opts), C.POINTER(vp)]
+        L.pmn_sched_align_files.argtypes = [vp, C.c_int, C.POINTER(cp), C.POINTER(cp), C.POINTER(cp), C.POINTER(Opts)]
         _LIB = L
     return _LIB
 
@@ -122,9 +133,9 @@ class Context:
         self.device = device
 
     def close(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and not getattr(self, "borrowed", False):
             lib().pmn_ctx_destroy(self.h)
-            self.h = None
+        self.h = None
 
     def __enter__(self):
         return self
@@ -152,6 +163,70 @@ class Context:
 
     def sequence_from_file(self, path: str):
         return Sequence(self, path=path)
+
+
+class Scheduler:
+    """W worker threads sharing one GPU (pmn_sched): the in-process form of the reference's
+    run_nucmers fan-out (lib/base/job_processor.ml:128-154)."""
+
+    def __init__(self, device=0, workers=4):
+        self.h = C.c_void_p()
+        _check(lib().pmn_sched_create(device, workers, C.byref(self.h)))
+        self.device, self.workers = device, workers
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().pmn_sched_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def counters(self):
+        out = (C.c_int64 * 4)()
+        lib().pmn_sched_counters(self.h, out)
+        return {"launches": out[0], "h2d_bytes": out[1], "d2h_bytes": out[2], "pairs": out[3]}
+
+    def context(self, k=0):
+        """Worker k's context as a borrowed Context (do not close it)."""
+        c = Context.__new__(Context)
+        c.h = C.c_void_p(lib().pmn_sched_ctx(self.h, k)); c.device = self.device; c.borrowed = True
+        return c
+
+    @staticmethod
+    def _pairs(pairs):
+        n = len(pairs)
+        return n, (C.c_int32 * n)(*[p[0] for p in pairs]), (C.c_int32 * n)(*[p[1] for p in pairs])
+
+    def align_fasta(self, fastas, pairs, names=None, opts=None, **kw):
+        """fastas: list of FASTA bytes in host memory; pairs: [(ref index, qry index)] -> [Result]."""
+        o = opts if opts is not None else default_opts(**kw)
+        g = len(fastas)
+        fa = (C.c_char_p * g)(*fastas); nb = (C.c_size_t * g)(*[len(f) for f in fastas])
+        nm = (C.c_char_p * g)(*[os.fsencode(x) for x in names]) if names else None
+        n, r, q = self._pairs(pairs)
+        out = (C.c_void_p * n)()
+        _check(lib().pmn_sched_align_fasta(self.h, g, fa, nb, nm, n, r, q, C.byref(o), out))
+        return [Result(C.c_void_p(h)) for h in out]
+
+    def align_seqs(self, seqs, pairs, names=None, opts=None, **kw):
+        """seqs: list of Sequence objects resident on this GPU."""
+        o = opts if opts is not None else default_opts(**kw)
+        g = len(seqs)
+        sh = (C.c_void_p * g)(*[s.h for s in seqs])
+        nm = (C.c_char_p * g)(*[os.fsencode(x) for x in names]) if names else None
+        n, r, q = self._pairs(pairs)
+        out = (C.c_void_p * n)()
+        _check(lib().pmn_sched_align_seqs(self.h, g, sh, nm, n, r, q, C.byref(o), out))
+        return [Result(C.c_void_p(h)) for h in out]
+
+    def align_files(self, refs, qrys, outs, opts=None, **kw):
+        o = opts if opts is not None else default_opts(**kw)
+        arr = lambda xs: (C.c_char_p * len(xs))(*[os.fsencode(x) for x in xs])
+        _check(lib().pmn_sched_align_files(self.h, len(refs), arr(refs), arr(qrys), arr(outs), C.byref(o)))
 
 
 class Sequence:

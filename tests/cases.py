@@ -101,7 +101,29 @@ def c_self():
     return synth.fasta("ref.1", g), synth.fasta("qry.1", g), {"do_simplify": 0}
 
 
+def c_trim_everything():
+    # homopolymer tails that share nothing: extensions out of the last / first cluster run into
+    # A-against-C, every cell falls below the trimming threshold before the break length is reached
+    g = synth.random_genome(3_000, 271)
+    return (synth.fasta("ref.1", b"A" * 1_500 + g + b"A" * 1_500), synth.fasta("qry.1", b"C" * 1_500 + synth.mutate(g, 0.02, 272) + b"C" * 1_500), {})
+
+
+def c_wide_band_b500():
+    # a long break length keeps bands several hundred cells wide: register layouts up to 8 columns
+    # per lane and the shared/global-memory fallback
+    return (*_pair(30_000, 0.13, 281, inv=1, inv_len=3_000), {"breaklen": 500})
+
+
+def c_gap_ladder():
+    # gaps of growing size between exact blocks: band widths cross every layout boundary, both ways
+    blocks = [synth.random_genome(120, 300 + k) for k in range(40)]
+    junk_r = [synth.random_genome(4 * k, 400 + k) for k in range(40)]
+    junk_q = [synth.random_genome(3 * k + 1, 500 + k) for k in range(40)]
+    ref = b"".join(b + j for b, j in zip(blocks, junk_r)); qry = b"".join(b + j for b, j in zip(blocks, junk_q))
+    return synth.fasta("ref.1", ref), synth.fasta("qry.1", qry), {}
+
+
 CASES = {f.__name__[2:]: f for f in (
     c_1k_99, c_10k_95, c_100k_98_inv, c_100k_90, c_60k_85, c_identical, c_unrelated, c_short_and_empty, c_n_runs,
     c_multirecord, c_repeats, c_tandem_low_complexity, c_big_indels, c_opts_l12_c30, c_opts_forward_only_noextend,
-    c_opts_nosimplify_diag, c_self)}
+    c_opts_nosimplify_diag, c_self, c_trim_everything, c_wide_band_b500, c_gap_ladder)}

@@ -159,3 +159,36 @@ def test_error_paths(ctx):
     with pytest.raises(lib.PmnError):
         ix.align(rs, minmatch=0)
     ix.close(); rs.close()
+
+
+def test_scheduler_results_do_not_depend_on_workers(oracle, tmp_path):
+    """pmn_sched: the in-process form of run_nucmers (lib/base/job_processor.ml:128-154).  Several
+    pairs in flight on one GPU, shared indexes; every .delta equals the oracle's whatever the
+    number of workers, from host FASTA bytes, from resident genomes and from files."""
+    from paramugsy_b200 import lib
+    gs = synth.config_c2(n=80_000, count=5, inv_len=2_500)
+    fastas = [synth.fasta(n, s) for n, s in gs]
+    names = [n for n, _ in gs]
+    pairs = [(i, j) for i in range(5) for j in range(i + 1, 5)] + [(2, 2)]
+    want = [oracle.nucmer(fastas[i], fastas[j], names[i], names[j], fast_chain=1) for i, j in pairs]
+    for workers in (1, 3):
+        with lib.Scheduler(0, workers) as s:
+            res = s.align_fasta(fastas, pairs, names=names)
+            assert [r.delta for r in res] == want
+            assert s.counters()["pairs"] == len(pairs) and s.counters()["launches"] > 0
+            c = s.context(0)
+            seqs = [c.sequence(f) for f in fastas]
+            res = s.align_seqs(seqs, pairs, names=names)
+            assert [r.delta for r in res] == want
+            for q in seqs:
+                q.close()
+            paths = []
+            for n, f in zip(names, fastas):
+                p = tmp_path / f"{workers}_{n}.fa"; p.write_bytes(f); paths.append(str(p))
+            outs = [str(tmp_path / f"{workers}_{i}_{j}.delta") for i, j in pairs]
+            s.align_files([paths[i] for i, _ in pairs], [paths[j] for _, j in pairs], outs)
+            for (i, j), o in zip(pairs, outs):
+                assert open(o, "rb").read() == oracle.nucmer(fastas[i], fastas[j], paths[i], paths[j], fast_chain=1)
+            with pytest.raises(lib.PmnError):
+                s.align_fasta(fastas[:2] + [b"not fasta"], [(0, 1), (0, 2)])
+            assert [r.delta for r in s.align_fasta(fastas, pairs[:3], names=names)] == want[:3]     # usable after an error
