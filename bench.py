@@ -108,23 +108,22 @@ def run_gpu(args):
     ctx = sched.context(0)
 
     genomes, fastas, pairs = workload(args)
-    my_pairs = pairs
-    if args.mode == "strong" and world > 1:
-        # group by reference, deal the references to the ranks largest-first
-        by_ref = {}
-        for p in pairs:
-            by_ref.setdefault(p[0], []).append(p)
-        load = [0] * world; mine = []
-        for r, ps in sorted(by_ref.items(), key=lambda kv: -len(kv[1])):
-            k = load.index(min(load)); load[k] += len(ps)
-            if k == rank:
-                mine += ps
-        my_pairs = mine
-    refs = sorted({i for i, _ in my_pairs})
-    total_bp_in = sum(len(genomes[i][1]) + len(genomes[j][1]) for i, j in my_pairs)
-
     names = [g[0] for g in genomes]
     fasta_bytes = [f[1] for f in fastas]
+    strong = args.mode == "strong" and world > 1
+    if strong:
+        # the 28 pairs are dealt to the ranks; every reference index is built once in the whole job and
+        # replicated to the ranks that need it by an NCCL broadcast of its image (paramugsy_b200/multi.py)
+        from paramugsy_b200 import multi
+        assignment = multi.assign_pairs(pairs, world)
+        plan = multi.index_plan(pairs, assignment)
+        my_pairs = [pairs[k] for k in assignment[rank]]
+        needed = sorted({g for p in my_pairs for g in p} | {ref for ref, (o, rs) in plan.items() if o == rank or rank in rs})
+    else:
+        my_pairs = pairs
+        needed = list(range(len(genomes)))
+    refs = sorted({i for i, _ in my_pairs})
+    total_bp_in = sum(len(genomes[i][1]) + len(genomes[j][1]) for i, j in my_pairs)
 
     def step_resident(seqs, collect=None, one_worker=None):
         """One pass of the hot path over the batch, genomes already packed in HBM: every reference
@@ -139,11 +138,22 @@ def run_gpu(args):
                         res.close()
                 ix.close()
             return
+        if strong:
+            out = multi.AllVsAll(sched, [seqs.get(g) for g in range(len(genomes))], names, pairs, rank, world, dist).step()
+            for res in out.values():
+                res.close()
+            return
         for res in sched.align_seqs([seqs[g] for g in range(len(genomes))], my_pairs, names=names):
             res.close()
 
     def step_e2e():
         """The same from FASTA bytes in host memory (parse, H2D, pack inside)."""
+        if strong:
+            seqs = {g: ctx.sequence(fasta_bytes[g]) for g in needed}
+            step_resident(seqs)
+            for q in seqs.values():
+                q.close()
+            return
         for res in sched.align_fasta(fasta_bytes, my_pairs, names=names):
             res.close()
 
@@ -174,7 +184,7 @@ def run_gpu(args):
         return ms, d
 
     # ---- resident arm
-    resident = {g: ctx.sequence(fastas[g][1]) for g in range(len(genomes))}
+    resident = {g: ctx.sequence(fastas[g][1]) for g in needed}
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()          # before the warm-up: nvidia-smi's own start-up must not land in the timed region

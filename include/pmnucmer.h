@@ -97,12 +97,28 @@ int  pmn_seq_records(const pmn_seq *s);
 /* ---- index of a reference (kept by the caller while it aligns queries against it) ---- */
 int  pmn_index_build(pmn_ctx *c, const pmn_seq *ref, pmn_index **out);
 void pmn_index_free(pmn_index *ix);
+/* Replication across GPUs (north_star: "the reference index is replicated with an NCCL broadcast over
+ * NVLink").  An index is ONE contiguous image in HBM (header, SA, LCP, k-mer table): the owner hands
+ * {pointer, size} to the collective, a receiver allocates an empty index for its own packed copy of the
+ * same reference, receives into the image in place and calls pmn_index_adopt to validate the header. */
+int  pmn_index_image(const pmn_index *ix, void **dev_ptr, size_t *bytes);
+size_t pmn_index_image_bytes(int64_t n_bases);      /* image size for a reference of n_bases (incl. separators) */
+int  pmn_index_alloc(pmn_ctx *c, const pmn_seq *ref, pmn_index **out);
+int  pmn_index_adopt(pmn_index *ix);
 
 /* ---- one pair: seeding, clustering, extension, .delta text (host memory) ----
  * ref_path / qry_path are only echoed on line 1 of the .delta
  * (lib/profiles/m_delta.ml:56 splits it on the last space). */
 int  pmn_align(pmn_ctx *c, const pmn_index *ix, const pmn_seq *qry, const pmn_opts *o,
                const char *ref_path, const char *qry_path, pmn_result **out);
+/* One large pair on G GPUs: index and query are replicated, part k of G seeds the
+ * query positions of its range and leaves its anchors (int32 x4: ref pos, query pos, length, tag) in the
+ * context's scratch; the parts' lists concatenated in part order (an all-gather) are exactly the anchor
+ * list of the undivided run, from which pmn_align_anchors continues (clustering, extension, .delta). */
+int  pmn_seed_part(pmn_ctx *c, const pmn_index *ix, const pmn_seq *qry, const pmn_opts *o, int part, int nparts,
+                   void **dev_anchors, int64_t *n_anchors);
+int  pmn_align_anchors(pmn_ctx *c, const pmn_index *ix, const pmn_seq *qry, const pmn_opts *o, const void *dev_anchors, int64_t n_anchors,
+                       const char *ref_path, const char *qry_path, pmn_result **out);
 const char *pmn_result_delta(const pmn_result *r, size_t *len);
 void pmn_result_stats(const pmn_result *r, pmn_stats *out);
 void pmn_result_free(pmn_result *r);
@@ -139,6 +155,10 @@ int  pmn_sched_align_fasta(pmn_sched *s, int n_genomes, const char *const *fasta
 /* genomes already packed in HBM (any context of the scheduler's device) */
 int  pmn_sched_align_seqs(pmn_sched *s, int n_genomes, const pmn_seq *const *seqs, const char *const *names,
                           int n_pairs, const int32_t *ref, const int32_t *qry, const pmn_opts *o, pmn_result **out);
+/* the same with some reference indexes supplied by the caller (indexes[g] may be NULL): built earlier, or
+ * received from the GPU that built them (pmn_index_alloc / pmn_index_adopt); they are never freed here */
+int  pmn_sched_align_indexed(pmn_sched *s, int n_genomes, const pmn_seq *const *seqs, const pmn_index *const *indexes, const char *const *names,
+                             int n_pairs, const int32_t *ref, const int32_t *qry, const pmn_opts *o, pmn_result **out);
 /* genomes and results as files: one call per Nucmer_task.t.searches */
 int  pmn_sched_align_files(pmn_sched *s, int n, const char *const *ref_fasta_paths, const char *const *qry_fasta_paths,
                            const char *const *out_delta_paths, const pmn_opts *o);

@@ -259,7 +259,7 @@ extern "C" int pmn_index_build(pmn_ctx *c, const pmn_seq *ref, pmn_index **out)
     const double t0 = now_ms();
     int rc = pmn_index_build_impl(c, ref, ix.get());
     ix->wall_ms_build = (float)(now_ms() - t0);
-    if (rc) { ix->sa.release(); ix->lcp.release(); ix->table.release(); return rc; }
+    if (rc) { ix->blob.release(); return rc; }
     *out = ix.release();
     return 0;
 }
@@ -268,18 +268,54 @@ extern "C" void pmn_index_free(pmn_index *ix)
 {
     if (!ix) return;
     cudaSetDevice(ix->ctx->device);
-    pmn_pool_put(ix->ctx, ix->sa); pmn_pool_put(ix->ctx, ix->lcp); pmn_pool_put(ix->ctx, ix->table);
+    pmn_pool_put(ix->ctx, ix->blob);
     delete ix;
 }
 
 extern "C" int64_t pmn_index_size(const pmn_index *ix) { return ix ? ix->n : 0; }
 
+// ---- replication of an index (multi-GPU): the image is one contiguous range of HBM, so a
+// collective can send / receive it in place
+extern "C" int pmn_index_image(const pmn_index *ix, void **dev_ptr, size_t *bytes)
+{
+    if (!ix || !dev_ptr || !bytes) return pmn_set_error(PMN_E_ARG, "pmn_index_image: NULL argument");
+    *dev_ptr = ix->blob.p; *bytes = ix->blob_bytes;
+    return 0;
+}
+
+extern "C" int pmn_index_alloc(pmn_ctx *c, const pmn_seq *ref, pmn_index **out)
+{
+    if (!c || !ref || !out) return pmn_set_error(PMN_E_ARG, "pmn_index_alloc: NULL argument");
+    *out = nullptr;
+    PMN_CUDA_OK(cudaSetDevice(c->device));
+    std::unique_ptr<pmn_index> ix(new pmn_index());
+    int rc = pmn_index_layout(c, ref, ix.get());
+    if (rc) return rc;
+    PMN_CUDA_OK(cudaMemsetAsync(ix->blob.p, 0, 256, c->stream));
+    PMN_CUDA_OK(cudaStreamSynchronize(c->stream));
+    *out = ix.release();
+    return 0;
+}
+
+extern "C" int pmn_index_adopt(pmn_index *ix)
+{
+    if (!ix) return pmn_set_error(PMN_E_ARG, "pmn_index_adopt: NULL index");
+    PMN_CUDA_OK(cudaSetDevice(ix->ctx->device));
+    PmnIndexHeader h;
+    PMN_CUDA_OK(cudaMemcpy(&h, ix->blob.p, sizeof h, cudaMemcpyDeviceToHost));
+    if (h.magic != PMN_INDEX_MAGIC || h.n != ix->n || h.K != ix->K)
+        return pmn_set_error(PMN_E_ARG, "pmn_index_adopt: the received image does not belong to this reference (n %lld vs %lld, K %d vs %d)",
+                             (long long)h.n, (long long)ix->n, h.K, ix->K);
+    ix->rounds = h.rounds;
+    return 0;
+}
+
 extern "C" int pmn_index_copy_sa(const pmn_index *ix, int32_t *sa_out, int32_t *lcp_out)
 {
     if (!ix) return pmn_set_error(PMN_E_ARG, "pmn_index_copy_sa: NULL index");
     PMN_CUDA_OK(cudaSetDevice(ix->ctx->device));
-    if (sa_out) PMN_CUDA_OK(cudaMemcpy(sa_out, ix->sa.p, 4 * (size_t)ix->n, cudaMemcpyDeviceToHost));
-    if (lcp_out) PMN_CUDA_OK(cudaMemcpy(lcp_out, ix->lcp.p, 4 * (size_t)ix->n, cudaMemcpyDeviceToHost));
+    if (sa_out) PMN_CUDA_OK(cudaMemcpy(sa_out, ix->sa(), 4 * (size_t)ix->n, cudaMemcpyDeviceToHost));
+    if (lcp_out) PMN_CUDA_OK(cudaMemcpy(lcp_out, ix->lcp(), 4 * (size_t)ix->n, cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -332,15 +368,21 @@ static void write_delta_text(const pmn_seq *ref, const pmn_seq *qry, const char 
     r->stats.aligned_ref_bases = aligned;
 }
 
-extern "C" int pmn_align(pmn_ctx *c, const pmn_index *ix, const pmn_seq *qry, const pmn_opts *o_in,
-                         const char *ref_path, const char *qry_path, pmn_result **out)
+static int check_opts(const pmn_opts *o_in, pmn_opts &o)
 {
-    if (!c || !ix || !qry || !out) return pmn_set_error(PMN_E_ARG, "pmn_align: NULL argument");
-    *out = nullptr;
-    pmn_opts o; if (o_in) o = *o_in; else pmn_default_opts(&o);
+    if (o_in) o = *o_in; else pmn_default_opts(&o);
     if (!o.do_optimize) return pmn_set_error(PMN_E_ARG, "--nooptimize is not supported");
     if (o.minmatch < 1 || o.maxgap < 0 || o.breaklen < 1 || o.mincluster < 0 || o.diagdiff < 0 || o.diagfactor < 0)
         return pmn_set_error(PMN_E_ARG, "pmn_align: option out of range");
+    return 0;
+}
+
+// seeding (unless the anchors are given), clustering, extension, .delta text
+static int align_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *qry, const pmn_opts *o_in, const void *given_anchors, int64_t n_given,
+                      const char *ref_path, const char *qry_path, pmn_result **out)
+{
+    *out = nullptr;
+    pmn_opts o; { int rc = check_opts(o_in, o); if (rc) return rc; }
     PMN_CUDA_OK(cudaSetDevice(c->device));
     Scratch &S = *c->scratch;
     cudaStream_t st = c->stream;
@@ -352,8 +394,17 @@ extern "C" int pmn_align(pmn_ctx *c, const pmn_index *ix, const pmn_seq *qry, co
 
     PMN_CUDA_OK(cudaEventRecord(c->ev[2], st));
     int64_t nanc = 0;
-    int rc = pmn_seed_impl(c, ix, qry, &o, &nanc);
-    if (rc) return rc;
+    int rc = 0;
+    if (given_anchors || n_given == 0) {
+        nanc = n_given;
+        if (nanc > 0 && given_anchors != S.anchors.p) {
+            if (S.anchors.ensure(16 * (size_t)nanc)) return -3;
+            PMN_CUDA_OK(cudaMemcpyAsync(S.anchors.p, given_anchors, 16 * (size_t)nanc, cudaMemcpyDeviceToDevice, st));
+        }
+    } else {
+        rc = pmn_seed_impl(c, ix, qry, &o, &nanc);
+        if (rc) return rc;
+    }
     PMN_CUDA_OK(cudaEventRecord(c->ev[3], st));
     r->stats.anchors = nanc;
     if (o.keep_stages && nanc > 0) {
@@ -372,7 +423,7 @@ extern "C" int pmn_align(pmn_ctx *c, const pmn_index *ix, const pmn_seq *qry, co
     cudaEventElapsedTime(&r->stats.ms_cluster, c->ev[3], c->ev[4]);
     cudaEventElapsedTime(&r->stats.ms_extend, c->ev[4], c->ev[5]);
     cudaEventElapsedTime(&r->stats.ms_total, c->ev[2], c->ev[5]);
-    if (nanc >= 0 && qry->n >= o.minmatch) { if (cudaEventElapsedTime(&r->stats.ms_seed_kernel, c->ev[6], c->ev[7]) != cudaSuccess) { cudaGetLastError(); r->stats.ms_seed_kernel = 0; } }
+    if (!given_anchors && n_given != 0 && qry->n >= o.minmatch) { if (cudaEventElapsedTime(&r->stats.ms_seed_kernel, c->ev[6], c->ev[7]) != cudaSuccess) { cudaGetLastError(); r->stats.ms_seed_kernel = 0; } }
     c->pairs++;
     const double t1 = now_ms();
     write_delta_text(ix->seq, qry, ref_path ? ref_path : "ref", qry_path ? qry_path : "qry", r.get());
@@ -382,6 +433,34 @@ extern "C" int pmn_align(pmn_ctx *c, const pmn_index *ix, const pmn_seq *qry, co
     r->stats.wall_ms_index = ix->wall_ms_build;
     *out = r.release();
     return 0;
+}
+
+extern "C" int pmn_align(pmn_ctx *c, const pmn_index *ix, const pmn_seq *qry, const pmn_opts *o_in,
+                         const char *ref_path, const char *qry_path, pmn_result **out)
+{
+    if (!c || !ix || !qry || !out) return pmn_set_error(PMN_E_ARG, "pmn_align: NULL argument");
+    return align_impl(c, ix, qry, o_in, nullptr, -1, ref_path, qry_path, out);
+}
+
+// ---- one large pair on several GPUs: the query positions are sharded, everything else is replicated
+extern "C" int pmn_seed_part(pmn_ctx *c, const pmn_index *ix, const pmn_seq *qry, const pmn_opts *o_in, int part, int nparts,
+                             void **dev_anchors, int64_t *n_anchors)
+{
+    if (!c || !ix || !qry || !dev_anchors || !n_anchors || nparts < 1 || part < 0 || part >= nparts) return pmn_set_error(PMN_E_ARG, "pmn_seed_part: bad argument");
+    pmn_opts o; { int rc = check_opts(o_in, o); if (rc) return rc; }
+    PMN_CUDA_OK(cudaSetDevice(c->device));
+    int rc = pmn_seed_impl(c, ix, qry, &o, n_anchors, part, nparts);
+    if (rc) return rc;
+    PMN_CUDA_OK(cudaStreamSynchronize(c->stream));
+    *dev_anchors = *n_anchors > 0 ? c->scratch->anchors.p : nullptr;
+    return 0;
+}
+
+extern "C" int pmn_align_anchors(pmn_ctx *c, const pmn_index *ix, const pmn_seq *qry, const pmn_opts *o_in, const void *dev_anchors, int64_t n_anchors,
+                                 const char *ref_path, const char *qry_path, pmn_result **out)
+{
+    if (!c || !ix || !qry || !out || n_anchors < 0 || (n_anchors > 0 && !dev_anchors)) return pmn_set_error(PMN_E_ARG, "pmn_align_anchors: bad argument");
+    return align_impl(c, ix, qry, o_in, dev_anchors, n_anchors, ref_path, qry_path, out);
 }
 
 extern "C" const char *pmn_result_delta(const pmn_result *r, size_t *len) { if (len) *len = r ? r->delta.size() : 0; return r ? r->delta.c_str() : ""; }

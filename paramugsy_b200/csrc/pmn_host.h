@@ -26,7 +26,13 @@ struct pmn_index {
     pmn_ctx *ctx = nullptr;
     const pmn_seq *seq = nullptr;       // borrowed: the caller keeps the sequence alive
     int64_t n = 0;
-    DevBuf sa, lcp, table;              // int32[n], int32[n], uint32[4^K + 1]
+    // one contiguous image in HBM (so that it can be replicated by a single NCCL broadcast):
+    //   [0,256) header {magic, n, K, rounds} | int32 SA[n] | int32 LCP[n] | uint32 table[4^K + 1], each 256-byte aligned
+    DevBuf blob;
+    size_t off_sa = 0, off_lcp = 0, off_table = 0, blob_bytes = 0;
+    uint32_t *sa() const { return (uint32_t *)((char *)blob.p + off_sa); }
+    int32_t *lcp() const { return (int32_t *)((char *)blob.p + off_lcp); }
+    uint32_t *table() const { return (uint32_t *)((char *)blob.p + off_table); }
     int K = 0;
     int rounds = 0;                     // prefix-doubling rounds after the 16-mer pass
     float ms_build = 0, wall_ms_build = 0;
@@ -79,7 +85,10 @@ void pmn_pool_put(pmn_ctx *c, DevBuf &b);
 // stage entry points (defined in the .cu files)
 int pmn_fasta_to_device(pmn_ctx *c, pmn_seq *s, const char *txt, size_t nb, const std::vector<int64_t> &header_pos);
 int pmn_index_build_impl(pmn_ctx *c, const pmn_seq *ref, pmn_index *ix);
-int pmn_seed_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_opts *o, int64_t *n_anchors);
+int pmn_index_layout(pmn_ctx *c, const pmn_seq *ref, pmn_index *ix);   // sizes the image for ref and takes it from the pool
+struct PmnIndexHeader { uint64_t magic; int64_t n; int32_t K, rounds; };
+#define PMN_INDEX_MAGIC 0x31584449304e4d50ull   /* "PMN0IDX1" */
+int pmn_seed_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_opts *o, int64_t *n_anchors, int part = 0, int nparts = 1);
 int pmn_cluster_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_opts *o, int64_t n_anchors);
 int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_opts *o, pmn_result *res);
 int pmn_read_file(const char *path, std::string &out);

@@ -309,21 +309,41 @@ __global__ void __launch_bounds__(256) k_bucket_fill(PackedView s, const uint32_
 
 static inline int bits_for(int64_t v) { int b = 1; while ((1ll << b) <= v) b++; return b; }
 
+static inline int index_K(int64_t n) { int K = 8; while (K < 13 && (1ll << (2 * K)) < n) K++; return K; }
+
+static inline size_t up256(size_t x) { return (x + 255) / 256 * 256; }
+
+extern "C" size_t pmn_index_image_bytes(int64_t n_bases)
+{
+    if (n_bases < 1) return 0;
+    return 256 + 2 * up256(4 * (size_t)n_bases) + up256(4 * (((size_t)1 << (2 * index_K(n_bases))) + 1));
+}
+
+int pmn_index_layout(pmn_ctx *c, const pmn_seq *ref, pmn_index *ix)
+{
+    const int64_t n = ref->n;
+    if (n < 1) return pmn_set_error(PMN_E_ARG, "index: empty reference");
+    if (n > 0x7ffffff0ll) return pmn_set_error(PMN_E_ARG, "index: reference longer than 2^31 bases");
+    ix->ctx = c; ix->seq = ref; ix->n = n; ix->K = index_K(n);
+    ix->off_sa = 256; ix->off_lcp = ix->off_sa + up256(4 * (size_t)n); ix->off_table = ix->off_lcp + up256(4 * (size_t)n);
+    ix->blob_bytes = pmn_index_image_bytes(n);
+    return pmn_pool_get(c, ix->blob, ix->blob_bytes) ? -3 : 0;
+}
+
+__global__ void k_index_header(PmnIndexHeader *h, int64_t n, int K, int rounds) { h->magic = PMN_INDEX_MAGIC; h->n = n; h->K = K; h->rounds = rounds; }
+
 int pmn_index_build_impl(pmn_ctx *c, const pmn_seq *ref, pmn_index *ix)
 {
     Scratch &S = *c->scratch;
     cudaStream_t st = c->stream;
+    { int rc = pmn_index_layout(c, ref, ix); if (rc) return rc; }
     const int64_t n = ref->n;
-    if (n < 1) return pmn_set_error(PMN_E_ARG, "index: empty reference");
-    if (n > 0x7ffffff0ll) return pmn_set_error(PMN_E_ARG, "index: reference longer than 2^31 bases");
-    ix->ctx = c; ix->seq = ref; ix->n = n;
     PackedView T = ref->fwd();
 
     if (S.k0.ensure(8 * (size_t)n) || S.k1.ensure(8 * (size_t)n) || S.v0.ensure(4 * (size_t)n) || S.v1.ensure(4 * (size_t)n)) return -3;
     if (S.gs.ensure(4 * (size_t)n) || S.rank.ensure(4 * (size_t)(n + 1)) || S.flags.ensure(4 * (size_t)n) ||
         S.list0.ensure(4 * (size_t)n) || S.list1.ensure(4 * (size_t)n) || S.gsn.ensure(4 * (size_t)n)) return -3;
     if (S.scan_tmp.ensure(8 * pmn_scan_scratch_elems(n))) return -3;
-    if (pmn_pool_get(c, ix->sa, 4 * (size_t)n) || pmn_pool_get(c, ix->lcp, 4 * (size_t)n)) return -3;
     if (S.ensure_pinned(64)) return -3;
 
     PMN_CUDA_OK(cudaEventRecord(c->ev[0], st));
@@ -336,7 +356,7 @@ int pmn_index_build_impl(pmn_ctx *c, const pmn_seq *ref, pmn_index *ix)
     if (where < 0) return -3;
     const uint64_t *skeys = where ? S.k1.as<uint64_t>() : S.k0.as<uint64_t>();
     const uint32_t *svals = where ? S.v1.as<uint32_t>() : S.v0.as<uint32_t>();
-    uint32_t *sa = ix->sa.as<uint32_t>();
+    uint32_t *sa = ix->sa();
     PMN_CUDA_OK(cudaMemcpyAsync(sa, svals, 4 * (size_t)n, cudaMemcpyDeviceToDevice, st));
 
     // 2. groups of equal 16-mers -> ranks; slots that still share a group go on the work list
@@ -379,13 +399,12 @@ int pmn_index_build_impl(pmn_ctx *c, const pmn_seq *ref, pmn_index *ix)
     ix->rounds = rounds;
 
     // 3. LCP in text order
-    k_lcp<<<(unsigned)(((n + PMN_LCP_CHUNK - 1) / PMN_LCP_CHUNK + 255) / 256), 256, 0, st>>>(T, sa, rank, ix->lcp.as<int32_t>()); launches++;
+    k_lcp<<<(unsigned)(((n + PMN_LCP_CHUNK - 1) / PMN_LCP_CHUNK + 255) / 256), 256, 0, st>>>(T, sa, rank, ix->lcp()); launches++;
 
     // 4. bucket table over the first K bases
-    int K = 8; while (K < 13 && (1ll << (2 * K)) < n) K++;
-    ix->K = K;
-    if (pmn_pool_get(c, ix->table, 4 * ((size_t)1 << (2 * K)) + 16)) return -3;
-    k_bucket_fill<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(T, sa, K, ix->table.as<uint32_t>()); launches++;
+    const int K = ix->K;
+    k_bucket_fill<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(T, sa, K, ix->table()); launches++;
+    k_index_header<<<1, 1, 0, st>>>((PmnIndexHeader *)ix->blob.p, n, K, rounds); launches++;
 
     PMN_CUDA_OK(cudaEventRecord(c->ev[1], st));
     PMN_CUDA_OK(cudaStreamSynchronize(st));

@@ -76,16 +76,19 @@ extern "C" void pmn_sched_counters(const pmn_sched *s, int64_t out[4])
 // The common engine: genomes either as host FASTA buffers (packed on demand) or as resident
 // pmn_seq handles; pairs as index pairs into the genome list.
 static int sched_run(pmn_sched *s, int ng, const char *const *fasta, const size_t *bytes, const pmn_seq *const *resident,
-                     const char *const *names, int np, const int32_t *ref, const int32_t *qry, const pmn_opts *opts, pmn_result **out)
+                     const pmn_index *const *given_idx, const char *const *names, int np, const int32_t *ref, const int32_t *qry, const pmn_opts *opts, pmn_result **out)
 {
     if (!s || ng < 0 || np < 0 || (np && (!ref || !qry || !out)) || (!fasta && !resident && ng)) return pmn_set_error(PMN_E_ARG, "pmn_sched: bad argument");
     for (int p = 0; p < np; p++) {
         out[p] = nullptr;
         if (ref[p] < 0 || ref[p] >= ng || qry[p] < 0 || qry[p] >= ng) return pmn_set_error(PMN_E_ARG, "pmn_sched: pair %d names a genome out of range", p);
+        if (resident && (!resident[ref[p]] || !resident[qry[p]])) return pmn_set_error(PMN_E_ARG, "pmn_sched: pair %d names a genome that is not resident", p);
     }
     std::vector<Slot> seqs((size_t)ng), idx((size_t)ng);
     for (int p = 0; p < np; p++) { seqs[(size_t)ref[p]].users++; seqs[(size_t)qry[p]].users++; idx[(size_t)ref[p]].users++; }
     if (resident) for (int g = 0; g < ng; g++) { seqs[(size_t)g].state = ST_READY; seqs[(size_t)g].obj = (void *)resident[g]; }
+    // indexes the caller already holds (built here or received from another GPU) are used as they are and never freed
+    if (given_idx) for (int g = 0; g < ng; g++) if (given_idx[g]) { idx[(size_t)g].state = ST_READY; idx[(size_t)g].obj = (void *)given_idx[g]; idx[(size_t)g].users += 1 << 30; }
     // pairs in reference order, so that at most a few indexes are alive at a time
     std::vector<int> order((size_t)np);
     for (int p = 0; p < np; p++) order[(size_t)p] = p;
@@ -146,7 +149,7 @@ static int sched_run(pmn_sched *s, int ng, const char *const *fasta, const size_
 
     if (s->err_code) {
         for (int p = 0; p < np; p++) { pmn_result_free(out[p]); out[p] = nullptr; }
-        for (auto &sl : idx) if (sl.obj) pmn_index_free((pmn_index *)sl.obj);
+        for (auto &sl : idx) if (sl.obj && sl.users < (1 << 30)) pmn_index_free((pmn_index *)sl.obj);
         if (!resident) for (auto &sl : seqs) if (sl.obj) pmn_seq_free((pmn_seq *)sl.obj);
         return pmn_set_error(s->err_code, "%s", s->err.c_str());
     }
@@ -157,15 +160,23 @@ extern "C" int pmn_sched_align_fasta(pmn_sched *s, int n_genomes, const char *co
                                      int n_pairs, const int32_t *ref, const int32_t *qry, const pmn_opts *o, pmn_result **out)
 {
     if (n_genomes && (!fasta || !bytes)) return pmn_set_error(PMN_E_ARG, "pmn_sched_align_fasta: NULL genome list");
-    return sched_run(s, n_genomes, fasta, bytes, nullptr, names, n_pairs, ref, qry, o, out);
+    return sched_run(s, n_genomes, fasta, bytes, nullptr, nullptr, names, n_pairs, ref, qry, o, out);
 }
 
 extern "C" int pmn_sched_align_seqs(pmn_sched *s, int n_genomes, const pmn_seq *const *seqs, const char *const *names,
                                     int n_pairs, const int32_t *ref, const int32_t *qry, const pmn_opts *o, pmn_result **out)
 {
     if (!s || (n_genomes && !seqs)) return pmn_set_error(PMN_E_ARG, "pmn_sched_align_seqs: NULL argument");
-    for (int g = 0; g < n_genomes; g++) if (!seqs[g] || seqs[g]->ctx->device != s->device) return pmn_set_error(PMN_E_ARG, "pmn_sched_align_seqs: genome %d is not resident on device %d", g, s->device);
-    return sched_run(s, n_genomes, nullptr, nullptr, seqs, names, n_pairs, ref, qry, o, out);
+    for (int g = 0; g < n_genomes; g++) if (seqs[g] && seqs[g]->ctx->device != s->device) return pmn_set_error(PMN_E_ARG, "pmn_sched_align_seqs: genome %d is not resident on device %d", g, s->device);
+    return sched_run(s, n_genomes, nullptr, nullptr, seqs, nullptr, names, n_pairs, ref, qry, o, out);
+}
+
+extern "C" int pmn_sched_align_indexed(pmn_sched *s, int n_genomes, const pmn_seq *const *seqs, const pmn_index *const *indexes, const char *const *names,
+                                       int n_pairs, const int32_t *ref, const int32_t *qry, const pmn_opts *o, pmn_result **out)
+{
+    if (!s || (n_genomes && !seqs)) return pmn_set_error(PMN_E_ARG, "pmn_sched_align_indexed: NULL argument");
+    for (int g = 0; g < n_genomes; g++) if (seqs[g] && seqs[g]->ctx->device != s->device) return pmn_set_error(PMN_E_ARG, "pmn_sched_align_indexed: genome %d is not resident on device %d", g, s->device);
+    return sched_run(s, n_genomes, nullptr, nullptr, seqs, indexes, names, n_pairs, ref, qry, o, out);
 }
 
 // File level, one call per Nucmer_task.t.searches (lib/base/nucmer_task.ml:6,48-59): every distinct
@@ -194,7 +205,7 @@ extern "C" int pmn_sched_align_files(pmn_sched *s, int n, const char *const *ref
     std::vector<const char *> fa(text.size()); std::vector<size_t> nb(text.size());
     for (size_t g = 0; g < text.size(); g++) { fa[g] = text[g].data(); nb[g] = text[g].size(); }
     std::vector<pmn_result *> res((size_t)n, nullptr);
-    int rc = sched_run(s, (int)text.size(), fa.data(), nb.data(), nullptr, names.data(), n, ref.data(), qry.data(), o, res.data());
+    int rc = sched_run(s, (int)text.size(), fa.data(), nb.data(), nullptr, nullptr, names.data(), n, ref.data(), qry.data(), o, res.data());
     for (int i = 0; i < n && !rc; i++) { size_t len; const char *d = pmn_result_delta(res[(size_t)i], &len); rc = pmn_write_file_atomic(out_delta_paths[i], d, len); }
     for (pmn_result *r : res) pmn_result_free(r);
     return rc;

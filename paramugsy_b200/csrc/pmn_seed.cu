@@ -80,8 +80,9 @@ __device__ __forceinline__ bool ref_lt_query(const PackedView &R, int64_t s, con
 __global__ void __launch_bounds__(SEED_THREADS) k_seed(PackedView R, const uint32_t *__restrict__ sa, const int32_t *__restrict__ lcp,
                                                       const uint32_t *__restrict__ table, int K, PackedView QF, PackedView QR,
                                                       const SeedSection *__restrict__ secs, int nsec, int minmatch,
-                                                      int4 *__restrict__ stage, uint32_t *__restrict__ tile_cnt)
+                                                      int4 *__restrict__ stage, uint32_t *__restrict__ tile_cnt, unsigned tile_base)
 {
+    const int64_t tile = (int64_t)blockIdx.x + tile_base;     // blockIdx.x is local to the launched tile range
     __shared__ __align__(16) uint64_t s_w[SEED_WORDS];
     __shared__ __align__(16) uint32_t s_x[SEED_WORDS];
     __shared__ __align__(8) uint64_t s_bar;
@@ -90,10 +91,10 @@ __global__ void __launch_bounds__(SEED_THREADS) k_seed(PackedView R, const uint3
 
     // which section does this tile belong to
     int lo_s = 0, hi_s = nsec - 1;
-    while (lo_s < hi_s) { int mid = (lo_s + hi_s + 1) >> 1; if (secs[mid].tile0 <= (int64_t)blockIdx.x) lo_s = mid; else hi_s = mid - 1; }
+    while (lo_s < hi_s) { int mid = (lo_s + hi_s + 1) >> 1; if (secs[mid].tile0 <= tile) lo_s = mid; else hi_s = mid - 1; }
     const SeedSection sec = secs[lo_s];
     const PackedView Q = sec.strand ? QR : QF;
-    const int64_t off0 = ((int64_t)blockIdx.x - sec.tile0) * SEED_TILE;    // first position of the tile inside the record
+    const int64_t off0 = (tile - sec.tile0) * SEED_TILE;    // first position of the tile inside the record
     const int64_t g0 = sec.start + off0;
     const int64_t w0 = (g0 >> 5) & ~3ll;                                   // 16-byte aligned for text and mask
 
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(256) k_seed_gather(const int4 *__restrict__ st
     for (uint32_t k = threadIdx.x; k < cnt; k += blockDim.x) anchors[off + k] = stage[(size_t)blockIdx.x * SEED_TILE + k];
 }
 
-int pmn_seed_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_opts *o, int64_t *n_anchors)
+int pmn_seed_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_opts *o, int64_t *n_anchors, int part, int nparts)
 {
     Scratch &S = *c->scratch;
     cudaStream_t st = c->stream;
@@ -193,16 +194,22 @@ int pmn_seed_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_o
             tiles += (npos + SEED_TILE - 1) / SEED_TILE;
         }
     }
-    if (tiles == 0) return 0;
     if (tiles > 0x7fffffffll) return pmn_set_error(PMN_E_ARG, "seed: query too large");
+    // query-range sharding of one large pair: part k of G takes the tiles
+    // [k*T/G, (k+1)*T/G); tiles are in (record, strand, position) order, so the parts'
+    // anchor lists concatenated in part order are the full, ordered anchor list
+    const int64_t all_tiles = tiles;
+    const int64_t t_lo = all_tiles * part / nparts, t_hi = all_tiles * (part + 1) / nparts;
+    tiles = t_hi - t_lo;
+    if (tiles == 0) return 0;
     if (S.sections.ensure(sizeof(SeedSection) * secs.size()) || S.stage.ensure(sizeof(int4) * (size_t)tiles * SEED_TILE) ||
         S.tile_cnt.ensure(4 * (size_t)tiles) || S.tile_off.ensure(4 * (size_t)tiles) ||
         S.scan_tmp.ensure(8 * pmn_scan_scratch_elems(tiles)) || S.ensure_pinned(64)) return -3;
     PMN_H2D(c, S.sections.p, secs.data(), sizeof(SeedSection) * secs.size());
     PMN_CUDA_OK(cudaEventRecord(c->ev[6], st));
-    k_seed<<<(unsigned)tiles, SEED_THREADS, 0, st>>>(ix->seq->fwd(), ix->sa.as<uint32_t>(), ix->lcp.as<int32_t>(), ix->table.as<uint32_t>(), ix->K,
+    k_seed<<<(unsigned)tiles, SEED_THREADS, 0, st>>>(ix->seq->fwd(), ix->sa(), ix->lcp(), ix->table(), ix->K,
                                                      q->fwd(), q->rev(), S.sections.as<SeedSection>(), (int)secs.size(), o->minmatch,
-                                                     S.stage.as<int4>(), S.tile_cnt.as<uint32_t>());
+                                                     S.stage.as<int4>(), S.tile_cnt.as<uint32_t>(), (unsigned)t_lo);
     PMN_CUDA_OK(cudaEventRecord(c->ev[7], st));
     pmn_scan<uint32_t, OpAddU32, false>(S.tile_cnt.as<uint32_t>(), S.tile_off.as<uint32_t>(), tiles, S.scan_tmp.as<uint32_t>(), st);
     uint32_t *tail = (uint32_t *)S.pinned;

@@ -46,13 +46,13 @@ SYMBOLS = [
     "pmn_default_opts", "pmn_ctx_create", "pmn_ctx_destroy", "pmn_last_error", "pmn_device_count",
     "pmn_ctx_stream", "pmn_ctx_counters", "pmn_measure_int32_peak",
     "pmn_seq_from_fasta", "pmn_seq_from_file", "pmn_seq_free", "pmn_seq_bases", "pmn_seq_records",
-    "pmn_index_build", "pmn_index_free", "pmn_align", "pmn_result_delta", "pmn_result_stats",
+    "pmn_index_build", "pmn_index_free", "pmn_index_image", "pmn_index_image_bytes", "pmn_index_alloc", "pmn_index_adopt", "pmn_align", "pmn_seed_part", "pmn_align_anchors", "pmn_result_delta", "pmn_result_stats",
     "pmn_result_free", "pmn_align_pair", "pmn_align_batch", "pmn_index_size", "pmn_index_copy_sa",
     "pmn_result_n_anchors", "pmn_result_copy_anchors", "pmn_result_n_clusters",
     "pmn_result_n_cluster_matches", "pmn_result_copy_clusters", "pmn_result_n_alignments",
     "pmn_result_n_deltas", "pmn_result_copy_alignments",
     "pmn_sched_create", "pmn_sched_destroy", "pmn_sched_workers", "pmn_sched_ctx", "pmn_sched_counters",
-    "pmn_sched_align_fasta", "pmn_sched_align_seqs", "pmn_sched_align_files",
+    "pmn_sched_align_fasta", "pmn_sched_align_seqs", "pmn_sched_align_indexed", "pmn_sched_align_files",
 ]
 
 
@@ -82,7 +82,13 @@ def lib():
         L.pmn_seq_records.argtypes = [vp]
         L.pmn_index_build.argtypes = [vp, vp, C.POINTER(vp)]
         L.pmn_index_free.argtypes = [vp]
+        L.pmn_index_image.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+        L.pmn_index_image_bytes.argtypes = [i64]; L.pmn_index_image_bytes.restype = C.c_size_t
+        L.pmn_index_alloc.argtypes = [vp, vp, C.POINTER(vp)]
+        L.pmn_index_adopt.argtypes = [vp]
         L.pmn_align.argtypes = [vp, vp, vp, C.POINTER(Opts), cp, cp, C.POINTER(vp)]
+        L.pmn_seed_part.argtypes = [vp, vp, vp, C.POINTER(Opts), C.c_int, C.c_int, C.POINTER(vp), i64p]
+        L.pmn_align_anchors.argtypes = [vp, vp, vp, C.POINTER(Opts), vp, i64, cp, cp, C.POINTER(vp)]
         L.pmn_result_delta.argtypes = [vp, C.POINTER(C.c_size_t)]; L.pmn_result_delta.restype = vp
         L.pmn_result_stats.argtypes = [vp, C.POINTER(Stats)]
         L.pmn_result_free.argtypes = [vp]
@@ -104,9 +110,14 @@ def lib():
         L.pmn_sched_counters.argtypes = [vp, i64p]
         L.pmn_sched_align_fasta.argtypes = [vp, C.c_int, C.POINTER(cp), C.POINTER(C.c_size_t), C.POINTER(cp), C.c_int, i32a, i32a, C.POINTER(Opts), C.POINTER(vp)]
         L.pmn_sched_align_seqs.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(cp), C.c_int, i32a, i32a, C.POINTER(Opts), C.POINTER(vp)]
+        L.pmn_sched_align_indexed.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(cp), C.c_int, i32a, i32a, C.POINTER(Opts), C.POINTER(vp)]
         L.pmn_sched_align_files.argtypes = [vp, C.c_int, C.POINTER(cp), C.POINTER(cp), C.POINTER(cp), C.POINTER(Opts)]
         _LIB = L
     return _LIB
+
+
+def index_image_bytes(n_bases: int) -> int:
+    return lib().pmn_index_image_bytes(n_bases)
 
 
 def default_opts(**kw):
@@ -212,15 +223,20 @@ class Scheduler:
         _check(lib().pmn_sched_align_fasta(self.h, g, fa, nb, nm, n, r, q, C.byref(o), out))
         return [Result(C.c_void_p(h)) for h in out]
 
-    def align_seqs(self, seqs, pairs, names=None, opts=None, **kw):
-        """seqs: list of Sequence objects resident on this GPU."""
+    def align_seqs(self, seqs, pairs, names=None, opts=None, indexes=None, **kw):
+        """seqs: list of Sequence objects resident on this GPU; indexes: optional list (None entries allowed)
+        of Index objects the caller already holds for some of them."""
         o = opts if opts is not None else default_opts(**kw)
         g = len(seqs)
-        sh = (C.c_void_p * g)(*[s.h for s in seqs])
+        sh = (C.c_void_p * g)(*[(s.h if s is not None else None) for s in seqs])      # genomes no pair names may be None
         nm = (C.c_char_p * g)(*[os.fsencode(x) for x in names]) if names else None
         n, r, q = self._pairs(pairs)
         out = (C.c_void_p * n)()
-        _check(lib().pmn_sched_align_seqs(self.h, g, sh, nm, n, r, q, C.byref(o), out))
+        if indexes is None:
+            _check(lib().pmn_sched_align_seqs(self.h, g, sh, nm, n, r, q, C.byref(o), out))
+        else:
+            ih = (C.c_void_p * g)(*[(ix.h if ix is not None else None) for ix in indexes])
+            _check(lib().pmn_sched_align_indexed(self.h, g, sh, ih, nm, n, r, q, C.byref(o), out))
         return [Result(C.c_void_p(h)) for h in out]
 
     def align_files(self, refs, qrys, outs, opts=None, **kw):
@@ -251,16 +267,43 @@ class Sequence:
             lib().pmn_seq_free(self.h)
         self.h = None
 
-    def index(self):
-        return Index(self)
+    def index(self, empty=False):
+        return Index(self, empty=empty)
+
+
+class _DeviceBytes:
+    """A range of HBM as a uint8 array for torch.as_tensor (zero copy, __cuda_array_interface__)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
 
 
 class Index:
-    def __init__(self, seq):
+    def __init__(self, seq, empty=False):
+        """Builds the index of `seq`; with empty=True only allocates its image, to be filled by a
+        collective (Index.image) and validated with adopt()."""
         self.seq = seq           # keeps the sequence alive
         self.ctx = seq.ctx
         self.h = C.c_void_p()
-        _check(lib().pmn_index_build(self.ctx.h, seq.h, C.byref(self.h)))
+        if empty:
+            _check(lib().pmn_index_alloc(self.ctx.h, seq.h, C.byref(self.h)))
+        else:
+            _check(lib().pmn_index_build(self.ctx.h, seq.h, C.byref(self.h)))
+
+    def image(self):
+        """(device pointer, bytes) of the index image in HBM."""
+        p, n = C.c_void_p(), C.c_size_t()
+        _check(lib().pmn_index_image(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def image_tensor(self):
+        """The image as a torch uint8 CUDA tensor aliasing the index memory (for torch.distributed)."""
+        import torch
+        p, n = self.image()
+        return torch.as_tensor(_DeviceBytes(p, n), device=torch.device("cuda", self.ctx.device))
+
+    def adopt(self):
+        _check(lib().pmn_index_adopt(self.h))
 
     def close(self):
         if getattr(self, "h", None) and self.ctx.h:
@@ -280,13 +323,40 @@ class Index:
         return Result(r)
 
 
+    def seed_part(self, qry, part, nparts, opts=None, **kw):
+        """Anchors of query-position part `part` of `nparts` as (device pointer, count); they live in the
+        context's scratch until its next call."""
+        o = opts if opts is not None else default_opts(**kw)
+        p, n = C.c_void_p(), C.c_int64()
+        _check(lib().pmn_seed_part(self.ctx.h, self.h, qry.h, C.byref(o), part, nparts, C.byref(p), C.byref(n)))
+        return p.value or 0, n.value
+
+    def seed_part_tensor(self, qry, part, nparts, opts=None, **kw):
+        """The same as an (n, 4) int32 CUDA tensor (a copy, safe to keep)."""
+        import torch
+        p, n = self.seed_part(qry, part, nparts, opts, **kw)
+        dev = torch.device("cuda", self.ctx.device)
+        if n == 0:
+            return torch.empty((0, 4), dtype=torch.int32, device=dev)
+        return torch.as_tensor(_DeviceBytes(p, 16 * n), device=dev).view(torch.int32).view(n, 4).clone()
+
+    def align_anchors(self, qry, anchors, opts=None, ref_path="ref.fa", qry_path="qry.fa", **kw):
+        """Clustering, extension and .delta from a given anchor list ((n, 4) int32 CUDA tensor)."""
+        o = opts if opts is not None else default_opts(**kw)
+        r = C.c_void_p()
+        a = anchors.contiguous()
+        _check(lib().pmn_align_anchors(self.ctx.h, self.h, qry.h, C.byref(o), C.c_void_p(a.data_ptr() if a.numel() else 0), a.shape[0],
+                                       os.fsencode(ref_path), os.fsencode(qry_path), C.byref(r)))
+        return Result(r)
+
+
 class Result:
     def __init__(self, h):
         self.h = h
 
     def close(self):
-        if getattr(self, "h", None):
-            lib().pmn_result_free(self.h)
+        if getattr(self, "h", None) and _LIB is not None:      # _LIB is gone at interpreter shutdown
+            _LIB.pmn_result_free(self.h)
         self.h = None
 
     __del__ = close

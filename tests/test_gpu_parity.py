@@ -192,3 +192,42 @@ def test_scheduler_results_do_not_depend_on_workers(oracle, tmp_path):
             with pytest.raises(lib.PmnError):
                 s.align_fasta(fastas[:2] + [b"not fasta"], [(0, 1), (0, 2)])
             assert [r.delta for r in s.align_fasta(fastas, pairs[:3], names=names)] == want[:3]     # usable after an error
+
+
+def test_sharded_seeding_and_replicated_index(ctx, oracle):
+    """SURVEY.md §8e on one GPU: (1) the anchors of query-position parts, concatenated in part order,
+    are the anchor list of the undivided run, and the alignment continued from them is the same
+    .delta for any number of parts; (2) an index image copied into an empty index of another context
+    (what the NCCL broadcast does between GPUs) serves the same results."""
+    import torch
+    from paramugsy_b200 import lib
+    gs = synth.config_c2(n=300_000, count=2, inv_len=6_000)
+    ref, qry = synth.fasta(*gs[0]), synth.fasta(*gs[1]) + synth.fasta("extra.1", synth.random_genome(700, 5))
+    rs, qs = ctx.sequence(ref), ctx.sequence(qry)
+    ix = rs.index()
+    whole = ix.align(qs, ref_path="r", qry_path="q", keep_stages=1)
+    want_anchors = torch.from_numpy(whole.anchors())
+    want = whole.delta
+    assert want == oracle.nucmer(ref, qry, "r", "q", fast_chain=1)
+    for parts in (1, 2, 3, 8):
+        got = torch.cat([ix.seed_part_tensor(qs, k, parts).cpu() for k in range(parts)])
+        assert torch.equal(got, want_anchors), f"{parts} parts"
+        res = ix.align_anchors(qs, got.cuda(), ref_path="r", qry_path="q")
+        assert res.delta == want
+        res.close()
+    empty = ix.align_anchors(qs, torch.empty((0, 4), dtype=torch.int32, device="cuda"), ref_path="r", qry_path="q")
+    assert empty.delta == b"r q\nNUCMER\n"
+    # replicated index
+    with lib.Context(0) as other:
+        rs2, qs2 = other.sequence(ref), other.sequence(qry)
+        ix2 = rs2.index(empty=True)
+        with pytest.raises(lib.PmnError):
+            ix2.adopt()                                   # nothing received yet
+        assert ix2.image()[1] == ix.image()[1] == lib.index_image_bytes(rs.bases)
+        ix2.image_tensor().copy_(ix.image_tensor())
+        torch.cuda.synchronize()
+        ix2.adopt()
+        r2 = ix2.align(qs2, ref_path="r", qry_path="q")
+        assert r2.delta == want
+        r2.close(); ix2.close(); qs2.close(); rs2.close()
+    whole.close(); ix.close(); qs.close(); rs.close()
