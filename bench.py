@@ -166,7 +166,7 @@ def run_gpu(args):
         # the workers launch on their own streams and every call returns with all of them drained, so
         # events recorded on the (idle) current stream around the calls bracket exactly the device work
         barrier()
-        c0 = sched.counters()
+        c0 = sched.counters(); a0 = lib.alloc_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         walls = []
@@ -180,7 +180,7 @@ def run_gpu(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         c1 = sched.counters()
-        d = {k: c1[k] - c0[k] for k in c0}; d["walls"] = [round(w, 2) for w in walls]
+        d = {k: c1[k] - c0[k] for k in c0}; d["walls"] = [round(w, 2) for w in walls]; d["allocs"] = lib.alloc_count() - a0
         return ms, d
 
     # ---- resident arm
@@ -192,7 +192,8 @@ def run_gpu(args):
         step_resident(resident)
     ms_res, cnt_res = timed(lambda: step_resident(resident), args.steps)
     # ---- end-to-end arm (host FASTA bytes -> host .delta bytes)
-    step_e2e()
+    for _ in range(args.warmup):
+        step_e2e()
     ms_e2e, cnt_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     # ---- one instrumented pass for the per-kernel figures
@@ -257,6 +258,7 @@ def run_gpu(args):
                     "h2d_bytes_per_step": cnt_e2e["h2d_bytes"] // args.steps, "d2h_bytes_per_step": cnt_e2e["d2h_bytes"] // args.steps,
                     "delta_bytes_per_step": sum(d[3] for d in detail)},
             "gpu_launches": cnt_res["launches"], "step_wall_ms": {"resident": cnt_res["walls"], "e2e": cnt_e2e["walls"]},
+            "device_allocations_in_timed_region": {"resident": cnt_res["allocs"], "e2e": cnt_e2e["allocs"]},
             "clocks": clocks,
             "stage_ms_per_step": stage_ms,
             "host_wall_ms_per_step": {"index_build": sum({a: st["wall_ms_index"] for a, _, st, _ in detail}.values()),

@@ -77,6 +77,9 @@ int  pmn_ctx_create(int device, pmn_ctx **out);
 void pmn_ctx_destroy(pmn_ctx *c);
 const char *pmn_last_error(const pmn_ctx *c);      /* c may be NULL: last error of the calling thread */
 int  pmn_device_count(void);
+/* device allocations (cudaMalloc) made by the library in this process so far: all scratch is grow-only, so the
+ * number stops changing once the working set has been seen; bench.py reports the count inside its timed region */
+int64_t pmn_alloc_count(void);
 /* the CUDA stream (cudaStream_t) every kernel of this context is launched on, so that a caller
  * can bracket calls with its own CUDA events */
 void *pmn_ctx_stream(const pmn_ctx *c);

@@ -2,6 +2,7 @@
 // batch, .delta text.  Replaces the `nucmer` child process of
 // /root/reference/lib/nucmer/mugsy_nucmer.ml:96-100 (see INTEGRATION.md for the OCaml stub).
 #include <algorithm>
+#include <atomic>
 #include <cerrno>
 #include <chrono>
 #include <cstdarg>
@@ -27,6 +28,10 @@ int pmn_set_error(int code, const char *fmt, ...)
 
 extern "C" const char *pmn_last_error(const pmn_ctx *) { return g_err.msg; }
 
+static std::atomic<long long> g_allocs{0};
+void pmn_count_alloc() { g_allocs++; }
+extern "C" int64_t pmn_alloc_count(void) { return (int64_t)g_allocs.load(); }
+
 extern "C" void pmn_default_opts(pmn_opts *o)
 {
     o->minmatch = PMN_DEF_MINMATCH; o->mincluster = PMN_DEF_MINCLUSTER; o->maxgap = PMN_DEF_MAXGAP;
@@ -45,7 +50,7 @@ void pmn_scratch_free(Scratch *s)
                        &s->cl_a, &s->cl_b, &s->cl_c, &s->cl_d, &s->cl_e, &s->cl_f, &s->cl_g, &s->cl_h, &s->cl_i, &s->cl_j, &s->cl_k, &s->cl_l,
                        &s->cl_matches, &s->cl_recs, &s->cl_counters,
                        &s->ex_a, &s->ex_b, &s->ex_c, &s->ex_d, &s->ex_e, &s->ex_f, &s->ex_g, &s->ex_h, &s->ex_i, &s->ex_j, &s->ex_k, &s->ex_l,
-                       &s->ex_scores, &s->ex_tb, &s->ex_tbidx, &s->ex_pool, &s->ex_counters, &s->ex_arena, &s->ex_dbg };
+                       &s->ex_scores, &s->ex_tb, &s->ex_tbidx, &s->ex_pool, &s->ex_counters, &s->ex_arena, &s->ex_dbg, &s->ex_desc };
     for (DevBuf *b : bufs) b->release();
     if (s->pinned) cudaFreeHost(s->pinned);
     delete s;
@@ -88,7 +93,7 @@ int pmn_pool_get(pmn_ctx *c, DevBuf &b, size_t bytes)
     int best = -1;
     for (size_t i = 0; i < P.bufs.size(); i++)
         if (P.bufs[i].cap >= bytes && (best < 0 || P.bufs[i].cap < P.bufs[(size_t)best].cap)) best = (int)i;
-    if (best >= 0 && P.bufs[(size_t)best].cap <= 2 * bytes + (1u << 20)) {
+    if (best >= 0 && P.bufs[(size_t)best].cap <= 4 * bytes + (1u << 20)) {
         b = P.bufs[(size_t)best];
         P.bufs.erase(P.bufs.begin() + best);
         return 0;

@@ -30,6 +30,7 @@ struct PmnError { int code; char msg[480]; };
     } while (0)
 
 int pmn_set_error(int code, const char *fmt, ...);
+void pmn_count_alloc();       // counts cudaMalloc calls (bench.py reports how many fell into the timed region)
 
 // ---- a grow-only device buffer: no cudaMalloc at steady state -------------------------------
 struct DevBuf {
@@ -39,10 +40,16 @@ struct DevBuf {
     {
         if (bytes <= cap) return 0;
         if (p) cudaFree(p);
-        size_t want = bytes + bytes / 4 + 256;
+        // capacities are quantised (powers of two up to 64 MB, multiples of 64 MB above) so that the
+        // slightly different sizes of successive pairs settle on one allocation after a few calls:
+        // cudaMalloc / cudaFree serialise the whole device, which would stall every other worker
+        size_t want = 4096;
+        if (bytes > ((size_t)64 << 20)) want = (bytes + bytes / 8 + ((size_t)64 << 20) - 1) / ((size_t)64 << 20) * ((size_t)64 << 20);
+        else while (want < 2 * bytes) want <<= 1;           // 2x head room: every worker converges after its first pair
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) { p = nullptr; cap = 0; return pmn_set_error(-3, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); }
         cap = want;
+        pmn_count_alloc();
         return 0;
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }

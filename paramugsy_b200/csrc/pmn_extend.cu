@@ -27,9 +27,7 @@
 
 #include "pmn_scratch.cuh"
 
-#define EX_RW 256                      /* shared-memory ring width (cells) per score row          */
 #define EX_BAND_SMEM 224                /* widest band kept in shared memory (ring and base caches)  */
-#define EX_SMEM_WARP (EX_ROWS * EX_RW * 4 + 512 + 256)   /* bytes per warp: score ring + reference base ring (512 B) + query nibble ring (256 B) */
 #define EX_WCAP (PMN_MAX_ALIGNMENT_LENGTH + 8)   /* global score row capacity                    */
 #define EX_ROWS 12                     /* 3 anti-diagonals x (DEL, INS, MAT, cell max)            */
 #define EX_DMAX (2 * PMN_MAX_ALIGNMENT_LENGTH + 8)
@@ -50,6 +48,9 @@ struct ExSynteny {
     int32_t alfirst, alcap, nodefirst, nodecap;
 };
 struct ExJob { int32_t endA, endB, dcnt, target; uint32_t doff; int32_t reached, valid, asum; };   // asum: sum of (d>0 ? d : |d|-1) over the job's deltas
+// everything wave 1 needs to know about one forward alignment, written by k_ex_jobdesc so that a warp
+// fetches a job with one coalesced load instead of chasing match -> cluster -> synteny
+struct ExJobDesc { int64_t Abase, Bbase; int32_t eA, eB, tA, tB, g, dir, m_o, target; };   // m_o < 0: no job
 struct ExAlign { int32_t dirB, sA, sB, eA, eB, P, head, tail, ndelta, live, pad0, pad1; };   // P: reference position consumed through the last indel (sA-1 when none)
 // a piece of an alignment's delta list: type 0 = `cnt` pool entries at `a` whose first value gets +-`b` added;
 // type 1 = the deltas of the wave-1 jobs [a, cnt) (all reached their targets), `b` = P before the range
@@ -82,6 +83,8 @@ struct ExShared {                       // everything the device code needs, pas
     const long long *lastP;             // per job g: (piece << 32 | j+1), j = latest job <= g of the same cluster that has deltas
     const uint8_t *anyfail;             // per cluster: some match -> next match job did not reach its target
     unsigned long long *markkey;        // per job: set at the first job of a claimed range
+    const ExJobDesc *descA, *descB;     // wave-1 jobs: cluster ends (nC), match -> next match (nM)
+    int32_t *overflow;                  // inner jobs the small kernel handed to the big one (count = counters[7])
     int4 *dbg; unsigned dbg_cap;        // PMN_JOBLOG: two int4 per engine call (cursor = counters[15])
 };
 
@@ -129,7 +132,32 @@ __device__ __forceinline__ int max_state(int vD, int vI, int vM)
 // ring (one LDS per anti-diagonal); the query nibbles of its K columns come from a nibble-packed
 // ring (one LDS).  Both rings are filled 32 bases at a time, one batch ahead of their use.
 
-#define EX_CR 512                       /* base ring entries (reference: bytes, query: nibbles) */
+// Shared memory of one warp, two layouts (offsets in 32-bit words):
+//   CfgBig    K up to 8 and the wide fallback: 12 score rows x 256 columns (rows 0-2 / 4-6 = the two live
+//             anti-diagonals at a change of K; all 12 belong to the wide fallback).  The rows only the wide
+//             fallback uses are free while the register band runs; short alignments keep their whole
+//             traceback there, so that the walk back never touches global memory: row 3 = per-diagonal
+//             (row offset << 16 | first column), row 7 = reversed deltas, rows 8-11 = traceback rows (4 KB).
+//   CfgSmall  K <= 2, no fallback (an alignment that needs more is handed to the big kernel): 7 rows x 64
+//             columns, then meta / reversed deltas / 2 KB of traceback rows.  5 KB per warp instead of 13,
+//             so that the kernel for the many small gaps runs 24 warps per SM.
+struct CfgBig {
+    static constexpr int MAXK = 8, RW = 256, CR = 512;
+    static constexpr int META_OFF = 3 * 256, META_N = 256, REV_OFF = 7 * 256, REV_N = 256, TBROWS_OFF = 8 * 256, TBROWS_BYTES = 4096;
+    static constexpr int BASE_OFF = 12 * 256;
+    static constexpr int WARP_BYTES = 12 * 256 * 4 + 512 + 256;      // rows + reference ring (CR bytes) + query nibble ring (CR / 2 bytes)
+};
+struct CfgSmall {
+    static constexpr int MAXK = 2, RW = 64, CR = 256;
+    static constexpr int META_OFF = 7 * 64, META_N = 128, REV_OFF = META_OFF + 128, REV_N = 64, TBROWS_OFF = REV_OFF + 64, TBROWS_BYTES = 2048;
+    static constexpr int BASE_OFF = TBROWS_OFF + 512;
+    static constexpr int WARP_BYTES = (BASE_OFF + 64 + 32) * 4;
+};
+template <class Cfg> __device__ __forceinline__ int32_t *eng_warp_smem()
+{
+    extern __shared__ int32_t smem_all[];
+    return smem_all + (threadIdx.x >> 5) * (Cfg::WARP_BYTES / 4);
+}
 
 struct EngCtx {                          // warp-uniform progress of one alignment
     int N, M, dir, breaklen;
@@ -138,12 +166,13 @@ struct EngCtx {                          // warp-uniform progress of one alignme
     int high, best_d, best_j, reached;   // high: plain (unscaled) score
     unsigned long long cells;
     uint8_t *tcur, *tend; bool arena_fail;
+    int tb_sm_used, tb_sm_n; bool tb_sm_open;   // traceback rows kept in shared memory: bytes used, diagonals [0, tb_sm_n), still appending
     int ca_hi, cb_hi;                    // first unfilled index of the reference / query ring
     int pa, pb;                          // this lane's nibble of the batch fetched ahead
     int64_t Apos0, Bpos0;
 };
 
-#define SCR(buf, st, j) ring[((buf) * 4 + (st)) * EX_RW + ((j) & (EX_RW - 1))]
+#define SCR(buf, st, j) ring[((buf) * 4 + (st)) * Cfg::RW + ((j) & (Cfg::RW - 1))]
 
 __device__ __forceinline__ int eng_ref_nibble(const ExShared &X, const EngCtx &c, int i)
 {
@@ -159,18 +188,20 @@ __device__ __forceinline__ int eng_qry_nibble(const PackedView &Q, const EngCtx 
 }
 
 // write the batch fetched ahead into the ring, fetch the next one
+template <class Cfg>
 __device__ __forceinline__ void eng_fill_ref(const ExShared &X, EngCtx &c, uint8_t *ca, int lane)
 {
-    ca[(c.ca_hi + lane) & (EX_CR - 1)] = (uint8_t)c.pa;
+    ca[(c.ca_hi + lane) & (Cfg::CR - 1)] = (uint8_t)c.pa;
     c.ca_hi += 32;
     c.pa = eng_ref_nibble(X, c, c.ca_hi + lane);
     __syncwarp();
 }
+template <class Cfg>
 __device__ __forceinline__ void eng_fill_qry(const PackedView &Q, EngCtx &c, uint32_t *cbw, int lane)
 {
     unsigned v = (unsigned)c.pb << (4 * (lane & 7));
     v |= __shfl_xor_sync(0xffffffffu, v, 1); v |= __shfl_xor_sync(0xffffffffu, v, 2); v |= __shfl_xor_sync(0xffffffffu, v, 4);
-    if ((lane & 7) == 0) cbw[((c.cb_hi >> 3) + (lane >> 3)) & (EX_CR / 8 - 1)] = v;
+    if ((lane & 7) == 0) cbw[((c.cb_hi >> 3) + (lane >> 3)) & (Cfg::CR / 8 - 1)] = v;
     c.cb_hi += 32;
     c.pb = eng_qry_nibble(Q, c, c.cb_hi + lane);
     __syncwarp();
@@ -184,7 +215,7 @@ __device__ __forceinline__ void eng_fill_qry(const PackedView &Q, EngCtx &c, uin
 // band needs more columns (ENG_GROW) or fits half as many (ENG_SHRINK).  Enters and leaves with
 // the two live anti-diagonals in the shared-memory ring (plain scores; rows 0-2 = diagonal d-2,
 // rows 4-6 = diagonal d-1).
-template <int K>
+template <int K, class Cfg>
 __device__ __forceinline__ int eng_run_reg(const Eng &E, EngCtx &c, const PackedView &Q, uint8_t **tboff, int32_t *tblo)
 {
     constexpr int LOGK = K == 1 ? 0 : (K == 2 ? 1 : (K == 4 ? 2 : 3));
@@ -192,10 +223,9 @@ __device__ __forceinline__ int eng_run_reg(const Eng &E, EngCtx &c, const Packed
     constexpr unsigned QMASK = K == 8 ? 0xffffffffu : ((1u << (4 * K)) - 1u);
     const ExShared &X = *E.X;
     const int lane = E.lane;
-    extern __shared__ int32_t smem_all[];
-    int32_t *ring = smem_all + (threadIdx.x >> 5) * (EX_SMEM_WARP / 4);
-    uint8_t *ca = (uint8_t *)(ring + EX_ROWS * EX_RW);
-    uint32_t *cbw = (uint32_t *)(ca + EX_CR);
+    int32_t *ring = eng_warp_smem<Cfg>();
+    uint8_t *ca = (uint8_t *)(ring + Cfg::BASE_OFF);
+    uint32_t *cbw = (uint32_t *)(ca + Cfg::CR);
     const int N = c.N, M = c.M;
     const int NEG4 = PMN_NEG * 4;
     const int max_diff4 = 4 * PMN_GOOD_SCORE * c.breaklen;
@@ -234,29 +264,35 @@ __device__ __forceinline__ int eng_run_reg(const Eng &E, EngCtx &c, const Packed
         const int b = Bb + ((lane - Bb) & 31), jbase = b << LOGK;
         Bb_last = Bb;
         // base rings
-        { const int need_i = d - clo < N ? d - clo : N; while (c.ca_hi <= need_i) eng_fill_ref(X, c, ca, lane); }
-        while (c.cb_hi <= chi + 7) eng_fill_qry(Q, c, cbw, lane);
+        { const int need_i = d - clo < N ? d - clo : N; while (c.ca_hi <= need_i) eng_fill_ref<Cfg>(X, c, ca, lane); }
+        while (c.cb_hi <= chi + 7) eng_fill_qry<Cfg>(Q, c, cbw, lane);
         const int i0 = d - jbase;       // reference index of slot 0
         if (K > 1 && b != b_cur) {
 #pragma unroll
-            for (int s = K - 1; s >= 1; s--) aw = (aw << 4) | ca[(i0 - s) & (EX_CR - 1)];
+            for (int s = K - 1; s >= 1; s--) aw = (aw << 4) | ca[(i0 - s) & (Cfg::CR - 1)];
         }
         b_cur = b;
-        aw = (aw << 4) | ca[i0 & (EX_CR - 1)];
-        const unsigned qw = (cbw[(jbase >> 3) & (EX_CR / 8 - 1)] >> (4 * (jbase & 7))) & QMASK;
+        aw = (aw << 4) | ca[i0 & (Cfg::CR - 1)];
+        const unsigned qw = (cbw[(jbase >> 3) & (Cfg::CR / 8 - 1)] >> (4 * (jbase & 7))) & QMASK;
         const unsigned x = aw ^ qw;
-        // traceback row
-        uint8_t *trow = nullptr;
+        // traceback row: in shared memory while it fits (short alignments never leave it), else global
+        uint8_t *trow = nullptr; int trow_s = -1;
         if (!c.search) {
-            if (c.tcur + W > c.tend) {
-                unsigned long long at = 0;
-                if (lane == 0) at = atomicAdd(X.counters + 1, (unsigned long long)EX_ARENA_CHUNK);
-                at = __shfl_sync(0xffffffffu, at, 0);
-                if (at + EX_ARENA_CHUNK > X.arena_cap) { c.arena_fail = true; break; }
-                c.tcur = X.arena + at; c.tend = c.tcur + EX_ARENA_CHUNK;
+            if (c.tb_sm_open && d < Cfg::META_N && c.tb_sm_used + W <= Cfg::TBROWS_BYTES) {
+                trow_s = c.tb_sm_used; c.tb_sm_used += W; c.tb_sm_n = d + 1;
+                if (lane == 0) ring[Cfg::META_OFF + d] = (trow_s << 16) | ((Bb << LOGK) & 0xffff);
+            } else {
+                c.tb_sm_open = false;
+                if (c.tcur + W > c.tend) {
+                    unsigned long long at = 0;
+                    if (lane == 0) at = atomicAdd(X.counters + 1, (unsigned long long)EX_ARENA_CHUNK);
+                    at = __shfl_sync(0xffffffffu, at, 0);
+                    if (at + EX_ARENA_CHUNK > X.arena_cap) { c.arena_fail = true; break; }
+                    c.tcur = X.arena + at; c.tend = c.tcur + EX_ARENA_CHUNK;
+                }
+                trow = c.tcur; c.tcur += W;
+                if (lane == 0) { tboff[d] = trow; tblo[d] = Bb << LOGK; }
             }
-            trow = c.tcur; c.tcur += W;
-            if (lane == 0) { tboff[d] = trow; tblo[d] = Bb << LOGK; }
         }
         // left neighbour of slot 0: slot K-1 of the lane below (ring rotation)
         int LD = __shfl_sync(0xffffffffu, pD[K - 1], (lane + 31) & 31);
@@ -285,11 +321,20 @@ __device__ __forceinline__ int eng_run_reg(const Eng &E, EngCtx &c, const Packed
             cm[s] = act ? (mc & ~3) : INT32_MIN;
         }
         if (!c.search) {
-            uint8_t *dst = trow + (((lane - Bb) & 31) << LOGK);
-            if (K == 1) *dst = (uint8_t)tbw[0];
-            else if (K == 2) *(uint16_t *)dst = (uint16_t)tbw[0];
-            else if (K == 4) *(uint32_t *)dst = tbw[0];
-            else *(uint2 *)dst = make_uint2(tbw[0], tbw[(K + 3) / 4 - 1]);
+            const int at = ((lane - Bb) & 31) << LOGK;
+            if (trow_s >= 0) {
+                uint8_t *dst = (uint8_t *)(ring + Cfg::TBROWS_OFF) + trow_s + at;
+                if (K == 1) *dst = (uint8_t)tbw[0];
+                else if (K == 2) *(uint16_t *)dst = (uint16_t)tbw[0];
+                else if (K == 4) *(uint32_t *)dst = tbw[0];
+                else *(uint2 *)dst = make_uint2(tbw[0], tbw[(K + 3) / 4 - 1]);
+            } else {
+                uint8_t *dst = trow + at;
+                if (K == 1) *dst = (uint8_t)tbw[0];
+                else if (K == 2) *(uint16_t *)dst = (uint16_t)tbw[0];
+                else if (K == 4) *(uint32_t *)dst = tbw[0];
+                else *(uint2 *)dst = make_uint2(tbw[0], tbw[(K + 3) / 4 - 1]);
+            }
         }
         int lmax = cm[0];
 #pragma unroll
@@ -343,11 +388,33 @@ __device__ __noinline__ EngCtx eng_run_wide(const Eng &E, EngCtx c, const Packed
     const int N = c.N, M = c.M, dir = c.dir;
     const int max_diff = PMN_GOOD_SCORE * c.breaklen;
     bool in_smem = true;
-    extern __shared__ int32_t smem_all[];
-    int32_t *base = smem_all + (threadIdx.x >> 5) * (EX_SMEM_WARP / 4); int stride = EX_RW; int mask = EX_RW - 1;
+    typedef CfgBig Cfg;
+    int32_t *base = eng_warp_smem<Cfg>(); int stride = Cfg::RW; int mask = Cfg::RW - 1;
     int bpp = 0, bp = 1, bc = 2;
 #define SC(buf, st, j) base[((buf) * 4 + (st)) * stride + ((j) & mask)]
-    for (; c.d <= N + M; c.d++) {
+    if (!c.search && c.tb_sm_n > 0) {
+        // the rows this path is about to use hold the traceback of the first diagonals: move it to global memory
+        const int32_t *meta = base + Cfg::META_OFF;
+        const uint8_t *rows = (const uint8_t *)(base + Cfg::TBROWS_OFF);
+        for (int dd = 0; dd < c.tb_sm_n; dd++) {
+            const int m0 = meta[dd], off = m0 >> 16, end = dd + 1 < c.tb_sm_n ? (meta[dd + 1] >> 16) : c.tb_sm_used;
+            const int len = end - off;
+            if (c.tcur + len > c.tend) {
+                unsigned long long at = 0;
+                if (lane == 0) at = atomicAdd(X.counters + 1, (unsigned long long)EX_ARENA_CHUNK);
+                at = __shfl_sync(0xffffffffu, at, 0);
+                if (at + EX_ARENA_CHUNK > X.arena_cap) { c.arena_fail = true; break; }
+                c.tcur = X.arena + at; c.tend = c.tcur + EX_ARENA_CHUNK;
+            }
+            for (int k = lane; k < len; k += 32) c.tcur[k] = rows[off + k];
+            if (lane == 0) { tboff[dd] = c.tcur; tblo[dd] = (int)(short)(m0 & 0xffff); }
+            c.tcur += len;
+        }
+        __syncwarp();
+        c.tb_sm_n = 0;
+    }
+    c.tb_sm_open = false;
+    for (; !c.arena_fail && c.d <= N + M; c.d++) {
         const int d = c.d;
         if (!c.forced && d - c.best_d > c.breaklen) break;
         const int clo = c.tlo > d - N ? c.tlo : d - N, chi = c.thi + 1 < M ? c.thi + 1 : M;
@@ -444,6 +511,7 @@ __device__ __noinline__ EngCtx eng_run_wide(const Eng &E, EngCtx c, const Packed
 // One alignment.  All 32 lanes call with identical arguments and get identical results.
 // Returns reached (0/1); Aend/Bend become the finish cell.  Unless SEARCH, the deltas are
 // appended to the pool: *doff, *dcnt.
+template <class Cfg>
 __device__ __noinline__ int align_engine(const Eng &E, int64_t Abase, int64_t Astart, int64_t &Aend, const PackedView &Q, int64_t Bbase, int64_t Bstart, int64_t &Bend,
                                          unsigned m_o, uint32_t *doff, int32_t *dcnt, int32_t *dasum)
 {
@@ -460,48 +528,52 @@ __device__ __noinline__ int align_engine(const Eng &E, int64_t Abase, int64_t As
         if (lane == 0) atomicOr(X.counters + 4, (unsigned long long)EX_ERR_LOGIC);
         return 0;
     }
-    if (lane == 0) atomicAdd(X.counters + 3, 1ull);
     const long long dbg_t0 = X.dbg ? clock64() : 0;
 
     uint8_t **tboff = (uint8_t **)E.tbp;
     int32_t *tblo = (int32_t *)(E.tbp + (size_t)EX_DMAX * 8);
     int32_t *rev = (int32_t *)(E.tbp + (size_t)EX_DMAX * 12);
     c.tcur = E.tbp + EX_TB_HDR; c.tend = E.tbp + EX_TBW; c.arena_fail = false;
-    if (lane == 0 && !c.search) { tboff[0] = c.tcur; tblo[0] = 0; c.tcur[0] = (uint8_t)(PMN_ST_NONE | PMN_ST_NONE << 2 | PMN_ST_NONE << 4 | PMN_ST_MAT << 6); }
-    if (!c.search) c.tcur += 32;
+    c.tb_sm_used = 32; c.tb_sm_n = 1; c.tb_sm_open = true;      // row 0 = cell (0,0), written below
 
     c.Apos0 = Abase + Astart - 1; c.Bpos0 = Bbase + Bstart - 1;
     c.d = 1; c.tlo = 0; c.thi = 0; c.plo = 0; c.phi = 0; c.pplo = 1; c.pphi = 0;
     c.high = 0; c.best_d = 0; c.best_j = 0; c.reached = 0; c.cells = 0;
     {   // cell (0,0) into the ring; base rings: everything in front of the window matches nothing
-        extern __shared__ int32_t smem_all[];
-        int32_t *ring = smem_all + (threadIdx.x >> 5) * (EX_SMEM_WARP / 4);
-        uint8_t *ca = (uint8_t *)(ring + EX_ROWS * EX_RW);
-        uint32_t *cbw = (uint32_t *)(ca + EX_CR);
-        if (lane == 0) { SCR(1, 0, 0) = PMN_NEG; SCR(1, 1, 0) = PMN_NEG; SCR(1, 2, 0) = 0; }
+        int32_t *ring = eng_warp_smem<Cfg>();
+        uint8_t *ca = (uint8_t *)(ring + Cfg::BASE_OFF);
+        uint32_t *cbw = (uint32_t *)(ca + Cfg::CR);
+        if (lane == 0) {
+            SCR(1, 0, 0) = PMN_NEG; SCR(1, 1, 0) = PMN_NEG; SCR(1, 2, 0) = 0;
+            ring[Cfg::META_OFF] = 0;
+            *(uint8_t *)(ring + Cfg::TBROWS_OFF) = (uint8_t)(PMN_ST_NONE | PMN_ST_NONE << 2 | PMN_ST_NONE << 4 | PMN_ST_MAT << 6);
+        }
 #pragma unroll
-        for (int k = 0; k < EX_CR / 128; k++) ((uint32_t *)ca)[k * 32 + lane] = 0x08080808u;
+        for (int k = 0; k < Cfg::CR / 128; k++) ((uint32_t *)ca)[k * 32 + lane] = 0x08080808u;
         c.ca_hi = 1; c.pa = eng_ref_nibble(X, c, 1 + lane);
         c.cb_hi = 0; c.pb = eng_qry_nibble(Q, c, lane);
         __syncwarp();
-        eng_fill_ref(X, c, ca, lane);
-        eng_fill_qry(Q, c, cbw, lane);
+        eng_fill_ref<Cfg>(X, c, ca, lane);
+        eng_fill_qry<Cfg>(Q, c, cbw, lane);
     }
 
     int mode = 1, path = 0;
     for (;;) {
         int rc;
-        if (mode == 1) rc = eng_run_reg<1>(E, c, Q, tboff, tblo);
-        else if (mode == 2) rc = eng_run_reg<2>(E, c, Q, tboff, tblo);
-        else if (mode == 4) rc = eng_run_reg<4>(E, c, Q, tboff, tblo);
-        else if (mode == 8) rc = eng_run_reg<8>(E, c, Q, tboff, tblo);
-        else { c = eng_run_wide(E, c, Q, tboff, tblo); rc = ENG_DONE; }
+        if (mode > Cfg::MAXK) {
+            if (Cfg::MAXK < 8) return -1;          // too wide for this kernel: the caller hands the alignment to the big one
+            c = eng_run_wide(E, c, Q, tboff, tblo); rc = ENG_DONE;
+        }
+        else if (mode == 1) rc = eng_run_reg<1, Cfg>(E, c, Q, tboff, tblo);
+        else if (mode == 2) rc = eng_run_reg<2, Cfg>(E, c, Q, tboff, tblo);
+        else if (Cfg::MAXK >= 4 && mode == 4) rc = eng_run_reg<(Cfg::MAXK >= 4 ? 4 : 1), Cfg>(E, c, Q, tboff, tblo);
+        else rc = eng_run_reg<(Cfg::MAXK >= 8 ? 8 : 1), Cfg>(E, c, Q, tboff, tblo);
         if (rc == ENG_DONE) break;
         mode = rc == ENG_GROW ? mode * 2 : mode / 2;
         if (mode > path) path = mode;
     }
     const int d = c.d;
-    if (lane == 0) atomicAdd(X.counters + 2, c.cells);
+    if (lane == 0) { atomicAdd(X.counters + 2, c.cells); atomicAdd(X.counters + 3, 1ull); }
     if (X.dbg && lane == 0) {
         const unsigned long long at = atomicAdd(X.counters + 15, 1ull);
         if (at < X.dbg_cap) {
@@ -520,22 +592,32 @@ __device__ __noinline__ int align_engine(const Eng &E, int64_t Abase, int64_t As
 
     if (!c.search) {
         __syncwarp();
+        int32_t *ring = eng_warp_smem<Cfg>();
+        const int32_t *meta = ring + Cfg::META_OFF;
+        const uint8_t *rows = (const uint8_t *)(ring + Cfg::TBROWS_OFF);
+        int32_t *rev_s = ring + Cfg::REV_OFF;
+        const int n_sm = c.tb_sm_n;
         int nrev = 0;
         if (lane == 0) {
+            auto cell = [&](int cd, int cj) -> unsigned {
+                if (cd < n_sm) { const int m0 = meta[cd]; return rows[(m0 >> 16) + cj - (int)(short)(m0 & 0xffff)]; }
+                return tboff[cd][cj - tblo[cd]];
+            };
+            auto emit = [&](int v) { if (nrev < Cfg::REV_N) rev_s[nrev] = v; else rev[nrev] = v; nrev++; };
             int cd = fd, cj = fj;
-            int st = tboff[cd][cj - tblo[cd]] >> 6;
+            int st = cell(cd, cj) >> 6;
             int pending = 0, run = 0;
             while (cd > 0) {
-                const uint8_t b = tboff[cd][cj - tblo[cd]];
+                const unsigned b = cell(cd, cj);
                 if (st == PMN_ST_MAT) { run++; st = (b >> 4) & 3; cd -= 2; cj -= 1; }
                 else {
-                    if (pending) rev[nrev++] = pending * (run + 1);
+                    if (pending) emit(pending * (run + 1));
                     run = 0;
                     if (st == PMN_ST_INS) { pending = 1; st = (b >> 2) & 3; cd -= 1; }
                     else { pending = -1; st = b & 3; cd -= 1; cj -= 1; }
                 }
             }
-            if (pending) rev[nrev++] = pending * (run + 1);
+            if (pending) emit(pending * (run + 1));
         }
         nrev = __shfl_sync(0xffffffffu, nrev, 0);
         __syncwarp();
@@ -545,7 +627,11 @@ __device__ __noinline__ int align_engine(const Eng &E, int64_t Abase, int64_t As
             at = __shfl_sync(0xffffffffu, at, 0);
             if (at + (unsigned long long)nrev > X.pool_cap) { if (lane == 0) atomicOr(X.counters + 4, (unsigned long long)EX_ERR_POOL); return reached; }
             int asum = 0;
-            for (int k = lane; k < nrev; k += 32) { const int dv = rev[nrev - 1 - k]; X.pool[at + k] = dv; asum += dv > 0 ? dv : -dv - 1; }
+            for (int k = lane; k < nrev; k += 32) {
+                const int idx = nrev - 1 - k;
+                const int dv = idx < Cfg::REV_N ? rev_s[idx] : rev[idx];
+                X.pool[at + k] = dv; asum += dv > 0 ? dv : -dv - 1;
+            }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) asum += __shfl_xor_sync(0xffffffffu, asum, o);
             *doff = (uint32_t)at; *dcnt = nrev; *dasum = asum;
@@ -590,7 +676,7 @@ __device__ int forward_job(const Eng &E, const ExSynteny &S, int dirB, int64_t e
     if (targetA - eA + 1 > PMN_MAX_ALIGNMENT_LENGTH) { targetA = eA + PMN_MAX_ALIGNMENT_LENGTH - 1; overflow = 1; m_o |= PMN_OPTIMAL_BIT; }
     if (targetB - eB + 1 > PMN_MAX_ALIGNMENT_LENGTH) { targetB = eB + PMN_MAX_ALIGNMENT_LENGTH - 1; overflow = 1; m_o |= PMN_OPTIMAL_BIT; }
     uint32_t doff; int32_t dcnt, dasum;
-    int reached = align_engine(E, S.Abase, eA, targetA, dirB ? E.X->QR : E.X->QF, dirB ? S.BbaseR : S.BbaseF, eB, targetB, m_o, &doff, &dcnt, &dasum);
+    int reached = align_engine<CfgBig>(E, S.Abase, eA, targetA, dirB ? E.X->QR : E.X->QF, dirB ? S.BbaseR : S.BbaseF, eB, targetB, m_o, &doff, &dcnt, &dasum);
     if (reached && overflow) reached = 0;
     out.endA = (int32_t)targetA; out.endB = (int32_t)targetB; out.dcnt = dcnt; out.doff = doff; out.reached = reached; out.valid = 1; out.asum = dasum;
     return reached;
@@ -598,54 +684,216 @@ __device__ int forward_job(const Eng &E, const ExSynteny &S, int dirB, int64_t e
 
 // ------------------------------------------------------------------------------------ E2: wave 1
 
-__device__ __forceinline__ Eng make_eng(const ExShared &X, int32_t *smem_all)
+__device__ __forceinline__ Eng make_eng(const ExShared &X, int32_t *)
 {
     Eng E;
     const int warp = threadIdx.x >> 5;
     const size_t slot = (size_t)blockIdx.x * EX_WARPS_PER_BLOCK + warp;
     E.X = &X; E.lane = threadIdx.x & 31;
-    E.ssc = smem_all + (size_t)warp * (EX_SMEM_WARP / 4);
+    E.ssc = nullptr;
     E.gsc = X.gscore + slot * (size_t)EX_ROWS * EX_WCAP;
     E.tbp = X.tbpriv + slot * (size_t)EX_TBW;
     E.kid = 0;
     return E;
 }
 
-__global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32) k_ex_wave1(ExShared X)
+__device__ __forceinline__ int run_mismatches(const PackedView &R, int64_t a, const PackedView &Q, int64_t b, int64_t run);
+
+// one thread per match: its forward job (match -> next match), and for the last match of a cluster the
+// cluster-end job (-> target cluster or as far as the score carries).
+//
+// Shortcut (most gaps between two matches are a single substitution): a square window of k <= 20 columns
+// with at most one mismatching column is solved here.  The gap-free path scores >= 3k - 10, any path with
+// a gap has at most k-1 match columns and two gap openings, <= 3(k-1) - 14; the same holds for every prefix,
+// so the engine's traceback would follow the main diagonal: target reached, no deltas.  No cell of such a
+// window can fall 3*breaklen below the high score when breaklen >= 100 (worst cell -223, high <= 60), so the engine would have evaluated the full
+// (k+1)^2 - 1 cells, which is what the counters are credited with.
+__global__ void __launch_bounds__(256) k_ex_jobdesc(ExShared X, ExJobDesc *__restrict__ descA, ExJobDesc *__restrict__ descB)
 {
-    extern __shared__ int32_t smem_all[];
-    Eng E = make_eng(X, smem_all); E.kid = 1;
-    const int lane = E.lane;
-    // pass A: cluster-end extensions (the long ones) first; pass B: match -> next match
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= X.nM) return;
+    const int k = X.mcl[g];
+    const ExCluster c = X.cl[k];
+    const ExSynteny S = X.syn[c.syn];
+    ExJobDesc d;
+    d.Abase = S.Abase; d.Bbase = c.dir ? S.BbaseR : S.BbaseF;
+    d.eA = X.mA[g] + X.mL[g] - 1; d.eB = X.mB[g] + X.mL[g] - 1; d.g = (int32_t)g; d.dir = c.dir;
+    if ((int)g != c.mfirst + c.nm - 1) {
+        d.tA = X.mA[g + 1]; d.tB = X.mB[g + 1]; d.m_o = PMN_FORWARD_ALIGN; d.target = -1;
+        const int n = d.tA - d.eA + 1, m = d.tB - d.eB + 1;
+        if (n == m && n >= 1 && n <= 20 && X.breaklen >= 100 &&
+            run_mismatches(X.R, d.Abase + d.eA - 1, c.dir ? X.QR : X.QF, d.Bbase + d.eB - 1, n) <= 1) {
+            ExJob r; r.endA = d.tA; r.endB = d.tB; r.dcnt = 0; r.target = -1; r.doff = 0; r.reached = 1; r.valid = 1; r.asum = 0;
+            X.jobs[g] = r;
+            atomicAdd(X.counters + 2, (unsigned long long)((n + 1) * (m + 1) - 1));
+            atomicAdd(X.counters + 3, 1ull);
+            d.m_o = -1;
+        }
+        descB[g] = d;
+        return;
+    }
+    d.m_o = -1; d.tA = d.tB = 0; d.target = -1;
+    descB[g] = d;                                       // the last match has no inner job
     if (X.do_extend) {
-        for (;;) {
-            unsigned long long k = 0;
-            if (lane == 0) k = atomicAdd(X.counters + 5, 1ull);
-            k = __shfl_sync(0xffffffffu, k, 0);
-            if (k >= (unsigned long long)X.nC) break;
-            const ExCluster c = X.cl[k];
-            const ExSynteny S = X.syn[c.syn];
-            const int g = c.mfirst + c.nm - 1;
-            int64_t targetA = S.lenA, targetB = S.lenB;
-            const int end = S.cfirst + S.nC;
-            int tc = get_forward_target_cluster(X, (int)k, end, targetA, targetB);
-            unsigned m_o = PMN_FORWARD_ALIGN; if (tc == end) m_o |= PMN_OPTIMAL_BIT;
-            ExJob r; r.target = tc;
-            forward_job(E, S, c.dir, (int64_t)X.mA[g] + X.mL[g] - 1, (int64_t)X.mB[g] + X.mL[g] - 1, targetA, targetB, m_o, r);
-            if (lane == 0) X.jobs[g] = r;
+        int64_t targetA = S.lenA, targetB = S.lenB;
+        const int end = S.cfirst + S.nC;
+        const int tc = get_forward_target_cluster(X, k, end, targetA, targetB);
+        d.tA = (int32_t)targetA; d.tB = (int32_t)targetB; d.target = tc;
+        d.m_o = PMN_FORWARD_ALIGN | (tc == end ? PMN_OPTIMAL_BIT : 0);
+    }
+    descA[k] = d;
+}
+
+// A forward alignment (not OPTIMAL) over a window of at most 31 x 31 bases, the bulk of wave 1.  With
+// breaklen >= 134 no cell of such a window can fall 3*breaklen below the running high score (worst cell
+// >= -7*31 - 4*30 - 7, high <= 93), so the engine would evaluate the full matrix and finish on the target
+// cell: the band, high-score and trimming logic drop out.  Lane j owns column j for the whole alignment,
+// the traceback (one byte per cell, 32 per anti-diagonal) stays in shared memory.
+template <class Cfg>
+__device__ __noinline__ void eng_small_full(const Eng &E, const ExShared &X, const ExJobDesc &d, int N, int M, uint32_t *doff, int32_t *dcnt, int32_t *dasum)
+{
+    const int lane = E.lane;
+    int32_t *ring = eng_warp_smem<Cfg>();
+    uint8_t *rows = (uint8_t *)(ring + Cfg::TBROWS_OFF);
+    int32_t *rev_s = ring + Cfg::REV_OFF;
+    const PackedView &Q = d.dir ? X.QR : X.QF;
+    const int NEG4 = PMN_NEG * 4;
+    *doff = 0; *dcnt = 0; *dasum = 0;
+    // lane l holds reference base A'[l] and query base B'[l] (index 0: nothing)
+    int an = 8, qn = 4;
+    if (lane >= 1 && lane <= N) { const int b = pmn_base_at(X.R, d.Abase + d.eA - 1 + (lane - 1)); an = b < 4 ? b : 8; }
+    if (lane >= 1 && lane <= M) { const int b = pmn_base_at(Q, d.Bbase + d.eB - 1 + (lane - 1)); qn = b < 4 ? b : 4; }
+    int pD = NEG4, pI = NEG4, pM = lane == 0 ? 0 : NEG4, qD = NEG4, qI = NEG4, qM = NEG4;
+    if (lane == 0) rows[0] = (uint8_t)(PMN_ST_NONE | PMN_ST_NONE << 2 | PMN_ST_NONE << 4 | PMN_ST_MAT << 6);
+    const int D = N + M;
+#pragma unroll 2
+    for (int dd = 1; dd <= D; dd++) {
+        int lD = __shfl_up_sync(0xffffffffu, pD, 1), lI = __shfl_up_sync(0xffffffffu, pI, 1), lM = __shfl_up_sync(0xffffffffu, pM, 1);
+        const int i = dd - lane;
+        const int ai = __shfl_sync(0xffffffffu, an, i & 31);
+        if (lane == 0) { lD = NEG4; lI = NEG4; lM = NEG4; }
+        const bool act = (unsigned)i <= (unsigned)N && lane <= M;
+        const int sc = ((ai ^ qn) == 0 && i >= 1) ? 4 * PMN_GOOD_SCORE : 4 * PMN_BAD_SCORE;
+        const int mD = __vimax3_s32(lD + (4 * PMN_CONT_GAP_SCORE + PMN_ST_DEL), lI + (4 * PMN_OPEN_GAP_SCORE + PMN_ST_INS), lM + (4 * PMN_OPEN_GAP_SCORE + PMN_ST_MAT));
+        const int mI = __vimax3_s32(pD + (4 * PMN_OPEN_GAP_SCORE + PMN_ST_DEL), pI + (4 * PMN_CONT_GAP_SCORE + PMN_ST_INS), pM + (4 * PMN_OPEN_GAP_SCORE + PMN_ST_MAT));
+        const int mM = __vimax3_s32(qD + sc + PMN_ST_DEL, qI + sc + PMN_ST_INS, qM + sc + PMN_ST_MAT);
+        const int vD = mD & ~3, vI = mI & ~3, vM = mM & ~3;
+        const int mc = __vimax3_s32(vD + PMN_ST_DEL, vI + PMN_ST_INS, vM + PMN_ST_MAT);
+        rows[dd * 32 + lane] = (uint8_t)(((unsigned)mD & 3u) | (((unsigned)mI & 3u) << 2) | (((unsigned)mM & 3u) << 4) | (((unsigned)mc & 3u) << 6));
+        qD = lD; qI = lI; qM = lM;
+        pD = act ? vD : NEG4; pI = act ? vI : NEG4; pM = act ? vM : NEG4;
+    }
+    if (lane == 0) { atomicAdd(X.counters + 2, (unsigned long long)((N + 1) * (M + 1) - 1)); atomicAdd(X.counters + 3, 1ull); }
+    __syncwarp();
+    int nrev = 0;
+    if (lane == 0) {
+        int cd = D, cj = M;
+        int st = rows[cd * 32 + cj] >> 6;
+        int pending = 0, run = 0;
+        while (cd > 0) {
+            const unsigned b = rows[cd * 32 + cj];
+            if (st == PMN_ST_MAT) { run++; st = (b >> 4) & 3; cd -= 2; cj -= 1; }
+            else {
+                if (pending) rev_s[nrev++] = pending * (run + 1);
+                run = 0;
+                if (st == PMN_ST_INS) { pending = 1; st = (b >> 2) & 3; cd -= 1; }
+                else { pending = -1; st = b & 3; cd -= 1; cj -= 1; }
+            }
+        }
+        if (pending) rev_s[nrev++] = pending * (run + 1);
+    }
+    nrev = __shfl_sync(0xffffffffu, nrev, 0);
+    __syncwarp();
+    if (nrev > 0) {
+        unsigned long long at = 0;
+        if (lane == 0) at = atomicAdd(X.counters + 0, (unsigned long long)nrev);
+        at = __shfl_sync(0xffffffffu, at, 0);
+        if (at + (unsigned long long)nrev > X.pool_cap) { if (lane == 0) atomicOr(X.counters + 4, (unsigned long long)EX_ERR_POOL); return; }
+        int asum = 0;
+        for (int k = lane; k < nrev; k += 32) { const int dv = rev_s[nrev - 1 - k]; X.pool[at + k] = dv; asum += dv > 0 ? dv : -dv - 1; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) asum += __shfl_xor_sync(0xffffffffu, asum, o);
+        *doff = (uint32_t)at; *dcnt = nrev; *dasum = asum;
+    }
+    __syncwarp();
+}
+
+// returns false when the alignment is too wide for this kernel's layout (CfgSmall only)
+template <class Cfg>
+__device__ __forceinline__ bool wave1_run(const Eng &E, const ExShared &X, const ExJobDesc &d)
+{
+    {
+        const int N = d.tA - d.eA + 1, M = d.tB - d.eB + 1;
+        if (d.m_o == PMN_FORWARD_ALIGN && N >= 1 && M >= 1 && N <= 31 && M <= 31 && X.breaklen >= 134) {
+            uint32_t doff; int32_t dcnt, dasum;
+            eng_small_full<Cfg>(E, X, d, N, M, &doff, &dcnt, &dasum);
+            if (E.lane == 0) {
+                ExJob r; r.endA = d.tA; r.endB = d.tB; r.dcnt = dcnt; r.doff = doff; r.reached = 1; r.valid = 1; r.asum = dasum; r.target = d.target;
+                X.jobs[d.g] = r;
+            }
+            return true;
         }
     }
+    int64_t targetA = d.tA, targetB = d.tB; unsigned m_o = (unsigned)d.m_o;
+    int overflow = 0;
+    if (targetA - d.eA + 1 > PMN_MAX_ALIGNMENT_LENGTH) { targetA = d.eA + PMN_MAX_ALIGNMENT_LENGTH - 1; overflow = 1; m_o |= PMN_OPTIMAL_BIT; }
+    if (targetB - d.eB + 1 > PMN_MAX_ALIGNMENT_LENGTH) { targetB = d.eB + PMN_MAX_ALIGNMENT_LENGTH - 1; overflow = 1; m_o |= PMN_OPTIMAL_BIT; }
+    uint32_t doff; int32_t dcnt, dasum;
+    int reached = align_engine<Cfg>(E, d.Abase, d.eA, targetA, d.dir ? X.QR : X.QF, d.Bbase, d.eB, targetB, m_o, &doff, &dcnt, &dasum);
+    if (reached < 0) return false;
+    if (reached && overflow) reached = 0;
+    if (E.lane == 0) {
+        ExJob r; r.endA = (int32_t)targetA; r.endB = (int32_t)targetB; r.dcnt = dcnt; r.doff = doff; r.reached = reached; r.valid = 1; r.asum = dasum; r.target = d.target;
+        X.jobs[d.g] = r;
+    }
+    return true;
+}
+
+#define EX_JOB_BATCH 4
+#define EX_SMALL_BLOCKS_PER_SM 6
+
+// Wave 1, small kernel: every match -> next match alignment, EX_JOB_BATCH descriptors per fetch, in the
+// 5 KB layout (24 warps per SM).  The few alignments whose band outgrows two columns per lane are
+// queued for the big kernel.
+__global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32, EX_SMALL_BLOCKS_PER_SM) k_ex_wave1_small(ExShared X)
+{
+    Eng E = make_eng(X, nullptr); E.kid = 1;
+    const int lane = E.lane;
     for (;;) {
-        unsigned long long g = 0;
-        if (lane == 0) g = atomicAdd(X.counters + 6, 1ull);
-        g = __shfl_sync(0xffffffffu, g, 0);
-        if (g >= (unsigned long long)X.nM) break;
-        const ExCluster c = X.cl[X.mcl[g]];
-        if ((int)g == c.mfirst + c.nm - 1) continue;
-        const ExSynteny S = X.syn[c.syn];
-        ExJob r; r.target = -1;
-        forward_job(E, S, c.dir, (int64_t)X.mA[g] + X.mL[g] - 1, (int64_t)X.mB[g] + X.mL[g] - 1, X.mA[g + 1], X.mB[g + 1], PMN_FORWARD_ALIGN, r);
-        if (lane == 0) X.jobs[g] = r;
+        unsigned long long g0 = 0;
+        if (lane == 0) g0 = atomicAdd(X.counters + 6, (unsigned long long)EX_JOB_BATCH);
+        g0 = __shfl_sync(0xffffffffu, g0, 0);
+        if (g0 >= (unsigned long long)X.nM) break;
+        ExJobDesc mine; mine.m_o = -1;
+        if (lane < EX_JOB_BATCH && g0 + lane < (unsigned long long)X.nM) mine = X.descB[g0 + lane];
+#pragma unroll 1
+        for (int t = 0; t < EX_JOB_BATCH; t++) {
+            ExJobDesc d;
+            d.Abase = __shfl_sync(0xffffffffu, mine.Abase, t); d.Bbase = __shfl_sync(0xffffffffu, mine.Bbase, t);
+            d.eA = __shfl_sync(0xffffffffu, mine.eA, t); d.eB = __shfl_sync(0xffffffffu, mine.eB, t);
+            d.tA = __shfl_sync(0xffffffffu, mine.tA, t); d.tB = __shfl_sync(0xffffffffu, mine.tB, t);
+            d.g = __shfl_sync(0xffffffffu, mine.g, t); d.dir = __shfl_sync(0xffffffffu, mine.dir, t);
+            d.m_o = __shfl_sync(0xffffffffu, mine.m_o, t); d.target = -1;
+            if (d.m_o >= 0 && !wave1_run<CfgSmall>(E, X, d) && lane == 0)
+                X.overflow[atomicAdd(X.counters + 7, 1ull)] = d.g;
+        }
+    }
+}
+
+// Wave 1, big kernel: the cluster-end extensions (break-length searches, bands up to hundreds of cells)
+// and what the small kernel handed over.
+__global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32, 4) k_ex_wave1_big(ExShared X)
+{
+    Eng E = make_eng(X, nullptr); E.kid = 1;
+    const int lane = E.lane;
+    const unsigned long long nA = X.do_extend ? (unsigned long long)X.nC : 0ull, nO = X.counters[7];
+    for (;;) {
+        unsigned long long k = 0;
+        if (lane == 0) k = atomicAdd(X.counters + 5, 1ull);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= nA + nO) break;
+        const ExJobDesc d = k < nA ? X.descA[k] : X.descB[X.overflow[k - nA]];
+        if (d.m_o >= 0) wave1_run<CfgBig>(E, X, d);
     }
 }
 
@@ -817,7 +1065,7 @@ __device__ int st_extend_backward(Stitch &T, int tp, int dirB)
     if (a.sA - targetA + 1 > PMN_MAX_ALIGNMENT_LENGTH) { targetA = a.sA - PMN_MAX_ALIGNMENT_LENGTH + 1; overflow = 1; m_o |= PMN_OPTIMAL_BIT; }
     if (a.sB - targetB + 1 > PMN_MAX_ALIGNMENT_LENGTH) { targetB = a.sB - PMN_MAX_ALIGNMENT_LENGTH + 1; overflow = 1; m_o |= PMN_OPTIMAL_BIT; }
     const PackedView &Q = dirB ? X.QR : X.QF; const int64_t Bbase = dirB ? S.BbaseR : S.BbaseF;
-    int reached = align_engine(*T.E, S.Abase, a.sA, targetA, Q, Bbase, a.sB, targetB, m_o, nullptr, nullptr, nullptr);
+    int reached = align_engine<CfgBig>(*T.E, S.Abase, a.sA, targetA, Q, Bbase, a.sB, targetB, m_o, nullptr, nullptr, nullptr);
     if (overflow || tp < 0) reached = 0;
     if (reached) {
         // merge: the target alignment is extended (forced) up to this one's start and absorbs it
@@ -827,7 +1075,7 @@ __device__ int st_extend_backward(Stitch &T, int tp, int dirB)
         T.cur.eA += a.eA - a.sA; T.cur.eB += a.eB - a.sB;
     } else {
         int64_t eA = a.sA, eB = a.sB; uint32_t doff; int32_t dcnt, dasum;
-        align_engine(*T.E, S.Abase, targetA, eA, Q, Bbase, targetB, eB, PMN_FORCED_FORWARD_ALIGN, &doff, &dcnt, &dasum);
+        align_engine<CfgBig>(*T.E, S.Abase, targetA, eA, Q, Bbase, targetB, eB, PMN_FORCED_FORWARD_ALIGN, &doff, &dcnt, &dasum);
         if (dcnt > 0) cur_append(T, 0, doff, dcnt, 0, dcnt);
         T.cur.sA = (int32_t)targetA; T.cur.sB = (int32_t)targetB; T.cur.P = (int32_t)targetA - 1 + dasum;
     }
@@ -837,8 +1085,7 @@ __device__ int st_extend_backward(Stitch &T, int tp, int dirB)
 // extendClusters for one synteny; every lane runs the same control flow on the same values
 __global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32) k_ex_stitch(ExShared X, uint8_t *fused)
 {
-    extern __shared__ int32_t smem_all[];
-    Eng E = make_eng(X, smem_all); E.kid = 2;
+    Eng E = make_eng(X, nullptr); E.kid = 2;
     const int lane = E.lane;
     const int s = blockIdx.x * EX_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     if (s >= X.nS) return;
@@ -1251,7 +1498,8 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     // ---- E2/E3 storage
     const int blocks1 = c->sm_count * 4;                      // 4 warps per block, 4 blocks per SM
     const int blocks_st = (nS + EX_WARPS_PER_BLOCK - 1) / EX_WARPS_PER_BLOCK;
-    const int nslots = std::max(blocks1, blocks_st) * EX_WARPS_PER_BLOCK;
+    const int nslots = std::max(blocks1, blocks_st) * EX_WARPS_PER_BLOCK;                 // warps that may run the wide fallback (global score rows)
+    const int nslots_tb = std::max(nslots, c->sm_count * EX_SMALL_BLOCKS_PER_SM * EX_WARPS_PER_BLOCK);   // warps that keep a private traceback header
     const size_t pool_cap = (size_t)std::max<int64_t>(1 << 20, 8 * nm + (ref->n + q->n) / 8);
     const size_t arena_cap = (size_t)1 << 31;
     const size_t ncap_al = (size_t)nm, ncap_nodes = 3 * (size_t)nm + 8 * (size_t)nS;
@@ -1259,7 +1507,7 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     const size_t l_bytes = npad * 2 + 8 * (size_t)nS + 64;      // fused, anyfail, syn_nal (2 x nS)
     if (S.ex_i.ensure(sizeof(ExJob) * (size_t)nm) || S.ex_j.ensure(sizeof(ExAlign) * ncap_al) || S.ex_k.ensure(sizeof(ExNode) * ncap_nodes) ||
         S.ex_pool.ensure(4 * pool_cap) || S.ex_arena.ensure(arena_cap) || S.ex_scores.ensure(4 * (size_t)EX_ROWS * EX_WCAP * (size_t)nslots) ||
-        S.ex_tb.ensure((size_t)EX_TBW * (size_t)nslots) || S.ex_counters.ensure(128) || S.ex_l.ensure(l_bytes) ||
+        S.ex_tb.ensure((size_t)EX_TBW * (size_t)nslots_tb) || S.ex_counters.ensure(128) || S.ex_l.ensure(l_bytes) ||
         S.ex_tbidx.ensure(8 * 3 * (size_t)(nm + 1)) || S.ex_a.ensure(8 * h.size() + 0) || S.cl_l.ensure(sizeof(ExCSum) * (size_t)np)) return -3;
     PMN_CUDA_OK(cudaMemsetAsync(S.ex_i.p, 0, sizeof(ExJob) * (size_t)nm, st));
     PMN_CUDA_OK(cudaMemsetAsync(S.ex_counters.p, 0, 128, st));
@@ -1284,6 +1532,9 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     ExCSum *cs = S.cl_l.as<ExCSum>();      // the clustering scratch is free by now
     X.cs = cs;
     PMN_CUDA_OK(cudaMemsetAsync(markkey, 0, 8 * (size_t)(nm + 1), st));
+    if (S.ex_desc.ensure(sizeof(ExJobDesc) * (size_t)(np + nm + 1) + 4 * (size_t)(nm + 1))) return -3;
+    ExJobDesc *descA = S.ex_desc.as<ExJobDesc>(), *descB = descA + np;
+    X.descA = descA; X.descB = descB; X.overflow = (int32_t *)(descB + nm + 1);
     const char *joblog = getenv("PMN_JOBLOG");
     X.dbg = nullptr; X.dbg_cap = 0;
     if (joblog) {
@@ -1292,15 +1543,23 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
         X.dbg = S.ex_dbg.as<int4>();
     }
 
-    const size_t smem = (size_t)EX_WARPS_PER_BLOCK * EX_SMEM_WARP;
+    const size_t smem = (size_t)EX_WARPS_PER_BLOCK * CfgBig::WARP_BYTES, smem_small = (size_t)EX_WARPS_PER_BLOCK * CfgSmall::WARP_BYTES;
     if (!c->smem_attr_set) {
-        PMN_CUDA_OK(cudaFuncSetAttribute(k_ex_wave1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PMN_CUDA_OK(cudaFuncSetAttribute(k_ex_wave1_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PMN_CUDA_OK(cudaFuncSetAttribute(k_ex_wave1_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small));
         PMN_CUDA_OK(cudaFuncSetAttribute(k_ex_stitch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         c->smem_attr_set = true;
     }
     int b1 = blocks1; { int64_t need = (nm + EX_WARPS_PER_BLOCK - 1) / EX_WARPS_PER_BLOCK; if (need < b1) b1 = (int)need; if (b1 < 1) b1 = 1; }
+    k_ex_jobdesc<<<gm, 256, 0, st>>>(X, descA, descB);
     PMN_CUDA_OK(cudaEventRecord(c->ev[8], st));
-    k_ex_wave1<<<b1, EX_WARPS_PER_BLOCK * 32, smem, st>>>(X);
+    {
+        int bs = c->sm_count * EX_SMALL_BLOCKS_PER_SM;
+        const int64_t need = (nm + EX_WARPS_PER_BLOCK * EX_JOB_BATCH - 1) / (EX_WARPS_PER_BLOCK * EX_JOB_BATCH);
+        if (need < bs) bs = (int)std::max<int64_t>(1, need);
+        k_ex_wave1_small<<<bs, EX_WARPS_PER_BLOCK * 32, smem_small, st>>>(X);
+    }
+    k_ex_wave1_big<<<b1, EX_WARPS_PER_BLOCK * 32, smem, st>>>(X);
     PMN_CUDA_OK(cudaEventRecord(c->ev[9], st));
     PMN_D2H(c, (unsigned long long *)S.pinned + 24, X.counters + 2, 8);      // cells evaluated by wave 1
     k_ex_jobmeta<<<(unsigned)((nm + 1 + 255) / 256), 256, 0, st>>>(X.jobs, mcl, cl, pstart, ppos, nm, dcnt, pkey, anyfail);
@@ -1309,7 +1568,7 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     k_ex_csum<<<gp, 256, 0, st>>>(X, cs);
     k_ex_stitch<<<blocks_st, EX_WARPS_PER_BLOCK * 32, smem, st>>>(X, fused);
     PMN_CUDA_OK(cudaEventRecord(c->ev[10], st));
-    launches += 10;
+    launches += 12;
 
     // ---- E4
     if (S.ex_c.ensure(4 * 5 * (size_t)(nm + 1) + 64)) return -3;     // al_syn, al_slot, dcount, dstart, slot2out  (pstart/ppos are dead now)

@@ -43,7 +43,7 @@ class Stats(C.Structure):
 
 # every symbol include/pmnucmer.h declares (tests check the .so exports all of them)
 SYMBOLS = [
-    "pmn_default_opts", "pmn_ctx_create", "pmn_ctx_destroy", "pmn_last_error", "pmn_device_count",
+    "pmn_default_opts", "pmn_ctx_create", "pmn_ctx_destroy", "pmn_last_error", "pmn_device_count", "pmn_alloc_count",
     "pmn_ctx_stream", "pmn_ctx_counters", "pmn_measure_int32_peak",
     "pmn_seq_from_fasta", "pmn_seq_from_file", "pmn_seq_free", "pmn_seq_bases", "pmn_seq_records",
     "pmn_index_build", "pmn_index_free", "pmn_index_image", "pmn_index_image_bytes", "pmn_index_alloc", "pmn_index_adopt", "pmn_align", "pmn_seed_part", "pmn_align_anchors", "pmn_result_delta", "pmn_result_stats",
@@ -71,6 +71,7 @@ def lib():
         L.pmn_default_opts.argtypes = [C.POINTER(Opts)]
         L.pmn_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
         L.pmn_ctx_destroy.argtypes = [vp]
+        L.pmn_alloc_count.restype = i64
         L.pmn_last_error.argtypes = [vp]; L.pmn_last_error.restype = cp
         L.pmn_ctx_stream.argtypes = [vp]; L.pmn_ctx_stream.restype = vp
         L.pmn_ctx_counters.argtypes = [vp, i64p]
@@ -114,6 +115,10 @@ def lib():
         L.pmn_sched_align_files.argtypes = [vp, C.c_int, C.POINTER(cp), C.POINTER(cp), C.POINTER(cp), C.POINTER(Opts)]
         _LIB = L
     return _LIB
+
+
+def alloc_count() -> int:
+    return lib().pmn_alloc_count()
 
 
 def index_image_bytes(n_bases: int) -> int:

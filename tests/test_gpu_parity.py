@@ -45,6 +45,8 @@ def assert_same_as_oracle(oracle, g, ref, qry, **kw):
     for a, b, what in zip(g["alignments"], r.alignments(), ("alignment rows", "delta offsets", "deltas")):
         assert np.array_equal(a, b), what + " differ"
     assert g["delta"] == r.delta("ref.fa", "qry.fa"), ".delta text differs"
+    # dp_cells is NOT a parity quantity: wave 1 aligns every match -> next match gap up front, including
+    # those of clusters that extendClusters later skips as shadowed (tools/cells_check.py lists both counts)
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
