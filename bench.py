@@ -70,6 +70,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
+    def wait_first_sample(self, timeout=15.0):
+        """nvidia-smi takes up to a second to come up and holds driver locks while it does: the
+        warm-up and the timed region start only after its first sample has arrived."""
+        t = time.time()
+        while self.proc and not self.rows and time.time() - t < timeout and self.proc.poll() is None:
+            time.sleep(0.05)
+
     def stop(self):
         if self.proc:
             self.proc.terminate()
@@ -188,6 +195,8 @@ def run_gpu(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()          # before the warm-up: nvidia-smi's own start-up must not land in the timed region
+        sampler.wait_first_sample()
+    barrier()
     for _ in range(args.warmup):
         step_resident(resident)
     ms_res, cnt_res = timed(lambda: step_resident(resident), args.steps)
@@ -358,7 +367,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="weak", choices=["weak", "strong"])

@@ -28,8 +28,15 @@ int pmn_set_error(int code, const char *fmt, ...)
 
 extern "C" const char *pmn_last_error(const pmn_ctx *) { return g_err.msg; }
 
+thread_local cudaStream_t pmn_tls_stream = nullptr;
+
 static std::atomic<long long> g_allocs{0};
-void pmn_count_alloc() { g_allocs++; }
+void pmn_count_alloc(size_t bytes, size_t had)
+{
+    g_allocs++;
+    static const bool log = getenv("PMN_ALLOC_LOG") != nullptr;      // which buffers still grow at steady state
+    if (log) fprintf(stderr, "[pmn] cudaMalloc %zu bytes (buffer had %zu)\n", bytes, had);
+}
 extern "C" int64_t pmn_alloc_count(void) { return (int64_t)g_allocs.load(); }
 
 extern "C" void pmn_default_opts(pmn_opts *o)
@@ -50,7 +57,7 @@ void pmn_scratch_free(Scratch *s)
                        &s->cl_a, &s->cl_b, &s->cl_c, &s->cl_d, &s->cl_e, &s->cl_f, &s->cl_g, &s->cl_h, &s->cl_i, &s->cl_j, &s->cl_k, &s->cl_l,
                        &s->cl_matches, &s->cl_recs, &s->cl_counters,
                        &s->ex_a, &s->ex_b, &s->ex_c, &s->ex_d, &s->ex_e, &s->ex_f, &s->ex_g, &s->ex_h, &s->ex_i, &s->ex_j, &s->ex_k, &s->ex_l,
-                       &s->ex_scores, &s->ex_tb, &s->ex_tbidx, &s->ex_pool, &s->ex_counters, &s->ex_arena, &s->ex_dbg, &s->ex_desc };
+                       &s->ex_scores, &s->ex_tb, &s->ex_tbidx, &s->ex_pool, &s->ex_counters, &s->ex_arena, &s->ex_dbg, &s->ex_desc, &s->ex_tkey, &s->ex_tscratch };
     for (DevBuf *b : bufs) b->release();
     if (s->pinned) cudaFreeHost(s->pinned);
     delete s;
@@ -77,6 +84,11 @@ extern "C" int pmn_ctx_create(int device, pmn_ctx **out)
     pmn_ctx *c = new pmn_ctx();
     c->device = device; c->sm_count = prop.multiProcessorCount;
     PMN_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {   // freed blocks stay in the device's default pool instead of going back to the driver
+        cudaMemPool_t mp; unsigned long long keep = ~0ull;
+        PMN_CUDA_OK(cudaDeviceGetDefaultMemPool(&mp, device));
+        PMN_CUDA_OK(cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     for (auto &e : c->ev) PMN_CUDA_OK(cudaEventCreate(&e));
     c->scratch = pmn_scratch_new();
     c->pool = std::make_shared<DevPool>();
@@ -169,6 +181,7 @@ extern "C" void pmn_ctx_destroy(pmn_ctx *c)
     cudaStreamSynchronize(c->stream);
     pmn_scratch_free(c->scratch);
     c->pool.reset();
+    { cudaMemPool_t mp; if (cudaDeviceGetDefaultMemPool(&mp, c->device) == cudaSuccess) cudaMemPoolTrimTo(mp, 0); }   // unused blocks go back to the driver
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;

@@ -298,6 +298,7 @@ __global__ void __launch_bounds__(256) k_cl_out_clusters(const int32_t *__restri
 
 int pmn_cluster_impl(pmn_ctx *c, const pmn_index *, const pmn_seq *, const pmn_opts *o, int64_t n)
 {
+    pmn_tls_stream = c->stream;
     Scratch &S = *c->scratch;
     cudaStream_t st = c->stream;
     S.n_clusters = S.n_cl_matches = 0;

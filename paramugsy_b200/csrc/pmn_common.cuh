@@ -30,26 +30,34 @@ struct PmnError { int code; char msg[480]; };
     } while (0)
 
 int pmn_set_error(int code, const char *fmt, ...);
-void pmn_count_alloc();       // counts cudaMalloc calls (bench.py reports how many fell into the timed region)
+void pmn_count_alloc(size_t bytes = 0, size_t had = 0);       // counts cudaMalloc calls (bench.py reports how many fell into the timed region)
 
-// ---- a grow-only device buffer: no cudaMalloc at steady state -------------------------------
+// The stream of the context the calling thread is working for (set by every stage entry point).
+// Growth of a buffer is stream-ordered on it (cudaMallocAsync / cudaFreeAsync from the device's
+// default memory pool, whose release threshold pmn_ctx_create lifts): unlike cudaMalloc / cudaFree
+// it does not serialise the device, so a worker that grows a buffer does not stall the others.
+extern thread_local cudaStream_t pmn_tls_stream;
+
+// ---- a grow-only device buffer: no allocation at steady state --------------------------------
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
     int ensure(size_t bytes)
     {
         if (bytes <= cap) return 0;
-        if (p) cudaFree(p);
+        const size_t had = cap;
+        cudaStream_t ts = pmn_tls_stream;
+        if (p) { if (ts) cudaFreeAsync(p, ts); else cudaFree(p); }
         // capacities are quantised (powers of two up to 64 MB, multiples of 64 MB above) so that the
         // slightly different sizes of successive pairs settle on one allocation after a few calls:
         // cudaMalloc / cudaFree serialise the whole device, which would stall every other worker
         size_t want = 4096;
         if (bytes > ((size_t)64 << 20)) want = (bytes + bytes / 8 + ((size_t)64 << 20) - 1) / ((size_t)64 << 20) * ((size_t)64 << 20);
         else while (want < 2 * bytes) want <<= 1;           // 2x head room: every worker converges after its first pair
-        cudaError_t e = cudaMalloc(&p, want);
+        cudaError_t e = ts ? cudaMallocAsync(&p, want, ts) : cudaMalloc(&p, want);
         if (e != cudaSuccess) { p = nullptr; cap = 0; return pmn_set_error(-3, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); }
         cap = want;
-        pmn_count_alloc();
+        pmn_count_alloc(want, had);
         return 0;
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }

@@ -84,7 +84,11 @@ struct ExShared {                       // everything the device code needs, pas
     const uint8_t *anyfail;             // per cluster: some match -> next match job did not reach its target
     unsigned long long *markkey;        // per job: set at the first job of a claimed range
     const ExJobDesc *descA, *descB;     // wave-1 jobs: cluster ends (nC), match -> next match (nM)
-    int32_t *overflow;                  // inner jobs the small kernel handed to the big one (count = counters[7])
+    int32_t *overflow;                  // inner jobs handed to the big kernel (count = counters[7])
+    uint2 *tkey;                        // per match: (bin, rank in bin) of its thread-per-job alignment, bin = ~0u when it has none
+    uint32_t *tbin;                     // TPJ_BINS counters, then TPJ_BINS + 1 bin starts
+    int32_t *tsorted;                   // thread-per-job alignments in bin order (count = counters[10], warp cursor = counters[11])
+    uint8_t *tscratch;                  // TPJ_SLOT_BYTES per resident warp of k_ex_wave1_tpj
     int4 *dbg; unsigned dbg_cap;        // PMN_JOBLOG: two int4 per engine call (cursor = counters[15])
 };
 
@@ -699,6 +703,30 @@ __device__ __forceinline__ Eng make_eng(const ExShared &X, int32_t *)
 
 __device__ __forceinline__ int run_mismatches(const PackedView &R, int64_t a, const PackedView &Q, int64_t b, int64_t run);
 
+
+// ------------------------------------------------------------------------------------ thread-per-job windows
+//
+// Most match -> next match alignments are small windows (N x M up to a few thousand cells).  For
+// those one THREAD runs the whole alignment (k_ex_wave1_tpj): a warp holds 32 jobs of similar shape
+// (counting sort by bin below), so the 32 lanes do useful work on every instruction instead of one
+// anti-diagonal of a single small matrix being spread thinly over them.
+#define TPJ_W 8                        /* columns per strip (kept in registers)                      */
+#define TPJ_TB_WORDS 608               /* traceback words (8 cells each) per thread                  */
+#define TPJ_BND_ROWS 104               /* strip boundary records (16 B) per thread, also delta staging */
+#define TPJ_MAXDIM 100
+#define TPJ_SLOT_BYTES (32 * (TPJ_TB_WORDS * 8 + TPJ_BND_ROWS * 16))
+#define TPJ_NB 26                      /* buckets of 4 rows                                          */
+#define TPJ_BINS (13 * TPJ_NB)
+#define TPJ_NEG (-(1 << 28))
+#define TPJ_BLOCKS_PER_SM 4
+
+__device__ __forceinline__ bool tpj_fits(int N, int M, int breaklen)
+{
+    return N >= 1 && M >= 1 && N <= TPJ_MAXDIM && M <= TPJ_MAXDIM && N + M <= breaklen && ((M + TPJ_W - 1) / TPJ_W) * (N + 1) <= TPJ_TB_WORDS;
+}
+// large windows first: (strips descending, rows descending)
+__device__ __forceinline__ int tpj_bin(int N, int M) { return (13 - (M + TPJ_W - 1) / TPJ_W) * TPJ_NB + (TPJ_NB - 1 - (N >> 2)); }
+
 // one thread per match: its forward job (match -> next match), and for the last match of a cluster the
 // cluster-end job (-> target cluster or as far as the score carries).
 //
@@ -729,6 +757,11 @@ __global__ void __launch_bounds__(256) k_ex_jobdesc(ExShared X, ExJobDesc *__res
             atomicAdd(X.counters + 3, 1ull);
             d.m_o = -1;
         }
+        else if (tpj_fits(n, m, X.breaklen)) {
+            const int bin = tpj_bin(n, m);
+            X.tkey[g] = make_uint2((unsigned)bin, atomicAdd(X.tbin + bin, 1u));
+        }
+        else X.overflow[atomicAdd(X.counters + 7, 1ull)] = (int32_t)g;
         descB[g] = d;
         return;
     }
@@ -894,6 +927,198 @@ __global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32, 4) k_ex_wave1_big(ExS
         if (k >= nA + nO) break;
         const ExJobDesc d = k < nA ? X.descA[k] : X.descB[X.overflow[k - nA]];
         if (d.m_o >= 0) wave1_run<CfgBig>(E, X, d);
+    }
+}
+
+
+// bin counters -> bin starts, total number of thread-per-job alignments
+__global__ void __launch_bounds__(512) k_ex_tbinscan(ExShared X)
+{
+    __shared__ uint32_t sh[512];
+    const int t = threadIdx.x;
+    const uint32_t v = t < TPJ_BINS ? X.tbin[t] : 0u;
+    sh[t] = v;
+    __syncthreads();
+    for (int o = 1; o < 512; o <<= 1) {
+        const uint32_t a = t >= o ? sh[t - o] : 0u;
+        __syncthreads();
+        sh[t] += a;
+        __syncthreads();
+    }
+    if (t < TPJ_BINS) X.tbin[TPJ_BINS + t] = sh[t] - v;
+    if (t == 511) X.counters[10] = sh[t];
+}
+
+__global__ void __launch_bounds__(256) k_ex_tscatter(ExShared X)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= X.nM) return;
+    const uint2 k = X.tkey[g];
+    if (k.x != ~0u) X.tsorted[X.tbin[TPJ_BINS + k.x] + k.y] = (int32_t)g;
+}
+
+// nibbles of the 8 query bases at 0-based positions p .. p+7 (nibble c = base p+c): code, or 4 when the base
+// matches nothing or lies behind the `left` bases the window still has
+__device__ __forceinline__ unsigned tpj_query_nibbles(const PackedView &Q, int64_t p, int left)
+{
+    const uint32_t w = (uint32_t)(pmn_window64(Q.w, p) >> 48);                 // 8 bases, base c in bits 15-2c, 14-2c
+    const uint32_t xm = Q.has_x ? (pmn_xwindow32(Q.xm, p) >> 24) : 0u;          // base c in bit 7-c
+    unsigned r = 0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        const unsigned code = (w >> (14 - 2 * c)) & 3u;
+        const bool bad = c >= left || ((xm >> (7 - c)) & 1u);
+        r |= (bad ? 4u : code) << (4 * c);
+    }
+    return r;
+}
+
+// Wave 1, thread-per-job kernel: every match -> next match alignment whose window passes tpj_fits().
+//
+// Why the full matrix is the engine's answer (oracle/pmn_oracle.c align_engine, FORWARD_ALIGN): with
+// N + M <= breaklen the break-length stop cannot fire, and the band is the whole anti-diagonal as long as
+// no cell ever falls 3*breaklen below the running high score.  The running high score after anti-diagonal
+// d is at most 3*floor(d/2); every thread checks the sufficient condition
+//     cell maximum >= 3*(i + j0 + 8)/2 - 3*breaklen     (scaled by 4, state bits allowed for)
+// on all its cells and hands the alignment to the general engine (big kernel) when it fails.  Then the
+// alignment reaches its target, finishes there, and the traceback is that of the untrimmed matrix.
+//
+// Per thread: the matrix is walked in strips of 8 columns, top to bottom; of the previous row the strip
+// keeps per column I and max(D, M+2) (scores x4, the two low bits carry the state a value came from, as in
+// eng_run_reg), the cells right of a strip reach the next strip through a 16-byte record per row in
+// global scratch, and every row of a strip stores its 8 traceback bytes with one 8-byte store
+// (lane-interleaved: a warp writes 256 contiguous bytes).
+__global__ void __launch_bounds__(128, TPJ_BLOCKS_PER_SM) k_ex_wave1_tpj(ExShared X)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t slot = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    uint8_t *sbase = X.tscratch + slot * (size_t)TPJ_SLOT_BYTES;
+    uint2 *tb = (uint2 *)sbase + lane;                                   // [word][lane]
+    int4 *bnd = (int4 *)(sbase + (size_t)32 * TPJ_TB_WORDS * 8) + lane;  // [row][lane]
+    const unsigned nT = (unsigned)X.counters[10];
+    const int min_slack = 3 - 4 * PMN_GOOD_SCORE * X.breaklen;           // see above: 4 * (GOOD_SCORE * breaklen), plus the state bits
+    for (;;) {
+        unsigned w = 0;
+        if (lane == 0) w = (unsigned)atomicAdd(X.counters + 11, 1ull);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if ((unsigned long long)w * 32ull >= nT) break;
+        const unsigned k = w * 32 + lane;
+        const bool have = k < nT;
+        const int g = have ? X.tsorted[k] : 0;
+        int N = 0, M = 0, dir = 0, tA = 0, tB = 0; int64_t Ap = 0, Bp = 0;
+        if (have) {
+            const ExJobDesc d = X.descB[g];
+            N = d.tA - d.eA + 1; M = d.tB - d.eB + 1; dir = d.dir; tA = d.tA; tB = d.tB;
+            Ap = d.Abase + d.eA - 1; Bp = d.Bbase + d.eB - 1;            // 0-based positions of window row 1 / column 1
+        }
+        const PackedView &Q = dir ? X.QR : X.QF;
+        const int strips = (M + TPJ_W - 1) / TPJ_W;
+        const int Nmax = __reduce_max_sync(0xffffffffu, N), Smax = __reduce_max_sync(0xffffffffu, strips);
+        const int stride = Smax * (Nmax + 1) <= TPJ_TB_WORDS ? Nmax + 1 : N + 1;     // lanes of similar jobs share rows
+        int slack = INT32_MAX, ms_fin = PMN_ST_MAT;
+        for (int s = 0; s < strips; s++) {
+            const int j0 = s * TPJ_W;
+            const unsigned qn = tpj_query_nibbles(Q, Bp + j0, M - j0);
+            int uI[TPJ_W], ug[TPJ_W];
+#pragma unroll
+            for (int c = 0; c < TPJ_W; c++) { uI[c] = TPJ_NEG; ug[c] = TPJ_NEG; }
+            int prev_bmc = TPJ_NEG;                 // cell maximum (with state) of (i-1, j0)
+            uint64_t aw = 0; uint32_t ax = 0;
+            const bool last = s + 1 == strips;
+            int4 nb = make_int4(TPJ_NEG, 2, 2, 0);  // boundary record of row 0 in strip 0: cell (0,0) = MAT 0
+            if (s) nb = bnd[0];
+            uint2 *trow = tb + (size_t)s * stride * 32;
+            for (int i = 0; i <= N; i++) {
+                const int lD0 = nb.x, hl0 = nb.y, bmc = nb.z;
+                if (i < N) {                         // next row's record, fetched one row ahead
+                    if (s) nb = bnd[(size_t)(i + 1) * 32];
+                    else { const int v = 4 * (PMN_OPEN_GAP_SCORE + PMN_CONT_GAP_SCORE * i) + PMN_ST_INS; nb = make_int4(TPJ_NEG, v, v, 0); }   // cell (i+1, 0): INS only
+                }
+                unsigned an = 8;
+                if (i >= 1) {
+                    if (((i - 1) & 31) == 0) { aw = pmn_window64(X.R.w, Ap + i - 1); ax = X.R.has_x ? pmn_xwindow32(X.R.xm, Ap + i - 1) : 0u; }
+                    an = (unsigned)(aw >> 62) | ((ax >> 31) << 3);
+                    aw <<= 2; ax <<= 1;
+                }
+                const unsigned x = (an * 0x11111111u) ^ qn;
+                const int rowoff = -6 * (i + j0 + TPJ_W);
+                int lD = lD0, hl = hl0, dmc = prev_bmc;
+                prev_bmc = bmc;
+                unsigned t0 = 0, t1 = 0;
+#pragma unroll
+                for (int c = 0; c < TPJ_W; c++) {
+                    const int sc = (x & (0xfu << (4 * c))) ? 4 * PMN_BAD_SCORE : 4 * PMN_GOOD_SCORE;
+                    const int mD = __viaddmax_s32(lD, 4 * PMN_CONT_GAP_SCORE + PMN_ST_DEL, hl + 4 * PMN_OPEN_GAP_SCORE);
+                    const int mI = __viaddmax_s32(uI[c], 4 * PMN_CONT_GAP_SCORE + PMN_ST_INS, ug[c] + 4 * PMN_OPEN_GAP_SCORE);
+                    const int mM = dmc + sc;
+                    dmc = __viaddmax_s32(uI[c], PMN_ST_INS, ug[c]);        // cell maximum of (i-1, j): the diagonal of the next column
+                    const int vD = mD & ~3, vI = mI & ~3, vM2 = (mM & ~3) + PMN_ST_MAT;
+                    hl = __viaddmax_s32(vI, PMN_ST_INS, vM2);
+                    const int mc = max(hl, vD);
+                    uI[c] = vI; ug[c] = max(vD, vM2);
+                    lD = vD;
+                    slack = __viaddmin_s32(mc, rowoff, slack);
+                    const unsigned tbits = ((unsigned)mD & 3u) | (((unsigned)mI & 3u) << 2) | (((unsigned)mM & 3u) << 4);
+                    if (c < 4) t0 |= tbits << (8 * c); else t1 |= tbits << (8 * (c - 4));
+                    if (c == TPJ_W - 1 && !last) bnd[(size_t)i * 32] = make_int4(vD, hl, mc, 0);
+                }
+                trow[(size_t)i * 32] = make_uint2(t0, t1);
+            }
+            if (last) {                               // state of the finish cell (N, M)
+                const int c = (M - 1) & (TPJ_W - 1);
+                int mcf = 0;
+#pragma unroll
+                for (int cc = 0; cc < TPJ_W; cc++) if (cc == c) mcf = __viaddmax_s32(uI[cc], PMN_ST_INS, ug[cc]);
+                ms_fin = mcf & 3;
+            }
+        }
+        const bool ok = have && slack >= min_slack;
+        if (have && !ok) X.overflow[atomicAdd(X.counters + 7, 1ull)] = g;     // the general engine decides
+        // walk back from (N, M); the reversed deltas go to this thread's boundary rows (free by now)
+        int nrev = 0, asum = 0;
+        int32_t *rev = (int32_t *)bnd;                 // entry e at rev[(e >> 2) * 128 + (e & 3)]
+        if (ok) {
+            int i = N, j = M, st = ms_fin, pending = 0, run = 0;
+            while (i > 0 || j > 0) {
+                unsigned b;
+                if (j == 0) b = (unsigned)(i == 1 ? PMN_ST_MAT : PMN_ST_INS) << 2;          // column 0: INS from above; cell (1,0) comes from (0,0) MAT
+                else {
+                    const uint2 wv = tb[((size_t)((j - 1) >> 3) * stride + i) * 32];
+                    const int c = (j - 1) & 7;
+                    b = ((c < 4 ? wv.x : wv.y) >> (8 * (c & 3))) & 0x3fu;
+                }
+                if (st == PMN_ST_MAT) { run++; st = (b >> 4) & 3; i--; j--; }
+                else {
+                    if (pending) { const int dv = pending * (run + 1); rev[(nrev >> 2) * 128 + (nrev & 3)] = dv; nrev++; asum += dv > 0 ? dv : -dv - 1; }
+                    run = 0;
+                    if (st == PMN_ST_INS) { pending = 1; st = (b >> 2) & 3; i--; }
+                    else { pending = -1; st = b & 3; j--; }
+                }
+            }
+            if (pending) { const int dv = pending * (run + 1); rev[(nrev >> 2) * 128 + (nrev & 3)] = dv; nrev++; asum += dv > 0 ? dv : -dv - 1; }
+        }
+        // delta pool: one atomic per warp
+        int incl = nrev;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        unsigned long long at = 0;
+        if (total > 0) {
+            if (lane == 31) at = atomicAdd(X.counters + 0, (unsigned long long)total);
+            at = __shfl_sync(0xffffffffu, at, 31);
+            if (at + (unsigned long long)total > X.pool_cap) { if (lane == 0) atomicOr(X.counters + 4, (unsigned long long)EX_ERR_POOL); continue; }
+        }
+        const unsigned long long mine = at + (unsigned long long)(incl - nrev);
+        for (int e = 0; e < nrev; e++) { const int r = nrev - 1 - e; X.pool[mine + e] = rev[(r >> 2) * 128 + (r & 3)]; }
+        if (ok) {
+            ExJob r; r.endA = tA; r.endB = tB; r.dcnt = nrev; r.target = -1; r.doff = nrev ? (uint32_t)mine : 0u; r.reached = 1; r.valid = 1; r.asum = asum;
+            X.jobs[g] = r;
+        }
+        unsigned long long cells = ok ? (unsigned long long)((N + 1) * (M + 1) - 1) : 0ull;
+        cells = __reduce_add_sync(0xffffffffu, (unsigned)cells);
+        const unsigned njobs = __popc(__ballot_sync(0xffffffffu, ok));
+        if (lane == 0) { atomicAdd(X.counters + 2, cells); atomicAdd(X.counters + 3, (unsigned long long)njobs); }
+        __syncwarp();
     }
 }
 
@@ -1425,6 +1650,7 @@ struct OpMaxU64 { __device__ __forceinline__ unsigned long long operator()(unsig
 
 int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_opts *o, pmn_result *res)
 {
+    pmn_tls_stream = c->stream;
     Scratch &S = *c->scratch;
     cudaStream_t st = c->stream;
     const pmn_seq *ref = ix->seq;
@@ -1535,6 +1761,14 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     if (S.ex_desc.ensure(sizeof(ExJobDesc) * (size_t)(np + nm + 1) + 4 * (size_t)(nm + 1))) return -3;
     ExJobDesc *descA = S.ex_desc.as<ExJobDesc>(), *descB = descA + np;
     X.descA = descA; X.descB = descB; X.overflow = (int32_t *)(descB + nm + 1);
+    // thread-per-job windows: (bin, rank) per match, bin counters and starts, the sorted list, per-warp scratch
+    const int blocks_tpj = c->sm_count * TPJ_BLOCKS_PER_SM;
+    const size_t tkey_bytes = 8 * (size_t)nm, tbin_bytes = 4 * (size_t)(2 * TPJ_BINS + 2);
+    if (S.ex_tkey.ensure(tkey_bytes + tbin_bytes + 4 * (size_t)nm + 64) || S.ex_tscratch.ensure((size_t)blocks_tpj * 4 * TPJ_SLOT_BYTES)) return -3;
+    X.tkey = S.ex_tkey.as<uint2>(); X.tbin = (uint32_t *)(X.tkey + nm); X.tsorted = (int32_t *)(X.tbin + 2 * TPJ_BINS + 2);
+    X.tscratch = S.ex_tscratch.as<uint8_t>();
+    PMN_CUDA_OK(cudaMemsetAsync(X.tkey, 0xff, tkey_bytes, st));
+    PMN_CUDA_OK(cudaMemsetAsync(X.tbin, 0, tbin_bytes, st));
     const char *joblog = getenv("PMN_JOBLOG");
     X.dbg = nullptr; X.dbg_cap = 0;
     if (joblog) {
@@ -1553,11 +1787,13 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     int b1 = blocks1; { int64_t need = (nm + EX_WARPS_PER_BLOCK - 1) / EX_WARPS_PER_BLOCK; if (need < b1) b1 = (int)need; if (b1 < 1) b1 = 1; }
     k_ex_jobdesc<<<gm, 256, 0, st>>>(X, descA, descB);
     PMN_CUDA_OK(cudaEventRecord(c->ev[8], st));
+    k_ex_tbinscan<<<1, 512, 0, st>>>(X);
+    k_ex_tscatter<<<gm, 256, 0, st>>>(X);
     {
-        int bs = c->sm_count * EX_SMALL_BLOCKS_PER_SM;
-        const int64_t need = (nm + EX_WARPS_PER_BLOCK * EX_JOB_BATCH - 1) / (EX_WARPS_PER_BLOCK * EX_JOB_BATCH);
-        if (need < bs) bs = (int)std::max<int64_t>(1, need);
-        k_ex_wave1_small<<<bs, EX_WARPS_PER_BLOCK * 32, smem_small, st>>>(X);
+        int bt = blocks_tpj;
+        const int64_t need = (nm + 127) / 128;
+        if (need < bt) bt = (int)std::max<int64_t>(1, need);
+        k_ex_wave1_tpj<<<bt, 128, 0, st>>>(X);
     }
     k_ex_wave1_big<<<b1, EX_WARPS_PER_BLOCK * 32, smem, st>>>(X);
     PMN_CUDA_OK(cudaEventRecord(c->ev[9], st));
@@ -1568,7 +1804,7 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     k_ex_csum<<<gp, 256, 0, st>>>(X, cs);
     k_ex_stitch<<<blocks_st, EX_WARPS_PER_BLOCK * 32, smem, st>>>(X, fused);
     PMN_CUDA_OK(cudaEventRecord(c->ev[10], st));
-    launches += 12;
+    launches += 14;
 
     // ---- E4
     if (S.ex_c.ensure(4 * 5 * (size_t)(nm + 1) + 64)) return -3;     // al_syn, al_slot, dcount, dstart, slot2out  (pstart/ppos are dead now)

@@ -129,6 +129,7 @@ __global__ void k_fa_gather(const uint32_t *__restrict__ pos, const int64_t *__r
 // locates the header lines (for the record ids); everything per base happens on the device.
 int pmn_fasta_to_device(pmn_ctx *c, pmn_seq *s, const char *txt, size_t nb, const std::vector<int64_t> &header_pos)
 {
+    pmn_tls_stream = c->stream;
     Scratch &S = *c->scratch;
     cudaStream_t st = c->stream;
     const int nrec = (int)header_pos.size();
@@ -321,6 +322,7 @@ extern "C" size_t pmn_index_image_bytes(int64_t n_bases)
 
 int pmn_index_layout(pmn_ctx *c, const pmn_seq *ref, pmn_index *ix)
 {
+    pmn_tls_stream = c->stream;
     const int64_t n = ref->n;
     if (n < 1) return pmn_set_error(PMN_E_ARG, "index: empty reference");
     if (n > 0x7ffffff0ll) return pmn_set_error(PMN_E_ARG, "index: reference longer than 2^31 bases");
@@ -334,6 +336,7 @@ __global__ void k_index_header(PmnIndexHeader *h, int64_t n, int K, int rounds) 
 
 int pmn_index_build_impl(pmn_ctx *c, const pmn_seq *ref, pmn_index *ix)
 {
+    pmn_tls_stream = c->stream;
     Scratch &S = *c->scratch;
     cudaStream_t st = c->stream;
     { int rc = pmn_index_layout(c, ref, ix); if (rc) return rc; }

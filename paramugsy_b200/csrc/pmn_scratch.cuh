@@ -19,7 +19,7 @@ struct Scratch {
     DevBuf cl_matches, cl_recs, cl_counters;
     // extension
     DevBuf ex_a, ex_b, ex_c, ex_d, ex_e, ex_f, ex_g, ex_h, ex_i, ex_j, ex_k, ex_l;
-    DevBuf ex_scores, ex_tb, ex_tbidx, ex_pool, ex_counters, ex_arena, ex_dbg, ex_desc;
+    DevBuf ex_scores, ex_tb, ex_tbidx, ex_pool, ex_counters, ex_arena, ex_dbg, ex_desc, ex_tkey, ex_tscratch;
     // host-side counts handed from one stage to the next (one pair in flight per context)
     int64_t n_anchors = 0, n_clusters = 0, n_cl_matches = 0;
     // pinned host staging

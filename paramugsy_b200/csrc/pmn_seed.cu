@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(256) k_seed_gather(const int4 *__restrict__ st
 
 int pmn_seed_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_opts *o, int64_t *n_anchors, int part, int nparts)
 {
+    pmn_tls_stream = c->stream;
     Scratch &S = *c->scratch;
     cudaStream_t st = c->stream;
     *n_anchors = 0;
