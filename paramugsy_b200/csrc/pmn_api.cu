@@ -84,6 +84,9 @@ extern "C" int pmn_ctx_create(int device, pmn_ctx **out)
     pmn_ctx *c = new pmn_ctx();
     c->device = device; c->sm_count = prop.multiProcessorCount;
     PMN_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    PMN_CUDA_OK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    PMN_CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    PMN_CUDA_OK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     {   // freed blocks stay in the device's default pool instead of going back to the driver
         cudaMemPool_t mp; unsigned long long keep = ~0ull;
         PMN_CUDA_OK(cudaDeviceGetDefaultMemPool(&mp, device));
@@ -102,10 +105,13 @@ int pmn_pool_get(pmn_ctx *c, DevBuf &b, size_t bytes)
     DevPool &P = *c->pool;
     std::lock_guard<std::mutex> lk(P.mu);
     if (b.p) { if (P.bufs.size() >= 256) b.release(); else { P.bufs.push_back(b); b.p = nullptr; b.cap = 0; } }
+    // only a buffer of exactly the size class a fresh allocation would get: requests of different classes never
+    // take each other's buffers, so the pool stops growing after the first batch
+    const size_t want = DevBuf::size_class(bytes);
     int best = -1;
     for (size_t i = 0; i < P.bufs.size(); i++)
-        if (P.bufs[i].cap >= bytes && (best < 0 || P.bufs[i].cap < P.bufs[(size_t)best].cap)) best = (int)i;
-    if (best >= 0 && P.bufs[(size_t)best].cap <= 4 * bytes + (1u << 20)) {
+        if (P.bufs[i].cap == want) { best = (int)i; break; }
+    if (best >= 0) {
         b = P.bufs[(size_t)best];
         P.bufs.erase(P.bufs.begin() + best);
         return 0;
@@ -184,6 +190,9 @@ extern "C" void pmn_ctx_destroy(pmn_ctx *c)
     { cudaMemPool_t mp; if (cudaDeviceGetDefaultMemPool(&mp, c->device) == cudaSuccess) cudaMemPoolTrimTo(mp, 0); }   // unused blocks go back to the driver
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     delete c;
 }
 

@@ -42,6 +42,13 @@ extern thread_local cudaStream_t pmn_tls_stream;
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    static size_t size_class(size_t bytes)
+    {
+        size_t want = 4096;
+        if (bytes > ((size_t)64 << 20)) want = (bytes + bytes / 8 + ((size_t)64 << 20) - 1) / ((size_t)64 << 20) * ((size_t)64 << 20);
+        else while (want < 2 * bytes) want <<= 1;           // 2x head room: every worker converges after its first pair
+        return want;
+    }
     int ensure(size_t bytes)
     {
         if (bytes <= cap) return 0;
@@ -51,9 +58,7 @@ struct DevBuf {
         // capacities are quantised (powers of two up to 64 MB, multiples of 64 MB above) so that the
         // slightly different sizes of successive pairs settle on one allocation after a few calls:
         // cudaMalloc / cudaFree serialise the whole device, which would stall every other worker
-        size_t want = 4096;
-        if (bytes > ((size_t)64 << 20)) want = (bytes + bytes / 8 + ((size_t)64 << 20) - 1) / ((size_t)64 << 20) * ((size_t)64 << 20);
-        else while (want < 2 * bytes) want <<= 1;           // 2x head room: every worker converges after its first pair
+        const size_t want = size_class(bytes);
         cudaError_t e = ts ? cudaMallocAsync(&p, want, ts) : cudaMalloc(&p, want);
         if (e != cudaSuccess) { p = nullptr; cap = 0; return pmn_set_error(-3, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); }
         cap = want;

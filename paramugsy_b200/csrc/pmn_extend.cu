@@ -11,7 +11,9 @@
 //       reference record) and sorted by (synteny, first reference start, mgaps order)
 //   E2  WAVE 1, fully parallel: every forward alignment of postnuc is a pure function of the
 //       cluster list (match -> next match inside a cluster; last match -> target cluster),
-//       so all of them run at once, one warp per job, persistent warps pulling jobs
+//       so all of them run at once: small match -> next match windows one THREAD per job
+//       (k_ex_wave1_tpj, full matrix in register strips), cluster ends and large windows one
+//       warp per job (k_ex_wave1_big, the banded engine), persistent warps pulling jobs
 //   E3  STITCH, one warp per synteny: the sequential control flow of extendClusters
 //       (merging, shadow test, backward extension) consumes the wave-1 results; the few
 //       alignments that depend on earlier outcomes (backward searches, forced merges) run
@@ -84,7 +86,7 @@ struct ExShared {                       // everything the device code needs, pas
     const uint8_t *anyfail;             // per cluster: some match -> next match job did not reach its target
     unsigned long long *markkey;        // per job: set at the first job of a claimed range
     const ExJobDesc *descA, *descB;     // wave-1 jobs: cluster ends (nC), match -> next match (nM)
-    int32_t *overflow;                  // inner jobs handed to the big kernel (count = counters[7])
+    int32_t *overflow, *overflow2;      // inner jobs handed to the big kernel by k_ex_jobdesc (count = counters[7]) / by k_ex_wave1_tpj (counters[12])
     uint2 *tkey;                        // per match: (bin, rank in bin) of its thread-per-job alignment, bin = ~0u when it has none
     uint32_t *tbin;                     // TPJ_BINS counters, then TPJ_BINS + 1 bin starts
     int32_t *tsorted;                   // thread-per-job alignments in bin order (count = counters[10], warp cursor = counters[11])
@@ -136,26 +138,17 @@ __device__ __forceinline__ int max_state(int vD, int vI, int vM)
 // ring (one LDS per anti-diagonal); the query nibbles of its K columns come from a nibble-packed
 // ring (one LDS).  Both rings are filled 32 bases at a time, one batch ahead of their use.
 
-// Shared memory of one warp, two layouts (offsets in 32-bit words):
+// Shared memory of one warp (offsets in 32-bit words):
 //   CfgBig    K up to 8 and the wide fallback: 12 score rows x 256 columns (rows 0-2 / 4-6 = the two live
 //             anti-diagonals at a change of K; all 12 belong to the wide fallback).  The rows only the wide
 //             fallback uses are free while the register band runs; short alignments keep their whole
 //             traceback there, so that the walk back never touches global memory: row 3 = per-diagonal
 //             (row offset << 16 | first column), row 7 = reversed deltas, rows 8-11 = traceback rows (4 KB).
-//   CfgSmall  K <= 2, no fallback (an alignment that needs more is handed to the big kernel): 7 rows x 64
-//             columns, then meta / reversed deltas / 2 KB of traceback rows.  5 KB per warp instead of 13,
-//             so that the kernel for the many small gaps runs 24 warps per SM.
 struct CfgBig {
     static constexpr int MAXK = 8, RW = 256, CR = 512;
     static constexpr int META_OFF = 3 * 256, META_N = 256, REV_OFF = 7 * 256, REV_N = 256, TBROWS_OFF = 8 * 256, TBROWS_BYTES = 4096;
     static constexpr int BASE_OFF = 12 * 256;
     static constexpr int WARP_BYTES = 12 * 256 * 4 + 512 + 256;      // rows + reference ring (CR bytes) + query nibble ring (CR / 2 bytes)
-};
-struct CfgSmall {
-    static constexpr int MAXK = 2, RW = 64, CR = 256;
-    static constexpr int META_OFF = 7 * 64, META_N = 128, REV_OFF = META_OFF + 128, REV_N = 64, TBROWS_OFF = REV_OFF + 64, TBROWS_BYTES = 2048;
-    static constexpr int BASE_OFF = TBROWS_OFF + 512;
-    static constexpr int WARP_BYTES = (BASE_OFF + 64 + 32) * 4;
 };
 template <class Cfg> __device__ __forceinline__ int32_t *eng_warp_smem()
 {
@@ -711,7 +704,7 @@ __device__ __forceinline__ int run_mismatches(const PackedView &R, int64_t a, co
 // (counting sort by bin below), so the 32 lanes do useful work on every instruction instead of one
 // anti-diagonal of a single small matrix being spread thinly over them.
 #define TPJ_W 8                        /* columns per strip (kept in registers)                      */
-#define TPJ_TB_WORDS 608               /* traceback words (8 cells each) per thread                  */
+#define TPJ_TB_WORDS (13 * 101)        /* traceback words (8 cells each) per thread: any window up to 100 x 100 */
 #define TPJ_BND_ROWS 104               /* strip boundary records (16 B) per thread, also delta staging */
 #define TPJ_MAXDIM 100
 #define TPJ_SLOT_BYTES (32 * (TPJ_TB_WORDS * 8 + TPJ_BND_ROWS * 16))
@@ -851,7 +844,7 @@ __device__ __noinline__ void eng_small_full(const Eng &E, const ExShared &X, con
     __syncwarp();
 }
 
-// returns false when the alignment is too wide for this kernel's layout (CfgSmall only)
+// returns false when the alignment is too wide for this kernel's layout (never for CfgBig)
 template <class Cfg>
 __device__ __forceinline__ bool wave1_run(const Eng &E, const ExShared &X, const ExJobDesc &d)
 {
@@ -882,50 +875,22 @@ __device__ __forceinline__ bool wave1_run(const Eng &E, const ExShared &X, const
     return true;
 }
 
-#define EX_JOB_BATCH 4
-#define EX_SMALL_BLOCKS_PER_SM 6
-
-// Wave 1, small kernel: every match -> next match alignment, EX_JOB_BATCH descriptors per fetch, in the
-// 5 KB layout (24 warps per SM).  The few alignments whose band outgrows two columns per lane are
-// queued for the big kernel.
-__global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32, EX_SMALL_BLOCKS_PER_SM) k_ex_wave1_small(ExShared X)
-{
-    Eng E = make_eng(X, nullptr); E.kid = 1;
-    const int lane = E.lane;
-    for (;;) {
-        unsigned long long g0 = 0;
-        if (lane == 0) g0 = atomicAdd(X.counters + 6, (unsigned long long)EX_JOB_BATCH);
-        g0 = __shfl_sync(0xffffffffu, g0, 0);
-        if (g0 >= (unsigned long long)X.nM) break;
-        ExJobDesc mine; mine.m_o = -1;
-        if (lane < EX_JOB_BATCH && g0 + lane < (unsigned long long)X.nM) mine = X.descB[g0 + lane];
-#pragma unroll 1
-        for (int t = 0; t < EX_JOB_BATCH; t++) {
-            ExJobDesc d;
-            d.Abase = __shfl_sync(0xffffffffu, mine.Abase, t); d.Bbase = __shfl_sync(0xffffffffu, mine.Bbase, t);
-            d.eA = __shfl_sync(0xffffffffu, mine.eA, t); d.eB = __shfl_sync(0xffffffffu, mine.eB, t);
-            d.tA = __shfl_sync(0xffffffffu, mine.tA, t); d.tB = __shfl_sync(0xffffffffu, mine.tB, t);
-            d.g = __shfl_sync(0xffffffffu, mine.g, t); d.dir = __shfl_sync(0xffffffffu, mine.dir, t);
-            d.m_o = __shfl_sync(0xffffffffu, mine.m_o, t); d.target = -1;
-            if (d.m_o >= 0 && !wave1_run<CfgSmall>(E, X, d) && lane == 0)
-                X.overflow[atomicAdd(X.counters + 7, 1ull)] = d.g;
-        }
-    }
-}
-
 // Wave 1, big kernel: the cluster-end extensions (break-length searches, bands up to hundreds of cells)
 // and what the small kernel handed over.
-__global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32, 4) k_ex_wave1_big(ExShared X)
+__global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32, 4) k_ex_wave1_big(ExShared X, int pass)
 {
     Eng E = make_eng(X, nullptr); E.kid = 1;
     const int lane = E.lane;
-    const unsigned long long nA = X.do_extend ? (unsigned long long)X.nC : 0ull, nO = X.counters[7];
+    // pass 0 (runs beside the thread-per-job kernel): cluster ends + the windows k_ex_jobdesc found too large;
+    // pass 1 (after it): the windows the thread-per-job kernel handed back
+    const unsigned long long nA = (pass == 0 && X.do_extend) ? (unsigned long long)X.nC : 0ull, nO = X.counters[pass ? 12 : 7];
+    const int32_t *list = pass ? X.overflow2 : X.overflow;
     for (;;) {
         unsigned long long k = 0;
-        if (lane == 0) k = atomicAdd(X.counters + 5, 1ull);
+        if (lane == 0) k = atomicAdd(X.counters + (pass ? 13 : 5), 1ull);
         k = __shfl_sync(0xffffffffu, k, 0);
         if (k >= nA + nO) break;
-        const ExJobDesc d = k < nA ? X.descA[k] : X.descB[X.overflow[k - nA]];
+        const ExJobDesc d = k < nA ? X.descA[k] : X.descB[list[k - nA]];
         if (d.m_o >= 0) wave1_run<CfgBig>(E, X, d);
     }
 }
@@ -1026,14 +991,13 @@ __global__ void __launch_bounds__(128, TPJ_BLOCKS_PER_SM) k_ex_wave1_tpj(ExShare
             uint64_t aw = 0; uint32_t ax = 0;
             const bool last = s + 1 == strips;
             int4 nb = make_int4(TPJ_NEG, 2, 2, 0);  // boundary record of row 0 in strip 0: cell (0,0) = MAT 0
-            if (s) nb = bnd[0];
+            int4 nb2 = nb;                          // the record after it: loads run two rows ahead of their use
+            if (s) { nb = bnd[0]; if (N >= 1) nb2 = bnd[32]; }
             uint2 *trow = tb + (size_t)s * stride * 32;
             for (int i = 0; i <= N; i++) {
                 const int lD0 = nb.x, hl0 = nb.y, bmc = nb.z;
-                if (i < N) {                         // next row's record, fetched one row ahead
-                    if (s) nb = bnd[(size_t)(i + 1) * 32];
-                    else { const int v = 4 * (PMN_OPEN_GAP_SCORE + PMN_CONT_GAP_SCORE * i) + PMN_ST_INS; nb = make_int4(TPJ_NEG, v, v, 0); }   // cell (i+1, 0): INS only
-                }
+                if (s) { nb = nb2; if (i + 2 <= N) nb2 = bnd[(size_t)(i + 2) * 32]; }
+                else { const int v = 4 * (PMN_OPEN_GAP_SCORE + PMN_CONT_GAP_SCORE * i) + PMN_ST_INS; nb = make_int4(TPJ_NEG, v, v, 0); }   // cell (i+1, 0): INS only
                 unsigned an = 8;
                 if (i >= 1) {
                     if (((i - 1) & 31) == 0) { aw = pmn_window64(X.R.w, Ap + i - 1); ax = X.R.has_x ? pmn_xwindow32(X.R.xm, Ap + i - 1) : 0u; }
@@ -1073,7 +1037,7 @@ __global__ void __launch_bounds__(128, TPJ_BLOCKS_PER_SM) k_ex_wave1_tpj(ExShare
             }
         }
         const bool ok = have && slack >= min_slack;
-        if (have && !ok) X.overflow[atomicAdd(X.counters + 7, 1ull)] = g;     // the general engine decides
+        if (have && !ok) X.overflow2[atomicAdd(X.counters + 12, 1ull)] = g;   // the general engine decides
         // walk back from (N, M); the reversed deltas go to this thread's boundary rows (free by now)
         int nrev = 0, asum = 0;
         int32_t *rev = (int32_t *)bnd;                 // entry e at rev[(e >> 2) * 128 + (e & 3)]
@@ -1725,7 +1689,7 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     const int blocks1 = c->sm_count * 4;                      // 4 warps per block, 4 blocks per SM
     const int blocks_st = (nS + EX_WARPS_PER_BLOCK - 1) / EX_WARPS_PER_BLOCK;
     const int nslots = std::max(blocks1, blocks_st) * EX_WARPS_PER_BLOCK;                 // warps that may run the wide fallback (global score rows)
-    const int nslots_tb = std::max(nslots, c->sm_count * EX_SMALL_BLOCKS_PER_SM * EX_WARPS_PER_BLOCK);   // warps that keep a private traceback header
+    const int nslots_tb = nslots;                                                          // warps that keep a private traceback header
     const size_t pool_cap = (size_t)std::max<int64_t>(1 << 20, 8 * nm + (ref->n + q->n) / 8);
     const size_t arena_cap = (size_t)1 << 31;
     const size_t ncap_al = (size_t)nm, ncap_nodes = 3 * (size_t)nm + 8 * (size_t)nS;
@@ -1758,9 +1722,9 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     ExCSum *cs = S.cl_l.as<ExCSum>();      // the clustering scratch is free by now
     X.cs = cs;
     PMN_CUDA_OK(cudaMemsetAsync(markkey, 0, 8 * (size_t)(nm + 1), st));
-    if (S.ex_desc.ensure(sizeof(ExJobDesc) * (size_t)(np + nm + 1) + 4 * (size_t)(nm + 1))) return -3;
+    if (S.ex_desc.ensure(sizeof(ExJobDesc) * (size_t)(np + nm + 1) + 8 * (size_t)(nm + 1))) return -3;
     ExJobDesc *descA = S.ex_desc.as<ExJobDesc>(), *descB = descA + np;
-    X.descA = descA; X.descB = descB; X.overflow = (int32_t *)(descB + nm + 1);
+    X.descA = descA; X.descB = descB; X.overflow = (int32_t *)(descB + nm + 1); X.overflow2 = X.overflow + (nm + 1);
     // thread-per-job windows: (bin, rank) per match, bin counters and starts, the sorted list, per-warp scratch
     const int blocks_tpj = c->sm_count * TPJ_BLOCKS_PER_SM;
     const size_t tkey_bytes = 8 * (size_t)nm, tbin_bytes = 4 * (size_t)(2 * TPJ_BINS + 2);
@@ -1777,16 +1741,20 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
         X.dbg = S.ex_dbg.as<int4>();
     }
 
-    const size_t smem = (size_t)EX_WARPS_PER_BLOCK * CfgBig::WARP_BYTES, smem_small = (size_t)EX_WARPS_PER_BLOCK * CfgSmall::WARP_BYTES;
+    const size_t smem = (size_t)EX_WARPS_PER_BLOCK * CfgBig::WARP_BYTES;
     if (!c->smem_attr_set) {
         PMN_CUDA_OK(cudaFuncSetAttribute(k_ex_wave1_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PMN_CUDA_OK(cudaFuncSetAttribute(k_ex_wave1_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small));
         PMN_CUDA_OK(cudaFuncSetAttribute(k_ex_stitch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         c->smem_attr_set = true;
     }
     int b1 = blocks1; { int64_t need = (nm + EX_WARPS_PER_BLOCK - 1) / EX_WARPS_PER_BLOCK; if (need < b1) b1 = (int)need; if (b1 < 1) b1 = 1; }
     k_ex_jobdesc<<<gm, 256, 0, st>>>(X, descA, descB);
     PMN_CUDA_OK(cudaEventRecord(c->ev[8], st));
+    // the warp-per-job kernel (cluster ends: few, long) runs beside the thread-per-job kernel on the context's second stream
+    PMN_CUDA_OK(cudaEventRecord(c->ev_fork, st));
+    PMN_CUDA_OK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+    k_ex_wave1_big<<<b1, EX_WARPS_PER_BLOCK * 32, smem, c->stream2>>>(X, 0);
+    PMN_CUDA_OK(cudaEventRecord(c->ev_join, c->stream2));
     k_ex_tbinscan<<<1, 512, 0, st>>>(X);
     k_ex_tscatter<<<gm, 256, 0, st>>>(X);
     {
@@ -1795,7 +1763,8 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
         if (need < bt) bt = (int)std::max<int64_t>(1, need);
         k_ex_wave1_tpj<<<bt, 128, 0, st>>>(X);
     }
-    k_ex_wave1_big<<<b1, EX_WARPS_PER_BLOCK * 32, smem, st>>>(X);
+    PMN_CUDA_OK(cudaStreamWaitEvent(st, c->ev_join, 0));
+    k_ex_wave1_big<<<b1, EX_WARPS_PER_BLOCK * 32, smem, st>>>(X, 1);
     PMN_CUDA_OK(cudaEventRecord(c->ev[9], st));
     PMN_D2H(c, (unsigned long long *)S.pinned + 24, X.counters + 2, 8);      // cells evaluated by wave 1
     k_ex_jobmeta<<<(unsigned)((nm + 1 + 255) / 256), 256, 0, st>>>(X.jobs, mcl, cl, pstart, ppos, nm, dcnt, pkey, anyfail);
@@ -1804,7 +1773,7 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     k_ex_csum<<<gp, 256, 0, st>>>(X, cs);
     k_ex_stitch<<<blocks_st, EX_WARPS_PER_BLOCK * 32, smem, st>>>(X, fused);
     PMN_CUDA_OK(cudaEventRecord(c->ev[10], st));
-    launches += 14;
+    launches += 15;
 
     // ---- E4
     if (S.ex_c.ensure(4 * 5 * (size_t)(nm + 1) + 64)) return -3;     // al_syn, al_slot, dcount, dstart, slot2out  (pstart/ppos are dead now)

@@ -63,6 +63,8 @@ struct pmn_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;     // forked from `stream` where two independent kernels of one pair can run side by side
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev[16] = {};
     PmnError err{};
     Scratch *scratch = nullptr;
