@@ -67,6 +67,10 @@ struct ExCSum {
     int32_t bulk_cnt, bulk_P;          // deltas / last P of the inner jobs [mfirst, last) taken together
 };
 
+// the backward extension of a cluster's first match, computed ahead of the stitcher (wave 2): search from the match
+// start towards the sequence starts, then the forced alignment over the region found
+struct ExBack { int32_t fA, fB, ext_i, ext_j; uint32_t doff; int32_t dcnt, asum, valid; };
+
 struct ExShared {                       // everything the device code needs, passed by value
     PackedView R, QF, QR;
     const int32_t *mA, *mB, *mL;        // matches (local reference coordinate)
@@ -91,6 +95,8 @@ struct ExShared {                       // everything the device code needs, pas
     uint32_t *tbin;                     // TPJ_BINS counters, then TPJ_BINS + 1 bin starts
     int32_t *tsorted;                   // thread-per-job alignments in bin order (count = counters[10], warp cursor = counters[11])
     uint8_t *tscratch;                  // TPJ_SLOT_BYTES per resident warp of k_ex_wave1_tpj
+    ExBack *back;                       // per cluster (wave 2), valid = 0 where none was computed
+    uint8_t *entered;                   // per cluster: some cluster's end job reached it (it will most likely be merged, not started)
     int4 *dbg; unsigned dbg_cap;        // PMN_JOBLOG: two int4 per engine call (cursor = counters[15])
 };
 
@@ -162,6 +168,7 @@ struct EngCtx {                          // warp-uniform progress of one alignme
     int d, tlo, thi, plo, phi, pplo, pphi;
     int high, best_d, best_j, reached;   // high: plain (unscaled) score
     unsigned long long cells;
+    int ext_i, ext_j;                    // largest reference / query index of any evaluated cell
     uint8_t *tcur, *tend; bool arena_fail;
     int tb_sm_used, tb_sm_n; bool tb_sm_open;   // traceback rows kept in shared memory: bytes used, diagonals [0, tb_sm_n), still appending
     int ca_hi, cb_hi;                    // first unfilled index of the reference / query ring
@@ -338,6 +345,7 @@ __device__ __forceinline__ int eng_run_reg(const Eng &E, EngCtx &c, const Packed
         for (int s = 1; s < K; s++) lmax = max(lmax, cm[s]);
         const int cmax = __reduce_max_sync(0xffffffffu, lmax);
         c.cells += (unsigned long long)width;
+        c.ext_i = max(c.ext_i, d - clo); c.ext_j = max(c.ext_j, chi);
         if (cmax >= high4) {
             int jm = -1;
 #pragma unroll
@@ -474,6 +482,7 @@ __device__ __noinline__ EngCtx eng_run_wide(const Eng &E, EngCtx c, const Packed
             if (cmax >= dmax) { dmax = cmax; dmaxj = jb + 31 - __clz((int)eq); }
         }
         c.cells += (unsigned long long)width;
+        c.ext_i = max(c.ext_i, d - clo); c.ext_j = max(c.ext_j, chi);
         __syncwarp();
         if (dmax >= c.high) { c.high = dmax; c.best_d = d; c.best_j = dmaxj; }
         c.pplo = c.plo; c.pphi = c.phi; c.plo = clo; c.phi = chi;
@@ -510,7 +519,7 @@ __device__ __noinline__ EngCtx eng_run_wide(const Eng &E, EngCtx c, const Packed
 // appended to the pool: *doff, *dcnt.
 template <class Cfg>
 __device__ __noinline__ int align_engine(const Eng &E, int64_t Abase, int64_t Astart, int64_t &Aend, const PackedView &Q, int64_t Bbase, int64_t Bstart, int64_t &Bend,
-                                         unsigned m_o, uint32_t *doff, int32_t *dcnt, int32_t *dasum)
+                                         unsigned m_o, uint32_t *doff, int32_t *dcnt, int32_t *dasum, int *ext_i = nullptr, int *ext_j = nullptr)
 {
     const ExShared &X = *E.X;
     const int lane = E.lane;
@@ -535,7 +544,7 @@ __device__ __noinline__ int align_engine(const Eng &E, int64_t Abase, int64_t As
 
     c.Apos0 = Abase + Astart - 1; c.Bpos0 = Bbase + Bstart - 1;
     c.d = 1; c.tlo = 0; c.thi = 0; c.plo = 0; c.phi = 0; c.pplo = 1; c.pphi = 0;
-    c.high = 0; c.best_d = 0; c.best_j = 0; c.reached = 0; c.cells = 0;
+    c.high = 0; c.best_d = 0; c.best_j = 0; c.reached = 0; c.cells = 0; c.ext_i = 0; c.ext_j = 0;
     {   // cell (0,0) into the ring; base rings: everything in front of the window matches nothing
         int32_t *ring = eng_warp_smem<Cfg>();
         uint8_t *ca = (uint8_t *)(ring + Cfg::BASE_OFF);
@@ -580,6 +589,7 @@ __device__ __noinline__ int align_engine(const Eng &E, int64_t Abase, int64_t As
     }
     if (c.arena_fail) { if (lane == 0) atomicOr(X.counters + 4, (unsigned long long)EX_ERR_ARENA); return 0; }
     const int reached = c.reached;
+    if (ext_i) { *ext_i = c.ext_i; *ext_j = c.ext_j; }
 
     int fd, fj;
     if (reached && !(m_o & PMN_OPTIMAL_BIT)) { fd = N + M; fj = M; } else { fd = c.best_d; fj = c.best_j; }
@@ -1132,6 +1142,49 @@ __global__ void __launch_bounds__(256) k_ex_csum(ExShared X, ExCSum *__restrict_
     s.bulk_cnt = (int32_t)(X.dcnt_ex[l] - X.dcnt_ex[f]);
     s.bulk_P = c.nm > 1 ? range_last_P(X, f, l - 1, -1) : -1;
     out[k] = s;
+    const ExSynteny S = X.syn[c.syn];
+    if (j.valid && j.reached && j.target >= 0 && j.target < S.cfirst + S.nC) X.entered[j.target] = 1;
+}
+
+// Wave 2: the backward extension of every cluster that no end job reached (those start new alignments in the
+// stitcher unless they turn out to be shadowed).  The search runs in the largest window extendBackward can ask
+// for (towards the sequence starts, OPTIMAL); the stitcher takes the result when its own window, bounded by the
+// target alignment, contains every cell this search evaluated (ext_i, ext_j) -- then the two runs are the same
+// cell for cell -- and runs the engine itself otherwise.
+__global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32, 4) k_ex_wave2(ExShared X)
+{
+    Eng E = make_eng(X, nullptr); E.kid = 3;
+    const int lane = E.lane;
+    for (;;) {
+        unsigned long long k = 0;
+        if (lane == 0) k = atomicAdd(X.counters + 14, 1ull);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= (unsigned long long)X.nC) break;
+        if (X.entered[k]) continue;
+        const ExCluster c = X.cl[k];
+        const ExSynteny S = X.syn[c.syn];
+        const int g = c.mfirst;
+        const int64_t sA = X.mA[g], sB = X.mB[g];
+        // A search that finds nothing dies within breaklen anti-diagonals of its best cell; one that is still alive
+        // further out is following homologous sequence towards an earlier alignment and will most likely be
+        // merged into it by the stitcher, which this kernel cannot know.  So the window is capped, and a search
+        // that touches the cap is left to the stitcher.
+        const int64_t cap = X.breaklen + 128;
+        const int64_t fullN = sA < PMN_MAX_ALIGNMENT_LENGTH ? sA : PMN_MAX_ALIGNMENT_LENGTH, fullM = sB < PMN_MAX_ALIGNMENT_LENGTH ? sB : PMN_MAX_ALIGNMENT_LENGTH;
+        const int64_t Ns = fullN < cap ? fullN : cap, Ms = fullM < cap ? fullM : cap;
+        int64_t targetA = sA - Ns + 1, targetB = sB - Ms + 1;
+        const PackedView &Q = c.dir ? X.QR : X.QF; const int64_t Bbase = c.dir ? S.BbaseR : S.BbaseF;
+        int ext_i = INT32_MAX, ext_j = INT32_MAX;
+        align_engine<CfgBig>(E, S.Abase, sA, targetA, Q, Bbase, sB, targetB, PMN_BACKWARD_SEARCH | PMN_OPTIMAL_BIT, nullptr, nullptr, nullptr, &ext_i, &ext_j);
+        if ((Ns != fullN && ext_i >= Ns) || (Ms != fullM && ext_j >= Ms)) continue;      // clipped by the cap: not the search the stitcher would run
+        int64_t eA = sA, eB = sB; uint32_t doff = 0; int32_t dcnt = 0, dasum = 0;
+        align_engine<CfgBig>(E, S.Abase, targetA, eA, Q, Bbase, targetB, eB, PMN_FORCED_FORWARD_ALIGN, &doff, &dcnt, &dasum);
+        if (lane == 0) {
+            ExBack b; b.fA = (int32_t)targetA; b.fB = (int32_t)targetB; b.ext_i = ext_i; b.ext_j = ext_j; b.doff = doff; b.dcnt = dcnt; b.asum = dasum; b.valid = 1;
+            X.back[k] = b;
+        }
+        __syncwarp();
+    }
 }
 
 // ------------------------------------------------------------------------------------ E3: stitch
@@ -1319,7 +1372,24 @@ __global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32) k_ex_stitch(ExShared 
                     T.cur.P = gA - 1; T.cur.head = -1; T.cur.tail = -1; T.cur.ndelta = 0; T.cur.live = 1; T.cur.pad0 = T.cur.pad1 = 0;
                     if (X.do_extend || CurrMp != 0) {
                         const int TargetAp = st_get_reverse_target(T, T.cur_slot, c.dir, gA, gB);
-                        st_extend_backward(T, TargetAp, c.dir);
+                        bool taken = false;
+                        if (CurrMp == 0 && X.do_extend) {
+                            const ExBack b = X.back[CurrCp];
+                            if (b.valid) {
+                                // the window extendBackward would search: up to the target alignment's end, or the sequence starts
+                                int64_t tA = 1, tB = 1;
+                                if (TargetAp >= 0) { const ExAlign t = T.al[TargetAp]; tA = t.eA; tB = t.eB; }
+                                int64_t Nw = gA - tA + 1, Mw = gB - tB + 1;
+                                if (Nw > PMN_MAX_ALIGNMENT_LENGTH) Nw = PMN_MAX_ALIGNMENT_LENGTH;
+                                if (Mw > PMN_MAX_ALIGNMENT_LENGTH) Mw = PMN_MAX_ALIGNMENT_LENGTH;
+                                if (TargetAp < 0 || (b.ext_i < Nw && b.ext_j < Mw)) {
+                                    if (b.dcnt > 0) cur_append(T, 0, b.doff, b.dcnt, 0, b.dcnt);
+                                    T.cur.sA = b.fA; T.cur.sB = b.fB; T.cur.P = b.fA - 1 + b.asum;
+                                    taken = true;
+                                }
+                            }
+                        }
+                        if (!taken) st_extend_backward(T, TargetAp, c.dir);
                     }
                 }
             }
@@ -1694,7 +1764,7 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     const size_t arena_cap = (size_t)1 << 31;
     const size_t ncap_al = (size_t)nm, ncap_nodes = 3 * (size_t)nm + 8 * (size_t)nS;
     const size_t npad = ((size_t)np + 63) / 64 * 64;
-    const size_t l_bytes = npad * 2 + 8 * (size_t)nS + 64;      // fused, anyfail, syn_nal (2 x nS)
+    const size_t l_bytes = npad * 3 + 8 * (size_t)nS + 64 + sizeof(ExBack) * npad;      // fused, anyfail, entered, syn_nal (2 x nS), back
     if (S.ex_i.ensure(sizeof(ExJob) * (size_t)nm) || S.ex_j.ensure(sizeof(ExAlign) * ncap_al) || S.ex_k.ensure(sizeof(ExNode) * ncap_nodes) ||
         S.ex_pool.ensure(4 * pool_cap) || S.ex_arena.ensure(arena_cap) || S.ex_scores.ensure(4 * (size_t)EX_ROWS * EX_WCAP * (size_t)nslots) ||
         S.ex_tb.ensure((size_t)EX_TBW * (size_t)nslots_tb) || S.ex_counters.ensure(128) || S.ex_l.ensure(l_bytes) ||
@@ -1713,7 +1783,9 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     X.breaklen = o->breaklen; X.do_extend = o->do_extend; X.do_simplify = o->do_simplify;
     uint8_t *fused = S.ex_l.as<uint8_t>();
     uint8_t *anyfail = fused + npad;
-    X.syn_nal = (int32_t *)(anyfail + npad);
+    X.entered = anyfail + npad;
+    X.syn_nal = (int32_t *)(X.entered + npad);
+    X.back = (ExBack *)(X.syn_nal + 2 * (size_t)nS + 16);
     long long *pkey = S.ex_tbidx.as<long long>();                          // nm+1
     unsigned long long *markkey = (unsigned long long *)(pkey + (nm + 1));  // nm+1
     uint32_t *dcnt = (uint32_t *)(markkey + (nm + 1));                      // nm+1, then dcnt_ex nm+1
@@ -1745,6 +1817,7 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     if (!c->smem_attr_set) {
         PMN_CUDA_OK(cudaFuncSetAttribute(k_ex_wave1_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PMN_CUDA_OK(cudaFuncSetAttribute(k_ex_stitch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PMN_CUDA_OK(cudaFuncSetAttribute(k_ex_wave2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         c->smem_attr_set = true;
     }
     int b1 = blocks1; { int64_t need = (nm + EX_WARPS_PER_BLOCK - 1) / EX_WARPS_PER_BLOCK; if (need < b1) b1 = (int)need; if (b1 < 1) b1 = 1; }
@@ -1771,6 +1844,8 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     pmn_scan<uint32_t, OpAddU32, false>(dcnt, dcnt_ex, nm + 1, S.scan_tmp.as<uint32_t>(), st);
     pmn_scan<long long, OpMaxI64x, true>(pkey, pkey, nm, S.scan_tmp.as<long long>(), st);
     k_ex_csum<<<gp, 256, 0, st>>>(X, cs);
+    if (o->do_extend) { k_ex_wave2<<<std::min<int>(blocks1, (int)((np + EX_WARPS_PER_BLOCK - 1) / EX_WARPS_PER_BLOCK)), EX_WARPS_PER_BLOCK * 32, smem, st>>>(X); launches++; }
+    PMN_CUDA_OK(cudaEventRecord(c->ev[11], st));
     k_ex_stitch<<<blocks_st, EX_WARPS_PER_BLOCK * 32, smem, st>>>(X, fused);
     PMN_CUDA_OK(cudaEventRecord(c->ev[10], st));
     launches += 15;
@@ -1800,7 +1875,7 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     res->stats.dp_cells = (int64_t)hc[2]; res->stats.dp_jobs = (int64_t)hc[3];
     res->stats.wave1_cells = (int64_t)hc[24];
     cudaEventElapsedTime(&res->stats.ms_wave1, c->ev[8], c->ev[9]);
-    cudaEventElapsedTime(&res->stats.ms_stitch, c->ev[9], c->ev[10]);
+    cudaEventElapsedTime(&res->stats.ms_stitch, c->ev[11], c->ev[10]);
     c->launches += launches; launches = 0;
     if (errflags & EX_ERR_POOL) return pmn_set_error(PMN_E_NOMEM, "extend: delta pool exhausted (%zu entries)", pool_cap);
     if (errflags & EX_ERR_ARENA) return pmn_set_error(PMN_E_NOMEM, "extend: traceback arena exhausted (%zu bytes)", arena_cap);

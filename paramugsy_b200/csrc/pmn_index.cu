@@ -310,7 +310,13 @@ __global__ void __launch_bounds__(256) k_bucket_fill(PackedView s, const uint32_
 
 static inline int bits_for(int64_t v) { int b = 1; while ((1ll << b) <= v) b++; return b; }
 
-static inline int index_K(int64_t n) { int K = 8; while (K < 13 && (1ll << (2 * K)) < n) K++; return K; }
+static inline int index_K(int64_t n)
+{
+    static const int shift = getenv("PMN_INDEX_KSHIFT") ? atoi(getenv("PMN_INDEX_KSHIFT")) : 0;     // experiment: smaller table
+    int K = 8; while (K < 13 && (1ll << (2 * K)) < n) K++;
+    K -= shift; if (K < 8) K = 8;
+    return K;
+}
 
 static inline size_t up256(size_t x) { return (x + 255) / 256 * 256; }
 

@@ -17,7 +17,7 @@
 #include <thread>
 #include <vector>
 
-#include "pmn_host.h"
+#include "pmn_scratch.cuh"
 
 namespace {
 
@@ -37,7 +37,32 @@ struct pmn_sched {
     std::mutex mu;
     std::condition_variable cv;
     std::string err; int err_code = 0;
+    // Packing a genome and building an index need large scratch that aligning a pair does not.  Which worker
+    // gets to build is a race, so instead of every worker growing its own copy over many batches the
+    // scheduler owns a few sets that the builder borrows: the working set is complete after the first batch.
+    std::vector<Scratch *> build_scratch;
+    std::mutex bmu;
+    std::condition_variable bcv;
 };
+
+namespace {
+struct BorrowedScratch {
+    pmn_sched *s; pmn_ctx *c; Scratch *own;
+    BorrowedScratch(pmn_sched *s_, pmn_ctx *c_) : s(s_), c(c_), own(c_->scratch)
+    {
+        std::unique_lock<std::mutex> lk(s->bmu);
+        s->bcv.wait(lk, [&] { return !s->build_scratch.empty(); });
+        c->scratch = s->build_scratch.back(); s->build_scratch.pop_back();
+    }
+    ~BorrowedScratch()
+    {
+        cudaStreamSynchronize(c->stream);
+        { std::lock_guard<std::mutex> lk(s->bmu); s->build_scratch.push_back(c->scratch); }
+        c->scratch = own;
+        s->bcv.notify_one();
+    }
+};
+}  // namespace
 
 extern "C" int pmn_sched_create(int device, int workers, pmn_sched **out)
 {
@@ -52,6 +77,7 @@ extern "C" int pmn_sched_create(int device, int workers, pmn_sched **out)
         if (!s->ctx.empty()) c->pool = s->ctx[0]->pool;
         s->ctx.push_back(c);
     }
+    for (int k = 0; k < std::min(workers, 2); k++) s->build_scratch.push_back(pmn_scratch_new());
     *out = s;
     return 0;
 }
@@ -59,6 +85,8 @@ extern "C" int pmn_sched_create(int device, int workers, pmn_sched **out)
 extern "C" void pmn_sched_destroy(pmn_sched *s)
 {
     if (!s) return;
+    if (!s->ctx.empty()) cudaSetDevice(s->ctx[0]->device);
+    for (Scratch *b : s->build_scratch) pmn_scratch_free(b);
     for (pmn_ctx *c : s->ctx) pmn_ctx_destroy(c);
     delete s;
 }
@@ -125,10 +153,10 @@ static int sched_run(pmn_sched *s, int ng, const char *const *fasta, const size_
             const int k = next.fetch_add(1);
             if (k >= np) return;
             const int p = order[(size_t)k], r = ref[p], q = qry[p];
-            auto pack = [&](int g) { return acquire(seqs, g, [&]() -> void * { pmn_seq *x = nullptr; return pmn_seq_from_fasta(c, fasta[g], bytes[g], &x) ? nullptr : (void *)x; }); };
+            auto pack = [&](int g) { return acquire(seqs, g, [&]() -> void * { BorrowedScratch b(s, c); pmn_seq *x = nullptr; return pmn_seq_from_fasta(c, fasta[g], bytes[g], &x) ? nullptr : (void *)x; }); };
             pmn_seq *rs = (pmn_seq *)pack(r); if (!rs) return;
             pmn_seq *qs = (pmn_seq *)pack(q); if (!qs) return;
-            pmn_index *ix = (pmn_index *)acquire(idx, r, [&]() -> void * { pmn_index *x = nullptr; return pmn_index_build(c, rs, &x) ? nullptr : (void *)x; });
+            pmn_index *ix = (pmn_index *)acquire(idx, r, [&]() -> void * { BorrowedScratch b(s, c); pmn_index *x = nullptr; return pmn_index_build(c, rs, &x) ? nullptr : (void *)x; });
             if (!ix) return;
             pmn_result *res = nullptr;
             int rc = pmn_align(c, ix, qs, opts, names ? names[r] : nullptr, names ? names[q] : nullptr, &res);
