@@ -52,13 +52,7 @@ Scratch *pmn_scratch_new() { return new Scratch(); }
 void pmn_scratch_free(Scratch *s)
 {
     if (!s) return;
-    DevBuf *bufs[] = { &s->rs.hist, &s->rs.spine, &s->k0, &s->k1, &s->v0, &s->v1, &s->scan_tmp, &s->codes, &s->gs, &s->rank, &s->flags,
-                       &s->list0, &s->list1, &s->gsn, &s->sections, &s->stage, &s->tile_cnt, &s->tile_off, &s->anchors,
-                       &s->cl_a, &s->cl_b, &s->cl_c, &s->cl_d, &s->cl_e, &s->cl_f, &s->cl_g, &s->cl_h, &s->cl_i, &s->cl_j, &s->cl_k, &s->cl_l,
-                       &s->cl_matches, &s->cl_recs, &s->cl_counters,
-                       &s->ex_a, &s->ex_b, &s->ex_c, &s->ex_d, &s->ex_e, &s->ex_f, &s->ex_g, &s->ex_h, &s->ex_i, &s->ex_j, &s->ex_k, &s->ex_l,
-                       &s->ex_scores, &s->ex_tb, &s->ex_tbidx, &s->ex_pool, &s->ex_counters, &s->ex_arena, &s->ex_dbg, &s->ex_desc, &s->ex_tkey, &s->ex_tscratch };
-    for (DevBuf *b : bufs) b->release();
+    for (DevBuf *b : s->all()) b->release();
     if (s->pinned) cudaFreeHost(s->pinned);
     delete s;
 }

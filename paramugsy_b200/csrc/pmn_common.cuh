@@ -49,16 +49,16 @@ struct DevBuf {
         else while (want < 2 * bytes) want <<= 1;           // 2x head room: every worker converges after its first pair
         return want;
     }
-    int ensure(size_t bytes)
+    int ensure(size_t bytes) { return bytes <= cap ? 0 : grow_to(size_class(bytes)); }
+    int grow_to(size_t want)            // want: a capacity some buffer of this role already has (a size class)
     {
-        if (bytes <= cap) return 0;
+        if (want <= cap) return 0;
         const size_t had = cap;
         cudaStream_t ts = pmn_tls_stream;
         if (p) { if (ts) cudaFreeAsync(p, ts); else cudaFree(p); }
         // capacities are quantised (powers of two up to 64 MB, multiples of 64 MB above) so that the
         // slightly different sizes of successive pairs settle on one allocation after a few calls:
         // cudaMalloc / cudaFree serialise the whole device, which would stall every other worker
-        const size_t want = size_class(bytes);
         cudaError_t e = ts ? cudaMallocAsync(&p, want, ts) : cudaMalloc(&p, want);
         if (e != cudaSuccess) { p = nullptr; cap = 0; return pmn_set_error(-3, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); }
         cap = want;

@@ -41,6 +41,10 @@ struct pmn_sched {
     // gets to build is a race, so instead of every worker growing its own copy over many batches the
     // scheduler owns a few sets that the builder borrows: the working set is complete after the first batch.
     std::vector<Scratch *> build_scratch;
+    // Pairs differ a little in size and land on workers at random, so each worker's grow-only scratch would keep
+    // meeting "its largest pair so far" for many batches.  Workers publish the capacities they ended up with and
+    // pre-grow to the largest any of them has seen: the working set of the whole scheduler settles with the first batch.
+    std::vector<size_t> hiwater;
     std::mutex bmu;
     std::condition_variable bcv;
 };
@@ -159,7 +163,19 @@ static int sched_run(pmn_sched *s, int ng, const char *const *fasta, const size_
             pmn_index *ix = (pmn_index *)acquire(idx, r, [&]() -> void * { BorrowedScratch b(s, c); pmn_index *x = nullptr; return pmn_index_build(c, rs, &x) ? nullptr : (void *)x; });
             if (!ix) return;
             pmn_result *res = nullptr;
+            {
+                std::vector<DevBuf *> mine = c->scratch->all();
+                std::vector<size_t> want;
+                { std::lock_guard<std::mutex> lk(s->bmu); if (s->hiwater.size() != mine.size()) s->hiwater.assign(mine.size(), 0); want = s->hiwater; }
+                pmn_tls_stream = c->stream;
+                for (size_t i = 0; i < mine.size(); i++) if (want[i] > mine[i]->cap) mine[i]->grow_to(want[i]);
+            }
             int rc = pmn_align(c, ix, qs, opts, names ? names[r] : nullptr, names ? names[q] : nullptr, &res);
+            {
+                std::vector<DevBuf *> mine = c->scratch->all();
+                std::lock_guard<std::mutex> lk(s->bmu);
+                for (size_t i = 0; i < mine.size() && i < s->hiwater.size(); i++) s->hiwater[i] = std::max(s->hiwater[i], mine[i]->cap);
+            }
             std::lock_guard<std::mutex> lk(s->mu);
             if (rc) { if (!s->err_code) { s->err_code = rc; s->err = pmn_last_error(nullptr); } return; }
             out[p] = res;
