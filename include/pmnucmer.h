@@ -137,6 +137,14 @@ int  pmn_align_pair(pmn_ctx *c, const char *ref_fasta_path, const char *qry_fast
 int  pmn_align_batch(pmn_ctx *c, int n, const char *const *ref_fasta_paths, const char *const *qry_fasta_paths,
                      const char *const *out_delta_paths, const pmn_opts *o);
 
+/* ---- the two post-steps of lib/nucmer/mugsy_nucmer.ml, on .delta text in host memory ----
+ * pmn_delta_filter: `delta-filter -1` (mode 1) / `-m` (mode 2), mugsy_nucmer.ml:102-105; maxolap is delta-filter's -o (75.0).
+ * pmn_delta2maf:    `delta2maf`, mugsy_nucmer.ml:118-124; ref / qry are the packed genomes the delta was computed from.
+ * *out is allocated by the library (release with pmn_free_text), *nout its length. */
+int  pmn_delta_filter(pmn_ctx *c, const char *delta, size_t n, int mode, double maxolap, char **out, size_t *nout);
+int  pmn_delta2maf(pmn_ctx *c, const char *delta, size_t n, const pmn_seq *ref, const pmn_seq *qry, char **out, size_t *nout);
+void pmn_free_text(char *p);
+
 /* ---- in-process batch scheduler ----
  * Replaces the reference's fan-out of one `mugsy_nucmer` process per pair: run_nucmers
  * (lib/base/job_processor.ml:128-154) cuts the pair list into Nucmer_task.t.searches

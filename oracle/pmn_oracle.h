@@ -84,6 +84,12 @@ const int64_t *pmo_deltas(const pmo_run *r);
 
 const char *pmo_delta_text(const pmo_run *r, size_t *len);
 
+/* ---- the two post-steps of lib/nucmer/mugsy_nucmer.ml (pmn_post_oracle.c; ORACLE_SPEC.md §8, §9) ----
+ * text in, malloc'd text out (release with pmo_free); 0 on success */
+int pmo_delta_filter(const char *delta, size_t n, int mode /* 1: -1, 2: -m */, double maxolap /* 75.0 */, char **out, size_t *nout);
+int pmo_delta2maf(const char *delta, size_t n, const char *ref_fasta, size_t nr, const char *qry_fasta, size_t nq, char **out, size_t *nout);
+void pmo_free(void *p);
+
 /* work counters for the benchmark (cells = DP cells evaluated by the extension engine) */
 int64_t pmo_dp_cells(const pmo_run *r);
 

@@ -48,6 +48,9 @@ def lib():
         L.pmo_delta_text.restype = C.c_void_p
         L.pmo_delta_text.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
         L.pmo_default_opts.argtypes = [C.POINTER(Opts)]
+        L.pmo_delta_filter.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_double, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+        L.pmo_delta2maf.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+        L.pmo_free.argtypes = [C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -134,3 +137,24 @@ def nucmer(ref_fasta: bytes, qry_fasta: bytes, ref_path="ref.fa", qry_path="qry.
         return r.delta(ref_path, qry_path)
     finally:
         r.close()
+
+
+def _text_out(rc, p, n, what):
+    if rc != 0:
+        raise ValueError(f"{what}: malformed input")
+    try:
+        return C.string_at(p.value, n.value) if n.value else b""
+    finally:
+        lib().pmo_free(p)
+
+
+def delta_filter(delta: bytes, mode: int = 1, maxolap: float = 75.0) -> bytes:
+    """`delta-filter -1` (mode 1) / `-m` (mode 2) on .delta text (lib/nucmer/mugsy_nucmer.ml:102-105)."""
+    p, n = C.c_void_p(), C.c_size_t()
+    return _text_out(lib().pmo_delta_filter(delta, len(delta), mode, maxolap, C.byref(p), C.byref(n)), p, n, "delta_filter")
+
+
+def delta2maf(delta: bytes, ref_fasta: bytes, qry_fasta: bytes) -> bytes:
+    """`delta2maf` on .delta text and the two FASTA texts (lib/nucmer/mugsy_nucmer.ml:118-124)."""
+    p, n = C.c_void_p(), C.c_size_t()
+    return _text_out(lib().pmo_delta2maf(delta, len(delta), ref_fasta, len(ref_fasta), qry_fasta, len(qry_fasta), C.byref(p), C.byref(n)), p, n, "delta2maf")

@@ -2,6 +2,7 @@
    _lib/libpmnucmer.so  — CUDA kernels + C ABI, sm_100a only
    _lib/libpmn_synth.so — synthetic genome generator (plain C)
    _lib/nucmer          — `nucmer`-argv-compatible CLI shim
+   _lib/delta-filter, _lib/delta2maf — argv-compatible front ends of the two post-steps
 """
 import glob
 import os
@@ -50,6 +51,13 @@ def build(force=False, verbose=False):
     if os.path.exists(cli_src) and (force or _stale(cli, [cli_src, so])):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", os.path.join(HERE, "..", "include"), cli_src, "-o", cli,
                                "-L", LIB, "-lpmnucmer", "-Wl,-rpath,$ORIGIN"])
+    post_src = os.path.join(CSRC, "post_main.cpp")
+    post = os.path.join(LIB, "delta-filter")
+    if os.path.exists(post_src) and (force or _stale(post, [post_src, so])):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", os.path.join(HERE, "..", "include"), post_src, "-o", post,
+                               "-L", LIB, "-lpmnucmer", "-Wl,-rpath,$ORIGIN"])
+        import shutil
+        shutil.copy2(post, os.path.join(LIB, "delta2maf"))      # one binary, the program name decides
     return so
 
 

@@ -233,7 +233,7 @@ extern "C" int pmn_seq_from_fasta(pmn_ctx *c, const char *fasta, size_t bytes, p
     int rc = find_headers(fasta, bytes, s.get(), hp);
     if (rc) return rc;
     rc = pmn_fasta_to_device(c, s.get(), fasta, bytes, hp);
-    if (rc) { s->w_fwd.release(); s->xm_fwd.release(); s->w_rev.release(); s->xm_rev.release(); return rc; }
+    if (rc) { s->w_fwd.release(); s->xm_fwd.release(); s->w_rev.release(); s->xm_rev.release(); s->residues.release(); return rc; }
     *out = s.release();
     return 0;
 }
@@ -264,6 +264,7 @@ extern "C" void pmn_seq_free(pmn_seq *s)
     if (!s) return;
     cudaSetDevice(s->ctx->device);
     pmn_pool_put(s->ctx, s->w_fwd); pmn_pool_put(s->ctx, s->xm_fwd); pmn_pool_put(s->ctx, s->w_rev); pmn_pool_put(s->ctx, s->xm_rev);
+    pmn_pool_put(s->ctx, s->residues);
     delete s;
 }
 extern "C" int64_t pmn_seq_bases(const pmn_seq *s) { return s ? s->n : 0; }

@@ -18,6 +18,7 @@ struct pmn_seq {
     int64_t nwords = 0;                 // words in each packed array (incl. padding)
     DevBuf w_fwd, xm_fwd;               // forward text
     DevBuf w_rev, xm_rev;               // reverse complement of the whole concatenation
+    DevBuf residues;                    // the concatenation as characters, one byte per base (forward strand; delta2maf prints these)
     PackedView fwd() const { return PackedView{ w_fwd.as<uint64_t>(), xm_fwd.as<uint32_t>(), n, has_x }; }
     PackedView rev() const { return PackedView{ w_rev.as<uint64_t>(), xm_rev.as<uint32_t>(), n, has_x }; }
 };

@@ -107,11 +107,12 @@ __global__ void __launch_bounds__(256) k_fa_keep(const uint8_t *__restrict__ txt
 }
 
 __global__ void __launch_bounds__(256) k_fa_emit(const uint8_t *__restrict__ txt, const uint32_t *__restrict__ keep, const uint32_t *__restrict__ pos, int64_t nb,
-                                                uint8_t *__restrict__ codes, uint32_t *__restrict__ any_x)
+                                                uint8_t *__restrict__ codes, uint8_t *__restrict__ residues, uint32_t *__restrict__ any_x)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nb || !keep[i]) return;
     const uint8_t ch = txt[i];
+    residues[pos[i]] = ch;                // the characters as given (case, IUPAC codes): what delta2maf prints
     uint32_t cd = ch == '>' ? (uint32_t)PMN_CODE_X : fa_code(ch);
     if (ch == '>') cd = PMN_CODE_X;       // a '>' is only kept as a record separator ('>' inside a sequence line is a plain non-acgt base)
     codes[pos[i]] = (uint8_t)cd;
@@ -148,7 +149,8 @@ int pmn_fasta_to_device(pmn_ctx *c, pmn_seq *s, const char *txt, size_t nb, cons
     pmn_scan<uint32_t, OpMaxU32, true>(ev, ev, (int64_t)nb, S.scan_tmp.as<uint32_t>(), st);
     k_fa_keep<<<g, 256, 0, st>>>(dtxt, ev, (int64_t)nb, header_pos[0], keep);
     pmn_scan<uint32_t, OpAddU32, false>(keep, pos, (int64_t)nb + 1, S.scan_tmp.as<uint32_t>(), st);
-    k_fa_emit<<<g, 256, 0, st>>>(dtxt, keep, pos, (int64_t)nb, S.codes.as<uint8_t>(), anyx);
+    if (pmn_pool_get(c, s->residues, nb + 128)) return -3;
+    k_fa_emit<<<g, 256, 0, st>>>(dtxt, keep, pos, (int64_t)nb, S.codes.as<uint8_t>(), s->residues.as<uint8_t>(), anyx);
     k_fa_gather<<<(nrec + 1 + 255) / 256, 256, 0, st>>>(pos, dhp, nrec, (int64_t)nb, dout);
     c->launches += 10;
     uint32_t *h = (uint32_t *)S.pinned;

@@ -53,6 +53,7 @@ SYMBOLS = [
     "pmn_result_n_deltas", "pmn_result_copy_alignments",
     "pmn_sched_create", "pmn_sched_destroy", "pmn_sched_workers", "pmn_sched_ctx", "pmn_sched_counters",
     "pmn_sched_align_fasta", "pmn_sched_align_seqs", "pmn_sched_align_indexed", "pmn_sched_align_files",
+    "pmn_delta_filter", "pmn_delta2maf", "pmn_free_text",
 ]
 
 
@@ -113,6 +114,9 @@ def lib():
         L.pmn_sched_align_seqs.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(cp), C.c_int, i32a, i32a, C.POINTER(Opts), C.POINTER(vp)]
         L.pmn_sched_align_indexed.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(cp), C.c_int, i32a, i32a, C.POINTER(Opts), C.POINTER(vp)]
         L.pmn_sched_align_files.argtypes = [vp, C.c_int, C.POINTER(cp), C.POINTER(cp), C.POINTER(cp), C.POINTER(Opts)]
+        L.pmn_delta_filter.argtypes = [vp, cp, C.c_size_t, C.c_int, C.c_double, C.POINTER(vp), C.POINTER(C.c_size_t)]
+        L.pmn_delta2maf.argtypes = [vp, cp, C.c_size_t, vp, vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+        L.pmn_free_text.argtypes = [vp]
         _LIB = L
     return _LIB
 
@@ -173,6 +177,23 @@ class Context:
         g, mhz = C.c_double(), C.c_double()
         _check(lib().pmn_measure_int32_peak(self.h, C.byref(g), C.byref(mhz)))
         return g.value, mhz.value
+
+    def _text(self, rc, p, n):
+        _check(rc)
+        try:
+            return C.string_at(p.value, n.value) if n.value else b""
+        finally:
+            lib().pmn_free_text(p)
+
+    def delta_filter(self, delta: bytes, mode: int = 1, maxolap: float = 75.0) -> bytes:
+        """`delta-filter -1` (mode 1) / `-m` (mode 2) on .delta text (lib/nucmer/mugsy_nucmer.ml:102-105)."""
+        p, n = C.c_void_p(), C.c_size_t()
+        return self._text(lib().pmn_delta_filter(self.h, delta, len(delta), mode, maxolap, C.byref(p), C.byref(n)), p, n)
+
+    def delta2maf(self, delta: bytes, ref: "Sequence", qry: "Sequence") -> bytes:
+        """`delta2maf` on .delta text and the two packed genomes it was computed from (mugsy_nucmer.ml:118-124)."""
+        p, n = C.c_void_p(), C.c_size_t()
+        return self._text(lib().pmn_delta2maf(self.h, delta, len(delta), ref.h, qry.h, C.byref(p), C.byref(n)), p, n)
 
     def sequence(self, fasta: bytes):
         return Sequence(self, fasta=fasta)

@@ -6,8 +6,11 @@ differs is the reference's
 which here calls the B200 library through its C ABI instead of forking MUMmer.
 
 `delta-filter` (mugsy_nucmer.ml:102-105) and `delta2maf` (:118-124) are external programs in the
-reference too and are rows "next" of SURVEY.md §8f: they are run from $PATH exactly as the
-reference does, and a missing program raises Failure like Shell.sh would.
+reference (MUMmer 3.20 / Mugsy).  Here they are calls into the same library (pmn_delta_filter,
+pmn_delta2maf: SURVEY.md §8f rows 1 and 2) on the same context, with the same intermediate files
+(nucmer.delta, nucmer.filt.delta) so that -debug runs can be compared file by file; a user
+post-processor (-delta_pp) is still run from $PATH, and a missing program raises Failure like
+Shell.sh would.
 """
 import os
 import shlex
@@ -123,13 +126,19 @@ def nucmer(options: Options, ref_file: str, query_file: str, ctx: Optional[lib.C
         rc = lib.lib().pmn_align_pair(c.h, os.fsencode(ref_file), os.fsencode(query_file), o, os.fsencode(delta_file))
         if rc != 0:
             raise Failure(lib.lib().pmn_last_error(None).decode(errors="replace"))
+        if options.filter:
+            # mugsy_nucmer.ml:102-105: "delta-filter %s %s > %s" with -m when -colinear, else -1
+            try:
+                with open(delta_file, "rb") as f:
+                    filtered = c.delta_filter(f.read(), 2 if options.colinear else 1)
+            except lib.PmnError as e:
+                raise Failure(str(e))
+            with open(delta_filt_file, "wb") as f:
+                f.write(filtered)
+            delta_file = delta_filt_file
     finally:
         if own:
             c.close()
-    if options.filter:
-        chaining_opt = "-m" if options.colinear else "-1"
-        _sh(options, f"delta-filter {chaining_opt} {shlex.quote(delta_file)} > {shlex.quote(delta_filt_file)}")
-        delta_file = delta_filt_file
     if options.delta_pp is not None:
         delta_pp_file = f"{obname}.pp.delta"
         _sh(options, f"{options.delta_pp} < {shlex.quote(delta_file)} > {shlex.quote(delta_pp_file)}")
@@ -137,9 +146,25 @@ def nucmer(options: Options, ref_file: str, query_file: str, ctx: Optional[lib.C
     return delta_file
 
 
-def generate_maf(options: Options):
-    """mugsy_nucmer.ml:118-124."""
-    _sh(options, f"delta2maf {shlex.quote(options.delta_out)} > {shlex.quote(options.maf_out)}")
+def generate_maf(options: Options, ctx: Optional[lib.Context] = None):
+    """mugsy_nucmer.ml:118-124: "delta2maf %s > %s" on delta_out."""
+    own = ctx is None
+    c = ctx or lib.Context(int(os.environ.get("PMN_DEVICE", "0")))
+    try:
+        with open(options.delta_out, "rb") as f:
+            delta = f.read()
+        rs, qs = c.sequence_from_file(options.ref_seq), c.sequence_from_file(options.query_seq)
+        try:
+            maf = c.delta2maf(delta, rs, qs)
+        finally:
+            qs.close(); rs.close()
+    except lib.PmnError as e:
+        raise Failure(str(e))
+    finally:
+        if own:
+            c.close()
+    with open(options.maf_out, "wb") as f:
+        f.write(maf)
 
 
 def run_search(options: Options, ctx=None, maf=True):
@@ -147,7 +172,7 @@ def run_search(options: Options, ctx=None, maf=True):
     delta_file = nucmer(options, options.ref_seq, options.query_seq, ctx)
     shutil.copyfile(delta_file, options.delta_out)
     if maf:
-        generate_maf(options)
+        generate_maf(options, ctx)
 
 
 def main(argv=None):
