@@ -58,21 +58,60 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
         ::"r"(smem_u32(bar)), "r"(phase) : "memory");
 }
 
+// Positions fit 31 bits (pmn_fasta_to_device refuses more than 2^31 bases): the per-position code below does all its
+// index arithmetic in 32 bits, which is a third fewer instructions than the int64 helpers of pmn_common.cuh.
+struct View32 { const uint64_t *w; const uint32_t *xm; uint32_t n; int has_x; };
+__device__ __forceinline__ View32 view32(const PackedView &v) { return View32{ v.w, v.xm, (uint32_t)v.n, v.has_x }; }
+__device__ __forceinline__ uint64_t win32(const uint64_t *__restrict__ w, uint32_t p)
+{
+    const uint32_t k = p >> 5; const int sh = (int)(p & 31u) * 2;
+    const uint64_t a = __ldg(w + k), b = __ldg(w + k + 1);
+    return sh ? (a << sh) | (b >> (64 - sh)) : a;
+}
+// matchable bases among the 32 starting at p (stops at the first X or at the end)
+__device__ __forceinline__ int valid32(const View32 &s, uint32_t p)
+{
+    if (p >= s.n) return 0;
+    if (s.has_x) { const uint32_t k = p >> 5; const int sh = (int)(p & 31u); const uint32_t x = __funnelshift_l(__ldg(s.xm + k + 1), __ldg(s.xm + k), sh); return x ? __clz((int)x) : 32; }
+    const uint32_t r = s.n - p;
+    return r < 32u ? (int)r : 32;
+}
+__device__ __forceinline__ int base32(const View32 &s, uint32_t p)      // 0..3, or 4; p = 0xffffffff (one before the start) is X
+{
+    if (p >= s.n) return PMN_CODE_X;
+    if (s.has_x && ((__ldg(s.xm + (p >> 5)) >> (31 - (int)(p & 31u))) & 1u)) return PMN_CODE_X;
+    return (int)((__ldg(s.w + (p >> 5)) >> (62 - 2 * (int)(p & 31u))) & 3ull);
+}
+// common prefix in matchable bases of a[pa..] and b[pb..]
+__device__ __forceinline__ uint32_t lcp32(const View32 &a, uint32_t pa, const View32 &b, uint32_t pb)
+{
+    uint32_t l = 0;
+    for (;;) {
+        const int va = valid32(a, pa + l), vb = valid32(b, pb + l);
+        const int v = va < vb ? va : vb;
+        const uint64_t x = win32(a.w, pa + l) ^ win32(b.w, pb + l);
+        int m = x ? (__clzll((long long)x) >> 1) : 32;
+        if (m > v) m = v;
+        l += (uint32_t)m;
+        if (m < 32) return l;
+    }
+}
+
 // true iff the reference suffix at s sorts before Q[g..] (order of pmn_index.cu; a query X or
 // the query end compares greater than every reference symbol)
-__device__ __forceinline__ bool ref_lt_query(const PackedView &R, int64_t s, const PackedView &Q, int64_t g, uint64_t qw0, int vq0)
+__device__ __forceinline__ bool ref_lt_query(const View32 &R, uint32_t s, const View32 &Q, uint32_t g, uint64_t qw0, int vq0)
 {
-    int64_t off = 0;
+    uint32_t off = 0;
     uint64_t qw = qw0; int vq = vq0;
     for (;;) {
-        int vr = pmn_valid32(R, s + off);
-        uint64_t rw = pmn_window64(R.w, s + off);
-        uint64_t x = rw ^ qw;
-        int m = x ? (__clzll((long long)x) >> 1) : 32;
-        int v = vr < vq ? vr : vq;
+        const int vr = valid32(R, s + off);
+        const uint64_t rw = win32(R.w, s + off);
+        const uint64_t x = rw ^ qw;
+        const int m = x ? (__clzll((long long)x) >> 1) : 32;
+        const int v = vr < vq ? vr : vq;
         if (m < v) return ((rw >> (62 - 2 * m)) & 3ull) < ((qw >> (62 - 2 * m)) & 3ull);
-        if (v == 32) { off += 32; vq = pmn_valid32(Q, g + off); qw = pmn_window64(Q.w, g + off); continue; }
-        if (vr < vq) return s + off + vr >= R.n;     // reference ran out (END, smallest) or hit an X (greater)
+        if (v == 32) { off += 32; vq = valid32(Q, g + off); qw = win32(Q.w, g + off); continue; }
+        if (vr < vq) return s + off + (uint32_t)vr >= R.n;     // reference ran out (END, smallest) or hit an X (greater)
         return true;                                 // the query hit X/END first, or both did: query is greater
     }
 }
@@ -86,8 +125,6 @@ __global__ void __launch_bounds__(SEED_THREADS) k_seed(PackedView R, const uint3
     __shared__ __align__(16) uint64_t s_w[SEED_WORDS];
     __shared__ __align__(16) uint32_t s_x[SEED_WORDS];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ uint32_t s_wc[SEED_THREADS / 32];
-    __shared__ uint32_t s_count;
 
     // which section does this tile belong to
     int lo_s = 0, hi_s = nsec - 1;
@@ -98,7 +135,7 @@ __global__ void __launch_bounds__(SEED_THREADS) k_seed(PackedView R, const uint3
     const int64_t g0 = sec.start + off0;
     const int64_t w0 = (g0 >> 5) & ~3ll;                                   // 16-byte aligned for text and mask
 
-    if (threadIdx.x == 0) { mbar_init(&s_bar, 1); s_count = 0; }
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t bytes = SEED_WORDS * 8 + (Q.has_x ? SEED_WORDS * 4 : 0);
@@ -111,66 +148,64 @@ __global__ void __launch_bounds__(SEED_THREADS) k_seed(PackedView R, const uint3
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt = pmn_lanemask_lt();
     const int first_need = minmatch < 32 ? minmatch : 32;
-
+    const View32 R32 = view32(R), Q32 = view32(Q);
+    const uint32_t sa_n = R32.n;
+    // Warp w owns the SEED_ITERS * 32 consecutive positions [w * 256, (w + 1) * 256) of the tile and its own run of the
+    // staging area, so the anchors come out in position order without any block-wide step inside the loop.
+    int4 *wstage = stage + ((size_t)blockIdx.x * (SEED_THREADS / 32) + warp) * (SEED_ITERS * 32);
+    uint32_t wcount = 0;
     for (int it = 0; it < SEED_ITERS; it++) {
-        const int64_t off = off0 + it * SEED_THREADS + threadIdx.x;   // position inside the record
+        const int64_t off = off0 + warp * (SEED_ITERS * 32) + it * 32 + lane;   // position inside the record
         bool found = false; int4 out = make_int4(0, 0, 0, 0);
         if (off < sec.npos) {
-            const int64_t g = sec.start + off;
+            const uint32_t g = (uint32_t)(sec.start + off);
             // first window from the staged tile
-            int64_t rel = g - (w0 << 5); int k = (int)(rel >> 5), sh = (int)(rel & 31);
-            uint64_t a = s_w[k], b = s_w[k + 1];
-            uint64_t qw = sh ? (a << (2 * sh)) | (b >> (64 - 2 * sh)) : a;
+            const uint32_t rel = g - (uint32_t)(w0 << 5); const int k = (int)(rel >> 5), sh = (int)(rel & 31);
+            const uint64_t a = s_w[k], b = s_w[k + 1];
+            const uint64_t qw = sh ? (a << (2 * sh)) | (b >> (64 - 2 * sh)) : a;
             int vq;
-            if (Q.has_x) { uint32_t xw = __funnelshift_l(s_x[k + 1], s_x[k], sh); vq = xw ? __clz((int)xw) : 32; }
-            else { int64_t r = Q.n - g; vq = r < 32 ? (int)r : 32; }
+            if (Q.has_x) { const uint32_t xw = __funnelshift_l(s_x[k + 1], s_x[k], sh); vq = xw ? __clz((int)xw) : 32; }
+            else { const uint32_t r = Q32.n - g; vq = r < 32u ? (int)r : 32; }
             if (vq >= first_need) {
                 uint32_t lo, hi;
-                if (minmatch >= K) { uint32_t km = (uint32_t)(qw >> (64 - 2 * K)); lo = __ldg(table + km); hi = __ldg(table + km + 1); }
-                else { lo = 0; hi = (uint32_t)R.n; }
+                if (minmatch >= K) { const uint32_t km = (uint32_t)(qw >> (64 - 2 * K)); lo = __ldg(table + km); hi = __ldg(table + km + 1); }
+                else { lo = 0; hi = sa_n; }
                 if (lo < hi) {
                     while (lo < hi) {
-                        uint32_t mid = (lo + hi) >> 1;
-                        if (ref_lt_query(R, __ldg(sa + mid), Q, g, qw, vq)) lo = mid + 1; else hi = mid;
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (ref_lt_query(R32, __ldg(sa + mid), Q32, g, qw, vq)) lo = mid + 1; else hi = mid;
                     }
-                    const int64_t p = lo;
-                    int64_t L1 = p > 0 ? pmn_lcp(Q, g, R, __ldg(sa + p - 1), 0, Q.n) : -1;
-                    int64_t L2 = p < R.n ? pmn_lcp(Q, g, R, __ldg(sa + p), 0, Q.n) : -1;
-                    int64_t L = L1 > L2 ? L1 : L2;
+                    const uint32_t p = lo;
+                    const int64_t L1 = p > 0 ? (int64_t)lcp32(Q32, g, R32, __ldg(sa + p - 1)) : -1;
+                    const int64_t L2 = p < sa_n ? (int64_t)lcp32(Q32, g, R32, __ldg(sa + p)) : -1;
+                    const int64_t L = L1 > L2 ? L1 : L2;
                     if (L >= minmatch && L1 != L2) {
-                        bool unique; int64_t r;
-                        if (L2 > L1) { r = __ldg(sa + p); unique = !(p + 1 < R.n && __ldg(lcp + p + 1) >= L); }
+                        bool unique; uint32_t r;
+                        if (L2 > L1) { r = __ldg(sa + p); unique = !(p + 1 < sa_n && __ldg(lcp + p + 1) >= L); }
                         else { r = __ldg(sa + p - 1); unique = !(__ldg(lcp + p - 1) >= L); }
                         if (unique) {
-                            int qb = pmn_base_at(Q, g - 1), rb = pmn_base_at(R, r - 1);
+                            const int qb = base32(Q32, g - 1), rb = base32(R32, r - 1);
                             if (!(qb == rb && qb < 4)) { found = true; out = make_int4((int)(r + 1), (int)(off + 1), (int)L, sec.tag); }
                         }
                     }
                 }
             }
         }
-        // ordered compaction of this iteration's 256 positions
-        unsigned bal = __ballot_sync(0xffffffffu, found);
-        if (lane == 0) s_wc[warp] = __popc(bal);
-        __syncthreads();
-        uint32_t before = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < SEED_THREADS / 32; w++) { uint32_t cw = s_wc[w]; if (w < warp) before += cw; total += cw; }
-        uint32_t base = s_count;
-        if (found) stage[(size_t)blockIdx.x * SEED_TILE + base + before + __popc(bal & lt)] = out;
-        __syncthreads();
-        if (threadIdx.x == 0) s_count = base + total;
-        __syncthreads();
+        const unsigned bal = __ballot_sync(0xffffffffu, found);
+        if (found) wstage[wcount + __popc(bal & lt)] = out;
+        wcount += __popc(bal);
     }
-    if (threadIdx.x == 0) tile_cnt[blockIdx.x] = s_count;
+    if (lane == 0) tile_cnt[(size_t)blockIdx.x * (SEED_THREADS / 32) + warp] = wcount;
 }
 
 // gather the per-tile runs into one contiguous, ordered anchor array
-__global__ void __launch_bounds__(256) k_seed_gather(const int4 *__restrict__ stage, const uint32_t *__restrict__ tile_cnt,
-                                                    const uint32_t *__restrict__ tile_off, int4 *__restrict__ anchors)
+__global__ void __launch_bounds__(256) k_seed_gather(const int4 *__restrict__ stage, const uint32_t *__restrict__ run_cnt,
+                                                    const uint32_t *__restrict__ run_off, int64_t nruns, int4 *__restrict__ anchors)
 {
-    uint32_t cnt = tile_cnt[blockIdx.x], off = tile_off[blockIdx.x];
-    for (uint32_t k = threadIdx.x; k < cnt; k += blockDim.x) anchors[off + k] = stage[(size_t)blockIdx.x * SEED_TILE + k];
+    const int64_t run = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // one warp per run of SEED_ITERS * 32 positions
+    if (run >= nruns) return;
+    const uint32_t cnt = run_cnt[run], off = run_off[run];
+    for (uint32_t k = threadIdx.x & 31; k < cnt; k += 32) anchors[off + k] = stage[(size_t)run * (SEED_ITERS * 32) + k];
 }
 
 int pmn_seed_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_opts *o, int64_t *n_anchors, int part, int nparts)
@@ -203,25 +238,26 @@ int pmn_seed_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_o
     const int64_t t_lo = all_tiles * part / nparts, t_hi = all_tiles * (part + 1) / nparts;
     tiles = t_hi - t_lo;
     if (tiles == 0) return 0;
+    const int64_t runs = tiles * (SEED_THREADS / 32);          // one anchor run per warp of a tile
     if (S.sections.ensure(sizeof(SeedSection) * secs.size()) || S.stage.ensure(sizeof(int4) * (size_t)tiles * SEED_TILE) ||
-        S.tile_cnt.ensure(4 * (size_t)tiles) || S.tile_off.ensure(4 * (size_t)tiles) ||
-        S.scan_tmp.ensure(8 * pmn_scan_scratch_elems(tiles)) || S.ensure_pinned(64)) return -3;
+        S.tile_cnt.ensure(4 * (size_t)runs) || S.tile_off.ensure(4 * (size_t)runs) ||
+        S.scan_tmp.ensure(8 * pmn_scan_scratch_elems(runs)) || S.ensure_pinned(64)) return -3;
     PMN_H2D(c, S.sections.p, secs.data(), sizeof(SeedSection) * secs.size());
     PMN_CUDA_OK(cudaEventRecord(c->ev[6], st));
     k_seed<<<(unsigned)tiles, SEED_THREADS, 0, st>>>(ix->seq->fwd(), ix->sa(), ix->lcp(), ix->table(), ix->K,
                                                      q->fwd(), q->rev(), S.sections.as<SeedSection>(), (int)secs.size(), o->minmatch,
                                                      S.stage.as<int4>(), S.tile_cnt.as<uint32_t>(), (unsigned)t_lo);
     PMN_CUDA_OK(cudaEventRecord(c->ev[7], st));
-    pmn_scan<uint32_t, OpAddU32, false>(S.tile_cnt.as<uint32_t>(), S.tile_off.as<uint32_t>(), tiles, S.scan_tmp.as<uint32_t>(), st);
+    pmn_scan<uint32_t, OpAddU32, false>(S.tile_cnt.as<uint32_t>(), S.tile_off.as<uint32_t>(), runs, S.scan_tmp.as<uint32_t>(), st);
     uint32_t *tail = (uint32_t *)S.pinned;
-    PMN_D2H(c, tail, S.tile_off.as<uint32_t>() + (tiles - 1), 4);
-    PMN_D2H(c, tail + 1, S.tile_cnt.as<uint32_t>() + (tiles - 1), 4);
+    PMN_D2H(c, tail, S.tile_off.as<uint32_t>() + (runs - 1), 4);
+    PMN_D2H(c, tail + 1, S.tile_cnt.as<uint32_t>() + (runs - 1), 4);
     PMN_CUDA_OK(cudaStreamSynchronize(st));   // the secs vector is also safe to drop after this
     int64_t total = (int64_t)tail[0] + tail[1];
     c->launches += 4;
     if (total > 0) {
         if (S.anchors.ensure(sizeof(int4) * (size_t)total)) return -3;
-        k_seed_gather<<<(unsigned)tiles, 256, 0, st>>>(S.stage.as<int4>(), S.tile_cnt.as<uint32_t>(), S.tile_off.as<uint32_t>(), S.anchors.as<int4>());
+        k_seed_gather<<<(unsigned)((runs + 7) / 8), 256, 0, st>>>(S.stage.as<int4>(), S.tile_cnt.as<uint32_t>(), S.tile_off.as<uint32_t>(), runs, S.anchors.as<int4>());
         c->launches += 1;
     }
     PMN_CUDA_OK(cudaGetLastError());
