@@ -116,7 +116,9 @@ def run_gpu(args):
 
     genomes, fastas, pairs = workload(args)
     names = [g[0] for g in genomes]
-    fasta_bytes = [f[1] for f in fastas]
+    # end-to-end arm: the FASTA text of every genome sits in PINNED host memory and is copied to the device every step
+    pinned = [torch.frombuffer(bytearray(f[1]), dtype=torch.uint8).pin_memory() for f in fastas]
+    fasta_bytes = [(t.data_ptr(), t.numel()) for t in pinned]
     strong = args.mode == "strong" and world > 1
     if strong:
         # the 28 pairs are dealt to the ranks; every reference index is built once in the whole job and
@@ -142,6 +144,10 @@ def run_gpu(args):
                     if a == i:
                         res = ix.align(seqs[b], ref_path=names[a], qry_path=names[b])
                         collect.append((a, b, res.stats, len(res.delta)))
+                        # the two post-steps every pair goes through in the reference (mugsy_nucmer.ml:102-105,118-124)
+                        t0 = time.perf_counter(); filt = ctx.delta_filter(res.delta, 1)
+                        t1 = time.perf_counter(); maf = ctx.delta2maf(filt, seqs[a], seqs[b]); t2 = time.perf_counter()
+                        post.append(((t1 - t0) * 1e3, (t2 - t1) * 1e3, len(filt), len(maf)))
                         res.close()
                 ix.close()
             return
@@ -156,7 +162,7 @@ def run_gpu(args):
     def step_e2e():
         """The same from FASTA bytes in host memory (parse, H2D, pack inside)."""
         if strong:
-            seqs = {g: ctx.sequence(fasta_bytes[g]) for g in needed}
+            seqs = {g: ctx.sequence(fastas[g][1]) for g in needed}
             step_resident(seqs)
             for q in seqs.values():
                 q.close()
@@ -170,6 +176,8 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     def timed(fn, steps):
+        if os.environ.get("PMN_ALLOC_LOG"):
+            print(f"[bench] timed region starts, {lib.alloc_count()} allocations so far", file=sys.stderr, flush=True)
         # the workers launch on their own streams and every call returns with all of them drained, so
         # events recorded on the (idle) current stream around the calls bracket exactly the device work
         barrier()
@@ -206,7 +214,7 @@ def run_gpu(args):
     ms_e2e, cnt_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     # ---- one instrumented pass for the per-kernel figures
-    detail = []
+    detail = []; post = []
     step_resident(resident, detail, one_worker=True)
     int32_gops, _ = ctx.int32_peak()
 
@@ -242,7 +250,7 @@ def run_gpu(args):
                      "share_of_step": seed_kernel_ms / (sum(stage_ms.values()) or 1)}
         roof_seed["frac"] = roof_seed["achieved"] / hbm_peak if roof_seed["achieved"] else None
         gcups = wave1_cells / (wave1_ms * 1e-3) / 1e9 if wave1_ms else None
-        roof_ext = {"kernel": "k_ex_wave1", "bound": "int32", "achieved": gcups * 16 if gcups else None, "peak": int32_gops, "unit": "Gop/s",
+        roof_ext = {"kernel": "k_ex_wave1_tpj + k_ex_wave1_big (side by side on two streams)", "bound": "int32", "traffic": None, "achieved": gcups * 16 if gcups else None, "peak": int32_gops, "unit": "Gop/s",
                     "peak_source": "measured (pmn_measure_int32_peak, add+max chains)", "gcups": gcups, "ops_per_cell": 16,
                     "cells_per_step": wave1_cells, "launch_ms": wave1_ms / max(1, len(detail)),
                     "share_of_step": wave1_ms / (sum(stage_ms.values()) or 1)}
@@ -250,6 +258,13 @@ def run_gpu(args):
         roof_idx = {"kernel": "index build (sort + doubling + lcp + table)", "bound": "hbm", "achieved": b_index / (stage_ms["index"] * 1e-3) / 1e9 if stage_ms["index"] else None,
                     "peak": hbm_peak, "unit": "GB/s"}
         roof_idx["frac"] = roof_idx["achieved"] / hbm_peak if roof_idx["achieved"] else None
+        # DRAM bytes per launch from the committed ncu --set full capture of one 5 Mbp pair (profiles/): static, not measured in this run
+        tr = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+        if os.path.exists(tr) and args.genome_bp == 5_000_000:
+            kt = json.load(open(tr))["kernels"]
+            if "k_seed" in kt: roof_seed["traffic"] = kt["k_seed"]["dram_bytes_per_launch"]
+            roof_ext["traffic"] = sum(kt[k]["dram_bytes_per_launch"] for k in ("k_ex_wave1_tpj", "k_ex_wave1_big") if k in kt) or None
+            roof_ext["traffic_source"] = roof_seed["traffic_source"] = "profiles/r01_ncu_traffic.json (ncu --set full, one pair)"
         dominant = roof_ext if wave1_ms >= seed_kernel_ms else roof_seed
         out = {
             "metric": METRIC, "value": npairs_all * args.steps / (ms_res * 1e-3), "unit": UNIT,
@@ -272,6 +287,9 @@ def run_gpu(args):
             "stage_ms_per_step": stage_ms,
             "host_wall_ms_per_step": {"index_build": sum({a: st["wall_ms_index"] for a, _, st, _ in detail}.values()),
                                       "align_calls": S("wall_ms_align"), "of_which_delta_text": S("wall_ms_text")},
+            "post_steps_per_pair": {"what": "delta-filter -1 then delta2maf on each pair's .delta (pmn_delta_filter, pmn_delta2maf: host text in, host text out), one pair at a time, wall clock",
+                                    "delta_filter_ms": statistics.mean(p[0] for p in post), "delta2maf_ms": statistics.mean(p[1] for p in post),
+                                    "maf_bytes": statistics.mean(p[3] for p in post), "maf_gb_per_s": sum(p[3] for p in post) / 1e9 / (sum(p[1] for p in post) * 1e-3)} if post else None,
             "roofline": dominant, "roofline_seed": roof_seed, "roofline_extend": roof_ext, "roofline_index": roof_idx,
             "counts_per_step": {"anchors": S("anchors"), "clusters": S("clusters"), "alignments": S("alignments"), "dp_cells": S("dp_cells"),
                                 "dp_jobs": S("dp_jobs"), "aligned_ref_bases": aligned_bp},

@@ -30,12 +30,17 @@ extern "C" const char *pmn_last_error(const pmn_ctx *) { return g_err.msg; }
 
 thread_local cudaStream_t pmn_tls_stream = nullptr;
 
+static inline double now_ms();
+static const double g_t_start = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 static std::atomic<long long> g_allocs{0};
 void pmn_count_alloc(size_t bytes, size_t had)
 {
     g_allocs++;
     static const bool log = getenv("PMN_ALLOC_LOG") != nullptr;      // which buffers still grow at steady state
-    if (log) fprintf(stderr, "[pmn] cudaMalloc %zu bytes (buffer had %zu)\n", bytes, had);
+    if (log) {
+        const double t0 = now_ms();
+        fprintf(stderr, "[pmn] t=%.1f ms: allocation of %zu bytes (buffer had %zu)\n", t0 - g_t_start, bytes, had);
+    }
 }
 extern "C" int64_t pmn_alloc_count(void) { return (int64_t)g_allocs.load(); }
 

@@ -63,7 +63,7 @@ struct BorrowedScratch {
         cudaStreamSynchronize(c->stream);
         { std::lock_guard<std::mutex> lk(s->bmu); s->build_scratch.push_back(c->scratch); }
         c->scratch = own;
-        s->bcv.notify_one();
+        s->bcv.notify_all();
     }
 };
 }  // namespace
@@ -81,7 +81,7 @@ extern "C" int pmn_sched_create(int device, int workers, pmn_sched **out)
         if (!s->ctx.empty()) c->pool = s->ctx[0]->pool;
         s->ctx.push_back(c);
     }
-    for (int k = 0; k < std::min(workers, 2); k++) s->build_scratch.push_back(pmn_scratch_new());
+    for (int k = 0; k < std::min(workers, 4); k++) s->build_scratch.push_back(pmn_scratch_new());
     *out = s;
     return 0;
 }
@@ -128,6 +128,9 @@ static int sched_run(pmn_sched *s, int ng, const char *const *fasta, const size_
     std::atomic<int> next{0};
     s->err.clear(); s->err_code = 0;
 
+    const int MAX_LIVE_INDEXES = 4;
+    int live_indexes = 0;                      // guarded by s->bmu
+    std::atomic<int> failed{0};                // some worker gave up: nobody may keep waiting for an index slot
     // get a shared object: build it if nobody has, wait if somebody is
     auto acquire = [&](std::vector<Slot> &v, int g, auto &&build) -> void * {
         std::unique_lock<std::mutex> lk(s->mu);
@@ -142,6 +145,7 @@ static int sched_run(pmn_sched *s, int ng, const char *const *fasta, const size_
                 lk.lock();
                 sl.obj = o; sl.state = o ? ST_READY : ST_FAILED;
                 if (!o && !s->err_code) { s->err_code = PMN_E_INTERNAL; s->err = pmn_last_error(nullptr); }
+                if (!o) { failed.store(1); s->bcv.notify_all(); }
                 s->cv.notify_all();
                 return o;
             }
@@ -149,18 +153,29 @@ static int sched_run(pmn_sched *s, int ng, const char *const *fasta, const size_
         }
     };
 
+    const int W_active = (int)std::min<size_t>(s->ctx.size(), (size_t)std::max(1, np));
     auto worker = [&](int w) {
         pmn_ctx *c = s->ctx[(size_t)w];
         cudaSetDevice(c->device);
+        auto pack = [&](int g) { return acquire(seqs, g, [&]() -> void * { BorrowedScratch b(s, c); pmn_seq *x = nullptr; return pmn_seq_from_fasta(c, fasta[g], bytes[g], &x) ? nullptr : (void *)x; }); };
+        // genomes given as FASTA text: the workers pack them side by side first (H2D + parse + 2-bit pack per genome),
+        // instead of every worker waiting for the reference of the first pairs and then packing its query alone
+        if (!resident) for (int g = w; g < ng; g += W_active) if (seqs[(size_t)g].users > 0 && !pack(g)) return;
         for (;;) {
             { std::lock_guard<std::mutex> lk(s->mu); if (s->err_code) return; }
             const int k = next.fetch_add(1);
             if (k >= np) return;
             const int p = order[(size_t)k], r = ref[p], q = qry[p];
-            auto pack = [&](int g) { return acquire(seqs, g, [&]() -> void * { BorrowedScratch b(s, c); pmn_seq *x = nullptr; return pmn_seq_from_fasta(c, fasta[g], bytes[g], &x) ? nullptr : (void *)x; }); };
             pmn_seq *rs = (pmn_seq *)pack(r); if (!rs) return;
             pmn_seq *qs = (pmn_seq *)pack(q); if (!qs) return;
-            pmn_index *ix = (pmn_index *)acquire(idx, r, [&]() -> void * { BorrowedScratch b(s, c); pmn_index *x = nullptr; return pmn_index_build(c, rs, &x) ? nullptr : (void *)x; });
+            pmn_index *ix = (pmn_index *)acquire(idx, r, [&]() -> void * {
+                // at most MAX_LIVE_INDEXES indexes built by this run are alive at a time: pairs are taken in reference order, so the
+                // holders of the oldest ones finish without needing another; bounds the memory (8.25 B/base each) and keeps the
+                // number of index images the pool ever holds fixed, i.e. no allocation in later batches
+                { std::unique_lock<std::mutex> lk(s->bmu); s->bcv.wait(lk, [&] { return live_indexes < MAX_LIVE_INDEXES || failed.load(); }); if (failed.load()) return nullptr; live_indexes++; }
+                BorrowedScratch b(s, c); pmn_index *x = nullptr;
+                if (pmn_index_build(c, rs, &x)) { std::lock_guard<std::mutex> lk(s->bmu); live_indexes--; s->bcv.notify_all(); return nullptr; }
+                return (void *)x; });
             if (!ix) return;
             pmn_result *res = nullptr;
             {
@@ -177,19 +192,31 @@ static int sched_run(pmn_sched *s, int ng, const char *const *fasta, const size_
                 for (size_t i = 0; i < mine.size() && i < s->hiwater.size(); i++) s->hiwater[i] = std::max(s->hiwater[i], mine[i]->cap);
             }
             std::lock_guard<std::mutex> lk(s->mu);
-            if (rc) { if (!s->err_code) { s->err_code = rc; s->err = pmn_last_error(nullptr); } return; }
+            if (rc) { if (!s->err_code) { s->err_code = rc; s->err = pmn_last_error(nullptr); } failed.store(1); s->bcv.notify_all(); return; }
             out[p] = res;
             // the last user of an index / of a genome packed by this run frees it
-            if (--idx[(size_t)r].users == 0) { pmn_index_free(ix); idx[(size_t)r].obj = nullptr; idx[(size_t)r].state = ST_NONE; }
+            if (--idx[(size_t)r].users == 0) {
+                pmn_index_free(ix); idx[(size_t)r].obj = nullptr; idx[(size_t)r].state = ST_NONE;
+                { std::lock_guard<std::mutex> lk2(s->bmu); live_indexes--; }
+                s->bcv.notify_all();
+            }
             if (!resident) for (int g : { r, q }) if (--seqs[(size_t)g].users == 0) { pmn_seq_free((pmn_seq *)seqs[(size_t)g].obj); seqs[(size_t)g].obj = nullptr; seqs[(size_t)g].state = ST_NONE; }
         }
     };
 
-    const int W = (int)std::min<size_t>(s->ctx.size(), (size_t)std::max(1, np));
+    const int W = W_active;
     std::vector<std::thread> th;
     for (int w = 1; w < W; w++) th.emplace_back(worker, w);
     worker(0);
     for (auto &t : th) t.join();
+    {   // level the build-scratch sets: a set that only comes into use when several builds coincide is full size by then
+        std::lock_guard<std::mutex> lk(s->bmu);
+        std::vector<size_t> mx;
+        for (Scratch *b : s->build_scratch) { auto v = b->all(); if (mx.size() != v.size()) mx.assign(v.size(), 0); for (size_t i = 0; i < v.size(); i++) mx[i] = std::max(mx[i], v[i]->cap); }
+        pmn_tls_stream = s->ctx[0]->stream;
+        for (Scratch *b : s->build_scratch) { auto v = b->all(); for (size_t i = 0; i < v.size(); i++) if (mx[i] > v[i]->cap) v[i]->grow_to(mx[i]); }
+        cudaStreamSynchronize(s->ctx[0]->stream);
+    }
 
     if (s->err_code) {
         for (int p = 0; p < np; p++) { pmn_result_free(out[p]); out[p] = nullptr; }

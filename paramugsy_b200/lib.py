@@ -242,7 +242,10 @@ class Scheduler:
         """fastas: list of FASTA bytes in host memory; pairs: [(ref index, qry index)] -> [Result]."""
         o = opts if opts is not None else default_opts(**kw)
         g = len(fastas)
-        fa = (C.c_char_p * g)(*fastas); nb = (C.c_size_t * g)(*[len(f) for f in fastas])
+        # an entry may also be (address, length) of FASTA text the caller keeps in (pinned) host memory
+        addr = [C.cast(C.c_char_p(f), C.c_void_p).value if isinstance(f, (bytes, bytearray)) else int(f[0]) for f in fastas]
+        fa = C.cast((C.c_void_p * g)(*addr), C.POINTER(C.c_char_p))
+        nb = (C.c_size_t * g)(*[len(f) if isinstance(f, (bytes, bytearray)) else int(f[1]) for f in fastas])
         nm = (C.c_char_p * g)(*[os.fsencode(x) for x in names]) if names else None
         n, r, q = self._pairs(pairs)
         out = (C.c_void_p * n)()
