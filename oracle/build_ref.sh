@@ -12,3 +12,7 @@ mkdir -p "$HERE/_ref"
 P="$REF/lib/profiles_lib"
 g++ -O2 -std=c++11 -I"$P" "$P/m_delta.cc" "$P/m_delta_stream_test.cc" -o "$HERE/_ref/m_delta_stream_test"
 g++ -O2 -std=c++11 -I"$P" "$P/m_delta.cc" "$HERE/ref_delta_roundtrip.cc" -o "$HERE/_ref/ref_delta_roundtrip"
+# the reference's own consumer of these deltas at merge nodes (lib/m_translate): compiled as it is,
+# run by the tests on our .delta files to see that they drive it without assertion failures (m_translate.cc:42-43,550-551)
+T="$REF/lib/m_translate"
+g++ -O2 -std=c++11 -I"$P" -I"$T" "$P/m_delta.cc" "$P/m_delta_builder.cc" "$P/m_profile.cc" "$P/m_fileutils.cc" "$T/m_translate.cc" "$T/m_translate_main.cc" -o "$HERE/_ref/m_translate"

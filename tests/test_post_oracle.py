@@ -152,3 +152,44 @@ def test_filtered_delta_goes_through_the_reference_parser(oracle, deltas, tmp_pa
         # M_delta_stream -> M_delta_stream_writer re-encodes every alignment (metadata written as 1 2 3, m_delta_stream_writer.hh:71)
         got = [(a[1][:4], a[2]) for a in alignments(b"x y\nNUCMER\n" + out.stdout.split(b"\n", 2)[2])] if out.stdout.count(b"\n") > 2 else []
         assert got == [(a[1][:4], a[2]) for a in alignments(one)]
+
+
+# ---- the reference's own consumer of these deltas at merge nodes (lib/m_translate, compiled as it is)
+
+M_TRANSLATE = os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref", "m_translate")
+
+
+def run_m_translate(tmp_path, delta: bytes, ref: bytes, qry: bytes, split_ref_at=None):
+    """Writes profile directories in the format of lib/profiles_lib/m_profile.cc:15-84 (one gap-free profile per
+    record, or two per reference record when split_ref_at is given) and runs `m_translate left right list out`
+    (lib/m_translate/m_translate_main.cc:22-45)."""
+    (tmp_path / "in.delta").write_bytes(delta)
+    for side, fa in (("left", ref), ("right", qry)):
+        os.makedirs(tmp_path / side, exist_ok=True)
+        with open(tmp_path / side / "profiles", "w") as f:
+            for k, (name, seq) in enumerate(H.parse_fasta(fa)):
+                cuts = [(1, len(seq))]
+                if side == "left" and split_ref_at and len(seq) > split_ref_at:
+                    cuts = [(1, split_ref_at), (split_ref_at + 1, len(seq))]
+                for m, (s, e) in enumerate(cuts):
+                    f.write(f"{side[0].upper()}{k} {m} {name} {s} {e} {e - s + 1} {len(seq)}\n0\n{seq[s - 1:e].decode()}\n")
+    (tmp_path / "list").write_text(str(tmp_path / "in.delta") + "\n")
+    out = subprocess.run([M_TRANSLATE, str(tmp_path / "left"), str(tmp_path / "right"), str(tmp_path / "list"), str(tmp_path / "out.delta")], capture_output=True)
+    assert out.returncode == 0, out.stderr          # an assertion failure of m_translate.cc aborts with a non-zero status
+    return (tmp_path / "out.delta").read_bytes()
+
+
+@pytest.mark.parametrize("name", ["100k_98_inv", "multirecord", "shuffled_records", "big_indels", "10k_95"])
+def test_deltas_drive_the_reference_m_translate(oracle, deltas, tmp_path, name):
+    if not os.path.exists(M_TRANSLATE):
+        pytest.skip("oracle/_ref/m_translate not built (no /root/reference here)")
+    ref, qry, d = deltas[name]
+    d = oracle.delta_filter(d, 1)                   # what reaches the merge nodes is the filtered delta
+    # identity profiles: the translation must give back every alignment, coordinates and deltas unchanged
+    got = alignments(run_m_translate(tmp_path, d, ref, qry))
+    assert [(a[1][:4], a[2]) for a in got] == [(a[1][:4], a[2]) for a in alignments(d)]
+    # the reference sequence cut into two profiles: alignments are split at the cut, nothing is lost
+    cut = 4_000
+    got2 = alignments(run_m_translate(tmp_path, d, ref, qry, split_ref_at=cut))
+    assert len(got2) >= len(got)
+    assert sum(a[1][1] - a[1][0] + 1 for a in got2) == sum(a[1][1] - a[1][0] + 1 for a in got)
