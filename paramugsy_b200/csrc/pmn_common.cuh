@@ -37,6 +37,9 @@ void pmn_count_alloc(size_t bytes = 0, size_t had = 0);       // counts cudaMall
 // default memory pool, whose release threshold pmn_ctx_create lifts): unlike cudaMalloc / cudaFree
 // it does not serialise the device, so a worker that grows a buffer does not stall the others.
 extern thread_local cudaStream_t pmn_tls_stream;
+// callers count three launches per scan; the one-launch path for short arrays notes the difference here and the
+// API entry points subtract it from the context's launch counter (bench.py's gpu_launches is a count, not an estimate)
+extern thread_local long pmn_tls_launches_saved;
 
 // ---- a grow-only device buffer: no allocation at steady state --------------------------------
 struct DevBuf {

@@ -99,11 +99,47 @@ __global__ void __launch_bounds__(PMN_SCAN_THREADS) pmn_scan_down(const T *__res
     }
 }
 
+// short arrays (most scans of a pair: a few hundred clusters, a few thousand tiles, 10^5 matches): one block walks the
+// array with a running carry — one launch instead of three; with several pairs in flight per GPU the stages are chains of
+// small kernels whose cost is the launch, not the work
+#define PMN_SCAN_SMALL_ITEMS 8
+#define PMN_SCAN_SMALL_MAX (1024 * PMN_SCAN_SMALL_ITEMS)   /* one pass of the block: longer arrays are faster on three wide kernels */
+template <class T, class Op, bool INCLUSIVE>
+__global__ void __launch_bounds__(1024) pmn_scan_small(const T *__restrict__ in, T *__restrict__ out, int64_t n)
+{
+    __shared__ T sm[32]; __shared__ T carry_s;
+    Op op;
+    if (threadIdx.x == 0) carry_s = Op::identity();
+    __syncthreads();
+    for (int64_t cbase = 0; cbase < n; cbase += 1024 * PMN_SCAN_SMALL_ITEMS) {
+        const int64_t base = cbase + (int64_t)threadIdx.x * PMN_SCAN_SMALL_ITEMS;
+        T loc[PMN_SCAN_SMALL_ITEMS]; T acc = Op::identity();
+#pragma unroll
+        for (int k = 0; k < PMN_SCAN_SMALL_ITEMS; k++) { loc[k] = base + k < n ? in[base + k] : Op::identity(); acc = op(acc, loc[k]); }
+        const T inc = pmn_block_scan_incl(acc, op, sm);
+        T prev = __shfl_up_sync(0xffffffffu, inc, 1);
+        if ((threadIdx.x & 31) == 0) prev = threadIdx.x ? sm[(threadIdx.x >> 5) - 1] : Op::identity();
+        const T carry = carry_s;
+        T run = threadIdx.x ? op(carry, prev) : carry;
+#pragma unroll
+        for (int k = 0; k < PMN_SCAN_SMALL_ITEMS; k++) {
+            if (base + k < n) {
+                if (INCLUSIVE) { run = op(run, loc[k]); out[base + k] = run; }
+                else { out[base + k] = run; run = op(run, loc[k]); }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = op(carry, inc);
+        __syncthreads();
+    }
+}
+
 // scratch must hold ceil(n / PMN_SCAN_TILE) + 1 elements of T.  in == out is allowed.
 template <class T, class Op, bool INCLUSIVE>
 static inline void pmn_scan(const T *in, T *out, int64_t n, T *scratch, cudaStream_t st)
 {
     if (n <= 0) return;
+    if (n <= PMN_SCAN_SMALL_MAX) { pmn_scan_small<T, Op, INCLUSIVE><<<1, 1024, 0, st>>>(in, out, n); pmn_tls_launches_saved += 2; return; }
     int64_t tiles = (n + PMN_SCAN_TILE - 1) / PMN_SCAN_TILE;
     pmn_scan_reduce<T, Op><<<(unsigned)tiles, PMN_SCAN_THREADS, 0, st>>>(in, scratch, n);
     pmn_scan_spine<T, Op><<<1, 1024, 0, st>>>(scratch, tiles);

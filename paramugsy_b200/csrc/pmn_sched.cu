@@ -131,6 +131,11 @@ static int sched_run(pmn_sched *s, int ng, const char *const *fasta, const size_
     const int MAX_LIVE_INDEXES = 4;
     int live_indexes = 0;                      // guarded by s->bmu
     std::atomic<int> failed{0};                // some worker gave up: nobody may keep waiting for an index slot
+    std::vector<int> first_refs;               // the first distinct references in processing order that have no index yet
+    for (int k = 0; k < np && (int)first_refs.size() < MAX_LIVE_INDEXES; k++) {
+        const int r = ref[order[(size_t)k]];
+        if (idx[(size_t)r].state == ST_NONE && std::find(first_refs.begin(), first_refs.end(), r) == first_refs.end()) first_refs.push_back(r);
+    }
     // get a shared object: build it if nobody has, wait if somebody is
     auto acquire = [&](std::vector<Slot> &v, int g, auto &&build) -> void * {
         std::unique_lock<std::mutex> lk(s->mu);
@@ -161,14 +166,8 @@ static int sched_run(pmn_sched *s, int ng, const char *const *fasta, const size_
         // genomes given as FASTA text: the workers pack them side by side first (H2D + parse + 2-bit pack per genome),
         // instead of every worker waiting for the reference of the first pairs and then packing its query alone
         if (!resident) for (int g = w; g < ng; g += W_active) if (seqs[(size_t)g].users > 0 && !pack(g)) return;
-        for (;;) {
-            { std::lock_guard<std::mutex> lk(s->mu); if (s->err_code) return; }
-            const int k = next.fetch_add(1);
-            if (k >= np) return;
-            const int p = order[(size_t)k], r = ref[p], q = qry[p];
-            pmn_seq *rs = (pmn_seq *)pack(r); if (!rs) return;
-            pmn_seq *qs = (pmn_seq *)pack(q); if (!qs) return;
-            pmn_index *ix = (pmn_index *)acquire(idx, r, [&]() -> void * {
+        auto get_index = [&](int r, pmn_seq *rs) {
+            return (pmn_index *)acquire(idx, r, [&]() -> void * {
                 // at most MAX_LIVE_INDEXES indexes built by this run are alive at a time: pairs are taken in reference order, so the
                 // holders of the oldest ones finish without needing another; bounds the memory (8.25 B/base each) and keeps the
                 // number of index images the pool ever holds fixed, i.e. no allocation in later batches
@@ -176,6 +175,18 @@ static int sched_run(pmn_sched *s, int ng, const char *const *fasta, const size_
                 BorrowedScratch b(s, c); pmn_index *x = nullptr;
                 if (pmn_index_build(c, rs, &x)) { std::lock_guard<std::mutex> lk(s->bmu); live_indexes--; s->bcv.notify_all(); return nullptr; }
                 return (void *)x; });
+        };
+        // the first MAX_LIVE_INDEXES references of the batch are indexed side by side by the first workers, so that the batch
+        // does not open with every worker waiting for one build (the gaps of one build are filled by the others)
+        if (w < (int)first_refs.size()) { const int r = first_refs[(size_t)w]; pmn_seq *rs = (pmn_seq *)pack(r); if (!rs || !get_index(r, rs)) return; }
+        for (;;) {
+            { std::lock_guard<std::mutex> lk(s->mu); if (s->err_code) return; }
+            const int k = next.fetch_add(1);
+            if (k >= np) return;
+            const int p = order[(size_t)k], r = ref[p], q = qry[p];
+            pmn_seq *rs = (pmn_seq *)pack(r); if (!rs) return;
+            pmn_seq *qs = (pmn_seq *)pack(q); if (!qs) return;
+            pmn_index *ix = get_index(r, rs);
             if (!ix) return;
             pmn_result *res = nullptr;
             {
