@@ -158,7 +158,7 @@ struct CfgBig {
 };
 template <class Cfg> __device__ __forceinline__ int32_t *eng_warp_smem()
 {
-    extern __shared__ int32_t smem_all[];
+    extern __shared__ __align__(16) int32_t smem_all[];
     return smem_all + (threadIdx.x >> 5) * (Cfg::WARP_BYTES / 4);
 }
 
@@ -605,12 +605,37 @@ __device__ __noinline__ int align_engine(const Eng &E, int64_t Abase, int64_t As
         int32_t *rev_s = ring + Cfg::REV_OFF;
         const int n_sm = c.tb_sm_n;
         int nrev = 0;
-        if (lane == 0) {
+        {
+            // The walk back is a chain of dependent reads.  Rows that left shared memory would cost two dependent global loads
+            // per step (row pointer, then the byte) — more than the DP itself on long alignments.  So the warp stages 32
+            // anti-diagonals at a time: lane l fetches row pointer and first column of diagonal top-l (one coalesced load each)
+            // and the 48 bytes of that row the path can touch (after l steps it is at most l columns left of where it is now)
+            // into the score ring, which is dead by now; all lanes then walk in lockstep on shared memory, lane 0 emits.
+            uint8_t *seg = (uint8_t *)ring;                     // rows 0-1 of the ring: 64 bytes per lane
+            int32_t *segcol = ring + 2 * Cfg::RW;               // row 2: column of byte 0 of each lane's segment
+            int win_top = -1, win_bot = 0;
             auto cell = [&](int cd, int cj) -> unsigned {
                 if (cd < n_sm) { const int m0 = meta[cd]; return rows[(m0 >> 16) + cj - (int)(short)(m0 & 0xffff)]; }
-                return tboff[cd][cj - tblo[cd]];
+                if (cd > win_top || cd < win_bot) {
+                    __syncwarp();
+                    const int dd = cd - lane;
+                    if (dd >= n_sm && dd >= 0) {
+                        const uint8_t *p = tboff[dd]; const int lo = tblo[dd];
+                        int o = cj - lane - lo; if (o < 0) o = 0;
+                        const uint8_t *ab = (const uint8_t *)((uintptr_t)(p + o) & ~(uintptr_t)15);
+                        const uint4 *src = (const uint4 *)ab;
+                        const uint4 v0 = src[0], v1 = src[1], v2 = src[2];
+                        uint4 *dst = (uint4 *)(seg + lane * 64);
+                        dst[0] = v0; dst[1] = v1; dst[2] = v2;
+                        segcol[lane] = lo + (int)(ab - p);
+                    }
+                    win_top = cd; win_bot = cd - 31 > n_sm ? cd - 31 : n_sm; if (win_bot < 0) win_bot = 0;
+                    __syncwarp();
+                }
+                const int L = win_top - cd;
+                return seg[L * 64 + (cj - segcol[L])];
             };
-            auto emit = [&](int v) { if (nrev < Cfg::REV_N) rev_s[nrev] = v; else rev[nrev] = v; nrev++; };
+            auto emit = [&](int v) { if (lane == 0) { if (nrev < Cfg::REV_N) rev_s[nrev] = v; else rev[nrev] = v; } nrev++; };
             int cd = fd, cj = fj;
             int st = cell(cd, cj) >> 6;
             int pending = 0, run = 0;
@@ -1766,8 +1791,8 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     const size_t npad = ((size_t)np + 63) / 64 * 64;
     const size_t l_bytes = npad * 3 + 8 * (size_t)nS + 64 + sizeof(ExBack) * npad;      // fused, anyfail, entered, syn_nal (2 x nS), back
     if (S.ex_i.ensure(sizeof(ExJob) * (size_t)nm) || S.ex_j.ensure(sizeof(ExAlign) * ncap_al) || S.ex_k.ensure(sizeof(ExNode) * ncap_nodes) ||
-        S.ex_pool.ensure(4 * pool_cap) || S.ex_arena.ensure(arena_cap) || S.ex_scores.ensure(4 * (size_t)EX_ROWS * EX_WCAP * (size_t)nslots) ||
-        S.ex_tb.ensure((size_t)EX_TBW * (size_t)nslots_tb) || S.ex_counters.ensure(128) || S.ex_l.ensure(l_bytes) ||
+        S.ex_pool.ensure(4 * pool_cap) || S.ex_arena.ensure(arena_cap + 4096) || S.ex_scores.ensure(4 * (size_t)EX_ROWS * EX_WCAP * (size_t)nslots) ||
+        S.ex_tb.ensure((size_t)EX_TBW * (size_t)nslots_tb + 4096) || S.ex_counters.ensure(128) || S.ex_l.ensure(l_bytes) ||
         S.ex_tbidx.ensure(8 * 3 * (size_t)(nm + 1)) || S.ex_a.ensure(8 * h.size() + 0) || S.cl_l.ensure(sizeof(ExCSum) * (size_t)np)) return -3;
     PMN_CUDA_OK(cudaMemsetAsync(S.ex_i.p, 0, sizeof(ExJob) * (size_t)nm, st));
     PMN_CUDA_OK(cudaMemsetAsync(S.ex_counters.p, 0, 128, st));

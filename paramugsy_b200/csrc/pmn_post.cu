@@ -384,8 +384,11 @@ extern "C" int pmn_delta2maf(pmn_ctx *c, const char *delta, size_t n, const pmn_
         const long long chunks = (gcol + MAF_CHUNK - 1) / MAF_CHUNK;
         k_maf_expand<<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(dal, (int)na, gcol, dd, sc, sa, sb, ref->residues.as<uint8_t>(), qry->residues.as<uint8_t>(), dout);
         c->launches += 11;
-        PMN_D2H(c, res, dout, total);
+        // through the context's pinned staging: a device -> pageable copy of 10 MB would crawl through the driver's bounce buffer
+        if (S.ensure_pinned(total)) { free(res); return -3; }
+        PMN_D2H(c, S.pinned, dout, total);
         cudaError_t e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess) memcpy(res, S.pinned, total);
         if (e == cudaSuccess) e = cudaGetLastError();
         if (e != cudaSuccess) { free(res); return pmn_set_error(-2, "pmn_delta2maf: %s", cudaGetErrorString(e)); }
     }
