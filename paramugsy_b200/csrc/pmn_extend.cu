@@ -912,7 +912,7 @@ __device__ __forceinline__ bool wave1_run(const Eng &E, const ExShared &X, const
 
 // Wave 1, big kernel: the cluster-end extensions (break-length searches, bands up to hundreds of cells)
 // and what the small kernel handed over.
-__global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32, 4) k_ex_wave1_big(ExShared X, int pass)
+__global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32, 3) k_ex_wave1_big(ExShared X, int pass)
 {
     Eng E = make_eng(X, nullptr); E.kid = 1;
     const int lane = E.lane;
@@ -1176,7 +1176,7 @@ __global__ void __launch_bounds__(256) k_ex_csum(ExShared X, ExCSum *__restrict_
 // for (towards the sequence starts, OPTIMAL); the stitcher takes the result when its own window, bounded by the
 // target alignment, contains every cell this search evaluated (ext_i, ext_j) -- then the two runs are the same
 // cell for cell -- and runs the engine itself otherwise.
-__global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32, 4) k_ex_wave2(ExShared X)
+__global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32, 3) k_ex_wave2(ExShared X)
 {
     Eng E = make_eng(X, nullptr); E.kid = 3;
     const int lane = E.lane;
