@@ -3,7 +3,7 @@ import csv, json, os, shutil, subprocess, sys
 R = sys.argv[1] if len(sys.argv) > 1 else "r01"
 G, P = "gpurun_out", "profiles"
 os.makedirs(P, exist_ok=True)
-for src, dst in (("bench.json", f"{R}_bench_c2_final.json"), ("bench_ref.json", f"{R}_bench_c2_reference_arm.json"), ("c4.json", f"{R}_c4_100mbp_pair.json"), ("c5.json", f"{R}_c5_divergence_sweep.json")):
+for src, dst in (("bench.json", f"{R}_bench_c2_final.json"), ("bench_ref.json", f"{R}_bench_c2_reference_arm.json"), ("c4.json", f"{R}_c4_100mbp_pair.json"), ("c5.json", f"{R}_c5_divergence_sweep.json"), ("c3.json", f"{R}_c3_57x2mbp_job_tree.json")):
     if os.path.exists(os.path.join(G, src)):
         d = json.load(open(os.path.join(G, src)))
         json.dump(d, open(os.path.join(P, dst), "w"), indent=1)
