@@ -14,6 +14,7 @@
 // The host parses the .delta text (it is the interface of the reference, a few hundred kB); the chain DP
 // and the expansion of the edit scripts into the two gapped rows of every block run on the device.
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <map>
 #include <string>
@@ -324,7 +325,11 @@ extern "C" int pmn_delta2maf(pmn_ctx *c, const char *delta, size_t n, const pmn_
 {
     if (!c || !delta || !ref || !qry || !out || !nout) return pmn_set_error(PMN_E_ARG, "pmn_delta2maf: bad argument");
     *out = nullptr; *nout = 0;
+    static const bool timing = getenv("PMN_POST_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_0 = now();
     PDelta d; { int rc = parse_delta(delta, n, d); if (rc) return rc; }
+    const double t_parse = now();
     PMN_CUDA_OK(cudaSetDevice(c->device));
     pmn_tls_stream = c->stream;
     cudaStream_t st = c->stream;
@@ -366,6 +371,7 @@ extern "C" int pmn_delta2maf(pmn_ctx *c, const char *delta, size_t n, const pmn_
     const size_t total = at;
     char *res = (char *)malloc(total + 1);
     if (!res) return pmn_set_error(PMN_E_NOMEM, "pmn_delta2maf: out of memory (%zu bytes)", total);
+    const double t_layout = now(); double t_dev = t_layout, t_copy = t_layout;
     if (na && gcol > 0) {
         Scratch &S = *c->scratch;
         const int64_t nd = (int64_t)d.dl.size();
@@ -388,7 +394,9 @@ extern "C" int pmn_delta2maf(pmn_ctx *c, const char *delta, size_t n, const pmn_
         if (S.ensure_pinned(total)) { free(res); return -3; }
         PMN_D2H(c, S.pinned, dout, total);
         cudaError_t e = cudaStreamSynchronize(st);
+        t_dev = now();
         if (e == cudaSuccess) memcpy(res, S.pinned, total);
+        t_copy = now();
         if (e == cudaSuccess) e = cudaGetLastError();
         if (e != cudaSuccess) { free(res); return pmn_set_error(-2, "pmn_delta2maf: %s", cudaGetErrorString(e)); }
     }
@@ -402,5 +410,7 @@ extern "C" int pmn_delta2maf(pmn_ctx *c, const char *delta, size_t n, const pmn_
     }
     res[total] = 0;
     *out = res; *nout = total;
+    if (timing) fprintf(stderr, "[pmn] delta2maf: parse %.2f ms, layout %.2f ms, device (H2D, kernels, D2H) %.2f ms, copy %.2f ms, headers %.2f ms; %zu bytes\n",
+                        t_parse - t_0, t_layout - t_parse, t_dev - t_layout, t_copy - t_dev, now() - t_copy, total);
     return 0;
 }
