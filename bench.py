@@ -28,7 +28,15 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries the one JSON line and nothing else
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries the one JSON line and nothing else: libraries that print to file descriptor 1 (NCCL's version banner
+# is a plain printf) are sent to stderr, the JSON line goes to a private copy of the original stdout
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(obj):
+    print(json.dumps(obj), file=_REAL_STDOUT, flush=True)
 
 from paramugsy_b200 import synth  # noqa: E402
 
@@ -297,7 +305,7 @@ def run_gpu(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(args, genomes, fastas, pairs, budget_s=args.cpu_budget)
-        print(json.dumps(out))
+        emit(out)
     for s in resident.values():
         s.close()
     sched.close()
@@ -380,7 +388,7 @@ def run_reference(args):
                             "sample": f"each step: {nproc} pairs truncated to {sample_bp} bp, one process per pair; scaled linearly to full-size pairs"},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "note": "the reference's own CPU path is MUMmer 3.20 (not vendored, absent here); this times the in-repo CPU restatement"}
-    print(json.dumps(out))
+    emit(out)
 
 
 def main():

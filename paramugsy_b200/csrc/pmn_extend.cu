@@ -220,8 +220,11 @@ __device__ __forceinline__ void eng_fill_qry(const PackedView &Q, EngCtx &c, uin
 // the two live anti-diagonals in the shared-memory ring (plain scores; rows 0-2 = diagonal d-2,
 // rows 4-6 = diagonal d-1).
 template <int K, class Cfg>
-__device__ __forceinline__ int eng_run_reg(const Eng &E, EngCtx &c, const PackedView &Q, uint8_t **tboff, int32_t *tblo)
+__device__ __forceinline__ int eng_run_reg(const Eng &E, EngCtx &cref, const PackedView &Q, uint8_t **tboff, int32_t *tblo)
 {
+    // the caller's context lives in local memory (it is handed to the wide fallback by value); the loop works on a copy
+    // whose address never leaves this function, so that every field stays in a register
+    EngCtx c = cref;
     constexpr int LOGK = K == 1 ? 0 : (K == 2 ? 1 : (K == 4 ? 2 : 3));
     constexpr int W = 32 * K;
     constexpr unsigned QMASK = K == 8 ? 0xffffffffu : ((1u << (4 * K)) - 1u);
@@ -381,6 +384,7 @@ __device__ __forceinline__ int eng_run_reg(const Eng &E, EngCtx &c, const Packed
         }
         __syncwarp();
     }
+    cref = c;
     return rc;
 }
 
