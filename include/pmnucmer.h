@@ -53,6 +53,9 @@ typedef struct pmn_opts {
     int32_t do_optimize;   /* --[no]optimize; only 1 is implemented */
     int32_t do_simplify;   /* --[no]simplify */
     int32_t keep_stages;   /* 1: keep anchors / clusters / alignments in the result (tests) */
+    int32_t post;          /* 0: .delta only.  1 / 2: the pair also goes through the two post-steps of lib/nucmer/mugsy_nucmer.ml
+                            * in the same call, without their text round trip: `delta-filter -1` (1) or `-m` (2, -colinear, :103)
+                            * and `delta2maf` of the filtered delta (:118-131); see pmn_result_filtered / pmn_result_maf */
 } pmn_opts;
 
 typedef struct pmn_stats {
@@ -68,6 +71,7 @@ typedef struct pmn_stats {
     int64_t kernel_launches;     /* kernels launched for this pair                     */
     int64_t wave1_cells;         /* DP cells evaluated inside k_ex_wave1               */
     float   wall_ms_index, wall_ms_align, wall_ms_text;   /* host wall clock: index build, pmn_align, .delta formatting */
+    float   wall_ms_post;        /* host wall clock of the two post-steps (pmn_opts.post) */
 } pmn_stats;
 
 void pmn_default_opts(pmn_opts *o);
@@ -123,6 +127,8 @@ int  pmn_seed_part(pmn_ctx *c, const pmn_index *ix, const pmn_seq *qry, const pm
 int  pmn_align_anchors(pmn_ctx *c, const pmn_index *ix, const pmn_seq *qry, const pmn_opts *o, const void *dev_anchors, int64_t n_anchors,
                        const char *ref_path, const char *qry_path, pmn_result **out);
 const char *pmn_result_delta(const pmn_result *r, size_t *len);
+const char *pmn_result_filtered(const pmn_result *r, size_t *len);   /* pmn_opts.post != 0: the filtered .delta */
+const char *pmn_result_maf(const pmn_result *r, size_t *len);        /* pmn_opts.post != 0: its MAF */
 void pmn_result_stats(const pmn_result *r, pmn_stats *out);
 void pmn_result_free(pmn_result *r);
 

@@ -49,8 +49,49 @@ extern "C" void pmn_default_opts(pmn_opts *o)
 {
     o->minmatch = PMN_DEF_MINMATCH; o->mincluster = PMN_DEF_MINCLUSTER; o->maxgap = PMN_DEF_MAXGAP;
     o->diagdiff = PMN_DEF_DIAGDIFF; o->diagfactor = PMN_DEF_DIAGFACTOR; o->breaklen = PMN_DEF_BREAKLEN;
-    o->do_forward = 1; o->do_reverse = 1; o->do_extend = 1; o->do_optimize = 1; o->do_simplify = 1; o->keep_stages = 0;
+    o->do_forward = 1; o->do_reverse = 1; o->do_extend = 1; o->do_optimize = 1; o->do_simplify = 1; o->keep_stages = 0; o->post = 0;
 }
+
+// ------------------------------------------------------------------------------------ pinned host buffers for large texts
+
+namespace {
+struct PinnedPool {
+    std::mutex mu;
+    std::multimap<size_t, void *> idle;         // capacity -> buffer
+    std::map<void *, size_t> all;               // every buffer the pool ever handed out -> capacity
+};
+PinnedPool &pinned_pool() { static PinnedPool *p = new PinnedPool(); return *p; }      // never destroyed: outlives the CUDA runtime's own teardown
+}  // namespace
+
+char *pmn_pinned_get(size_t bytes)
+{
+    size_t cap = (size_t)1 << 20;
+    while (cap < bytes + 1) cap <<= 1;
+    PinnedPool &P = pinned_pool();
+    {
+        std::lock_guard<std::mutex> lk(P.mu);
+        auto it = P.idle.find(cap);
+        if (it != P.idle.end()) { void *p = it->second; P.idle.erase(it); return (char *)p; }
+    }
+    void *p = nullptr;
+    if (cudaMallocHost(&p, cap) != cudaSuccess) { cudaGetLastError(); pmn_set_error(PMN_E_NOMEM, "cudaMallocHost(%zu) failed", cap); return nullptr; }
+    std::lock_guard<std::mutex> lk(P.mu);
+    P.all[p] = cap;
+    return (char *)p;
+}
+
+bool pmn_pinned_put(void *p)
+{
+    if (!p) return true;
+    PinnedPool &P = pinned_pool();
+    std::lock_guard<std::mutex> lk(P.mu);
+    auto it = P.all.find(p);
+    if (it == P.all.end()) return false;
+    P.idle.emplace(it->second, p);
+    return true;
+}
+
+pmn_result::~pmn_result() { pmn_pinned_put(maf); }
 
 // ------------------------------------------------------------------------------------ context
 
@@ -406,6 +447,7 @@ static int check_opts(const pmn_opts *o_in, pmn_opts &o)
     if (!o.do_optimize) return pmn_set_error(PMN_E_ARG, "--nooptimize is not supported");
     if (o.minmatch < 1 || o.maxgap < 0 || o.breaklen < 1 || o.mincluster < 0 || o.diagdiff < 0 || o.diagfactor < 0)
         return pmn_set_error(PMN_E_ARG, "pmn_align: option out of range");
+    if (o.post < 0 || o.post > 2) return pmn_set_error(PMN_E_ARG, "pmn_align: post must be 0, 1 or 2");
     return 0;
 }
 
@@ -461,8 +503,15 @@ static int align_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *qry, const
     const double t1 = now_ms();
     write_delta_text(ix->seq, qry, ref_path ? ref_path : "ref", qry_path ? qry_path : "qry", r.get());
     c->launches -= pmn_tls_launches_saved; pmn_tls_launches_saved = 0;
-    r->stats.kernel_launches = c->launches - launches0;
     r->stats.wall_ms_text = (float)(now_ms() - t1);
+    if (o.post) {
+        const double t2 = now_ms();
+        int prc = pmn_post_impl(c, ix->seq, qry, ref_path ? ref_path : "ref", qry_path ? qry_path : "qry", o.post, r.get());
+        if (prc) return prc;
+        c->launches -= pmn_tls_launches_saved; pmn_tls_launches_saved = 0;
+        r->stats.wall_ms_post = (float)(now_ms() - t2);
+    }
+    r->stats.kernel_launches = c->launches - launches0;
     r->stats.wall_ms_align = (float)(now_ms() - t0);
     r->stats.wall_ms_index = ix->wall_ms_build;
     *out = r.release();
@@ -498,6 +547,8 @@ extern "C" int pmn_align_anchors(pmn_ctx *c, const pmn_index *ix, const pmn_seq 
 }
 
 extern "C" const char *pmn_result_delta(const pmn_result *r, size_t *len) { if (len) *len = r ? r->delta.size() : 0; return r ? r->delta.c_str() : ""; }
+extern "C" const char *pmn_result_filtered(const pmn_result *r, size_t *len) { if (len) *len = r ? r->filtered.size() : 0; return r ? r->filtered.data() : nullptr; }
+extern "C" const char *pmn_result_maf(const pmn_result *r, size_t *len) { if (len) *len = r ? r->maf_len : 0; return r ? r->maf : nullptr; }
 extern "C" void pmn_result_stats(const pmn_result *r, pmn_stats *out) { if (r && out) *out = r->stats; }
 extern "C" void pmn_result_free(pmn_result *r) { delete r; }
 

@@ -43,6 +43,9 @@ struct StageTimes { float pack = 0, index = 0, seed = 0, cluster = 0, extend = 0
 
 struct pmn_result {
     std::string delta;
+    std::string filtered;                       // pmn_opts.post: `delta-filter` of delta
+    char *maf = nullptr; size_t maf_len = 0;    // ... and `delta2maf` of that, in a buffer of the pinned-host pool (the device writes it directly)
+    ~pmn_result();
     pmn_stats stats{};
     // stage dumps kept for parity tests
     std::vector<int32_t> anchors;             // n x 4
@@ -94,6 +97,11 @@ struct PmnIndexHeader { uint64_t magic; int64_t n; int32_t K, rounds; };
 int pmn_seed_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_opts *o, int64_t *n_anchors, int part = 0, int nparts = 1);
 int pmn_cluster_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_opts *o, int64_t n_anchors);
 int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_opts *o, pmn_result *res);
+// MAF texts are some 10 MB per pair: they are copied from the device straight into pinned host buffers that are recycled
+// (pmn_free_text / pmn_result_free hand them back), instead of a bounce buffer plus a 10 MB memcpy per pair
+char *pmn_pinned_get(size_t bytes);
+bool pmn_pinned_put(void *p);          // false: p is not a buffer of the pool
+int pmn_post_impl(pmn_ctx *c, const pmn_seq *ref, const pmn_seq *qry, const char *ref_path, const char *qry_path, int mode, pmn_result *r);
 int pmn_read_file(const char *path, std::string &out);
 int pmn_write_file_atomic(const char *path, const char *data, size_t len);
 Scratch *pmn_scratch_new();

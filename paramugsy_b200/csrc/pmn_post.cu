@@ -142,16 +142,15 @@ __global__ void __launch_bounds__(128) k_filter_lis(const long long *__restrict_
     if (lane == 0) for (int k = besti; k >= 0; k = from[k]) flags[item[k]] = 1;
 }
 
-extern "C" int pmn_delta_filter(pmn_ctx *c, const char *delta, size_t n, int mode, double maxolap, char **out, size_t *nout)
+// which alignments of d survive `delta-filter -1` (mode 1) / `-m` (mode 2)
+static int filter_keep(pmn_ctx *c, const PDelta &d, int mode, double maxolap, std::vector<uint8_t> &keep)
 {
-    if (!c || !delta || !out || !nout || (mode != 1 && mode != 2)) return pmn_set_error(PMN_E_ARG, "pmn_delta_filter: bad argument");
-    *out = nullptr; *nout = 0;
-    PDelta d; { int rc = parse_delta(delta, n, d); if (rc) return rc; }
     PMN_CUDA_OK(cudaSetDevice(c->device));
     pmn_tls_stream = c->stream;
     cudaStream_t st = c->stream;
     const size_t na = d.al.size();
     std::vector<uint8_t> flagR(na, 0), flagQ(na, 0);
+    keep.assign(na, 0);
     if (na) {
         // groups: reference sequences, then query sequences, each in order of first appearance
         std::map<std::string, int> rix, qix;
@@ -206,14 +205,20 @@ extern "C" int pmn_delta_filter(pmn_ctx *c, const char *delta, size_t n, int mod
         PMN_CUDA_OK(cudaGetLastError());
         for (size_t k = 0; k < na; k++) { flagR[k] = fl[k]; flagQ[k] = fl[na + k]; }
     }
-    // text out: the surviving alignments in input order, '>' lines only where something survives
-    std::string t;
-    t.reserve(n + 64);
+    for (size_t k = 0; k < na; k++) keep[k] = mode == 1 ? (flagR[k] && flagQ[k]) : (flagR[k] || flagQ[k]);
+    return 0;
+}
+
+// .delta text of the alignments with keep[k] != 0 (all when keep is empty), in input order, '>' lines only where one follows
+static void emit_delta(const PDelta &d, const std::vector<uint8_t> &keep, std::string &t)
+{
+    const size_t na = d.al.size();
+    t.clear();
+    t.reserve(d.line1.size() + d.line2.size() + 64 + na * 120 + d.dl.size() * 8);
     t += d.line1; t += '\n'; t += d.line2; t += '\n';
     int last_block = -1; char buf[256];
     for (size_t k = 0; k < na; k++) {
-        const bool keep = mode == 1 ? (flagR[k] && flagQ[k]) : (flagR[k] || flagQ[k]);
-        if (!keep) continue;
+        if (!keep.empty() && !keep[k]) continue;
         const PAlign &a = d.al[k];
         if (a.block != last_block) {
             const PBlock &b = d.blk[(size_t)a.block];
@@ -225,17 +230,37 @@ extern "C" int pmn_delta_filter(pmn_ctx *c, const char *delta, size_t n, int mod
         char *p = buf;
         for (int i = 0; i < 7; i++) { p = put_ll(p, v[i]); *p++ = i < 6 ? ' ' : '\n'; }
         t.append(buf, p);
-        for (size_t u = 0; u < a.dcnt; u++) { p = put_ll(buf, d.dl[a.doff + u]); *p++ = '\n'; t.append(buf, p); }
+        const size_t before = t.size();
+        t.resize(before + a.dcnt * 12);
+        char *q = &t[before];
+        for (size_t u = 0; u < a.dcnt; u++) { q = put_ll(q, d.dl[a.doff + u]); *q++ = '\n'; }
+        t.resize((size_t)(q - &t[0]));
         t += "0\n";
     }
+}
+
+static int text_out(const std::string &t, char **out, size_t *nout)
+{
     char *r = (char *)malloc(t.size() + 1);
-    if (!r) return pmn_set_error(PMN_E_NOMEM, "pmn_delta_filter: out of memory");
+    if (!r) return pmn_set_error(PMN_E_NOMEM, "out of memory (%zu bytes)", t.size());
     memcpy(r, t.data(), t.size()); r[t.size()] = 0;
     *out = r; *nout = t.size();
     return 0;
 }
 
-extern "C" void pmn_free_text(char *p) { free(p); }
+extern "C" int pmn_delta_filter(pmn_ctx *c, const char *delta, size_t n, int mode, double maxolap, char **out, size_t *nout)
+{
+    if (!c || !delta || !out || !nout || (mode != 1 && mode != 2)) return pmn_set_error(PMN_E_ARG, "pmn_delta_filter: bad argument");
+    *out = nullptr; *nout = 0;
+    PDelta d; { int rc = parse_delta(delta, n, d); if (rc) return rc; }
+    std::vector<uint8_t> keep;
+    { int rc = filter_keep(c, d, mode, maxolap, keep); if (rc) return rc; }
+    std::string t;
+    emit_delta(d, keep, t);
+    return text_out(t, out, nout);
+}
+
+extern "C" void pmn_free_text(char *p) { if (p && !pmn_pinned_put(p)) free(p); }
 
 // ------------------------------------------------------------------------------------ delta2maf
 
@@ -320,15 +345,17 @@ __global__ void __launch_bounds__(256) k_maf_expand(const MafAlign *__restrict__
     }
 }
 
-// delta2maf on .delta text; `ref` / `qry` are the packed genomes the delta was computed from (their residues stay in HBM)
-extern "C" int pmn_delta2maf(pmn_ctx *c, const char *delta, size_t n, const pmn_seq *ref, const pmn_seq *qry, char **out, size_t *nout)
+// MAF text of the alignments of d with keep[k] != 0 (all when keep is empty); `ref` / `qry` are the packed genomes the
+// delta was computed from (their residues stay in HBM).  *text comes from the pinned-host pool (pmn_pinned_put / pmn_free_text).
+static int maf_of(pmn_ctx *c, const PDelta &d_all, const std::vector<uint8_t> &keep, const pmn_seq *ref, const pmn_seq *qry, char **text, size_t *text_len)
 {
-    if (!c || !delta || !ref || !qry || !out || !nout) return pmn_set_error(PMN_E_ARG, "pmn_delta2maf: bad argument");
-    *out = nullptr; *nout = 0;
     static const bool timing = getenv("PMN_POST_TIMING") != nullptr;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_0 = now();
-    PDelta d; { int rc = parse_delta(delta, n, d); if (rc) return rc; }
+    // the surviving alignments (their deltas stay where they are in d_all.dl)
+    struct View { const std::vector<PBlock> &blk; std::vector<PAlign> al; const std::vector<int32_t> &dl; };
+    View d{ d_all.blk, {}, d_all.dl };
+    if (keep.empty()) d.al = d_all.al; else for (size_t k = 0; k < d_all.al.size(); k++) if (keep[k]) d.al.push_back(d_all.al[k]);
     const double t_parse = now();
     PMN_CUDA_OK(cudaSetDevice(c->device));
     pmn_tls_stream = c->stream;
@@ -369,14 +396,15 @@ extern "C" int pmn_delta2maf(pmn_ctx *c, const char *delta, size_t n, const pmn_
         gcol += cols;
     }
     const size_t total = at;
-    char *res = (char *)malloc(total + 1);
-    if (!res) return pmn_set_error(PMN_E_NOMEM, "pmn_delta2maf: out of memory (%zu bytes)", total);
+    char *res = pmn_pinned_get(total);
+    if (!res) return PMN_E_NOMEM;
+    struct Guard { char *p; ~Guard() { if (p) pmn_pinned_put(p); } } guard{ res };
     const double t_layout = now(); double t_dev = t_layout, t_copy = t_layout;
     if (na && gcol > 0) {
         Scratch &S = *c->scratch;
         const int64_t nd = (int64_t)d.dl.size();
         if (S.ex_d.ensure(4 * (size_t)(nd + 1) + 64) || S.ex_b.ensure(3 * 4 * (size_t)(nd + 1) + 64) || S.ex_c.ensure(3 * 4 * (size_t)(nd + 1) + 64) ||
-            S.ex_g.ensure(sizeof(MafAlign) * na + 64) || S.ex_pool.ensure(total + 64) || S.scan_tmp.ensure(8 * pmn_scan_scratch_elems(nd + 1))) { free(res); return -3; }
+            S.ex_g.ensure(sizeof(MafAlign) * na + 64) || S.ex_pool.ensure(total + 64) || S.scan_tmp.ensure(8 * pmn_scan_scratch_elems(nd + 1))) return -3;
         int32_t *dd = S.ex_d.as<int32_t>();
         uint32_t *fc = S.ex_b.as<uint32_t>(), *fa = fc + (nd + 1), *fb = fa + (nd + 1);
         uint32_t *sc = S.ex_c.as<uint32_t>(), *sa = sc + (nd + 1), *sb = sa + (nd + 1);
@@ -390,15 +418,12 @@ extern "C" int pmn_delta2maf(pmn_ctx *c, const char *delta, size_t n, const pmn_
         const long long chunks = (gcol + MAF_CHUNK - 1) / MAF_CHUNK;
         k_maf_expand<<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(dal, (int)na, gcol, dd, sc, sa, sb, ref->residues.as<uint8_t>(), qry->residues.as<uint8_t>(), dout);
         c->launches += 11;
-        // through the context's pinned staging: a device -> pageable copy of 10 MB would crawl through the driver's bounce buffer
-        if (S.ensure_pinned(total)) { free(res); return -3; }
-        PMN_D2H(c, S.pinned, dout, total);
+        PMN_D2H(c, res, dout, total);          // straight into the pinned result buffer
         cudaError_t e = cudaStreamSynchronize(st);
         t_dev = now();
-        if (e == cudaSuccess) memcpy(res, S.pinned, total);
         t_copy = now();
         if (e == cudaSuccess) e = cudaGetLastError();
-        if (e != cudaSuccess) { free(res); return pmn_set_error(-2, "pmn_delta2maf: %s", cudaGetErrorString(e)); }
+        if (e != cudaSuccess) return pmn_set_error(-2, "pmn_delta2maf: %s", cudaGetErrorString(e));
     }
     // the host fills in what is not sequence text
     memcpy(res, head, strlen(head));
@@ -409,8 +434,49 @@ extern "C" int pmn_delta2maf(pmn_ctx *c, const char *delta, size_t n, const pmn_
         res[al[k].outQ + cols] = '\n'; res[al[k].outQ + cols + 1] = '\n';
     }
     res[total] = 0;
-    *out = res; *nout = total;
-    if (timing) fprintf(stderr, "[pmn] delta2maf: parse %.2f ms, layout %.2f ms, device (H2D, kernels, D2H) %.2f ms, copy %.2f ms, headers %.2f ms; %zu bytes\n",
+    guard.p = nullptr; *text = res; *text_len = total;
+    if (timing) fprintf(stderr, "[pmn] delta2maf: select %.2f ms, layout %.2f ms, device (H2D, kernels, D2H) %.2f ms, copy %.2f ms, headers %.2f ms; %zu bytes\n",
                         t_parse - t_0, t_layout - t_parse, t_dev - t_layout, t_copy - t_dev, now() - t_copy, total);
     return 0;
+}
+
+extern "C" int pmn_delta2maf(pmn_ctx *c, const char *delta, size_t n, const pmn_seq *ref, const pmn_seq *qry, char **out, size_t *nout)
+{
+    if (!c || !delta || !ref || !qry || !out || !nout) return pmn_set_error(PMN_E_ARG, "pmn_delta2maf: bad argument");
+    *out = nullptr; *nout = 0;
+    PDelta d; { int rc = parse_delta(delta, n, d); if (rc) return rc; }
+    return maf_of(c, d, std::vector<uint8_t>(), ref, qry, out, nout);
+}
+
+// ------------------------------------------------------------------------------------ both post-steps inside pmn_align
+
+// pmn_opts.post: the alignments of a finished pair go through delta-filter and delta2maf without the text round trip of
+// the reference's three child processes (mugsy_nucmer.ml:100,104,122): the rows and deltas the extension left on the
+// host become the parsed form directly.
+int pmn_post_impl(pmn_ctx *c, const pmn_seq *ref, const pmn_seq *qry, const char *ref_path, const char *qry_path, int mode, pmn_result *r)
+{
+    PDelta d;
+    d.line1 = std::string(ref_path) + " " + qry_path; d.line2 = "NUCMER";
+    const size_t na = r->al_rows.size() / 10;
+    d.dl.assign(r->al_deltas.begin(), r->al_deltas.end());
+    int64_t prev_r = -1, prev_q = -1;
+    for (size_t k = 0; k < na; k++) {
+        const int64_t *a = &r->al_rows[k * 10];
+        if (a[0] != prev_r || a[1] != prev_q) {
+            PBlock b; b.rid = ref->ids[(size_t)a[0]]; b.qid = qry->ids[(size_t)a[1]]; b.rlen = ref->len[(size_t)a[0]]; b.qlen = qry->len[(size_t)a[1]];
+            d.blk.push_back(b); prev_r = a[0]; prev_q = a[1];
+        }
+        PAlign p; p.block = (int)d.blk.size() - 1;
+        const int64_t lenB = qry->len[(size_t)a[1]];
+        p.sR = a[3]; p.eR = a[4]; p.sQ = a[2] ? lenB - a[5] + 1 : a[5]; p.eQ = a[2] ? lenB - a[6] + 1 : a[6];
+        p.e1 = a[7]; p.e2 = a[8]; p.e3 = a[9];
+        p.doff = (size_t)r->al_doff[k]; p.dcnt = (size_t)(r->al_doff[k + 1] - r->al_doff[k]); p.neg = 0;
+        for (size_t u = 0; u < p.dcnt; u++) if (d.dl[p.doff + u] < 0) p.neg++;
+        d.al.push_back(p);
+    }
+    std::vector<uint8_t> keep;
+    int rc = filter_keep(c, d, mode, 75.0, keep);
+    if (rc) return rc;
+    emit_delta(d, keep, r->filtered);
+    return maf_of(c, d, keep, ref, qry, &r->maf, &r->maf_len);
 }

@@ -23,7 +23,7 @@ class Opts(C.Structure):
     _fields_ = [("minmatch", C.c_int32), ("mincluster", C.c_int32), ("maxgap", C.c_int32),
                 ("diagdiff", C.c_int32), ("diagfactor", C.c_double), ("breaklen", C.c_int32),
                 ("do_forward", C.c_int32), ("do_reverse", C.c_int32), ("do_extend", C.c_int32),
-                ("do_optimize", C.c_int32), ("do_simplify", C.c_int32), ("keep_stages", C.c_int32)]
+                ("do_optimize", C.c_int32), ("do_simplify", C.c_int32), ("keep_stages", C.c_int32), ("post", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -35,7 +35,7 @@ class Stats(C.Structure):
                 ("ms_extend", C.c_float), ("ms_total", C.c_float), ("ms_seed_kernel", C.c_float),
                 ("ms_wave1", C.c_float), ("ms_stitch", C.c_float), ("kernel_launches", C.c_int64),
                 ("wave1_cells", C.c_int64), ("wall_ms_index", C.c_float), ("wall_ms_align", C.c_float),
-                ("wall_ms_text", C.c_float)]
+                ("wall_ms_text", C.c_float), ("wall_ms_post", C.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -53,7 +53,7 @@ SYMBOLS = [
     "pmn_result_n_deltas", "pmn_result_copy_alignments",
     "pmn_sched_create", "pmn_sched_destroy", "pmn_sched_workers", "pmn_sched_ctx", "pmn_sched_counters",
     "pmn_sched_align_fasta", "pmn_sched_align_seqs", "pmn_sched_align_indexed", "pmn_sched_align_files",
-    "pmn_delta_filter", "pmn_delta2maf", "pmn_free_text",
+    "pmn_delta_filter", "pmn_delta2maf", "pmn_free_text", "pmn_result_filtered", "pmn_result_maf",
 ]
 
 
@@ -93,6 +93,8 @@ def lib():
         L.pmn_align_anchors.argtypes = [vp, vp, vp, C.POINTER(Opts), vp, i64, cp, cp, C.POINTER(vp)]
         L.pmn_result_delta.argtypes = [vp, C.POINTER(C.c_size_t)]; L.pmn_result_delta.restype = vp
         L.pmn_result_stats.argtypes = [vp, C.POINTER(Stats)]
+        L.pmn_result_filtered.argtypes = [vp, C.POINTER(C.c_size_t)]; L.pmn_result_filtered.restype = vp
+        L.pmn_result_maf.argtypes = [vp, C.POINTER(C.c_size_t)]; L.pmn_result_maf.restype = vp
         L.pmn_result_free.argtypes = [vp]
         L.pmn_align_pair.argtypes = [vp, cp, cp, C.POINTER(Opts), cp]
         L.pmn_align_batch.argtypes = [vp, C.c_int, C.POINTER(cp), C.POINTER(cp), C.POINTER(cp), C.POINTER(Opts)]
@@ -395,6 +397,20 @@ class Result:
         n = C.c_size_t()
         p = lib().pmn_result_delta(self.h, C.byref(n))
         return C.string_at(p, n.value)
+
+    @property
+    def filtered(self) -> bytes:
+        """`delta-filter` of .delta (options post=1: -1, post=2: -m); empty without the option."""
+        n = C.c_size_t()
+        p = lib().pmn_result_filtered(self.h, C.byref(n))
+        return C.string_at(p, n.value) if n.value else b""
+
+    @property
+    def maf(self) -> bytes:
+        """`delta2maf` of the filtered delta (option post); empty without the option."""
+        n = C.c_size_t()
+        p = lib().pmn_result_maf(self.h, C.byref(n))
+        return C.string_at(p, n.value) if n.value else b""
 
     @property
     def stats(self):

@@ -142,3 +142,30 @@ def test_front_ends_and_mirror(oracle, tmp_path):
     o2 = M.parse_argv(["-ref_seq", str(rp), "-query_seq", str(qp), "-maf_out", "c.maf", "-delta_out", "c.delta", "-out_dir", str(outd), "-tmp_dir", str(tmpd), "-colinear"])
     M.run_search(o2)
     assert (outd / "c.delta").read_bytes() == oracle.delta_filter(oracle.nucmer(ref, qry, str(rp), str(qp), fast_chain=1), 2)
+
+
+def test_post_steps_inside_the_batch_call(oracle):
+    """pmn_opts.post: nucmer, delta-filter and delta2maf of every pair in one scheduler call (what one mugsy_nucmer
+    process does, lib/nucmer/mugsy_nucmer.ml:127-131) equal the three text-level steps and the oracle."""
+    from paramugsy_b200 import lib
+    gs = synth.config_c2(n=120_000, count=4, inv_len=3_000)
+    dup = gs[1][1] + synth.random_genome(300, 77) + gs[1][1][40_000:60_000]         # a second copy: something for the filter to drop
+    gs = gs + [("dup.1", dup)]
+    fastas = [synth.fasta(n, s) for n, s in gs]; names = [n for n, _ in gs]
+    pairs = [(i, j) for i in range(len(gs)) for j in range(i + 1, len(gs))]
+    for mode in (1, 2):
+        with lib.Scheduler(0, 3) as s:
+            res = s.align_fasta(fastas, pairs, names=names, post=mode)
+            dropped = 0
+            for (i, j), r in zip(pairs, res):
+                d = oracle.nucmer(fastas[i], fastas[j], names[i], names[j], fast_chain=1)
+                f = oracle.delta_filter(d, mode)
+                assert r.delta == d and r.filtered == f and r.maf == oracle.delta2maf(f, fastas[i], fastas[j])
+                assert r.stats["wall_ms_post"] > 0
+                dropped += d.count(b"\n0\n") - f.count(b"\n0\n")
+            assert (dropped > 0) == (mode == 1)
+    with lib.Scheduler(0, 2) as s:
+        r = s.align_fasta(fastas[:2], [(0, 1)], names=names[:2])[0]
+        assert r.filtered == b"" and r.maf == b""
+        with pytest.raises(lib.PmnError):
+            s.align_fasta(fastas[:2], [(0, 1)], post=3)
