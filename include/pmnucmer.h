@@ -143,6 +143,12 @@ int  pmn_align_pair(pmn_ctx *c, const char *ref_fasta_path, const char *qry_fast
 int  pmn_align_batch(pmn_ctx *c, int n, const char *const *ref_fasta_paths, const char *const *qry_fasta_paths,
                      const char *const *out_delta_paths, const pmn_opts *o);
 
+/* The job of n `mugsy_nucmer` worker processes (lib/base/nucmer_task.ml:48-59 emits one command per pair,
+ * lib/nucmer/mugsy_nucmer.ml:127-131 runs nucmer, delta-filter, delta2maf): with o->post = 1 (`-1`) or 2 (`-m`, -colinear)
+ * delta_outs[i] receives the FILTERED delta (what the reference copies to delta_out) and maf_outs[i] its MAF; atomic writes. */
+int  pmn_worker_batch(pmn_ctx *c, int n, const char *const *ref_fasta_paths, const char *const *qry_fasta_paths,
+                      const char *const *delta_outs, const char *const *maf_outs, const pmn_opts *o);
+
 /* ---- the two post-steps of lib/nucmer/mugsy_nucmer.ml, on .delta text in host memory ----
  * pmn_delta_filter: `delta-filter -1` (mode 1) / `-m` (mode 2), mugsy_nucmer.ml:102-105; maxolap is delta-filter's -o (75.0).
  * pmn_delta2maf:    `delta2maf`, mugsy_nucmer.ml:118-124; ref / qry are the packed genomes the delta was computed from.

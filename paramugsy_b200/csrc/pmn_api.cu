@@ -593,9 +593,10 @@ int pmn_write_file_atomic(const char *path, const char *data, size_t len)
     return 0;
 }
 
-extern "C" int pmn_align_batch(pmn_ctx *c, int n, const char *const *refs, const char *const *qrys, const char *const *outs, const pmn_opts *o)
+static int batch_files(pmn_ctx *c, int n, const char *const *refs, const char *const *qrys, const char *const *outs, const char *const *mafs, const pmn_opts *o)
 {
     if (!c || n < 0 || (n && (!refs || !qrys || !outs))) return pmn_set_error(PMN_E_ARG, "pmn_align_batch: bad argument");
+    if (mafs && !(o && o->post)) return pmn_set_error(PMN_E_ARG, "pmn_worker_batch: MAF output needs pmn_opts.post = 1 or 2");
     // pairs are processed grouped by reference so that every index is built once; sequences
     // used several times are packed once
     std::map<std::string, pmn_seq *> seqs;
@@ -624,12 +625,27 @@ extern "C" int pmn_align_batch(pmn_ctx *c, int n, const char *const *refs, const
         pmn_seq *qs; rc = get_seq(qrys[i], &qs); if (rc) break;
         pmn_result *res = nullptr;
         rc = pmn_align(c, cur_ix, qs, o, refs[i], qrys[i], &res); if (rc) break;
-        rc = pmn_write_file_atomic(outs[i], res->delta.data(), res->delta.size());
+        if (mafs) {         // the files one mugsy_nucmer process leaves behind: delta_out is the FILTERED delta (mugsy_nucmer.ml:128-130), maf_out its MAF
+            rc = pmn_write_file_atomic(outs[i], res->filtered.data(), res->filtered.size());
+            if (!rc && mafs[i]) rc = pmn_write_file_atomic(mafs[i], res->maf, res->maf_len);
+        } else rc = pmn_write_file_atomic(outs[i], res->delta.data(), res->delta.size());
         pmn_result_free(res);
     }
     if (cur_ix) pmn_index_free(cur_ix);
     for (auto &kv : seqs) pmn_seq_free(kv.second);
     return rc;
+}
+
+extern "C" int pmn_align_batch(pmn_ctx *c, int n, const char *const *refs, const char *const *qrys, const char *const *outs, const pmn_opts *o)
+{
+    return batch_files(c, n, refs, qrys, outs, nullptr, o);
+}
+
+extern "C" int pmn_worker_batch(pmn_ctx *c, int n, const char *const *refs, const char *const *qrys, const char *const *delta_outs,
+                                const char *const *maf_outs, const pmn_opts *o)
+{
+    if (!maf_outs) return pmn_set_error(PMN_E_ARG, "pmn_worker_batch: bad argument");
+    return batch_files(c, n, refs, qrys, delta_outs, maf_outs, o);
 }
 
 extern "C" int pmn_align_pair(pmn_ctx *c, const char *ref_fasta_path, const char *qry_fasta_path, const pmn_opts *o, const char *out_delta_path)

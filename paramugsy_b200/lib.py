@@ -53,7 +53,7 @@ SYMBOLS = [
     "pmn_result_n_deltas", "pmn_result_copy_alignments",
     "pmn_sched_create", "pmn_sched_destroy", "pmn_sched_workers", "pmn_sched_ctx", "pmn_sched_counters",
     "pmn_sched_align_fasta", "pmn_sched_align_seqs", "pmn_sched_align_indexed", "pmn_sched_align_files",
-    "pmn_delta_filter", "pmn_delta2maf", "pmn_free_text", "pmn_result_filtered", "pmn_result_maf",
+    "pmn_delta_filter", "pmn_delta2maf", "pmn_free_text", "pmn_result_filtered", "pmn_result_maf", "pmn_worker_batch",
 ]
 
 
@@ -98,6 +98,7 @@ def lib():
         L.pmn_result_free.argtypes = [vp]
         L.pmn_align_pair.argtypes = [vp, cp, cp, C.POINTER(Opts), cp]
         L.pmn_align_batch.argtypes = [vp, C.c_int, C.POINTER(cp), C.POINTER(cp), C.POINTER(cp), C.POINTER(Opts)]
+        L.pmn_worker_batch.argtypes = [vp, C.c_int, C.POINTER(cp), C.POINTER(cp), C.POINTER(cp), C.POINTER(cp), C.POINTER(Opts)]
         L.pmn_index_size.argtypes = [vp]; L.pmn_index_size.restype = i64
         L.pmn_index_copy_sa.argtypes = [vp, vp, vp]
         for name in ("pmn_result_n_anchors", "pmn_result_n_clusters", "pmn_result_n_cluster_matches",

@@ -227,10 +227,12 @@ def chunk(n: int, items):
     return [items[i:i + n] for i in range(0, len(items), n)]
 
 
-def run_nucmers(searches_, tmp_dir: str, nucmer_chunk: int = 10, ctx=None, filter=False):
+def run_nucmers(searches_, tmp_dir: str, nucmer_chunk: int = 10, ctx=None, filter=True, colinear=False):
     """job_processor.ml:128-154 without the script/queue machinery: every chunk of pairs goes to the
     library's batch entry point (the batch unit of the reference, nucmer_task.ml:6); returns the
-    out_paths map.  Any failing pair raises Failure (job_processor.ml:72-73 fails the whole node)."""
+    out_paths map.  With `filter` (mugsy_nucmer's default, mugsy_nucmer.ml:54) every pair leaves what one
+    mugsy_nucmer process leaves: <bname>.delta = the filtered delta and <bname>.maf (pmn_worker_batch); without it
+    the unfiltered delta only.  Any failing pair raises Failure (job_processor.ml:72-73 fails the whole node)."""
     import ctypes as C
     os.makedirs(tmp_dir, exist_ok=True)
     own = ctx is None
@@ -239,7 +241,12 @@ def run_nucmers(searches_, tmp_dir: str, nucmer_chunk: int = 10, ctx=None, filte
         for part in chunk(nucmer_chunk, list(searches_)):
             outs = [os.path.join(tmp_dir, basename(a, b) + ".delta") for a, b in part]
             arr = lambda xs: (C.c_char_p * len(xs))(*[os.fsencode(x) for x in xs])
-            rc = lib.lib().pmn_align_batch(c.h, len(part), arr([a for a, _ in part]), arr([b for _, b in part]), arr(outs), None)
+            if filter:
+                mafs = [os.path.join(tmp_dir, basename(a, b) + ".maf") for a, b in part]
+                o = lib.default_opts(post=2 if colinear else 1)
+                rc = lib.lib().pmn_worker_batch(c.h, len(part), arr([a for a, _ in part]), arr([b for _, b in part]), arr(outs), arr(mafs), C.byref(o))
+            else:
+                rc = lib.lib().pmn_align_batch(c.h, len(part), arr([a for a, _ in part]), arr([b for _, b in part]), arr(outs), None)
             if rc != 0:
                 raise Failure(lib.lib().pmn_last_error(None).decode(errors="replace"))
     finally:

@@ -169,3 +169,25 @@ def test_post_steps_inside_the_batch_call(oracle):
         assert r.filtered == b"" and r.maf == b""
         with pytest.raises(lib.PmnError):
             s.align_fasta(fastas[:2], [(0, 1)], post=3)
+
+
+def test_run_nucmers_leaves_the_files_of_the_reference_workers(oracle, tmp_path):
+    """The mirror of run_nucmers (lib/base/job_processor.ml:128-154) over pmn_worker_batch: per pair <bname>.delta is the
+    filtered delta and <bname>.maf its MAF, named as lib/base/nucmer_task.ml:10-23 names them."""
+    from paramugsy_b200 import mugsy_nucmer as M
+    gs = synth.config_c2(n=90_000, count=3, inv_len=2_000)
+    paths = []
+    for name, seq in gs:
+        p = tmp_path / name; p.write_bytes(synth.fasta(name, seq)); paths.append(str(p))
+    searches = M.searches(paths)
+    out = M.run_nucmers(searches, str(tmp_path / "nuc"))
+    assert len(out) == 2 * len(searches)
+    for a, b in searches:
+        fa, fb = open(a, "rb").read(), open(b, "rb").read()
+        f = oracle.delta_filter(oracle.nucmer(fa, fb, a, b, fast_chain=1), 1)
+        bn = M.basename(a, b)
+        assert open(out[bn + "-delta"], "rb").read() == f
+        assert open(out[bn + "-maf"], "rb").read() == oracle.delta2maf(f, fa, fb)
+    out2 = M.run_nucmers(searches[:1], str(tmp_path / "nuc2"), filter=False)
+    a, b = searches[0]
+    assert open(out2[M.basename(a, b) + "-delta"], "rb").read() == oracle.nucmer(open(a, "rb").read(), open(b, "rb").read(), a, b, fast_chain=1)
