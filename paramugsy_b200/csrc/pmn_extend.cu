@@ -518,6 +518,91 @@ __device__ __noinline__ EngCtx eng_run_wide(const Eng &E, EngCtx c, const Packed
     return c;
 }
 
+
+// ------------------------------------------------------------------------------------ forced alignments: the whole matrix, one warp
+//
+// A FORCED forward alignment (extendBackward's re-alignment of the region a search found, or the bridge to the alignment
+// it reached: oracle/pmn_oracle.c extend_backward) has no trimming and no early stop: every cell of the N x M matrix is
+// evaluated and the traceback starts in (N, M).  At 10-15 % divergence these windows are several hundred bases on a side
+// and the banded engine would run them in its widest fallback.  Here the warp is a systolic array instead: lane l owns a
+// strip of 8 columns, handles row t - l at step t and hands the right edge of its strip to lane l + 1 by one shuffle; 32
+// strips (256 columns) form a pass, the right edge of a pass goes through a 16-byte record per row.  Cell arithmetic,
+// state bits and traceback bytes are those of k_ex_wave1_tpj.  Returns the state of the finish cell.
+#define SYS_NEG (-(1 << 28))
+__device__ __forceinline__ unsigned tpj_query_nibbles(const PackedView &Q, int64_t p, int left);
+
+__device__ __noinline__ int eng_forced_systolic(const Eng &E, const PackedView &Q, int64_t Apos0, int64_t Bpos0, int N, int M, uint2 *tb, int4 *bnd)
+{
+    const ExShared &X = *E.X;
+    const int lane = E.lane;
+    const int npass = (M + 255) >> 8;
+    int ms_fin = PMN_ST_MAT;
+    for (int ps = 0; ps < npass; ps++) {
+        const int j0 = ps * 256 + lane * 8;                 // this lane's columns: j0 + 1 .. j0 + 8
+        const bool have = j0 < M;
+        int nl = (M - ps * 256 + 7) >> 3; if (nl > 32) nl = 32;     // active lanes of this pass
+        const unsigned qn = have ? tpj_query_nibbles(Q, Bpos0 + j0, M - j0) : 0x44444444u;
+        int uI[8], ug[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) { uI[c] = SYS_NEG; ug[c] = SYS_NEG; }
+        int prev_bmc = SYS_NEG;
+        int oD = SYS_NEG, oH = SYS_NEG, oC = SYS_NEG;       // right edge of the row this lane finished last: (D, max(I+1, M+2), cell maximum)
+        uint64_t aw = 0; uint32_t ax = 0;
+        uint2 *trow = tb + (size_t)ps * (N + 1) * 32 + lane;
+        const int steps = N + nl;
+        for (int t = 0; t < steps; t++) {
+            int lD = __shfl_up_sync(0xffffffffu, oD, 1), hl = __shfl_up_sync(0xffffffffu, oH, 1), bmc = __shfl_up_sync(0xffffffffu, oC, 1);
+            const int i = t - lane;
+            const bool act = have && i >= 0 && i <= N;
+            if (lane == 0 && act) {
+                if (ps == 0) {
+                    if (i == 0) { lD = SYS_NEG; hl = 2; bmc = 2; }                       // cell (0,0) = MAT 0
+                    else { const int v = 4 * (PMN_OPEN_GAP_SCORE + PMN_CONT_GAP_SCORE * (i - 1)) + PMN_ST_INS; lD = SYS_NEG; hl = v; bmc = v; }
+                } else { const int4 b = bnd[i]; lD = b.x; hl = b.y; bmc = b.z; }
+            }
+            if (act) {
+                unsigned an = 8;
+                if (i >= 1) {
+                    if (((i - 1) & 31) == 0 || i == 1) { aw = pmn_window64(X.R.w, Apos0 + i - 1); ax = X.R.has_x ? pmn_xwindow32(X.R.xm, Apos0 + i - 1) : 0u; }
+                    an = (unsigned)(aw >> 62) | ((ax >> 31) << 3);
+                    aw <<= 2; ax <<= 1;
+                }
+                const unsigned x = (an * 0x11111111u) ^ qn;
+                int dmc = prev_bmc;
+                prev_bmc = bmc;
+                unsigned t0 = 0, t1 = 0; int mc = 0;
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    const int sc = (x & (0xfu << (4 * c))) ? 4 * PMN_BAD_SCORE : 4 * PMN_GOOD_SCORE;
+                    const int mD = __viaddmax_s32(lD, 4 * PMN_CONT_GAP_SCORE + PMN_ST_DEL, hl + 4 * PMN_OPEN_GAP_SCORE);
+                    const int mI = __viaddmax_s32(uI[c], 4 * PMN_CONT_GAP_SCORE + PMN_ST_INS, ug[c] + 4 * PMN_OPEN_GAP_SCORE);
+                    const int mM = dmc + sc;
+                    dmc = __viaddmax_s32(uI[c], PMN_ST_INS, ug[c]);
+                    const int vD = mD & ~3, vI = mI & ~3, vM2 = (mM & ~3) + PMN_ST_MAT;
+                    hl = __viaddmax_s32(vI, PMN_ST_INS, vM2);
+                    mc = max(hl, vD);
+                    uI[c] = vI; ug[c] = max(vD, vM2);
+                    lD = vD;
+                    const unsigned tbits = ((unsigned)mD & 3u) | (((unsigned)mI & 3u) << 2) | (((unsigned)mM & 3u) << 4);
+                    if (c < 4) t0 |= tbits << (8 * c); else t1 |= tbits << (8 * (c - 4));
+                }
+                trow[(size_t)i * 32] = make_uint2(t0, t1);
+                oD = lD; oH = hl; oC = mc;
+                if (lane == nl - 1 && ps + 1 < npass) bnd[i] = make_int4(lD, hl, mc, 0);
+            }
+        }
+        if (ps == npass - 1) {                              // the finish cell (N, M) sits in column (M-1) & 7 of lane ((M-1) >> 3) & 31
+            const int c = (M - 1) & 7;
+            int mcf = 0;
+#pragma unroll
+            for (int cc = 0; cc < 8; cc++) if (cc == c) mcf = __viaddmax_s32(uI[cc], PMN_ST_INS, ug[cc]);
+            ms_fin = __shfl_sync(0xffffffffu, mcf, ((M - 1) >> 3) & 31) & 3;
+        }
+        __syncwarp();                                       // the records of this pass are read by lane 0 in the next one
+    }
+    return ms_fin;
+}
+
 // One alignment.  All 32 lanes call with identical arguments and get identical results.
 // Returns reached (0/1); Aend/Bend become the finish cell.  Unless SEARCH, the deltas are
 // appended to the pool: *doff, *dcnt.
@@ -567,8 +652,23 @@ __device__ __noinline__ int align_engine(const Eng &E, int64_t Abase, int64_t As
         eng_fill_qry<Cfg>(Q, c, cbw, lane);
     }
 
+    // forced alignments over large windows: the systolic full-matrix path
+    uint2 *sys_tb = nullptr; int sys_ms = PMN_ST_MAT;
+    if (c.forced && !c.search && c.dir > 0 && (N < M ? N : M) >= 64) {
+        const unsigned long long need = (unsigned long long)((M + 255) >> 8) * (unsigned long long)(N + 1) * 256ull;
+        if (need <= (64ull << 20)) {
+            unsigned long long at = 0;
+            if (lane == 0) at = atomicAdd(X.counters + 1, need);
+            at = __shfl_sync(0xffffffffu, at, 0);
+            if (at + need <= X.arena_cap) sys_tb = (uint2 *)(X.arena + at);       // else: the banded engine below reports the exhausted arena
+        }
+    }
     int mode = 1, path = 0;
-    for (;;) {
+    if (sys_tb) {
+        sys_ms = eng_forced_systolic(E, Q, c.Apos0, c.Bpos0, N, M, sys_tb, (int4 *)E.gsc);
+        c.reached = 1; c.d = N + M; c.cells = (unsigned long long)(N + 1) * (unsigned long long)(M + 1) - 1ull; c.ext_i = N; c.ext_j = M; path = 32;
+    }
+    else for (;;) {
         int rc;
         if (mode > Cfg::MAXK) {
             if (Cfg::MAXK < 8) return -1;          // too wide for this kernel: the caller hands the alignment to the big one
@@ -619,6 +719,13 @@ __device__ __noinline__ int align_engine(const Eng &E, int64_t Abase, int64_t As
             int32_t *segcol = ring + 2 * Cfg::RW;               // row 2: column of byte 0 of each lane's segment
             int win_top = -1, win_bot = 0;
             auto cell = [&](int cd, int cj) -> unsigned {
+                if (sys_tb) {                           // systolic layout: [pass][row][lane] words of 8 columns; column 0 is implicit
+                    const int ci = cd - cj;
+                    if (cj == 0) return (unsigned)(ci == 1 ? PMN_ST_MAT : PMN_ST_INS) << 2;
+                    const uint2 wv = sys_tb[((size_t)((cj - 1) >> 8) * (N + 1) + ci) * 32 + (((cj - 1) >> 3) & 31)];
+                    const int cc = (cj - 1) & 7;
+                    return ((cc < 4 ? wv.x : wv.y) >> (8 * (cc & 3))) & 0x3fu;
+                }
                 if (cd < n_sm) { const int m0 = meta[cd]; return rows[(m0 >> 16) + cj - (int)(short)(m0 & 0xffff)]; }
                 if (cd > win_top || cd < win_bot) {
                     __syncwarp();
@@ -641,7 +748,7 @@ __device__ __noinline__ int align_engine(const Eng &E, int64_t Abase, int64_t As
             };
             auto emit = [&](int v) { if (lane == 0) { if (nrev < Cfg::REV_N) rev_s[nrev] = v; else rev[nrev] = v; } nrev++; };
             int cd = fd, cj = fj;
-            int st = cell(cd, cj) >> 6;
+            int st = sys_tb ? sys_ms : (int)(cell(cd, cj) >> 6);
             int pending = 0, run = 0;
             while (cd > 0) {
                 const unsigned b = cell(cd, cj);
