@@ -234,17 +234,17 @@ struct RadixScratch {
     }
 };
 
-// Sorts bits [0, nbits) of the keys, stable.  Ping-pongs between (k0,v0) and (k1,v1);
+// Sorts bits [first_shift, nbits) of the keys, stable.  Ping-pongs between (k0,v0) and (k1,v1);
 // returns 0 if the result is in (k0,v0), 1 if in (k1,v1), negative on error.
 static inline int pmn_radix_sort(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint32_t *v1, int64_t n, int nbits,
-                                 RadixScratch &rs, cudaStream_t st, int *launches = nullptr)
+                                 RadixScratch &rs, cudaStream_t st, int *launches = nullptr, int first_shift = 0)
 {
     if (n <= 1 || nbits <= 0) return 0;
     if (rs.reserve(n)) return -1;
     int ntiles = (int)((n + PMN_RS_TILE - 1) / PMN_RS_TILE);
     int64_t cells = (int64_t)ntiles * PMN_RS_RADIX;
     int cur = 0;
-    for (int shift = 0; shift < nbits; shift += 8) {
+    for (int shift = first_shift; shift < nbits; shift += 8) {       // first_shift > 0: the input is already ordered by the bits below it
         uint64_t *ki = cur ? k1 : k0, *ko = cur ? k0 : k1; uint32_t *vi = cur ? v1 : v0, *vo = cur ? v0 : v1;
         pmn_rs_hist<<<ntiles, PMN_RS_THREADS, 0, st>>>(ki, n, shift, rs.hist.as<uint32_t>(), ntiles);
         pmn_scan<uint32_t, OpAddU32, false>(rs.hist.as<uint32_t>(), rs.hist.as<uint32_t>(), cells, rs.spine.as<uint32_t>(), st);
