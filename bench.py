@@ -304,7 +304,7 @@ def run_gpu(args):
             "e2e_worker": {"what": "nucmer + delta-filter -1 + delta2maf per pair in the same call (pmn_opts.post = 1): .delta, filtered .delta and MAF in host memory",
                            "value": npairs_all * args.steps / (ms_wrk * 1e-3), "unit": UNIT, "ms_per_step": ms_wrk / args.steps,
                            "h2d_bytes_per_step": cnt_wrk["h2d_bytes"] // args.steps, "d2h_bytes_per_step": cnt_wrk["d2h_bytes"] // args.steps} if ms_wrk else None,
-            "gpu_launches": cnt_res["launches"], "step_wall_ms": {"resident": cnt_res["walls"], "e2e": cnt_e2e["walls"]},
+            "gpu_launches": cnt_res["launches"], "step_wall_ms": {"resident": cnt_res["walls"], "e2e": cnt_e2e["walls"], "e2e_worker": cnt_wrk["walls"] if cnt_wrk else None},
             "device_allocations_in_timed_region": {"resident": cnt_res["allocs"], "e2e": cnt_e2e["allocs"]},
             "clocks": clocks,
             "stage_ms_per_step": stage_ms,

@@ -188,11 +188,11 @@ int pmn_fasta_to_device(pmn_ctx *c, pmn_seq *s, const char *txt, size_t nb, cons
 // class_first: (text without X) the 15 suffixes that end inside their window are written in front, shortest first, and the
 // rest behind them in text order: the array is then ordered by the 6 class bits among equal 16-mers, and the stable sort can
 // skip its pass over them
-__global__ void __launch_bounds__(256) k_sa_keys(PackedView s, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals, int class_first)
+template <bool CLASS_FIRST>
+__global__ void __launch_bounds__(256) k_sa_keys(PackedView s, uint64_t *__restrict__ keys, uint32_t *__restrict__ keys32, uint32_t *__restrict__ vals)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= s.n) return;
-    const int64_t at = !class_first ? i : (i >= s.n - 15 ? s.n - 1 - i : i + 15);
     int v = pmn_valid32(s, i);
     uint32_t hi = (uint32_t)(pmn_window64(s.w, i) >> 32);
     uint32_t cls;
@@ -202,8 +202,10 @@ __global__ void __launch_bounds__(256) k_sa_keys(PackedView s, uint64_t *__restr
         if (i + v >= s.n) { hi &= keep; cls = (uint32_t)(v - 1); }
         else { hi = (hi & keep) | ~keep; cls = 16u + (16u - (uint32_t)v); }
     }
-    keys[at] = (uint64_t)hi << 6 | cls;
-    vals[at] = (uint32_t)i;
+    if (CLASS_FIRST) {      // the class bits stay out of the key: 32-bit keys, a third less traffic per sort pass
+        const int64_t at = i >= s.n - 15 ? s.n - 1 - i : i + 15;
+        keys32[at] = hi; vals[at] = (uint32_t)i;
+    } else { keys[i] = (uint64_t)hi << 6 | cls; vals[i] = (uint32_t)i; }
 }
 
 __global__ void __launch_bounds__(256) k_sa_heads(const uint64_t *__restrict__ keys, int64_t n, int32_t *__restrict__ headpos)
@@ -212,6 +214,16 @@ __global__ void __launch_bounds__(256) k_sa_heads(const uint64_t *__restrict__ k
     if (p >= n) return;
     uint64_t k = keys[p];
     bool head = p == 0 || k != keys[p - 1] || (k & 63) != CLS_REGULAR;
+    headpos[p] = head ? (int32_t)p : -1;
+}
+
+// class-first keys (text without X): the suffixes whose class is not CLS_REGULAR are the last 15 of the text
+__global__ void __launch_bounds__(256) k_sa_heads32(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, int64_t n, int32_t *__restrict__ headpos)
+{
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    uint32_t k = keys[p];
+    bool head = p == 0 || k != keys[p - 1] || (int64_t)vals[p] >= n - 15 || (int64_t)vals[p - 1] >= n - 15;    // a group never contains a suffix of another class
     headpos[p] = head ? (int32_t)p : -1;
 }
 
@@ -367,10 +379,16 @@ int pmn_index_build_impl(pmn_ctx *c, const pmn_seq *ref, pmn_index *ix)
 
     // 1. sort all suffixes by their first 16 symbols
     const int class_first = (!T.has_x && n > 15) ? 1 : 0;       // 4 sort passes over the 32 bits of the 16-mer instead of 5 over all 38
-    k_sa_keys<<<gn, 256, 0, st>>>(T, S.k0.as<uint64_t>(), S.v0.as<uint32_t>(), class_first); launches++;
-    int where = pmn_radix_sort(S.k0.as<uint64_t>(), S.v0.as<uint32_t>(), S.k1.as<uint64_t>(), S.v1.as<uint32_t>(), n, 38, S.rs, st, &launches, class_first ? 6 : 0);
+    int where;
+    if (class_first) {
+        k_sa_keys<true><<<gn, 256, 0, st>>>(T, nullptr, S.k0.as<uint32_t>(), S.v0.as<uint32_t>()); launches++;
+        where = pmn_radix_sort(S.k0.as<uint32_t>(), S.v0.as<uint32_t>(), S.k1.as<uint32_t>(), S.v1.as<uint32_t>(), n, 32, S.rs, st, &launches);
+    } else {
+        k_sa_keys<false><<<gn, 256, 0, st>>>(T, S.k0.as<uint64_t>(), nullptr, S.v0.as<uint32_t>()); launches++;
+        where = pmn_radix_sort(S.k0.as<uint64_t>(), S.v0.as<uint32_t>(), S.k1.as<uint64_t>(), S.v1.as<uint32_t>(), n, 38, S.rs, st, &launches);
+    }
     if (where < 0) return -3;
-    const uint64_t *skeys = where ? S.k1.as<uint64_t>() : S.k0.as<uint64_t>();
+    const void *skeys = where ? S.k1.p : S.k0.p;
     const uint32_t *svals = where ? S.v1.as<uint32_t>() : S.v0.as<uint32_t>();
     uint32_t *sa = ix->sa();
     PMN_CUDA_OK(cudaMemcpyAsync(sa, svals, 4 * (size_t)n, cudaMemcpyDeviceToDevice, st));
@@ -378,7 +396,9 @@ int pmn_index_build_impl(pmn_ctx *c, const pmn_seq *ref, pmn_index *ix)
     // 2. groups of equal 16-mers -> ranks; slots that still share a group go on the work list
     int32_t *gs = S.gs.as<int32_t>(), *rank = S.rank.as<int32_t>(), *gsn = S.gsn.as<int32_t>();
     uint32_t *flags = S.flags.as<uint32_t>();
-    k_sa_heads<<<gn, 256, 0, st>>>(skeys, n, gs); launches++;
+    if (class_first) k_sa_heads32<<<gn, 256, 0, st>>>((const uint32_t *)skeys, svals, n, gs);
+    else k_sa_heads<<<gn, 256, 0, st>>>((const uint64_t *)skeys, n, gs);
+    launches++;
     pmn_scan<int32_t, OpMaxI32, true>(gs, gs, n, S.scan_tmp.as<int32_t>(), st); launches += 3;
     k_sa_init_rank<<<gn, 256, 0, st>>>(sa, gs, n, rank, flags); launches++;
 

@@ -149,77 +149,170 @@ static inline size_t pmn_scan_scratch_elems(int64_t n) { return (size_t)((n + PM
 
 // ------------------------------------------------------------------------------------ radix sort
 
-#define PMN_RS_THREADS 256
-#define PMN_RS_WARPS (PMN_RS_THREADS / 32)
-#define PMN_RS_ITEMS 16                                   /* keys per lane */
-#define PMN_RS_TILE (PMN_RS_THREADS * PMN_RS_ITEMS)       /* 4096 keys per block */
 #define PMN_RS_RADIX 256
+#define PMN_RS_TILE 4096                                  /* keys per block of the tiled sort */
+#define PMN_RS_HIST_THREADS 256
+#define PMN_RS_WARPS 16                                   /* scatter kernel: 16 warps x 8 keys per lane */
+#define PMN_RS_ITEMS (PMN_RS_TILE / (PMN_RS_WARPS * 32))
 
 // histogram of one digit per tile: hist[d * ntiles + tile]
-static __global__ void __launch_bounds__(PMN_RS_THREADS) pmn_rs_hist(const uint64_t *__restrict__ keys, int64_t n, int shift, uint32_t *__restrict__ hist, int ntiles)
+template <class KeyT>
+static __global__ void __launch_bounds__(PMN_RS_HIST_THREADS) pmn_rs_hist(const KeyT *__restrict__ keys, int64_t n, int shift, uint32_t *__restrict__ hist, int ntiles)
 {
     __shared__ uint32_t h[PMN_RS_RADIX];
     h[threadIdx.x] = 0;
     __syncthreads();
     int64_t base = (int64_t)blockIdx.x * PMN_RS_TILE;
 #pragma unroll
-    for (int k = 0; k < PMN_RS_ITEMS; k++) {
-        int64_t i = base + k * PMN_RS_THREADS + threadIdx.x;
-        if (i < n) atomicAdd(&h[(keys[i] >> shift) & 0xff], 1u);
+    for (int k = 0; k < PMN_RS_TILE / PMN_RS_HIST_THREADS; k++) {
+        int64_t i = base + k * PMN_RS_HIST_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&h[(unsigned)(keys[i] >> shift) & 0xff], 1u);
     }
     __syncthreads();
     hist[(size_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
 }
 
-// stable scatter.  Warp w of the block owns keys [base + w*512, base + (w+1)*512) and walks
-// them 32 at a time in order; lanes with equal digits are ranked by lane id (match_any).
-static __global__ void __launch_bounds__(PMN_RS_THREADS) pmn_rs_scatter(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
-                                                                 uint64_t *__restrict__ kout, uint32_t *__restrict__ vout,
-                                                                 int64_t n, int shift, const uint32_t *__restrict__ offs, int ntiles)
+// lanes of `act` that hold the same 8-bit digit as the caller: eight ballots (MATCH.ANY walks the distinct values of the
+// warp one after the other and was what the scatter kernel waited for)
+__device__ __forceinline__ unsigned pmn_match_digit(unsigned act, unsigned d)
 {
-    __shared__ uint32_t cnt[PMN_RS_WARPS][PMN_RS_RADIX];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int k = threadIdx.x; k < PMN_RS_WARPS * PMN_RS_RADIX; k += PMN_RS_THREADS) (&cnt[0][0])[k] = 0;
-    __syncthreads();
-    const int64_t wbase = (int64_t)blockIdx.x * PMN_RS_TILE + (int64_t)warp * (32 * PMN_RS_ITEMS);
-    uint64_t key[PMN_RS_ITEMS]; uint32_t val[PMN_RS_ITEMS];
+    unsigned peers = act;
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+        const unsigned bal = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+        peers &= ((d >> b) & 1u) ? bal : ~bal;
+    }
+    return peers;
+}
+
+// One pass of the stable sort over one tile, shared by the scatter kernel and the one-block sort.  Warp w owns keys
+// [w*32*ITEMS, (w+1)*32*ITEMS) of the tile and walks them 32 at a time in order; lanes with equal digits are ranked by
+// lane id.  The keys are first placed in shared memory at their rank inside the tile, so that what leaves the block are
+// runs of consecutive addresses per digit (a tile of 4096 random keys: 16 keys per run) instead of 32 unrelated stores per
+// warp instruction.
+//   cnt[w][d]: scratch, NWARPS x 256;  on return skey/sval hold the tile in sorted order and, when dstart is not null,
+//   dstart[d] = first slot of digit d inside the tile.  Every thread of the block must call it.
+template <class KeyT, int NWARPS, int ITEMS>
+__device__ __forceinline__ void pmn_rs_tile_pass(const KeyT (&key)[ITEMS], const uint32_t (&val)[ITEMS], unsigned okmask, int shift,
+                                                 KeyT *skey, uint32_t *sval, uint32_t (*cnt)[PMN_RS_RADIX], uint32_t *dstart, uint32_t *stmp)
+{
+    const int warp = threadIdx.x >> 5;
     const unsigned lt = pmn_lanemask_lt();
+    for (int k = threadIdx.x; k < NWARPS * PMN_RS_RADIX; k += NWARPS * 32) (&cnt[0][0])[k] = 0;
+    __syncthreads();
+    uint32_t rank[ITEMS];           // rank of the key among the keys of its warp with the same digit
 #pragma unroll
-    for (int k = 0; k < PMN_RS_ITEMS; k++) {
-        int64_t i = wbase + k * 32 + lane;
-        bool ok = i < n;
-        key[k] = ok ? kin[i] : ~0ull; val[k] = ok ? vin[i] : 0u;
-        unsigned act = __ballot_sync(0xffffffffu, ok);
-        if (ok) {
-            unsigned d = (unsigned)(key[k] >> shift) & 0xff;
-            unsigned m = __match_any_sync(act, d);
-            if ((m & lt) == 0) cnt[warp][d] += __popc(m);
-        }
+    for (int k = 0; k < ITEMS; k++) {
+        const bool ok = (okmask >> k) & 1u;
+        const unsigned act = __ballot_sync(0xffffffffu, ok);
+        const unsigned d = (unsigned)(key[k] >> shift) & 0xff;
+        const unsigned peers = pmn_match_digit(act, d);
+        uint32_t old = 0;
+        const bool leader = ok && (peers & lt) == 0;
+        if (leader) { old = cnt[warp][d]; cnt[warp][d] = old + __popc(peers); }
+        old = __shfl_sync(0xffffffffu, old, ok ? __ffs(peers) - 1 : 0);
+        rank[k] = old + __popc(peers & lt);
         __syncwarp();
     }
     __syncthreads();
-    {   // digit threadIdx.x: global offset of this tile, then exclusive prefix across the warps
-        unsigned d = threadIdx.x;
-        uint32_t run = offs[(size_t)d * ntiles + blockIdx.x];
+    {   // digit d = threadIdx.x: exclusive prefix across the warps, then across the digits
+        uint32_t run = 0;
+        const unsigned d = threadIdx.x;
+        if (d < PMN_RS_RADIX) {
 #pragma unroll
-        for (int w = 0; w < PMN_RS_WARPS; w++) { uint32_t t = cnt[w][d]; cnt[w][d] = run; run += t; }
+            for (int w = 0; w < NWARPS; w++) { uint32_t t = cnt[w][d]; cnt[w][d] = run; run += t; }
+        }
+        const uint32_t incl = pmn_block_scan_incl(run, OpAddU32(), stmp);
+        if (d < PMN_RS_RADIX) {
+            const uint32_t excl = incl - run;
+#pragma unroll
+            for (int w = 0; w < NWARPS; w++) cnt[w][d] += excl;
+            if (dstart) dstart[d] = excl;
+        }
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < PMN_RS_ITEMS; k++) {
-        int64_t i = wbase + k * 32 + lane;
-        bool ok = i < n;
-        unsigned act = __ballot_sync(0xffffffffu, ok);
-        if (ok) {
-            unsigned d = (unsigned)(key[k] >> shift) & 0xff;
-            unsigned m = __match_any_sync(act, d);
-            uint32_t pos = cnt[warp][d] + __popc(m & lt);
-            kout[pos] = key[k]; vout[pos] = val[k];
-            __syncwarp(m);
-            if ((m & lt) == 0) cnt[warp][d] += __popc(m);
+    for (int k = 0; k < ITEMS; k++) {
+        if ((okmask >> k) & 1u) {
+            const uint32_t pos = cnt[warp][(unsigned)(key[k] >> shift) & 0xff] + rank[k];
+            skey[pos] = key[k]; sval[pos] = val[k];
         }
-        __syncwarp();
     }
+    __syncthreads();
+}
+
+#define PMN_RS_SMEM_BYTES(KeyT, NWARPS, ITEMS) ((size_t)(NWARPS) * 32 * (ITEMS) * (sizeof(KeyT) + 4) + ((size_t)(NWARPS) * PMN_RS_RADIX + PMN_RS_RADIX + 32) * 4)
+
+// stable scatter of one tile per block; offs = exclusive scan of the per-tile histograms
+template <class KeyT>
+static __global__ void __launch_bounds__(PMN_RS_WARPS * 32) pmn_rs_scatter(const KeyT *__restrict__ kin, const uint32_t *__restrict__ vin,
+                                                                      KeyT *__restrict__ kout, uint32_t *__restrict__ vout,
+                                                                      int64_t n, int shift, const uint32_t *__restrict__ offs, int ntiles)
+{
+    extern __shared__ __align__(16) unsigned char pmn_rs_smem[];
+    KeyT *skey = (KeyT *)pmn_rs_smem;
+    uint32_t *sval = (uint32_t *)(skey + PMN_RS_TILE);
+    uint32_t (*cnt)[PMN_RS_RADIX] = (uint32_t (*)[PMN_RS_RADIX])(sval + PMN_RS_TILE);
+    uint32_t *dstart = &cnt[0][0] + PMN_RS_WARPS * PMN_RS_RADIX;
+    uint32_t *stmp = dstart + PMN_RS_RADIX;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t tbase = (int64_t)blockIdx.x * PMN_RS_TILE;
+    const int64_t wbase = tbase + (int64_t)warp * (32 * PMN_RS_ITEMS);
+    KeyT key[PMN_RS_ITEMS]; uint32_t val[PMN_RS_ITEMS]; unsigned okmask = 0;
+#pragma unroll
+    for (int k = 0; k < PMN_RS_ITEMS; k++) {
+        const int64_t i = wbase + k * 32 + lane;
+        const bool ok = i < n;
+        key[k] = ok ? kin[i] : (KeyT)0; val[k] = ok ? vin[i] : 0u;
+        okmask |= (ok ? 1u : 0u) << k;
+    }
+    pmn_rs_tile_pass<KeyT, PMN_RS_WARPS, PMN_RS_ITEMS>(key, val, okmask, shift, skey, sval, cnt, dstart, stmp);
+    // dstart[d] becomes (global offset of this tile's run of digit d) - (its first slot in the tile)
+    if (threadIdx.x < PMN_RS_RADIX) dstart[threadIdx.x] = offs[(size_t)threadIdx.x * ntiles + blockIdx.x] - dstart[threadIdx.x];
+    __syncthreads();
+    const int count = (int)(n - tbase < PMN_RS_TILE ? n - tbase : PMN_RS_TILE);
+#pragma unroll 4
+    for (int j = threadIdx.x; j < count; j += PMN_RS_WARPS * 32) {
+        const KeyT kk = skey[j];
+        const uint32_t g = dstart[(unsigned)(kk >> shift) & 0xff] + (uint32_t)j;
+        kout[g] = kk; vout[g] = sval[j];
+    }
+}
+
+// short arrays (the work lists of the doubling rounds, the cluster pieces of a pair): one block runs every pass in shared
+// memory — one launch instead of three per pass
+#define PMN_BS_WARPS 16
+#define PMN_BS_ITEMS 16
+#define PMN_BS_THREADS (PMN_BS_WARPS * 32)
+#define PMN_BS_CAP (PMN_BS_THREADS * PMN_BS_ITEMS)        /* 8192 keys */
+template <class KeyT>
+static __global__ void __launch_bounds__(PMN_BS_THREADS) pmn_rs_block_sort(const KeyT *__restrict__ kin, const uint32_t *__restrict__ vin,
+                                                                      KeyT *__restrict__ kout, uint32_t *__restrict__ vout, int n, int first_shift, int nbits)
+{
+    extern __shared__ __align__(16) unsigned char pmn_rs_smem[];
+    KeyT *skey = (KeyT *)pmn_rs_smem;
+    uint32_t *sval = (uint32_t *)(skey + PMN_BS_CAP);
+    uint32_t (*cnt)[PMN_RS_RADIX] = (uint32_t (*)[PMN_RS_RADIX])(sval + PMN_BS_CAP);
+    uint32_t *stmp = &cnt[0][0] + PMN_BS_WARPS * PMN_RS_RADIX + PMN_RS_RADIX;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wbase = warp * (32 * PMN_BS_ITEMS);
+    KeyT key[PMN_BS_ITEMS]; uint32_t val[PMN_BS_ITEMS]; unsigned okmask = 0;
+#pragma unroll
+    for (int k = 0; k < PMN_BS_ITEMS; k++) {
+        const int i = wbase + k * 32 + lane;
+        const bool ok = i < n;
+        key[k] = ok ? kin[i] : (KeyT)0; val[k] = ok ? vin[i] : 0u;
+        okmask |= (ok ? 1u : 0u) << k;
+    }
+    for (int shift = first_shift; shift < nbits; shift += 8) {
+        pmn_rs_tile_pass<KeyT, PMN_BS_WARPS, PMN_BS_ITEMS>(key, val, okmask, shift, skey, sval, cnt, nullptr, stmp);
+        if (shift + 8 < nbits) {
+#pragma unroll
+            for (int k = 0; k < PMN_BS_ITEMS; k++) { const int i = wbase + k * 32 + lane; if (i < n) { key[k] = skey[i]; val[k] = sval[i]; } }
+            __syncthreads();
+        }
+    }
+    for (int j = threadIdx.x; j < n; j += PMN_BS_THREADS) { kout[j] = skey[j]; vout[j] = sval[j]; }
 }
 
 struct RadixScratch {
@@ -234,21 +327,42 @@ struct RadixScratch {
     }
 };
 
+// the two kernels above use more than 48 KB of shared memory: opt in once per device and instantiation
+template <class KeyT>
+static inline int pmn_rs_prepare()
+{
+    static unsigned long long done = 0;         // bit per device; a race only repeats the calls
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (dev < 64 && ((done >> dev) & 1ull)) return 0;
+    if (cudaFuncSetAttribute(pmn_rs_scatter<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PMN_RS_SMEM_BYTES(KeyT, PMN_RS_WARPS, PMN_RS_ITEMS)) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(pmn_rs_block_sort<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PMN_RS_SMEM_BYTES(KeyT, PMN_BS_WARPS, PMN_BS_ITEMS)) != cudaSuccess) return -1;
+    if (dev < 64) done |= 1ull << dev;
+    return 0;
+}
+
 // Sorts bits [first_shift, nbits) of the keys, stable.  Ping-pongs between (k0,v0) and (k1,v1);
 // returns 0 if the result is in (k0,v0), 1 if in (k1,v1), negative on error.
-static inline int pmn_radix_sort(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint32_t *v1, int64_t n, int nbits,
+template <class KeyT>
+static inline int pmn_radix_sort(KeyT *k0, uint32_t *v0, KeyT *k1, uint32_t *v1, int64_t n, int nbits,
                                  RadixScratch &rs, cudaStream_t st, int *launches = nullptr, int first_shift = 0)
 {
-    if (n <= 1 || nbits <= 0) return 0;
+    if (n <= 1 || nbits <= first_shift) return 0;
+    if (pmn_rs_prepare<KeyT>()) return -1;
+    if (n <= PMN_BS_CAP) {
+        pmn_rs_block_sort<KeyT><<<1, PMN_BS_THREADS, PMN_RS_SMEM_BYTES(KeyT, PMN_BS_WARPS, PMN_BS_ITEMS), st>>>(k0, v0, k1, v1, (int)n, first_shift, nbits);
+        if (launches) *launches += 1;
+        return 1;
+    }
     if (rs.reserve(n)) return -1;
     int ntiles = (int)((n + PMN_RS_TILE - 1) / PMN_RS_TILE);
     int64_t cells = (int64_t)ntiles * PMN_RS_RADIX;
     int cur = 0;
     for (int shift = first_shift; shift < nbits; shift += 8) {       // first_shift > 0: the input is already ordered by the bits below it
-        uint64_t *ki = cur ? k1 : k0, *ko = cur ? k0 : k1; uint32_t *vi = cur ? v1 : v0, *vo = cur ? v0 : v1;
-        pmn_rs_hist<<<ntiles, PMN_RS_THREADS, 0, st>>>(ki, n, shift, rs.hist.as<uint32_t>(), ntiles);
+        KeyT *ki = cur ? k1 : k0, *ko = cur ? k0 : k1; uint32_t *vi = cur ? v1 : v0, *vo = cur ? v0 : v1;
+        pmn_rs_hist<KeyT><<<ntiles, PMN_RS_HIST_THREADS, 0, st>>>(ki, n, shift, rs.hist.as<uint32_t>(), ntiles);
         pmn_scan<uint32_t, OpAddU32, false>(rs.hist.as<uint32_t>(), rs.hist.as<uint32_t>(), cells, rs.spine.as<uint32_t>(), st);
-        pmn_rs_scatter<<<ntiles, PMN_RS_THREADS, 0, st>>>(ki, vi, ko, vo, n, shift, rs.hist.as<uint32_t>(), ntiles);
+        pmn_rs_scatter<KeyT><<<ntiles, PMN_RS_WARPS * 32, PMN_RS_SMEM_BYTES(KeyT, PMN_RS_WARPS, PMN_RS_ITEMS), st>>>(ki, vi, ko, vo, n, shift, rs.hist.as<uint32_t>(), ntiles);
         if (launches) *launches += 5;
         cur ^= 1;
     }

@@ -11,6 +11,7 @@
 #include <atomic>
 #include <map>
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -81,7 +82,7 @@ extern "C" int pmn_sched_create(int device, int workers, pmn_sched **out)
         if (!s->ctx.empty()) c->pool = s->ctx[0]->pool;
         s->ctx.push_back(c);
     }
-    for (int k = 0; k < std::min(workers, 4); k++) s->build_scratch.push_back(pmn_scratch_new());
+    for (int k = 0; k < std::min(workers, 8); k++) s->build_scratch.push_back(pmn_scratch_new());
     *out = s;
     return 0;
 }
@@ -128,7 +129,25 @@ static int sched_run(pmn_sched *s, int ng, const char *const *fasta, const size_
     std::atomic<int> next{0};
     s->err.clear(); s->err_code = 0;
 
-    const int MAX_LIVE_INDEXES = 4;
+    // Indexes alive at a time: as many as fit a quarter of the device memory (8.25 B/base each), between 2 and 16.  A batch
+    // over a handful of bacterial genomes (C2: 7 references of 41 MB) then builds all its indexes side by side at the start —
+    // wide, HBM-bound kernels that fill the GPU — and no pair ever waits for a build in the tail of the batch.
+    int MAX_LIVE_INDEXES = 4;
+    {
+        int64_t longest = 1;
+        for (int p = 0; p < np; p++) {
+            const int r = ref[p];
+            const int64_t nb = resident ? resident[r]->n : (int64_t)bytes[r];
+            longest = std::max(longest, nb);
+        }
+        size_t free_b = 0, total_b = 0;
+        cudaSetDevice(s->device);
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b) {
+            const size_t per = pmn_index_image_bytes(longest) + 1;
+            MAX_LIVE_INDEXES = (int)std::min<size_t>(16, std::max<size_t>(2, total_b / 4 / per));
+        }
+        if (const char *e = getenv("PMN_SCHED_LIVE_INDEXES")) MAX_LIVE_INDEXES = std::max(1, atoi(e));
+    }
     int live_indexes = 0;                      // guarded by s->bmu
     std::atomic<int> failed{0};                // some worker gave up: nobody may keep waiting for an index slot
     std::vector<int> first_refs;               // the first distinct references in processing order that have no index yet

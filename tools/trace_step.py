@@ -56,4 +56,63 @@ ra = collections.defaultdict(lambda: [0, 0.0])
 for e in rt: a = ra[e["name"]]; a[0] += 1; a[1] += e["dur"]
 print("host API:")
 for name, (c, d) in sorted(ra.items(), key=lambda kv: -kv[1][1])[:10]: print(f"  {name:40s} n={c:6d} total {d / 1e3:8.2f} ms  avg {d / c:7.1f} us")
+# per-stream (= per-worker) view: when each stream ran which pair phase, and how much of the span its stream was busy
+by = collections.defaultdict(list)
+for e in k: by[e.get("args", {}).get("stream", 0)].append(e)
+print("per stream: first kernel, last kernel, busy (union) ms, kernels; then the start times (ms) of k_sa_keys [I], k_seed [S], k_ex_stitch [X]")
+for sid, evs in sorted(by.items()):
+    evs.sort(key=lambda e: e["ts"])
+    marks = []
+    for e in evs:
+        nm = e["name"]
+        if nm.startswith("k_sa_keys"): marks.append(f"I{(e['ts'] - t0) / 1e3:.1f}")
+        elif nm.startswith("k_seed("): marks.append(f"S{(e['ts'] - t0) / 1e3:.1f}")
+        elif nm.startswith("k_ex_stitch"): marks.append(f"X{(e['ts'] + e['dur'] - t0) / 1e3:.1f}")
+    print(f"  stream {sid}: {(evs[0]['ts'] - t0) / 1e3:6.2f} .. {(evs[-1]['ts'] + evs[-1]['dur'] - t0) / 1e3:6.2f}  busy {union([(e['ts'], e['ts'] + e['dur']) for e in evs]) / 1e3:6.2f}  n={len(evs)}  " + " ".join(marks))
+# what one worker does between the end of its first stitch and its next seed launch
+sid0 = sorted(by)[0]
+evs = sorted(by[sid0], key=lambda e: e["ts"])
+xs = [e for e in evs if e["name"].startswith("k_ex_stitch")]
+if xs:
+    xa = xs[0]["ts"] + xs[0]["dur"]
+    nxt = [e for e in evs if e["name"].startswith("k_seed(") and e["ts"] > xa]
+    xb = nxt[0]["ts"] if nxt else xa + 3000
+    print(f"stream {sid0} between stitch end {(xa - t0) / 1e3:.2f} and next seed {(xb - t0) / 1e3:.2f} ms (GPU side):")
+    for e in sorted(k + mc, key=lambda e: e["ts"]):
+        if e.get("args", {}).get("stream", 0) == sid0 and xa - 50 <= e["ts"] <= xb:
+            print(f"   +{(e['ts'] - xa):8.1f} us  dur {e['dur']:7.1f}  {e['name'][:60]}  {e.get('args', {}).get('bytes', '')}")
+    # the host thread that launched the stitch
+    corr = xs[0].get("args", {}).get("correlation")
+    tid = None
+    for e in rt:
+        if e.get("args", {}).get("correlation") == corr: tid = e.get("tid")
+    print(f"host thread {tid} in the same window:")
+    for e in sorted(rt, key=lambda e: e["ts"]):
+        if e.get("tid") == tid and xa - 50 <= e["ts"] <= xb and (e["dur"] > 15 or e["name"] != "cudaLaunchKernel"):
+            print(f"   +{(e['ts'] - xa):8.1f} us  dur {e['dur']:7.1f}  {e['name']}")
+# inside one pair (second seed of the first stream .. its stitch end): where the stream sat idle
+seeds = [e for e in evs if e["name"].startswith("k_seed(")]
+if len(seeds) >= 2 and len(xs) >= 2:
+    a = seeds[1]["ts"]; xe = [e for e in xs if e["ts"] > a]
+    b = xe[0]["ts"] + xe[0]["dur"] if xe else a
+    act = sorted([e for e in k + mc if e.get("args", {}).get("stream", 0) in (sid0, sid0 + 1) and a <= e["ts"] <= b], key=lambda e: e["ts"])
+    busy_in = union([(e["ts"], e["ts"] + e["dur"]) for e in act])
+    print(f"pair window {(b - a) / 1e3:.2f} ms, stream busy {busy_in / 1e3:.2f} ms, {len(act)} activities; idle gaps > 20 us:")
+    end = act[0]["ts"] + act[0]["dur"]; prev = act[0]
+    for e in act[1:]:
+        if e["ts"] - end > 20: print(f"   gap {e['ts'] - end:7.1f} us at +{(end - a) / 1e3:6.3f} ms after {prev['name'][:36]:36s} before {e['name'][:36]}")
+        if e["ts"] + e["dur"] > end: end = e["ts"] + e["dur"]; prev = e
+print("host cores:", os.cpu_count())
+# concurrency histogram in 1 ms bins: kernels running, wide kernels running (time-weighted averages)
+nb = int((t1 - t0) / 1e3) + 1
+run = [0.0] * nb; wrun = [0.0] * nb
+wide_ids = set(id(e) for e in wide)
+for e in k:
+    a, b = e["ts"] - t0, e["ts"] + e["dur"] - t0
+    for bi in range(int(a / 1e3), min(nb - 1, int(b / 1e3)) + 1):
+        ov = max(0.0, min(b, (bi + 1) * 1e3) - max(a, bi * 1e3)) / 1e3
+        run[bi] += ov
+        if id(e) in wide_ids: wrun[bi] += ov
+print("avg kernels running per 1 ms bin:", " ".join(f"{x:.1f}" for x in run))
+print("avg wide kernels running per 1 ms bin:", " ".join(f"{x:.1f}" for x in wrun))
 os.remove(out)
