@@ -53,13 +53,13 @@ struct ExJob { int32_t endA, endB, dcnt, target; uint32_t doff; int32_t reached,
 // everything wave 1 needs to know about one forward alignment, written by k_ex_jobdesc so that a warp
 // fetches a job with one coalesced load instead of chasing match -> cluster -> synteny
 struct ExJobDesc { int64_t Abase, Bbase; int32_t eA, eB, tA, tB, g, dir, m_o, target; };   // m_o < 0: no job
-struct ExAlign { int32_t dirB, sA, sB, eA, eB, P, head, tail, ndelta, live, pad0, pad1; };   // P: reference position consumed through the last indel (sA-1 when none)
+struct __align__(16) ExAlign { int32_t dirB, sA, sB, eA, eB, P, head, tail, ndelta, live, pad0, pad1; };   // P: reference position consumed through the last indel (sA-1 when none)
 // a piece of an alignment's delta list: type 0 = `cnt` pool entries at `a` whose first value gets +-`b` added;
 // type 1 = the deltas of the wave-1 jobs [a, cnt) (all reached their targets), `b` = P before the range
 struct ExNode { int32_t type; uint32_t a; int32_t cnt, b, outoff, next, alslot, pad; };
 
 // everything the stitcher needs to know about a cluster in one 80-byte record
-struct ExCSum {
+struct __align__(16) ExCSum {
     int32_t sA0, sB0, len0;            // first match
     int32_t sAl, sBl, eAl, eBl;        // last match: start and end
     int32_t mfirst, nm, dir, anyfail;
@@ -69,7 +69,7 @@ struct ExCSum {
 
 // the backward extension of a cluster's first match, computed ahead of the stitcher (wave 2): search from the match
 // start towards the sequence starts, then the forced alignment over the region found
-struct ExBack { int32_t fA, fB, ext_i, ext_j; uint32_t doff; int32_t dcnt, asum, valid; };
+struct __align__(16) ExBack { int32_t fA, fB, ext_i, ext_j; uint32_t doff; int32_t dcnt, asum, valid; };
 
 struct ExShared {                       // everything the device code needs, passed by value
     PackedView R, QF, QR;
@@ -1325,17 +1325,23 @@ __global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32, 3) k_ex_wave2(ExShare
 
 // ------------------------------------------------------------------------------------ E3: stitch
 
+// The stitcher is one warp walking a dependent chain, so what it costs is the number of global-memory round trips per
+// cluster.  The first ST_AL_CACHE alignments of the synteny are mirrored in shared memory (the shadow test and the reverse
+// target search read all of them for every cluster that starts an alignment), and the cluster records are read a window of
+// 32 at a time (k_ex_stitch).
+#define ST_AL_CACHE 64
 struct Stitch {
-    const Eng *E; const ExSynteny *S; ExAlign *al; ExNode *nodes; int nAl, nNodes; bool fail;
+    const Eng *E; const ExSynteny *S; ExAlign *al; ExAlign *sal; ExNode *nodes; int nAl, nNodes; bool fail;
     ExAlign cur; int cur_slot;          // the alignment being grown lives in registers (identical on all lanes)
 };
 
+__device__ __forceinline__ ExAlign st_al(const Stitch &T, int i) { return i < ST_AL_CACHE ? T.sal[i] : T.al[i]; }
 __device__ __forceinline__ void st_flush(Stitch &T)
 {
-    if (T.cur_slot >= 0 && T.E->lane == 0) T.al[T.cur_slot] = T.cur;
+    if (T.cur_slot >= 0 && T.E->lane == 0) { T.al[T.cur_slot] = T.cur; if (T.cur_slot < ST_AL_CACHE) T.sal[T.cur_slot] = T.cur; }
     __syncwarp();
 }
-__device__ __forceinline__ void st_load(Stitch &T, int slot) { T.cur = T.al[slot]; T.cur_slot = slot; }
+__device__ __forceinline__ void st_load(Stitch &T, int slot) { T.cur = st_al(T, slot); T.cur_slot = slot; }
 
 // append a node to the alignment held in registers
 __device__ void cur_append(Stitch &T, int type, uint32_t a, int cnt_field, int b, int ndeltas)
@@ -1398,7 +1404,7 @@ __device__ int st_get_reverse_target(const Stitch &T, int ap, int dirB, int64_t 
         const int i = top - lane;
         bool valid = false, close = false; long long score = 0;
         if (i >= 0) {
-            const ExAlign a = T.al[i];
+            const ExAlign a = st_al(T, i);
             if (a.dirB == dirB && a.eA <= sA && a.eB <= sB) {
                 valid = true;
                 long long greater, lesser;
@@ -1424,7 +1430,7 @@ __device__ bool st_is_shadowed(const Stitch &T, const ExCSum &c)
     for (int top = T.nAl - 1; top >= 0; top -= 32) {
         const int i = top - lane;
         bool hit = false;
-        if (i >= 0) { const ExAlign a = T.al[i]; hit = a.dirB == c.dir && a.eA >= c.eAl && a.eB >= c.eBl && a.sA <= c.sA0 && a.sB <= c.sB0; }
+        if (i >= 0) { const ExAlign a = st_al(T, i); hit = a.dirB == c.dir && a.eA >= c.eAl && a.eB >= c.eBl && a.sA <= c.sA0 && a.sB <= c.sB0; }
         if (__ballot_sync(0xffffffffu, hit)) return true;
     }
     return false;
@@ -1439,7 +1445,7 @@ __device__ int st_extend_backward(Stitch &T, int tp, int dirB)
     const ExAlign a = T.cur;
     int overflow = 0; unsigned m_o = PMN_BACKWARD_SEARCH;
     int64_t targetA, targetB;
-    if (tp >= 0) { const ExAlign t = T.al[tp]; targetA = t.eA; targetB = t.eB; } else { targetA = 1; targetB = 1; m_o |= PMN_OPTIMAL_BIT; }
+    if (tp >= 0) { const ExAlign t = st_al(T, tp); targetA = t.eA; targetB = t.eB; } else { targetA = 1; targetB = 1; m_o |= PMN_OPTIMAL_BIT; }
     if (a.sA - targetA + 1 > PMN_MAX_ALIGNMENT_LENGTH) { targetA = a.sA - PMN_MAX_ALIGNMENT_LENGTH + 1; overflow = 1; m_o |= PMN_OPTIMAL_BIT; }
     if (a.sB - targetB + 1 > PMN_MAX_ALIGNMENT_LENGTH) { targetB = a.sB - PMN_MAX_ALIGNMENT_LENGTH + 1; overflow = 1; m_o |= PMN_OPTIMAL_BIT; }
     const PackedView &Q = dirB ? X.QR : X.QF; const int64_t Bbase = dirB ? S.BbaseR : S.BbaseF;
@@ -1468,18 +1474,48 @@ __global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32) k_ex_stitch(ExShared 
     const int s = blockIdx.x * EX_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     if (s >= X.nS) return;
     const ExSynteny S = X.syn[s];
-    Stitch T; T.E = &E; T.S = &S; T.al = X.al + S.alfirst; T.nodes = X.nodes + S.nodefirst; T.nAl = 0; T.nNodes = 0; T.fail = false; T.cur_slot = -1;
+    __shared__ __align__(16) ExCSum s_cs[EX_WARPS_PER_BLOCK][32];
+    __shared__ __align__(16) ExBack s_back[EX_WARPS_PER_BLOCK][32];
+    __shared__ __align__(16) ExAlign s_al[EX_WARPS_PER_BLOCK][ST_AL_CACHE];
+    __shared__ uint8_t s_fused[EX_WARPS_PER_BLOCK][32];
+    const int wib = threadIdx.x >> 5;
+    Stitch T; T.E = &E; T.S = &S; T.al = X.al + S.alfirst; T.sal = s_al[wib]; T.nodes = X.nodes + S.nodefirst; T.nAl = 0; T.nNodes = 0; T.fail = false; T.cur_slot = -1;
     const int c0 = S.cfirst, cend = S.cfirst + S.nC;
     int target_reached = 0, CurrCp = c0, PrevCp = c0, TargetCp = cend;
     bool logic_err = false;
+    int wbase = -64;                    // clusters [wbase, wbase + 32) are in the window; only this warp writes their fused flags
+#ifdef PMN_STITCH_TIMING            // cycles per section of the loop, printed by the host when the variable of the same name is set
+    long long tk_window = 0, tk_shadow = 0, tk_start = 0, tk_match = 0, tk_end = 0, n_cl = 0, n_start = 0, n_nf = 0, n_fwd = 0;
+    const long long tk0 = clock64();
+#define ST_TICK(acc) { const long long t2__ = clock64(); acc += t2__ - tk; tk = t2__; }
+#define ST_COUNT(x) x++
+#else
+#define ST_TICK(acc)
+#define ST_COUNT(x)
+#endif
     while (CurrCp < cend && !T.fail && !logic_err) {
-        const ExCSum c = X.cs[CurrCp];
-        const int was_fused = fused[CurrCp];
+#ifdef PMN_STITCH_TIMING
+        long long tk = clock64();
+        n_cl++;
+#endif
+        if (CurrCp < wbase || CurrCp >= wbase + 32) {
+            __syncwarp();
+            wbase = CurrCp;
+            const int k = CurrCp + lane;
+            if (k < cend) { s_cs[wib][lane] = X.cs[k]; s_back[wib][lane] = X.back[k]; s_fused[wib][lane] = fused[k]; }
+            __syncwarp();
+        }
+        const int wi = CurrCp - wbase;
+        const ExCSum c = s_cs[wib][wi];
+        const int was_fused = s_fused[wib][wi];
+        ST_TICK(tk_window)
         if (X.do_extend && !target_reached && was_fused) { CurrCp++; continue; }
         if (!target_reached && X.do_simplify) {
             st_flush(T);
-            if (st_is_shadowed(T, c)) {
-                if (lane == 0) fused[CurrCp] = 1;
+            const bool sh = st_is_shadowed(T, c);
+            ST_TICK(tk_shadow)
+            if (sh) {
+                if (lane == 0) { fused[CurrCp] = 1; s_fused[wib][wi] = 1; }
                 __syncwarp();
                 CurrCp = ++PrevCp; continue;
             }
@@ -1492,16 +1528,31 @@ __global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32) k_ex_stitch(ExShared 
         while (CurrMp < c.nm && !T.fail) {
             const int g = c.mfirst + CurrMp;
             int gA, gB, gL;                            // match g
-            if (CurrMp == 0) { gA = c.sA0; gB = c.sB0; gL = c.len0; } else { gA = X.mA[g]; gB = X.mB[g]; gL = X.mL[g]; }
+            // first and last match come with the cluster record: no global-memory round trip on the common path
+            if (CurrMp == 0) { gA = c.sA0; gB = c.sB0; gL = c.len0; }
+            else if (CurrMp == c.nm - 1) { gA = c.sAl; gB = c.sBl; gL = c.eAl - c.sAl + 1; }
+            else if (!positioned || allow_bulk) { gA = X.mA[g]; gB = X.mB[g]; gL = X.mL[g]; }
+            else { gA = gB = gL = 0; }          // positioned and not bulk: the values are not looked at
             if (!positioned) {
                 if (target_reached) {
                     if (T.cur.eA != gA || T.cur.eB != gB) {
-                        if (CurrMp >= c.nm - 1) { logic_err = true; break; }
-                        CurrMp++; continue;
+                        // the alignment was extended onto a later match of this cluster: the first one that starts where
+                        // it ends, 32 candidates per step
+                        int hit = -1;
+                        for (int b = CurrMp + 1; b < c.nm && hit < 0; b += 32) {
+                            const int k = b + lane;
+                            const unsigned bal = __ballot_sync(0xffffffffu, k < c.nm && X.mA[c.mfirst + k] == T.cur.eA && X.mB[c.mfirst + k] == T.cur.eB);
+                            if (bal) hit = b + __ffs(bal) - 1;
+                        }
+                        if (hit < 0) { logic_err = true; break; }
+                        CurrMp = hit; continue;
                     }
                     T.cur.eA += gL - 1; T.cur.eB += gL - 1;
                 } else {
                     if (T.nAl >= S.alcap) { logic_err = true; break; }
+#ifdef PMN_STITCH_TIMING
+                    const long long ts0 = clock64(); n_start++;
+#endif
                     st_flush(T);
                     T.cur_slot = T.nAl++;
                     T.cur.dirB = c.dir; T.cur.sA = gA; T.cur.sB = gB; T.cur.eA = gA + gL - 1; T.cur.eB = gB + gL - 1;
@@ -1510,11 +1561,11 @@ __global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32) k_ex_stitch(ExShared 
                         const int TargetAp = st_get_reverse_target(T, T.cur_slot, c.dir, gA, gB);
                         bool taken = false;
                         if (CurrMp == 0 && X.do_extend) {
-                            const ExBack b = X.back[CurrCp];
+                            const ExBack b = s_back[wib][wi];
                             if (b.valid) {
                                 // the window extendBackward would search: up to the target alignment's end, or the sequence starts
                                 int64_t tA = 1, tB = 1;
-                                if (TargetAp >= 0) { const ExAlign t = T.al[TargetAp]; tA = t.eA; tB = t.eB; }
+                                if (TargetAp >= 0) { const ExAlign t = st_al(T, TargetAp); tA = t.eA; tB = t.eB; }
                                 int64_t Nw = gA - tA + 1, Mw = gB - tB + 1;
                                 if (Nw > PMN_MAX_ALIGNMENT_LENGTH) Nw = PMN_MAX_ALIGNMENT_LENGTH;
                                 if (Mw > PMN_MAX_ALIGNMENT_LENGTH) Mw = PMN_MAX_ALIGNMENT_LENGTH;
@@ -1527,6 +1578,9 @@ __global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32) k_ex_stitch(ExShared 
                         }
                         if (!taken) st_extend_backward(T, TargetAp, c.dir);
                     }
+#ifdef PMN_STITCH_TIMING
+                    tk_start += clock64() - ts0;
+#endif
                 }
             }
             positioned = false;
@@ -1535,6 +1589,7 @@ __global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32) k_ex_stitch(ExShared 
                     int f, cnt, Pn;
                     if (CurrMp == 0 && !c.anyfail) { f = last; cnt = c.bulk_cnt; Pn = c.bulk_P; }
                     else {
+                        ST_COUNT(n_nf);
                         f = c.anyfail ? st_next_fail(X, g, last, lane) : last;
                         cnt = f > g ? (int)(X.dcnt_ex[f] - X.dcnt_ex[g]) : 0;
                         Pn = f > g ? range_last_P(X, g, f - 1, -1) : -1;
@@ -1553,8 +1608,12 @@ __global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32) k_ex_stitch(ExShared 
                         continue;
                     }
                 }
+                ST_COUNT(n_fwd);
                 target_reached = cur_extend_forward(T, c.dir, X.mA[g + 1], X.mB[g + 1], PMN_FORWARD_ALIGN, g);
             } else if (X.do_extend) {
+#ifdef PMN_STITCH_TIMING
+                const long long te0 = clock64();
+#endif
                 if (c.e_dcnt >= 0 && T.cur.eA == c.eAl && T.cur.eB == c.eBl) {
                     TargetCp = c.target;
                     target_reached = cur_apply_job(T, c.e_doff, c.e_dcnt, c.e_asum, c.endA, c.endB, c.e_reached);
@@ -1564,17 +1623,30 @@ __global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32) k_ex_stitch(ExShared 
                     if (TargetCp == cend) m_o |= PMN_OPTIMAL_BIT;
                     target_reached = cur_extend_forward(T, c.dir, targetA, targetB, m_o, -1);
                 }
+#ifdef PMN_STITCH_TIMING
+                tk_end += clock64() - te0;
+#endif
             }
             CurrMp++;
         }
+#ifdef PMN_STITCH_TIMING
+        tk_match += clock64() - tk;
+#endif
         if (TargetCp == cend) target_reached = 0;
-        if (lane == 0) fused[CurrCp] = 1;
+        if (lane == 0) { fused[CurrCp] = 1; s_fused[wib][wi] = 1; }
         __syncwarp();
         if (!target_reached) CurrCp = ++PrevCp; else CurrCp = TargetCp;
     }
     st_flush(T);
     if (lane == 0) {
         X.syn_nal[s] = T.nAl; X.syn_nal[X.nS + s] = T.nNodes;
+#ifdef PMN_STITCH_TIMING
+        atomicMax(X.counters + 16, (unsigned long long)(clock64() - tk0));
+        atomicAdd(X.counters + 17, (unsigned long long)tk_window); atomicAdd(X.counters + 18, (unsigned long long)tk_shadow);
+        atomicAdd(X.counters + 19, (unsigned long long)tk_start); atomicAdd(X.counters + 20, (unsigned long long)tk_match);
+        atomicAdd(X.counters + 21, (unsigned long long)tk_end); atomicAdd(X.counters + 22, (unsigned long long)n_cl);
+        atomicAdd(X.counters + 23, (unsigned long long)n_start); atomicAdd(X.counters + 24, (unsigned long long)n_nf); atomicAdd(X.counters + 25, (unsigned long long)n_fwd);
+#endif
         if (T.fail) atomicOr(X.counters + 4, (unsigned long long)EX_ERR_NODES);
         if (logic_err) atomicOr(X.counters + 4, (unsigned long long)EX_ERR_LOGIC);
     }
@@ -1892,7 +1964,8 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     launches++;
 
     // ---- E2/E3 storage
-    const int blocks1 = c->sm_count * 4;                      // 4 warps per block, 4 blocks per SM
+    static const int big_bps = getenv("PMN_BIG_BPS") ? std::max(1, atoi(getenv("PMN_BIG_BPS"))) : 4, tpj_bps = getenv("PMN_TPJ_BPS") ? std::min(TPJ_BLOCKS_PER_SM, std::max(1, atoi(getenv("PMN_TPJ_BPS")))) : TPJ_BLOCKS_PER_SM;
+    const int blocks1 = c->sm_count * big_bps;                // 4 warps per block
     const int blocks_st = (nS + EX_WARPS_PER_BLOCK - 1) / EX_WARPS_PER_BLOCK;
     const int nslots = std::max(blocks1, blocks_st) * EX_WARPS_PER_BLOCK;                 // warps that may run the wide fallback (global score rows)
     const int nslots_tb = nslots;                                                          // warps that keep a private traceback header
@@ -1900,13 +1973,13 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     const size_t arena_cap = (size_t)1 << 31;
     const size_t ncap_al = (size_t)nm, ncap_nodes = 3 * (size_t)nm + 8 * (size_t)nS;
     const size_t npad = ((size_t)np + 63) / 64 * 64;
-    const size_t l_bytes = npad * 3 + 8 * (size_t)nS + 64 + sizeof(ExBack) * npad;      // fused, anyfail, entered, syn_nal (2 x nS), back
+    const size_t l_bytes = npad * 3 + 8 * (size_t)nS + 64 + 16 + sizeof(ExBack) * npad;      // fused, anyfail, entered, syn_nal (2 x nS), back
     if (S.ex_i.ensure(sizeof(ExJob) * (size_t)nm) || S.ex_j.ensure(sizeof(ExAlign) * ncap_al) || S.ex_k.ensure(sizeof(ExNode) * ncap_nodes) ||
         S.ex_pool.ensure(4 * pool_cap) || S.ex_arena.ensure(arena_cap + 4096) || S.ex_scores.ensure(4 * (size_t)EX_ROWS * EX_WCAP * (size_t)nslots) ||
-        S.ex_tb.ensure((size_t)EX_TBW * (size_t)nslots_tb + 4096) || S.ex_counters.ensure(128) || S.ex_l.ensure(l_bytes) ||
+        S.ex_tb.ensure((size_t)EX_TBW * (size_t)nslots_tb + 4096) || S.ex_counters.ensure(256) || S.ex_l.ensure(l_bytes) ||
         S.ex_tbidx.ensure(8 * 3 * (size_t)(nm + 1)) || S.ex_a.ensure(8 * h.size() + 0) || S.cl_l.ensure(sizeof(ExCSum) * (size_t)np)) return -3;
     PMN_CUDA_OK(cudaMemsetAsync(S.ex_i.p, 0, sizeof(ExJob) * (size_t)nm, st));
-    PMN_CUDA_OK(cudaMemsetAsync(S.ex_counters.p, 0, 128, st));
+    PMN_CUDA_OK(cudaMemsetAsync(S.ex_counters.p, 0, 256, st));
     PMN_CUDA_OK(cudaMemsetAsync(S.ex_l.p, 0, l_bytes, st));
     ExShared X;
     X.R = ref->fwd(); X.QF = q->fwd(); X.QR = q->rev();
@@ -1921,7 +1994,7 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     uint8_t *anyfail = fused + npad;
     X.entered = anyfail + npad;
     X.syn_nal = (int32_t *)(X.entered + npad);
-    X.back = (ExBack *)(X.syn_nal + 2 * (size_t)nS + 16);
+    X.back = (ExBack *)(X.syn_nal + ((2 * (size_t)nS + 16 + 3) & ~(size_t)3));      // 16-byte aligned: the records are read with vector loads
     long long *pkey = S.ex_tbidx.as<long long>();                          // nm+1
     unsigned long long *markkey = (unsigned long long *)(pkey + (nm + 1));  // nm+1
     uint32_t *dcnt = (uint32_t *)(markkey + (nm + 1));                      // nm+1, then dcnt_ex nm+1
@@ -1934,7 +2007,7 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     ExJobDesc *descA = S.ex_desc.as<ExJobDesc>(), *descB = descA + np;
     X.descA = descA; X.descB = descB; X.overflow = (int32_t *)(descB + nm + 1); X.overflow2 = X.overflow + (nm + 1);
     // thread-per-job windows: (bin, rank) per match, bin counters and starts, the sorted list, per-warp scratch
-    const int blocks_tpj = c->sm_count * TPJ_BLOCKS_PER_SM;
+    const int blocks_tpj = c->sm_count * tpj_bps;
     const size_t tkey_bytes = 8 * (size_t)nm, tbin_bytes = 4 * (size_t)(2 * TPJ_BINS + 2);
     if (S.ex_tkey.ensure(tkey_bytes + tbin_bytes + 4 * (size_t)nm + 64) || S.ex_tscratch.ensure((size_t)blocks_tpj * 4 * TPJ_SLOT_BYTES)) return -3;
     X.tkey = S.ex_tkey.as<uint2>(); X.tbin = (uint32_t *)(X.tkey + nm); X.tsorted = (int32_t *)(X.tbin + 2 * TPJ_BINS + 2);
@@ -1975,7 +2048,7 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     PMN_CUDA_OK(cudaStreamWaitEvent(st, c->ev_join, 0));
     k_ex_wave1_big<<<b1, EX_WARPS_PER_BLOCK * 32, smem, st>>>(X, 1);
     PMN_CUDA_OK(cudaEventRecord(c->ev[9], st));
-    PMN_D2H(c, (unsigned long long *)S.pinned + 24, X.counters + 2, 8);      // cells evaluated by wave 1
+    PMN_D2H(c, (unsigned long long *)S.pinned + 40, X.counters + 2, 8);      // cells evaluated by wave 1
     k_ex_jobmeta<<<(unsigned)((nm + 1 + 255) / 256), 256, 0, st>>>(X.jobs, mcl, cl, pstart, ppos, nm, dcnt, pkey, anyfail);
     pmn_scan<uint32_t, OpAddU32, false>(dcnt, dcnt_ex, nm + 1, S.scan_tmp.as<uint32_t>(), st);
     pmn_scan<long long, OpMaxI64x, true>(pkey, pkey, nm, S.scan_tmp.as<long long>(), st);
@@ -1994,7 +2067,7 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     k_ex_list<<<1, 32, 0, st>>>(syn, X.syn_nal, nS, X.al, al_syn, al_slot, dcount, slot2out, X.counters + 8);
     launches++;
     unsigned long long *hc = (unsigned long long *)S.pinned;
-    PMN_D2H(c, hc, X.counters, 128);
+    PMN_D2H(c, hc, X.counters, 256);
     PMN_CUDA_OK(cudaStreamSynchronize(st));
     const unsigned long long errflags = hc[4];
     if (joblog) {
@@ -2009,7 +2082,12 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
         }
     }
     res->stats.dp_cells = (int64_t)hc[2]; res->stats.dp_jobs = (int64_t)hc[3];
-    res->stats.wave1_cells = (int64_t)hc[24];
+    res->stats.wave1_cells = (int64_t)hc[40];
+#ifdef PMN_STITCH_TIMING
+    if (getenv("PMN_STITCH_TIMING"))     // cycles of the slowest synteny warp per section (k_ex_stitch)
+        fprintf(stderr, "stitch cycles: total %llu window %llu shadow %llu start %llu match %llu end %llu clusters %llu starts %llu nextfail %llu fwd-calls %llu\n",
+                hc[16], hc[17], hc[18], hc[19], hc[20], hc[21], hc[22], hc[23], hc[24], hc[25]);
+#endif
     cudaEventElapsedTime(&res->stats.ms_wave1, c->ev[8], c->ev[9]);
     cudaEventElapsedTime(&res->stats.ms_stitch, c->ev[11], c->ev[10]);
     c->launches += launches; launches = 0;

@@ -277,50 +277,70 @@ __global__ void __launch_bounds__(256) k_round_apply(const uint32_t *__restrict_
     flags[k] = (g != (int32_t)p || (k + 1 < m && gsn[k + 1] == g)) ? 1u : 0u;
 }
 
-// ------------------------------------------------------------------------------------ LCP (Kasai-style)
+// ------------------------------------------------------------------------------------ LCP
 
-// Thread t walks text positions [t*C, (t+1)*C) in order and carries l-1 from one position
-// to the next (Kasai et al.): lcp(i+1, phi(i+1)) >= lcp(i, phi(i)) - 1.  Comparisons run
-// 32 bases per step on the packed text.
-#define PMN_LCP_CHUNK 16
-__global__ void __launch_bounds__(256) k_lcp(PackedView s, const uint32_t *__restrict__ sa, const int32_t *__restrict__ rank, int32_t *__restrict__ lcp)
+// The 16-mer keys in sorted order already hold most of the LCP array: two neighbours with different keys, both with 16
+// matchable bases, share clz(xor)/2 bases — no text access.  What is left are the members of groups of equal 16-mers (their
+// order is only final after the doubling rounds) and the suffixes that meet an X or the end inside their first 16 bases,
+// and their successors.  Those suffixes are flagged by text position; k_lcp_text runs Kasai's walk over the flagged
+// positions only.  HI(k) = the padded 16-mer of key k, REG(p) = slot p holds a suffix with 16 matchable bases.
+template <class KeyT>
+__global__ void __launch_bounds__(256) k_lcp_keys(const KeyT *__restrict__ keys, const uint32_t *__restrict__ vals, int64_t n,
+                                                 int32_t *__restrict__ lcp, uint8_t *__restrict__ unres)
 {
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t i0 = t * PMN_LCP_CHUNK;
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    auto hi = [&](int64_t q) -> uint32_t { return sizeof(KeyT) == 4 ? (uint32_t)keys[q] : (uint32_t)((uint64_t)keys[q] >> 6); };
+    auto reg = [&](int64_t q) -> bool { return sizeof(KeyT) == 4 ? (int64_t)vals[q] < n - 15 : ((uint64_t)keys[q] & 63) == CLS_REGULAR; };
+    const uint32_t h = hi(p);
+    bool open_ = !reg(p);
+    uint32_t hp = 0;
+    if (p > 0) { hp = hi(p - 1); open_ = open_ || !reg(p - 1) || hp == h; }
+    if (p + 1 < n && reg(p + 1) && hi(p + 1) == h) open_ = true;
+    if (open_) unres[vals[p]] = 1;
+    else lcp[p] = p > 0 ? (__clz((int)(hp ^ h)) >> 1) : 0;
+}
+
+#define PMN_LCP_CHUNK 16
+__global__ void __launch_bounds__(256) k_lcp_text(PackedView s, const uint32_t *__restrict__ sa, const int32_t *__restrict__ rank,
+                                                 const uint8_t *__restrict__ unres, int32_t *__restrict__ lcp)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i0 = t * PMN_LCP_CHUNK;
     if (i0 >= s.n) return;
-    int64_t i1 = i0 + PMN_LCP_CHUNK < s.n ? i0 + PMN_LCP_CHUNK : s.n;
-    int64_t l = 0;
+    const uint4 f = *reinterpret_cast<const uint4 *>(unres + i0);        // the array is padded to a multiple of 16
+    if (!(f.x | f.y | f.z | f.w)) return;
+    const uint32_t fw[4] = { f.x, f.y, f.z, f.w };
+    const int64_t i1 = i0 + PMN_LCP_CHUNK < s.n ? i0 + PMN_LCP_CHUNK : s.n;
+    int64_t l = 0, last = i0;
     for (int64_t i = i0; i < i1; i++) {
-        int32_t p = rank[i] - 1;
+        const int k = (int)(i - i0);
+        if (!((fw[k >> 2] >> (8 * (k & 3))) & 0xffu)) continue;
+        const int32_t p = rank[i] - 1;
+        l -= i - last; if (l < 0) l = 0;          // Kasai: lcp at position i is at least the one at `last` minus the distance
+        last = i;
         if (p == 0) { lcp[0] = 0; l = 0; continue; }
-        int64_t j = sa[p - 1];
-        l = pmn_lcp(s, i, s, j, l > 0 ? l - 1 : 0, s.n);
+        const int64_t j = sa[p - 1];
+        l = pmn_lcp(s, i, s, j, l, s.n);
         lcp[p] = (int32_t)l;
     }
 }
 
 // ------------------------------------------------------------------------------------ K-mer bucket table
 
-// bucket key of SA slot p: first K symbols, END padded with a, X padded with t — monotone in p
-__device__ __forceinline__ uint32_t bucket_key(const PackedView &s, int64_t pos, int K)
-{
-    int v = pmn_valid32(s, pos);
-    uint32_t km = (uint32_t)(pmn_window64(s.w, pos) >> (64 - 2 * K));
-    if (v >= K) return km;
-    uint32_t full = (K == 16) ? ~0u : ((1u << (2 * K)) - 1u);
-    uint32_t keep = v ? (full >> (2 * (K - v))) << (2 * (K - v)) : 0u;
-    if (pos + v >= s.n) return km & keep;
-    return (km & keep) | (full & ~keep);
-}
-
+// bucket key of SA slot p: first K symbols, END padded with a, X padded with t — monotone in p.  It is the top 2K bits of
+// the padded 16-mer the suffix was sorted by (same padding rule), and the doubling rounds only permute suffixes with equal
+// 16-mers, so the table is filled from the sorted keys right after the first sort.
 // table[k] = first slot whose bucket key is >= k, k = 0 .. 4^K   (table[4^K] = n)
-__global__ void __launch_bounds__(256) k_bucket_fill(PackedView s, const uint32_t *__restrict__ sa, int K, uint32_t *__restrict__ table)
+template <class KeyT>
+__global__ void __launch_bounds__(256) k_bucket_fill(const KeyT *__restrict__ keys, int64_t n, int K, uint32_t *__restrict__ table)
 {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p > s.n) return;
+    if (p > n) return;
+    auto bk = [&](int64_t q) -> int64_t { const uint32_t hi = sizeof(KeyT) == 4 ? (uint32_t)keys[q] : (uint32_t)((uint64_t)keys[q] >> 6); return (int64_t)(hi >> (32 - 2 * K)); };
     int64_t nb = 1ll << (2 * K);
-    int64_t cur = p < s.n ? (int64_t)bucket_key(s, sa[p], K) : nb;
-    int64_t prev = p > 0 ? (int64_t)bucket_key(s, sa[p - 1], K) : -1;
+    int64_t cur = p < n ? bk(p) : nb;
+    int64_t prev = p > 0 ? bk(p - 1) : -1;
     for (int64_t k = prev + 1; k <= cur; k++) table[k] = (uint32_t)p;
 }
 
@@ -370,7 +390,7 @@ int pmn_index_build_impl(pmn_ctx *c, const pmn_seq *ref, pmn_index *ix)
     if (S.k0.ensure(8 * (size_t)n) || S.k1.ensure(8 * (size_t)n) || S.v0.ensure(4 * (size_t)n) || S.v1.ensure(4 * (size_t)n)) return -3;
     if (S.gs.ensure(4 * (size_t)n) || S.rank.ensure(4 * (size_t)(n + 1)) || S.flags.ensure(4 * (size_t)n) ||
         S.list0.ensure(4 * (size_t)n) || S.list1.ensure(4 * (size_t)n) || S.gsn.ensure(4 * (size_t)n)) return -3;
-    if (S.scan_tmp.ensure(8 * pmn_scan_scratch_elems(n))) return -3;
+    if (S.scan_tmp.ensure(8 * pmn_scan_scratch_elems(n)) || S.codes.ensure((size_t)n + 64)) return -3;
     if (S.ensure_pinned(64)) return -3;
 
     PMN_CUDA_OK(cudaEventRecord(c->ev[0], st));
@@ -392,6 +412,18 @@ int pmn_index_build_impl(pmn_ctx *c, const pmn_seq *ref, pmn_index *ix)
     const uint32_t *svals = where ? S.v1.as<uint32_t>() : S.v0.as<uint32_t>();
     uint32_t *sa = ix->sa();
     PMN_CUDA_OK(cudaMemcpyAsync(sa, svals, 4 * (size_t)n, cudaMemcpyDeviceToDevice, st));
+    // what the sorted 16-mers already decide: the bucket table and the LCP entries between different 16-mers
+    const int K = ix->K;
+    uint8_t *unres = S.codes.as<uint8_t>();
+    PMN_CUDA_OK(cudaMemsetAsync(unres, 0, (size_t)n + 32, st));
+    if (class_first) {
+        k_bucket_fill<uint32_t><<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>((const uint32_t *)skeys, n, K, ix->table());
+        k_lcp_keys<uint32_t><<<gn, 256, 0, st>>>((const uint32_t *)skeys, svals, n, ix->lcp(), unres);
+    } else {
+        k_bucket_fill<uint64_t><<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>((const uint64_t *)skeys, n, K, ix->table());
+        k_lcp_keys<uint64_t><<<gn, 256, 0, st>>>((const uint64_t *)skeys, svals, n, ix->lcp(), unres);
+    }
+    launches += 2;
 
     // 2. groups of equal 16-mers -> ranks; slots that still share a group go on the work list
     int32_t *gs = S.gs.as<int32_t>(), *rank = S.rank.as<int32_t>(), *gsn = S.gsn.as<int32_t>();
@@ -434,12 +466,9 @@ int pmn_index_build_impl(pmn_ctx *c, const pmn_seq *ref, pmn_index *ix)
     }
     ix->rounds = rounds;
 
-    // 3. LCP in text order
-    k_lcp<<<(unsigned)(((n + PMN_LCP_CHUNK - 1) / PMN_LCP_CHUNK + 255) / 256), 256, 0, st>>>(T, sa, rank, ix->lcp()); launches++;
+    // 3. the LCP entries the keys left open, in text order
+    k_lcp_text<<<(unsigned)(((n + PMN_LCP_CHUNK - 1) / PMN_LCP_CHUNK + 255) / 256), 256, 0, st>>>(T, sa, rank, unres, ix->lcp()); launches++;
 
-    // 4. bucket table over the first K bases
-    const int K = ix->K;
-    k_bucket_fill<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(T, sa, K, ix->table()); launches++;
     k_index_header<<<1, 1, 0, st>>>((PmnIndexHeader *)ix->blob.p, n, K, rounds); launches++;
 
     PMN_CUDA_OK(cudaEventRecord(c->ev[1], st));

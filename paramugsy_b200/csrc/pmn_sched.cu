@@ -48,6 +48,7 @@ struct pmn_sched {
     std::vector<size_t> hiwater;
     std::mutex bmu;
     std::condition_variable bcv;
+    size_t total_mem = 0;               // device memory, read once (bounds the number of live indexes)
 };
 
 namespace {
@@ -83,6 +84,7 @@ extern "C" int pmn_sched_create(int device, int workers, pmn_sched **out)
         s->ctx.push_back(c);
     }
     for (int k = 0; k < std::min(workers, 8); k++) s->build_scratch.push_back(pmn_scratch_new());
+    { size_t free_b = 0, total_b = 0; if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) s->total_mem = total_b; else cudaGetLastError(); }
     *out = s;
     return 0;
 }
@@ -140,11 +142,9 @@ static int sched_run(pmn_sched *s, int ng, const char *const *fasta, const size_
             const int64_t nb = resident ? resident[r]->n : (int64_t)bytes[r];
             longest = std::max(longest, nb);
         }
-        size_t free_b = 0, total_b = 0;
-        cudaSetDevice(s->device);
-        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b) {
+        if (s->total_mem) {
             const size_t per = pmn_index_image_bytes(longest) + 1;
-            MAX_LIVE_INDEXES = (int)std::min<size_t>(16, std::max<size_t>(2, total_b / 4 / per));
+            MAX_LIVE_INDEXES = (int)std::min<size_t>(16, std::max<size_t>(2, s->total_mem / 4 / per));
         }
         if (const char *e = getenv("PMN_SCHED_LIVE_INDEXES")) MAX_LIVE_INDEXES = std::max(1, atoi(e));
     }

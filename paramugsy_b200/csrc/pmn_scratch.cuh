@@ -13,7 +13,7 @@ struct Scratch {
     // index build
     DevBuf gs, rank, flags, list0, list1, gsn;
     // seeding
-    DevBuf sections, stage, tile_cnt, tile_off, anchors;   // anchors: int4 (r, q, len, tag)
+    DevBuf sections, stage, tile_cnt, tile_off, seed_bits, anchors;   // anchors: int4 (r, q, len, tag)
     // clustering
     DevBuf cl_a, cl_b, cl_c, cl_d, cl_e, cl_f, cl_g, cl_h, cl_i, cl_j, cl_k, cl_l;
     DevBuf cl_matches, cl_recs, cl_counters;
@@ -23,7 +23,7 @@ struct Scratch {
     // every device buffer above, in a fixed order (the scheduler levels capacities between its workers; pmn_scratch_free)
     std::vector<DevBuf *> all()
     {
-        return { &rs.hist, &rs.spine, &k0, &k1, &v0, &v1, &scan_tmp, &codes, &gs, &rank, &flags, &list0, &list1, &gsn, &sections, &stage, &tile_cnt, &tile_off, &anchors,
+        return { &rs.hist, &rs.spine, &k0, &k1, &v0, &v1, &scan_tmp, &codes, &gs, &rank, &flags, &list0, &list1, &gsn, &sections, &stage, &tile_cnt, &tile_off, &seed_bits, &anchors,
                  &cl_a, &cl_b, &cl_c, &cl_d, &cl_e, &cl_f, &cl_g, &cl_h, &cl_i, &cl_j, &cl_k, &cl_l, &cl_matches, &cl_recs, &cl_counters,
                  &ex_a, &ex_b, &ex_c, &ex_d, &ex_e, &ex_f, &ex_g, &ex_h, &ex_i, &ex_j, &ex_k, &ex_l,
                  &ex_scores, &ex_tb, &ex_tbidx, &ex_pool, &ex_counters, &ex_arena, &ex_dbg, &ex_desc, &ex_tkey, &ex_tscratch };

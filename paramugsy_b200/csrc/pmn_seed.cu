@@ -14,6 +14,8 @@
 //      other neighbour is shorter and the LCP entry on the far side is shorter too
 //   5. left-maximality, then ordered compaction of the tile's anchors
 // Output order equals the oracle's sort order, so no sort follows.
+#include <algorithm>
+
 #include "pmn_scratch.cuh"
 
 #define SEED_THREADS 256
@@ -116,15 +118,58 @@ __device__ __forceinline__ bool ref_lt_query(const View32 &R, uint32_t s, const 
     }
 }
 
+// The general case of one position: lower bound of Q[g..] in [lo, hi), the better of its two neighbours, uniqueness from
+// the LCP array, left-maximality.
+__device__ __forceinline__ bool seed_general(const View32 &R32, const View32 &Q32, const uint32_t *__restrict__ sa, const int32_t *__restrict__ lcp,
+                                             uint32_t lo, uint32_t hi, uint32_t g, uint64_t qw, int vq, int minmatch, uint32_t *r_out, uint32_t *l_out)
+{
+    const uint32_t sa_n = R32.n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (ref_lt_query(R32, __ldg(sa + mid), Q32, g, qw, vq)) lo = mid + 1; else hi = mid;
+    }
+    const uint32_t p = lo;
+    const int64_t L1 = p > 0 ? (int64_t)lcp32(Q32, g, R32, __ldg(sa + p - 1)) : -1;
+    const int64_t L2 = p < sa_n ? (int64_t)lcp32(Q32, g, R32, __ldg(sa + p)) : -1;
+    const int64_t L = L1 > L2 ? L1 : L2;
+    if (L < minmatch || L1 == L2) return false;
+    bool unique; uint32_t r;
+    if (L2 > L1) { r = __ldg(sa + p); unique = !(p + 1 < sa_n && __ldg(lcp + p + 1) >= L); }
+    else { r = __ldg(sa + p - 1); unique = !(__ldg(lcp + p - 1) >= L); }
+    if (!unique) return false;
+    const int qb = base32(Q32, g - 1), rb = base32(R32, r - 1);
+    if (qb == rb && qb < 4) return false;
+    *r_out = r; *l_out = (uint32_t)L;
+    return true;
+}
+
+// Two passes per warp over its 256 positions.
+//   Pass 1, every position: the bucket of the first K bases.  Empty: nothing matches minmatch >= K bases.  One suffix s: it
+//   is the only candidate, every other suffix shares fewer than K bases with the query and with s, so the match is unique
+//   and the anchor exists iff it is left-maximal and >= minmatch long — the one-base test comes first and ends 98 % of the
+//   positions inside a longer match (it needs one reference word instead of the comparison loops).  Two or more suffixes:
+//   the position goes on the warp's list.
+//   Pass 2, the listed positions 32 at a time: binary search and both neighbours (seed_general).  In a random 5 Mbp genome
+//   one position in seven is listed, so the divergent loops run for a seventh of the warp iterations they ran for when every
+//   position took them.
+// Anchors are written at the slot of their position (stage is one int4 per position) with a bitmap per warp run; the gather
+// kernel compacts them in position order.
 __global__ void __launch_bounds__(SEED_THREADS) k_seed(PackedView R, const uint32_t *__restrict__ sa, const int32_t *__restrict__ lcp,
                                                       const uint32_t *__restrict__ table, int K, PackedView QF, PackedView QR,
                                                       const SeedSection *__restrict__ secs, int nsec, int minmatch,
-                                                      int4 *__restrict__ stage, uint32_t *__restrict__ tile_cnt, unsigned tile_base)
+                                                      int4 *__restrict__ stage, uint32_t *__restrict__ run_bits, uint32_t *__restrict__ tile_cnt, unsigned tile_base, unsigned ntiles)
 {
-    const int64_t tile = (int64_t)blockIdx.x + tile_base;     // blockIdx.x is local to the launched tile range
     __shared__ __align__(16) uint64_t s_w[SEED_WORDS];
     __shared__ __align__(16) uint32_t s_x[SEED_WORDS];
     __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint8_t s_list[SEED_THREADS / 32][SEED_ITERS * 32];
+    __shared__ uint32_t s_bits[SEED_THREADS / 32][SEED_ITERS];
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    uint32_t phase = 0;
+    // a block walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... (one tile per block unless the host caps the grid)
+    for (unsigned ltile = blockIdx.x; ltile < ntiles; ltile += gridDim.x, phase ^= 1u) {
+    const int64_t tile = (int64_t)ltile + tile_base;          // ltile is local to the launched tile range
 
     // which section does this tile belong to
     int lo_s = 0, hi_s = nsec - 1;
@@ -135,77 +180,99 @@ __global__ void __launch_bounds__(SEED_THREADS) k_seed(PackedView R, const uint3
     const int64_t g0 = sec.start + off0;
     const int64_t w0 = (g0 >> 5) & ~3ll;                                   // 16-byte aligned for text and mask
 
-    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
-    __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t bytes = SEED_WORDS * 8 + (Q.has_x ? SEED_WORDS * 4 : 0);
         mbar_expect_tx(&s_bar, bytes);
         tma_bulk_g2s(s_w, Q.w + w0, SEED_WORDS * 8, &s_bar);
         if (Q.has_x) tma_bulk_g2s(s_x, Q.xm + w0, SEED_WORDS * 4, &s_bar);
     }
-    mbar_wait(&s_bar, 0);
+    mbar_wait(&s_bar, phase);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt = pmn_lanemask_lt();
     const int first_need = minmatch < 32 ? minmatch : 32;
     const View32 R32 = view32(R), Q32 = view32(Q);
-    const uint32_t sa_n = R32.n;
-    // Warp w owns the SEED_ITERS * 32 consecutive positions [w * 256, (w + 1) * 256) of the tile and its own run of the
-    // staging area, so the anchors come out in position order without any block-wide step inside the loop.
-    int4 *wstage = stage + ((size_t)blockIdx.x * (SEED_THREADS / 32) + warp) * (SEED_ITERS * 32);
-    uint32_t wcount = 0;
+    const bool use_table = minmatch >= K;
+    // Warp w owns the SEED_ITERS * 32 consecutive positions [w * 256, (w + 1) * 256) of the tile and their slots of the staging area
+    const size_t run = (size_t)ltile * (SEED_THREADS / 32) + warp;
+    int4 *wstage = stage + run * (SEED_ITERS * 32);
+    const int64_t woff = off0 + warp * (SEED_ITERS * 32);
+    uint32_t nlist = 0, wcount = 0;
+    // the first window of position woff + idx, from the staged tile
+    auto window = [&](int idx, uint32_t &g, uint64_t &qw, int &vq) {
+        g = (uint32_t)(sec.start + woff + idx);
+        const uint32_t rel = g - (uint32_t)(w0 << 5); const int k = (int)(rel >> 5), sh = (int)(rel & 31);
+        const uint64_t a = s_w[k], b = s_w[k + 1];
+        qw = sh ? (a << (2 * sh)) | (b >> (64 - 2 * sh)) : a;
+        if (Q.has_x) { const uint32_t xw = __funnelshift_l(s_x[k + 1], s_x[k], sh); vq = xw ? __clz((int)xw) : 32; }
+        else { const uint32_t r = Q32.n - g; vq = r < 32u ? (int)r : 32; }
+    };
     for (int it = 0; it < SEED_ITERS; it++) {
-        const int64_t off = off0 + warp * (SEED_ITERS * 32) + it * 32 + lane;   // position inside the record
-        bool found = false; int4 out = make_int4(0, 0, 0, 0);
-        if (off < sec.npos) {
-            const uint32_t g = (uint32_t)(sec.start + off);
-            // first window from the staged tile
-            const uint32_t rel = g - (uint32_t)(w0 << 5); const int k = (int)(rel >> 5), sh = (int)(rel & 31);
-            const uint64_t a = s_w[k], b = s_w[k + 1];
-            const uint64_t qw = sh ? (a << (2 * sh)) | (b >> (64 - 2 * sh)) : a;
-            int vq;
-            if (Q.has_x) { const uint32_t xw = __funnelshift_l(s_x[k + 1], s_x[k], sh); vq = xw ? __clz((int)xw) : 32; }
-            else { const uint32_t r = Q32.n - g; vq = r < 32u ? (int)r : 32; }
+        const int idx = it * 32 + lane;
+        bool found = false, later = false;
+        if (woff + idx < sec.npos) {
+            uint32_t g; uint64_t qw; int vq;
+            window(idx, g, qw, vq);
             if (vq >= first_need) {
-                uint32_t lo, hi;
-                if (minmatch >= K) { const uint32_t km = (uint32_t)(qw >> (64 - 2 * K)); lo = __ldg(table + km); hi = __ldg(table + km + 1); }
-                else { lo = 0; hi = sa_n; }
-                if (lo < hi) {
-                    while (lo < hi) {
-                        const uint32_t mid = (lo + hi) >> 1;
-                        if (ref_lt_query(R32, __ldg(sa + mid), Q32, g, qw, vq)) lo = mid + 1; else hi = mid;
-                    }
-                    const uint32_t p = lo;
-                    const int64_t L1 = p > 0 ? (int64_t)lcp32(Q32, g, R32, __ldg(sa + p - 1)) : -1;
-                    const int64_t L2 = p < sa_n ? (int64_t)lcp32(Q32, g, R32, __ldg(sa + p)) : -1;
-                    const int64_t L = L1 > L2 ? L1 : L2;
-                    if (L >= minmatch && L1 != L2) {
-                        bool unique; uint32_t r;
-                        if (L2 > L1) { r = __ldg(sa + p); unique = !(p + 1 < sa_n && __ldg(lcp + p + 1) >= L); }
-                        else { r = __ldg(sa + p - 1); unique = !(__ldg(lcp + p - 1) >= L); }
-                        if (unique) {
-                            const int qb = base32(Q32, g - 1), rb = base32(R32, r - 1);
-                            if (!(qb == rb && qb < 4)) { found = true; out = make_int4((int)(r + 1), (int)(off + 1), (int)L, sec.tag); }
+                if (!use_table) later = true;
+                else {
+                    const uint32_t km = (uint32_t)(qw >> (64 - 2 * K));
+                    const uint32_t lo = __ldg(table + km), hi = __ldg(table + km + 1);
+                    if (hi - lo == 1u) {
+                        const uint32_t s = __ldg(sa + lo);
+                        const int qb = base32(Q32, g - 1), rb = base32(R32, s - 1);
+                        if (!(qb == rb && qb < 4)) {
+                            const uint32_t L = lcp32(Q32, g, R32, s);
+                            if (L >= (uint32_t)minmatch) { found = true; wstage[idx] = make_int4((int)(s + 1), (int)(woff + idx + 1), (int)L, sec.tag); }
                         }
-                    }
+                    } else if (hi > lo) later = true;
                 }
             }
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, found);
-        if (found) wstage[wcount + __popc(bal & lt)] = out;
+        const unsigned bal = __ballot_sync(0xffffffffu, found), bl = __ballot_sync(0xffffffffu, later);
+        if (lane == 0) s_bits[warp][it] = bal;
         wcount += __popc(bal);
+        if (later) s_list[warp][nlist + __popc(bl & lt)] = (uint8_t)idx;
+        nlist += __popc(bl);
     }
-    if (lane == 0) tile_cnt[(size_t)blockIdx.x * (SEED_THREADS / 32) + warp] = wcount;
+    __syncwarp();
+    for (uint32_t c = 0; c < nlist; c += 32) {
+        bool found = false; int idx = 0;
+        if (c + lane < nlist) {
+            idx = s_list[warp][c + lane];
+            uint32_t g; uint64_t qw; int vq;
+            window(idx, g, qw, vq);
+            uint32_t lo = 0, hi = R32.n;
+            if (use_table) { const uint32_t km = (uint32_t)(qw >> (64 - 2 * K)); lo = __ldg(table + km); hi = __ldg(table + km + 1); }
+            uint32_t r, L;
+            if (seed_general(R32, Q32, sa, lcp, lo, hi, g, qw, vq, minmatch, &r, &L)) {
+                found = true; wstage[idx] = make_int4((int)(r + 1), (int)(woff + idx + 1), (int)L, sec.tag);
+            }
+        }
+        if (found) atomicOr(&s_bits[warp][idx >> 5], 1u << (idx & 31));
+        wcount += __popc(__ballot_sync(0xffffffffu, found));
+    }
+    __syncwarp();
+    if (lane < SEED_ITERS) run_bits[run * SEED_ITERS + lane] = s_bits[warp][lane];
+    if (lane == 0) tile_cnt[run] = wcount;
+    __syncthreads();            // the staged tile is free for the next copy
+    }
 }
 
-// gather the per-tile runs into one contiguous, ordered anchor array
-__global__ void __launch_bounds__(256) k_seed_gather(const int4 *__restrict__ stage, const uint32_t *__restrict__ run_cnt,
+// gather the per-run anchors into one contiguous, ordered anchor array
+__global__ void __launch_bounds__(256) k_seed_gather(const int4 *__restrict__ stage, const uint32_t *__restrict__ run_bits,
                                                     const uint32_t *__restrict__ run_off, int64_t nruns, int4 *__restrict__ anchors)
 {
     const int64_t run = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // one warp per run of SEED_ITERS * 32 positions
     if (run >= nruns) return;
-    const uint32_t cnt = run_cnt[run], off = run_off[run];
-    for (uint32_t k = threadIdx.x & 31; k < cnt; k += 32) anchors[off + k] = stage[(size_t)run * (SEED_ITERS * 32) + k];
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = pmn_lanemask_lt();
+    uint32_t off = run_off[run];
+    for (int w = 0; w < SEED_ITERS; w++) {
+        const uint32_t word = run_bits[run * SEED_ITERS + w];
+        if ((word >> lane) & 1u) anchors[off + __popc(word & lt)] = stage[(size_t)run * (SEED_ITERS * 32) + w * 32 + lane];
+        off += __popc(word);
+    }
 }
 
 int pmn_seed_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_opts *o, int64_t *n_anchors, int part, int nparts)
@@ -240,13 +307,17 @@ int pmn_seed_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_o
     if (tiles == 0) return 0;
     const int64_t runs = tiles * (SEED_THREADS / 32);          // one anchor run per warp of a tile
     if (S.sections.ensure(sizeof(SeedSection) * secs.size()) || S.stage.ensure(sizeof(int4) * (size_t)tiles * SEED_TILE) ||
-        S.tile_cnt.ensure(4 * (size_t)runs) || S.tile_off.ensure(4 * (size_t)runs) ||
+        S.tile_cnt.ensure(4 * (size_t)runs) || S.tile_off.ensure(4 * (size_t)runs) || S.seed_bits.ensure(4 * SEED_ITERS * (size_t)runs) ||
         S.scan_tmp.ensure(8 * pmn_scan_scratch_elems(runs)) || S.ensure_pinned(64)) return -3;
     PMN_H2D(c, S.sections.p, secs.data(), sizeof(SeedSection) * secs.size());
     PMN_CUDA_OK(cudaEventRecord(c->ev[6], st));
-    k_seed<<<(unsigned)tiles, SEED_THREADS, 0, st>>>(ix->seq->fwd(), ix->sa(), ix->lcp(), ix->table(), ix->K,
+    // one block per tile by default (the hardware deals tiles to SMs as they free up); PMN_SEED_BPS = k caps the grid at k
+    // blocks per SM that stride over the tiles (experiment: leave thread slots to the kernels of other pairs)
+    static const int seed_bps = getenv("PMN_SEED_BPS") ? atoi(getenv("PMN_SEED_BPS")) : 0;
+    const unsigned seed_grid = seed_bps > 0 ? (unsigned)std::min<int64_t>(tiles, (int64_t)c->sm_count * seed_bps) : (unsigned)tiles;
+    k_seed<<<seed_grid, SEED_THREADS, 0, st>>>(ix->seq->fwd(), ix->sa(), ix->lcp(), ix->table(), ix->K,
                                                      q->fwd(), q->rev(), S.sections.as<SeedSection>(), (int)secs.size(), o->minmatch,
-                                                     S.stage.as<int4>(), S.tile_cnt.as<uint32_t>(), (unsigned)t_lo);
+                                                     S.stage.as<int4>(), S.seed_bits.as<uint32_t>(), S.tile_cnt.as<uint32_t>(), (unsigned)t_lo, (unsigned)tiles);
     PMN_CUDA_OK(cudaEventRecord(c->ev[7], st));
     pmn_scan<uint32_t, OpAddU32, false>(S.tile_cnt.as<uint32_t>(), S.tile_off.as<uint32_t>(), runs, S.scan_tmp.as<uint32_t>(), st);
     uint32_t *tail = (uint32_t *)S.pinned;
@@ -257,7 +328,7 @@ int pmn_seed_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_o
     c->launches += 4;
     if (total > 0) {
         if (S.anchors.ensure(sizeof(int4) * (size_t)total)) return -3;
-        k_seed_gather<<<(unsigned)((runs + 7) / 8), 256, 0, st>>>(S.stage.as<int4>(), S.tile_cnt.as<uint32_t>(), S.tile_off.as<uint32_t>(), runs, S.anchors.as<int4>());
+        k_seed_gather<<<(unsigned)((runs + 7) / 8), 256, 0, st>>>(S.stage.as<int4>(), S.seed_bits.as<uint32_t>(), S.tile_off.as<uint32_t>(), runs, S.anchors.as<int4>());
         c->launches += 1;
     }
     PMN_CUDA_OK(cudaGetLastError());
