@@ -83,6 +83,7 @@ struct ExShared {                       // everything the device code needs, pas
     int32_t *gscore; uint8_t *tbpriv;   // per warp slot: EX_ROWS*EX_WCAP ints, EX_TBW bytes
     unsigned long long *counters;       // [0] pool cursor [1] arena cursor [2] cells [3] engine calls [4] error flags [5] job cursor A [6] job cursor B
     int breaklen, do_extend, do_simplify;
+    int tpj_cells;                      // largest N x M window the thread-per-job kernel takes (larger ones: one warp each)
     int32_t *syn_nal;                   // alignments produced per synteny (then: nodes used per synteny at [nS + s])
     const struct ExCSum *cs;            // per cluster summary for the stitcher
     const uint32_t *dcnt_ex;            // exclusive prefix of jobs[].dcnt, nM + 1 entries
@@ -859,9 +860,9 @@ __device__ __forceinline__ int run_mismatches(const PackedView &R, int64_t a, co
 #define TPJ_NEG (-(1 << 28))
 #define TPJ_BLOCKS_PER_SM 4
 
-__device__ __forceinline__ bool tpj_fits(int N, int M, int breaklen)
+__device__ __forceinline__ bool tpj_fits(int N, int M, int breaklen, int maxcells)
 {
-    return N >= 1 && M >= 1 && N <= TPJ_MAXDIM && M <= TPJ_MAXDIM && N + M <= breaklen && ((M + TPJ_W - 1) / TPJ_W) * (N + 1) <= TPJ_TB_WORDS;
+    return N >= 1 && M >= 1 && N <= TPJ_MAXDIM && M <= TPJ_MAXDIM && N * M <= maxcells && N + M <= breaklen && ((M + TPJ_W - 1) / TPJ_W) * (N + 1) <= TPJ_TB_WORDS;
 }
 // large windows first: (strips descending, rows descending)
 __device__ __forceinline__ int tpj_bin(int N, int M) { return (13 - (M + TPJ_W - 1) / TPJ_W) * TPJ_NB + (TPJ_NB - 1 - (N >> 2)); }
@@ -896,7 +897,7 @@ __global__ void __launch_bounds__(256) k_ex_jobdesc(ExShared X, ExJobDesc *__res
             atomicAdd(X.counters + 3, 1ull);
             d.m_o = -1;
         }
-        else if (tpj_fits(n, m, X.breaklen)) {
+        else if (tpj_fits(n, m, X.breaklen, X.tpj_cells)) {
             const int bin = tpj_bin(n, m);
             X.tkey[g] = make_uint2((unsigned)bin, atomicAdd(X.tbin + bin, 1u));
         }
@@ -1509,7 +1510,9 @@ __global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32) k_ex_stitch(ExShared 
         const ExCSum c = s_cs[wib][wi];
         const int was_fused = s_fused[wib][wi];
         ST_TICK(tk_window)
-        if (X.do_extend && !target_reached && was_fused) { CurrCp++; continue; }
+        // A fused cluster is stepped over.  Flags are never cleared, so the restart point moves along with it: every later
+        // restart would walk over the same fused clusters again and end up where this one does.
+        if (X.do_extend && !target_reached && was_fused) { CurrCp++; PrevCp = CurrCp; continue; }
         if (!target_reached && X.do_simplify) {
             st_flush(T);
             const bool sh = st_is_shadowed(T, c);
@@ -1990,6 +1993,7 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     X.gscore = S.ex_scores.as<int32_t>(); X.tbpriv = S.ex_tb.as<uint8_t>();
     X.counters = S.ex_counters.as<unsigned long long>();
     X.breaklen = o->breaklen; X.do_extend = o->do_extend; X.do_simplify = o->do_simplify;
+    { static const int cells = getenv("PMN_TPJ_CELLS") ? atoi(getenv("PMN_TPJ_CELLS")) : TPJ_MAXDIM * TPJ_MAXDIM; X.tpj_cells = cells; }
     uint8_t *fused = S.ex_l.as<uint8_t>();
     uint8_t *anyfail = fused + npad;
     X.entered = anyfail + npad;
