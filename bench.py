@@ -205,12 +205,17 @@ def run_gpu(args):
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
+        ranks_ms = [round(ms / steps, 2)]
         if world > 1:
+            allms = torch.zeros(world, device="cuda", dtype=torch.float64); allms[rank] = ms
+            dist.all_reduce(allms)                              # every rank's own time (diagnostic: stragglers)
+            ranks_ms = [round(float(x) / steps, 2) for x in allms.tolist()]
             t = torch.tensor([ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         c1 = sched.counters()
         d = {k: c1[k] - c0[k] for k in c0}; d["walls"] = [round(w, 2) for w in walls]; d["allocs"] = lib.alloc_count() - a0
+        d["ranks_ms"] = ranks_ms
         return ms, d
 
     # ---- resident arm
@@ -269,6 +274,14 @@ def run_gpu(args):
                      "algorithmic_bytes_per_launch": b_seed / max(1, len(detail)), "launch_ms": seed_kernel_ms / max(1, len(detail)),
                      "share_of_step": seed_kernel_ms / (sum(stage_ms.values()) or 1)}
         roof_seed["frac"] = roof_seed["achieved"] / hbm_peak if roof_seed["achieved"] else None
+        # SURVEY §8d counts a full binary search per position (12 B x log2 n); the K-mer table replaces it, so the kernel
+        # moves far fewer bytes than that model (hence frac > 1 at 5 Mbp, where the index is also L2-resident).  The bytes the
+        # table path itself needs per (position, strand): table 8 + suffix 4 + reference word 8 + query 0.375.
+        b_seed_table = sum(2 * st["qry_bases"] * 20.375 + 16 * st["anchors"] for _, _, st, _ in detail)
+        roof_seed["table_path"] = {"bytes_per_launch": b_seed_table / max(1, len(detail)),
+                                   "achieved": b_seed_table / (seed_kernel_ms * 1e-3) / 1e9 if seed_kernel_ms else None,
+                                   "frac": b_seed_table / (seed_kernel_ms * 1e-3) / 1e9 / hbm_peak if seed_kernel_ms else None,
+                                   "what": "bytes the K-mer-table path needs (20.375 B per position and strand), same launch time"}
         gcups = wave1_cells / (wave1_ms * 1e-3) / 1e9 if wave1_ms else None
         roof_ext = {"kernel": "k_ex_wave1_tpj + k_ex_wave1_big (side by side on two streams)", "bound": "int32", "traffic": None, "achieved": gcups * 16 if gcups else None, "peak": int32_gops, "unit": "Gop/s",
                     "peak_source": "measured (pmn_measure_int32_peak, add+max chains)", "gcups": gcups, "ops_per_cell": 16,
@@ -306,6 +319,7 @@ def run_gpu(args):
                            "h2d_bytes_per_step": cnt_wrk["h2d_bytes"] // args.steps, "d2h_bytes_per_step": cnt_wrk["d2h_bytes"] // args.steps} if ms_wrk else None,
             "gpu_launches": cnt_res["launches"], "step_wall_ms": {"resident": cnt_res["walls"], "e2e": cnt_e2e["walls"], "e2e_worker": cnt_wrk["walls"] if cnt_wrk else None},
             "device_allocations_in_timed_region": {"resident": cnt_res["allocs"], "e2e": cnt_e2e["allocs"]},
+            "ms_per_step_by_rank": {"resident": cnt_res["ranks_ms"], "e2e": cnt_e2e["ranks_ms"]}, "host_cores": os.cpu_count(),
             "clocks": clocks,
             "stage_ms_per_step": stage_ms,
             "host_wall_ms_per_step": {"index_build": sum({a: st["wall_ms_index"] for a, _, st, _ in detail}.values()),

@@ -86,6 +86,21 @@ def c_opts_l12_c30():
     return (*_pair(20_000, 0.12, 231), {"minmatch": 12, "mincluster": 30, "maxgap": 120, "breaklen": 100})
 
 
+def c_opts_l6():
+    # minmatch below the K of the k-mer table (K >= 8): no bucket lookup, every position takes the full binary search
+    return (*_pair(2_500, 0.04, 241), {"minmatch": 6, "mincluster": 20})
+
+
+def c_x_runs_30k():
+    # a text with N runs, IUPAC codes and three records above one sort tile: 64-bit keys with class bits in the tiled sort,
+    # LCP entries next to X-limited suffixes, one-suffix buckets that end on an X
+    a = synth.random_genome(14_000, 251); b = synth.random_genome(9_000, 252); c = synth.random_genome(6_000, 253)
+    ref = synth.fasta("r.1", a[:5_000] + b"N" * 300 + a[5_000:9_000] + b"RYSWKM" + a[9_000:]) + synth.fasta("r.2", b + b"N" * 17 + c[:2_000]) + synth.fasta("r.3", c)
+    qa = synth.mutate(a, 0.03, 254); qb = synth.mutate(b, 0.02, 255); qc = synth.mutate(c, 0.05, 256)
+    qry = synth.fasta("q.1", qb[:4_000] + b"NNNN" + qb[4_000:]) + synth.fasta("q.2", synth.invert(qa, 1, 2_000, 257) + b"N" * 50 + qc)
+    return ref, qry, {}
+
+
 def c_opts_forward_only_noextend():
     return (*_pair(20_000, 0.04, 241, inv=1, inv_len=2_000), {"do_reverse": 0, "do_extend": 0})
 
@@ -125,5 +140,5 @@ def c_gap_ladder():
 
 CASES = {f.__name__[2:]: f for f in (
     c_1k_99, c_10k_95, c_100k_98_inv, c_100k_90, c_60k_85, c_identical, c_unrelated, c_short_and_empty, c_n_runs,
-    c_multirecord, c_repeats, c_tandem_low_complexity, c_big_indels, c_opts_l12_c30, c_opts_forward_only_noextend,
+    c_multirecord, c_repeats, c_tandem_low_complexity, c_big_indels, c_opts_l12_c30, c_opts_l6, c_x_runs_30k, c_opts_forward_only_noextend,
     c_opts_nosimplify_diag, c_self, c_trim_everything, c_wide_band_b500, c_gap_ladder)}
