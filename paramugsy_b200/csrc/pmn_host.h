@@ -88,6 +88,8 @@ struct pmn_ctx {
 int pmn_pool_get(pmn_ctx *c, DevBuf &b, size_t bytes);
 void pmn_pool_put(pmn_ctx *c, DevBuf &b);
 
+void pmn_apply_device_sched(int workers);     // whether host threads spin or yield while they wait for the device (pmn_api.cu)
+
 // stage entry points (defined in the .cu files)
 int pmn_fasta_to_device(pmn_ctx *c, pmn_seq *s, const char *txt, size_t nb, const std::vector<int64_t> &header_pos);
 int pmn_index_build_impl(pmn_ctx *c, const pmn_seq *ref, pmn_index *ix);

@@ -85,6 +85,7 @@ extern "C" int pmn_sched_create(int device, int workers, pmn_sched **out)
     }
     for (int k = 0; k < std::min(workers, 8); k++) s->build_scratch.push_back(pmn_scratch_new());
     { size_t free_b = 0, total_b = 0; if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) s->total_mem = total_b; else cudaGetLastError(); }
+    pmn_apply_device_sched(workers);
     *out = s;
     return 0;
 }
