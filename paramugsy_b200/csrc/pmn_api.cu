@@ -417,24 +417,17 @@ extern "C" int pmn_index_copy_sa(const pmn_index *ix, int32_t *sa_out, int32_t *
 // .delta grammar exactly as the reference parses it: lib/profiles_lib/m_delta.cc:72-92 (two
 // header lines), :154-162 ('>' line), :177-185 (seven ints), :187-196 (deltas up to "0");
 // lib/profiles/m_delta.ml:76-79,91 needs single spaces and no trailing blanks.
-static inline char *fmt_int(char *p, long long v)
+static void write_delta_text(pmn_ctx *c, const pmn_seq *ref, const pmn_seq *qry, const char *ref_path, const char *qry_path, pmn_result *r)
 {
-    if (v < 0) { *p++ = '-'; v = -v; }
-    char tmp[24]; int n = 0;
-    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
-    while (n) *p++ = tmp[--n];
-    return p;
-}
-
-static void write_delta_text(const pmn_seq *ref, const pmn_seq *qry, const char *ref_path, const char *qry_path, pmn_result *r)
-{
-    std::string &t = r->delta;
+    // formatted in the context's staging buffer (worst-case size, its pages are touched once in the life of the context), then
+    // copied into a string of the exact size
+    std::vector<char> &t = c->text_buf;
     const size_t na = r->al_rows.size() / 10;
     size_t idlen = 0;
     for (auto &x : ref->ids) idlen = std::max(idlen, x.size());
     for (auto &x : qry->ids) idlen = std::max(idlen, x.size());
     const size_t head = strlen(ref_path) + strlen(qry_path) + 16;
-    t.resize(head + na * (2 * idlen + 64 + 7 * 21 + 4) + r->al_deltas.size() * 12 + 16);
+    { const size_t need = head + na * (2 * idlen + 64 + 7 * 21 + 4) + r->al_deltas.size() * 12 + 16; if (t.size() < need) t.resize(need + need / 4); }
     char *p = &t[0];
     p += sprintf(p, "%s %s\nNUCMER\n", ref_path, qry_path);
     int64_t prev_r = -1, prev_q = -1, aligned = 0;
@@ -445,18 +438,18 @@ static void write_delta_text(const pmn_seq *ref, const pmn_seq *qry, const char 
             const std::string &ri = ref->ids[(size_t)a[0]], &qi = qry->ids[(size_t)a[1]];
             memcpy(p, ri.data(), ri.size()); p += ri.size(); *p++ = ' ';
             memcpy(p, qi.data(), qi.size()); p += qi.size(); *p++ = ' ';
-            p = fmt_int(p, ref->len[(size_t)a[0]]); *p++ = ' '; p = fmt_int(p, qry->len[(size_t)a[1]]); *p++ = '\n';
+            p = pmn_fmt_int(p, ref->len[(size_t)a[0]]); *p++ = ' '; p = pmn_fmt_int(p, qry->len[(size_t)a[1]]); *p++ = '\n';
             prev_r = a[0]; prev_q = a[1];
         }
         int64_t sB = a[5], eB = a[6]; const int64_t lenB = qry->len[(size_t)a[1]];
         if (a[2]) { sB = lenB - sB + 1; eB = lenB - eB + 1; }
-        p = fmt_int(p, a[3]); *p++ = ' '; p = fmt_int(p, a[4]); *p++ = ' '; p = fmt_int(p, sB); *p++ = ' '; p = fmt_int(p, eB); *p++ = ' ';
-        p = fmt_int(p, a[7]); *p++ = ' '; p = fmt_int(p, a[8]); *p++ = ' '; p = fmt_int(p, a[9]); *p++ = '\n';
-        for (int64_t d = r->al_doff[k]; d < r->al_doff[k + 1]; d++) { p = fmt_int(p, r->al_deltas[(size_t)d]); *p++ = '\n'; }
+        p = pmn_fmt_int(p, a[3]); *p++ = ' '; p = pmn_fmt_int(p, a[4]); *p++ = ' '; p = pmn_fmt_int(p, sB); *p++ = ' '; p = pmn_fmt_int(p, eB); *p++ = ' ';
+        p = pmn_fmt_int(p, a[7]); *p++ = ' '; p = pmn_fmt_int(p, a[8]); *p++ = ' '; p = pmn_fmt_int(p, a[9]); *p++ = '\n';
+        for (int64_t d = r->al_doff[k]; d < r->al_doff[k + 1]; d++) { p = pmn_fmt_int(p, r->al_deltas[(size_t)d]); *p++ = '\n'; }
         *p++ = '0'; *p++ = '\n';
         aligned += a[4] - a[3] + 1;
     }
-    t.resize((size_t)(p - &t[0]));
+    r->delta.assign(&t[0], (size_t)(p - &t[0]));
     r->stats.alignments = (int64_t)na;
     r->stats.aligned_ref_bases = aligned;
 }
@@ -521,7 +514,7 @@ static int align_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *qry, const
     if (!given_anchors && n_given != 0 && qry->n >= o.minmatch) { if (cudaEventElapsedTime(&r->stats.ms_seed_kernel, c->ev[6], c->ev[7]) != cudaSuccess) { cudaGetLastError(); r->stats.ms_seed_kernel = 0; } }
     c->pairs++;
     const double t1 = now_ms();
-    write_delta_text(ix->seq, qry, ref_path ? ref_path : "ref", qry_path ? qry_path : "qry", r.get());
+    write_delta_text(c, ix->seq, qry, ref_path ? ref_path : "ref", qry_path ? qry_path : "qry", r.get());
     c->launches -= pmn_tls_launches_saved; pmn_tls_launches_saved = 0;
     r->stats.wall_ms_text = (float)(now_ms() - t1);
     if (o.post) {

@@ -1,5 +1,6 @@
 // pmn_host.h — host-side objects behind the C ABI of include/pmnucmer.h.
 #pragma once
+#include <cstring>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -78,6 +79,7 @@ struct pmn_ctx {
                                         // the worker contexts of one pmn_sched share one pool (a genome packed or an index
                                         // built by one worker is freed by whichever worker finishes its last pair)
     bool smem_attr_set = false;         // opt-in dynamic shared memory of the extension kernels (per device)
+    std::vector<char> text_buf;         // grow-only staging of the .delta formatter (worst-case size, touched once)
 };
 
 // host<->device copies on the context's stream, counted for bench.py's e2e byte figures
@@ -87,6 +89,29 @@ struct pmn_ctx {
 // take a buffer of at least `bytes` from the context's pool (smallest that fits), else allocate
 int pmn_pool_get(pmn_ctx *c, DevBuf &b, size_t bytes);
 void pmn_pool_put(pmn_ctx *c, DevBuf &b);
+
+// ---- decimal formatting of the .delta writers (pmn_api.cu, pmn_post.cu)
+static const char PMN_DIGITS2[201] =
+    "00010203040506070809101112131415161718192021222324252627282930313233343536373839404142434445464748495051525354555657585960616263646566676869707172737475767778798081828384858687888990919293949596979899";
+// most numbers of a .delta are deltas of one to three digits: two digits per step from a table, 32-bit arithmetic
+static inline char *pmn_fmt_int(char *p, long long v)
+{
+    if (v < 0) { *p++ = '-'; v = -v; }
+    if (v < 10000) {
+        const unsigned u = (unsigned)v;
+        if (u < 10) { *p++ = (char)('0' + u); return p; }
+        if (u < 100) { memcpy(p, PMN_DIGITS2 + 2 * u, 2); return p + 2; }
+        const unsigned hi = u / 100, lo = u % 100;
+        if (u < 1000) { *p++ = (char)('0' + hi); memcpy(p, PMN_DIGITS2 + 2 * lo, 2); return p + 2; }
+        memcpy(p, PMN_DIGITS2 + 2 * hi, 2); memcpy(p + 2, PMN_DIGITS2 + 2 * lo, 2); return p + 4;
+    }
+    char tmp[24]; int n = 0;
+    unsigned long long w = (unsigned long long)v;
+    while (w >= 100) { const unsigned lo = (unsigned)(w % 100); w /= 100; tmp[n++] = PMN_DIGITS2[2 * lo + 1]; tmp[n++] = PMN_DIGITS2[2 * lo]; }
+    if (w >= 10) { tmp[n++] = PMN_DIGITS2[2 * w + 1]; tmp[n++] = PMN_DIGITS2[2 * w]; } else tmp[n++] = (char)('0' + w);
+    while (n) *p++ = tmp[--n];
+    return p;
+}
 
 void pmn_apply_device_sched(int workers);     // whether host threads spin or yield while they wait for the device (pmn_api.cu)
 

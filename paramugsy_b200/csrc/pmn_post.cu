@@ -89,14 +89,7 @@ static int parse_delta(const char *t, size_t n, PDelta &d)
     return 0;
 }
 
-static inline char *put_ll(char *p, long long v)
-{
-    if (v < 0) { *p++ = '-'; v = -v; }
-    char tmp[24]; int n = 0;
-    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
-    while (n) *p++ = tmp[--n];
-    return p;
-}
+static inline char *put_ll(char *p, long long v) { return pmn_fmt_int(p, v); }
 
 }  // namespace
 
