@@ -93,20 +93,25 @@ void pmn_pool_put(pmn_ctx *c, DevBuf &b);
 // ---- decimal formatting of the .delta writers (pmn_api.cu, pmn_post.cu)
 static const char PMN_DIGITS2[201] =
     "00010203040506070809101112131415161718192021222324252627282930313233343536373839404142434445464748495051525354555657585960616263646566676869707172737475767778798081828384858687888990919293949596979899";
-// most numbers of a .delta are deltas of one to three digits: two digits per step from a table, 32-bit arithmetic
+// Most numbers of a .delta are deltas of one to three digits with a random sign: below 10000 there is no data-dependent
+// branch (sign by pointer arithmetic, four digits from a table, the copy starts at the first significant one; it writes up to
+// three bytes past the number, the callers' buffers have that slack).
 static inline char *pmn_fmt_int(char *p, long long v)
 {
-    if (v < 0) { *p++ = '-'; v = -v; }
-    if (v < 10000) {
-        const unsigned u = (unsigned)v;
-        if (u < 10) { *p++ = (char)('0' + u); return p; }
-        if (u < 100) { memcpy(p, PMN_DIGITS2 + 2 * u, 2); return p + 2; }
-        const unsigned hi = u / 100, lo = u % 100;
-        if (u < 1000) { *p++ = (char)('0' + hi); memcpy(p, PMN_DIGITS2 + 2 * lo, 2); return p + 2; }
-        memcpy(p, PMN_DIGITS2 + 2 * hi, 2); memcpy(p + 2, PMN_DIGITS2 + 2 * lo, 2); return p + 4;
+    const bool neg = v < 0;
+    *p = '-'; p += neg;
+    const unsigned long long w0 = neg ? 0ull - (unsigned long long)v : (unsigned long long)v;
+    if (w0 < 10000) {
+        const unsigned u = (unsigned)w0, hi = u / 100, lo = u % 100;
+        uint16_t a, b;
+        memcpy(&a, PMN_DIGITS2 + 2 * hi, 2); memcpy(&b, PMN_DIGITS2 + 2 * lo, 2);
+        const int n = 1 + (u >= 10) + (u >= 100) + (u >= 1000);
+        const uint32_t x = ((uint32_t)a | (uint32_t)b << 16) >> (8 * (4 - n));      // little-endian host: the four digits in memory order, leading zeros shifted out
+        memcpy(p, &x, 4);
+        return p + n;
     }
     char tmp[24]; int n = 0;
-    unsigned long long w = (unsigned long long)v;
+    unsigned long long w = w0;
     while (w >= 100) { const unsigned lo = (unsigned)(w % 100); w /= 100; tmp[n++] = PMN_DIGITS2[2 * lo + 1]; tmp[n++] = PMN_DIGITS2[2 * lo]; }
     if (w >= 10) { tmp[n++] = PMN_DIGITS2[2 * w + 1]; tmp[n++] = PMN_DIGITS2[2 * w]; } else tmp[n++] = (char)('0' + w);
     while (n) *p++ = tmp[--n];
