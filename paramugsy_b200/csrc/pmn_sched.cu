@@ -76,6 +76,7 @@ extern "C" int pmn_sched_create(int device, int workers, pmn_sched **out)
     *out = nullptr;
     pmn_sched *s = new pmn_sched();
     s->device = device;
+    if (cudaSetDevice(device) == cudaSuccess) pmn_apply_device_sched(workers); else cudaGetLastError();      // before the workers' streams exist
     for (int k = 0; k < workers; k++) {
         pmn_ctx *c = nullptr;
         int rc = pmn_ctx_create(device, &c);
@@ -85,7 +86,6 @@ extern "C" int pmn_sched_create(int device, int workers, pmn_sched **out)
     }
     for (int k = 0; k < std::min(workers, 8); k++) s->build_scratch.push_back(pmn_scratch_new());
     { size_t free_b = 0, total_b = 0; if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) s->total_mem = total_b; else cudaGetLastError(); }
-    pmn_apply_device_sched(workers);
     *out = s;
     return 0;
 }
