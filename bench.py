@@ -29,6 +29,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# one hardware work queue per stream of the scheduler (default 8: the 16+ streams of the workers alias and serialise), read by
+# the driver when the CUDA context is created: before anything touches the GPU
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 # stdout carries the one JSON line and nothing else: libraries that print to file descriptor 1 (NCCL's version banner
 # is a plain printf) are sent to stderr, the JSON line goes to a private copy of the original stdout
 _REAL_STDOUT = os.fdopen(os.dup(1), "w")
@@ -426,13 +429,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="weak", choices=["weak", "strong"])
-    ap.add_argument("--workers", type=int, default=8, help="pairs in flight per GPU (pmn_sched worker threads)")
+    ap.add_argument("--workers", type=int, default=0, help="pairs in flight per GPU (pmn_sched worker threads); 0 = twice the host cores per local rank, between 8 and 16")
     ap.add_argument("--genomes", type=int, default=8)
     ap.add_argument("--genome-bp", type=int, default=5_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     ap.add_argument("--ref-sample-bp", type=int, default=1_000_000)
     args = ap.parse_args()
+    if args.workers <= 0:
+        # 16 pairs in flight fill one B200 (20 no longer fit its memory); a host with few cores per GPU (8 ranks on 32 cores)
+        # is better off with 8 worker threads per rank
+        local_ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))
+        args.workers = max(8, min(16, 2 * (os.cpu_count() or 16) // local_ranks))
     if args.impl == "reference":
         run_reference(args)
     else:

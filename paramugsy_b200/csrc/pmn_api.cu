@@ -111,6 +111,12 @@ extern "C" int pmn_device_count(void)
     return n;
 }
 
+// The streams of a scheduler's workers need a hardware work queue each: with the driver's default of 8 connections the 16+
+// streams alias and kernels of different pairs serialise behind each other (C2, one GPU: 1004 pairs/s with 8 connections,
+// 1225 with 32 at 8 workers, 1505 at 16 workers).  The driver reads the variable when the context is created, so the
+// library sets it when it is loaded — it has no effect if the host process initialised CUDA before that and did not set it.
+__attribute__((constructor)) static void pmn_set_connections() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+
 // How host threads wait for the device.  A scheduler keeps W threads per GPU waiting in cudaStreamSynchronize most of the
 // time.  Spinning is the fastest wake-up while every waiting thread has a core of its own (one GPU, 16 cores: 953 pairs/s
 // spinning, 935 yielding); on a host with fewer cores than waiting threads the spinners fight for the cores (8 GPUs, 8 ranks of

@@ -4,6 +4,10 @@ The extension is built in-tree by paramugsy_b200/build.py (nvcc, sm_100a).  Ther
 CPU fallback anywhere: if the library is missing it is built, if it cannot be loaded or no
 B200 is visible every computing call raises.
 """
+import os as _os
+# one hardware work queue per stream (the driver reads this when the CUDA context is created; default 8 makes the
+# streams of a scheduler's workers alias): set before anything in this process touches the GPU
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import ctypes as C
 import os
 
@@ -209,7 +213,7 @@ class Scheduler:
     """W worker threads sharing one GPU (pmn_sched): the in-process form of the reference's
     run_nucmers fan-out (lib/base/job_processor.ml:128-154)."""
 
-    def __init__(self, device=0, workers=4):
+    def __init__(self, device=0, workers=8):
         self.h = C.c_void_p()
         _check(lib().pmn_sched_create(device, workers, C.byref(self.h)))
         self.device, self.workers = device, workers

@@ -50,7 +50,7 @@ elif what == "c3":
             nxt.append(groups[k] + groups[k + 1])
         if len(groups) % 2: nxt.append(groups[-1])
         levels.append(pairs); groups = nxt
-    sched = lib.Scheduler(0, 8); ctx = sched.context(0)
+    sched = lib.Scheduler(0, 16); ctx = sched.context(0)
     t = time.time(); seqs = [ctx.sequence(synth.fasta(*g)) for g in gs]; out["pack_s"] = round(time.time() - t, 2)
     names = [g[0] for g in gs]
     out["pairs_per_level"] = [len(l) for l in levels]; out["pairs"] = sum(len(l) for l in levels)
