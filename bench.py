@@ -123,6 +123,10 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if getattr(args, "workers_auto", False):
+        # a worker holds about 9 GB of scratch and traceback arenas: no more workers than the free memory takes
+        free_b, _ = torch.cuda.mem_get_info()
+        args.workers = max(4, min(args.workers, int((free_b / 2**30 - 20) // 9.5)))
     sched = lib.Scheduler(local, args.workers)
     ctx = sched.context(0)
 
@@ -436,6 +440,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     ap.add_argument("--ref-sample-bp", type=int, default=1_000_000)
     args = ap.parse_args()
+    args.workers_auto = args.workers <= 0
     if args.workers <= 0:
         # 16 pairs in flight fill one B200 (20 no longer fit its memory); a host with few cores per GPU (8 ranks on 32 cores)
         # is better off with 8 worker threads per rank
