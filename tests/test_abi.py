@@ -75,3 +75,39 @@ def test_product_never_touches_the_oracle():
                 if re.search(r"#\s*include[^\n]*oracle|libpmn_oracle|from\s+oracle|import\s+oracle|\bpmo_\w+\s*\(|oracle/", txt):
                     bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_library_asks_for_a_hardware_queue_per_stream():
+    """A scheduler's workers launch on 2 W streams; with the driver's default of 8 connections they alias and serialise
+    (DESIGN.md §6).  The library sets the variable when it is loaded (a host that set it keeps its value), the binding when
+    it is imported."""
+    code = ("import os, ctypes; os.environ.pop('CUDA_DEVICE_MAX_CONNECTIONS', None); "
+            "from paramugsy_b200 import build; ctypes.CDLL(build.build()); "
+            "libc = ctypes.CDLL(None); libc.getenv.restype = ctypes.c_char_p; print(libc.getenv(b'CUDA_DEVICE_MAX_CONNECTIONS'))")
+    out = subprocess.check_output([os.sys.executable, "-c", code], cwd=ROOT).decode()
+    assert "b'32'" in out, out
+    code = ("import os; os.environ['CUDA_DEVICE_MAX_CONNECTIONS'] = '4'; import paramugsy_b200.lib as l; l.lib(); "
+            "print(os.environ['CUDA_DEVICE_MAX_CONNECTIONS'])")
+    assert subprocess.check_output([os.sys.executable, "-c", code], cwd=ROOT).decode().strip() == "4"
+
+
+def test_small_numbers_are_formatted_like_printf():
+    """The .delta writers' integer formatter (pmn_host.h: branch-free below 10000, two digits per step above) against printf."""
+    src = open(os.path.join(ROOT, "paramugsy_b200", "csrc", "pmn_host.h")).read()
+    a = src.index("static const char PMN_DIGITS2[201]"); b = src.index("void pmn_apply_device_sched(int workers);")
+    prog = ("#include <cstdio>\n#include <cstring>\n#include <cstdlib>\n#include <climits>\n#include <cstdint>\n" + src[a:b] + """
+int main() {
+    long long edge[] = {0, 1, -1, 9, 10, 99, 100, 999, 1000, 9999, -9999, 10000, -10000, 10001, 99999, 100000, 2147483647LL, -2147483648LL, LLONG_MAX, LLONG_MIN};
+    char x[64], y[64]; int bad = 0;
+    for (long long v : edge) { memset(x, '#', 64); *pmn_fmt_int(x, v) = 0; sprintf(y, "%lld", v); bad += strcmp(x, y) != 0; }
+    for (long long v = -20000; v <= 20000; v++) { *pmn_fmt_int(x, v) = 0; sprintf(y, "%lld", v); bad += strcmp(x, y) != 0; }
+    srand(7);
+    for (int i = 0; i < 200000; i++) { long long v = ((long long)rand() << (rand() % 33)) - (1LL << (rand() % 40)); *pmn_fmt_int(x, v) = 0; sprintf(y, "%lld", v); bad += strcmp(x, y) != 0; }
+    printf("%d\\n", bad); return bad != 0;
+}
+""")
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.cpp"), "w").write(prog)
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", os.path.join(d, "t"), os.path.join(d, "t.cpp")])
+        assert subprocess.check_output([os.path.join(d, "t")]).decode().strip() == "0"
