@@ -133,7 +133,7 @@ static int sched_run(pmn_sched *s, int ng, const char *const *fasta, const size_
     s->err.clear(); s->err_code = 0;
 
     // Indexes alive at a time: as many as fit a quarter of the device memory (8.25 B/base each), between 2 and 16.  A batch
-    // over a handful of bacterial genomes (C2: 7 references of 41 MB) then builds all its indexes side by side at the start —
+    // over a handful of bacterial genomes (C2: 7 references of 107 MB) then builds all its indexes side by side at the start —
     // wide, HBM-bound kernels that fill the GPU — and no pair ever waits for a build in the tail of the batch.
     int MAX_LIVE_INDEXES = 4;
     {
