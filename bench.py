@@ -314,6 +314,7 @@ def run_gpu(args):
             "config": {"workload": f"{args.genomes} synthetic {args.genome_bp / 1e6:g} Mbp genomes, all-vs-all {len(pairs)} pairs "
                                    f"(BASELINE.json configs[1]); per rank: {npairs_rank} pairs, {len(refs)} index builds per step",
                        "mode": args.mode, "pairs_per_step_all_ranks": npairs_all, "workers_per_gpu": args.workers,
+                       "hw_queues": int(os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS", "8")),
                        "l2": "no explicit flush: one step streams > 1 GB of index, staging and score data per pair through a 126 MB L2"},
             "aligned_mbp_per_s": aligned_bp * world / 1e6 / (step_ms * 1e-3) if args.mode == "weak" else aligned_bp / 1e6 / (step_ms * 1e-3),
             "input_mbp_per_s": bp_all / 1e6 / (step_ms * 1e-3),
