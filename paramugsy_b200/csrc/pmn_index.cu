@@ -1,6 +1,7 @@
 // pmn_index.cu — reference index on the device:
 //   pack (codes -> 2-bit text + x-mask, both strands), suffix array by radix-sort prefix
-//   doubling, Kasai-style LCP, and the K-mer bucket table the seeding kernel starts from.
+//   doubling, LCP (from the sorted 16-mer keys where they decide it, a Kasai-style walk over the rest), and
+//   the K-mer bucket table the seeding kernel starts from.
 //
 // Stands in for MUMmer's suffix-tree construction inside `mummer`, first stage of the
 // `nucmer` child process of /root/reference/lib/nucmer/mugsy_nucmer.ml:100.

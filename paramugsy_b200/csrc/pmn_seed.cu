@@ -8,11 +8,13 @@
 //   1. 32-base window of the query from shared memory (the tile of packed query text and
 //      its x-mask is staged by one TMA bulk copy per block, cp.async.bulk + mbarrier)
 //   2. bucket [lo,hi) of the window's first K bases from the K-mer table
-//   3. lower bound of Q[i..] among the bucket's suffixes (binary search on packed text,
-//      32 bases per probe)
-//   4. longest match = better of the two neighbours of the insertion point; unique iff the
-//      other neighbour is shorter and the LCP entry on the far side is shorter too
-//   5. left-maximality, then ordered compaction of the tile's anchors
+//   3. a bucket of one suffix is decided at once (left-maximality base, then the match
+//      length); larger buckets go on the warp's list and are worked off densely:
+//      lower bound of Q[i..] among the bucket's suffixes (binary search on packed text,
+//      32 bases per probe), longest match = better of the two neighbours of the insertion
+//      point, unique iff the other neighbour is shorter and the LCP entry on the far side
+//      is shorter too, left-maximality
+//   4. anchors are written at the slot of their position; k_seed_gather compacts them in order
 // Output order equals the oracle's sort order, so no sort follows.
 #include <algorithm>
 
