@@ -76,6 +76,24 @@ typedef struct pmn_stats {
 
 void pmn_default_opts(pmn_opts *o);
 
+/* MUMmer 3.x `nucmer` option spellings, read in one place for the three callers that meet them: the `nucmer` argv shim
+ * (the child process of lib/nucmer/mugsy_nucmer.ml:100), the OCaml stub (integration/pmn_stubs.c) and the Python mirror.
+ *   -l/--minmatch -c/--mincluster -g/--maxgap -D/--diagdiff -d/--diagfactor -b/--breaklen -f/--forward -r/--reverse
+ *   --mumreference --[no]extend --[no]simplify --optimize --delta -p/--prefix --device -h -V   (--long=value is accepted)
+ *   --mum --maxmatch --nooptimize --banded --nodelta: PMN_E_ARG ("not implemented on the B200 path"); anything else
+ *   starting with '-': PMN_E_ARG ("unknown option").
+ * pmn_nucmer_parse_argv: argv WITHOUT the program name; the char pointers of *out borrow argv.  device is -1 when not given.
+ * pmn_opts_parse: the free-form -nucmer_opts string the reference appends to the command line verbatim (mugsy_nucmer.ml:100;
+ *   lib/base/nucmer_task.ml:53 never sets it), split like a shell would; *o = defaults with the named options applied. */
+typedef struct pmn_nucmer_args {
+    pmn_opts opts;
+    const char *prefix;          /* -p, default "out": the output is <prefix>.delta */
+    const char *ref, *qry;       /* the two positional arguments, NULL when absent */
+    int32_t device, help, version;
+} pmn_nucmer_args;
+int  pmn_nucmer_parse_argv(int argc, const char *const *argv, pmn_nucmer_args *out);
+int  pmn_opts_parse(const char *nucmer_opts, pmn_opts *o);
+
 /* ---- context ---- */
 int  pmn_ctx_create(int device, pmn_ctx **out);
 void pmn_ctx_destroy(pmn_ctx *c);
@@ -84,6 +102,11 @@ int  pmn_device_count(void);
 /* device allocations (cudaMalloc) made by the library in this process so far: all scratch is grow-only, so the
  * number stops changing once the working set has been seen; bench.py reports the count inside its timed region */
 int64_t pmn_alloc_count(void);
+/* MAF texts (pmn_opts.post, pmn_delta2maf) are written by the device straight into page-locked host buffers that are
+ * recycled when the caller frees the result.  out[0] = idle bytes the pool holds for reuse (never more than out[2]),
+ * out[1] = all page-locked bytes it accounts for (idle + in the hands of callers), out[2] = the idle budget
+ * (1 GB, PMN_PINNED_POOL_MB overrides): what comes back beyond the budget is released with cudaFreeHost. */
+void pmn_pinned_pool_stats(int64_t out[3]);
 /* the CUDA stream (cudaStream_t) every kernel of this context is launched on, so that a caller
  * can bracket calls with its own CUDA events */
 void *pmn_ctx_stream(const pmn_ctx *c);

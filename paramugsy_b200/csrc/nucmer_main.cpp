@@ -6,11 +6,12 @@
 // (scripts/pm_qsub_template.sh:6-7) — and ParaMugsy runs the B200 path unchanged.
 // Option spellings follow MUMmer 3.x's nucmer script.  Exit 0 on success, 1 otherwise with a
 // message on stderr (Shell.sh raises on non-zero, mugsy_nucmer.ml:100).
+#include <cerrno>
+#include <climits>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
-#include <vector>
 
 #include "pmnucmer.h"
 
@@ -31,48 +32,28 @@ static void usage(FILE *f)
             "  --device <int>         CUDA device (default 0 or $PMN_DEVICE)\n");
 }
 
-static bool need(int i, int argc, const char *o) { if (i + 1 >= argc) { fprintf(stderr, "nucmer: option %s needs a value\n", o); return false; } return true; }
-
 int main(int argc, char **argv)
 {
-    pmn_opts o; pmn_default_opts(&o);
-    std::string prefix = "out";
-    std::vector<const char *> pos;
-    int device = getenv("PMN_DEVICE") ? atoi(getenv("PMN_DEVICE")) : 0;
-    for (int i = 1; i < argc; i++) {
-        const char *a = argv[i];
-        auto is = [&](const char *s, const char *l) { return !strcmp(a, s) || !strcmp(a, l); };
-        if (is("-p", "--prefix")) { if (!need(i, argc, a)) return 1; prefix = argv[++i]; }
-        else if (!strncmp(a, "--prefix=", 9)) prefix = a + 9;
-        else if (is("-l", "--minmatch")) { if (!need(i, argc, a)) return 1; o.minmatch = atoi(argv[++i]); }
-        else if (is("-c", "--mincluster")) { if (!need(i, argc, a)) return 1; o.mincluster = atoi(argv[++i]); }
-        else if (is("-g", "--maxgap")) { if (!need(i, argc, a)) return 1; o.maxgap = atoi(argv[++i]); }
-        else if (is("-D", "--diagdiff")) { if (!need(i, argc, a)) return 1; o.diagdiff = atoi(argv[++i]); }
-        else if (is("-d", "--diagfactor")) { if (!need(i, argc, a)) return 1; o.diagfactor = atof(argv[++i]); }
-        else if (is("-b", "--breaklen")) { if (!need(i, argc, a)) return 1; o.breaklen = atoi(argv[++i]); }
-        else if (is("-f", "--forward")) o.do_reverse = 0;
-        else if (is("-r", "--reverse")) o.do_forward = 0;
-        else if (!strcmp(a, "--mumreference") || !strcmp(a, "--delta")) {}
-        else if (!strcmp(a, "--extend")) o.do_extend = 1;
-        else if (!strcmp(a, "--noextend")) o.do_extend = 0;
-        else if (!strcmp(a, "--simplify")) o.do_simplify = 1;
-        else if (!strcmp(a, "--nosimplify")) o.do_simplify = 0;
-        else if (!strcmp(a, "--optimize")) o.do_optimize = 1;
-        else if (!strcmp(a, "--device")) { if (!need(i, argc, a)) return 1; device = atoi(argv[++i]); }
-        else if (is("-h", "--help")) { usage(stdout); return 0; }
-        else if (is("-V", "--version")) { printf("nucmer (paramugsy_b200, MUMmer 3.20 compatible front end)\n"); return 0; }
-        else if (!strcmp(a, "--nooptimize") || !strcmp(a, "--mum") || !strcmp(a, "--maxmatch") || !strcmp(a, "--banded") || !strcmp(a, "--nodelta")) {
-            fprintf(stderr, "nucmer: option %s is not implemented on the B200 path\n", a); return 1;
-        }
-        else if (a[0] == '-' && a[1]) { fprintf(stderr, "nucmer: unknown option %s\n", a); usage(stderr); return 1; }
-        else pos.push_back(a);
+    pmn_nucmer_args a;
+    if (pmn_nucmer_parse_argv(argc - 1, (const char *const *)(argv + 1), &a)) {       // the option table shared with the OCaml stub and the Python mirror
+        fprintf(stderr, "%s\n", pmn_last_error(nullptr));
+        usage(stderr);
+        return 1;
     }
-    if (pos.size() != 2) { usage(stderr); return 1; }
-    if (!o.do_forward && !o.do_reverse) { fprintf(stderr, "nucmer: -f and -r are mutually exclusive\n"); return 1; }
+    if (a.help) { usage(stdout); return 0; }
+    if (a.version) { printf("nucmer (paramugsy_b200, MUMmer 3.20 compatible front end)\n"); return 0; }
+    if (!a.ref || !a.qry) { usage(stderr); return 1; }
+    const int device = a.device >= 0 ? a.device : getenv("PMN_DEVICE") ? atoi(getenv("PMN_DEVICE")) : 0;
+    // MUMmer's nucmer writes ABSOLUTE paths on line 1 of the .delta; delta2maf re-opens them from wherever it is run
+    // (lib/base/mugsy_profiles_task.ml:60 runs it from another directory)
+    char rbuf[PATH_MAX], qbuf[PATH_MAX];
+    const char *rp = realpath(a.ref, rbuf), *qp = realpath(a.qry, qbuf);
+    if (!rp) { fprintf(stderr, "nucmer: cannot open %s: %s\n", a.ref, strerror(errno)); return 1; }
+    if (!qp) { fprintf(stderr, "nucmer: cannot open %s: %s\n", a.qry, strerror(errno)); return 1; }
     pmn_ctx *ctx = nullptr;
     if (pmn_ctx_create(device, &ctx)) { fprintf(stderr, "nucmer: %s\n", pmn_last_error(nullptr)); return 1; }
-    const std::string out = prefix + ".delta";
-    int rc = pmn_align_pair(ctx, pos[0], pos[1], &o, out.c_str());
+    const std::string out = std::string(a.prefix) + ".delta";
+    int rc = pmn_align_pair(ctx, rp, qp, &a.opts, out.c_str());
     if (rc) fprintf(stderr, "nucmer: %s\n", pmn_last_error(ctx));
     pmn_ctx_destroy(ctx);
     return rc ? 1 : 0;

@@ -58,7 +58,16 @@ namespace {
 struct PinnedPool {
     std::mutex mu;
     std::multimap<size_t, void *> idle;         // capacity -> buffer
-    std::map<void *, size_t> all;               // every buffer the pool ever handed out -> capacity
+    std::map<void *, size_t> all;               // every buffer the pool handed out and has not freed -> capacity
+    size_t idle_bytes = 0;
+    // Page-locked memory the pool keeps for reuse.  Buffers in the hands of callers are theirs (a batch call returns all its
+    // results alive); what comes back beyond the budget is released, so a process never sits on more idle pinned memory than
+    // this — 1 GB by default (a C2 step hands back 28 MAF buffers of 16 MB), PMN_PINNED_POOL_MB overrides, 0 = keep nothing.
+    size_t budget() const
+    {
+        static const size_t b = getenv("PMN_PINNED_POOL_MB") ? (size_t)atoll(getenv("PMN_PINNED_POOL_MB")) << 20 : (size_t)1 << 30;
+        return b;
+    }
 };
 PinnedPool &pinned_pool() { static PinnedPool *p = new PinnedPool(); return *p; }      // never destroyed: outlives the CUDA runtime's own teardown
 }  // namespace
@@ -71,7 +80,7 @@ char *pmn_pinned_get(size_t bytes)
     {
         std::lock_guard<std::mutex> lk(P.mu);
         auto it = P.idle.find(cap);
-        if (it != P.idle.end()) { void *p = it->second; P.idle.erase(it); return (char *)p; }
+        if (it != P.idle.end()) { void *p = it->second; P.idle.erase(it); P.idle_bytes -= cap; return (char *)p; }
     }
     void *p = nullptr;
     if (cudaMallocHost(&p, cap) != cudaSuccess) { cudaGetLastError(); pmn_set_error(PMN_E_NOMEM, "cudaMallocHost(%zu) failed", cap); return nullptr; }
@@ -87,8 +96,24 @@ bool pmn_pinned_put(void *p)
     std::lock_guard<std::mutex> lk(P.mu);
     auto it = P.all.find(p);
     if (it == P.all.end()) return false;
+    if (P.idle_bytes + it->second > P.budget()) {        // over the budget: back to the system (cudaFreeHost waits for the device; rare)
+        P.all.erase(it);
+        if (cudaFreeHost(p) != cudaSuccess) cudaGetLastError();
+        return true;
+    }
     P.idle.emplace(it->second, p);
+    P.idle_bytes += it->second;
     return true;
+}
+
+extern "C" void pmn_pinned_pool_stats(int64_t out[3])
+{
+    if (!out) return;
+    PinnedPool &P = pinned_pool();
+    std::lock_guard<std::mutex> lk(P.mu);
+    size_t live = 0;
+    for (auto &kv : P.all) live += kv.second;
+    out[0] = (int64_t)P.idle_bytes; out[1] = (int64_t)live; out[2] = (int64_t)P.budget();
 }
 
 pmn_result::~pmn_result() { pmn_pinned_put(maf); }
@@ -136,6 +161,35 @@ void pmn_apply_device_sched(int workers)
     if (cudaSetDeviceFlags(fl) != cudaSuccess) cudaGetLastError();
 }
 
+static int ctx_init(pmn_ctx *c)
+{
+    PMN_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    PMN_CUDA_OK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    PMN_CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    PMN_CUDA_OK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    {   // freed blocks stay in the device's default pool instead of going back to the driver
+        cudaMemPool_t mp; unsigned long long keep = ~0ull;
+        PMN_CUDA_OK(cudaDeviceGetDefaultMemPool(&mp, c->device));
+        PMN_CUDA_OK(cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
+    for (auto &e : c->ev) PMN_CUDA_OK(cudaEventCreate(&e));
+    c->scratch = pmn_scratch_new();
+    c->pool = std::make_shared<DevPool>();
+    return 0;
+}
+
+static void ctx_teardown(pmn_ctx *c)
+{
+    pmn_scratch_free(c->scratch);
+    c->pool.reset();
+    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    delete c;
+}
+
 extern "C" int pmn_ctx_create(int device, pmn_ctx **out)
 {
     if (!out) return pmn_set_error(PMN_E_ARG, "pmn_ctx_create: out is NULL");
@@ -150,18 +204,8 @@ extern "C" int pmn_ctx_create(int device, pmn_ctx **out)
     if (prop.major < 10) return pmn_set_error(PMN_E_NOGPU, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     pmn_ctx *c = new pmn_ctx();
     c->device = device; c->sm_count = prop.multiProcessorCount;
-    PMN_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    PMN_CUDA_OK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
-    PMN_CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-    PMN_CUDA_OK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
-    {   // freed blocks stay in the device's default pool instead of going back to the driver
-        cudaMemPool_t mp; unsigned long long keep = ~0ull;
-        PMN_CUDA_OK(cudaDeviceGetDefaultMemPool(&mp, device));
-        PMN_CUDA_OK(cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep));
-    }
-    for (auto &e : c->ev) PMN_CUDA_OK(cudaEventCreate(&e));
-    c->scratch = pmn_scratch_new();
-    c->pool = std::make_shared<DevPool>();
+    const int rc = ctx_init(c);
+    if (rc) { ctx_teardown(c); return rc; }       // streams and events created so far are destroyed, the context freed
     *out = c;
     return 0;
 }
@@ -228,6 +272,7 @@ extern "C" int pmn_measure_int32_peak(pmn_ctx *c, double *gops_per_s, double *sm
 {
     if (!c || !gops_per_s) return pmn_set_error(PMN_E_ARG, "pmn_measure_int32_peak: NULL argument");
     PMN_CUDA_OK(cudaSetDevice(c->device));
+    pmn_tls_stream = c->stream;
     Scratch &S = *c->scratch;
     if (S.ex_counters.ensure(128)) return -3;
     const int iters = 2048, blocks = c->sm_count * 2;
@@ -252,15 +297,10 @@ extern "C" void pmn_ctx_destroy(pmn_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    pmn_scratch_free(c->scratch);
-    c->pool.reset();
-    { cudaMemPool_t mp; if (cudaDeviceGetDefaultMemPool(&mp, c->device) == cudaSuccess) cudaMemPoolTrimTo(mp, 0); }   // unused blocks go back to the driver
-    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
-    if (c->stream) cudaStreamDestroy(c->stream);
-    if (c->stream2) cudaStreamDestroy(c->stream2);
-    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-    if (c->ev_join) cudaEventDestroy(c->ev_join);
-    delete c;
+    const int device = c->device;
+    if (pmn_tls_stream == c->stream || pmn_tls_stream == c->stream2) pmn_tls_stream = nullptr;      // never grow a buffer on a dead stream
+    ctx_teardown(c);
+    { cudaMemPool_t mp; if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) cudaMemPoolTrimTo(mp, 0); }   // unused blocks go back to the driver
 }
 
 // ------------------------------------------------------------------------------------ FASTA
@@ -477,6 +517,7 @@ static int align_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *qry, const
     *out = nullptr;
     pmn_opts o; { int rc = check_opts(o_in, o); if (rc) return rc; }
     PMN_CUDA_OK(cudaSetDevice(c->device));
+    pmn_tls_stream = c->stream;          // buffers grow stream-ordered on THIS context's stream (given-anchors path: before any stage sets it)
     Scratch &S = *c->scratch;
     cudaStream_t st = c->stream;
     std::unique_ptr<pmn_result> r(new pmn_result());
@@ -628,13 +669,14 @@ static int batch_files(pmn_ctx *c, int n, const char *const *refs, const char *c
         if (!e) seqs[p] = *s;
         return e;
     };
+    for (int i = 0; i < n; i++)
+        if (!refs[i] || !qrys[i] || !outs[i]) return pmn_set_error(PMN_E_ARG, "pmn_align_batch: NULL path in pair %d", i);
     std::vector<int> order(n);
     for (int i = 0; i < n; i++) order[i] = i;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return strcmp(refs[a], refs[b]) < 0; });
     std::string cur_ref; pmn_index *cur_ix = nullptr;
     for (int oi = 0; oi < n && !rc; oi++) {
         int i = order[oi];
-        if (!refs[i] || !qrys[i] || !outs[i]) { rc = pmn_set_error(PMN_E_ARG, "pmn_align_batch: NULL path in pair %d", i); break; }
         if (!cur_ix || cur_ref != refs[i]) {
             if (cur_ix) { pmn_index_free(cur_ix); cur_ix = nullptr; }
             pmn_seq *rs; rc = get_seq(refs[i], &rs); if (rc) break;

@@ -325,7 +325,7 @@ int pmn_cluster_impl(pmn_ctx *c, const pmn_index *, const pmn_seq *, const pmn_o
     PMN_D2H(c, tail + 1, good + (n - 1), 4);
     PMN_CUDA_OK(cudaStreamSynchronize(st));
     const int64_t nf = (int64_t)tail[0] + tail[1];
-    if (nf <= 0) return pmn_set_error(PMN_E_INTERNAL, "cluster: filter removed every anchor");
+    if (nf <= 0) return 0;       // nothing left to cluster: an empty result (a pair without clusters), not a failure of the whole batch
     const unsigned gf = (unsigned)((nf + 255) / 256);
 
     // 2. union-find

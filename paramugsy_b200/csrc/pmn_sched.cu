@@ -170,7 +170,7 @@ static int sched_run(pmn_sched *s, int ng, const char *const *fasta, const size_
                 lk.lock();
                 sl.obj = o; sl.state = o ? ST_READY : ST_FAILED;
                 if (!o && !s->err_code) { s->err_code = PMN_E_INTERNAL; s->err = pmn_last_error(nullptr); }
-                if (!o) { failed.store(1); s->bcv.notify_all(); }
+                if (!o) { std::lock_guard<std::mutex> lk2(s->bmu); failed.store(1); s->bcv.notify_all(); }      // under bmu: a waiter between its predicate and its block cannot miss it
                 s->cv.notify_all();
                 return o;
             }
@@ -223,7 +223,12 @@ static int sched_run(pmn_sched *s, int ng, const char *const *fasta, const size_
                 for (size_t i = 0; i < mine.size() && i < s->hiwater.size(); i++) s->hiwater[i] = std::max(s->hiwater[i], mine[i]->cap);
             }
             std::lock_guard<std::mutex> lk(s->mu);
-            if (rc) { if (!s->err_code) { s->err_code = rc; s->err = pmn_last_error(nullptr); } failed.store(1); s->bcv.notify_all(); return; }
+            if (rc) {
+                if (!s->err_code) { s->err_code = rc; s->err = pmn_last_error(nullptr); }
+                std::lock_guard<std::mutex> lk2(s->bmu);      // the store must not land between a waiter's predicate check and its block (lost wake-up)
+                failed.store(1); s->bcv.notify_all();
+                return;
+            }
             out[p] = res;
             // the last user of an index / of a genome packed by this run frees it
             if (--idx[(size_t)r].users == 0) {

@@ -30,6 +30,12 @@ class Opts(C.Structure):
                 ("do_optimize", C.c_int32), ("do_simplify", C.c_int32), ("keep_stages", C.c_int32), ("post", C.c_int32)]
 
 
+class NucmerArgs(C.Structure):
+    """pmn_nucmer_args: what the `nucmer` command line of lib/nucmer/mugsy_nucmer.ml:100 says."""
+    _fields_ = [("opts", Opts), ("prefix", C.c_char_p), ("ref", C.c_char_p), ("qry", C.c_char_p),
+                ("device", C.c_int32), ("help", C.c_int32), ("version", C.c_int32)]
+
+
 class Stats(C.Structure):
     _fields_ = [("ref_bases", C.c_int64), ("qry_bases", C.c_int64), ("anchors", C.c_int64),
                 ("clusters", C.c_int64), ("cluster_matches", C.c_int64), ("alignments", C.c_int64),
@@ -47,7 +53,7 @@ class Stats(C.Structure):
 
 # every symbol include/pmnucmer.h declares (tests check the .so exports all of them)
 SYMBOLS = [
-    "pmn_default_opts", "pmn_ctx_create", "pmn_ctx_destroy", "pmn_last_error", "pmn_device_count", "pmn_alloc_count",
+    "pmn_default_opts", "pmn_nucmer_parse_argv", "pmn_opts_parse", "pmn_ctx_create", "pmn_ctx_destroy", "pmn_last_error", "pmn_device_count", "pmn_alloc_count", "pmn_pinned_pool_stats",
     "pmn_ctx_stream", "pmn_ctx_counters", "pmn_measure_int32_peak",
     "pmn_seq_from_fasta", "pmn_seq_from_file", "pmn_seq_free", "pmn_seq_bases", "pmn_seq_records",
     "pmn_index_build", "pmn_index_free", "pmn_index_image", "pmn_index_image_bytes", "pmn_index_alloc", "pmn_index_adopt", "pmn_align", "pmn_seed_part", "pmn_align_anchors", "pmn_result_delta", "pmn_result_stats",
@@ -74,9 +80,12 @@ def lib():
         L = C.CDLL(lib_path())
         vp, cp, i64, i32p, i64p = C.c_void_p, C.c_char_p, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int64)
         L.pmn_default_opts.argtypes = [C.POINTER(Opts)]
+        L.pmn_nucmer_parse_argv.argtypes = [C.c_int, C.POINTER(cp), C.POINTER(NucmerArgs)]
+        L.pmn_opts_parse.argtypes = [cp, C.POINTER(Opts)]
         L.pmn_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
         L.pmn_ctx_destroy.argtypes = [vp]
         L.pmn_alloc_count.restype = i64
+        L.pmn_pinned_pool_stats.argtypes = [i64p]
         L.pmn_last_error.argtypes = [vp]; L.pmn_last_error.restype = cp
         L.pmn_ctx_stream.argtypes = [vp]; L.pmn_ctx_stream.restype = vp
         L.pmn_ctx_counters.argtypes = [vp, i64p]
@@ -132,6 +141,12 @@ def alloc_count() -> int:
     return lib().pmn_alloc_count()
 
 
+def pinned_pool_stats():
+    out = (C.c_int64 * 3)()
+    lib().pmn_pinned_pool_stats(out)
+    return {"idle_bytes": out[0], "accounted_bytes": out[1], "idle_budget_bytes": out[2]}
+
+
 def index_image_bytes(n_bases: int) -> int:
     return lib().pmn_index_image_bytes(n_bases)
 
@@ -144,6 +159,24 @@ def default_opts(**kw):
             raise TypeError(f"unknown nucmer option {k!r}")
         setattr(o, k, v)
     return o
+
+
+def opts_from_nucmer_string(nucmer_opts: str) -> Opts:
+    """The free-form option string the reference appends to the nucmer command line (mugsy_nucmer.ml:100), read by the
+    library's own option table (pmn_opts_parse); raises PmnError(PMN_E_ARG) on an unknown or unsupported option."""
+    o = Opts()
+    _check(lib().pmn_opts_parse(os.fsencode(nucmer_opts), C.byref(o)))
+    return o
+
+
+def nucmer_parse_argv(argv):
+    """argv (without the program name) -> (Opts, prefix, ref, qry, device or None, help, version)."""
+    arr = (C.c_char_p * len(argv))(*[os.fsencode(a) for a in argv])
+    a = NucmerArgs()
+    _check(lib().pmn_nucmer_parse_argv(len(argv), arr, C.byref(a)))
+    dec = lambda b: os.fsdecode(b) if b is not None else None
+    o = Opts.from_buffer_copy(a.opts)
+    return o, dec(a.prefix), dec(a.ref), dec(a.qry), (a.device if a.device >= 0 else None), bool(a.help), bool(a.version)
 
 
 def _check(rc):

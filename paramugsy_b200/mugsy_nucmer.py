@@ -76,31 +76,12 @@ def parse_argv(argv) -> Options:
 
 
 def nucmer_opts_to_pmn(opts: str) -> lib.Opts:
-    """The string the reference hands to nucmer verbatim (mugsy_nucmer.ml:100), as pmn_opts."""
-    o = lib.default_opts()
-    toks = shlex.split(opts)
-    i = 0
-    ints = {"-l": "minmatch", "--minmatch": "minmatch", "-c": "mincluster", "--mincluster": "mincluster", "-g": "maxgap",
-            "--maxgap": "maxgap", "-D": "diagdiff", "--diagdiff": "diagdiff", "-b": "breaklen", "--breaklen": "breaklen"}
-    while i < len(toks):
-        t = toks[i]
-        if t in ints:
-            setattr(o, ints[t], int(toks[i + 1])); i += 2
-        elif t in ("-d", "--diagfactor"):
-            o.diagfactor = float(toks[i + 1]); i += 2
-        elif t in ("-f", "--forward"):
-            o.do_reverse = 0; i += 1
-        elif t in ("-r", "--reverse"):
-            o.do_forward = 0; i += 1
-        elif t in ("--mumreference", "--delta", "--extend", "--simplify", "--optimize"):
-            i += 1
-        elif t == "--noextend":
-            o.do_extend = 0; i += 1
-        elif t == "--nosimplify":
-            o.do_simplify = 0; i += 1
-        else:
-            raise Failure(f"nucmer option {t!r} is not implemented on the B200 path")
-    return o
+    """The string the reference hands to nucmer verbatim (mugsy_nucmer.ml:100), as pmn_opts — read by the library's
+    own option table (pmn_opts_parse), the one the `nucmer` shim and the OCaml stub use."""
+    try:
+        return lib.opts_from_nucmer_string(opts)
+    except lib.PmnError as e:
+        raise Failure(str(e))
 
 
 def _sh(options: Options, cmd: str):
@@ -232,7 +213,7 @@ def run_nucmers(searches_, tmp_dir: str, nucmer_chunk: int = 10, ctx=None, filte
     library's batch entry point (the batch unit of the reference, nucmer_task.ml:6); returns the
     out_paths map.  With `filter` (mugsy_nucmer's default, mugsy_nucmer.ml:54) every pair leaves what one
     mugsy_nucmer process leaves: <bname>.delta = the filtered delta and <bname>.maf (pmn_worker_batch); without it
-    the unfiltered delta only.  Any failing pair raises Failure (job_processor.ml:72-73 fails the whole node)."""
+    (-nofilter) the unfiltered delta and its MAF.  Any failing pair raises Failure (job_processor.ml:72-73 fails the whole node)."""
     import ctypes as C
     os.makedirs(tmp_dir, exist_ok=True)
     own = ctx is None
@@ -249,6 +230,11 @@ def run_nucmers(searches_, tmp_dir: str, nucmer_chunk: int = 10, ctx=None, filte
                 rc = lib.lib().pmn_align_batch(c.h, len(part), arr([a for a, _ in part]), arr([b for _, b in part]), arr(outs), None)
             if rc != 0:
                 raise Failure(lib.lib().pmn_last_error(None).decode(errors="replace"))
+            if not filter:
+                # -nofilter only skips delta-filter: delta2maf still runs, on the unfiltered delta (mugsy_nucmer.ml:127-131)
+                for (a, b), out in zip(part, outs):
+                    o = Options(ref_seq=a, query_seq=b, maf_out=out[:-len(".delta")] + ".maf", delta_out=out)
+                    generate_maf(o, c)
     finally:
         if own:
             c.close()
