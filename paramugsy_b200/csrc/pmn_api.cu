@@ -27,6 +27,7 @@ int pmn_set_error(int code, const char *fmt, ...)
 }
 
 extern "C" const char *pmn_last_error(const pmn_ctx *) { return g_err.msg; }
+int pmn_last_code() { return g_err.code; }
 
 thread_local cudaStream_t pmn_tls_stream = nullptr;
 thread_local long pmn_tls_launches_saved = 0;

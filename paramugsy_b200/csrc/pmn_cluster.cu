@@ -169,10 +169,16 @@ struct ChainArrays {
     uint32_t *oc_valid;
 };
 
-// Process_Matches for the component occupying sorted slots [a, a+m).  One warp; the DP itself
-// is run by lane 0 (it is a chain of dependent steps), the other lanes feed it coalesced
-// loads and do the parallel parts (marking, emitting, compacting).
-__device__ void chain_component(const ChainArrays &C, int64_t a, int m, int mincluster)
+// Process_Matches for the component occupying sorted slots [a, a+m).  One warp.  The DP is a chain of dependent steps and
+// is run by lane 0; what it reads and writes per step lives in shared memory: the anchors arrive 32 at a time (coalesced
+// loads by all lanes) in a ring of the last CH_RING entries, where scores and prefix maxima stay for the look-back (a clean
+// colinear run looks back one or two entries; an entry written to global memory comes back from L2, 300 cycles per step of
+// the chain), and results leave 32 at a time (coalesced stores).  The walk over the best chain's `from` links is served the
+// same way, one chunk of 32 links in shared memory at a time, instead of one L2 round trip per link.
+#define CH_RING 64
+struct ChainShared { int s1[CH_RING], s2[CH_RING], ln[CH_RING], sc[CH_RING], pm[CH_RING]; int from[32], adj[32]; };
+
+__device__ void chain_component(const ChainArrays &C, int64_t a, int m, int mincluster, ChainShared &W)
 {
     const int lane = threadIdx.x & 31;
     const unsigned lt = pmn_lanemask_lt();
@@ -180,44 +186,62 @@ __device__ void chain_component(const ChainArrays &C, int64_t a, int m, int minc
     int cm = 0, ck = 0;       // matches / clusters emitted so far by this component
     while (m > 0) {
         // ---- DP: score[i] = len[i] + max(0, max_{j<i}(score[j] - pen(i,j))), lowest j among the best
-        int bestIdx = 0, bestScore = INT32_MIN;
-        int p_s1 = 0, p_s2 = 0, p_ln = 0, p_sc = 0, p_pm = 0;      // element i-1, lane 0 only
+        int bestIdx = 0, bestScore = INT32_MIN;                    // lane 0 only
         for (int base = 0; base < m; base += 32) {
-            int idx = base + lane;
-            int my1 = 0, my2 = 0, myl = 0;
-            if (idx < m) { my1 = C.s1[a + idx]; my2 = C.s2[a + idx]; myl = C.ln[a + idx]; }
-            int cnt = m - base < 32 ? m - base : 32;
-            for (int t = 0; t < cnt; t++) {
-                int i1 = __shfl_sync(0xffffffffu, my1, t), i2 = __shfl_sync(0xffffffffu, my2, t), il = __shfl_sync(0xffffffffu, myl, t);
-                if (lane == 0) {
-                    const int i = base + t;
+            const int idx = base + lane;
+            if (idx < m) { const int sl = idx & (CH_RING - 1); W.s1[sl] = C.s1[a + idx]; W.s2[sl] = C.s2[a + idx]; W.ln[sl] = C.ln[a + idx]; }
+            __syncwarp();
+            const int cnt = m - base < 32 ? m - base : 32;
+            if (lane == 0) {
+                const int lo_ring = base - (CH_RING - 32);         // entries [lo_ring, base + 32) are in the ring
+                for (int t = 0; t < cnt; t++) {
+                    const int i = base + t, sl = i & (CH_RING - 1);
+                    const int i1 = W.s1[sl], i2 = W.s2[sl], il = W.ln[sl];
                     int best = il, from = -1, adj = 0;
                     const int idiag = i2 - i1;
                     for (int j = i - 1; j >= 0; j--) {
-                        int j1, j2, jl, jsc, jpm;
-                        if (j == i - 1) { j1 = p_s1; j2 = p_s2; jl = p_ln; jsc = p_sc; jpm = p_pm; }
-                        else { jpm = C.pm[a + j]; }
+                        const bool in_ring = j >= lo_ring;
+                        const int js = j & (CH_RING - 1);
+                        const int jpm = in_ring ? W.pm[js] : C.pm[a + j];
                         if (jpm + il < best || (from == -1 && jpm + il <= best)) break;
-                        if (j != i - 1) { j1 = C.s1[a + j]; j2 = C.s2[a + j]; jl = C.ln[a + j]; jsc = C.score[a + j]; }
+                        int j1, j2, jl, jsc;
+                        if (in_ring) { j1 = W.s1[js]; j2 = W.s2[js]; jl = W.ln[js]; jsc = W.sc[js]; }
+                        else { j1 = C.s1[a + j]; j2 = C.s2[a + j]; jl = C.ln[a + j]; jsc = C.score[a + j]; }
                         int ol1 = j1 + jl - i1, ol = ol1 > 0 ? ol1 : 0, ol2 = j2 + jl - i2;
                         if (ol2 > ol) ol = ol2;
                         int dd = idiag - (j2 - j1); if (dd < 0) dd = -dd;
                         int v = jsc + il - (ol + dd);
                         if (v > best || (v == best && from != -1)) { best = v; from = j; adj = ol; }
                     }
-                    int pmv = i == 0 || best > p_pm ? best : p_pm;
-                    C.score[a + i] = best; C.from[a + i] = from; C.adj[a + i] = adj; C.pm[a + i] = pmv;
+                    const int ppm = i > 0 ? W.pm[(i - 1) & (CH_RING - 1)] : 0;
+                    const int pmv = i == 0 || best > ppm ? best : ppm;
+                    W.sc[sl] = best; W.pm[sl] = pmv; W.from[t] = from; W.adj[t] = adj;
                     if (best > bestScore) { bestScore = best; bestIdx = i; }
-                    p_s1 = i1; p_s2 = i2; p_ln = il; p_sc = best; p_pm = pmv;
                 }
             }
+            __syncwarp();
+            if (idx < m) { const int sl = idx & (CH_RING - 1); C.score[a + idx] = W.sc[sl]; C.from[a + idx] = W.from[lane]; C.adj[a + idx] = W.adj[lane]; C.pm[a + idx] = W.pm[sl]; }
+            __syncwarp();
         }
-        // ---- mark the best chain, sum its lengths
+        // ---- mark the best chain, sum its lengths (from[i] < i: the walk only moves down)
         int total = 0, root = 0;
-        if (lane == 0) {
-            for (int i = bestIdx; i >= 0; i = C.from[a + i]) { C.good[a + i] = 1; total += C.ln[a + i]; root = i; }
+        int cur = __shfl_sync(0xffffffffu, bestIdx, 0);
+        while (cur >= 0) {
+            const int base = cur & ~31, idx = base + lane;
+            int f = -1, l = 0;
+            if (idx < m) { f = C.from[a + idx]; l = C.ln[a + idx]; }
+            W.from[lane] = f; W.adj[lane] = l;
+            __syncwarp();
+            unsigned mark = 0;
+            if (lane == 0) {
+                int c = cur;
+                while (c >= base) { mark |= 1u << (c - base); total += W.adj[c - base]; root = c; c = W.from[c - base]; }
+                cur = c;
+            }
+            mark = __shfl_sync(0xffffffffu, mark, 0); cur = __shfl_sync(0xffffffffu, cur, 0);
+            if ((mark >> lane) & 1u) C.good[a + idx] = 1;
+            __syncwarp();
         }
-        __syncwarp();
         total = __shfl_sync(0xffffffffu, total, 0); root = __shfl_sync(0xffffffffu, root, 0);
         // ---- emit (chain members in index order, trimmed by their overlap with the predecessor)
         if (total >= mincluster) {
@@ -259,6 +283,7 @@ __device__ void chain_component(const ChainArrays &C, int64_t a, int m, int minc
 
 __global__ void __launch_bounds__(128) k_cl_chains(ChainArrays C, const uint32_t *__restrict__ cstart, uint32_t *counters, int64_t n, int mincluster)
 {
+    __shared__ ChainShared W[4];
     const int lane = threadIdx.x & 31;
     const uint32_t ncomp = counters[0];
     for (;;) {
@@ -268,7 +293,8 @@ __global__ void __launch_bounds__(128) k_cl_chains(ChainArrays C, const uint32_t
         if (c >= ncomp) break;
         int64_t a = cstart[c];
         int64_t b = c + 1 < ncomp ? (int64_t)cstart[c + 1] : n;
-        chain_component(C, a, (int)(b - a), mincluster);
+        chain_component(C, a, (int)(b - a), mincluster, W[threadIdx.x >> 5]);
+        __syncwarp();
     }
 }
 

@@ -118,6 +118,7 @@ static inline char *pmn_fmt_int(char *p, long long v)
     return p;
 }
 
+int pmn_last_code();                          // code of the calling thread's last pmn_set_error (pmn_api.cu)
 void pmn_apply_device_sched(int workers);     // whether host threads spin or yield while they wait for the device (pmn_api.cu)
 
 // stage entry points (defined in the .cu files)

@@ -169,7 +169,7 @@ static int sched_run(pmn_sched *s, int ng, const char *const *fasta, const size_
                 void *o = build();
                 lk.lock();
                 sl.obj = o; sl.state = o ? ST_READY : ST_FAILED;
-                if (!o && !s->err_code) { s->err_code = PMN_E_INTERNAL; s->err = pmn_last_error(nullptr); }
+                if (!o && !s->err_code) { const int ec = pmn_last_code(); s->err_code = ec < 0 ? ec : PMN_E_INTERNAL; s->err = pmn_last_error(nullptr); }   // the builder ran on this thread: its code and message
                 if (!o) { std::lock_guard<std::mutex> lk2(s->bmu); failed.store(1); s->bcv.notify_all(); }      // under bmu: a waiter between its predicate and its block cannot miss it
                 s->cv.notify_all();
                 return o;

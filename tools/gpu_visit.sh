@@ -1,0 +1,18 @@
+#!/bin/bash
+# One GPU visit (run under gpurun): tools/gpu_visit.sh <tag> [steps...]
+#   steps: tests smoke bench bench_ref ncu_launches ncu_full  (default: tests smoke bench)
+# Everything lands in gpurun_out/<tag>_*.  Each step has its own timeout, a failing step does not stop the others.
+tag=${1:-visit}; shift
+steps=${@:-tests smoke bench}
+mkdir -p gpurun_out
+for s in $steps; do
+  case $s in
+    tests)   timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${tag}_pytest.log; tail -5 gpurun_out/${tag}_pytest.log ;;
+    tests_all) timeout 1800 python -m pytest tests -m gpu -q > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${tag}_pytest.log; tail -15 gpurun_out/${tag}_pytest.log ;;
+    smoke)   timeout 300 python __graft_entry__.py smoke > gpurun_out/${tag}_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/${tag}_smoke.log ;;
+    bench)   timeout 900 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"; head -c 400 gpurun_out/${tag}_bench.json; echo ;;
+    bench_ref) timeout 900 python bench.py --impl reference --steps 1 --warmup 1 > gpurun_out/${tag}_bench_ref.json 2> gpurun_out/${tag}_bench_ref.err; echo "ref rc=$?"; head -c 300 gpurun_out/${tag}_bench_ref.json; echo ;;
+    ncu_launches) timeout 900 ncu --metrics gpu__time_duration.sum,sm__cycles_active.avg,smsp__inst_executed.sum --clock-control none --csv --log-file gpurun_out/${tag}_launches_bench.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/${tag}_ncu_launches.log 2>&1; echo "ncu launches rc=$?" ;;
+    *) echo "unknown step $s" ;;
+  esac
+done
