@@ -113,6 +113,9 @@ void *pmn_ctx_stream(const pmn_ctx *c);
 /* running totals since pmn_ctx_create: out[0] kernels launched, out[1] host->device bytes,
  * out[2] device->host bytes, out[3] pairs aligned */
 void pmn_ctx_counters(const pmn_ctx *c, int64_t out[4]);
+/* host waits for the device (cudaStreamSynchronize between stages, where the host sizes the next stage from a device count)
+ * made for this context so far: 4 per single-record pair (anchors, clusters, alignments, rows), plus the index builds' */
+int64_t pmn_ctx_sync_count(const pmn_ctx *c);
 /* INT32 ALU issue rate of this GPU in 10^9 ops/s (dependent-free IADD3/VIMNMX chains on every SM):
  * the roofline denominator of the extension DP, which MEASURED_PEAKS.json does not hold */
 int  pmn_measure_int32_peak(pmn_ctx *c, double *gops_per_s, double *sm_mhz_effective);
@@ -202,6 +205,7 @@ void pmn_sched_destroy(pmn_sched *s);
 int  pmn_sched_workers(const pmn_sched *s);
 pmn_ctx *pmn_sched_ctx(const pmn_sched *s, int k);          /* worker k's context (borrowed) */
 void pmn_sched_counters(const pmn_sched *s, int64_t out[4]); /* pmn_ctx_counters summed over the workers */
+int64_t pmn_sched_sync_count(const pmn_sched *s);            /* pmn_ctx_sync_count summed over the workers */
 /* genomes as FASTA bytes in HOST memory */
 int  pmn_sched_align_fasta(pmn_sched *s, int n_genomes, const char *const *fasta, const size_t *bytes, const char *const *names,
                            int n_pairs, const int32_t *ref, const int32_t *qry, const pmn_opts *o, pmn_result **out);

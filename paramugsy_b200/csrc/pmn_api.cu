@@ -251,6 +251,8 @@ extern "C" void pmn_ctx_counters(const pmn_ctx *c, int64_t out[4])
     out[0] = c->launches; out[1] = c->h2d_bytes; out[2] = c->d2h_bytes; out[3] = c->pairs;
 }
 
+extern "C" int64_t pmn_ctx_sync_count(const pmn_ctx *c) { return c ? (int64_t)c->syncs : 0; }
+
 // dependent-free chains of (add, max) on 8 accumulators per thread: the instruction mix of the
 // DP inner loop (IADD3 / VIMNMX on the integer pipe)
 __global__ void __launch_bounds__(1024) k_int32_peak(int *out, int seed, int iters)

@@ -9,7 +9,9 @@
 // position) order from pmn_seed.cu):
 //   1. Filter_Matches: a segmented prefix-max of the match ends splits each section into
 //      independent overlap groups; one thread walks each group sequentially (the original
-//      is sequential by construction), then an ordered compaction drops the filtered ones
+//      is sequential by construction).  Filtered anchors stay in place as dead entries: they
+//      unite with nothing, sort as components of their own and emit nothing, so the host does
+//      not have to wait for their count
 //   2. union-find over the separation/diagonal window (lock-free hooking of the larger root
 //      under the smaller, so a component's label is its smallest member: deterministic)
 //   3. stable radix sort by label = mgaps' qsort by (cluster id, start2, start1)
@@ -76,14 +78,6 @@ __global__ void __launch_bounds__(128) k_cl_filter(int4 *__restrict__ anc, int64
     }
 }
 
-__global__ void __launch_bounds__(256) k_cl_compact_anchors(const int4 *__restrict__ anc, const uint32_t *__restrict__ good, const uint32_t *__restrict__ pos,
-                                                           int64_t n, int4 *__restrict__ out)
-{
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || !good[i]) return;
-    out[pos[i]] = anc[i];
-}
-
 // ------------------------------------------------------------------------------------ 2. union-find
 
 __device__ __forceinline__ uint32_t uf_find(uint32_t *parent, uint32_t x)
@@ -111,10 +105,11 @@ __global__ void __launch_bounds__(256) k_cl_init_parent(uint32_t *parent, int64_
 
 // lim[sep] = max(diagdiff, (long)(diagfactor * sep)) for sep = 0..maxgap, computed on the host in
 // double precision exactly like the oracle; a negative separation uses diagdiff
-__global__ void __launch_bounds__(256) k_cl_union(const int4 *__restrict__ f, int64_t n, int maxgap, int diagdiff, const int32_t *__restrict__ lim, uint32_t *parent)
+__global__ void __launch_bounds__(256) k_cl_union(const int4 *__restrict__ f, const uint32_t *__restrict__ good, int64_t n, int maxgap, int diagdiff,
+                                                 const int32_t *__restrict__ lim, uint32_t *parent)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= n || !good[i]) return;
     int4 A = f[i];
     int i_end = A.y + A.z, i_diag = A.y - A.x;
     for (int64_t j = i + 1; j < n; j++) {
@@ -122,6 +117,7 @@ __global__ void __launch_bounds__(256) k_cl_union(const int4 *__restrict__ f, in
         if (B.w != A.w) break;
         int sep = B.y - i_end;
         if (sep > maxgap) break;
+        if (!good[j]) continue;                                  // filtered out: as if it were not in the list
         int dd = (B.y - B.x) - i_diag; if (dd < 0) dd = -dd;
         int l = sep >= 0 ? lim[sep] : diagdiff;
         if (dd <= l) uf_unite(parent, (uint32_t)i, (uint32_t)j);
@@ -138,13 +134,15 @@ __global__ void __launch_bounds__(256) k_cl_labels(uint32_t *parent, int64_t n, 
 
 // ------------------------------------------------------------------------------------ 3. gather in (label, start2, start1) order
 
-__global__ void __launch_bounds__(256) k_cl_gather(const int4 *__restrict__ f, const uint64_t *__restrict__ skeys, const uint32_t *__restrict__ svals, int64_t n,
+__global__ void __launch_bounds__(256) k_cl_gather(const int4 *__restrict__ f, const uint32_t *__restrict__ good, const uint64_t *__restrict__ skeys, const uint32_t *__restrict__ svals, int64_t n,
                                                   int32_t *__restrict__ s1, int32_t *__restrict__ s2, int32_t *__restrict__ ln, int32_t *__restrict__ tg,
-                                                  uint32_t *__restrict__ cflag)
+                                                  uint32_t *__restrict__ cflag, uint8_t *__restrict__ alive)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int4 a = f[svals[i]];
+    const uint32_t src = svals[i];
+    int4 a = f[src];
+    alive[i] = good[src] ? 1 : 0;                  // a filtered anchor is a component of its own (it was never united) that emits nothing
     s1[i] = a.x; s2[i] = a.y; ln[i] = a.z; tg[i] = a.w;
     cflag[i] = (i == 0 || skeys[i] != skeys[i - 1]) ? 1u : 0u;
 }
@@ -162,6 +160,7 @@ __global__ void __launch_bounds__(256) k_cl_compstarts(const uint32_t *__restric
 
 struct ChainArrays {
     int32_t *s1, *s2, *ln; const int32_t *tg;
+    const uint8_t *alive;   // 0: the slot holds an anchor Filter_Matches dropped
     int32_t *score, *from, *adj, *pm; uint8_t *good;
     int32_t *om;            // emitted matches, 3 ints per slot
     uint32_t *om_valid;     // slot holds a match
@@ -293,6 +292,7 @@ __global__ void __launch_bounds__(128) k_cl_chains(ChainArrays C, const uint32_t
         if (c >= ncomp) break;
         int64_t a = cstart[c];
         int64_t b = c + 1 < ncomp ? (int64_t)cstart[c + 1] : n;
+        if (!C.alive[a]) continue;
         chain_component(C, a, (int)(b - a), mincluster, W[threadIdx.x >> 5]);
         __syncwarp();
     }
@@ -334,85 +334,80 @@ int pmn_cluster_impl(pmn_ctx *c, const pmn_index *, const pmn_seq *, const pmn_o
     const unsigned g = (unsigned)((n + 255) / 256);
     int4 *anc = S.anchors.as<int4>();
     if (S.cl_a.ensure(8 * (size_t)n) || S.cl_b.ensure(4 * (size_t)n) || S.cl_c.ensure((size_t)n) || S.cl_d.ensure((size_t)n) ||
-        S.cl_e.ensure(4 * (size_t)n) || S.cl_f.ensure(16 * (size_t)n) || S.scan_tmp.ensure(8 * pmn_scan_scratch_elems(n)) || S.ensure_pinned(64)) return -3;
+        S.cl_e.ensure(4 * (size_t)n) || S.cl_f.ensure(4 * (size_t)n) || S.scan_tmp.ensure(8 * pmn_scan_scratch_elems(n)) || S.ensure_pinned(64)) return -3;
     uint32_t *tail = (uint32_t *)S.pinned;
 
-    // 1. filter
+    // 1. filter (in place: `good` marks the survivors)
     long long *ekey = S.cl_a.as<long long>(); uint32_t *good = S.cl_b.as<uint32_t>(); uint8_t *gstart = S.cl_c.as<uint8_t>(), *tent = S.cl_d.as<uint8_t>();
-    uint32_t *pos = S.cl_e.as<uint32_t>(); int4 *filt = S.cl_f.as<int4>();
     k_cl_endkeys<<<g, 256, 0, st>>>(anc, n, ekey);
     pmn_scan<long long, OpMaxI64, true>(ekey, ekey, n, S.scan_tmp.as<long long>(), st);
     k_cl_groupflags<<<g, 256, 0, st>>>(anc, ekey, n, gstart);
     k_cl_filter<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(anc, n, gstart, tent, good);
-    pmn_scan<uint32_t, OpAddU32, false>(good, pos, n, S.scan_tmp.as<uint32_t>(), st);
-    k_cl_compact_anchors<<<g, 256, 0, st>>>(anc, good, pos, n, filt);
-    launches += 10;
-    PMN_D2H(c, tail, pos + (n - 1), 4);
-    PMN_D2H(c, tail + 1, good + (n - 1), 4);
-    PMN_CUDA_OK(cudaStreamSynchronize(st));
-    const int64_t nf = (int64_t)tail[0] + tail[1];
-    if (nf <= 0) return 0;       // nothing left to cluster: an empty result (a pair without clusters), not a failure of the whole batch
-    const unsigned gf = (unsigned)((nf + 255) / 256);
+    launches += 6;
 
-    // 2. union-find
-    std::vector<int32_t> lim((size_t)o->maxgap + 1);
-    for (int s = 0; s <= o->maxgap; s++) { long l = (long)(o->diagfactor * (double)s); lim[(size_t)s] = (int32_t)(l > o->diagdiff ? l : o->diagdiff); }
-    if (S.cl_g.ensure(4 * lim.size()) || S.cl_h.ensure(4 * (size_t)nf) || S.k0.ensure(8 * (size_t)nf) || S.k1.ensure(8 * (size_t)nf) ||
-        S.v0.ensure(4 * (size_t)nf) || S.v1.ensure(4 * (size_t)nf)) return -3;
-    PMN_H2D(c, S.cl_g.p, lim.data(), 4 * lim.size());
+    // 2. union-find.  lim[sep] = max(diagdiff, (long)(diagfactor * sep)) lives in the context and is uploaded when the options change
+    if (S.lim_maxgap != o->maxgap || S.lim_diagdiff != o->diagdiff || S.lim_diagfactor != o->diagfactor) {
+        S.lim_host.resize((size_t)o->maxgap + 1);
+        for (int s = 0; s <= o->maxgap; s++) { long l = (long)(o->diagfactor * (double)s); S.lim_host[(size_t)s] = (int32_t)(l > o->diagdiff ? l : o->diagdiff); }
+        if (S.cl_g.ensure(4 * S.lim_host.size())) return -3;
+        PMN_H2D(c, S.cl_g.p, S.lim_host.data(), 4 * S.lim_host.size());
+        S.lim_maxgap = o->maxgap; S.lim_diagdiff = o->diagdiff; S.lim_diagfactor = o->diagfactor;
+    }
+    if (S.cl_h.ensure(4 * (size_t)n) || S.k0.ensure(8 * (size_t)n) || S.k1.ensure(8 * (size_t)n) ||
+        S.v0.ensure(4 * (size_t)n) || S.v1.ensure(4 * (size_t)n)) return -3;
     uint32_t *parent = S.cl_h.as<uint32_t>();
-    k_cl_init_parent<<<gf, 256, 0, st>>>(parent, nf);
-    k_cl_union<<<gf, 256, 0, st>>>(filt, nf, o->maxgap, o->diagdiff, S.cl_g.as<int32_t>(), parent);
-    k_cl_labels<<<gf, 256, 0, st>>>(parent, nf, S.k0.as<uint64_t>(), S.v0.as<uint32_t>());
+    k_cl_init_parent<<<g, 256, 0, st>>>(parent, n);
+    k_cl_union<<<g, 256, 0, st>>>(anc, good, n, o->maxgap, o->diagdiff, S.cl_g.as<int32_t>(), parent);
+    k_cl_labels<<<g, 256, 0, st>>>(parent, n, S.k0.as<uint64_t>(), S.v0.as<uint32_t>());
     launches += 3;
-    PMN_CUDA_OK(cudaStreamSynchronize(st));   // lim is a stack vector
 
     // 3. sort by label (stable: members stay in (start2, start1) order)
-    int nb = 1; while ((1ll << nb) < nf) nb++;
-    int where = pmn_radix_sort(S.k0.as<uint64_t>(), S.v0.as<uint32_t>(), S.k1.as<uint64_t>(), S.v1.as<uint32_t>(), nf, nb, S.rs, st, &launches);
+    int nb = 1; while ((1ll << nb) < n) nb++;
+    int where = pmn_radix_sort(S.k0.as<uint64_t>(), S.v0.as<uint32_t>(), S.k1.as<uint64_t>(), S.v1.as<uint32_t>(), n, nb, S.rs, st, &launches);
     if (where < 0) return -3;
     const uint64_t *skeys = where ? S.k1.as<uint64_t>() : S.k0.as<uint64_t>();
     const uint32_t *svals = where ? S.v1.as<uint32_t>() : S.v0.as<uint32_t>();
 
     // 4. chains
-    if (S.cl_i.ensure(4 * 4 * (size_t)nf) || S.cl_j.ensure(4 * 4 * (size_t)nf) || S.cl_k.ensure((size_t)nf + 16) ||
-        S.cl_l.ensure(4 * 8 * (size_t)nf) || S.cl_counters.ensure(64) || S.cl_b.ensure(4 * (size_t)nf) || S.cl_e.ensure(4 * (size_t)nf) ||
-        S.cl_a.ensure(4 * 2 * (size_t)nf)) return -3;
+    if (S.cl_i.ensure(4 * 4 * (size_t)n) || S.cl_j.ensure(4 * 4 * (size_t)n) || S.cl_k.ensure(2 * (size_t)n + 32) ||
+        S.cl_l.ensure(4 * 8 * (size_t)n) || S.cl_counters.ensure(64)) return -3;
     int32_t *blk = S.cl_i.as<int32_t>();          // s1, s2, ln, tg
     int32_t *blk2 = S.cl_j.as<int32_t>();         // score, from, adj, pm
     int32_t *outb = S.cl_l.as<int32_t>();         // om (3n), oc (3n), om_valid (n), oc_valid (n)
     ChainArrays C;
-    C.s1 = blk; C.s2 = blk + nf; C.ln = blk + 2 * nf; C.tg = blk + 3 * nf;
-    C.score = blk2; C.from = blk2 + nf; C.adj = blk2 + 2 * nf; C.pm = blk2 + 3 * nf;
+    C.s1 = blk; C.s2 = blk + n; C.ln = blk + 2 * n; C.tg = blk + 3 * n;
+    C.score = blk2; C.from = blk2 + n; C.adj = blk2 + 2 * n; C.pm = blk2 + 3 * n;
     C.good = S.cl_k.as<uint8_t>();
-    C.om = outb; C.oc = outb + 3 * nf; C.om_valid = (uint32_t *)(outb + 6 * nf); C.oc_valid = (uint32_t *)(outb + 7 * nf);
-    uint32_t *cflag = S.cl_b.as<uint32_t>(), *cpos = S.cl_e.as<uint32_t>(), *cstart = S.cl_a.as<uint32_t>();
+    uint8_t *alive = C.good + ((size_t)n + 15) / 16 * 16; C.alive = alive;
+    C.om = outb; C.oc = outb + 3 * n; C.om_valid = (uint32_t *)(outb + 6 * n); C.oc_valid = (uint32_t *)(outb + 7 * n);
+    uint32_t *cflag = S.cl_f.as<uint32_t>(), *cpos = S.cl_e.as<uint32_t>(), *cstart = S.cl_a.as<uint32_t>();      // `good` (cl_b) is read by the gather
     uint32_t *counters = S.cl_counters.as<uint32_t>();
-    PMN_CUDA_OK(cudaMemsetAsync(C.good, 0, (size_t)nf, st));
-    PMN_CUDA_OK(cudaMemsetAsync(C.om_valid, 0, 8 * (size_t)nf, st));     // om_valid and oc_valid are adjacent
-    k_cl_gather<<<gf, 256, 0, st>>>(filt, skeys, svals, nf, C.s1, C.s2, C.ln, (int32_t *)C.tg, cflag);
-    pmn_scan<uint32_t, OpAddU32, false>(cflag, cpos, nf, S.scan_tmp.as<uint32_t>(), st);
-    k_cl_compstarts<<<gf, 256, 0, st>>>(cflag, cpos, nf, cstart, counters);
+    PMN_CUDA_OK(cudaMemsetAsync(C.good, 0, (size_t)n, st));
+    PMN_CUDA_OK(cudaMemsetAsync(C.om_valid, 0, 8 * (size_t)n, st));     // om_valid and oc_valid are adjacent
+    k_cl_gather<<<g, 256, 0, st>>>(anc, good, skeys, svals, n, C.s1, C.s2, C.ln, (int32_t *)C.tg, cflag, alive);
+    pmn_scan<uint32_t, OpAddU32, false>(cflag, cpos, n, S.scan_tmp.as<uint32_t>(), st);
+    k_cl_compstarts<<<g, 256, 0, st>>>(cflag, cpos, n, cstart, counters);
     int blocks = c->sm_count * 4;
-    { int64_t need = (nf + 3) / 4; if (need < blocks) blocks = (int)need; if (blocks < 1) blocks = 1; }
-    k_cl_chains<<<blocks, 128, 0, st>>>(C, cstart, counters, nf, o->mincluster);
+    { int64_t need = (n + 3) / 4; if (need < blocks) blocks = (int)need; if (blocks < 1) blocks = 1; }
+    k_cl_chains<<<blocks, 128, 0, st>>>(C, cstart, counters, n, o->mincluster);
     launches += 6;
 
     // 5. compact matches and clusters, in (component, extraction) order
     uint32_t *mpos = cflag, *kpos = cpos;      // reuse
-    pmn_scan<uint32_t, OpAddU32, false>(C.om_valid, mpos, nf, S.scan_tmp.as<uint32_t>(), st);
-    pmn_scan<uint32_t, OpAddU32, false>(C.oc_valid, kpos, nf, S.scan_tmp.as<uint32_t>(), st);
-    PMN_D2H(c, tail, mpos + (nf - 1), 4);
-    PMN_D2H(c, tail + 1, C.om_valid + (nf - 1), 4);
-    PMN_D2H(c, tail + 2, kpos + (nf - 1), 4);
-    PMN_D2H(c, tail + 3, C.oc_valid + (nf - 1), 4);
-    PMN_CUDA_OK(cudaStreamSynchronize(st));
+    pmn_scan<uint32_t, OpAddU32, false>(C.om_valid, mpos, n, S.scan_tmp.as<uint32_t>(), st);
+    pmn_scan<uint32_t, OpAddU32, false>(C.oc_valid, kpos, n, S.scan_tmp.as<uint32_t>(), st);
+    PMN_D2H(c, tail, mpos + (n - 1), 4);
+    PMN_D2H(c, tail + 1, C.om_valid + (n - 1), 4);
+    PMN_D2H(c, tail + 2, kpos + (n - 1), 4);
+    PMN_D2H(c, tail + 3, C.oc_valid + (n - 1), 4);
+    PMN_CUDA_OK(cudaStreamSynchronize(st));      // the one host round trip of the stage: the extension sizes its grids from these counts
+    c->syncs++;
     const int64_t nm = (int64_t)tail[0] + tail[1], nc = (int64_t)tail[2] + tail[3];
     launches += 6;
     if (nc > 0) {
         if (S.cl_matches.ensure(12 * (size_t)nm) || S.cl_recs.ensure(16 * (size_t)nc)) return -3;
-        k_cl_out_matches<<<gf, 256, 0, st>>>(C.om, C.om_valid, mpos, nf, S.cl_matches.as<int32_t>());
-        k_cl_out_clusters<<<gf, 256, 0, st>>>(C.oc, C.oc_valid, kpos, mpos, nf, S.cl_recs.as<int4>());
+        k_cl_out_matches<<<g, 256, 0, st>>>(C.om, C.om_valid, mpos, n, S.cl_matches.as<int32_t>());
+        k_cl_out_clusters<<<g, 256, 0, st>>>(C.oc, C.oc_valid, kpos, mpos, n, S.cl_recs.as<int4>());
         launches += 2;
     }
     PMN_CUDA_OK(cudaGetLastError());

@@ -16,7 +16,7 @@
 
 #include "../../include/pmn_params.h"
 
-#define PMN_PAD_WORDS 96   /* >= seeding tile words + slack, see pmn_seed.cu */
+#define PMN_PAD_WORDS 192  /* >= words one seeding tile stages (SEED_WORDS, pmn_seed.cu: static_assert there) + slack */
 
 struct PmnError { int code; char msg[480]; };
 
@@ -64,6 +64,10 @@ struct DevBuf {
         // cudaMalloc / cudaFree serialise the whole device, which would stall every other worker
         cudaError_t e = ts ? cudaMallocAsync(&p, want, ts) : cudaMalloc(&p, want);
         if (e != cudaSuccess) { p = nullptr; cap = 0; return pmn_set_error(-3, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); }
+        // new memory is zeroed once: the scan descriptors and ticket counters that live in scratch buffers (pmn_prims.cuh) rely on
+        // never seeing anything but zeros or what an earlier scan of this process wrote
+        e = ts ? cudaMemsetAsync(p, 0, want, ts) : cudaMemset(p, 0, want);
+        if (e != cudaSuccess) { if (ts) cudaFreeAsync(p, ts); else cudaFree(p); p = nullptr; cap = 0; return pmn_set_error(-2, "cudaMemset(%zu) failed: %s", want, cudaGetErrorString(e)); }
         cap = want;
         pmn_count_alloc(want, had);
         return 0;

@@ -1931,10 +1931,14 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     pmn_scan<uint32_t, OpAddU32, false>(pstart, ppos, nm, S.scan_tmp.as<uint32_t>(), st);
     launches += 4;
     uint32_t *tail = (uint32_t *)S.pinned;
-    PMN_D2H(c, tail, ppos + (nm - 1), 4);
-    PMN_D2H(c, tail + 1, pstart + (nm - 1), 4);
-    PMN_CUDA_OK(cudaStreamSynchronize(st));       // also: h may go out of scope
-    const int64_t np = (int64_t)tail[0] + tail[1];
+    int64_t np = nc0;           // one reference record: no mgaps cluster is split, the pieces are the clusters and the host knows their number
+    if (nref > 1) {
+        PMN_D2H(c, tail, ppos + (nm - 1), 4);
+        PMN_D2H(c, tail + 1, pstart + (nm - 1), 4);
+        PMN_CUDA_OK(cudaStreamSynchronize(st));
+        c->syncs++;
+        np = (int64_t)tail[0] + tail[1];
+    }
 
     // pieces sorted by (query record, reference record, first reference start), stable
     if (S.k0.ensure(8 * (size_t)np) || S.k1.ensure(8 * (size_t)np) || S.v0.ensure(4 * (size_t)np) || S.v1.ensure(4 * (size_t)np) ||
@@ -1959,10 +1963,14 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     pmn_scan<uint32_t, OpAddU32, false>(sflag, spos, np, S.scan_tmp.as<uint32_t>(), st);
     k_ex_syntenies<<<gp, 256, 0, st>>>(skeys, sflag, spos, np, cl, syn, roff, rlen, qoff, qlen, q->n);
     launches += 6;
-    PMN_D2H(c, tail, spos + (np - 1), 4);
-    PMN_D2H(c, tail + 1, sflag + (np - 1), 4);
-    PMN_CUDA_OK(cudaStreamSynchronize(st));
-    const int nS = (int)(tail[0] + tail[1]);
+    int nS = 1;                 // one reference record and one query record: one synteny
+    if (nref > 1 || nqry > 1) {
+        PMN_D2H(c, tail, spos + (np - 1), 4);
+        PMN_D2H(c, tail + 1, sflag + (np - 1), 4);
+        PMN_CUDA_OK(cudaStreamSynchronize(st));
+        c->syncs++;
+        nS = (int)(tail[0] + tail[1]);
+    }
     k_ex_syn_caps<<<1, 32, 0, st>>>(syn, nS, cl);
     launches++;
 
@@ -2073,6 +2081,7 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     unsigned long long *hc = (unsigned long long *)S.pinned;
     PMN_D2H(c, hc, X.counters, 256);
     PMN_CUDA_OK(cudaStreamSynchronize(st));
+    c->syncs++;
     const unsigned long long errflags = hc[4];
     if (joblog) {
         const size_t nrec = (size_t)std::min<unsigned long long>(hc[15], X.dbg_cap);
@@ -2126,6 +2135,7 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
         if (nd) PMN_D2H(c, res->al_deltas.data(), dflat, 4 * (size_t)nd);
         PMN_D2H(c, ds.data(), dstart, 4 * (size_t)(nal + 1));
         PMN_CUDA_OK(cudaStreamSynchronize(st));
+        c->syncs++;
         res->al_doff.assign(ds.begin(), ds.end());
     }
     PMN_CUDA_OK(cudaGetLastError());

@@ -29,12 +29,16 @@ struct pmn_index {
     const pmn_seq *seq = nullptr;       // borrowed: the caller keeps the sequence alive
     int64_t n = 0;
     // one contiguous image in HBM (so that it can be replicated by a single NCCL broadcast):
-    //   [0,256) header {magic, n, K, rounds} | int32 SA[n] | int32 LCP[n] | uint32 table[4^K + 1], each 256-byte aligned
+    //   [0,256) header {magic, n, K, rounds} | int32 SA[n] | int32 LCP[n] | uint32 table[4^K + 1] | uint8 skip[n + 1], each 256-byte aligned
     DevBuf blob;
-    size_t off_sa = 0, off_lcp = 0, off_table = 0, blob_bytes = 0;
+    size_t off_sa = 0, off_lcp = 0, off_table = 0, off_skip = 0, blob_bytes = 0;
     uint32_t *sa() const { return (uint32_t *)((char *)blob.p + off_sa); }
     int32_t *lcp() const { return (int32_t *)((char *)blob.p + off_lcp); }
     uint32_t *table() const { return (uint32_t *)((char *)blob.p + off_table); }
+    // skip[E] for a reference coordinate E (one past the end of a match): E - skip[E] is the first reference position p whose
+    // suffix shares E - p or more bases with another suffix (255: further back than 254).  A query position whose match ends at E
+    // and starts before that p is matched nowhere else as long: the seeding kernel steps over those positions (pmn_seed.cu).
+    uint8_t *skip() const { return (uint8_t *)blob.p + off_skip; }
     int K = 0;
     int rounds = 0;                     // prefix-doubling rounds after the 16-mer pass
     float ms_build = 0, wall_ms_build = 0;
@@ -74,6 +78,7 @@ struct pmn_ctx {
     PmnError err{};
     Scratch *scratch = nullptr;
     long launches = 0;                  // kernels launched by this library (bench.py's gpu_launches)
+    long syncs = 0;                     // host waits for the device (cudaStreamSynchronize) inside the stages
     int64_t h2d_bytes = 0, d2h_bytes = 0, pairs = 0;
     std::shared_ptr<DevPool> pool;      // device buffers handed back by freed sequences / indexes, reused by the next ones;
                                         // the worker contexts of one pmn_sched share one pool (a genome packed or an index
@@ -126,7 +131,7 @@ int pmn_fasta_to_device(pmn_ctx *c, pmn_seq *s, const char *txt, size_t nb, cons
 int pmn_index_build_impl(pmn_ctx *c, const pmn_seq *ref, pmn_index *ix);
 int pmn_index_layout(pmn_ctx *c, const pmn_seq *ref, pmn_index *ix);   // sizes the image for ref and takes it from the pool
 struct PmnIndexHeader { uint64_t magic; int64_t n; int32_t K, rounds; };
-#define PMN_INDEX_MAGIC 0x31584449304e4d50ull   /* "PMN0IDX1" */
+#define PMN_INDEX_MAGIC 0x32584449304e4d50ull   /* "PMN0IDX2" */
 int pmn_seed_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_opts *o, int64_t *n_anchors, int part = 0, int nparts = 1);
 int pmn_cluster_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_opts *o, int64_t n_anchors);
 int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_opts *o, pmn_result *res);

@@ -327,6 +327,32 @@ __global__ void __launch_bounds__(256) k_lcp_text(PackedView s, const uint32_t *
     }
 }
 
+// ------------------------------------------------------------------------------------ skip table of the seeding kernel
+
+// rep(p) = longest prefix of the suffix at text position p that another suffix shares = max(LCP[slot], LCP[slot + 1]), and
+// e(p) = p + rep(p), the text coordinate where that repeat ends.  e is non-decreasing (a repeat at p of length l is a repeat
+// at p + 1 of length l - 1).  For a coordinate E the first p with e(p) >= E is what the seeding kernel asks for: a match of
+// the query that ends at E and starts before that p is longer than any repeat of its reference suffix, so it is the unique
+// longest match of its query position.  Thread p writes skip[E] = E - p for E in (e(p-1), e(p)] (E >= p there, because
+// e(p-1) >= p - 1); e being monotone the ranges tile [0, e(n-1)], and the last thread closes the table up to E = n, which
+// only makes the kernel look up one position more than it would have to.
+__global__ void __launch_bounds__(256) k_skip_e(const int32_t *__restrict__ rank, const int32_t *__restrict__ lcp, int64_t n, int32_t *__restrict__ e)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int64_t slot = rank[p] - 1;
+    const int32_t a = lcp[slot], b = slot + 1 < n ? lcp[slot + 1] : 0;
+    e[p] = (int32_t)p + (a > b ? a : b);
+}
+__global__ void __launch_bounds__(256) k_skip_fill(const int32_t *__restrict__ e, int64_t n, uint8_t *__restrict__ skip)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int64_t lo = p > 0 ? (int64_t)e[p - 1] + 1 : 0;
+    const int64_t hi = p + 1 < n ? (int64_t)e[p] : n;          // the last position closes the table: E <= n
+    for (int64_t E = lo; E <= hi; E++) { const int64_t d = E - p; skip[E] = (uint8_t)(d < 255 ? d : 255); }
+}
+
 // ------------------------------------------------------------------------------------ K-mer bucket table
 
 // bucket key of SA slot p: first K symbols, END padded with a, X padded with t — monotone in p.  It is the top 2K bits of
@@ -362,7 +388,7 @@ static inline size_t up256(size_t x) { return (x + 255) / 256 * 256; }
 extern "C" size_t pmn_index_image_bytes(int64_t n_bases)
 {
     if (n_bases < 1) return 0;
-    return 256 + 2 * up256(4 * (size_t)n_bases) + up256(4 * (((size_t)1 << (2 * index_K(n_bases))) + 1));
+    return 256 + 2 * up256(4 * (size_t)n_bases) + up256(4 * (((size_t)1 << (2 * index_K(n_bases))) + 1)) + up256((size_t)n_bases + 1);
 }
 
 int pmn_index_layout(pmn_ctx *c, const pmn_seq *ref, pmn_index *ix)
@@ -373,6 +399,7 @@ int pmn_index_layout(pmn_ctx *c, const pmn_seq *ref, pmn_index *ix)
     if (n > 0x7ffffff0ll) return pmn_set_error(PMN_E_ARG, "index: reference longer than 2^31 bases");
     ix->ctx = c; ix->seq = ref; ix->n = n; ix->K = index_K(n);
     ix->off_sa = 256; ix->off_lcp = ix->off_sa + up256(4 * (size_t)n); ix->off_table = ix->off_lcp + up256(4 * (size_t)n);
+    ix->off_skip = ix->off_table + up256(4 * (((size_t)1 << (2 * ix->K)) + 1));
     ix->blob_bytes = pmn_index_image_bytes(n);
     return pmn_pool_get(c, ix->blob, ix->blob_bytes) ? -3 : 0;
 }
@@ -469,6 +496,10 @@ int pmn_index_build_impl(pmn_ctx *c, const pmn_seq *ref, pmn_index *ix)
 
     // 3. the LCP entries the keys left open, in text order
     k_lcp_text<<<(unsigned)(((n + PMN_LCP_CHUNK - 1) / PMN_LCP_CHUNK + 255) / 256), 256, 0, st>>>(T, sa, rank, unres, ix->lcp()); launches++;
+
+    // 4. the skip table (needs the final ranks and the complete LCP array)
+    k_skip_e<<<gn, 256, 0, st>>>(rank, ix->lcp(), n, gs);          // the group starts are dead after the last round
+    k_skip_fill<<<gn, 256, 0, st>>>(gs, n, ix->skip()); launches += 2;
 
     k_index_header<<<1, 1, 0, st>>>((PmnIndexHeader *)ix->blob.p, n, K, rounds); launches++;
 

@@ -1,10 +1,13 @@
 // pmn_prims.cuh — hand-written device-wide primitives used by every stage:
-//   * scan (inclusive/exclusive, any associative op) — reduce / spine / downsweep
+//   * scan (inclusive/exclusive, any associative op) — one pass with decoupled look-back
 //   * ordered stream compaction built on it
 //   * stable LSD radix sort of (64-bit key, 32-bit value) pairs, 8 bits per pass
 // All launches go to the caller's stream; no host synchronisation inside.
 // Grids are sized in multiples of the SM count where the work allows (148 on B200).
 #pragma once
+#include <atomic>
+#include <cstring>
+
 #include "pmn_common.cuh"
 
 #ifdef __CUDACC__
@@ -39,63 +42,83 @@ __device__ __forceinline__ T pmn_block_scan_incl(T v, Op op, T *smem /* [32] */)
     return v;
 }
 
-// phase 1: one partial per tile
-template <class T, class Op>
-__global__ void __launch_bounds__(PMN_SCAN_THREADS) pmn_scan_reduce(const T *__restrict__ in, T *__restrict__ partial, int64_t n)
-{
-    __shared__ T sm[32];
-    Op op; T acc = Op::identity();
-    int64_t base = (int64_t)blockIdx.x * PMN_SCAN_TILE + (int64_t)threadIdx.x * PMN_SCAN_ITEMS;
-#pragma unroll
-    for (int k = 0; k < PMN_SCAN_ITEMS; k++) if (base + k < n) acc = op(acc, in[base + k]);
-    acc = pmn_block_scan_incl(acc, op, sm);
-    if (threadIdx.x == PMN_SCAN_THREADS - 1) partial[blockIdx.x] = acc;
-}
+// One pass over the data (decoupled look-back): a block takes the next tile (a ticket from a device counter, so every tile a
+// block waits for belongs to a block that is already running), scans it, publishes the tile's aggregate, adds up the
+// aggregates of the tiles before it (warp 0, 32 descriptors per step, back to the nearest tile whose inclusive prefix is
+// already known), publishes its own inclusive prefix and writes its part of the output.  One launch that reads the input
+// once instead of reduce / spine / downsweep: 2 n elements of traffic instead of 3 n and a third of the launches.
+//   A descriptor is {status, aggregate, inclusive}.  status = 2 * epoch (aggregate valid) or 2 * epoch + 1 (inclusive valid
+//   too); every scan of the process has its own epoch (a host counter), scratch memory is zeroed when it is allocated
+//   (DevBuf::grow_to), so whatever an earlier scan left in the scratch reads as "not yet".  The two counters in front (ticket,
+//   finished tiles) are put back to zero by the block that finishes last.
+struct PmnScanDesc { unsigned long long status, agg, incl; };
 
-// phase 2: one block scans the partials in place (exclusive), looping over them
-template <class T, class Op>
-__global__ void __launch_bounds__(1024) pmn_scan_spine(T *__restrict__ partial, int64_t m)
-{
-    __shared__ T sm[32]; __shared__ T carry_s;
-    Op op;
-    if (threadIdx.x == 0) carry_s = Op::identity();
-    __syncthreads();
-    for (int64_t base = 0; base < m; base += blockDim.x) {
-        int64_t i = base + threadIdx.x;
-        T v = i < m ? partial[i] : Op::identity();
-        T inc = pmn_block_scan_incl(v, op, sm);
-        T carry = carry_s;
-        // exclusive = carry (+) inclusive-of-previous; the shuffle runs on all lanes
-        T prev = __shfl_up_sync(0xffffffffu, inc, 1);
-        if ((threadIdx.x & 31) == 0) prev = threadIdx.x ? sm[(threadIdx.x >> 5) - 1] : Op::identity();
-        __syncthreads();
-        if (i < m) partial[i] = threadIdx.x ? op(carry, prev) : carry;
-        if (threadIdx.x == blockDim.x - 1) carry_s = op(carry, inc);
-        __syncthreads();
-    }
-}
+template <class T> __device__ __forceinline__ unsigned long long pmn_scan_pack(T v) { unsigned long long u = 0; memcpy(&u, &v, sizeof(T)); return u; }
+template <class T> __device__ __forceinline__ T pmn_scan_unpack(unsigned long long u) { T v; memcpy(&v, &u, sizeof(T)); return v; }
 
-// phase 3: rescan each tile with its offset
 template <class T, class Op, bool INCLUSIVE>
-__global__ void __launch_bounds__(PMN_SCAN_THREADS) pmn_scan_down(const T *__restrict__ in, T *__restrict__ out, const T *__restrict__ partial, int64_t n)
+__global__ void __launch_bounds__(PMN_SCAN_THREADS) pmn_scan_onepass(const T *__restrict__ in, T *__restrict__ out, int64_t n, unsigned *__restrict__ counters,
+                                                                    PmnScanDesc *__restrict__ desc, unsigned long long epoch, unsigned tiles)
 {
-    __shared__ T sm[32];
-    Op op; T loc[PMN_SCAN_ITEMS];
-    int64_t base = (int64_t)blockIdx.x * PMN_SCAN_TILE + (int64_t)threadIdx.x * PMN_SCAN_ITEMS;
+    __shared__ T sm[32]; __shared__ T s_prefix; __shared__ unsigned s_tile;
+    Op op;
+    if (threadIdx.x == 0) s_tile = atomicAdd(counters, 1u);
+    __syncthreads();
+    const unsigned tile = s_tile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T loc[PMN_SCAN_ITEMS];
+    const int64_t base = (int64_t)tile * PMN_SCAN_TILE + (int64_t)threadIdx.x * PMN_SCAN_ITEMS;
     T acc = Op::identity();
 #pragma unroll
     for (int k = 0; k < PMN_SCAN_ITEMS; k++) { loc[k] = base + k < n ? in[base + k] : Op::identity(); acc = op(acc, loc[k]); }
-    T inc = pmn_block_scan_incl(acc, op, sm);
-    // exclusive prefix of this thread = (tile offset) (+) (inclusive of previous thread)
+    const T inc = pmn_block_scan_incl(acc, op, sm);         // sm[w] = inclusive total of warps 0..w afterwards
+    const T block_agg = sm[PMN_SCAN_THREADS / 32 - 1];
+    volatile unsigned long long *my = (volatile unsigned long long *)&desc[tile];
+    if (threadIdx.x == 0) {
+        if (tile == 0) { my[2] = pmn_scan_pack(block_agg); __threadfence(); my[0] = 2 * epoch + 1; }
+        else { my[1] = pmn_scan_pack(block_agg); __threadfence(); my[0] = 2 * epoch; }
+    }
+    if (tile > 0 && warp == 0) {
+        T running = Op::identity();                       // aggregate of the tiles looked at so far, in tile order
+        for (int64_t look = (int64_t)tile - 1;; look -= 32) {
+            const int64_t t = look - lane;                // lane 0 looks at the nearest tile
+            unsigned long long st = 2 * epoch + 1; T val = Op::identity();       // before tile 0: an inclusive prefix of nothing
+            if (t >= 0) {
+                volatile unsigned long long *d = (volatile unsigned long long *)&desc[t];
+                do { st = d[0]; } while ((st >> 1) != epoch);
+                __threadfence();
+                val = pmn_scan_unpack<T>((st & 1ull) ? d[2] : d[1]);
+            }
+            const unsigned incl_mask = __ballot_sync(0xffffffffu, (st & 1ull) != 0);
+            const int first = incl_mask ? __ffs((int)incl_mask) - 1 : 31;          // nearest lane that holds an inclusive prefix
+            T v = lane <= first ? val : Op::identity();
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const T u = __shfl_down_sync(0xffffffffu, v, o); if (lane + o < 32) v = op(u, v); }   // lane 0: val[first] (+) ... (+) val[0]
+            const T window = __shfl_sync(0xffffffffu, v, 0);
+            running = op(window, running);
+            if (incl_mask) break;
+        }
+        if (lane == 0) {
+            s_prefix = running;
+            my[2] = pmn_scan_pack(op(running, block_agg)); __threadfence(); my[0] = 2 * epoch + 1;
+        }
+    }
+    __syncthreads();
+    // exclusive prefix of this thread = (tile prefix) (+) (inclusive of the previous thread)
     T prev = __shfl_up_sync(0xffffffffu, inc, 1);
-    if ((threadIdx.x & 31) == 0) prev = threadIdx.x ? sm[(threadIdx.x >> 5) - 1] : Op::identity();
-    T run = threadIdx.x ? op(partial[blockIdx.x], prev) : partial[blockIdx.x];
+    if (lane == 0) prev = warp ? sm[warp - 1] : Op::identity();
+    T run = threadIdx.x ? prev : Op::identity();
+    if (tile > 0) run = threadIdx.x ? op(s_prefix, prev) : s_prefix;
 #pragma unroll
     for (int k = 0; k < PMN_SCAN_ITEMS; k++) {
         if (base + k < n) {
             if (INCLUSIVE) { run = op(run, loc[k]); out[base + k] = run; }
             else { out[base + k] = run; run = op(run, loc[k]); }
         }
+    }
+    if (threadIdx.x == 0) {                                // the block that finishes last rearms the counters for the next scan
+        const unsigned done = atomicAdd(counters + 1, 1u);
+        if (done == tiles - 1) { counters[0] = 0; counters[1] = 0; }
     }
 }
 
@@ -134,18 +157,25 @@ __global__ void __launch_bounds__(1024) pmn_scan_small(const T *__restrict__ in,
     }
 }
 
-// scratch must hold ceil(n / PMN_SCAN_TILE) + 1 elements of T.  in == out is allowed.
+inline std::atomic<unsigned long long> pmn_scan_epoch{0};      // one epoch per scan of the process (C++17 inline variable: one object for all translation units)
+
+// scratch: 8 * pmn_scan_scratch_elems(n) bytes of a DevBuf (zeroed when allocated); consecutive scans on one stream may share
+// it.  in == out is allowed.  Every scan is ONE launch (callers that still count three note the difference in
+// pmn_tls_launches_saved, which the API entry points subtract from the context's launch counter).
 template <class T, class Op, bool INCLUSIVE>
 static inline void pmn_scan(const T *in, T *out, int64_t n, T *scratch, cudaStream_t st)
 {
+    static_assert(sizeof(T) <= 8, "descriptor slots are 8 bytes");
     if (n <= 0) return;
-    if (n <= PMN_SCAN_SMALL_MAX) { pmn_scan_small<T, Op, INCLUSIVE><<<1, 1024, 0, st>>>(in, out, n); pmn_tls_launches_saved += 2; return; }
-    int64_t tiles = (n + PMN_SCAN_TILE - 1) / PMN_SCAN_TILE;
-    pmn_scan_reduce<T, Op><<<(unsigned)tiles, PMN_SCAN_THREADS, 0, st>>>(in, scratch, n);
-    pmn_scan_spine<T, Op><<<1, 1024, 0, st>>>(scratch, tiles);
-    pmn_scan_down<T, Op, INCLUSIVE><<<(unsigned)tiles, PMN_SCAN_THREADS, 0, st>>>(in, out, scratch, n);
+    pmn_tls_launches_saved += 2;
+    if (n <= PMN_SCAN_SMALL_MAX) { pmn_scan_small<T, Op, INCLUSIVE><<<1, 1024, 0, st>>>(in, out, n); return; }
+    const int64_t tiles = (n + PMN_SCAN_TILE - 1) / PMN_SCAN_TILE;
+    const unsigned long long epoch = ++pmn_scan_epoch;
+    unsigned *counters = (unsigned *)scratch;
+    PmnScanDesc *desc = (PmnScanDesc *)((char *)scratch + 16);
+    pmn_scan_onepass<T, Op, INCLUSIVE><<<(unsigned)tiles, PMN_SCAN_THREADS, 0, st>>>(in, out, n, counters, desc, epoch, (unsigned)tiles);
 }
-static inline size_t pmn_scan_scratch_elems(int64_t n) { return (size_t)((n + PMN_SCAN_TILE - 1) / PMN_SCAN_TILE + 1); }
+static inline size_t pmn_scan_scratch_elems(int64_t n) { return (size_t)(3 * ((n + PMN_SCAN_TILE - 1) / PMN_SCAN_TILE) + 4); }   // in units of 8 bytes
 
 // ------------------------------------------------------------------------------------ radix sort
 
@@ -322,7 +352,7 @@ struct RadixScratch {
         int64_t tiles = (n + PMN_RS_TILE - 1) / PMN_RS_TILE; if (tiles < 1) tiles = 1;
         int64_t cells = tiles * PMN_RS_RADIX;
         if (hist.ensure(sizeof(uint32_t) * (size_t)cells)) return -1;
-        if (spine.ensure(sizeof(uint32_t) * pmn_scan_scratch_elems(cells))) return -1;
+        if (spine.ensure(8 * pmn_scan_scratch_elems(cells))) return -1;
         return 0;
     }
 };

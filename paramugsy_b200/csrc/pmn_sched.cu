@@ -109,6 +109,13 @@ extern "C" void pmn_sched_counters(const pmn_sched *s, int64_t out[4])
     for (pmn_ctx *c : s->ctx) { int64_t t[4]; pmn_ctx_counters(c, t); for (int k = 0; k < 4; k++) out[k] += t[k]; }
 }
 
+extern "C" int64_t pmn_sched_sync_count(const pmn_sched *s)
+{
+    int64_t n = 0;
+    if (s) for (pmn_ctx *c : s->ctx) n += pmn_ctx_sync_count(c);
+    return n;
+}
+
 // The common engine: genomes either as host FASTA buffers (packed on demand) or as resident
 // pmn_seq handles; pairs as index pairs into the genome list.
 static int sched_run(pmn_sched *s, int ng, const char *const *fasta, const size_t *bytes, const pmn_seq *const *resident,

@@ -28,6 +28,8 @@ struct Scratch {
                  &ex_a, &ex_b, &ex_c, &ex_d, &ex_e, &ex_f, &ex_g, &ex_h, &ex_i, &ex_j, &ex_k, &ex_l,
                  &ex_scores, &ex_tb, &ex_tbidx, &ex_pool, &ex_counters, &ex_arena, &ex_dbg, &ex_desc, &ex_tkey, &ex_tscratch };
     }
+    // the diagonal-difference limits of the clustering stage as they are in cl_g, and the options they were computed from
+    std::vector<int32_t> lim_host; int lim_maxgap = -1, lim_diagdiff = -1; double lim_diagfactor = -1.0;
     // host-side counts handed from one stage to the next (one pair in flight per context)
     int64_t n_anchors = 0, n_clusters = 0, n_cl_matches = 0;
     // pinned host staging

@@ -8,22 +8,31 @@
 //   1. 32-base window of the query from shared memory (the tile of packed query text and
 //      its x-mask is staged by one TMA bulk copy per block, cp.async.bulk + mbarrier)
 //   2. bucket [lo,hi) of the window's first K bases from the K-mer table
-//   3. a bucket of one suffix is decided at once (left-maximality base, then the match
-//      length); larger buckets go on the warp's list and are worked off densely:
-//      lower bound of Q[i..] among the bucket's suffixes (binary search on packed text,
-//      32 bases per probe), longest match = better of the two neighbours of the insertion
-//      point, unique iff the other neighbour is shorter and the LCP entry on the far side
-//      is shorter too, left-maximality
-//   4. anchors are written at the slot of their position; k_seed_gather compacts them in order
+//   3. a bucket of one suffix is decided at once (match length, left-maximality base); larger
+//      buckets go on the warp's list and are worked off densely: lower bound of Q[i..] among
+//      the bucket's suffixes (binary search on packed text, 32 bases per probe), longest match
+//      = better of the two neighbours of the insertion point, unique iff the other neighbour
+//      is shorter and the LCP entry on the far side is shorter too, left-maximality
+//   4. a lane owns 32 CONSECUTIVE positions: once it knows that Q[i..] matches R[r..] for m bases,
+//      the positions behind i continue that match at r+1, r+2, ... and cannot be left-maximal
+//      there; as long as the rest of the match is longer than any repeat of its reference
+//      suffix (the index's skip table, one byte load) it is also their unique longest match,
+//      so they yield no anchor and are stepped over without any table, suffix-array or text
+//      access: 3 of 4 positions at 2 % divergence
+//   5. anchors are written at the slot of their position; k_seed_gather compacts them in order
 // Output order equals the oracle's sort order, so no sort follows.
 #include <algorithm>
 
 #include "pmn_scratch.cuh"
 
-#define SEED_THREADS 256
-#define SEED_ITERS 8
-#define SEED_TILE (SEED_THREADS * SEED_ITERS)      /* query positions per block */
+#define SEED_THREADS 128
+#define SEED_WARPS (SEED_THREADS / 32)
+#define SEED_CHUNK 32                              /* consecutive positions per lane: lane l owns word l of its warp's anchor bitmap */
+#define SEED_RUN (32 * SEED_CHUNK)                 /* positions per warp */
+#define SEED_TILE (SEED_THREADS * SEED_CHUNK)      /* query positions per block */
 #define SEED_WORDS (SEED_TILE / 32 + 8)            /* staged words: tile + alignment slack + one window */
+static_assert(SEED_WORDS + 8 <= PMN_PAD_WORDS, "the last tile of a text reads SEED_WORDS words from its first word on: the padding must cover them");
+static_assert((SEED_WORDS * 4) % 16 == 0, "TMA bulk copies move multiples of 16 bytes");
 
 struct SeedSection {
     int64_t start;      // offset of the record inside the strand's concatenated text
@@ -145,30 +154,34 @@ __device__ __forceinline__ bool seed_general(const View32 &R32, const View32 &Q3
     return true;
 }
 
-// Two passes per warp over its 256 positions.
-//   Pass 1, every position: the bucket of the first K bases.  Empty: nothing matches minmatch >= K bases.  One suffix s: it
-//   is the only candidate, every other suffix shares fewer than K bases with the query and with s, so the match is unique
-//   and the anchor exists iff it is left-maximal and >= minmatch long — the one-base test comes first and ends 98 % of the
-//   positions inside a longer match (it needs one reference word instead of the comparison loops).  Two or more suffixes:
-//   the position goes on the warp's list.
-//   Pass 2, the listed positions 32 at a time: binary search and both neighbours (seed_general).  In a random 5 Mbp genome
-//   one position in seven is listed, so the divergent loops run for a seventh of the warp iterations they ran for when every
-//   position took them.
+// Two passes per warp over its SEED_RUN positions.
+//   Pass 1: every lane walks its own chunk of SEED_CHUNK consecutive positions.  A look-up takes the bucket of the first K
+//   bases.  Empty: nothing matches minmatch >= K bases.  One suffix s: it is the only candidate, every other suffix shares
+//   fewer than K bases with the query and with s, so the match is unique; m = lcp(Q[g..], R[s..]) decides the anchor together
+//   with the left-maximality base, and starts a chain: position g+j continues the match at s+j with m-j bases, where it is
+//   not left-maximal (the base before it is matched); while m-j exceeds the longest repeat of the suffix at s+j that match
+//   is also the unique longest one, i.e. the position has no anchor.  With E = s+m those are exactly the positions before
+//   p_stop = E - skip[E] (pmn_index.cu: the repeat ends e(p) = p + rep(p) never decrease), so the lane jumps there with one
+//   byte load.  Two or more suffixes: the position goes on the warp's list and the chain is dropped (the next position is
+//   looked up).
+//   Pass 2, the listed positions 32 at a time: binary search and both neighbours (seed_general).
 // Anchors are written at the slot of their position (stage is one int4 per position) with a bitmap per warp run; the gather
 // kernel compacts them in position order.
 __global__ void __launch_bounds__(SEED_THREADS) k_seed(PackedView R, const uint32_t *__restrict__ sa, const int32_t *__restrict__ lcp,
-                                                      const uint32_t *__restrict__ table, int K, PackedView QF, PackedView QR,
+                                                      const uint32_t *__restrict__ table, const uint8_t *__restrict__ skip, int K, PackedView QF, PackedView QR,
                                                       const SeedSection *__restrict__ secs, int nsec, int minmatch,
-                                                      int4 *__restrict__ stage, uint32_t *__restrict__ run_bits, uint32_t *__restrict__ tile_cnt, unsigned tile_base, unsigned ntiles)
+                                                      int4 *__restrict__ stage, uint32_t *__restrict__ run_bits, uint32_t *__restrict__ tile_cnt, unsigned tile_base, unsigned ntiles,
+                                                      unsigned long long *__restrict__ lookups)
 {
     __shared__ __align__(16) uint64_t s_w[SEED_WORDS];
     __shared__ __align__(16) uint32_t s_x[SEED_WORDS];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ uint8_t s_list[SEED_THREADS / 32][SEED_ITERS * 32];
-    __shared__ uint32_t s_bits[SEED_THREADS / 32][SEED_ITERS];
+    __shared__ uint16_t s_list[SEED_WARPS][SEED_RUN];
+    __shared__ uint32_t s_bits[SEED_WARPS][SEED_CHUNK];
     if (threadIdx.x == 0) mbar_init(&s_bar, 1);
     __syncthreads();
     uint32_t phase = 0;
+    unsigned my_lookups = 0;
     // a block walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... (one tile per block unless the host caps the grid)
     for (unsigned ltile = blockIdx.x; ltile < ntiles; ltile += gridDim.x, phase ^= 1u) {
     const int64_t tile = (int64_t)ltile + tile_base;          // ltile is local to the launched tile range
@@ -195,11 +208,11 @@ __global__ void __launch_bounds__(SEED_THREADS) k_seed(PackedView R, const uint3
     const int first_need = minmatch < 32 ? minmatch : 32;
     const View32 R32 = view32(R), Q32 = view32(Q);
     const bool use_table = minmatch >= K;
-    // Warp w owns the SEED_ITERS * 32 consecutive positions [w * 256, (w + 1) * 256) of the tile and their slots of the staging area
-    const size_t run = (size_t)ltile * (SEED_THREADS / 32) + warp;
-    int4 *wstage = stage + run * (SEED_ITERS * 32);
-    const int64_t woff = off0 + warp * (SEED_ITERS * 32);
-    uint32_t nlist = 0, wcount = 0;
+    // Warp w owns the SEED_RUN consecutive positions [w * SEED_RUN, (w + 1) * SEED_RUN) of the tile and their slots of the staging area
+    const size_t run = (size_t)ltile * SEED_WARPS + warp;
+    int4 *wstage = stage + run * SEED_RUN;
+    const int64_t woff = off0 + warp * SEED_RUN;
+    uint32_t nlist = 0;
     // the first window of position woff + idx, from the staged tile
     auto window = [&](int idx, uint32_t &g, uint64_t &qw, int &vq) {
         g = (uint32_t)(sec.start + woff + idx);
@@ -209,35 +222,51 @@ __global__ void __launch_bounds__(SEED_THREADS) k_seed(PackedView R, const uint3
         if (Q.has_x) { const uint32_t xw = __funnelshift_l(s_x[k + 1], s_x[k], sh); vq = xw ? __clz((int)xw) : 32; }
         else { const uint32_t r = Q32.n - g; vq = r < 32u ? (int)r : 32; }
     };
-    for (int it = 0; it < SEED_ITERS; it++) {
-        const int idx = it * 32 + lane;
-        bool found = false, later = false;
-        if (woff + idx < sec.npos) {
+    // ---- pass 1: lane l walks positions [l * SEED_CHUNK, l * SEED_CHUNK + lim) of the run
+    int lim;
+    { const int64_t left = sec.npos - (woff + (int64_t)lane * SEED_CHUNK); lim = left <= 0 ? 0 : left < SEED_CHUNK ? (int)left : SEED_CHUNK; }
+    int k = 0;
+    uint32_t mybits = 0;
+    while (__any_sync(0xffffffffu, k < lim)) {
+        const bool act = k < lim;
+        bool later = false;
+        const int idx = lane * SEED_CHUNK + k;
+        if (act) {
             uint32_t g; uint64_t qw; int vq;
             window(idx, g, qw, vq);
+            int step = 1;                                       // positions this look-up settles, itself included
             if (vq >= first_need) {
+                my_lookups++;
                 if (!use_table) later = true;
                 else {
                     const uint32_t km = (uint32_t)(qw >> (64 - 2 * K));
                     const uint32_t lo = __ldg(table + km), hi = __ldg(table + km + 1);
                     if (hi - lo == 1u) {
                         const uint32_t s = __ldg(sa + lo);
-                        const int qb = base32(Q32, g - 1), rb = base32(R32, s - 1);
-                        if (!(qb == rb && qb < 4)) {
-                            const uint32_t L = lcp32(Q32, g, R32, s);
-                            if (L >= (uint32_t)minmatch) { found = true; wstage[idx] = make_int4((int)(s + 1), (int)(woff + idx + 1), (int)L, sec.tag); }
+                        const uint32_t L = lcp32(Q32, g, R32, s);
+                        if (L >= (uint32_t)minmatch) {
+                            const int qb = base32(Q32, g - 1), rb = base32(R32, s - 1);
+                            if (!(qb == rb && qb < 4)) { mybits |= 1u << k; wstage[idx] = make_int4((int)(s + 1), (int)(woff + idx + 1), (int)L, sec.tag); }
+                        }
+                        if (L >= 2u) {
+                            // the positions behind this one continue the match at s+1, s+2, ...: those before p_stop have it as their
+                            // unique longest match and are not left-maximal in it
+                            const uint32_t E = s + L;
+                            const uint32_t d = __ldg(skip + E);
+                            if (d < 255u) { const uint32_t p_stop = E - d; if (p_stop > s + 1u) step = (int)(p_stop - s); }
                         }
                     } else if (hi > lo) later = true;
                 }
             }
+            k += step;
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, found), bl = __ballot_sync(0xffffffffu, later);
-        if (lane == 0) s_bits[warp][it] = bal;
-        wcount += __popc(bal);
-        if (later) s_list[warp][nlist + __popc(bl & lt)] = (uint8_t)idx;
+        const unsigned bl = __ballot_sync(0xffffffffu, later);
+        if (later) s_list[warp][nlist + __popc(bl & lt)] = (uint16_t)idx;
         nlist += __popc(bl);
     }
+    s_bits[warp][lane] = mybits;
     __syncwarp();
+    // ---- pass 2: the listed positions, densely
     for (uint32_t c = 0; c < nlist; c += 32) {
         bool found = false; int idx = 0;
         if (c + lane < nlist) {
@@ -252,12 +281,20 @@ __global__ void __launch_bounds__(SEED_THREADS) k_seed(PackedView R, const uint3
             }
         }
         if (found) atomicOr(&s_bits[warp][idx >> 5], 1u << (idx & 31));
-        wcount += __popc(__ballot_sync(0xffffffffu, found));
     }
     __syncwarp();
-    if (lane < SEED_ITERS) run_bits[run * SEED_ITERS + lane] = s_bits[warp][lane];
+    const uint32_t word = s_bits[warp][lane];
+    run_bits[run * SEED_CHUNK + lane] = word;
+    uint32_t wcount = __popc(word);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) wcount += __shfl_xor_sync(0xffffffffu, wcount, o);
     if (lane == 0) tile_cnt[run] = wcount;
     __syncthreads();            // the staged tile is free for the next copy
+    }
+    if (lookups) {              // how many positions were looked up (the rest were stepped over): bench.py reports the share
+#pragma unroll
+        for (int o = 16; o; o >>= 1) my_lookups += __shfl_xor_sync(0xffffffffu, my_lookups, o);
+        if ((threadIdx.x & 31) == 0 && my_lookups) atomicAdd(lookups, (unsigned long long)my_lookups);
     }
 }
 
@@ -265,14 +302,16 @@ __global__ void __launch_bounds__(SEED_THREADS) k_seed(PackedView R, const uint3
 __global__ void __launch_bounds__(256) k_seed_gather(const int4 *__restrict__ stage, const uint32_t *__restrict__ run_bits,
                                                     const uint32_t *__restrict__ run_off, int64_t nruns, int4 *__restrict__ anchors)
 {
-    const int64_t run = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // one warp per run of SEED_ITERS * 32 positions
+    const int64_t run = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // one warp per run of SEED_RUN positions
     if (run >= nruns) return;
     const int lane = threadIdx.x & 31;
     const unsigned lt = pmn_lanemask_lt();
     uint32_t off = run_off[run];
-    for (int w = 0; w < SEED_ITERS; w++) {
-        const uint32_t word = run_bits[run * SEED_ITERS + w];
-        if ((word >> lane) & 1u) anchors[off + __popc(word & lt)] = stage[(size_t)run * (SEED_ITERS * 32) + w * 32 + lane];
+    const uint32_t mine = run_bits[run * SEED_CHUNK + lane];       // word w of the run's bitmap sits in lane w
+    for (int w = 0; w < SEED_CHUNK; w++) {
+        const uint32_t word = __shfl_sync(0xffffffffu, mine, w);
+        if (!word) continue;
+        if ((word >> lane) & 1u) anchors[off + __popc(word & lt)] = stage[(size_t)run * SEED_RUN + w * 32 + lane];
         off += __popc(word);
     }
 }
@@ -307,9 +346,9 @@ int pmn_seed_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_o
     const int64_t t_lo = all_tiles * part / nparts, t_hi = all_tiles * (part + 1) / nparts;
     tiles = t_hi - t_lo;
     if (tiles == 0) return 0;
-    const int64_t runs = tiles * (SEED_THREADS / 32);          // one anchor run per warp of a tile
+    const int64_t runs = tiles * SEED_WARPS;                   // one anchor run per warp of a tile
     if (S.sections.ensure(sizeof(SeedSection) * secs.size()) || S.stage.ensure(sizeof(int4) * (size_t)tiles * SEED_TILE) ||
-        S.tile_cnt.ensure(4 * (size_t)runs) || S.tile_off.ensure(4 * (size_t)runs) || S.seed_bits.ensure(4 * SEED_ITERS * (size_t)runs) ||
+        S.tile_cnt.ensure(4 * (size_t)runs + 16) || S.tile_off.ensure(4 * (size_t)runs) || S.seed_bits.ensure(4 * SEED_CHUNK * (size_t)runs) ||
         S.scan_tmp.ensure(8 * pmn_scan_scratch_elems(runs)) || S.ensure_pinned(64)) return -3;
     PMN_H2D(c, S.sections.p, secs.data(), sizeof(SeedSection) * secs.size());
     PMN_CUDA_OK(cudaEventRecord(c->ev[6], st));
@@ -317,15 +356,16 @@ int pmn_seed_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_o
     // blocks per SM that stride over the tiles (experiment: leave thread slots to the kernels of other pairs)
     static const int seed_bps = getenv("PMN_SEED_BPS") ? atoi(getenv("PMN_SEED_BPS")) : 0;
     const unsigned seed_grid = seed_bps > 0 ? (unsigned)std::min<int64_t>(tiles, (int64_t)c->sm_count * seed_bps) : (unsigned)tiles;
-    k_seed<<<seed_grid, SEED_THREADS, 0, st>>>(ix->seq->fwd(), ix->sa(), ix->lcp(), ix->table(), ix->K,
+    k_seed<<<seed_grid, SEED_THREADS, 0, st>>>(ix->seq->fwd(), ix->sa(), ix->lcp(), ix->table(), ix->skip(), ix->K,
                                                      q->fwd(), q->rev(), S.sections.as<SeedSection>(), (int)secs.size(), o->minmatch,
-                                                     S.stage.as<int4>(), S.seed_bits.as<uint32_t>(), S.tile_cnt.as<uint32_t>(), (unsigned)t_lo, (unsigned)tiles);
+                                                     S.stage.as<int4>(), S.seed_bits.as<uint32_t>(), S.tile_cnt.as<uint32_t>(), (unsigned)t_lo, (unsigned)tiles, nullptr);
     PMN_CUDA_OK(cudaEventRecord(c->ev[7], st));
     pmn_scan<uint32_t, OpAddU32, false>(S.tile_cnt.as<uint32_t>(), S.tile_off.as<uint32_t>(), runs, S.scan_tmp.as<uint32_t>(), st);
     uint32_t *tail = (uint32_t *)S.pinned;
     PMN_D2H(c, tail, S.tile_off.as<uint32_t>() + (runs - 1), 4);
     PMN_D2H(c, tail + 1, S.tile_cnt.as<uint32_t>() + (runs - 1), 4);
-    PMN_CUDA_OK(cudaStreamSynchronize(st));   // the secs vector is also safe to drop after this
+    PMN_CUDA_OK(cudaStreamSynchronize(st));   // the host sizes the clustering stage from the anchor count
+    c->syncs++;
     int64_t total = (int64_t)tail[0] + tail[1];
     c->launches += 4;
     if (total > 0) {

@@ -54,7 +54,7 @@ class Stats(C.Structure):
 # every symbol include/pmnucmer.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "pmn_default_opts", "pmn_nucmer_parse_argv", "pmn_opts_parse", "pmn_ctx_create", "pmn_ctx_destroy", "pmn_last_error", "pmn_device_count", "pmn_alloc_count", "pmn_pinned_pool_stats",
-    "pmn_ctx_stream", "pmn_ctx_counters", "pmn_measure_int32_peak",
+    "pmn_ctx_stream", "pmn_ctx_counters", "pmn_ctx_sync_count", "pmn_sched_sync_count", "pmn_measure_int32_peak",
     "pmn_seq_from_fasta", "pmn_seq_from_file", "pmn_seq_free", "pmn_seq_bases", "pmn_seq_records",
     "pmn_index_build", "pmn_index_free", "pmn_index_image", "pmn_index_image_bytes", "pmn_index_alloc", "pmn_index_adopt", "pmn_align", "pmn_seed_part", "pmn_align_anchors", "pmn_result_delta", "pmn_result_stats",
     "pmn_result_free", "pmn_align_pair", "pmn_align_batch", "pmn_index_size", "pmn_index_copy_sa",
@@ -89,6 +89,8 @@ def lib():
         L.pmn_last_error.argtypes = [vp]; L.pmn_last_error.restype = cp
         L.pmn_ctx_stream.argtypes = [vp]; L.pmn_ctx_stream.restype = vp
         L.pmn_ctx_counters.argtypes = [vp, i64p]
+        L.pmn_ctx_sync_count.argtypes = [vp]; L.pmn_ctx_sync_count.restype = i64
+        L.pmn_sched_sync_count.argtypes = [vp]; L.pmn_sched_sync_count.restype = i64
         L.pmn_measure_int32_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.pmn_seq_from_fasta.argtypes = [vp, cp, C.c_size_t, C.POINTER(vp)]
         L.pmn_seq_from_file.argtypes = [vp, cp, C.POINTER(vp)]
@@ -211,7 +213,7 @@ class Context:
     def counters(self):
         out = (C.c_int64 * 4)()
         lib().pmn_ctx_counters(self.h, out)
-        return {"launches": out[0], "h2d_bytes": out[1], "d2h_bytes": out[2], "pairs": out[3]}
+        return {"launches": out[0], "h2d_bytes": out[1], "d2h_bytes": out[2], "pairs": out[3], "syncs": lib().pmn_ctx_sync_count(self.h)}
 
     def int32_peak(self):
         g, mhz = C.c_double(), C.c_double()
@@ -265,7 +267,7 @@ class Scheduler:
     def counters(self):
         out = (C.c_int64 * 4)()
         lib().pmn_sched_counters(self.h, out)
-        return {"launches": out[0], "h2d_bytes": out[1], "d2h_bytes": out[2], "pairs": out[3]}
+        return {"launches": out[0], "h2d_bytes": out[1], "d2h_bytes": out[2], "pairs": out[3], "syncs": lib().pmn_sched_sync_count(self.h)}
 
     def context(self, k=0):
         """Worker k's context as a borrowed Context (do not close it)."""

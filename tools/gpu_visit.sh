@@ -7,8 +7,8 @@ steps=${@:-tests smoke bench}
 mkdir -p gpurun_out
 for s in $steps; do
   case $s in
-    tests)   timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${tag}_pytest.log; tail -5 gpurun_out/${tag}_pytest.log ;;
-    tests_all) timeout 1800 python -m pytest tests -m gpu -q > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${tag}_pytest.log; tail -15 gpurun_out/${tag}_pytest.log ;;
+    tests)   timeout 1500 python -m pytest tests -m gpu -x -q --timeout 600 > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${tag}_pytest.log; tail -5 gpurun_out/${tag}_pytest.log ;;
+    tests_all) timeout 1800 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${tag}_pytest.log; tail -15 gpurun_out/${tag}_pytest.log ;;
     smoke)   timeout 300 python __graft_entry__.py smoke > gpurun_out/${tag}_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/${tag}_smoke.log ;;
     bench)   timeout 900 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"; head -c 400 gpurun_out/${tag}_bench.json; echo ;;
     bench_ref) timeout 900 python bench.py --impl reference --steps 1 --warmup 1 > gpurun_out/${tag}_bench_ref.json 2> gpurun_out/${tag}_bench_ref.err; echo "ref rc=$?"; head -c 300 gpurun_out/${tag}_bench_ref.json; echo ;;
