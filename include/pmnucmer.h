@@ -72,6 +72,8 @@ typedef struct pmn_stats {
     int64_t wave1_cells;         /* DP cells evaluated inside k_ex_wave1               */
     float   wall_ms_index, wall_ms_align, wall_ms_text;   /* host wall clock: index build, pmn_align, .delta formatting */
     float   wall_ms_post;        /* host wall clock of the two post-steps (pmn_opts.post) */
+    int64_t seed_lookups;        /* query positions the seeding kernel looked up in the index; the rest were stepped over */
+    int64_t arena_bytes;         /* traceback arena the extension used for this pair */
 } pmn_stats;
 
 void pmn_default_opts(pmn_opts *o);
@@ -219,6 +221,32 @@ int  pmn_sched_align_indexed(pmn_sched *s, int n_genomes, const pmn_seq *const *
 /* genomes and results as files: one call per Nucmer_task.t.searches */
 int  pmn_sched_align_files(pmn_sched *s, int n, const char *const *ref_fasta_paths, const char *const *qry_fasta_paths,
                            const char *const *out_delta_paths, const pmn_opts *o);
+
+/* ---- several GPUs of one box from ONE process ----
+ * The reference's concurrency knob is `-cores N`: one paramugsy process keeps N `mugsy_nucmer` workers busy
+ * (lib/base/paramugsy.ml:54-57, lib/base/queued_task_server.ml:57-64).  A pmn_multi is that over the GPUs of a box: one
+ * pmn_sched per device, so that the `nucmer` shim's caller, the OCaml stub or any C host can use all of them without Python
+ * or torch.  devices = NULL means 0 .. n_devices-1; the same device may be named twice (two schedulers on it).
+ *   all-vs-all (pmn_multi_align_fasta / _files): the pairs are cut by reference into one contiguous run per device
+ *   (pmn_multi_plan: pure host arithmetic, device_of_pair[k] in 0 .. n_devices-1); every device packs the genomes and builds the
+ *   indexes its pairs name; nothing crosses between the devices.  Results do not depend on the number of devices.
+ *   one large pair (pmn_multi_align_large): both genomes and the index on every device, device k seeds query-position part k,
+ *   the anchor lists are gathered on the first device (peer copies), which clusters, extends and formats — the .delta is
+ *   byte-identical for any number of devices.  stats_ms (may be NULL): wall clock of [0] pack + index, [1] seeding,
+ *   [2] gather, [3] clustering + extension + text. */
+typedef struct pmn_multi pmn_multi;
+int  pmn_multi_plan(int n_devices, int n_genomes, const size_t *bytes /* may be NULL */, int n_pairs, const int32_t *ref, const int32_t *qry, int32_t *device_of_pair);
+int  pmn_multi_create(const int *devices, int n_devices, int workers_per_device, pmn_multi **out);
+void pmn_multi_destroy(pmn_multi *m);
+int  pmn_multi_devices(const pmn_multi *m);
+pmn_sched *pmn_multi_sched(const pmn_multi *m, int k);        /* device k's scheduler (borrowed) */
+int  pmn_multi_align_fasta(pmn_multi *m, int n_genomes, const char *const *fasta, const size_t *bytes, const char *const *names,
+                           int n_pairs, const int32_t *ref, const int32_t *qry, const pmn_opts *o, pmn_result **out);
+/* maf_outs may be NULL; with o->post = 1 | 2 and maf_outs, out_delta_paths[i] receives the FILTERED delta and maf_outs[i] its MAF */
+int  pmn_multi_align_files(pmn_multi *m, int n, const char *const *ref_fasta_paths, const char *const *qry_fasta_paths,
+                           const char *const *out_delta_paths, const char *const *maf_outs, const pmn_opts *o);
+int  pmn_multi_align_large(pmn_multi *m, const char *ref_fasta, size_t ref_bytes, const char *qry_fasta, size_t qry_bytes, const pmn_opts *o,
+                           const char *ref_path, const char *qry_path, pmn_result **out, double *stats_ms /* [4] or NULL */);
 
 /* ---- stage dumps for the parity tests (sizes via the n_* calls; buffers are caller-owned) ---- */
 int64_t pmn_index_size(const pmn_index *ix);

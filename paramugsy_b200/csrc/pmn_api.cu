@@ -545,6 +545,7 @@ static int align_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *qry, const
     }
     PMN_CUDA_OK(cudaEventRecord(c->ev[3], st));
     r->stats.anchors = nanc;
+    r->stats.seed_lookups = (given_anchors || n_given == 0) ? 0 : S.seed_lookups;
     if (o.keep_stages && nanc > 0) {
         r->anchors.resize((size_t)nanc * 4);
         PMN_D2H(c, r->anchors.data(), S.anchors.p, 16 * (size_t)nanc);
@@ -553,7 +554,13 @@ static int align_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *qry, const
     rc = pmn_cluster_impl(c, ix, qry, &o, nanc);
     if (rc) return rc;
     PMN_CUDA_OK(cudaEventRecord(c->ev[4], st));
-    rc = pmn_extend_impl(c, ix, qry, &o, r.get());
+    for (;;) {
+        rc = pmn_extend_impl(c, ix, qry, &o, r.get());
+        // the traceback arena is sized from what earlier pairs needed; a pair that needs more gets a larger one and the extension
+        // (a pure function of the cluster list, which is still in the scratch) runs again
+        if (rc == PMN_E_NOMEM && S.arena_retry) { S.arena_retry = false; continue; }
+        break;
+    }
     if (rc) return rc;
     PMN_CUDA_OK(cudaEventRecord(c->ev[5], st));
     PMN_CUDA_OK(cudaStreamSynchronize(st));

@@ -168,14 +168,140 @@ struct ChainArrays {
     uint32_t *oc_valid;
 };
 
-// Process_Matches for the component occupying sorted slots [a, a+m).  One warp.  The DP is a chain of dependent steps and
-// is run by lane 0; what it reads and writes per step lives in shared memory: the anchors arrive 32 at a time (coalesced
-// loads by all lanes) in a ring of the last CH_RING entries, where scores and prefix maxima stay for the look-back (a clean
-// colinear run looks back one or two entries; an entry written to global memory comes back from L2, 300 cycles per step of
-// the chain), and results leave 32 at a time (coalesced stores).  The walk over the best chain's `from` links is served the
-// same way, one chunk of 32 links in shared memory at a time, instead of one L2 round trip per link.
+// Process_Matches for the component occupying sorted slots [a, a+m).  One warp.
+//
+// The DP  score[i] = len[i] + max(0, max_{j<i}(score[j] - pen(i,j)))  (lowest j among the best) looks like a chain of m
+// dependent steps, and is one when lane 0 walks it (5 cycles per instruction with nothing else to issue: 600 cycles per
+// anchor, a component of 1000 anchors keeps its warp for 0.3 ms).  But in a component of colinear anchors almost every
+// anchor's best predecessor is the anchor before it, and under THAT assumption the scores are a prefix scan:
+//     c[i] = max(len[i], c[i-1] + len[i] - pen(i, i-1))        affine maps x -> max(A, x + B) compose associatively
+// So: (A) all lanes compute the guess c[] and its prefix maxima with warp scans; (B) every lane evaluates the TRUE step
+// of the DP for its own i — the same look-back loop, same pruning, same tie rule — reading the guessed scores of the
+// anchors before it, and checks that the step reproduces c[i].  If it does for every i, then by induction on i the guess IS
+// the score array of the sequential DP (score[i] is a function of score[0..i-1] alone), and the `from` / `adj` the lanes
+// found are the sequential ones.  If any lane disagrees, lane 0 runs the sequential DP over the component (dp_sequential:
+// the look-back served from a shared-memory ring).  Both paths run the one dp_step below.
 #define CH_RING 64
 struct ChainShared { int s1[CH_RING], s2[CH_RING], ln[CH_RING], sc[CH_RING], pm[CH_RING]; int from[32], adj[32]; };
+#define CH_NEG (INT32_MIN / 4)
+
+// one step of the DP for anchor i = (i1, i2, il); AT(j, &j1, &j2, &jl, &jsc) and PM(j) fetch anchor j < i, its score and the
+// prefix maximum of the scores up to j
+template <class At, class Pm>
+__device__ __forceinline__ void dp_step(int i, int i1, int i2, int il, At AT, Pm PM, int &best, int &from, int &adj)
+{
+    best = il; from = -1; adj = 0;
+    const int idiag = i2 - i1;
+    for (int j = i - 1; j >= 0; j--) {
+        const int jpm = PM(j);
+        if (jpm + il < best || (from == -1 && jpm + il <= best)) break;
+        int j1, j2, jl, jsc;
+        AT(j, j1, j2, jl, jsc);
+        int ol1 = j1 + jl - i1, ol = ol1 > 0 ? ol1 : 0, ol2 = j2 + jl - i2;
+        if (ol2 > ol) ol = ol2;
+        int dd = idiag - (j2 - j1); if (dd < 0) dd = -dd;
+        int v = jsc + il - (ol + dd);
+        if (v > best || (v == best && from != -1)) { best = v; from = j; adj = ol; }
+    }
+}
+
+// the sequential DP (lane 0), anchors and results 32 at a time through shared memory; returns the index of the best score
+__device__ int dp_sequential(const ChainArrays &C, int64_t a, int m, ChainShared &W)
+{
+    const int lane = threadIdx.x & 31;
+    int bestIdx = 0, bestScore = INT32_MIN;                    // lane 0 only
+    for (int base = 0; base < m; base += 32) {
+        const int idx = base + lane;
+        if (idx < m) { const int sl = idx & (CH_RING - 1); W.s1[sl] = C.s1[a + idx]; W.s2[sl] = C.s2[a + idx]; W.ln[sl] = C.ln[a + idx]; }
+        __syncwarp();
+        const int cnt = m - base < 32 ? m - base : 32;
+        if (lane == 0) {
+            const int lo_ring = base - (CH_RING - 32);         // entries [lo_ring, base + 32) are in the ring
+            for (int t = 0; t < cnt; t++) {
+                const int i = base + t, sl = i & (CH_RING - 1);
+                int best, from, adj;
+                dp_step(i, W.s1[sl], W.s2[sl], W.ln[sl],
+                        [&](int j, int &j1, int &j2, int &jl, int &jsc) {
+                            const int js = j & (CH_RING - 1);
+                            if (j >= lo_ring) { j1 = W.s1[js]; j2 = W.s2[js]; jl = W.ln[js]; jsc = W.sc[js]; }
+                            else { j1 = C.s1[a + j]; j2 = C.s2[a + j]; jl = C.ln[a + j]; jsc = C.score[a + j]; }
+                        },
+                        [&](int j) { return j >= lo_ring ? W.pm[j & (CH_RING - 1)] : C.pm[a + j]; }, best, from, adj);
+                const int ppm = i > 0 ? W.pm[(i - 1) & (CH_RING - 1)] : 0;
+                const int pmv = i == 0 || best > ppm ? best : ppm;
+                W.sc[sl] = best; W.pm[sl] = pmv; W.from[t] = from; W.adj[t] = adj;
+                if (best > bestScore) { bestScore = best; bestIdx = i; }
+            }
+        }
+        __syncwarp();
+        if (idx < m) { const int sl = idx & (CH_RING - 1); C.score[a + idx] = W.sc[sl]; C.from[a + idx] = W.from[lane]; C.adj[a + idx] = W.adj[lane]; C.pm[a + idx] = W.pm[sl]; }
+        __syncwarp();
+    }
+    return __shfl_sync(0xffffffffu, bestIdx, 0);
+}
+
+// guess by scan, verify by the true step; returns the index of the best score, or -1 when the guess was wrong somewhere
+__device__ int dp_parallel(const ChainArrays &C, int64_t a, int m)
+{
+    const int lane = threadIdx.x & 31;
+    // ---- (A) c[i] = max(len[i], c[i-1] + len[i] - pen(i, i-1)) and its prefix maxima
+    int c_carry = CH_NEG, pm_carry = CH_NEG;                   // c and prefix maximum of the last anchor of the previous chunk
+    int p1 = 0, p2 = 0, pl = 0;                                // that anchor
+    for (int base = 0; base < m; base += 32) {
+        const int idx = base + lane;
+        int i1 = 0, i2 = 0, il = 0;
+        if (idx < m) { i1 = C.s1[a + idx]; i2 = C.s2[a + idx]; il = C.ln[a + idx]; }
+        int j1 = __shfl_up_sync(0xffffffffu, i1, 1), j2 = __shfl_up_sync(0xffffffffu, i2, 1), jl = __shfl_up_sync(0xffffffffu, il, 1);
+        if (lane == 0) { j1 = p1; j2 = p2; jl = pl; }
+        int A = il, B = CH_NEG;                                // the map of this anchor: x -> max(A, x + B)
+        if (idx > 0 && idx < m) {
+            int ol1 = j1 + jl - i1, ol = ol1 > 0 ? ol1 : 0, ol2 = j2 + jl - i2;
+            if (ol2 > ol) ol = ol2;
+            int dd = (i2 - i1) - (j2 - j1); if (dd < 0) dd = -dd;
+            B = il - (ol + dd);
+        }
+        if (idx >= m) { A = CH_NEG; B = 0; }                   // identity behind the end
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {                     // (A, B) of lane l becomes the composition of the maps of lanes l-o+1 .. l after those before
+            const int Ap = __shfl_up_sync(0xffffffffu, A, o), Bp = __shfl_up_sync(0xffffffffu, B, o);
+            if (lane >= o) { const int t = Ap + B; A = A > t ? A : t; B = Bp + B < CH_NEG ? CH_NEG : Bp + B; }
+        }
+        int cval = c_carry + B; if (cval < A) cval = A;        // c_carry + B stays far from overflow: both are >= CH_NEG
+        if (c_carry == CH_NEG) cval = A;
+        int pmv = cval;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, pmv, o); if (lane >= o && t > pmv) pmv = t; }
+        if (pm_carry > pmv) pmv = pm_carry;
+        if (idx < m) { C.score[a + idx] = cval; C.pm[a + idx] = pmv; }
+        const int last = (m - base < 32 ? m - base : 32) - 1;
+        c_carry = __shfl_sync(0xffffffffu, cval, last); pm_carry = __shfl_sync(0xffffffffu, pmv, last);
+        p1 = __shfl_sync(0xffffffffu, i1, last); p2 = __shfl_sync(0xffffffffu, i2, last); pl = __shfl_sync(0xffffffffu, il, last);
+    }
+    __syncwarp();
+    // ---- (B) the true step of every anchor against the guessed scores before it
+    int bestIdx = 0, bestScore = INT32_MIN; bool wrong = false;
+    for (int base = 0; base < m; base += 32) {
+        const int idx = base + lane;
+        int best = INT32_MIN, from = -1, adj = 0;
+        if (idx < m) {
+            dp_step(idx, C.s1[a + idx], C.s2[a + idx], C.ln[a + idx],
+                    [&](int j, int &j1, int &j2, int &jl, int &jsc) { j1 = C.s1[a + j]; j2 = C.s2[a + j]; jl = C.ln[a + j]; jsc = C.score[a + j]; },
+                    [&](int j) { return C.pm[a + j]; }, best, from, adj);
+            if (best != C.score[a + idx]) wrong = true;
+            C.from[a + idx] = from; C.adj[a + idx] = adj;
+        }
+        // first index of the largest score so far (strictly greater replaces, like the sequential scan)
+        int v = best, vi = idx;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const int u = __shfl_xor_sync(0xffffffffu, v, o), ui = __shfl_xor_sync(0xffffffffu, vi, o);
+            if (u > v || (u == v && ui < vi)) { v = u; vi = ui; }
+        }
+        if (v > bestScore) { bestScore = v; bestIdx = vi; }
+    }
+    if (__any_sync(0xffffffffu, wrong)) return -1;
+    return bestIdx;
+}
 
 __device__ void chain_component(const ChainArrays &C, int64_t a, int m, int mincluster, ChainShared &W)
 {
@@ -184,64 +310,43 @@ __device__ void chain_component(const ChainArrays &C, int64_t a, int m, int minc
     const int tag = C.tg[a];
     int cm = 0, ck = 0;       // matches / clusters emitted so far by this component
     while (m > 0) {
-        // ---- DP: score[i] = len[i] + max(0, max_{j<i}(score[j] - pen(i,j))), lowest j among the best
-        int bestIdx = 0, bestScore = INT32_MIN;                    // lane 0 only
-        for (int base = 0; base < m; base += 32) {
-            const int idx = base + lane;
-            if (idx < m) { const int sl = idx & (CH_RING - 1); W.s1[sl] = C.s1[a + idx]; W.s2[sl] = C.s2[a + idx]; W.ln[sl] = C.ln[a + idx]; }
-            __syncwarp();
-            const int cnt = m - base < 32 ? m - base : 32;
-            if (lane == 0) {
-                const int lo_ring = base - (CH_RING - 32);         // entries [lo_ring, base + 32) are in the ring
-                for (int t = 0; t < cnt; t++) {
-                    const int i = base + t, sl = i & (CH_RING - 1);
-                    const int i1 = W.s1[sl], i2 = W.s2[sl], il = W.ln[sl];
-                    int best = il, from = -1, adj = 0;
-                    const int idiag = i2 - i1;
-                    for (int j = i - 1; j >= 0; j--) {
-                        const bool in_ring = j >= lo_ring;
-                        const int js = j & (CH_RING - 1);
-                        const int jpm = in_ring ? W.pm[js] : C.pm[a + j];
-                        if (jpm + il < best || (from == -1 && jpm + il <= best)) break;
-                        int j1, j2, jl, jsc;
-                        if (in_ring) { j1 = W.s1[js]; j2 = W.s2[js]; jl = W.ln[js]; jsc = W.sc[js]; }
-                        else { j1 = C.s1[a + j]; j2 = C.s2[a + j]; jl = C.ln[a + j]; jsc = C.score[a + j]; }
-                        int ol1 = j1 + jl - i1, ol = ol1 > 0 ? ol1 : 0, ol2 = j2 + jl - i2;
-                        if (ol2 > ol) ol = ol2;
-                        int dd = idiag - (j2 - j1); if (dd < 0) dd = -dd;
-                        int v = jsc + il - (ol + dd);
-                        if (v > best || (v == best && from != -1)) { best = v; from = j; adj = ol; }
-                    }
-                    const int ppm = i > 0 ? W.pm[(i - 1) & (CH_RING - 1)] : 0;
-                    const int pmv = i == 0 || best > ppm ? best : ppm;
-                    W.sc[sl] = best; W.pm[sl] = pmv; W.from[t] = from; W.adj[t] = adj;
-                    if (best > bestScore) { bestScore = best; bestIdx = i; }
-                }
-            }
-            __syncwarp();
-            if (idx < m) { const int sl = idx & (CH_RING - 1); C.score[a + idx] = W.sc[sl]; C.from[a + idx] = W.from[lane]; C.adj[a + idx] = W.adj[lane]; C.pm[a + idx] = W.pm[sl]; }
-            __syncwarp();
-        }
-        // ---- mark the best chain, sum its lengths (from[i] < i: the walk only moves down)
+        // ---- DP
+        int cur = dp_parallel(C, a, m);
+        __syncwarp();
+        if (cur < 0) { cur = dp_sequential(C, a, m, W); __syncwarp(); }
+        // ---- mark the best chain, sum its lengths (from[i] < i: the walk only moves down, a chunk of 32 links at a time)
         int total = 0, root = 0;
-        int cur = __shfl_sync(0xffffffffu, bestIdx, 0);
         while (cur >= 0) {
             const int base = cur & ~31, idx = base + lane;
             int f = -1, l = 0;
             if (idx < m) { f = C.from[a + idx]; l = C.ln[a + idx]; }
-            W.from[lane] = f; W.adj[lane] = l;
-            __syncwarp();
-            unsigned mark = 0;
-            if (lane == 0) {
-                int c = cur;
-                while (c >= base) { mark |= 1u << (c - base); total += W.adj[c - base]; root = c; c = W.from[c - base]; }
-                cur = c;
+            unsigned mark;
+            // the usual chunk: every link from `cur` down to the chunk's first anchor points to the anchor before it
+            const unsigned below = 0xffffffffu >> (31 - (cur - base));                     // lanes base .. cur
+            const unsigned plain = __ballot_sync(0xffffffffu, f == idx - 1);
+            if ((plain & below) == below) {
+                mark = below;
+                int lsum = (below >> lane) & 1u ? l : 0;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+                total += lsum; root = base; cur = base - 1;
+                if (base == 0) cur = -1;
+            } else {
+                W.from[lane] = f; W.adj[lane] = l;
+                __syncwarp();
+                mark = 0;
+                if (lane == 0) {
+                    int c = cur;
+                    while (c >= base) { mark |= 1u << (c - base); total += W.adj[c - base]; root = c; c = W.from[c - base]; }
+                    cur = c;
+                }
+                mark = __shfl_sync(0xffffffffu, mark, 0); cur = __shfl_sync(0xffffffffu, cur, 0);
+                total = __shfl_sync(0xffffffffu, total, 0); root = __shfl_sync(0xffffffffu, root, 0);
+                __syncwarp();
             }
-            mark = __shfl_sync(0xffffffffu, mark, 0); cur = __shfl_sync(0xffffffffu, cur, 0);
             if ((mark >> lane) & 1u) C.good[a + idx] = 1;
-            __syncwarp();
         }
-        total = __shfl_sync(0xffffffffu, total, 0); root = __shfl_sync(0xffffffffu, root, 0);
+        __syncwarp();
         // ---- emit (chain members in index order, trimmed by their overlap with the predecessor)
         if (total >= mincluster) {
             int nout = 0;

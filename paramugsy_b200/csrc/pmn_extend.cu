@@ -1981,7 +1981,12 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     const int nslots = std::max(blocks1, blocks_st) * EX_WARPS_PER_BLOCK;                 // warps that may run the wide fallback (global score rows)
     const int nslots_tb = nslots;                                                          // warps that keep a private traceback header
     const size_t pool_cap = (size_t)std::max<int64_t>(1 << 20, 8 * nm + (ref->n + q->n) / 8);
-    const size_t arena_cap = (size_t)1 << 31;
+    // Traceback arena: 2 GB for every pair made a worker hold 2.3 GB that a bacterial pair uses a few per cent of.  It starts at
+    // 256 MB (PMN_ARENA_MB), and a pair that runs out of it grows it fourfold and is extended again (pmn_api.cu).
+    if (!S.arena_cap) { static const size_t mb = getenv("PMN_ARENA_MB") ? (size_t)atoll(getenv("PMN_ARENA_MB")) : 256; S.arena_cap = std::max<size_t>(16, mb) << 20; }
+    S.arena_retry = false;
+    if (S.ex_arena.cap > S.arena_cap + 4096) S.arena_cap = S.ex_arena.cap - 4096;       // the scheduler levelled the buffer with a worker that had to grow
+    const size_t arena_cap = S.arena_cap;
     const size_t ncap_al = (size_t)nm, ncap_nodes = 3 * (size_t)nm + 8 * (size_t)nS;
     const size_t npad = ((size_t)np + 63) / 64 * 64;
     const size_t l_bytes = npad * 3 + 8 * (size_t)nS + 64 + 16 + sizeof(ExBack) * npad;      // fused, anyfail, entered, syn_nal (2 x nS), back
@@ -2095,6 +2100,7 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
         }
     }
     res->stats.dp_cells = (int64_t)hc[2]; res->stats.dp_jobs = (int64_t)hc[3];
+    res->stats.arena_bytes = (int64_t)hc[1];
     res->stats.wave1_cells = (int64_t)hc[40];
 #ifdef PMN_STITCH_TIMING
     if (getenv("PMN_STITCH_TIMING"))     // cycles of the slowest synteny warp per section (k_ex_stitch)
@@ -2105,7 +2111,10 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     cudaEventElapsedTime(&res->stats.ms_stitch, c->ev[11], c->ev[10]);
     c->launches += launches; launches = 0;
     if (errflags & EX_ERR_POOL) return pmn_set_error(PMN_E_NOMEM, "extend: delta pool exhausted (%zu entries)", pool_cap);
-    if (errflags & EX_ERR_ARENA) return pmn_set_error(PMN_E_NOMEM, "extend: traceback arena exhausted (%zu bytes)", arena_cap);
+    if (errflags & EX_ERR_ARENA) {
+        if (arena_cap < ((size_t)32 << 30)) { S.arena_cap = arena_cap * 4; S.arena_retry = true; }
+        return pmn_set_error(PMN_E_NOMEM, "extend: traceback arena exhausted (%zu bytes)", arena_cap);
+    }
     if (errflags & EX_ERR_NODES) return pmn_set_error(PMN_E_INTERNAL, "extend: delta segment list overflow");
     if (errflags & EX_ERR_LOGIC) return pmn_set_error(PMN_E_INTERNAL, "extend: inconsistent cluster chain (target match does not exist)");
     const int64_t nal = (int64_t)hc[8], nd = (int64_t)hc[9];

@@ -22,6 +22,7 @@
 //   5. anchors are written at the slot of their position; k_seed_gather compacts them in order
 // Output order equals the oracle's sort order, so no sort follows.
 #include <algorithm>
+#include <cstring>
 
 #include "pmn_scratch.cuh"
 
@@ -349,8 +350,10 @@ int pmn_seed_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_o
     const int64_t runs = tiles * SEED_WARPS;                   // one anchor run per warp of a tile
     if (S.sections.ensure(sizeof(SeedSection) * secs.size()) || S.stage.ensure(sizeof(int4) * (size_t)tiles * SEED_TILE) ||
         S.tile_cnt.ensure(4 * (size_t)runs + 16) || S.tile_off.ensure(4 * (size_t)runs) || S.seed_bits.ensure(4 * SEED_CHUNK * (size_t)runs) ||
-        S.scan_tmp.ensure(8 * pmn_scan_scratch_elems(runs)) || S.ensure_pinned(64)) return -3;
+        S.scan_tmp.ensure(8 * pmn_scan_scratch_elems(runs)) || S.ensure_pinned(64) || S.cl_counters.ensure(64)) return -3;
     PMN_H2D(c, S.sections.p, secs.data(), sizeof(SeedSection) * secs.size());
+    unsigned long long *lookups = (unsigned long long *)((char *)S.cl_counters.p + 32);      // the clustering stage uses the first 8 bytes, later
+    PMN_CUDA_OK(cudaMemsetAsync(lookups, 0, 8, st));
     PMN_CUDA_OK(cudaEventRecord(c->ev[6], st));
     // one block per tile by default (the hardware deals tiles to SMs as they free up); PMN_SEED_BPS = k caps the grid at k
     // blocks per SM that stride over the tiles (experiment: leave thread slots to the kernels of other pairs)
@@ -358,15 +361,17 @@ int pmn_seed_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_o
     const unsigned seed_grid = seed_bps > 0 ? (unsigned)std::min<int64_t>(tiles, (int64_t)c->sm_count * seed_bps) : (unsigned)tiles;
     k_seed<<<seed_grid, SEED_THREADS, 0, st>>>(ix->seq->fwd(), ix->sa(), ix->lcp(), ix->table(), ix->skip(), ix->K,
                                                      q->fwd(), q->rev(), S.sections.as<SeedSection>(), (int)secs.size(), o->minmatch,
-                                                     S.stage.as<int4>(), S.seed_bits.as<uint32_t>(), S.tile_cnt.as<uint32_t>(), (unsigned)t_lo, (unsigned)tiles, nullptr);
+                                                     S.stage.as<int4>(), S.seed_bits.as<uint32_t>(), S.tile_cnt.as<uint32_t>(), (unsigned)t_lo, (unsigned)tiles, lookups);
     PMN_CUDA_OK(cudaEventRecord(c->ev[7], st));
     pmn_scan<uint32_t, OpAddU32, false>(S.tile_cnt.as<uint32_t>(), S.tile_off.as<uint32_t>(), runs, S.scan_tmp.as<uint32_t>(), st);
     uint32_t *tail = (uint32_t *)S.pinned;
     PMN_D2H(c, tail, S.tile_off.as<uint32_t>() + (runs - 1), 4);
     PMN_D2H(c, tail + 1, S.tile_cnt.as<uint32_t>() + (runs - 1), 4);
+    PMN_D2H(c, tail + 2, lookups, 8);
     PMN_CUDA_OK(cudaStreamSynchronize(st));   // the host sizes the clustering stage from the anchor count
     c->syncs++;
     int64_t total = (int64_t)tail[0] + tail[1];
+    { unsigned long long lk; memcpy(&lk, tail + 2, 8); S.seed_lookups = (int64_t)lk; }
     c->launches += 4;
     if (total > 0) {
         if (S.anchors.ensure(sizeof(int4) * (size_t)total)) return -3;

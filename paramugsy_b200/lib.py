@@ -45,7 +45,8 @@ class Stats(C.Structure):
                 ("ms_extend", C.c_float), ("ms_total", C.c_float), ("ms_seed_kernel", C.c_float),
                 ("ms_wave1", C.c_float), ("ms_stitch", C.c_float), ("kernel_launches", C.c_int64),
                 ("wave1_cells", C.c_int64), ("wall_ms_index", C.c_float), ("wall_ms_align", C.c_float),
-                ("wall_ms_text", C.c_float), ("wall_ms_post", C.c_float)]
+                ("wall_ms_text", C.c_float), ("wall_ms_post", C.c_float),
+                ("seed_lookups", C.c_int64), ("arena_bytes", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -63,6 +64,8 @@ SYMBOLS = [
     "pmn_result_n_deltas", "pmn_result_copy_alignments",
     "pmn_sched_create", "pmn_sched_destroy", "pmn_sched_workers", "pmn_sched_ctx", "pmn_sched_counters",
     "pmn_sched_align_fasta", "pmn_sched_align_seqs", "pmn_sched_align_indexed", "pmn_sched_align_files",
+    "pmn_multi_plan", "pmn_multi_create", "pmn_multi_destroy", "pmn_multi_devices", "pmn_multi_sched", "pmn_multi_align_fasta",
+    "pmn_multi_align_files", "pmn_multi_align_large",
     "pmn_delta_filter", "pmn_delta2maf", "pmn_free_text", "pmn_result_filtered", "pmn_result_maf", "pmn_worker_batch",
 ]
 
@@ -132,6 +135,14 @@ def lib():
         L.pmn_sched_align_seqs.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(cp), C.c_int, i32a, i32a, C.POINTER(Opts), C.POINTER(vp)]
         L.pmn_sched_align_indexed.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(cp), C.c_int, i32a, i32a, C.POINTER(Opts), C.POINTER(vp)]
         L.pmn_sched_align_files.argtypes = [vp, C.c_int, C.POINTER(cp), C.POINTER(cp), C.POINTER(cp), C.POINTER(Opts)]
+        L.pmn_multi_plan.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_size_t), C.c_int, i32a, i32a, i32a]
+        L.pmn_multi_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(vp)]
+        L.pmn_multi_destroy.argtypes = [vp]
+        L.pmn_multi_devices.argtypes = [vp]
+        L.pmn_multi_sched.argtypes = [vp, C.c_int]; L.pmn_multi_sched.restype = vp
+        L.pmn_multi_align_fasta.argtypes = [vp, C.c_int, C.POINTER(cp), C.POINTER(C.c_size_t), C.POINTER(cp), C.c_int, i32a, i32a, C.POINTER(Opts), C.POINTER(vp)]
+        L.pmn_multi_align_files.argtypes = [vp, C.c_int, C.POINTER(cp), C.POINTER(cp), C.POINTER(cp), C.POINTER(cp), C.POINTER(Opts)]
+        L.pmn_multi_align_large.argtypes = [vp, cp, C.c_size_t, cp, C.c_size_t, C.POINTER(Opts), cp, cp, C.POINTER(vp), C.POINTER(C.c_double)]
         L.pmn_delta_filter.argtypes = [vp, cp, C.c_size_t, C.c_int, C.c_double, C.POINTER(vp), C.POINTER(C.c_size_t)]
         L.pmn_delta2maf.argtypes = [vp, cp, C.c_size_t, vp, vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
         L.pmn_free_text.argtypes = [vp]
@@ -314,6 +325,63 @@ class Scheduler:
         o = opts if opts is not None else default_opts(**kw)
         arr = lambda xs: (C.c_char_p * len(xs))(*[os.fsencode(x) for x in xs])
         _check(lib().pmn_sched_align_files(self.h, len(refs), arr(refs), arr(qrys), arr(outs), C.byref(o)))
+
+
+def multi_plan(n_devices, pairs, genome_bytes=None):
+    """pmn_multi_plan: the device of every pair [(ref, qry)] (pure host arithmetic, no GPU needed)."""
+    n = len(pairs)
+    ng = (max(max(p) for p in pairs) + 1) if pairs else 0
+    if genome_bytes is not None:
+        ng = len(genome_bytes)
+    r = (C.c_int32 * n)(*[p[0] for p in pairs]); q = (C.c_int32 * n)(*[p[1] for p in pairs]); out = (C.c_int32 * n)()
+    nb = (C.c_size_t * ng)(*genome_bytes) if genome_bytes is not None else None
+    _check(lib().pmn_multi_plan(n_devices, ng, nb, n, r, q, out))
+    return list(out)
+
+
+class Multi:
+    """Several GPUs of one box driven by ONE process (pmn_multi): one scheduler per device."""
+
+    def __init__(self, devices, workers=8):
+        devices = list(devices)
+        self.h = C.c_void_p()
+        _check(lib().pmn_multi_create((C.c_int * len(devices))(*devices), len(devices), workers, C.byref(self.h)))
+        self.devices = devices
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().pmn_multi_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def align_fasta(self, fastas, pairs, names=None, opts=None, **kw):
+        o = opts if opts is not None else default_opts(**kw)
+        g = len(fastas)
+        fa = (C.c_char_p * g)(*fastas)
+        nb = (C.c_size_t * g)(*[len(f) for f in fastas])
+        nm = (C.c_char_p * g)(*[os.fsencode(x) for x in names]) if names else None
+        n, r, q = Scheduler._pairs(pairs)
+        out = (C.c_void_p * n)()
+        _check(lib().pmn_multi_align_fasta(self.h, g, fa, nb, nm, n, r, q, C.byref(o), out))
+        return [Result(C.c_void_p(h)) for h in out]
+
+    def align_files(self, refs, qrys, outs, mafs=None, opts=None, **kw):
+        o = opts if opts is not None else default_opts(**kw)
+        arr = lambda xs: (C.c_char_p * len(xs))(*[os.fsencode(x) for x in xs])
+        _check(lib().pmn_multi_align_files(self.h, len(refs), arr(refs), arr(qrys), arr(outs), arr(mafs) if mafs else None, C.byref(o)))
+
+    def align_large(self, ref_fasta: bytes, qry_fasta: bytes, ref_path="ref.fa", qry_path="qry.fa", opts=None, **kw):
+        """-> (Result, [ms pack+index, ms seeding, ms gather, ms clustering+extension+text])."""
+        o = opts if opts is not None else default_opts(**kw)
+        r = C.c_void_p(); ms = (C.c_double * 4)()
+        _check(lib().pmn_multi_align_large(self.h, ref_fasta, len(ref_fasta), qry_fasta, len(qry_fasta), C.byref(o),
+                                          os.fsencode(ref_path), os.fsencode(qry_path), C.byref(r), ms))
+        return Result(r), list(ms)
 
 
 class Sequence:

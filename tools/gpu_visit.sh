@@ -13,6 +13,8 @@ for s in $steps; do
     bench)   timeout 900 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"; head -c 400 gpurun_out/${tag}_bench.json; echo ;;
     bench_ref) timeout 900 python bench.py --impl reference --steps 1 --warmup 1 > gpurun_out/${tag}_bench_ref.json 2> gpurun_out/${tag}_bench_ref.err; echo "ref rc=$?"; head -c 300 gpurun_out/${tag}_bench_ref.json; echo ;;
     ncu_launches) timeout 900 ncu --metrics gpu__time_duration.sum,sm__cycles_active.avg,smsp__inst_executed.sum --clock-control none --csv --log-file gpurun_out/${tag}_launches_bench.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/${tag}_ncu_launches.log 2>&1; echo "ncu launches rc=$?" ;;
+    ncu_pair) timeout 900 ncu --metrics gpu__time_duration.sum,sm__cycles_active.avg,smsp__inst_executed.sum --clock-control none --csv --log-file gpurun_out/launches_pair.csv python tools/profile_pair.py 5000000 2 > gpurun_out/${tag}_ncu_pair.log 2>&1; echo "ncu pair rc=$?"; cp gpurun_out/launches_pair.csv gpurun_out/${tag}_launches_pair.csv ;;
+    ncu_full) timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:k_ex_wave|k_ex_stitch|k_seed$|k_cl_chains|pmn_rs_scatter|pmn_scan_onepass" -c 14 -o gpurun_out/pair_full -f python tools/profile_pair.py 5000000 1 > gpurun_out/${tag}_ncu_full.log 2>&1; echo "ncu full rc=$?" ;;
     *) echo "unknown step $s" ;;
   esac
 done
