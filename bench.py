@@ -4,21 +4,27 @@
     python bench.py --gpus 1 --steps K --warmup W
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...          # the CPU path (oracle port) on the host cores
+    python bench.py --config c4 ...               # the single 100 Mbp pair, query-chunk partitioned over the ranks
 
-Workload (BASELINE.json configs[1]): 8 synthetic 5 Mbp genomes (2 % divergence from a common
-ancestor, two 50 kbp inversions each), all-vs-all = 28 (reference, query) pairs, the earlier
-genome being the reference (lib/base/pm_job.ml:43-51).  One STEP = one pass of the hot path
-over that batch: 7 index builds + 28 x (seeding, clustering, extension, .delta text).
+Workload (BASELINE.json configs[1]): 8 synthetic 5 Mbp genomes (2 % divergence from a common ancestor, two 50 kbp
+inversions each), all-vs-all = 28 (reference, query) pairs, the earlier genome being the reference
+(lib/base/pm_job.ml:43-51).  One STEP = one pass of the hot path over that batch: every reference index built, 28 x
+(seeding, clustering, extension, .delta text).
 
-  value   pairs/s with the packed genomes already resident in HBM (index build is inside).
-  e2e     the same through the C ABI from FASTA bytes in HOST memory to .delta bytes in HOST
-          memory: parse + H2D + pack of all 8 genomes and D2H of every result are inside.
-  N > 1   weak scaling: every rank runs the same 28-pair batch on its own GPU (the path is
-          embarrassingly parallel by pair; `--mode strong` shards the 28 pairs over the ranks
-          with the reference indexes built once and broadcast over NCCL instead).
+  value   pairs/s with the packed genomes already resident in HBM (index builds are inside).
+  e2e     the same through the C ABI from FASTA bytes in pinned HOST memory to .delta bytes in HOST memory: parse + H2D +
+          pack of the genomes and D2H of every result are inside.
+  N > 1   the 28 pairs are SHARDED over the ranks (pmn_multi_plan: the pair list in reference order cut into N runs), every
+          rank packs the genomes and builds the indexes its pairs name: no collective in the data path ("scaling": "strong",
+          the batch is fixed).  `extra_weak` in the same line is every rank running the whole batch (N replicas).
+          --replicate broadcast builds every index once in the job and sends its image to the consumers over NCCL instead.
+  parity  before anything is timed, the .delta of all 28 pairs is compared with the oracle's committed digests
+          (tests/golden/golden_configs.json) and, in the cpu_baseline leg, byte for byte with the oracle run on the host.
 """
 import argparse
+import hashlib
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -45,6 +51,8 @@ from paramugsy_b200 import synth  # noqa: E402
 
 METRIC = "nucmer_pair_alignments_per_s"
 UNIT = "pairs/s"
+PARITY_NOTE = ("bit-exact against the in-repo CPU oracle (oracle/pmn_oracle.c, a restatement of MUMmer 3.20's nucmer); the oracle "
+               "itself is UNPINNED against MUMmer, which the reference does not vendor")
 
 
 def peaks():
@@ -60,6 +68,15 @@ def workload(args):
     fastas = [(name, synth.fasta(name, seq)) for name, seq in genomes]
     pairs = [(i, j) for i in range(len(genomes)) for j in range(i + 1, len(genomes))]
     return genomes, fastas, pairs
+
+
+def golden(cfg):
+    p = os.path.join(ROOT, "tests", "golden", "golden_configs.json")
+    return json.load(open(p)).get(cfg, {}) if os.path.exists(p) else {}
+
+
+def sha(b):
+    return hashlib.sha256(b).hexdigest()
 
 
 class ClockSampler:
@@ -108,272 +125,418 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------------ GPU arm
+class Ranks:
+    """torch.distributed plumbing shared by the two workloads: barrier, device-timed regions, max over ranks."""
 
-def run_gpu(args):
-    import torch
-    import torch.distributed as dist
-    from paramugsy_b200 import lib
-
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0")); self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world == 1 and args.gpus > 1:
             raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    if getattr(args, "workers_auto", False):
-        # a worker holds about 9 GB of scratch and traceback arenas: no more workers than the free memory takes
-        free_b, _ = torch.cuda.mem_get_info()
-        args.workers = max(4, min(args.workers, int((free_b / 2**30 - 20) // 9.5)))
-    sched = lib.Scheduler(local, args.workers)
-    ctx = sched.context(0)
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
 
-    genomes, fastas, pairs = workload(args)
-    names = [g[0] for g in genomes]
-    # end-to-end arm: the FASTA text of every genome sits in PINNED host memory and is copied to the device every step
-    pinned = [torch.frombuffer(bytearray(f[1]), dtype=torch.uint8).pin_memory() for f in fastas]
-    fasta_bytes = [(t.data_ptr(), t.numel()) for t in pinned]
-    strong = args.mode == "strong" and world > 1
-    if strong:
-        # the 28 pairs are dealt to the ranks; every reference index is built once in the whole job and
-        # replicated to the ranks that need it by an NCCL broadcast of its image (paramugsy_b200/multi.py)
-        from paramugsy_b200 import multi
-        assignment = multi.assign_pairs(pairs, world)
-        plan = multi.index_plan(pairs, assignment)
-        my_pairs = [pairs[k] for k in assignment[rank]]
-        needed = sorted({g for p in my_pairs for g in p} | {ref for ref, (o, rs) in plan.items() if o == rank or rank in rs})
-    else:
-        my_pairs = pairs
-        needed = list(range(len(genomes)))
-    refs = sorted({i for i, _ in my_pairs})
-    total_bp_in = sum(len(genomes[i][1]) + len(genomes[j][1]) for i, j in my_pairs)
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    def step_resident(seqs, collect=None, one_worker=None):
-        """One pass of the hot path over the batch, genomes already packed in HBM: every reference
-        index is built once, all pairs are aligned, every .delta ends up in host memory."""
-        if one_worker is not None:          # the instrumented pass: one pair at a time, kernels timed alone
-            for i in refs:
-                ix = seqs[i].index()
-                for (a, b) in my_pairs:
-                    if a == i:
-                        res = ix.align(seqs[b], ref_path=names[a], qry_path=names[b])
-                        collect.append((a, b, res.stats, len(res.delta)))
-                        # the two post-steps every pair goes through in the reference (mugsy_nucmer.ml:102-105,118-124)
-                        t0 = time.perf_counter(); filt = ctx.delta_filter(res.delta, 1)
-                        t1 = time.perf_counter(); maf = ctx.delta2maf(filt, seqs[a], seqs[b]); t2 = time.perf_counter()
-                        post.append(((t1 - t0) * 1e3, (t2 - t1) * 1e3, len(filt), len(maf)))
-                        res.close()
-                ix.close()
-            return
-        if strong:
-            out = multi.AllVsAll(sched, [seqs.get(g) for g in range(len(genomes))], names, pairs, rank, world, dist).step()
-            for res in out.values():
-                res.close()
-            return
-        for res in sched.align_seqs([seqs[g] for g in range(len(genomes))], my_pairs, names=names):
-            res.close()
-
-    def step_e2e():
-        """The same from FASTA bytes in host memory (parse, H2D, pack inside)."""
-        if strong:
-            seqs = {g: ctx.sequence(fastas[g][1]) for g in needed}
-            step_resident(seqs)
-            for q in seqs.values():
-                q.close()
-            return
-        for res in sched.align_fasta(fasta_bytes, my_pairs, names=names):
-            res.close()
-
-    def step_worker():
-        """The whole reference worker per pair (lib/nucmer/mugsy_nucmer.ml:127-131): nucmer, delta-filter -1 and delta2maf,
-        from FASTA text in pinned host memory to the three texts in host memory, in one scheduler call (pmn_opts.post)."""
-        for res in sched.align_fasta(fasta_bytes, my_pairs, names=names, post=1):
-            res.close()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        if os.environ.get("PMN_ALLOC_LOG"):
-            print(f"[bench] timed region starts, {lib.alloc_count()} allocations so far", file=sys.stderr, flush=True)
-        # the workers launch on their own streams and every call returns with all of them drained, so
-        # events recorded on the (idle) current stream around the calls bracket exactly the device work
-        barrier()
-        c0 = sched.counters(); a0 = lib.alloc_count()
+    def timed(self, fn, steps, counters=None, allocs=None):
+        """K calls of fn bracketed by barrier + synchronize, timed with CUDA events on the (idle) current stream: every call
+        returns with all worker streams drained, so the two events bracket exactly the device work.  -> (ms max over ranks, info)"""
+        torch, dist = self.torch, self.dist
+        self.barrier()
+        c0 = counters() if counters else {}; a0 = allocs() if allocs else 0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         walls = []
         for _ in range(steps):
             t = time.perf_counter(); fn(); walls.append((time.perf_counter() - t) * 1e3)
         e1.record()
-        barrier()
+        self.barrier()
         ms = e0.elapsed_time(e1)
-        ranks_ms = [round(ms / steps, 2)]
-        if world > 1:
-            allms = torch.zeros(world, device="cuda", dtype=torch.float64); allms[rank] = ms
+        ranks_ms = [round(ms / steps, 3)]
+        if self.world > 1:
+            allms = torch.zeros(self.world, device="cuda", dtype=torch.float64); allms[self.rank] = ms
             dist.all_reduce(allms)                              # every rank's own time (diagnostic: stragglers)
-            ranks_ms = [round(float(x) / steps, 2) for x in allms.tolist()]
+            ranks_ms = [round(float(x) / steps, 3) for x in allms.tolist()]
             t = torch.tensor([ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        c1 = sched.counters()
-        d = {k: c1[k] - c0[k] for k in c0}; d["walls"] = [round(w, 2) for w in walls]; d["allocs"] = lib.alloc_count() - a0
-        d["ranks_ms"] = ranks_ms
+        c1 = counters() if counters else {}
+        d = {k: c1[k] - c0[k] for k in c0}
+        d["walls"] = [round(w, 2) for w in walls]; d["allocs"] = (allocs() - a0) if allocs else 0; d["ranks_ms"] = ranks_ms
         return ms, d
 
-    # ---- resident arm
+    def sum(self, *vals):
+        if self.world == 1:
+            return [float(v) for v in vals]
+        t = self.torch.tensor(list(vals), device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t)
+        return [float(x) for x in t.tolist()]
+
+    def close(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def spread(walls):
+    return {"min": min(walls), "median": statistics.median(walls), "max": max(walls), "n": len(walls)} if walls else None
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the kernels, from this round's committed `ncu --set full` capture of one C2 pair."""
+    for name in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            return json.load(open(p))["kernels"], f"profiles/{name} (ncu --set full --clock-control none, one C2 pair)"
+    return {}, None
+
+
+# ------------------------------------------------------------------------------------------ GPU arm, C2
+
+def run_gpu(args):
+    from paramugsy_b200 import lib
+    R = Ranks(args)
+    torch, rank, world, local = R.torch, R.rank, R.world, R.local
+    if args.workers_auto:
+        # a worker holds 3-4 GB of scratch, traceback slots and arena (DESIGN.md §3): no more workers than the free memory takes
+        free_b, _ = torch.cuda.mem_get_info()
+        args.workers = max(4, min(args.workers, int((free_b / 2**30 - 24) // 4.5)))
+    sched = lib.Scheduler(local, args.workers)
+    ctx = sched.context(0)
+
+    genomes, fastas, pairs = workload(args)
+    names = [g[0] + ".fa" for g in genomes]
+    nbytes = [len(f[1]) for f in fastas]
+    # end-to-end arm: the FASTA text of every genome sits in PINNED host memory and is copied to the device every step
+    pinned = [torch.frombuffer(bytearray(f[1]), dtype=torch.uint8).pin_memory() for f in fastas]
+    fasta_bytes = [(t.data_ptr(), t.numel()) for t in pinned]
+    mode = args.mode if args.mode != "auto" else ("strong" if world > 1 else "single")
+    sharded = mode == "strong" and world > 1
+    dev_of = lib.multi_plan(world, pairs, nbytes) if sharded else [rank] * len(pairs)
+    my_pairs = [p for p, d in zip(pairs, dev_of) if d == rank]
+    needed = sorted({g for p in my_pairs for g in p})
+    refs = sorted({i for i, _ in my_pairs})
+    total_bp_in = sum(len(genomes[i][1]) + len(genomes[j][1]) for i, j in my_pairs)
+    broadcast = sharded and args.replicate == "broadcast"
+    if broadcast:
+        from paramugsy_b200 import multi
+        needed = list(range(len(genomes)))       # an owner may build an index none of its own pairs names
+
     resident = {g: ctx.sequence(fastas[g][1]) for g in needed}
+    seq_list = [resident.get(g) for g in range(len(genomes))]
+    all_pairs_weak = pairs
+
+    def run_batch(plist, from_fasta, keep=None, post=0, deltas=False):
+        if broadcast and not from_fasta and plist is my_pairs:
+            out = multi.AllVsAll(sched, seq_list, names, pairs, rank, world, R.dist).step()
+            res = [out[k] for k in sorted(out)]
+        elif not plist:
+            res = []
+        elif from_fasta:
+            res = sched.align_fasta(fasta_bytes, plist, names=names, post=post)
+        else:
+            res = sched.align_seqs(seq_list, plist, names=names)
+        for r in res:
+            if keep is not None:
+                keep.append((r.delta if deltas else None, r.stats_raw))      # the raw struct: turned into numbers after the timed region
+            r.close()
+
+    # ---- parity before timing: every pair of this rank against the oracle's committed digests (tests/golden)
+    gold = golden("c2") if (args.genome_bp, args.genomes) == (5_000_000, 8) else {}
+    first = []
+    run_batch(my_pairs, False, keep=first, deltas=True)
+    checked, bad = 0, []
+    my_delta = {}
+    for (i, j), (d, st) in zip(my_pairs, first):
+        my_delta[(i, j)] = d
+        g = gold.get(f"{genomes[i][0]}-{genomes[j][0]}")
+        if g:
+            checked += 1
+            if sha(d) != g["delta_sha256"]:
+                bad.append(f"{genomes[i][0]}-{genomes[j][0]}")
+    if bad:
+        raise SystemExit(f"bench.py: PARITY FAILURE on rank {rank}: .delta of {bad} differs from the oracle's digest")
+    (checked_all,) = R.sum(checked)
+
+    def c_sched():
+        return sched.counters()
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()          # before the warm-up: nvidia-smi's own start-up must not land in the timed region
         sampler.wait_first_sample()
-    barrier()
+    R.barrier()
+    # ---- resident arm
     for _ in range(args.warmup):
-        step_resident(resident)
-    ms_res, cnt_res = timed(lambda: step_resident(resident), args.steps)
+        run_batch(my_pairs, False)
+    timed_stats = []
+    ms_res, cnt_res = R.timed(lambda: run_batch(my_pairs, False, keep=timed_stats), args.steps, c_sched, lib.alloc_count)
     # ---- end-to-end arm (host FASTA bytes -> host .delta bytes)
     for _ in range(args.warmup):
-        step_e2e()
-    ms_e2e, cnt_e2e = timed(step_e2e, args.steps)
-    ms_wrk, cnt_wrk = (None, None)
-    if not strong:
-        for _ in range(args.warmup):
-            step_worker()
-        ms_wrk, cnt_wrk = timed(step_worker, args.steps)
+        run_batch(my_pairs, True)
+    ms_e2e, cnt_e2e = R.timed(lambda: run_batch(my_pairs, True), args.steps, c_sched, lib.alloc_count)
+    # ---- the whole reference worker per pair: nucmer + delta-filter -1 + delta2maf in one call (pmn_opts.post)
+    for _ in range(args.warmup):
+        run_batch(my_pairs, True, post=1)
+    ms_wrk, cnt_wrk = R.timed(lambda: run_batch(my_pairs, True, post=1), args.steps, c_sched, lib.alloc_count)
     clocks = sampler.stop() if rank == 0 else None
-    # ---- one instrumented pass for the per-kernel figures
-    detail = []; post = []
-    step_resident(resident, detail, one_worker=True)
+    # ---- N > 1: the replica mode next to the sharded one (every rank runs the whole batch)
+    weak = None
+    if sharded:
+        for g in range(len(genomes)):
+            if g not in resident:
+                resident[g] = ctx.sequence(fastas[g][1])
+        seq_list = [resident.get(g) for g in range(len(genomes))]
+        for _ in range(args.warmup):
+            run_batch(all_pairs_weak, False)
+        ms_w, _ = R.timed(lambda: run_batch(all_pairs_weak, False), args.steps)
+        for _ in range(args.warmup):
+            run_batch(all_pairs_weak, True)
+        ms_we, _ = R.timed(lambda: run_batch(all_pairs_weak, True), args.steps)
+        weak = {"what": "every rank runs the whole 28-pair batch on its own GPU (N independent replicas, no sharding)", "scaling": "weak",
+                "value": len(pairs) * world * args.steps / (ms_w * 1e-3), "e2e": len(pairs) * world * args.steps / (ms_we * 1e-3), "unit": UNIT,
+                "ms_per_step": ms_w / args.steps}
+    # ---- one instrumented pass, one pair at a time (kernels alone on the GPU), and the INT32 roof
+    alone = []
+    for i in refs:
+        ix = resident[i].index()
+        for (a, b) in my_pairs:
+            if a == i:
+                res = ix.align(resident[b], ref_path=names[a], qry_path=names[b]); alone.append((a, b, res.stats, len(res.delta))); res.close()
+        ix.close()
     int32_gops, _ = ctx.int32_peak()
 
     npairs_rank = len(my_pairs)
-    if world > 1:
-        t = torch.tensor([npairs_rank, total_bp_in], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t)
-        npairs_all, bp_all = float(t[0].item()), float(t[1].item())
-    else:
-        npairs_all, bp_all = float(npairs_rank), float(total_bp_in)
-
+    npairs_all, bp_all, aligned_all = R.sum(npairs_rank, total_bp_in, sum(d[2]["aligned_ref_bases"] for d in alone))
     if rank == 0:
         hbm_peak, peak_src = peaks()
-        S = lambda k: sum(d[2][k] for d in detail)
+        stats_in = [st.as_dict() for _, st in timed_stats]      # every pair of every timed step, CUDA-event times taken under load
+        n_in = max(1, len(stats_in))
+        S_in = lambda k: sum(st[k] for st in stats_in)
+        S = lambda k: sum(d[2][k] for d in alone)
         aligned_bp = S("aligned_ref_bases")
-        stage_ms = {"index": 0.0, "seed": S("ms_seed"), "cluster": S("ms_cluster"), "extend": S("ms_extend")}
-        # every reference index is built once per step: take ms_index once per distinct reference
-        seen = {}
-        for a, b, st, _ in detail:
-            seen.setdefault(a, st["ms_index"])
-        stage_ms["index"] = sum(seen.values())
         step_ms = ms_res / args.steps
-        # algorithmic bytes (SURVEY.md §8d / DESIGN.md §6)
-        import math
-        b_seed = sum(2 * st["qry_bases"] * (12 * math.ceil(math.log2(max(2, st["ref_bases"]))) + 8.25) + 12 * st["anchors"] for _, _, st, _ in detail)
-        b_index = sum(len(genomes[a][1]) * (4.25 + 16 * max(1, rounds) + 12.5)
-                      for a, rounds in {a: st["sa_rounds"] for a, _, st, _ in detail}.items())
-        seed_kernel_ms = S("ms_seed_kernel")
-        wave1_ms, wave1_cells = S("ms_wave1"), S("wave1_cells")
-        roof_seed = {"kernel": "k_seed", "bound": "hbm", "achieved": b_seed / (seed_kernel_ms * 1e-3) / 1e9 if seed_kernel_ms else None,
-                     "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src, "traffic": None,
-                     "algorithmic_bytes_per_launch": b_seed / max(1, len(detail)), "launch_ms": seed_kernel_ms / max(1, len(detail)),
-                     "share_of_step": seed_kernel_ms / (sum(stage_ms.values()) or 1)}
+        seen = {}
+        for a, b, st, _ in alone:
+            seen.setdefault(a, st["ms_index"])
+        stage_alone = {"index": sum(seen.values()), "seed": S("ms_seed"), "cluster": S("ms_cluster"), "extend": S("ms_extend")}
+        stage_in = {"seed": S_in("ms_seed") / args.steps, "cluster": S_in("ms_cluster") / args.steps, "extend": S_in("ms_extend") / args.steps}
+        traffic, traffic_src = ncu_traffic()
+        if args.genome_bp != 5_000_000:
+            traffic, traffic_src = {}, None
+        # ---- seeding: bytes the kernel's own algorithm needs, per launch
+        #   per looked-up position: K-mer table entry pair 8 B + suffix-array entry 4 B + one 8-byte reference word + 1 B of the skip table;
+        #   per position (looked up or stepped over): 0.375 B of packed query (text + mask bits); 16 B per anchor written.
+        n_seed = max(1, len(alone))
+        b_own = sum(st["seed_lookups"] * 21.0 + 2 * st["qry_bases"] * 0.375 + 16 * st["anchors"] for _, _, st, _ in alone)
+        b_model = sum(2 * st["qry_bases"] * (12 * math.ceil(math.log2(max(2, st["ref_bases"]))) + 8.25) + 12 * st["anchors"] for _, _, st, _ in alone)
+        seed_ms_alone, seed_ms_in = S("ms_seed_kernel") / n_seed, S_in("ms_seed_kernel") / n_in
+        lookups = sum(st["seed_lookups"] for _, _, st, _ in alone); positions = sum(2 * st["qry_bases"] for _, _, st, _ in alone)
+        seed_traffic = (traffic.get("k_seed") or {}).get("dram_bytes_per_launch")
+        roof_seed = {"kernel": "k_seed", "bound": "hbm", "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": b_own / n_seed,
+                     "launch_ms": seed_ms_in, "launch_ms_alone": seed_ms_alone,
+                     "achieved": b_own / n_seed / (seed_ms_in * 1e-3) / 1e9 if seed_ms_in else None,
+                     "achieved_alone": b_own / n_seed / (seed_ms_alone * 1e-3) / 1e9 if seed_ms_alone else None,
+                     "traffic": seed_traffic, "traffic_source": traffic_src,
+                     "dram_gbs_alone": seed_traffic / (seed_ms_alone * 1e-3) / 1e9 if seed_traffic and seed_ms_alone else None,
+                     "positions_looked_up": lookups / max(1, positions),
+                     "survey_model": {"what": "SURVEY.md §8d counts a full binary search per position (12 B x log2 n + 8.25): work the kernel no longer does; "
+                                              "equivalent-work rate only, NOT a roofline fraction", "bytes_per_launch": b_model / n_seed,
+                                      "equivalent_gbs_alone": b_model / n_seed / (seed_ms_alone * 1e-3) / 1e9 if seed_ms_alone else None},
+                     "note": "random 32-byte sectors of a 64 MB table and a 20 MB suffix array: a latency-bound gather, not a stream"}
         roof_seed["frac"] = roof_seed["achieved"] / hbm_peak if roof_seed["achieved"] else None
-        # SURVEY §8d counts a full binary search per position (12 B x log2 n); the K-mer table replaces it, so the kernel
-        # moves far fewer bytes than that model (hence frac > 1 at 5 Mbp, where the index is also L2-resident).  The bytes the
-        # table path itself needs per (position, strand): table 8 + suffix 4 + reference word 8 + query 0.375.
-        b_seed_table = sum(2 * st["qry_bases"] * 20.375 + 16 * st["anchors"] for _, _, st, _ in detail)
-        roof_seed["table_path"] = {"bytes_per_launch": b_seed_table / max(1, len(detail)),
-                                   "achieved": b_seed_table / (seed_kernel_ms * 1e-3) / 1e9 if seed_kernel_ms else None,
-                                   "frac": b_seed_table / (seed_kernel_ms * 1e-3) / 1e9 / hbm_peak if seed_kernel_ms else None,
-                                   "what": "bytes the K-mer-table path needs (20.375 B per position and strand), same launch time"}
-        gcups = wave1_cells / (wave1_ms * 1e-3) / 1e9 if wave1_ms else None
-        roof_ext = {"kernel": "k_ex_wave1_tpj + k_ex_wave1_big (side by side on two streams)", "bound": "int32", "traffic": None, "achieved": gcups * 16 if gcups else None, "peak": int32_gops, "unit": "Gop/s",
-                    "peak_source": "measured (pmn_measure_int32_peak, add+max chains)", "gcups": gcups, "ops_per_cell": 16,
-                    "cells_per_step": wave1_cells, "launch_ms": wave1_ms / max(1, len(detail)),
-                    "share_of_step": wave1_ms / (sum(stage_ms.values()) or 1)}
+        roof_seed["frac_alone"] = roof_seed["achieved_alone"] / hbm_peak if roof_seed["achieved_alone"] else None
+        # ---- extension wave 1
+        w1_in, w1_alone = S_in("ms_wave1") / n_in, S("ms_wave1") / n_seed
+        cells_pair = S("wave1_cells") / n_seed
+        gcups_in = cells_pair / (w1_in * 1e-3) / 1e9 if w1_in else None
+        gcups_alone = cells_pair / (w1_alone * 1e-3) / 1e9 if w1_alone else None
+        roof_ext = {"kernel": "k_ex_wave1_tpj + k_ex_wave1_big (side by side on two streams)", "bound": "int32", "peak": int32_gops, "unit": "Gop/s",
+                    "peak_source": "measured (pmn_measure_int32_peak, add+max chains)", "ops_per_cell": 16, "cells_per_launch": cells_pair,
+                    "launch_ms": w1_in, "launch_ms_alone": w1_alone, "gcups": gcups_in, "gcups_alone": gcups_alone,
+                    "achieved": gcups_in * 16 if gcups_in else None, "achieved_alone": gcups_alone * 16 if gcups_alone else None,
+                    "traffic": sum((traffic.get(k) or {}).get("dram_bytes_per_launch", 0) for k in ("k_ex_wave1_tpj", "k_ex_wave1_big")) or None,
+                    "traffic_source": traffic_src,
+                    "note": "the window is bounded by a few long alignments (cluster-end searches one warp runs each), not by INT32 issue"}
         roof_ext["frac"] = roof_ext["achieved"] / int32_gops if roof_ext["achieved"] else None
-        roof_idx = {"kernel": "index build (sort + doubling + lcp + table)", "bound": "hbm", "achieved": b_index / (stage_ms["index"] * 1e-3) / 1e9 if stage_ms["index"] else None,
-                    "peak": hbm_peak, "unit": "GB/s"}
+        roof_ext["frac_alone"] = roof_ext["achieved_alone"] / int32_gops if roof_ext["achieved_alone"] else None
+        b_index = sum(len(genomes[a][1]) * (4.25 + 16 * max(1, rounds) + 12.5 + 6) for a, rounds in {a: st["sa_rounds"] for a, _, st, _ in alone}.items())
+        roof_idx = {"kernel": "index build (sort + doubling + lcp + table + skip table)", "bound": "hbm", "peak": hbm_peak, "unit": "GB/s",
+                    "achieved": b_index / (stage_alone["index"] * 1e-3) / 1e9 if stage_alone["index"] else None, "launch_ms": stage_alone["index"] / max(1, len(seen))}
         roof_idx["frac"] = roof_idx["achieved"] / hbm_peak if roof_idx["achieved"] else None
-        # DRAM bytes per launch from the committed ncu --set full capture of one 5 Mbp pair (profiles/): static, not measured in this run
-        tr = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-        if os.path.exists(tr) and args.genome_bp == 5_000_000:
-            kt = json.load(open(tr))["kernels"]
-            if "k_seed" in kt: roof_seed["traffic"] = kt["k_seed"]["dram_bytes_per_launch"]
-            roof_ext["traffic"] = sum(kt[k]["dram_bytes_per_launch"] for k in ("k_ex_wave1_tpj", "k_ex_wave1_big") if k in kt) or None
-            roof_ext["traffic_source"] = roof_seed["traffic_source"] = "profiles/r01_ncu_traffic.json (ncu --set full, one pair)"
-        dominant = roof_ext if wave1_ms >= seed_kernel_ms else roof_seed
+        # the kernel with the largest share of the time the pairs of the timed steps spent on the device
+        share = {"k_seed": S_in("ms_seed_kernel"), "wave1": S_in("ms_wave1")}
+        tot_in = S_in("ms_seed") + S_in("ms_cluster") + S_in("ms_extend")
+        roof_seed["share_of_pair_time"] = share["k_seed"] / tot_in if tot_in else None
+        roof_ext["share_of_pair_time"] = share["wave1"] / tot_in if tot_in else None
+        dominant = dict(roof_ext if share["wave1"] >= share["k_seed"] else roof_seed)
+        launches_pair = cnt_res["launches"] / max(1, npairs_rank * args.steps)
         out = {
             "metric": METRIC, "value": npairs_all * args.steps / (ms_res * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
-            "higher_is_better": True, "scaling": "weak" if args.mode == "weak" else "strong", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "weak" if mode == "weak" else "strong", "vs_baseline": None,
             "dtype": "int32 (2-bit packed text, u8 traceback)", "data": "synthetic",
             "config": {"workload": f"{args.genomes} synthetic {args.genome_bp / 1e6:g} Mbp genomes, all-vs-all {len(pairs)} pairs "
-                                   f"(BASELINE.json configs[1]); per rank: {npairs_rank} pairs, {len(refs)} index builds per step",
-                       "mode": args.mode, "pairs_per_step_all_ranks": npairs_all, "workers_per_gpu": args.workers,
+                                   f"(BASELINE.json configs[1]); rank 0: {npairs_rank} pairs, {len(refs)} index builds per step",
+                       "mode": ("sharded by pair over the ranks, indexes " + ("built once and broadcast over NCCL" if broadcast else "rebuilt by every rank that needs them (no collective)"))
+                               if sharded else ("every rank runs the whole batch" if world > 1 else "one GPU"),
+                       "pairs_per_step_all_ranks": npairs_all, "workers_per_gpu": args.workers,
                        "hw_queues": int(os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS", "8")),
-                       "l2": "no explicit flush: one step streams > 1 GB of index, staging and score data per pair through a 126 MB L2"},
-            "aligned_mbp_per_s": aligned_bp * world / 1e6 / (step_ms * 1e-3) if args.mode == "weak" else aligned_bp / 1e6 / (step_ms * 1e-3),
+                       "l2": "no explicit flush: one step streams > 1 GB of index, staging and score data per pair through a 126 MB L2",
+                       "parity": PARITY_NOTE},
+            "parity_checked_pairs": int(checked_all),
+            "parity_how": "sha256 of every pair's .delta == the oracle's committed digest (tests/golden/golden_configs.json), checked before the timed region on every rank",
+            "aligned_mbp_per_s": aligned_all / 1e6 / (step_ms * 1e-3),
             "input_mbp_per_s": bp_all / 1e6 / (step_ms * 1e-3),
-            "extension_gcups": gcups,
+            "extension_gcups": gcups_in, "extension_gcups_alone": gcups_alone,
             "e2e": {"value": npairs_all * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": cnt_e2e["h2d_bytes"] // args.steps, "d2h_bytes_per_step": cnt_e2e["d2h_bytes"] // args.steps,
-                    "delta_bytes_per_step": sum(d[3] for d in detail)},
+                    "delta_bytes_per_step": sum(d[3] for d in alone)},
             "e2e_worker": {"what": "nucmer + delta-filter -1 + delta2maf per pair in the same call (pmn_opts.post = 1): .delta, filtered .delta and MAF in host memory",
                            "value": npairs_all * args.steps / (ms_wrk * 1e-3), "unit": UNIT, "ms_per_step": ms_wrk / args.steps,
-                           "h2d_bytes_per_step": cnt_wrk["h2d_bytes"] // args.steps, "d2h_bytes_per_step": cnt_wrk["d2h_bytes"] // args.steps} if ms_wrk else None,
-            "gpu_launches": cnt_res["launches"], "step_wall_ms": {"resident": cnt_res["walls"], "e2e": cnt_e2e["walls"], "e2e_worker": cnt_wrk["walls"] if cnt_wrk else None},
+                           "h2d_bytes_per_step": cnt_wrk["h2d_bytes"] // args.steps, "d2h_bytes_per_step": cnt_wrk["d2h_bytes"] // args.steps},
+            "extra_weak": weak,
+            "gpu_launches": cnt_res["launches"], "launches_per_pair": launches_pair,
+            "host_syncs_per_pair": cnt_res["syncs"] / max(1, npairs_rank * args.steps),
+            "step_wall_ms": {"resident": spread(cnt_res["walls"]), "e2e": spread(cnt_e2e["walls"]), "e2e_worker": spread(cnt_wrk["walls"])},
             "device_allocations_in_timed_region": {"resident": cnt_res["allocs"], "e2e": cnt_e2e["allocs"]},
             "ms_per_step_by_rank": {"resident": cnt_res["ranks_ms"], "e2e": cnt_e2e["ranks_ms"]}, "host_cores": os.cpu_count(),
             "clocks": clocks,
-            "stage_ms_per_step": stage_ms,
-            "host_wall_ms_per_step": {"index_build": sum({a: st["wall_ms_index"] for a, _, st, _ in detail}.values()),
-                                      "align_calls": S("wall_ms_align"), "of_which_delta_text": S("wall_ms_text")},
-            "post_steps_per_pair": {"what": "delta-filter -1 then delta2maf on each pair's .delta (pmn_delta_filter, pmn_delta2maf: host text in, host text out), one pair at a time, wall clock",
-                                    "delta_filter_ms": statistics.mean(p[0] for p in post), "delta2maf_ms": statistics.mean(p[1] for p in post),
-                                    "maf_bytes": statistics.mean(p[3] for p in post), "maf_gb_per_s": sum(p[3] for p in post) / 1e9 / (sum(p[1] for p in post) * 1e-3)} if post else None,
+            "stage_ms_per_step": {"what": "sum over the pairs of a step of the CUDA-event time of each stage; under_load = inside the timed steps (16 pairs share the GPU), alone = one pair at a time",
+                                  "under_load": stage_in, "alone": stage_alone},
             "roofline": dominant, "roofline_seed": roof_seed, "roofline_extend": roof_ext, "roofline_index": roof_idx,
             "counts_per_step": {"anchors": S("anchors"), "clusters": S("clusters"), "alignments": S("alignments"), "dp_cells": S("dp_cells"),
-                                "dp_jobs": S("dp_jobs"), "aligned_ref_bases": aligned_bp},
+                                "dp_jobs": S("dp_jobs"), "aligned_ref_bases": aligned_bp, "seed_lookups": lookups, "arena_bytes_max": max(d[2]["arena_bytes"] for d in alone) if alone else 0},
         }
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(args, genomes, fastas, pairs, budget_s=args.cpu_budget)
+            out["cpu_baseline"] = cpu_baseline(args, fastas, pairs, names, my_delta, budget_s=args.cpu_budget)
+            out["parity_checked_pairs_live_oracle"] = out["cpu_baseline"].pop("parity_checked_pairs")
         emit(out)
     for s in resident.values():
         s.close()
     sched.close()
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    R.close()
+
+
+# ------------------------------------------------------------------------------------------ GPU arm, C4
+
+def run_gpu_c4(args):
+    """BASELINE.json configs[3]: one synthetic 100 Mbp pair, the query positions partitioned over the ranks.  Every rank holds
+    both packed genomes and builds the index itself (all ranks at once: faster than one build plus a broadcast the others wait
+    for), rank r seeds part r, the anchor lists are all-gathered, clustering and extension run on every rank (the .delta does
+    not depend on N).  One step = index build + the pair."""
+    from paramugsy_b200 import lib, multi
+    R = Ranks(args)
+    torch, rank, world, local = R.torch, R.rank, R.world, R.local
+    n = args.genome_bp if args.genome_bp != 5_000_000 else 100_000_000
+    gs = synth.config_c4(n=n, inv_len=max(1000, n // 100))
+    ref_fa, qry_fa = synth.fasta(*gs[0]), synth.fasta(*gs[1])
+    names = [gs[0][0] + ".fa", gs[1][0] + ".fa"]
+    pin = [torch.frombuffer(bytearray(f), dtype=torch.uint8).pin_memory() for f in (ref_fa, qry_fa)]
+    host = [(t.data_ptr(), t.numel()) for t in pin]
+    ctx = lib.Context(local)
+    rs, qs = ctx.sequence(ref_fa), ctx.sequence(qry_fa)
+    dist = R.dist if world > 1 else None
+    phases = []
+
+    def step(rseq, qseq, keep=None):
+        t0 = time.perf_counter()
+        if args.replicate == "broadcast" and world > 1:
+            ix = rseq.index() if rank == 0 else rseq.index(empty=True)
+            dist.broadcast(ix.image_tensor(), src=0); torch.cuda.synchronize()
+            if rank != 0:
+                ix.adopt()
+        else:
+            ix = rseq.index()
+        t1 = time.perf_counter()
+        res = multi.align_large_pair(ix, qseq, rank, world, dist, ref_path=names[0], qry_path=names[1])
+        t2 = time.perf_counter()
+        phases.append(((t1 - t0) * 1e3, (t2 - t1) * 1e3))
+        if keep is not None:
+            keep.append((res.delta, res.stats))
+        res.close(); ix.close()
+
+    def step_e2e():
+        a = lib.Sequence.from_address(ctx, *host[0]); b = lib.Sequence.from_address(ctx, *host[1])
+        step(a, b)
+        b.close(); a.close()
+
+    first = []
+    step(rs, qs, keep=first)
+    g = golden("c4").get("c0.1-c1.1") if n == 100_000_000 else None
+    if g and sha(first[0][0]) != g["delta_sha256"]:
+        raise SystemExit(f"bench.py: PARITY FAILURE on rank {rank}: the 100 Mbp .delta differs from the oracle's digest")
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start(); sampler.wait_first_sample()
+    for _ in range(args.warmup):
+        step(rs, qs)
+    del phases[:]
+    ms_res, cnt = R.timed(lambda: step(rs, qs), args.steps, ctx.counters, lib.alloc_count)
+    ph = list(phases)
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    ms_e2e, cnt_e = R.timed(step_e2e, args.steps, ctx.counters, lib.alloc_count)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        st = first[0][1]
+        step_ms = ms_res / args.steps
+        hbm_peak, peak_src = peaks()
+        out = {"metric": METRIC, "value": args.steps / (ms_res * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+               "dtype": "int32 (2-bit packed text, u8 traceback)", "data": "synthetic",
+               "config": {"workload": f"one synthetic {n / 1e6:g} Mbp pair (BASELINE.json configs[3]), query positions partitioned over {world} rank(s); "
+                                      "index " + ("built on rank 0 and broadcast over NCCL" if args.replicate == "broadcast" and world > 1 else "built by every rank") +
+                                      ", anchors all-gathered, clustering and extension on every rank", "parity": PARITY_NOTE},
+               "parity_checked_pairs": 1 if g else 0,
+               "input_mbp_per_s": 2 * n / 1e6 / (step_ms * 1e-3), "aligned_mbp_per_s": st["aligned_ref_bases"] / 1e6 / (step_ms * 1e-3),
+               "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                       "h2d_bytes_per_step": cnt_e["h2d_bytes"] // args.steps, "d2h_bytes_per_step": cnt_e["d2h_bytes"] // args.steps},
+               "gpu_launches": cnt["launches"], "phase_ms_rank0": {"index": statistics.mean(p[0] for p in ph), "seed_gather_cluster_extend_text": statistics.mean(p[1] for p in ph)},
+               "pair_stats": {k: st[k] for k in ("anchors", "clusters", "alignments", "aligned_ref_bases", "dp_cells", "seed_lookups", "arena_bytes", "sa_rounds", "kmer_bits")},
+               "ms_per_step_by_rank": cnt["ranks_ms"], "clocks": clocks, "host_cores": os.cpu_count(),
+               "roofline": {"kernel": "index build (radix-sort passes over 100 M suffixes)", "bound": "hbm", "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src,
+                            "achieved": n * (4.25 + 16 * max(1, st["sa_rounds"]) + 12.5 + 6) / (statistics.mean(p[0] for p in ph) * 1e-3) / 1e9, "traffic": None}}
+        out["roofline"]["frac"] = out["roofline"]["achieved"] / hbm_peak
+        emit(out)
+    qs.close(); rs.close(); ctx.close()
+    R.close()
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
 
 def _cpu_one(job):
-    ref, qry = job
+    ref, qry, rname, qname = job
     from oracle import pmn_oracle
     t = time.time()
     r = pmn_oracle.Run(ref, qry, fast_chain=1)
-    d = r.delta("ref", "qry")
+    d = r.delta(rname, qname)
     rows = r.alignments()[0]
     aligned = int((rows[:, 4] - rows[:, 3] + 1).sum()) if len(rows) else 0
     cells = r.dp_cells()
     r.close()
-    return time.time() - t, len(d), aligned, cells
+    return time.time() - t, d, aligned, cells
 
 
-def cpu_sample(args, fastas, pairs, nproc, sample_bp):
-    """`nproc` pairs of the workload, each truncated to sample_bp bases, one process per pair."""
+def cpu_sample(fastas, pairs, names, nproc, sample_bp):
+    """`nproc` pairs of the workload, each cut to its first sample_bp bases (0 = as they are), one process per pair."""
     import multiprocessing as mp
     jobs = []
     for (i, j) in pairs[:nproc]:
         def cut(name, fa):
+            if not sample_bp:
+                return fa
             seq = b"".join(fa.split(b"\n")[1:])[:sample_bp]
             return synth.fasta(name, seq)
-        jobs.append((cut(*fastas[i]), cut(*fastas[j])))
+        jobs.append((cut(*fastas[i]), cut(*fastas[j]), names[i], names[j]))
     t = time.time()
     with mp.get_context("fork").Pool(nproc) as pool:
         res = pool.map(_cpu_one, jobs)
@@ -381,47 +544,75 @@ def cpu_sample(args, fastas, pairs, nproc, sample_bp):
     return wall, res, len(jobs)
 
 
-def cpu_baseline(args, genomes, fastas, pairs, budget_s=25.0):
+def cpu_baseline(args, fastas, pairs, names, gpu_delta, budget_s=30.0):
+    """The oracle on FULL-SIZE pairs of the workload, one process per pair on the host cores; every .delta it produces is
+    compared byte for byte with what the GPU produced for the same pair."""
     from oracle import pmn_oracle
     pmn_oracle.build()
     ncores = os.cpu_count() or 1
     nproc = max(1, min(ncores, len(pairs), 8))
-    # the oracle needs ~3.5 s per Mbp of pair length on one core; bound the sample to the budget
-    sample_bp = int(min(args.genome_bp, max(100_000, budget_s / 4.0 * 1e6)))
-    wall, res, n = cpu_sample(args, fastas, pairs, nproc, sample_bp)
-    # pairs/s at FULL pair size, scaled linearly in sequence length from the sample
-    scale = sample_bp / args.genome_bp
+    # the oracle needs ~4 s per Mbp of pair length on one core; a full-size pair is taken whenever it fits the budget
+    full = args.genome_bp * 4.5e-6 <= budget_s
+    sample_bp = 0 if full else int(max(100_000, budget_s / 4.5 * 1e6))
+    wall, res, n = cpu_sample(fastas, pairs, names, nproc, sample_bp)
+    checked, bad = 0, []
+    if full:
+        for (i, j), r in zip(pairs[:nproc], res):
+            if (i, j) in gpu_delta:
+                checked += 1
+                if gpu_delta[(i, j)] != r[1]:
+                    bad.append((i, j))
+    if bad:
+        raise SystemExit(f"bench.py: PARITY FAILURE: the GPU .delta of pairs {bad} differs from the oracle run in this process")
+    scale = 1.0 if full else sample_bp / args.genome_bp
     return {"value": n / wall * scale, "unit": UNIT, "cores": nproc, "kind": "port",
-            "sample": f"{n} pairs of the workload truncated to {sample_bp} bp each, {nproc} processes, one pair per process, "
-                      f"wall {wall:.1f} s; scaled linearly to {args.genome_bp} bp pairs (oracle with fast_chain=1, identical output)",
-            "aligned_mbp_per_s": sum(r[2] for r in res) / 1e6 / wall, "what": "CPU restatement oracle/pmn_oracle.c, not MUMmer"}
+            "sample": (f"{n} full-size pairs of the workload ({args.genome_bp} bp each)" if full else f"{n} pairs cut to {sample_bp} bp, scaled linearly to {args.genome_bp} bp") +
+                      f", {nproc} processes, one pair per process, wall {wall:.1f} s (oracle with fast_chain=1, identical output)",
+            "aligned_mbp_per_s": sum(r[2] for r in res) / 1e6 / wall, "what": "CPU restatement oracle/pmn_oracle.c, not MUMmer",
+            "parity_checked_pairs": checked}
 
 
 def run_reference(args):
+    """The reference's own CPU implementation of the path is MUMmer 3.20, which the reference does not vendor: the oracle port is
+    timed instead, all host cores, one process per pair (`paramugsy local -cores N`: lib/base/paramugsy.ml:54-57).  A step is
+    `cores` pairs of the workload; they are full size (no scaling, same config) whenever K + W steps of ~22 s fit four
+    minutes, and cut to a stated prefix and scaled linearly otherwise."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import pmn_oracle
     pmn_oracle.build()
     genomes, fastas, pairs = workload(args)
+    names = [g[0] + ".fa" for g in genomes]
     ncores = os.cpu_count() or 1
     nproc = max(1, min(ncores, len(pairs)))
-    sample_bp = int(min(args.genome_bp, args.ref_sample_bp))
+    sec_per_bp = 4.5e-6
+    budget = args.ref_budget
+    full_s = args.genome_bp * sec_per_bp * (args.steps + 0.1 * args.warmup)
+    if args.ref_sample_bp:
+        sample_bp = int(min(args.genome_bp, args.ref_sample_bp))
+    elif full_s <= budget:
+        sample_bp = 0
+    else:
+        sample_bp = int(max(200_000, args.genome_bp * budget / full_s))
     for _ in range(args.warmup):
-        cpu_sample(args, fastas, pairs, nproc, min(sample_bp, 100_000))
+        cpu_sample(fastas, pairs, names, nproc, min(sample_bp or args.genome_bp, 100_000))
     t0 = time.time(); n = 0
     for _ in range(args.steps):
-        wall, res, k = cpu_sample(args, fastas, pairs, nproc, sample_bp)
+        wall, res, k = cpu_sample(fastas, pairs, names, nproc, sample_bp)
         n += k
     tot = time.time() - t0
-    scale = sample_bp / args.genome_bp
+    scale = 1.0 if not sample_bp else sample_bp / args.genome_bp
     v = n / tot * scale
+    sample = (f"each step: {nproc} full-size pairs ({args.genome_bp} bp), one process per pair, no scaling" if not sample_bp else
+              f"each step: {nproc} pairs cut to their first {sample_bp} bp, one process per pair; scaled linearly to {args.genome_bp} bp pairs "
+              f"(full-size steps would take {full_s:.0f} s for this K; the full-size rate is the cpu_baseline of the B200 arm's line)")
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": tot / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64 (CPU)",
+           "ms_per_step": tot / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64 (CPU)",
            "data": "synthetic",
-           "config": {"workload": f"{args.genomes} synthetic {args.genome_bp / 1e6:g} Mbp genomes, all-vs-all {len(pairs)} pairs (BASELINE.json configs[1])"},
-           "cpu_baseline": {"value": v, "unit": UNIT, "cores": nproc, "kind": "port",
-                            "sample": f"each step: {nproc} pairs truncated to {sample_bp} bp, one process per pair; scaled linearly to full-size pairs"},
+           "config": {"workload": f"{args.genomes} synthetic {args.genome_bp / 1e6:g} Mbp genomes, all-vs-all {len(pairs)} pairs (BASELINE.json configs[1])",
+                      "same_config": not sample_bp},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": nproc, "kind": "port", "sample": sample},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "note": "the reference's own CPU path is MUMmer 3.20 (not vendored, absent here); this times the in-repo CPU restatement"}
     emit(out)
@@ -433,24 +624,30 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default="weak", choices=["weak", "strong"])
-    ap.add_argument("--workers", type=int, default=0, help="pairs in flight per GPU (pmn_sched worker threads); 0 = twice the host cores per local rank, between 8 and 16")
+    ap.add_argument("--config", default="c2", choices=["c2", "c4"])
+    ap.add_argument("--mode", default="auto", choices=["auto", "weak", "strong"], help="N > 1: strong = the 28 pairs sharded over the ranks (default), weak = every rank runs the whole batch")
+    ap.add_argument("--replicate", default="rebuild", choices=["rebuild", "broadcast"], help="sharded runs: every rank builds the indexes it needs (default) or one build per index and an NCCL broadcast")
+    ap.add_argument("--workers", type=int, default=0, help="pairs in flight per GPU (pmn_sched worker threads); 0 = as many as the host cores per local rank carry, 8 ... 24")
     ap.add_argument("--genomes", type=int, default=8)
     ap.add_argument("--genome-bp", type=int, default=5_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-budget", type=float, default=25.0)
-    ap.add_argument("--ref-sample-bp", type=int, default=1_000_000)
+    ap.add_argument("--cpu-budget", type=float, default=30.0)
+    ap.add_argument("--ref-sample-bp", type=int, default=0, help="reference arm: cut every pair to this many bases (0 = decide from the step count)")
+    ap.add_argument("--ref-budget", type=float, default=240.0, help="reference arm: seconds the timed steps may take")
     args = ap.parse_args()
     args.workers_auto = args.workers <= 0
     if args.workers <= 0:
-        # 16 pairs in flight fill one B200 (20 no longer fit its memory); a host with few cores per GPU (8 ranks on 32 cores)
-        # is better off with 8 worker threads per rank
         local_ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))
-        args.workers = max(8, min(16, 2 * (os.cpu_count() or 16) // local_ranks))
+        args.workers = max(8, min(PMN_DEFAULT_WORKERS, 2 * (os.cpu_count() or 16) // local_ranks))
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "c4":
+        run_gpu_c4(args)
     else:
         run_gpu(args)
+
+
+PMN_DEFAULT_WORKERS = 16      # pairs in flight per GPU when the host has the cores for them (see DESIGN.md §6 for the sweep)
 
 
 if __name__ == "__main__":

@@ -13,12 +13,13 @@
 //      the bucket's suffixes (binary search on packed text, 32 bases per probe), longest match
 //      = better of the two neighbours of the insertion point, unique iff the other neighbour
 //      is shorter and the LCP entry on the far side is shorter too, left-maximality
-//   4. a lane owns 32 CONSECUTIVE positions: once it knows that Q[i..] matches R[r..] for m bases,
-//      the positions behind i continue that match at r+1, r+2, ... and cannot be left-maximal
-//      there; as long as the rest of the match is longer than any repeat of its reference
-//      suffix (the index's skip table, one byte load) it is also their unique longest match,
-//      so they yield no anchor and are stepped over without any table, suffix-array or text
-//      access: 3 of 4 positions at 2 % divergence
+//   4. once a position is known to match R[r..] for m bases, the positions behind it continue
+//      that match at r+1, r+2, ... and cannot be left-maximal there; as long as the rest of the
+//      match is longer than any repeat of its reference suffix (the index's skip table, one
+//      byte load) it is also their unique longest match, so they yield no anchor and are
+//      stepped over without any table, suffix-array or text access: 3 of 4 positions at 2 %
+//      divergence.  A warp runs its 1024 positions as a work list (bitmaps of positions to look
+//      up / settled), so that the look-ups that remain are made 32 at a time
 //   5. anchors are written at the slot of their position; k_seed_gather compacts them in order
 // Output order equals the oracle's sort order, so no sort follows.
 #include <algorithm>
@@ -155,19 +156,43 @@ __device__ __forceinline__ bool seed_general(const View32 &R32, const View32 &Q3
     return true;
 }
 
-// Two passes per warp over its SEED_RUN positions.
-//   Pass 1: every lane walks its own chunk of SEED_CHUNK consecutive positions.  A look-up takes the bucket of the first K
-//   bases.  Empty: nothing matches minmatch >= K bases.  One suffix s: it is the only candidate, every other suffix shares
-//   fewer than K bases with the query and with s, so the match is unique; m = lcp(Q[g..], R[s..]) decides the anchor together
-//   with the left-maximality base, and starts a chain: position g+j continues the match at s+j with m-j bases, where it is
-//   not left-maximal (the base before it is matched); while m-j exceeds the longest repeat of the suffix at s+j that match
-//   is also the unique longest one, i.e. the position has no anchor.  With E = s+m those are exactly the positions before
-//   p_stop = E - skip[E] (pmn_index.cu: the repeat ends e(p) = p + rep(p) never decrease), so the lane jumps there with one
-//   byte load.  Two or more suffixes: the position goes on the warp's list and the chain is dropped (the next position is
-//   looked up).
-//   Pass 2, the listed positions 32 at a time: binary search and both neighbours (seed_general).
+// A warp works through its run of SEED_RUN positions as a work list, so that every step has 32 lanes doing the same thing:
+//   need / done   one bit per position: "has to be looked up" / "settled" (looked up, or stepped over)
+//   A  select     the next 32 positions of `need` (the seeds are every 32nd position)
+//   B  classify   window of the query, bucket of its first K bases.  Empty bucket (3 of 4 look-ups at 2 % divergence): nothing
+//                 matches minmatch >= K bases; the next position is needed.  Two or more suffixes: the position goes on the
+//                 multi list, the next position is needed.  One suffix: (position, slot) goes into the single buffer.
+//   C  singles    32 at a time: the suffix s is the only candidate, every other suffix shares fewer than K bases with the query
+//                 and with s, so the match is unique; L = lcp(Q[g..], R[s..]) decides the anchor together with the
+//                 left-maximality base, and settles the positions behind it: position g+j continues the match at s+j with
+//                 L-j bases, where it is not left-maximal (the base before it is matched); while L-j exceeds the longest repeat
+//                 of the suffix at s+j that match is also its unique longest one, i.e. the position has no anchor.  With
+//                 E = s+L those are exactly the positions before p_stop = E - skip[E] (pmn_index.cu: the repeat ends
+//                 e(p) = p + rep(p) never decrease): they become `done` without any table, suffix-array or text access, and
+//                 the positions from p_stop to the one behind the mismatch become `need`.
+//   D  multis     the listed positions 32 at a time: binary search and both neighbours (seed_general).
+// Every settled position settles or schedules its successor, so the run is covered when `need` and the buffers are empty.
 // Anchors are written at the slot of their position (stage is one int4 per position) with a bitmap per warp run; the gather
 // kernel compacts them in position order.
+struct SeedWarp {
+    uint32_t need[32], done[32], bits[32];
+    uint32_t s_lo[64];
+    uint16_t s_idx[64], sel[32];
+    uint16_t mlist[SEED_RUN];
+};
+
+__device__ __forceinline__ void seed_or_range(uint32_t *bm, int a, int b)      // bits [a, b) of a SEED_RUN-bit map
+{
+    if (a >= b) return;
+    const int w0 = a >> 5, w1 = (b - 1) >> 5;
+    for (int w = w0; w <= w1; w++) {
+        uint32_t m = ~0u;
+        if (w == w0) m &= ~0u << (a & 31);
+        if (w == w1) m &= ~0u >> (31 - ((b - 1) & 31));
+        atomicOr(bm + w, m);
+    }
+}
+
 __global__ void __launch_bounds__(SEED_THREADS) k_seed(PackedView R, const uint32_t *__restrict__ sa, const int32_t *__restrict__ lcp,
                                                       const uint32_t *__restrict__ table, const uint8_t *__restrict__ skip, int K, PackedView QF, PackedView QR,
                                                       const SeedSection *__restrict__ secs, int nsec, int minmatch,
@@ -177,8 +202,7 @@ __global__ void __launch_bounds__(SEED_THREADS) k_seed(PackedView R, const uint3
     __shared__ __align__(16) uint64_t s_w[SEED_WORDS];
     __shared__ __align__(16) uint32_t s_x[SEED_WORDS];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ uint16_t s_list[SEED_WARPS][SEED_RUN];
-    __shared__ uint32_t s_bits[SEED_WARPS][SEED_CHUNK];
+    __shared__ SeedWarp s_warp[SEED_WARPS];
     if (threadIdx.x == 0) mbar_init(&s_bar, 1);
     __syncthreads();
     uint32_t phase = 0;
@@ -213,7 +237,7 @@ __global__ void __launch_bounds__(SEED_THREADS) k_seed(PackedView R, const uint3
     const size_t run = (size_t)ltile * SEED_WARPS + warp;
     int4 *wstage = stage + run * SEED_RUN;
     const int64_t woff = off0 + warp * SEED_RUN;
-    uint32_t nlist = 0;
+    SeedWarp &W = s_warp[warp];
     // the first window of position woff + idx, from the staged tile
     auto window = [&](int idx, uint32_t &g, uint64_t &qw, int &vq) {
         g = (uint32_t)(sec.start + woff + idx);
@@ -223,68 +247,101 @@ __global__ void __launch_bounds__(SEED_THREADS) k_seed(PackedView R, const uint3
         if (Q.has_x) { const uint32_t xw = __funnelshift_l(s_x[k + 1], s_x[k], sh); vq = xw ? __clz((int)xw) : 32; }
         else { const uint32_t r = Q32.n - g; vq = r < 32u ? (int)r : 32; }
     };
-    // ---- pass 1: lane l walks positions [l * SEED_CHUNK, l * SEED_CHUNK + lim) of the run
-    int lim;
-    { const int64_t left = sec.npos - (woff + (int64_t)lane * SEED_CHUNK); lim = left <= 0 ? 0 : left < SEED_CHUNK ? (int)left : SEED_CHUNK; }
-    int k = 0;
-    uint32_t mybits = 0;
-    while (__any_sync(0xffffffffu, k < lim)) {
-        const bool act = k < lim;
-        bool later = false;
-        const int idx = lane * SEED_CHUNK + k;
+    int run_lim;        // positions of the run that exist
+    { const int64_t left = sec.npos - woff; run_lim = left <= 0 ? 0 : left < SEED_RUN ? (int)left : SEED_RUN; }
+    const uint32_t vmask = run_lim >= (lane + 1) * 32 ? ~0u : run_lim <= lane * 32 ? 0u : (1u << (run_lim - lane * 32)) - 1u;
+    W.need[lane] = vmask & 1u; W.done[lane] = 0; W.bits[lane] = 0;       // the seeds: every 32nd position
+    uint32_t nsingle = 0, nmulti = 0;                                     // the same in every lane
+    __syncwarp();
+
+    // 32 buffered one-suffix positions (the last n of the buffer)
+    auto singles = [&](uint32_t n) {
+        nsingle -= n;
+        if ((uint32_t)lane < n) {
+            const int idx = W.s_idx[nsingle + lane];
+            const uint32_t s = __ldg(sa + W.s_lo[nsingle + lane]);
+            uint32_t g; uint64_t qw; int vq;
+            window(idx, g, qw, vq);
+            const uint32_t L = lcp32(Q32, g, R32, s);
+            if (L >= (uint32_t)minmatch) {
+                const int qb = base32(Q32, g - 1), rb = base32(R32, s - 1);
+                if (!(qb == rb && qb < 4)) { atomicOr(&W.bits[idx >> 5], 1u << (idx & 31)); wstage[idx] = make_int4((int)(s + 1), (int)(woff + idx + 1), (int)L, sec.tag); }
+            }
+            int step = 1;                                       // positions this look-up settles, itself included
+            if (L >= 2u) {
+                const uint32_t E = s + L;
+                const uint32_t d = __ldg(skip + E);
+                if (d < 255u) { const uint32_t p_stop = E - d; if (p_stop > s + 1u) step = (int)(p_stop - s); }
+            }
+            const int64_t upto = (int64_t)idx + (int64_t)L + 2;                     // one behind the position of the mismatch
+            const int c1 = idx + step < run_lim ? idx + step : run_lim;
+            const int n1 = upto < run_lim ? (int)upto : run_lim;
+            seed_or_range(W.done, idx + 1, c1);
+            seed_or_range(W.need, idx + step, n1);
+        }
+        __syncwarp();
+    };
+
+    for (;;) {
+        // ---- A. what is waiting
+        const uint32_t w = W.need[lane] & ~W.done[lane] & vmask;
+        const int pc = __popc(w);
+        int pre = pc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += t; }
+        const int total = __shfl_sync(0xffffffffu, pre, 31);
+        pre -= pc;
+        if (nsingle >= 32u || (nsingle > 0u && total < 32)) { singles(nsingle < 32u ? nsingle : 32u); continue; }
+        if (total == 0) break;
+        {   // every lane hands the first positions of its word to the selection, in position order
+            uint32_t take = 0, ww = w; int r = pre;
+            while (ww && r < 32) { const int b = __ffs((int)ww) - 1; ww &= ww - 1u; W.sel[r] = (uint16_t)(lane * 32 + b); take |= 1u << b; r++; }
+            W.need[lane] = w & ~take;
+            W.done[lane] |= take;
+        }
+        __syncwarp();
+        const int T = total < 32 ? total : 32;
+        // ---- B. classify
+        const bool act = lane < T;
+        const int idx = act ? (int)W.sel[lane] : 0;
+        int cls = 0; uint32_t lo = 0;
         if (act) {
             uint32_t g; uint64_t qw; int vq;
             window(idx, g, qw, vq);
-            int step = 1;                                       // positions this look-up settles, itself included
             if (vq >= first_need) {
-                my_lookups++;
-                if (!use_table) later = true;
+                if (!use_table) cls = 2;
                 else {
                     const uint32_t km = (uint32_t)(qw >> (64 - 2 * K));
-                    const uint32_t lo = __ldg(table + km), hi = __ldg(table + km + 1);
-                    if (hi - lo == 1u) {
-                        const uint32_t s = __ldg(sa + lo);
-                        const uint32_t L = lcp32(Q32, g, R32, s);
-                        if (L >= (uint32_t)minmatch) {
-                            const int qb = base32(Q32, g - 1), rb = base32(R32, s - 1);
-                            if (!(qb == rb && qb < 4)) { mybits |= 1u << k; wstage[idx] = make_int4((int)(s + 1), (int)(woff + idx + 1), (int)L, sec.tag); }
-                        }
-                        if (L >= 2u) {
-                            // the positions behind this one continue the match at s+1, s+2, ...: those before p_stop have it as their
-                            // unique longest match and are not left-maximal in it
-                            const uint32_t E = s + L;
-                            const uint32_t d = __ldg(skip + E);
-                            if (d < 255u) { const uint32_t p_stop = E - d; if (p_stop > s + 1u) step = (int)(p_stop - s); }
-                        }
-                    } else if (hi > lo) later = true;
+                    lo = __ldg(table + km);
+                    const uint32_t hi = __ldg(table + km + 1);
+                    cls = hi - lo == 1u ? 1 : hi > lo ? 2 : 0;
                 }
             }
-            k += step;
+            if (cls != 1 && idx + 1 < run_lim) atomicOr(&W.need[(idx + 1) >> 5], 1u << ((idx + 1) & 31));
         }
-        const unsigned bl = __ballot_sync(0xffffffffu, later);
-        if (later) s_list[warp][nlist + __popc(bl & lt)] = (uint16_t)idx;
-        nlist += __popc(bl);
+        const unsigned b1 = __ballot_sync(0xffffffffu, cls == 1), b2 = __ballot_sync(0xffffffffu, cls == 2);
+        if (cls == 1) { const uint32_t at = nsingle + __popc(b1 & lt); W.s_idx[at] = (uint16_t)idx; W.s_lo[at] = lo; }
+        if (cls == 2) W.mlist[nmulti + __popc(b2 & lt)] = (uint16_t)idx;
+        nsingle += __popc(b1); nmulti += __popc(b2);
+        if (lane == 0) my_lookups += (unsigned)T;
+        __syncwarp();
     }
-    s_bits[warp][lane] = mybits;
-    __syncwarp();
-    // ---- pass 2: the listed positions, densely
-    for (uint32_t c = 0; c < nlist; c += 32) {
-        bool found = false; int idx = 0;
-        if (c + lane < nlist) {
-            idx = s_list[warp][c + lane];
+    // ---- D. the multi list, densely
+    for (uint32_t c = 0; c < nmulti; c += 32) {
+        if (c + lane < nmulti) {
+            const int idx = W.mlist[c + lane];
             uint32_t g; uint64_t qw; int vq;
             window(idx, g, qw, vq);
             uint32_t lo = 0, hi = R32.n;
             if (use_table) { const uint32_t km = (uint32_t)(qw >> (64 - 2 * K)); lo = __ldg(table + km); hi = __ldg(table + km + 1); }
             uint32_t r, L;
             if (seed_general(R32, Q32, sa, lcp, lo, hi, g, qw, vq, minmatch, &r, &L)) {
-                found = true; wstage[idx] = make_int4((int)(r + 1), (int)(woff + idx + 1), (int)L, sec.tag);
+                atomicOr(&W.bits[idx >> 5], 1u << (idx & 31)); wstage[idx] = make_int4((int)(r + 1), (int)(woff + idx + 1), (int)L, sec.tag);
             }
         }
-        if (found) atomicOr(&s_bits[warp][idx >> 5], 1u << (idx & 31));
     }
     __syncwarp();
-    const uint32_t word = s_bits[warp][lane];
+    const uint32_t word = W.bits[lane];
     run_bits[run * SEED_CHUNK + lane] = word;
     uint32_t wcount = __popc(word);
 #pragma unroll
@@ -292,11 +349,7 @@ __global__ void __launch_bounds__(SEED_THREADS) k_seed(PackedView R, const uint3
     if (lane == 0) tile_cnt[run] = wcount;
     __syncthreads();            // the staged tile is free for the next copy
     }
-    if (lookups) {              // how many positions were looked up (the rest were stepped over): bench.py reports the share
-#pragma unroll
-        for (int o = 16; o; o >>= 1) my_lookups += __shfl_xor_sync(0xffffffffu, my_lookups, o);
-        if ((threadIdx.x & 31) == 0 && my_lookups) atomicAdd(lookups, (unsigned long long)my_lookups);
-    }
+    if (lookups && (threadIdx.x & 31) == 0 && my_lookups) atomicAdd(lookups, (unsigned long long)my_lookups);      // how many positions were looked up (the rest were stepped over)
 }
 
 // gather the per-run anchors into one contiguous, ordered anchor array

@@ -393,6 +393,15 @@ class Sequence:
         else:
             _check(lib().pmn_seq_from_file(ctx.h, os.fsencode(path), C.byref(self.h)))
 
+    @classmethod
+    def from_address(cls, ctx, address: int, nbytes: int):
+        """FASTA text the caller keeps in (pinned) host memory, given by address and length."""
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        _check(lib().pmn_seq_from_fasta(ctx.h, C.cast(C.c_void_p(address), C.c_char_p), nbytes, C.byref(self.h)))
+        return self
+
     @property
     def bases(self):
         return lib().pmn_seq_bases(self.h)
@@ -521,10 +530,14 @@ class Result:
         return C.string_at(p, n.value) if n.value else b""
 
     @property
-    def stats(self):
+    def stats_raw(self) -> Stats:
         s = Stats()
         lib().pmn_result_stats(self.h, C.byref(s))
-        return s.as_dict()
+        return s
+
+    @property
+    def stats(self):
+        return self.stats_raw.as_dict()
 
     def anchors(self):
         n = lib().pmn_result_n_anchors(self.h)

@@ -15,6 +15,20 @@ for s in $steps; do
     ncu_launches) timeout 900 ncu --metrics gpu__time_duration.sum,sm__cycles_active.avg,smsp__inst_executed.sum --clock-control none --csv --log-file gpurun_out/${tag}_launches_bench.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/${tag}_ncu_launches.log 2>&1; echo "ncu launches rc=$?" ;;
     ncu_pair) timeout 900 ncu --metrics gpu__time_duration.sum,sm__cycles_active.avg,smsp__inst_executed.sum --clock-control none --csv --log-file gpurun_out/launches_pair.csv python tools/profile_pair.py 5000000 2 > gpurun_out/${tag}_ncu_pair.log 2>&1; echo "ncu pair rc=$?"; cp gpurun_out/launches_pair.csv gpurun_out/${tag}_launches_pair.csv ;;
     ncu_full) timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:k_ex_wave|k_ex_stitch|k_seed$|k_cl_chains|pmn_rs_scatter|pmn_scan_onepass" -c 14 -o gpurun_out/pair_full -f python tools/profile_pair.py 5000000 1 > gpurun_out/${tag}_ncu_full.log 2>&1; echo "ncu full rc=$?" ;;
+    sweep)   # tools/sweep.txt: one run per line, "<name> [VAR=value ...] -- <bench.py arguments>"
+             while read -r name rest; do
+               [ -z "$name" ] && continue; case $name in \#*) continue;; esac
+               envs=${rest%%--*}; args=${rest#*--}
+               env $envs timeout 600 python bench.py --no-cpu-baseline $args > gpurun_out/${tag}_sweep_${name}.json 2> gpurun_out/${tag}_sweep_${name}.err
+               python - "$name" gpurun_out/${tag}_sweep_${name}.json <<'P'
+import json, sys
+try:
+    d = json.loads(open(sys.argv[2]).read().strip().splitlines()[-1])
+    print(f"{sys.argv[1]:24s} value {d['value']:8.1f}  e2e {d['e2e']['value']:8.1f}  worker {(d.get('e2e_worker') or {}).get('value', 0):8.1f}  ms/step {d['ms_per_step']:.2f}  W {d['config']['workers_per_gpu']}")
+except Exception as e:
+    print(f"{sys.argv[1]:24s} FAILED {e}")
+P
+             done < tools/sweep.txt ;;
     *) echo "unknown step $s" ;;
   esac
 done
