@@ -333,9 +333,10 @@ def run_gpu(args):
             traffic, traffic_src = {}, None
         # ---- seeding: bytes the kernel's own algorithm needs, per launch
         #   per looked-up position: K-mer table entry pair 8 B + suffix-array entry 4 B + one 8-byte reference word + 1 B of the skip table;
-        #   per position (looked up or stepped over): 0.375 B of packed query (text + mask bits); 16 B per anchor written.
+        #   per block probe: one 4-byte word of the presence bitmap;
+        #   per position (looked up, settled by a probe or stepped over): 0.375 B of packed query (text + mask bits); 16 B per anchor written.
         n_seed = max(1, len(alone))
-        b_own = sum(st["seed_lookups"] * 21.0 + 2 * st["qry_bases"] * 0.375 + 16 * st["anchors"] for _, _, st, _ in alone)
+        b_own = sum(st["seed_lookups"] * 21.0 + st["seed_probes"] * 4.0 + 2 * st["qry_bases"] * 0.375 + 16 * st["anchors"] for _, _, st, _ in alone)
         b_model = sum(2 * st["qry_bases"] * (12 * math.ceil(math.log2(max(2, st["ref_bases"]))) + 8.25) + 12 * st["anchors"] for _, _, st, _ in alone)
         seed_ms_alone, seed_ms_in = S("ms_seed_kernel") / n_seed, S_in("ms_seed_kernel") / n_in
         lookups = sum(st["seed_lookups"] for _, _, st, _ in alone); positions = sum(2 * st["qry_bases"] for _, _, st, _ in alone)
@@ -347,7 +348,7 @@ def run_gpu(args):
                      "achieved_alone": b_own / n_seed / (seed_ms_alone * 1e-3) / 1e9 if seed_ms_alone else None,
                      "traffic": seed_traffic, "traffic_source": traffic_src,
                      "dram_gbs_alone": seed_traffic / (seed_ms_alone * 1e-3) / 1e9 if seed_traffic and seed_ms_alone else None,
-                     "positions_looked_up": lookups / max(1, positions),
+                     "positions_looked_up": lookups / max(1, positions), "block_probes_per_position": sum(st["seed_probes"] for _, _, st, _ in alone) / max(1, positions),
                      "survey_model": {"what": "SURVEY.md §8d counts a full binary search per position (12 B x log2 n + 8.25): work the kernel no longer does; "
                                               "equivalent-work rate only, NOT a roofline fraction", "bytes_per_launch": b_model / n_seed,
                                       "equivalent_gbs_alone": b_model / n_seed / (seed_ms_alone * 1e-3) / 1e9 if seed_ms_alone else None},

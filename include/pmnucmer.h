@@ -74,6 +74,7 @@ typedef struct pmn_stats {
     float   wall_ms_post;        /* host wall clock of the two post-steps (pmn_opts.post) */
     int64_t seed_lookups;        /* query positions the seeding kernel looked up in the index; the rest were stepped over */
     int64_t arena_bytes;         /* traceback arena the extension used for this pair */
+    int64_t seed_probes;         /* bit probes of the presence bitmap (one per block of minmatch - P + 1 query positions) */
 } pmn_stats;
 
 void pmn_default_opts(pmn_opts *o);

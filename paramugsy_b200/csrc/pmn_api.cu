@@ -546,6 +546,7 @@ static int align_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *qry, const
     PMN_CUDA_OK(cudaEventRecord(c->ev[3], st));
     r->stats.anchors = nanc;
     r->stats.seed_lookups = (given_anchors || n_given == 0) ? 0 : S.seed_lookups;
+    r->stats.seed_probes = (given_anchors || n_given == 0) ? 0 : S.seed_probes;
     if (o.keep_stages && nanc > 0) {
         r->anchors.resize((size_t)nanc * 4);
         PMN_D2H(c, r->anchors.data(), S.anchors.p, 16 * (size_t)nanc);

@@ -29,9 +29,10 @@ struct pmn_index {
     const pmn_seq *seq = nullptr;       // borrowed: the caller keeps the sequence alive
     int64_t n = 0;
     // one contiguous image in HBM (so that it can be replicated by a single NCCL broadcast):
-    //   [0,256) header {magic, n, K, rounds} | int32 SA[n] | int32 LCP[n] | uint32 table[4^K + 1] | uint8 skip[n + 1], each 256-byte aligned
+    //   [0,256) header {magic, n, K, rounds} | int32 SA[n] | int32 LCP[n] | uint32 table[4^K + 1] | uint8 skip[n + 1] | uint32 present[4^P / 32],
+    //   each 256-byte aligned
     DevBuf blob;
-    size_t off_sa = 0, off_lcp = 0, off_table = 0, off_skip = 0, blob_bytes = 0;
+    size_t off_sa = 0, off_lcp = 0, off_table = 0, off_skip = 0, off_present = 0, blob_bytes = 0;
     uint32_t *sa() const { return (uint32_t *)((char *)blob.p + off_sa); }
     int32_t *lcp() const { return (int32_t *)((char *)blob.p + off_lcp); }
     uint32_t *table() const { return (uint32_t *)((char *)blob.p + off_table); }
@@ -39,6 +40,11 @@ struct pmn_index {
     // suffix shares E - p or more bases with another suffix (255: further back than 254).  A query position whose match ends at E
     // and starts before that p is matched nowhere else as long: the seeding kernel steps over those positions (pmn_seed.cu).
     uint8_t *skip() const { return (uint8_t *)blob.p + off_skip; }
+    // present: one bit per P-mer, set for (at least) every P-mer that occurs in the reference.  A match of minmatch bases that starts
+    // at any of minmatch - P + 1 consecutive query positions contains the P-mer at the last of them: when that P-mer is not in
+    // the reference none of those positions has an anchor, and the seeding kernel settles them with one bit probe.
+    uint32_t *present() const { return (uint32_t *)((char *)blob.p + off_present); }
+    int P = 0;
     int K = 0;
     int rounds = 0;                     // prefix-doubling rounds after the 16-mer pass
     float ms_build = 0, wall_ms_build = 0;
@@ -131,7 +137,7 @@ int pmn_fasta_to_device(pmn_ctx *c, pmn_seq *s, const char *txt, size_t nb, cons
 int pmn_index_build_impl(pmn_ctx *c, const pmn_seq *ref, pmn_index *ix);
 int pmn_index_layout(pmn_ctx *c, const pmn_seq *ref, pmn_index *ix);   // sizes the image for ref and takes it from the pool
 struct PmnIndexHeader { uint64_t magic; int64_t n; int32_t K, rounds; };
-#define PMN_INDEX_MAGIC 0x32584449304e4d50ull   /* "PMN0IDX2" */
+#define PMN_INDEX_MAGIC 0x33584449304e4d50ull   /* "PMN0IDX3" */
 int pmn_seed_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_opts *o, int64_t *n_anchors, int part = 0, int nparts = 1);
 int pmn_cluster_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_opts *o, int64_t n_anchors);
 int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_opts *o, pmn_result *res);

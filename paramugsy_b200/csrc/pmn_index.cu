@@ -371,6 +371,19 @@ __global__ void __launch_bounds__(256) k_bucket_fill(const KeyT *__restrict__ ke
     for (int64_t k = prev + 1; k <= cur; k++) table[k] = (uint32_t)p;
 }
 
+// presence bitmap: the top 2P bits of every sorted key (END / X padding only ever adds P-mers, which is harmless: a set bit
+// only means "look the position up"); one atomic per distinct P-mer
+template <class KeyT>
+__global__ void __launch_bounds__(256) k_present_fill(const KeyT *__restrict__ keys, int64_t n, int P, uint32_t *__restrict__ present)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    auto pk = [&](int64_t q) -> uint32_t { const uint32_t hi = sizeof(KeyT) == 4 ? (uint32_t)keys[q] : (uint32_t)((uint64_t)keys[q] >> 6); return P == 16 ? hi : hi >> (32 - 2 * P); };
+    const uint32_t k = pk(p);
+    if (p > 0 && pk(p - 1) == k) return;
+    atomicOr(present + (k >> 5), 1u << (k & 31));
+}
+
 // ------------------------------------------------------------------------------------ driver
 
 static inline int bits_for(int64_t v) { int b = 1; while ((1ll << b) <= v) b++; return b; }
@@ -383,12 +396,21 @@ static inline int index_K(int64_t n)
     return K;
 }
 
+// P of the presence bitmap: 4^P bits for n suffixes keep it under 1/32 full on random sequence (14 for a 5 Mbp genome: 32 MB,
+// 16 from 34 Mbp on: 512 MB)
+static inline int index_P(int64_t n)
+{
+    int P = 8; while (P < 16 && (1ll << (2 * P)) < 32 * n) P++;
+    return P;
+}
+
 static inline size_t up256(size_t x) { return (x + 255) / 256 * 256; }
 
 extern "C" size_t pmn_index_image_bytes(int64_t n_bases)
 {
     if (n_bases < 1) return 0;
-    return 256 + 2 * up256(4 * (size_t)n_bases) + up256(4 * (((size_t)1 << (2 * index_K(n_bases))) + 1)) + up256((size_t)n_bases + 1);
+    return 256 + 2 * up256(4 * (size_t)n_bases) + up256(4 * (((size_t)1 << (2 * index_K(n_bases))) + 1)) + up256((size_t)n_bases + 1) +
+           up256(((size_t)1 << (2 * index_P(n_bases))) / 8);
 }
 
 int pmn_index_layout(pmn_ctx *c, const pmn_seq *ref, pmn_index *ix)
@@ -400,6 +422,8 @@ int pmn_index_layout(pmn_ctx *c, const pmn_seq *ref, pmn_index *ix)
     ix->ctx = c; ix->seq = ref; ix->n = n; ix->K = index_K(n);
     ix->off_sa = 256; ix->off_lcp = ix->off_sa + up256(4 * (size_t)n); ix->off_table = ix->off_lcp + up256(4 * (size_t)n);
     ix->off_skip = ix->off_table + up256(4 * (((size_t)1 << (2 * ix->K)) + 1));
+    ix->P = index_P(n);
+    ix->off_present = ix->off_skip + up256((size_t)n + 1);
     ix->blob_bytes = pmn_index_image_bytes(n);
     return pmn_pool_get(c, ix->blob, ix->blob_bytes) ? -3 : 0;
 }
@@ -444,14 +468,17 @@ int pmn_index_build_impl(pmn_ctx *c, const pmn_seq *ref, pmn_index *ix)
     const int K = ix->K;
     uint8_t *unres = S.codes.as<uint8_t>();
     PMN_CUDA_OK(cudaMemsetAsync(unres, 0, (size_t)n + 32, st));
+    PMN_CUDA_OK(cudaMemsetAsync(ix->present(), 0, ((size_t)1 << (2 * ix->P)) / 8, st));
     if (class_first) {
         k_bucket_fill<uint32_t><<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>((const uint32_t *)skeys, n, K, ix->table());
         k_lcp_keys<uint32_t><<<gn, 256, 0, st>>>((const uint32_t *)skeys, svals, n, ix->lcp(), unres);
+        k_present_fill<uint32_t><<<gn, 256, 0, st>>>((const uint32_t *)skeys, n, ix->P, ix->present());
     } else {
         k_bucket_fill<uint64_t><<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>((const uint64_t *)skeys, n, K, ix->table());
         k_lcp_keys<uint64_t><<<gn, 256, 0, st>>>((const uint64_t *)skeys, svals, n, ix->lcp(), unres);
+        k_present_fill<uint64_t><<<gn, 256, 0, st>>>((const uint64_t *)skeys, n, ix->P, ix->present());
     }
-    launches += 2;
+    launches += 3;
 
     // 2. groups of equal 16-mers -> ranks; slots that still share a group go on the work list
     int32_t *gs = S.gs.as<int32_t>(), *rank = S.rank.as<int32_t>(), *gsn = S.gsn.as<int32_t>();

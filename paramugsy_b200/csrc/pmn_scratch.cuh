@@ -31,7 +31,7 @@ struct Scratch {
     // the diagonal-difference limits of the clustering stage as they are in cl_g, and the options they were computed from
     std::vector<int32_t> lim_host; int lim_maxgap = -1, lim_diagdiff = -1; double lim_diagfactor = -1.0;
     // host-side counts handed from one stage to the next (one pair in flight per context)
-    int64_t n_anchors = 0, n_clusters = 0, n_cl_matches = 0, seed_lookups = 0;
+    int64_t n_anchors = 0, n_clusters = 0, n_cl_matches = 0, seed_lookups = 0, seed_probes = 0;
     // traceback arena of the extension: sized from what pairs have needed so far (grown and the extension re-run when a pair needs more)
     size_t arena_cap = 0;
     bool arena_retry = false;          // set by the extension when it grew the arena after running out: run it again

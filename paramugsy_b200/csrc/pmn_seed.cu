@@ -158,7 +158,10 @@ __device__ __forceinline__ bool seed_general(const View32 &R32, const View32 &Q3
 
 // A warp works through its run of SEED_RUN positions as a work list, so that every step has 32 lanes doing the same thing:
 //   need / done   one bit per position: "has to be looked up" / "settled" (looked up, or stepped over)
-//   A  select     the next 32 positions of `need` (the seeds are every 32nd position)
+//   0  blocks     one bit probe per block of minmatch - P + 1 positions settles the block when the P-mer at its last position is not in
+//                 the reference (presence bitmap of the index): most of the strand without homology, and the positions in front of a
+//                 mismatch.  The seeds are every 32nd position and every position behind a settled one.
+//   A  select     the next 32 positions of `need`
 //   B  classify   window of the query, bucket of its first K bases.  Empty bucket (3 of 4 look-ups at 2 % divergence): nothing
 //                 matches minmatch >= K bases; the next position is needed.  Two or more suffixes: the position goes on the
 //                 multi list, the next position is needed.  One suffix: (position, slot) goes into the single buffer.
@@ -194,7 +197,8 @@ __device__ __forceinline__ void seed_or_range(uint32_t *bm, int a, int b)      /
 }
 
 __global__ void __launch_bounds__(SEED_THREADS) k_seed(PackedView R, const uint32_t *__restrict__ sa, const int32_t *__restrict__ lcp,
-                                                      const uint32_t *__restrict__ table, const uint8_t *__restrict__ skip, int K, PackedView QF, PackedView QR,
+                                                      const uint32_t *__restrict__ table, const uint8_t *__restrict__ skip, const uint32_t *__restrict__ present, int P, int K,
+                                                      PackedView QF, PackedView QR,
                                                       const SeedSection *__restrict__ secs, int nsec, int minmatch,
                                                       int4 *__restrict__ stage, uint32_t *__restrict__ run_bits, uint32_t *__restrict__ tile_cnt, unsigned tile_base, unsigned ntiles,
                                                       unsigned long long *__restrict__ lookups)
@@ -206,7 +210,7 @@ __global__ void __launch_bounds__(SEED_THREADS) k_seed(PackedView R, const uint3
     if (threadIdx.x == 0) mbar_init(&s_bar, 1);
     __syncthreads();
     uint32_t phase = 0;
-    unsigned my_lookups = 0;
+    unsigned my_lookups = 0, my_probes_total = 0;
     // a block walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... (one tile per block unless the host caps the grid)
     for (unsigned ltile = blockIdx.x; ltile < ntiles; ltile += gridDim.x, phase ^= 1u) {
     const int64_t tile = (int64_t)ltile + tile_base;          // ltile is local to the launched tile range
@@ -250,8 +254,36 @@ __global__ void __launch_bounds__(SEED_THREADS) k_seed(PackedView R, const uint3
     int run_lim;        // positions of the run that exist
     { const int64_t left = sec.npos - woff; run_lim = left <= 0 ? 0 : left < SEED_RUN ? (int)left : SEED_RUN; }
     const uint32_t vmask = run_lim >= (lane + 1) * 32 ? ~0u : run_lim <= lane * 32 ? 0u : (1u << (run_lim - lane * 32)) - 1u;
-    W.need[lane] = vmask & 1u; W.done[lane] = 0; W.bits[lane] = 0;       // the seeds: every 32nd position
+    W.done[lane] = 0; W.bits[lane] = 0;
     uint32_t nsingle = 0, nmulti = 0;                                     // the same in every lane
+    __syncwarp();
+    // ---- 0. blocks of B = minmatch - P + 1 positions: a match of minmatch bases that starts anywhere in a block contains the P-mer at
+    // the block's last position; when the reference does not hold that P-mer (or it is cut short by an X or the end of the
+    // record) the whole block is settled
+    const int Bk = minmatch - P + 1;
+    unsigned my_probes = 0;
+    if (Bk >= 2 && run_lim > 0) {
+        const int nblk = (run_lim + Bk - 1) / Bk;
+        for (int base = 0; base < nblk; base += 32) {
+            const int blk = base + lane;
+            if (blk < nblk) {
+                const int b0 = blk * Bk, b1 = b0 + Bk < run_lim ? b0 + Bk : run_lim;
+                uint32_t g; uint64_t qw; int vq;
+                window(b1 - 1, g, qw, vq);
+                bool here = false;
+                if (vq >= P) { const uint32_t pk = (uint32_t)(qw >> (64 - 2 * P)); here = (__ldg(present + (pk >> 5)) >> (pk & 31)) & 1u; }
+                if (!here) seed_or_range(W.done, b0, b1);
+            }
+        }
+        if (lane == 0) my_probes = (unsigned)nblk;
+        __syncwarp();
+    }
+    my_probes_total += my_probes;
+    {   // the seeds: every 32nd position, and every position behind a settled one
+        const uint32_t dw = W.done[lane];
+        const uint32_t carry = lane ? W.done[lane - 1] >> 31 : 0u;
+        W.need[lane] = (1u | ((dw << 1) | carry)) & ~dw & vmask;
+    }
     __syncwarp();
 
     // 32 buffered one-suffix positions (the last n of the buffer)
@@ -350,6 +382,7 @@ __global__ void __launch_bounds__(SEED_THREADS) k_seed(PackedView R, const uint3
     __syncthreads();            // the staged tile is free for the next copy
     }
     if (lookups && (threadIdx.x & 31) == 0 && my_lookups) atomicAdd(lookups, (unsigned long long)my_lookups);      // how many positions were looked up (the rest were stepped over)
+    if (lookups && (threadIdx.x & 31) == 0 && my_probes_total) atomicAdd(lookups + 1, (unsigned long long)my_probes_total);
 }
 
 // gather the per-run anchors into one contiguous, ordered anchor array
@@ -406,13 +439,13 @@ int pmn_seed_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_o
         S.scan_tmp.ensure(8 * pmn_scan_scratch_elems(runs)) || S.ensure_pinned(64) || S.cl_counters.ensure(64)) return -3;
     PMN_H2D(c, S.sections.p, secs.data(), sizeof(SeedSection) * secs.size());
     unsigned long long *lookups = (unsigned long long *)((char *)S.cl_counters.p + 32);      // the clustering stage uses the first 8 bytes, later
-    PMN_CUDA_OK(cudaMemsetAsync(lookups, 0, 8, st));
+    PMN_CUDA_OK(cudaMemsetAsync(lookups, 0, 16, st));
     PMN_CUDA_OK(cudaEventRecord(c->ev[6], st));
     // one block per tile by default (the hardware deals tiles to SMs as they free up); PMN_SEED_BPS = k caps the grid at k
     // blocks per SM that stride over the tiles (experiment: leave thread slots to the kernels of other pairs)
     static const int seed_bps = getenv("PMN_SEED_BPS") ? atoi(getenv("PMN_SEED_BPS")) : 0;
     const unsigned seed_grid = seed_bps > 0 ? (unsigned)std::min<int64_t>(tiles, (int64_t)c->sm_count * seed_bps) : (unsigned)tiles;
-    k_seed<<<seed_grid, SEED_THREADS, 0, st>>>(ix->seq->fwd(), ix->sa(), ix->lcp(), ix->table(), ix->skip(), ix->K,
+    k_seed<<<seed_grid, SEED_THREADS, 0, st>>>(ix->seq->fwd(), ix->sa(), ix->lcp(), ix->table(), ix->skip(), ix->present(), ix->P, ix->K,
                                                      q->fwd(), q->rev(), S.sections.as<SeedSection>(), (int)secs.size(), o->minmatch,
                                                      S.stage.as<int4>(), S.seed_bits.as<uint32_t>(), S.tile_cnt.as<uint32_t>(), (unsigned)t_lo, (unsigned)tiles, lookups);
     PMN_CUDA_OK(cudaEventRecord(c->ev[7], st));
@@ -420,11 +453,11 @@ int pmn_seed_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn_o
     uint32_t *tail = (uint32_t *)S.pinned;
     PMN_D2H(c, tail, S.tile_off.as<uint32_t>() + (runs - 1), 4);
     PMN_D2H(c, tail + 1, S.tile_cnt.as<uint32_t>() + (runs - 1), 4);
-    PMN_D2H(c, tail + 2, lookups, 8);
+    PMN_D2H(c, tail + 2, lookups, 16);
     PMN_CUDA_OK(cudaStreamSynchronize(st));   // the host sizes the clustering stage from the anchor count
     c->syncs++;
     int64_t total = (int64_t)tail[0] + tail[1];
-    { unsigned long long lk; memcpy(&lk, tail + 2, 8); S.seed_lookups = (int64_t)lk; }
+    { unsigned long long lk[2]; memcpy(lk, tail + 2, 16); S.seed_lookups = (int64_t)lk[0]; S.seed_probes = (int64_t)lk[1]; }
     c->launches += 4;
     if (total > 0) {
         if (S.anchors.ensure(sizeof(int4) * (size_t)total)) return -3;

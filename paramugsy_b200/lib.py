@@ -46,7 +46,7 @@ class Stats(C.Structure):
                 ("ms_wave1", C.c_float), ("ms_stitch", C.c_float), ("kernel_launches", C.c_int64),
                 ("wave1_cells", C.c_int64), ("wall_ms_index", C.c_float), ("wall_ms_align", C.c_float),
                 ("wall_ms_text", C.c_float), ("wall_ms_post", C.c_float),
-                ("seed_lookups", C.c_int64), ("arena_bytes", C.c_int64)]
+                ("seed_lookups", C.c_int64), ("arena_bytes", C.c_int64), ("seed_probes", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
