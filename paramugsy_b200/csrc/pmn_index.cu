@@ -346,11 +346,11 @@ __global__ void __launch_bounds__(256) k_skip_e(const int32_t *__restrict__ rank
 }
 __global__ void __launch_bounds__(256) k_skip_fill(const int32_t *__restrict__ e, int64_t n, uint8_t *__restrict__ skip)
 {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
-    const int64_t lo = p > 0 ? (int64_t)e[p - 1] + 1 : 0;
-    const int64_t hi = p + 1 < n ? (int64_t)e[p] : n;          // the last position closes the table: E <= n
-    for (int64_t E = lo; E <= hi; E++) { const int64_t d = E - p; skip[E] = (uint8_t)(d < 255 ? d : 255); }
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x, nn = (uint32_t)n;          // n < 2^31 and e <= n
+    if (p >= nn) return;
+    const uint32_t lo = p > 0 ? (uint32_t)e[p - 1] + 1u : 0u;
+    const uint32_t hi = p + 1 < nn ? (uint32_t)e[p] : nn;      // the last position closes the table: E <= n
+    for (uint32_t E = lo; E <= hi; E++) { const uint32_t d = E - p; skip[E] = (uint8_t)(d < 255u ? d : 255u); }
 }
 
 // ------------------------------------------------------------------------------------ K-mer bucket table
@@ -362,13 +362,14 @@ __global__ void __launch_bounds__(256) k_skip_fill(const int32_t *__restrict__ e
 template <class KeyT>
 __global__ void __launch_bounds__(256) k_bucket_fill(const KeyT *__restrict__ keys, int64_t n, int K, uint32_t *__restrict__ table)
 {
-    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p > n) return;
-    auto bk = [&](int64_t q) -> int64_t { const uint32_t hi = sizeof(KeyT) == 4 ? (uint32_t)keys[q] : (uint32_t)((uint64_t)keys[q] >> 6); return (int64_t)(hi >> (32 - 2 * K)); };
-    int64_t nb = 1ll << (2 * K);
-    int64_t cur = p < n ? bk(p) : nb;
-    int64_t prev = p > 0 ? bk(p - 1) : -1;
-    for (int64_t k = prev + 1; k <= cur; k++) table[k] = (uint32_t)p;
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;           // n < 2^31, 4^K <= 2^26: 32-bit arithmetic throughout
+    const uint32_t nn = (uint32_t)n;
+    if (p > nn) return;
+    const int sh = 32 - 2 * K;
+    auto bk = [&](uint32_t q) -> uint32_t { const uint32_t hi = sizeof(KeyT) == 4 ? (uint32_t)keys[q] : (uint32_t)((uint64_t)keys[q] >> 6); return hi >> sh; };
+    const uint32_t cur = p < nn ? bk(p) : 1u << (2 * K);
+    uint32_t k = p > 0 ? bk(p - 1) + 1u : 0u;
+    for (; k <= cur; k++) table[k] = p;
 }
 
 // presence bitmap: the top 2P bits of every sorted key (END / X padding only ever adds P-mers, which is harmless: a set bit

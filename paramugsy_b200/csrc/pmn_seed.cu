@@ -160,7 +160,7 @@ __device__ __forceinline__ bool seed_general(const View32 &R32, const View32 &Q3
 //   need / done   one bit per position: "has to be looked up" / "settled" (looked up, or stepped over)
 //   0  blocks     one bit probe per block of minmatch - P + 1 positions settles the block when the P-mer at its last position is not in
 //                 the reference (presence bitmap of the index): most of the strand without homology, and the positions in front of a
-//                 mismatch.  The seeds are every 32nd position and every position behind a settled one.
+//                 mismatch.  The work list starts from the positions of every block that follows a settled one.
 //   A  select     the next 32 positions of `need`
 //   B  classify   window of the query, bucket of its first K bases.  Empty bucket (3 of 4 look-ups at 2 % divergence): nothing
 //                 matches minmatch >= K bases; the next position is needed.  Two or more suffixes: the position goes on the
@@ -254,36 +254,37 @@ __global__ void __launch_bounds__(SEED_THREADS) k_seed(PackedView R, const uint3
     int run_lim;        // positions of the run that exist
     { const int64_t left = sec.npos - woff; run_lim = left <= 0 ? 0 : left < SEED_RUN ? (int)left : SEED_RUN; }
     const uint32_t vmask = run_lim >= (lane + 1) * 32 ? ~0u : run_lim <= lane * 32 ? 0u : (1u << (run_lim - lane * 32)) - 1u;
-    W.done[lane] = 0; W.bits[lane] = 0;
+    W.done[lane] = 0; W.bits[lane] = 0; W.need[lane] = 0;
     uint32_t nsingle = 0, nmulti = 0;                                     // the same in every lane
     __syncwarp();
     // ---- 0. blocks of B = minmatch - P + 1 positions: a match of minmatch bases that starts anywhere in a block contains the P-mer at
     // the block's last position; when the reference does not hold that P-mer (or it is cut short by an X or the end of the
-    // record) the whole block is settled
+    // record) the whole block is settled.  The work list starts from every position of the blocks that follow a settled block
+    // (and of the first block): that is where a mismatch has just been passed and a new match may begin — its look-ups are
+    // made side by side instead of one scheduling the next.
     const int Bk = minmatch - P + 1;
     unsigned my_probes = 0;
     if (Bk >= 2 && run_lim > 0) {
         const int nblk = (run_lim + Bk - 1) / Bk;
+        bool carry_here = false;                                          // was the last block of the previous round of 32 in the reference?
         for (int base = 0; base < nblk; base += 32) {
             const int blk = base + lane;
+            bool here = false; int b0 = 0, b1 = 0;
             if (blk < nblk) {
-                const int b0 = blk * Bk, b1 = b0 + Bk < run_lim ? b0 + Bk : run_lim;
+                b0 = blk * Bk; b1 = b0 + Bk < run_lim ? b0 + Bk : run_lim;
                 uint32_t g; uint64_t qw; int vq;
                 window(b1 - 1, g, qw, vq);
-                bool here = false;
                 if (vq >= P) { const uint32_t pk = (uint32_t)(qw >> (64 - 2 * P)); here = (__ldg(present + (pk >> 5)) >> (pk & 31)) & 1u; }
                 if (!here) seed_or_range(W.done, b0, b1);
             }
+            const unsigned hb = __ballot_sync(0xffffffffu, here);
+            const bool prev_here = lane ? (hb >> (lane - 1)) & 1u : carry_here;
+            if (here && !prev_here) seed_or_range(W.need, b0, b1);
+            carry_here = (hb >> 31) & 1u;
         }
         if (lane == 0) my_probes = (unsigned)nblk;
-        __syncwarp();
-    }
+    } else W.need[lane] = vmask & 1u;                                     // no filter (minmatch <= P): the seeds are every 32nd position
     my_probes_total += my_probes;
-    {   // the seeds: every 32nd position, and every position behind a settled one
-        const uint32_t dw = W.done[lane];
-        const uint32_t carry = lane ? W.done[lane - 1] >> 31 : 0u;
-        W.need[lane] = (1u | ((dw << 1) | carry)) & ~dw & vmask;
-    }
     __syncwarp();
 
     // 32 buffered one-suffix positions (the last n of the buffer)
@@ -323,7 +324,7 @@ __global__ void __launch_bounds__(SEED_THREADS) k_seed(PackedView R, const uint3
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += t; }
         const int total = __shfl_sync(0xffffffffu, pre, 31);
         pre -= pc;
-        if (nsingle >= 32u || (nsingle > 0u && total < 32)) { singles(nsingle < 32u ? nsingle : 32u); continue; }
+        if (nsingle >= 32u || (nsingle > 0u && total == 0)) { singles(nsingle < 32u ? nsingle : 32u); continue; }
         if (total == 0) break;
         {   // every lane hands the first positions of its word to the selection, in position order
             uint32_t take = 0, ww = w; int r = pre;
