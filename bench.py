@@ -235,7 +235,7 @@ def run_gpu(args):
 
     def run_batch(plist, from_fasta, keep=None, post=0, deltas=False):
         if broadcast and not from_fasta and plist is my_pairs:
-            out = multi.AllVsAll(sched, seq_list, names, pairs, rank, world, R.dist).step()
+            out = multi.AllVsAll(sched, seq_list, names, pairs, rank, world, R.dist, cost=[nbytes[a] + nbytes[b] for a, b in pairs]).step()
             res = [out[k] for k in sorted(out)]
         elif not plist:
             res = []

@@ -179,6 +179,21 @@ static int ctx_init(pmn_ctx *c)
     return 0;
 }
 
+cudaStream_t pmn_ctx_prio_stream(pmn_ctx *c, int level)
+{
+    int least = 0, greatest = 0;
+    if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    const int levels = least - greatest;                  // priorities above the default one (numerically lower = higher priority)
+    if (levels < 1) return nullptr;
+    if (level < 0) level = 0;
+    if (level > levels - 1) level = levels - 1;
+    if (level > 7) level = 7;
+    if (!c->prio_stream[level] && cudaStreamCreateWithPriority(&c->prio_stream[level], cudaStreamNonBlocking, greatest + level) != cudaSuccess) {
+        cudaGetLastError(); c->prio_stream[level] = nullptr;
+    }
+    return c->prio_stream[level];
+}
+
 static void ctx_teardown(pmn_ctx *c)
 {
     pmn_scratch_free(c->scratch);
@@ -186,6 +201,7 @@ static void ctx_teardown(pmn_ctx *c)
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->stream2) cudaStreamDestroy(c->stream2);
+    for (auto &ps : c->prio_stream) if (ps) cudaStreamDestroy(ps);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     delete c;

@@ -79,6 +79,7 @@ struct pmn_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;     // forked from `stream` where two independent kernels of one pair can run side by side
+    cudaStream_t prio_stream[8] = {};   // created on demand: streams of higher device priority than `stream` (level 0 = highest), see pmn_ctx_prio_stream
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev[16] = {};
     PmnError err{};
@@ -130,7 +131,12 @@ static inline char *pmn_fmt_int(char *p, long long v)
 }
 
 int pmn_last_code();                          // code of the calling thread's last pmn_set_error (pmn_api.cu)
-void pmn_apply_device_sched(int workers);     // whether host threads spin or yield while they wait for the device (pmn_api.cu)
+void pmn_apply_device_sched(int workers);
+// A stream of this context whose kernels the device schedules before those of the ordinary streams (level 0 first, then 1, ...;
+// as many levels as the device has above the default priority).  The scheduler builds the indexes of a batch on them, in
+// reference order: pairs wait for their index, so its kernels go first, and the index of the first reference — the one most
+// pairs are waiting for — is not slowed down by the six builds that started with it.  nullptr: no priorities on this device.
+cudaStream_t pmn_ctx_prio_stream(pmn_ctx *c, int level);     // whether host threads spin or yield while they wait for the device (pmn_api.cu)
 
 // stage entry points (defined in the .cu files)
 int pmn_fasta_to_device(pmn_ctx *c, pmn_seq *s, const char *txt, size_t nb, const std::vector<int64_t> &header_pos);

@@ -189,23 +189,34 @@ static int sched_run(pmn_sched *s, int ng, const char *const *fasta, const size_
     auto worker = [&](int w) {
         pmn_ctx *c = s->ctx[(size_t)w];
         cudaSetDevice(c->device);
-        auto pack = [&](int g) { return acquire(seqs, g, [&]() -> void * { BorrowedScratch b(s, c); pmn_seq *x = nullptr; return pmn_seq_from_fasta(c, fasta[g], bytes[g], &x) ? nullptr : (void *)x; }); };
+        // packing and index builds run on a stream the device schedules ahead of the pair kernels (pairs wait for them)
+        struct OnStream {
+            pmn_ctx *c; cudaStream_t saved;
+            OnStream(pmn_ctx *c_, cudaStream_t st) : c(c_), saved(c_->stream) { if (st) c->stream = st; }
+            ~OnStream() { c->stream = saved; }
+        };
+        static const bool use_prio = !(getenv("PMN_SCHED_PRIORITIES") && !strcmp(getenv("PMN_SCHED_PRIORITIES"), "0"));
+        auto pack = [&](int g) { return acquire(seqs, g, [&]() -> void * {
+            BorrowedScratch b(s, c); OnStream on(c, use_prio ? pmn_ctx_prio_stream(c, 0) : nullptr);
+            pmn_seq *x = nullptr; return pmn_seq_from_fasta(c, fasta[g], bytes[g], &x) ? nullptr : (void *)x; }); };
         // genomes given as FASTA text: the workers pack them side by side first (H2D + parse + 2-bit pack per genome),
         // instead of every worker waiting for the reference of the first pairs and then packing its query alone
         if (!resident) for (int g = w; g < ng; g += W_active) if (seqs[(size_t)g].users > 0 && !pack(g)) return;
-        auto get_index = [&](int r, pmn_seq *rs) {
+        auto get_index = [&](int r, pmn_seq *rs, int level = 0) {
             return (pmn_index *)acquire(idx, r, [&]() -> void * {
                 // at most MAX_LIVE_INDEXES indexes built by this run are alive at a time: pairs are taken in reference order, so the
                 // holders of the oldest ones finish without needing another; bounds the memory (8.25 B/base each) and keeps the
                 // number of index images the pool ever holds fixed, i.e. no allocation in later batches
                 { std::unique_lock<std::mutex> lk(s->bmu); s->bcv.wait(lk, [&] { return live_indexes < MAX_LIVE_INDEXES || failed.load(); }); if (failed.load()) return nullptr; live_indexes++; }
-                BorrowedScratch b(s, c); pmn_index *x = nullptr;
+                BorrowedScratch b(s, c); OnStream on(c, use_prio ? pmn_ctx_prio_stream(c, level) : nullptr);
+                pmn_index *x = nullptr;
                 if (pmn_index_build(c, rs, &x)) { std::lock_guard<std::mutex> lk(s->bmu); live_indexes--; s->bcv.notify_all(); return nullptr; }
                 return (void *)x; });
         };
         // the first MAX_LIVE_INDEXES references of the batch are indexed side by side by the first workers, so that the batch
         // does not open with every worker waiting for one build (the gaps of one build are filled by the others)
-        if (w < (int)first_refs.size()) { const int r = first_refs[(size_t)w]; pmn_seq *rs = (pmn_seq *)pack(r); if (!rs || !get_index(r, rs)) return; }
+        // ... in reference order of device priority: the first reference's index — most pairs wait for it — is ready first
+        if (w < (int)first_refs.size()) { const int r = first_refs[(size_t)w]; pmn_seq *rs = (pmn_seq *)pack(r); if (!rs || !get_index(r, rs, w)) return; }
         for (;;) {
             { std::lock_guard<std::mutex> lk(s->mu); if (s->err_code) return; }
             const int k = next.fetch_add(1);

@@ -93,3 +93,16 @@ def test_large_pair_over_several_devices_is_byte_identical(oracle, index, monkey
             assert res.delta == want, f"{len(devices)} devices, index {index}"
             assert len(ms) == 4 and all(x >= 0 for x in ms)
             res.close()
+
+
+def test_the_c_plan_and_the_torch_distributed_plan_are_the_same_rule():
+    """bench.py shards by pmn_multi_plan while multi.AllVsAll (index broadcast) uses assign_pairs: the same cut for any sizes."""
+    import random
+    rnd = random.Random(7)
+    for _ in range(100):
+        n, world = rnd.randint(2, 12), rnd.randint(1, 8)
+        nb = [rnd.randint(1_000_000, 6_000_000) for _ in range(n)]
+        pairs = all_pairs(n)
+        dev = lib.multi_plan(world, pairs, nb)
+        a = multi.assign_pairs(pairs, world, [nb[x] + nb[y] for x, y in pairs])
+        assert all(dev[k] == r for r, ks in enumerate(a) for k in ks), (n, world)

@@ -29,6 +29,26 @@ except Exception as e:
     print(f"{sys.argv[1]:24s} FAILED {e}")
 P
              done < tools/sweep.txt ;;
+    multi)   # GPUS=N tools/gpu_visit.sh <tag> multi : the sharded C2 batch (rebuild and broadcast) and the C4 pair on N ranks
+             N=${GPUS:-2}; run="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533"
+             timeout 600 $run bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/${tag}_c2_${N}gpu.json 2> gpurun_out/${tag}_c2_${N}gpu.err; echo "c2 x$N rc=$?"
+             timeout 600 $run bench.py --gpus $N --steps 20 --warmup 5 --replicate broadcast > gpurun_out/${tag}_c2_${N}gpu_broadcast.json 2> gpurun_out/${tag}_c2_${N}gpu_broadcast.err; echo "c2 broadcast x$N rc=$?"
+             timeout 900 $run bench.py --gpus $N --config c4 --steps 6 --warmup 2 > gpurun_out/${tag}_c4_${N}gpu.json 2> gpurun_out/${tag}_c4_${N}gpu.err; echo "c4 x$N rc=$?"
+             timeout 900 $run bench.py --gpus $N --config c4 --steps 6 --warmup 2 --replicate broadcast > gpurun_out/${tag}_c4_${N}gpu_broadcast.json 2> gpurun_out/${tag}_c4_${N}gpu_broadcast.err; echo "c4 broadcast x$N rc=$?"
+             python - gpurun_out/${tag}_c2_${N}gpu.json gpurun_out/${tag}_c2_${N}gpu_broadcast.json gpurun_out/${tag}_c4_${N}gpu.json gpurun_out/${tag}_c4_${N}gpu_broadcast.json <<'P'
+import json, sys
+for f in sys.argv[1:]:
+    try:
+        d = json.loads(open(f).read().strip().splitlines()[-1])
+        w = d.get("extra_weak") or {}
+        print(f"{f}: value {d['value']:.1f} e2e {d['e2e']['value']:.1f} ms/step {d['ms_per_step']:.2f} weak {w.get('value', 0):.1f} by rank {d.get('ms_per_step_by_rank')}")
+    except Exception as e:
+        print(f, "FAILED", e)
+P
+             ;;
+    c4)      timeout 900 python bench.py --config c4 --steps 6 --warmup 2 > gpurun_out/${tag}_c4_1gpu.json 2> gpurun_out/${tag}_c4_1gpu.err; echo "c4 rc=$?"; head -c 600 gpurun_out/${tag}_c4_1gpu.json; echo ;;
+    configs) timeout 600 python tools/run_configs.py c5 > gpurun_out/${tag}_c5.json 2> gpurun_out/${tag}_c5.err; echo "c5 rc=$?"
+             timeout 900 python tools/run_configs.py c3 > gpurun_out/${tag}_c3.json 2> gpurun_out/${tag}_c3.err; echo "c3 rc=$?"; tail -c 400 gpurun_out/${tag}_c3.json; echo ;;
     *) echo "unknown step $s" ;;
   esac
 done
