@@ -287,6 +287,8 @@ def run_gpu(args):
         run_batch(my_pairs, True, post=1)
     ms_wrk, cnt_wrk = R.timed(lambda: run_batch(my_pairs, True, post=1), args.steps, c_sched, lib.alloc_count)
     clocks = sampler.stop() if rank == 0 else None
+    free_b, total_b = torch.cuda.mem_get_info()
+    mem_used_gb = (total_b - free_b) / 2**30
     # ---- N > 1: the replica mode next to the sharded one (every rank runs the whole batch)
     weak = None
     if sharded:
@@ -410,7 +412,7 @@ def run_gpu(args):
             "step_wall_ms": {"resident": spread(cnt_res["walls"]), "e2e": spread(cnt_e2e["walls"]), "e2e_worker": spread(cnt_wrk["walls"])},
             "device_allocations_in_timed_region": {"resident": cnt_res["allocs"], "e2e": cnt_e2e["allocs"]},
             "ms_per_step_by_rank": {"resident": cnt_res["ranks_ms"], "e2e": cnt_e2e["ranks_ms"]}, "host_cores": os.cpu_count(),
-            "clocks": clocks,
+            "clocks": clocks, "device_memory_used_gb": round(mem_used_gb, 1),
             "stage_ms_per_step": {"what": "sum over the pairs of a step of the CUDA-event time of each stage; under_load = inside the timed steps (16 pairs share the GPU), alone = one pair at a time",
                                   "under_load": stage_in, "alone": stage_alone},
             "roofline": dominant, "roofline_seed": roof_seed, "roofline_extend": roof_ext, "roofline_index": roof_idx,
@@ -628,7 +630,7 @@ def main():
     ap.add_argument("--config", default="c2", choices=["c2", "c4"])
     ap.add_argument("--mode", default="auto", choices=["auto", "weak", "strong"], help="N > 1: strong = the 28 pairs sharded over the ranks (default), weak = every rank runs the whole batch")
     ap.add_argument("--replicate", default="rebuild", choices=["rebuild", "broadcast"], help="sharded runs: every rank builds the indexes it needs (default) or one build per index and an NCCL broadcast")
-    ap.add_argument("--workers", type=int, default=0, help="pairs in flight per GPU (pmn_sched worker threads); 0 = as many as the host cores per local rank carry, 8 ... 24")
+    ap.add_argument("--workers", type=int, default=0, help="pairs in flight per GPU (pmn_sched worker threads); 0 = twice the host cores per local rank, between 8 and 32")
     ap.add_argument("--genomes", type=int, default=8)
     ap.add_argument("--genome-bp", type=int, default=5_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -648,7 +650,7 @@ def main():
         run_gpu(args)
 
 
-PMN_DEFAULT_WORKERS = 16      # pairs in flight per GPU when the host has the cores for them (see DESIGN.md §6 for the sweep)
+PMN_DEFAULT_WORKERS = 32      # pairs in flight per GPU when the host has the cores for them (16 -> 1955, 28 -> 2030, 32 -> 2040 pairs/s)
 
 
 if __name__ == "__main__":

@@ -1975,7 +1975,10 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     launches++;
 
     // ---- E2/E3 storage
-    static const int big_bps = getenv("PMN_BIG_BPS") ? std::max(1, atoi(getenv("PMN_BIG_BPS"))) : 4, tpj_bps = getenv("PMN_TPJ_BPS") ? std::min(TPJ_BLOCKS_PER_SM, std::max(1, atoi(getenv("PMN_TPJ_BPS")))) : TPJ_BLOCKS_PER_SM;
+    // persistent blocks per SM of the warp-per-job and thread-per-job kernels.  Two each: with four, every worker held twice the
+    // private traceback slots and score rows (3.6 GB instead of 1.8 GB) and a batch was no faster (1734 vs 1759 pairs/s at 16
+    // workers); at two, 32 workers fit one B200 and all 28 pairs of a C2 step are in flight together (2040 pairs/s)
+    static const int big_bps = getenv("PMN_BIG_BPS") ? std::max(1, atoi(getenv("PMN_BIG_BPS"))) : 2, tpj_bps = getenv("PMN_TPJ_BPS") ? std::min(TPJ_BLOCKS_PER_SM, std::max(1, atoi(getenv("PMN_TPJ_BPS")))) : 2;
     const int blocks1 = c->sm_count * big_bps;                // 4 warps per block
     const int blocks_st = (nS + EX_WARPS_PER_BLOCK - 1) / EX_WARPS_PER_BLOCK;
     const int nslots = std::max(blocks1, blocks_st) * EX_WARPS_PER_BLOCK;                 // warps that may run the wide fallback (global score rows)
