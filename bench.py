@@ -333,54 +333,61 @@ def run_gpu(args):
         traffic, traffic_src = ncu_traffic()
         if args.genome_bp != 5_000_000:
             traffic, traffic_src = {}, None
+        # Roofline objects.  `achieved` / `frac` use the kernel's duration ALONE on the GPU (CUDA events on its stream in the one-pair-at-a-time
+        # pass of this same run): a roofline assumes the kernel has the machine.  `under_load` are the same events taken inside the timed
+        # steps, where up to 32 pairs share the GPU and an interval on one stream includes waiting for SMs other pairs hold — reported, but
+        # not a kernel duration.  `whole_step` is the aggregate: all launches of the kernel in a step over the step's duration.
+        n_pairs_alone = max(1, len(alone))
         # ---- seeding: bytes the kernel's own algorithm needs, per launch
         #   per looked-up position: K-mer table entry pair 8 B + suffix-array entry 4 B + one 8-byte reference word + 1 B of the skip table;
         #   per block probe: one 4-byte word of the presence bitmap;
         #   per position (looked up, settled by a probe or stepped over): 0.375 B of packed query (text + mask bits); 16 B per anchor written.
-        n_seed = max(1, len(alone))
-        b_own = sum(st["seed_lookups"] * 21.0 + st["seed_probes"] * 4.0 + 2 * st["qry_bases"] * 0.375 + 16 * st["anchors"] for _, _, st, _ in alone)
-        b_model = sum(2 * st["qry_bases"] * (12 * math.ceil(math.log2(max(2, st["ref_bases"]))) + 8.25) + 12 * st["anchors"] for _, _, st, _ in alone)
-        seed_ms_alone, seed_ms_in = S("ms_seed_kernel") / n_seed, S_in("ms_seed_kernel") / n_in
+        b_own = sum(st["seed_lookups"] * 21.0 + st["seed_probes"] * 4.0 + 2 * st["qry_bases"] * 0.375 + 16 * st["anchors"] for _, _, st, _ in alone) / n_pairs_alone
+        b_model = sum(2 * st["qry_bases"] * (12 * math.ceil(math.log2(max(2, st["ref_bases"]))) + 8.25) + 12 * st["anchors"] for _, _, st, _ in alone) / n_pairs_alone
+        seed_ms_alone, seed_ms_in = S("ms_seed_kernel") / n_pairs_alone, S_in("ms_seed_kernel") / n_in
         lookups = sum(st["seed_lookups"] for _, _, st, _ in alone); positions = sum(2 * st["qry_bases"] for _, _, st, _ in alone)
+        gbs = lambda nbytes, ms: nbytes / (ms * 1e-3) / 1e9 if ms else None
+        frac_of = lambda x, peak: x / peak if x else None
         seed_traffic = (traffic.get("k_seed") or {}).get("dram_bytes_per_launch")
         roof_seed = {"kernel": "k_seed", "bound": "hbm", "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": b_own / n_seed,
-                     "launch_ms": seed_ms_in, "launch_ms_alone": seed_ms_alone,
-                     "achieved": b_own / n_seed / (seed_ms_in * 1e-3) / 1e9 if seed_ms_in else None,
-                     "achieved_alone": b_own / n_seed / (seed_ms_alone * 1e-3) / 1e9 if seed_ms_alone else None,
+                     "algorithmic_bytes_per_launch": b_own, "launch_ms": seed_ms_alone,
+                     "achieved": gbs(b_own, seed_ms_alone), "frac": frac_of(gbs(b_own, seed_ms_alone), hbm_peak),
+                     "under_load": {"launch_ms": seed_ms_in, "achieved": gbs(b_own, seed_ms_in), "frac": frac_of(gbs(b_own, seed_ms_in), hbm_peak)},
+                     "whole_step": {"achieved": gbs(b_own * npairs_rank, step_ms), "frac": frac_of(gbs(b_own * npairs_rank, step_ms), hbm_peak)},
                      "traffic": seed_traffic, "traffic_source": traffic_src,
-                     "dram_gbs_alone": seed_traffic / (seed_ms_alone * 1e-3) / 1e9 if seed_traffic and seed_ms_alone else None,
+                     "dram_gbs_measured": gbs(seed_traffic, seed_ms_alone) if seed_traffic else None,
+                     "dram_frac_measured": frac_of(gbs(seed_traffic, seed_ms_alone), hbm_peak) if seed_traffic else None,
                      "positions_looked_up": lookups / max(1, positions), "block_probes_per_position": sum(st["seed_probes"] for _, _, st, _ in alone) / max(1, positions),
                      "survey_model": {"what": "SURVEY.md §8d counts a full binary search per position (12 B x log2 n + 8.25): work the kernel no longer does; "
-                                              "equivalent-work rate only, NOT a roofline fraction", "bytes_per_launch": b_model / n_seed,
-                                      "equivalent_gbs_alone": b_model / n_seed / (seed_ms_alone * 1e-3) / 1e9 if seed_ms_alone else None},
-                     "note": "random 32-byte sectors of a 64 MB table and a 20 MB suffix array: a latency-bound gather, not a stream"}
-        roof_seed["frac"] = roof_seed["achieved"] / hbm_peak if roof_seed["achieved"] else None
-        roof_seed["frac_alone"] = roof_seed["achieved_alone"] / hbm_peak if roof_seed["achieved_alone"] else None
+                                              "equivalent-work rate only, NOT a roofline fraction", "bytes_per_launch": b_model, "equivalent_gbs": gbs(b_model, seed_ms_alone)},
+                     "note": "random 32-byte sectors of a 64 MB table, a 20 MB suffix array and a 32 MB bitmap: a latency-bound gather, not a stream; "
+                             "north_star's 50 % of HBM does not apply to an algorithm that avoids the traffic (DESIGN.md §4.3)"}
         # ---- extension wave 1
-        w1_in, w1_alone = S_in("ms_wave1") / n_in, S("ms_wave1") / n_seed
-        cells_pair = S("wave1_cells") / n_seed
+        w1_in, w1_alone = S_in("ms_wave1") / n_in, S("ms_wave1") / n_pairs_alone
+        cells_pair = S("wave1_cells") / n_pairs_alone
+        gops = lambda cells, ms: cells * 16 / (ms * 1e-3) / 1e9 if ms else None
         gcups_in = cells_pair / (w1_in * 1e-3) / 1e9 if w1_in else None
         gcups_alone = cells_pair / (w1_alone * 1e-3) / 1e9 if w1_alone else None
         roof_ext = {"kernel": "k_ex_wave1_tpj + k_ex_wave1_big (side by side on two streams)", "bound": "int32", "peak": int32_gops, "unit": "Gop/s",
                     "peak_source": "measured (pmn_measure_int32_peak, add+max chains)", "ops_per_cell": 16, "cells_per_launch": cells_pair,
-                    "launch_ms": w1_in, "launch_ms_alone": w1_alone, "gcups": gcups_in, "gcups_alone": gcups_alone,
-                    "achieved": gcups_in * 16 if gcups_in else None, "achieved_alone": gcups_alone * 16 if gcups_alone else None,
+                    "launch_ms": w1_alone, "gcups": gcups_alone, "achieved": gops(cells_pair, w1_alone), "frac": frac_of(gops(cells_pair, w1_alone), int32_gops),
+                    "under_load": {"launch_ms": w1_in, "gcups": gcups_in, "achieved": gops(cells_pair, w1_in), "frac": frac_of(gops(cells_pair, w1_in), int32_gops)},
+                    "whole_step": {"gcups": cells_pair * npairs_rank / (step_ms * 1e-3) / 1e9, "achieved": gops(cells_pair * npairs_rank, step_ms),
+                                   "frac": frac_of(gops(cells_pair * npairs_rank, step_ms), int32_gops)},
                     "traffic": sum((traffic.get(k) or {}).get("dram_bytes_per_launch", 0) for k in ("k_ex_wave1_tpj", "k_ex_wave1_big")) or None,
                     "traffic_source": traffic_src,
-                    "note": "the window is bounded by a few long alignments (cluster-end searches one warp runs each), not by INT32 issue"}
-        roof_ext["frac"] = roof_ext["achieved"] / int32_gops if roof_ext["achieved"] else None
-        roof_ext["frac_alone"] = roof_ext["achieved_alone"] / int32_gops if roof_ext["achieved_alone"] else None
+                    "note": "the window is as long as its longest alignment (cluster-end searches one warp runs each, the largest windows of the thread-per-job kernel), "
+                            "not INT32 issue: the thread-per-job kernel keeps the SMs busy for 15 % of it (DESIGN.md §4.5)"}
         b_index = sum(len(genomes[a][1]) * (4.25 + 16 * max(1, rounds) + 12.5 + 6) for a, rounds in {a: st["sa_rounds"] for a, _, st, _ in alone}.items())
-        roof_idx = {"kernel": "index build (sort + doubling + lcp + table + skip table)", "bound": "hbm", "peak": hbm_peak, "unit": "GB/s",
+        roof_idx = {"kernel": "index build (sort + doubling + lcp + table + skip table + presence map)", "bound": "hbm", "peak": hbm_peak, "unit": "GB/s",
                     "achieved": b_index / (stage_alone["index"] * 1e-3) / 1e9 if stage_alone["index"] else None, "launch_ms": stage_alone["index"] / max(1, len(seen))}
         roof_idx["frac"] = roof_idx["achieved"] / hbm_peak if roof_idx["achieved"] else None
-        # the kernel with the largest share of the time the pairs of the timed steps spent on the device
-        share = {"k_seed": S_in("ms_seed_kernel"), "wave1": S_in("ms_wave1")}
-        tot_in = S_in("ms_seed") + S_in("ms_cluster") + S_in("ms_extend")
-        roof_seed["share_of_pair_time"] = share["k_seed"] / tot_in if tot_in else None
-        roof_ext["share_of_pair_time"] = share["wave1"] / tot_in if tot_in else None
-        dominant = dict(roof_ext if share["wave1"] >= share["k_seed"] else roof_seed)
+        # the dominant kernel: the largest share of the time a pair spends on the device when it has the GPU (the ncu launch list of this
+        # command, profiles/r02_launches_bench_summary.txt, gives the same order)
+        tot_alone = stage_alone["seed"] + stage_alone["cluster"] + stage_alone["extend"]
+        roof_seed["share_of_pair_time"] = S("ms_seed_kernel") / tot_alone if tot_alone else None
+        roof_ext["share_of_pair_time"] = S("ms_wave1") / tot_alone if tot_alone else None
+        dominant = dict(roof_ext if S("ms_wave1") >= S("ms_seed_kernel") else roof_seed)
         launches_pair = cnt_res["launches"] / max(1, npairs_rank * args.steps)
         out = {
             "metric": METRIC, "value": npairs_all * args.steps / (ms_res * 1e-3), "unit": UNIT,
@@ -399,7 +406,7 @@ def run_gpu(args):
             "parity_how": "sha256 of every pair's .delta == the oracle's committed digest (tests/golden/golden_configs.json), checked before the timed region on every rank",
             "aligned_mbp_per_s": aligned_all / 1e6 / (step_ms * 1e-3),
             "input_mbp_per_s": bp_all / 1e6 / (step_ms * 1e-3),
-            "extension_gcups": gcups_in, "extension_gcups_alone": gcups_alone,
+            "extension_gcups": gcups_alone, "extension_gcups_under_load": gcups_in,
             "e2e": {"value": npairs_all * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": cnt_e2e["h2d_bytes"] // args.steps, "d2h_bytes_per_step": cnt_e2e["d2h_bytes"] // args.steps,
                     "delta_bytes_per_step": sum(d[3] for d in alone)},

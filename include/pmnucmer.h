@@ -195,8 +195,9 @@ void pmn_free_text(char *p);
  * is built once and shared.  Pairs are (ref[k], qry[k]) indexes into the genome list;
  * names[g] is echoed on line 1 of the .delta files.  out[k] is owned by the caller
  * (pmn_result_free).  Results do not depend on `workers`.
- * Sizing: a worker holds 8-9 GB of device memory (traceback arenas, scratch); 16 workers fill one
- * B200 (1482 pairs/s on 8 x 5 Mbp all-vs-all), 8 are enough where the host has few cores per GPU.
+ * Sizing: a worker holds its scratch, 1 MB of private traceback per resident warp of the extension kernels and a traceback
+ * arena that starts at 256 MB and grows with the pairs it meets (PMN_ARENA_MB); 32 workers fit one B200 and carry all 28 pairs
+ * of an 8 x 5 Mbp all-vs-all at once (2040 pairs/s; 16 workers: 1955), 8 are enough where the host has few cores per GPU.
  * The workers launch on 2 x `workers` streams: the library sets CUDA_DEVICE_MAX_CONNECTIONS=32 when
  * it is loaded (unless the host set it) so that every stream has a hardware work queue of its own;
  * a host that initialises CUDA before loading the library has to set the variable itself.

@@ -14,7 +14,7 @@ for s in $steps; do
     bench_ref) timeout 900 python bench.py --impl reference --steps 1 --warmup 1 > gpurun_out/${tag}_bench_ref.json 2> gpurun_out/${tag}_bench_ref.err; echo "ref rc=$?"; head -c 300 gpurun_out/${tag}_bench_ref.json; echo ;;
     ncu_launches) timeout 900 ncu --metrics gpu__time_duration.sum,sm__cycles_active.avg,smsp__inst_executed.sum --clock-control none --csv --log-file gpurun_out/${tag}_launches_bench.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/${tag}_ncu_launches.log 2>&1; echo "ncu launches rc=$?" ;;
     ncu_pair) timeout 900 ncu --metrics gpu__time_duration.sum,sm__cycles_active.avg,smsp__inst_executed.sum --clock-control none --csv --log-file gpurun_out/launches_pair.csv python tools/profile_pair.py 5000000 2 > gpurun_out/${tag}_ncu_pair.log 2>&1; echo "ncu pair rc=$?"; cp gpurun_out/launches_pair.csv gpurun_out/${tag}_launches_pair.csv ;;
-    ncu_full) timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:k_ex_wave|k_ex_stitch|k_seed$|k_cl_chains|pmn_rs_scatter|pmn_scan_onepass" -c 14 -o gpurun_out/pair_full -f python tools/profile_pair.py 5000000 1 > gpurun_out/${tag}_ncu_full.log 2>&1; echo "ncu full rc=$?" ;;
+    ncu_full) timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:k_ex_wave1|k_ex_wave2|k_ex_stitch|k_seed$|k_cl_chains|pmn_rs_scatter|k_bucket_fill|k_skip_fill|k_present_fill" -c 24 -o gpurun_out/pair_full -f python tools/profile_pair.py 5000000 1 > gpurun_out/${tag}_ncu_full.log 2>&1; echo "ncu full rc=$?" ;;
     sweep)   # tools/sweep.txt: one run per line, "<name> [VAR=value ...] -- <bench.py arguments>"
              while read -r name rest; do
                [ -z "$name" ] && continue; case $name in \#*) continue;; esac
