@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "_lib")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-Xptxas", "-v" if os.environ.get("PMN_PTXAS_V") else "-O3"]
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v" if os.environ.get("PMN_PTXAS_V") else "-O3"] + os.environ.get("PMN_NVCC_EXTRA", "").split()
 
 
 def _stale(target, sources):

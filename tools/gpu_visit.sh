@@ -32,9 +32,9 @@ P
     multi)   # GPUS=N tools/gpu_visit.sh <tag> multi : the sharded C2 batch (rebuild and broadcast) and the C4 pair on N ranks
              N=${GPUS:-2}; run="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533"
              timeout 600 $run bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/${tag}_c2_${N}gpu.json 2> gpurun_out/${tag}_c2_${N}gpu.err; echo "c2 x$N rc=$?"
-             timeout 600 $run bench.py --gpus $N --steps 20 --warmup 5 --replicate broadcast > gpurun_out/${tag}_c2_${N}gpu_broadcast.json 2> gpurun_out/${tag}_c2_${N}gpu_broadcast.err; echo "c2 broadcast x$N rc=$?"
+             if [ -z "$NO_BROADCAST" ]; then timeout 600 $run bench.py --gpus $N --steps 20 --warmup 5 --replicate broadcast > gpurun_out/${tag}_c2_${N}gpu_broadcast.json 2> gpurun_out/${tag}_c2_${N}gpu_broadcast.err; echo "c2 broadcast x$N rc=$?"; fi
              timeout 900 $run bench.py --gpus $N --config c4 --steps 6 --warmup 2 > gpurun_out/${tag}_c4_${N}gpu.json 2> gpurun_out/${tag}_c4_${N}gpu.err; echo "c4 x$N rc=$?"
-             timeout 900 $run bench.py --gpus $N --config c4 --steps 6 --warmup 2 --replicate broadcast > gpurun_out/${tag}_c4_${N}gpu_broadcast.json 2> gpurun_out/${tag}_c4_${N}gpu_broadcast.err; echo "c4 broadcast x$N rc=$?"
+             if [ -z "$NO_BROADCAST" ]; then timeout 900 $run bench.py --gpus $N --config c4 --steps 6 --warmup 2 --replicate broadcast > gpurun_out/${tag}_c4_${N}gpu_broadcast.json 2> gpurun_out/${tag}_c4_${N}gpu_broadcast.err; echo "c4 broadcast x$N rc=$?"; fi
              python - gpurun_out/${tag}_c2_${N}gpu.json gpurun_out/${tag}_c2_${N}gpu_broadcast.json gpurun_out/${tag}_c4_${N}gpu.json gpurun_out/${tag}_c4_${N}gpu_broadcast.json <<'P'
 import json, sys
 for f in sys.argv[1:]:
@@ -49,6 +49,10 @@ P
     c4)      timeout 900 python bench.py --config c4 --steps 6 --warmup 2 > gpurun_out/${tag}_c4_1gpu.json 2> gpurun_out/${tag}_c4_1gpu.err; echo "c4 rc=$?"; head -c 600 gpurun_out/${tag}_c4_1gpu.json; echo ;;
     configs) timeout 600 python tools/run_configs.py c5 > gpurun_out/${tag}_c5.json 2> gpurun_out/${tag}_c5.err; echo "c5 rc=$?"
              timeout 900 python tools/run_configs.py c3 > gpurun_out/${tag}_c3.json 2> gpurun_out/${tag}_c3.err; echo "c3 rc=$?"; tail -c 400 gpurun_out/${tag}_c3.json; echo ;;
+    stress)  timeout 600 python tools/stress.py 5000000 8 24 12 > gpurun_out/${tag}_stress.log 2>&1; echo "stress rc=$?"; tail -3 gpurun_out/${tag}_stress.log
+             timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/stress.py 300000 5 6 1 > gpurun_out/${tag}_memcheck.log 2>&1; echo "memcheck rc=$?"; grep -c "Invalid\|ERROR SUMMARY" gpurun_out/${tag}_memcheck.log; tail -4 gpurun_out/${tag}_memcheck.log ;;
+    stitchprof) PMN_STITCH_TIMING=1 timeout 300 python tools/profile_div.py 0.10 > gpurun_out/${tag}_stitch_q10.log 2>&1; echo "rc=$?"; grep "stitch cycles" gpurun_out/${tag}_stitch_q10.log | tail -1
+             PMN_STITCH_TIMING=1 timeout 300 python tools/profile_div.py 0.02 > gpurun_out/${tag}_stitch_q02.log 2>&1; grep "stitch cycles" gpurun_out/${tag}_stitch_q02.log | tail -1 ;;
     *) echo "unknown step $s" ;;
   esac
 done
