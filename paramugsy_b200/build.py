@@ -11,7 +11,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "_lib")
+# PMN_LIB_DIR: an instrumented build (e.g. PMN_NVCC_EXTRA=-DPMN_STITCH_TIMING) goes to its own directory next to _lib
+LIB = os.path.join(HERE, os.environ.get("PMN_LIB_DIR", "_lib"))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v" if os.environ.get("PMN_PTXAS_V") else "-O3"] + os.environ.get("PMN_NVCC_EXTRA", "").split()

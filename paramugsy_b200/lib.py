@@ -71,7 +71,7 @@ SYMBOLS = [
 
 
 def lib_path():
-    return os.path.join(_HERE, "_lib", "libpmnucmer.so")
+    return os.path.join(_HERE, os.environ.get("PMN_LIB_DIR", "_lib"), "libpmnucmer.so")
 
 
 def lib():

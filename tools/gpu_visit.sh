@@ -53,6 +53,12 @@ P
              timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/stress.py 300000 5 6 1 > gpurun_out/${tag}_memcheck.log 2>&1; echo "memcheck rc=$?"; grep -c "Invalid\|ERROR SUMMARY" gpurun_out/${tag}_memcheck.log; tail -4 gpurun_out/${tag}_memcheck.log ;;
     stitchprof) PMN_STITCH_TIMING=1 timeout 300 python tools/profile_div.py 0.10 > gpurun_out/${tag}_stitch_q10.log 2>&1; echo "rc=$?"; grep "stitch cycles" gpurun_out/${tag}_stitch_q10.log | tail -1
              PMN_STITCH_TIMING=1 timeout 300 python tools/profile_div.py 0.02 > gpurun_out/${tag}_stitch_q02.log 2>&1; grep "stitch cycles" gpurun_out/${tag}_stitch_q02.log | tail -1 ;;
+    diag)    # where a single pair and a small share spend their time: stitch sections (instrumented build in _lib_timing), engine-call log, step timeline, shares of an N-GPU plan
+             PMN_LIB_DIR=_lib_timing PMN_STITCH_TIMING=1 timeout 300 python tools/probe_pairs.py c2 3 > gpurun_out/${tag}_stitch_c2.log 2>&1; grep "stitch cycles" gpurun_out/${tag}_stitch_c2.log | tail -1
+             PMN_JOBLOG_LAST=gpurun_out/${tag}_joblog_c2.txt timeout 300 python tools/probe_pairs.py c2 3 > gpurun_out/${tag}_probe_c2.log 2>&1; tail -1 gpurun_out/${tag}_probe_c2.log | cut -c1-900
+             python tools/joblog_summary.py gpurun_out/${tag}_joblog_c2.txt > gpurun_out/${tag}_joblog_c2_summary.txt 2>&1; rm -f gpurun_out/${tag}_joblog_c2.txt
+             timeout 300 python tools/trace_step.py 32 > gpurun_out/${tag}_trace_w32.log 2>&1; head -4 gpurun_out/${tag}_trace_w32.log
+             timeout 600 python tools/share_latency.py 32 > gpurun_out/${tag}_shares.log 2>&1; cat gpurun_out/${tag}_shares.log ;;
     *) echo "unknown step $s" ;;
   esac
 done

@@ -1,7 +1,7 @@
 """Summarise a PMN_JOBLOG file: per kernel, calls / cells / cycles, the slowest calls."""
 import sys, collections
 rows = [tuple(map(int, l.split())) for l in open(sys.argv[1]) if l.strip() and not l.startswith("#")]
-for kid, name in ((1, "wave1"), (2, "stitch")):
+for kid, name in ((1, "wave1"), (3, "wave2"), (2, "stitch")):
     r = [x for x in rows if x[6] == kid]
     if not r: continue
     cyc = sum(x[5] for x in r); cells = sum(x[4] for x in r); diags = sum(x[3] for x in r)
