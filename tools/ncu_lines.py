@@ -31,5 +31,5 @@ def getline(f, n):
         src[f] = open(p[0]).read().split("\n") if p else []
     return src[f][n - 1].strip()[:120] if src[f] and n <= len(src[f]) else ""
 print("total inst", tot, "samples", tots)
-for key, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+for key, a in sorted(agg.items(), key=lambda kv: -kv[1][1 if os.environ.get("BY_SAMPLES") else 0])[:top]:
     print(f"{100*a[0]/tot:5.1f}% inst {100*a[1]/tots:5.1f}% smp {a[2]:4d} sass  {key[0] if key else None}:{key[1] if key else 0}  {getline(*key) if key else ''}")
