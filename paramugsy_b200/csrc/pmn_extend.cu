@@ -56,7 +56,7 @@ struct ExJobDesc { int64_t Abase, Bbase; int32_t eA, eB, tA, tB, g, dir, m_o, ta
 struct __align__(16) ExAlign { int32_t dirB, sA, sB, eA, eB, P, head, tail, ndelta, live, pad0, pad1; };   // P: reference position consumed through the last indel (sA-1 when none)
 // a piece of an alignment's delta list: type 0 = `cnt` pool entries at `a` whose first value gets +-`b` added;
 // type 1 = the deltas of the wave-1 jobs [a, cnt) (all reached their targets), `b` = P before the range
-struct ExNode { int32_t type; uint32_t a; int32_t cnt, b, outoff, next, alslot, pad; };
+struct ExNode { int32_t type; uint32_t a; int32_t cnt, b, outoff, next, alslot, pad; };   // type 0: pool[a, a+cnt), first delta + b; 1: jobs [a, cnt), P before = b; 2: whole cluster `next` (1 + its end job)
 
 // everything the stitcher needs to know about a cluster in one 80-byte record
 struct __align__(16) ExCSum {
@@ -98,6 +98,7 @@ struct ExShared {                       // everything the device code needs, pas
     uint8_t *tscratch;                  // TPJ_SLOT_BYTES per resident warp of k_ex_wave1_tpj
     ExBack *back;                       // per cluster (wave 2), valid = 0 where none was computed
     uint8_t *entered;                   // per cluster: some cluster's end job reached it (it will most likely be merged, not started)
+    uint8_t *targeted;                  // per cluster: some cluster's end job aims at it (k_ex_jobdesc); the others start alignments for certain
     int4 *dbg; unsigned dbg_cap;        // PMN_JOBLOG: two int4 per engine call (cursor = counters[15])
 };
 
@@ -879,42 +880,46 @@ __device__ __forceinline__ int tpj_bin(int N, int M) { return (13 - (M + TPJ_W -
 __global__ void __launch_bounds__(256) k_ex_jobdesc(ExShared X, ExJobDesc *__restrict__ descA, ExJobDesc *__restrict__ descB)
 {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= X.nM) return;
-    const int k = X.mcl[g];
-    const ExCluster c = X.cl[k];
-    const ExSynteny S = X.syn[c.syn];
-    ExJobDesc d;
-    d.Abase = S.Abase; d.Bbase = c.dir ? S.BbaseR : S.BbaseF;
-    d.eA = X.mA[g] + X.mL[g] - 1; d.eB = X.mB[g] + X.mL[g] - 1; d.g = (int32_t)g; d.dir = c.dir;
-    if ((int)g != c.mfirst + c.nm - 1) {
-        d.tA = X.mA[g + 1]; d.tB = X.mB[g + 1]; d.m_o = PMN_FORWARD_ALIGN; d.target = -1;
-        const int n = d.tA - d.eA + 1, m = d.tB - d.eB + 1;
-        if (n == m && n >= 1 && n <= 20 && X.breaklen >= 100 &&
-            run_mismatches(X.R, d.Abase + d.eA - 1, c.dir ? X.QR : X.QF, d.Bbase + d.eB - 1, n) <= 1) {
-            ExJob r; r.endA = d.tA; r.endB = d.tB; r.dcnt = 0; r.target = -1; r.doff = 0; r.reached = 1; r.valid = 1; r.asum = 0;
-            X.jobs[g] = r;
-            atomicAdd(X.counters + 2, (unsigned long long)((n + 1) * (m + 1) - 1));
-            atomicAdd(X.counters + 3, 1ull);
-            d.m_o = -1;
+    unsigned sc_cells = 0, sc_jobs = 0;             // shortcut windows of this thread: one atomic per warp below (all of them hit two addresses)
+    if (g < X.nM) {
+        const int k = X.mcl[g];
+        const ExCluster c = X.cl[k];
+        const ExSynteny S = X.syn[c.syn];
+        ExJobDesc d;
+        d.Abase = S.Abase; d.Bbase = c.dir ? S.BbaseR : S.BbaseF;
+        d.eA = X.mA[g] + X.mL[g] - 1; d.eB = X.mB[g] + X.mL[g] - 1; d.g = (int32_t)g; d.dir = c.dir;
+        if ((int)g != c.mfirst + c.nm - 1) {
+            d.tA = X.mA[g + 1]; d.tB = X.mB[g + 1]; d.m_o = PMN_FORWARD_ALIGN; d.target = -1;
+            const int n = d.tA - d.eA + 1, m = d.tB - d.eB + 1;
+            if (n == m && n >= 1 && n <= 20 && X.breaklen >= 100 &&
+                run_mismatches(X.R, d.Abase + d.eA - 1, c.dir ? X.QR : X.QF, d.Bbase + d.eB - 1, n) <= 1) {
+                ExJob r; r.endA = d.tA; r.endB = d.tB; r.dcnt = 0; r.target = -1; r.doff = 0; r.reached = 1; r.valid = 1; r.asum = 0;
+                X.jobs[g] = r;
+                sc_cells = (unsigned)((n + 1) * (m + 1) - 1); sc_jobs = 1;
+                d.m_o = -1;
+            }
+            else if (tpj_fits(n, m, X.breaklen, X.tpj_cells)) {
+                const int bin = tpj_bin(n, m);
+                X.tkey[g] = make_uint2((unsigned)bin, atomicAdd(X.tbin + bin, 1u));
+            }
+            else X.overflow[atomicAdd(X.counters + 7, 1ull)] = (int32_t)g;
+            descB[g] = d;
+        } else {
+            d.m_o = -1; d.tA = d.tB = 0; d.target = -1;
+            descB[g] = d;                                       // the last match has no inner job
+            if (X.do_extend) {
+                int64_t targetA = S.lenA, targetB = S.lenB;
+                const int end = S.cfirst + S.nC;
+                const int tc = get_forward_target_cluster(X, k, end, targetA, targetB);
+                d.tA = (int32_t)targetA; d.tB = (int32_t)targetB; d.target = tc;
+                d.m_o = PMN_FORWARD_ALIGN | (tc == end ? PMN_OPTIMAL_BIT : 0);
+                if (tc < end) X.targeted[tc] = 1;               // some cluster's end job aims at tc (see k_ex_wave1_big, heads)
+            }
+            descA[k] = d;
         }
-        else if (tpj_fits(n, m, X.breaklen, X.tpj_cells)) {
-            const int bin = tpj_bin(n, m);
-            X.tkey[g] = make_uint2((unsigned)bin, atomicAdd(X.tbin + bin, 1u));
-        }
-        else X.overflow[atomicAdd(X.counters + 7, 1ull)] = (int32_t)g;
-        descB[g] = d;
-        return;
     }
-    d.m_o = -1; d.tA = d.tB = 0; d.target = -1;
-    descB[g] = d;                                       // the last match has no inner job
-    if (X.do_extend) {
-        int64_t targetA = S.lenA, targetB = S.lenB;
-        const int end = S.cfirst + S.nC;
-        const int tc = get_forward_target_cluster(X, k, end, targetA, targetB);
-        d.tA = (int32_t)targetA; d.tB = (int32_t)targetB; d.target = tc;
-        d.m_o = PMN_FORWARD_ALIGN | (tc == end ? PMN_OPTIMAL_BIT : 0);
-    }
-    descA[k] = d;
+    sc_cells = __reduce_add_sync(0xffffffffu, sc_cells); sc_jobs = __reduce_add_sync(0xffffffffu, sc_jobs);
+    if ((threadIdx.x & 31) == 0 && sc_jobs) { atomicAdd(X.counters + 2, (unsigned long long)sc_cells); atomicAdd(X.counters + 3, (unsigned long long)sc_jobs); }
 }
 
 // A forward alignment (not OPTIMAL) over a window of at most 31 x 31 bases, the bulk of wave 1.  With
@@ -1022,21 +1027,54 @@ __device__ __forceinline__ bool wave1_run(const Eng &E, const ExShared &X, const
     return true;
 }
 
+// The backward extension of the first match of cluster k, ahead of the stitcher (see k_ex_wave2).
+__device__ __forceinline__ void back_job(const Eng &E, const ExShared &X, int k)
+{
+    const ExCluster c = X.cl[k];
+    const ExSynteny S = X.syn[c.syn];
+    const int g = c.mfirst;
+    const int64_t sA = X.mA[g], sB = X.mB[g];
+    // A search that finds nothing dies within breaklen anti-diagonals of its best cell; one that is still alive
+    // further out is following homologous sequence towards an earlier alignment and will most likely be
+    // merged into it by the stitcher, which this kernel cannot know.  So the window is capped, and a search
+    // that touches the cap is left to the stitcher.
+    const int64_t cap = X.breaklen + 128;
+    const int64_t fullN = sA < PMN_MAX_ALIGNMENT_LENGTH ? sA : PMN_MAX_ALIGNMENT_LENGTH, fullM = sB < PMN_MAX_ALIGNMENT_LENGTH ? sB : PMN_MAX_ALIGNMENT_LENGTH;
+    const int64_t Ns = fullN < cap ? fullN : cap, Ms = fullM < cap ? fullM : cap;
+    int64_t targetA = sA - Ns + 1, targetB = sB - Ms + 1;
+    const PackedView &Q = c.dir ? X.QR : X.QF; const int64_t Bbase = c.dir ? S.BbaseR : S.BbaseF;
+    int ext_i = INT32_MAX, ext_j = INT32_MAX;
+    align_engine<CfgBig>(E, S.Abase, sA, targetA, Q, Bbase, sB, targetB, PMN_BACKWARD_SEARCH | PMN_OPTIMAL_BIT, nullptr, nullptr, nullptr, &ext_i, &ext_j);
+    if ((Ns != fullN && ext_i >= Ns) || (Ms != fullM && ext_j >= Ms)) return;        // clipped by the cap: not the search the stitcher would run
+    int64_t eA = sA, eB = sB; uint32_t doff = 0; int32_t dcnt = 0, dasum = 0;
+    align_engine<CfgBig>(E, S.Abase, targetA, eA, Q, Bbase, targetB, eB, PMN_FORCED_FORWARD_ALIGN, &doff, &dcnt, &dasum);
+    if (E.lane == 0) {
+        ExBack b; b.fA = (int32_t)targetA; b.fB = (int32_t)targetB; b.ext_i = ext_i; b.ext_j = ext_j; b.doff = doff; b.dcnt = dcnt; b.asum = dasum; b.valid = 1;
+        X.back[k] = b;
+    }
+    __syncwarp();
+}
+
 // Wave 1, big kernel: the cluster-end extensions (break-length searches, bands up to hundreds of cells)
 // and what the small kernel handed over.
 __global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32, 3) k_ex_wave1_big(ExShared X, int pass)
 {
     Eng E = make_eng(X, nullptr); E.kid = 1;
     const int lane = E.lane;
-    // pass 0 (runs beside the thread-per-job kernel): cluster ends + the windows k_ex_jobdesc found too large;
-    // pass 1 (after it): the windows the thread-per-job kernel handed back
-    const unsigned long long nA = (pass == 0 && X.do_extend) ? (unsigned long long)X.nC : 0ull, nO = X.counters[pass ? 12 : 7];
+    // pass 0 (runs beside the thread-per-job kernel): the heads, cluster ends + the windows k_ex_jobdesc found too large;
+    // pass 1 (after it): the windows the thread-per-job kernel handed back.
+    // Heads: a cluster no end job aims at starts an alignment in the stitcher whatever wave 1 finds, so its backward extension
+    // (two engine runs, as long as the longest jobs of this pass) runs here, first, instead of in a wave of its own afterwards.
+    const unsigned long long nH = (pass == 0 && X.do_extend) ? (unsigned long long)X.nC : 0ull;
+    const unsigned long long nA = nH, nO = X.counters[pass ? 12 : 7];
     const int32_t *list = pass ? X.overflow2 : X.overflow;
     for (;;) {
         unsigned long long k = 0;
         if (lane == 0) k = atomicAdd(X.counters + (pass ? 13 : 5), 1ull);
         k = __shfl_sync(0xffffffffu, k, 0);
-        if (k >= nA + nO) break;
+        if (k >= nH + nA + nO) break;
+        if (k < nH) { if (!X.targeted[k]) { E.kid = 3; back_job(E, X, (int)k); E.kid = 1; } continue; }
+        k -= nH;
         const ExJobDesc d = k < nA ? X.descA[k] : X.descB[list[k - nA]];
         if (d.m_o >= 0) wave1_run<CfgBig>(E, X, d);
     }
@@ -1297,30 +1335,8 @@ __global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32, 3) k_ex_wave2(ExShare
         if (lane == 0) k = atomicAdd(X.counters + 14, 1ull);
         k = __shfl_sync(0xffffffffu, k, 0);
         if (k >= (unsigned long long)X.nC) break;
-        if (X.entered[k]) continue;
-        const ExCluster c = X.cl[k];
-        const ExSynteny S = X.syn[c.syn];
-        const int g = c.mfirst;
-        const int64_t sA = X.mA[g], sB = X.mB[g];
-        // A search that finds nothing dies within breaklen anti-diagonals of its best cell; one that is still alive
-        // further out is following homologous sequence towards an earlier alignment and will most likely be
-        // merged into it by the stitcher, which this kernel cannot know.  So the window is capped, and a search
-        // that touches the cap is left to the stitcher.
-        const int64_t cap = X.breaklen + 128;
-        const int64_t fullN = sA < PMN_MAX_ALIGNMENT_LENGTH ? sA : PMN_MAX_ALIGNMENT_LENGTH, fullM = sB < PMN_MAX_ALIGNMENT_LENGTH ? sB : PMN_MAX_ALIGNMENT_LENGTH;
-        const int64_t Ns = fullN < cap ? fullN : cap, Ms = fullM < cap ? fullM : cap;
-        int64_t targetA = sA - Ns + 1, targetB = sB - Ms + 1;
-        const PackedView &Q = c.dir ? X.QR : X.QF; const int64_t Bbase = c.dir ? S.BbaseR : S.BbaseF;
-        int ext_i = INT32_MAX, ext_j = INT32_MAX;
-        align_engine<CfgBig>(E, S.Abase, sA, targetA, Q, Bbase, sB, targetB, PMN_BACKWARD_SEARCH | PMN_OPTIMAL_BIT, nullptr, nullptr, nullptr, &ext_i, &ext_j);
-        if ((Ns != fullN && ext_i >= Ns) || (Ms != fullM && ext_j >= Ms)) continue;      // clipped by the cap: not the search the stitcher would run
-        int64_t eA = sA, eB = sB; uint32_t doff = 0; int32_t dcnt = 0, dasum = 0;
-        align_engine<CfgBig>(E, S.Abase, targetA, eA, Q, Bbase, targetB, eB, PMN_FORCED_FORWARD_ALIGN, &doff, &dcnt, &dasum);
-        if (lane == 0) {
-            ExBack b; b.fA = (int32_t)targetA; b.fB = (int32_t)targetB; b.ext_i = ext_i; b.ext_j = ext_j; b.doff = doff; b.dcnt = dcnt; b.asum = dasum; b.valid = 1;
-            X.back[k] = b;
-        }
-        __syncwarp();
+        if (X.entered[k] || !X.targeted[k]) continue;       // merged, most likely / a head: done beside wave 1 (k_ex_wave1_big)
+        back_job(E, X, (int)k);
     }
 }
 
@@ -1352,7 +1368,6 @@ __device__ void cur_append(Stitch &T, int type, uint32_t a, int cnt_field, int b
     if (T.E->lane == 0) {
         ExNode n; n.type = type; n.a = a; n.cnt = cnt_field; n.b = b; n.outoff = T.cur.ndelta; n.next = -1; n.alslot = T.S->alfirst + T.cur_slot; n.pad = 0;
         T.nodes[nd] = n;
-        if (T.cur.head >= 0) T.nodes[T.cur.tail].next = nd;
     }
     if (T.cur.head < 0) T.cur.head = nd;
     T.cur.tail = nd; T.cur.ndelta += ndeltas;
@@ -1512,7 +1527,12 @@ __global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32) k_ex_stitch(ExShared 
         ST_TICK(tk_window)
         // A fused cluster is stepped over.  Flags are never cleared, so the restart point moves along with it: every later
         // restart would walk over the same fused clusters again and end up where this one does.
-        if (X.do_extend && !target_reached && was_fused) { CurrCp++; PrevCp = CurrCp; continue; }
+        if (X.do_extend && !target_reached && was_fused) {
+            // on to the first cluster of the window that is not fused, in one step (only this warp writes the flags, and it
+            // mirrors them in s_fused)
+            const unsigned m = __ballot_sync(0xffffffffu, lane >= wi && (wbase + lane >= cend || !s_fused[wib][lane]));
+            CurrCp = wbase + (m ? __ffs((int)m) - 1 : 32); PrevCp = CurrCp; continue;
+        }
         if (!target_reached && X.do_simplify) {
             st_flush(T);
             const bool sh = st_is_shadowed(T, c);
@@ -1527,7 +1547,33 @@ __global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32) k_ex_stitch(ExShared 
         // a cluster that is merged a second time (reached as a target after it was fused) goes job by
         // job, so that every wave-1 job belongs to at most one range node
         const bool allow_bulk = !was_fused;
-        int CurrMp = 0; bool positioned = false;       // positioned: the alignment already ends on the last base of match CurrMp
+        // The common case in one step: the alignment arrives on the first match of a cluster that was never visited, every
+        // match -> next match job of the cluster reached its target and wave 1 ran the cluster-end job from the last match.
+        // What the loop below would do then is known from the cluster record alone: one range node for the inner jobs, one node
+        // for the end job — written as ONE node of type 2 that the flattening kernels take apart — and the new P / end / target.
+        bool fast = false;
+        if (target_reached && !was_fused && !c.anyfail && X.do_extend && c.e_dcnt >= 0 && T.cur.eA == c.sA0 && T.cur.eB == c.sB0) {
+            fast = true;
+            if (c.bulk_cnt > 0 || c.e_dcnt > 0) {
+                if (T.nNodes >= S.nodecap) T.fail = true;
+                else {
+                    const int nd = T.nNodes++;
+                    if (lane == 0) {
+                        ExNode n; n.type = 2; n.a = (uint32_t)c.mfirst; n.cnt = last; n.b = T.cur.P; n.outoff = T.cur.ndelta; n.next = CurrCp; n.alslot = S.alfirst + T.cur_slot; n.pad = 0;
+                        T.nodes[nd] = n;
+                        if (c.bulk_cnt > 0) X.markkey[c.mfirst] = ((unsigned long long)(c.mfirst + 1) << 32) | (unsigned)(S.nodefirst + nd + 1);
+                    }
+                    if (T.cur.head < 0) T.cur.head = nd;
+                    T.cur.tail = nd;
+                }
+            }
+            if (c.bulk_cnt > 0 && c.bulk_P >= 0) T.cur.P = c.bulk_P;
+            if (c.e_dcnt > 0) T.cur.P = c.eAl - 1 + c.e_asum;
+            T.cur.ndelta += c.bulk_cnt + c.e_dcnt;
+            T.cur.eA = c.endA; T.cur.eB = c.endB;
+            TargetCp = c.target; target_reached = c.e_reached;
+        }
+        int CurrMp = fast ? c.nm : 0; bool positioned = false;       // positioned: the alignment already ends on the last base of match CurrMp
         while (CurrMp < c.nm && !T.fail) {
             const int g = c.mfirst + CurrMp;
             int gA, gB, gL;                            // match g
@@ -1716,34 +1762,47 @@ __global__ void __launch_bounds__(256) k_ex_mcl(const uint32_t *__restrict__ pst
 
 __global__ void __launch_bounds__(256) k_ex_syntenies(const uint64_t *__restrict__ skeys, const uint32_t *__restrict__ sflag, const uint32_t *__restrict__ spos, int64_t np,
                                                      ExCluster *__restrict__ cl, ExSynteny *__restrict__ syn, const int64_t *__restrict__ roff, const int64_t *__restrict__ rlen,
-                                                     const int64_t *__restrict__ qoff, const int64_t *__restrict__ qlen, int64_t qn)
+                                                     const int64_t *__restrict__ qoff, const int64_t *__restrict__ qlen, int64_t qn, int64_t single_nm)
 {
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= np) return;
     const uint32_t s = spos[k] + sflag[k] - 1;     // inclusive count of synteny starts up to k, minus one
     cl[k].syn = (int32_t)s;
     if (sflag[k]) {
-        int64_t e = k + 1; while (e < np && !sflag[e]) e++;
+        // single_nm >= 0: one reference and one query record, hence one synteny that holds every cluster and all single_nm
+        // matches; its capacities are written here (no walk over the flags, no k_ex_syn_caps)
+        int64_t e = k + 1; if (single_nm >= 0) e = np; else while (e < np && !sflag[e]) e++;
         const int qrec = (int)(skeys[k] >> 47), rrec = (int)((skeys[k] >> 32) & 0x7fff);
         ExSynteny S;
         S.cfirst = (int32_t)k; S.nC = (int32_t)(e - k); S.qrec = qrec; S.rrec = rrec;
         S.Abase = roff[rrec]; S.lenA = rlen[rrec]; S.BbaseF = qoff[qrec]; S.BbaseR = qn - qoff[qrec] - qlen[qrec]; S.lenB = qlen[qrec];
         S.alfirst = 0; S.alcap = 0; S.nodefirst = 0; S.nodecap = 0;
+        if (single_nm >= 0) { S.alcap = (int32_t)single_nm; S.nodecap = (int32_t)(3 * single_nm + 8); }
         syn[s] = S;
     }
 }
 
-// capacities per synteny: its clusters are contiguous in the sorted order and so are the prefix
-// sums of their match counts (one thread: nS is small)
-__global__ void k_ex_syn_caps(ExSynteny *__restrict__ syn, int nS, const ExCluster *__restrict__ cl)
+// capacities per synteny (its clusters are contiguous in the sorted order): one block, a thread per synteny, a running
+// carry from one chunk of 256 syntenies to the next
+struct OpAddI32 { __device__ __forceinline__ int operator()(int a, int b) const { return a + b; } static __device__ __forceinline__ int identity() { return 0; } };
+__global__ void __launch_bounds__(256) k_ex_syn_caps(ExSynteny *__restrict__ syn, int nS, const ExCluster *__restrict__ cl)
 {
-    if (blockIdx.x || threadIdx.x) return;
-    int al = 0, nd = 0;
-    for (int s = 0; s < nS; s++) {
+    __shared__ int sm[32]; __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < nS; base += 256) {
+        const int s = base + threadIdx.x;
         int m = 0;
-        for (int k = syn[s].cfirst; k < syn[s].cfirst + syn[s].nC; k++) m += cl[k].nm;
-        syn[s].alfirst = al; syn[s].alcap = m; syn[s].nodefirst = nd; syn[s].nodecap = 3 * m + 8;
-        al += m; nd += 3 * m + 8;
+        if (s < nS) { const int f = syn[s].cfirst, e = f + syn[s].nC; for (int k = f; k < e; k++) m += cl[k].nm; }
+        const int inc = pmn_block_scan_incl(m, OpAddI32(), sm);
+        const int carry = carry_s;
+        if (s < nS) {
+            const int al = carry + inc - m;          // matches of the syntenies before this one
+            syn[s].alfirst = al; syn[s].alcap = m; syn[s].nodefirst = 3 * al + 8 * s; syn[s].nodecap = 3 * m + 8;
+        }
+        __syncthreads();
+        if (threadIdx.x == 255) carry_s = carry + inc;
+        __syncthreads();
     }
 }
 
@@ -1776,13 +1835,21 @@ __global__ void __launch_bounds__(256) k_ex_flat_nodes(ExShared X, int64_t ncap,
     while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (X.syn[mid].nodefirst <= t) lo = mid; else hi = mid - 1; }
     if (t - X.syn[lo].nodefirst >= X.syn_nal[X.nS + lo]) return;
     const ExNode n = X.nodes[t];
-    if (n.type != 0) return;
+    if (n.type == 1) return;
     const int k = slot2out[n.alslot];
     if (k < 0) return;
-    int32_t *out = dout + dstart[k] + n.outoff;
-    for (int i = 0; i < n.cnt; i++) {
-        int d = X.pool[n.a + i];
-        if (i == 0) d += d > 0 ? n.b : -n.b;
+    uint32_t src = n.a; int cnt = n.cnt, b = n.b, outoff = n.outoff;
+    if (n.type == 2) {
+        // the end job of a cluster taken in one step (k_ex_stitch): it follows the deltas of the inner jobs, and its first delta
+        // counts from the last indel before it
+        const ExCSum c = X.cs[n.next];
+        const int P = (c.bulk_cnt > 0 && c.bulk_P >= 0) ? c.bulk_P : n.b;
+        src = c.e_doff; cnt = c.e_dcnt; b = c.eAl - P - 1; outoff = n.outoff + c.bulk_cnt;
+    }
+    int32_t *out = dout + dstart[k] + outoff;
+    for (int i = 0; i < cnt; i++) {
+        int d = X.pool[src + i];
+        if (i == 0) d += d > 0 ? b : -b;
         out[i] = d;
     }
 }
@@ -1797,7 +1864,7 @@ __global__ void __launch_bounds__(256) k_ex_flat_ranges(ExShared X, const unsign
     if (!key) return;
     const ExNode n = X.nodes[(uint32_t)(key & 0xffffffffull) - 1];
     const int g0 = (int)n.a;
-    if (n.type != 1 || g < g0 || g >= n.cnt) return;
+    if (n.type == 0 || g < g0 || g >= n.cnt) return;
     const ExJob j = X.jobs[g];
     if (j.dcnt <= 0) return;
     const int k = slot2out[n.alslot];
@@ -1857,24 +1924,32 @@ __global__ void __launch_bounds__(256) k_ex_errors(ExShared X, const int32_t *__
                                                   const uint32_t *__restrict__ sa_, const uint32_t *__restrict__ sb_, unsigned long long *__restrict__ errs)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nd + nal) return;
-    int64_t k;
-    if (t < nd) {
-        int64_t lo = 0, hi = nal - 1;      // last alignment whose first delta is <= t
-        while (lo < hi) { int64_t mid = (lo + hi + 1) >> 1; if ((int64_t)dstart[mid] <= t) lo = mid; else hi = mid - 1; }
-        k = lo;
-    } else k = t - nd;
-    const ExSynteny S = X.syn[al_syn[k]];
-    const ExAlign a = X.al[al_slot[k]];
-    const PackedView &Q = a.dirB ? X.QR : X.QF;
-    const int64_t Ab = S.Abase - 1, Bb = (a.dirB ? S.BbaseR : S.BbaseF) - 1;
-    const uint32_t first = dstart[k];
-    const int64_t idx = t < nd ? t : (int64_t)dstart[k + 1];
-    const int64_t Apos = a.sA + (int64_t)(uint32_t)(sa_[idx] - sa_[first]), Bpos = a.sB + (int64_t)(uint32_t)(sb_[idx] - sb_[first]);
-    int64_t run; unsigned long long e = 0;
-    if (t < nd) { const int v = d[t]; run = (v < 0 ? -v : v) - 1; e = 1; } else run = (int64_t)a.eA - Apos + 1;
-    if (run > 0) e += (unsigned long long)run_mismatches(X.R, Ab + Apos, Q, Bb + Bpos, run);
-    if (e) atomicAdd(errs + k, e);
+    int64_t k = -1; unsigned long long e = 0;
+    if (t < nd + nal) {
+        if (t < nd) {
+            int64_t lo = 0, hi = nal - 1;      // last alignment whose first delta is <= t
+            while (lo < hi) { int64_t mid = (lo + hi + 1) >> 1; if ((int64_t)dstart[mid] <= t) lo = mid; else hi = mid - 1; }
+            k = lo;
+        } else k = t - nd;
+        const ExSynteny S = X.syn[al_syn[k]];
+        const ExAlign a = X.al[al_slot[k]];
+        const PackedView &Q = a.dirB ? X.QR : X.QF;
+        const int64_t Ab = S.Abase - 1, Bb = (a.dirB ? S.BbaseR : S.BbaseF) - 1;
+        const uint32_t first = dstart[k];
+        const int64_t idx = t < nd ? t : (int64_t)dstart[k + 1];
+        const int64_t Apos = a.sA + (int64_t)(uint32_t)(sa_[idx] - sa_[first]), Bpos = a.sB + (int64_t)(uint32_t)(sb_[idx] - sb_[first]);
+        int64_t run;
+        if (t < nd) { const int v = d[t]; run = (v < 0 ? -v : v) - 1; e = 1; } else run = (int64_t)a.eA - Apos + 1;
+        if (run > 0) e += (unsigned long long)run_mismatches(X.R, Ab + Apos, Q, Bb + Bpos, run);
+    }
+    // a warp lies inside one alignment almost always (there are few of them): one atomic per warp then, not 32 on one address
+    const int64_t k0 = __shfl_sync(0xffffffffu, k, 0);
+    if (__all_sync(0xffffffffu, e == 0 || k == k0)) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+        if ((threadIdx.x & 31) == 0 && e) atomicAdd(errs + k0, e);
+    }
+    else if (e) atomicAdd(errs + k, e);
 }
 
 __global__ void __launch_bounds__(256) k_ex_rows(ExShared X, const int32_t *__restrict__ al_syn, const uint32_t *__restrict__ al_slot, int64_t nal,
@@ -1961,7 +2036,8 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     k_ex_clusters<<<gp, 256, 0, st>>>(skeys, svals, np, nm, pfirst, mtag, cl, inv, sflag);
     k_ex_mcl<<<gm, 256, 0, st>>>(pstart, ppos, inv, nm, mcl);
     pmn_scan<uint32_t, OpAddU32, false>(sflag, spos, np, S.scan_tmp.as<uint32_t>(), st);
-    k_ex_syntenies<<<gp, 256, 0, st>>>(skeys, sflag, spos, np, cl, syn, roff, rlen, qoff, qlen, q->n);
+    const bool single_syn = nref == 1 && nqry == 1;
+    k_ex_syntenies<<<gp, 256, 0, st>>>(skeys, sflag, spos, np, cl, syn, roff, rlen, qoff, qlen, q->n, single_syn ? nm : (int64_t)-1);
     launches += 6;
     int nS = 1;                 // one reference record and one query record: one synteny
     if (nref > 1 || nqry > 1) {
@@ -1971,8 +2047,7 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
         c->syncs++;
         nS = (int)(tail[0] + tail[1]);
     }
-    k_ex_syn_caps<<<1, 32, 0, st>>>(syn, nS, cl);
-    launches++;
+    if (!single_syn) { k_ex_syn_caps<<<1, 256, 0, st>>>(syn, nS, cl); launches++; }
 
     // ---- E2/E3 storage
     // persistent blocks per SM of the warp-per-job and thread-per-job kernels.  Two each: with four, every worker held twice the
@@ -1992,7 +2067,7 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     const size_t arena_cap = S.arena_cap;
     const size_t ncap_al = (size_t)nm, ncap_nodes = 3 * (size_t)nm + 8 * (size_t)nS;
     const size_t npad = ((size_t)np + 63) / 64 * 64;
-    const size_t l_bytes = npad * 3 + 8 * (size_t)nS + 64 + 16 + sizeof(ExBack) * npad;      // fused, anyfail, entered, syn_nal (2 x nS), back
+    const size_t l_bytes = npad * 4 + 8 * (size_t)nS + 64 + 16 + sizeof(ExBack) * npad;      // fused, anyfail, entered, targeted, syn_nal (2 x nS), back
     if (S.ex_i.ensure(sizeof(ExJob) * (size_t)nm) || S.ex_j.ensure(sizeof(ExAlign) * ncap_al) || S.ex_k.ensure(sizeof(ExNode) * ncap_nodes) ||
         S.ex_pool.ensure(4 * pool_cap) || S.ex_arena.ensure(arena_cap + 4096) || S.ex_scores.ensure(4 * (size_t)EX_ROWS * EX_WCAP * (size_t)nslots) ||
         S.ex_tb.ensure((size_t)EX_TBW * (size_t)nslots_tb + 4096) || S.ex_counters.ensure(256) || S.ex_l.ensure(l_bytes) ||
@@ -2013,7 +2088,8 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     uint8_t *fused = S.ex_l.as<uint8_t>();
     uint8_t *anyfail = fused + npad;
     X.entered = anyfail + npad;
-    X.syn_nal = (int32_t *)(X.entered + npad);
+    X.targeted = X.entered + npad;
+    X.syn_nal = (int32_t *)(X.targeted + npad);
     X.back = (ExBack *)(X.syn_nal + ((2 * (size_t)nS + 16 + 3) & ~(size_t)3));      // 16-byte aligned: the records are read with vector loads
     long long *pkey = S.ex_tbidx.as<long long>();                          // nm+1
     unsigned long long *markkey = (unsigned long long *)(pkey + (nm + 1));  // nm+1
