@@ -1547,31 +1547,61 @@ __global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32) k_ex_stitch(ExShared 
         // a cluster that is merged a second time (reached as a target after it was fused) goes job by
         // job, so that every wave-1 job belongs to at most one range node
         const bool allow_bulk = !was_fused;
-        // The common case in one step: the alignment arrives on the first match of a cluster that was never visited, every
-        // match -> next match job of the cluster reached its target and wave 1 ran the cluster-end job from the last match.
-        // What the loop below would do then is known from the cluster record alone: one range node for the inner jobs, one node
-        // for the end job — written as ONE node of type 2 that the flattening kernels take apart — and the new P / end / target.
+        // The common case without the loop below: the alignment arrives on the first match of a cluster that was never visited,
+        // every match -> next match job of the cluster reached its target and wave 1 ran the cluster-end job from the last match.
+        // What the loop would do then is known from the cluster record alone: one range node for the inner jobs, one node for the
+        // end job — written as ONE node of type 2 that the flattening kernels take apart — and the new P / end / target.  When
+        // that end job reaches the next cluster of the window and the same holds there, the step after this one is known too:
+        // lane j takes cluster wbase + j, the run of clusters that hand over to their successor is found with two ballots, P and
+        // the delta offsets are prefix operations over the run, and every lane writes the node of its own cluster.
         bool fast = false;
         if (target_reached && !was_fused && !c.anyfail && X.do_extend && c.e_dcnt >= 0 && T.cur.eA == c.sA0 && T.cur.eB == c.sB0) {
             fast = true;
-            if (c.bulk_cnt > 0 || c.e_dcnt > 0) {
-                if (T.nNodes >= S.nodecap) T.fail = true;
-                else {
-                    const int nd = T.nNodes++;
-                    if (lane == 0) {
-                        ExNode n; n.type = 2; n.a = (uint32_t)c.mfirst; n.cnt = last; n.b = T.cur.P; n.outoff = T.cur.ndelta; n.next = CurrCp; n.alslot = S.alfirst + T.cur_slot; n.pad = 0;
-                        T.nodes[nd] = n;
-                        if (c.bulk_cnt > 0) X.markkey[c.mfirst] = ((unsigned long long)(c.mfirst + 1) << 32) | (unsigned)(S.nodefirst + nd + 1);
-                    }
-                    if (T.cur.head < 0) T.cur.head = nd;
-                    T.cur.tail = nd;
-                }
+            const int kj = wbase + lane;
+            const bool inw = lane >= wi && kj < cend;
+            ExCSum cj = c;
+            if (inw) cj = s_cs[wib][lane];
+            const bool elig = inw && !s_fused[wib][lane] && !cj.anyfail && cj.e_dcnt >= 0;
+            bool link = false;
+            if (elig && lane < 31 && kj + 1 < cend && cj.e_reached && cj.target == kj + 1) {
+                const int nA = s_cs[wib][lane + 1].sA0, nB = s_cs[wib][lane + 1].sB0;
+                link = cj.endA == nA && cj.endB == nB;
             }
-            if (c.bulk_cnt > 0 && c.bulk_P >= 0) T.cur.P = c.bulk_P;
-            if (c.e_dcnt > 0) T.cur.P = c.eAl - 1 + c.e_asum;
-            T.cur.ndelta += c.bulk_cnt + c.e_dcnt;
-            T.cur.eA = c.endA; T.cur.eB = c.endB;
-            TargetCp = c.target; target_reached = c.e_reached;
+            const unsigned eligm = __ballot_sync(0xffffffffu, elig);
+            const unsigned good = __ballot_sync(0xffffffffu, link) & (eligm >> 1);      // bit j: cluster j hands over to cluster j + 1, which qualifies
+            const int e = __ffs((int)(~good & (0xffffffffu << wi))) - 1;                // the run is [wi, e]; bit 31 of good is never set
+            const bool mine = lane >= wi && lane <= e;
+            const int dn = mine ? cj.bulk_cnt + cj.e_dcnt : 0;
+            const bool node = dn > 0;
+            const bool sets = mine && (cj.e_dcnt > 0 || (cj.bulk_cnt > 0 && cj.bulk_P >= 0));
+            const int pval = cj.e_dcnt > 0 ? cj.eAl - 1 + cj.e_asum : cj.bulk_P;
+            const unsigned nodem = __ballot_sync(0xffffffffu, node), setm = __ballot_sync(0xffffffffu, sets);
+            const unsigned below = (1u << lane) - 1u;
+            const unsigned sb = setm & below;                                           // clusters of the run before mine that leave a new P
+            int Pin = __shfl_sync(0xffffffffu, pval, sb ? 31 - __clz((int)sb) : 0);
+            if (!sb) Pin = T.cur.P;
+            int incl = dn;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            const int total_dn = __shfl_sync(0xffffffffu, incl, 31);
+            const int nnodes = __popc(nodem);
+            if (T.nNodes + nnodes > S.nodecap) T.fail = true;
+            else {
+                if (node) {
+                    const int nd = T.nNodes + __popc(nodem & below);
+                    ExNode n; n.type = 2; n.a = (uint32_t)cj.mfirst; n.cnt = cj.mfirst + cj.nm - 1; n.b = Pin; n.outoff = T.cur.ndelta + incl - dn; n.next = kj; n.alslot = S.alfirst + T.cur_slot; n.pad = 0;
+                    T.nodes[nd] = n;
+                    if (cj.bulk_cnt > 0) X.markkey[cj.mfirst] = ((unsigned long long)(cj.mfirst + 1) << 32) | (unsigned)(S.nodefirst + nd + 1);
+                }
+                if (mine) { fused[kj] = 1; s_fused[wib][lane] = 1; }
+                T.nNodes += nnodes;
+            }
+            if (setm) T.cur.P = __shfl_sync(0xffffffffu, pval, 31 - __clz((int)setm));
+            T.cur.ndelta += total_dn;
+            T.cur.eA = __shfl_sync(0xffffffffu, cj.endA, e); T.cur.eB = __shfl_sync(0xffffffffu, cj.endB, e);
+            TargetCp = __shfl_sync(0xffffffffu, cj.target, e); target_reached = __shfl_sync(0xffffffffu, cj.e_reached, e);
+            CurrCp = wbase + e;                     // the last cluster of the run; what follows marks it (again) and moves on from it
+            __syncwarp();
         }
         int CurrMp = fast ? c.nm : 0; bool positioned = false;       // positioned: the alignment already ends on the last base of match CurrMp
         while (CurrMp < c.nm && !T.fail) {
@@ -1682,7 +1712,7 @@ __global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32) k_ex_stitch(ExShared 
         tk_match += clock64() - tk;
 #endif
         if (TargetCp == cend) target_reached = 0;
-        if (lane == 0) { fused[CurrCp] = 1; s_fused[wib][wi] = 1; }
+        if (lane == 0) { fused[CurrCp] = 1; s_fused[wib][CurrCp - wbase] = 1; }
         __syncwarp();
         if (!target_reached) CurrCp = ++PrevCp; else CurrCp = TargetCp;
     }

@@ -157,6 +157,8 @@ static int sched_run(pmn_sched *s, int ng, const char *const *fasta, const size_
         if (const char *e = getenv("PMN_SCHED_LIVE_INDEXES")) MAX_LIVE_INDEXES = std::max(1, atoi(e));
     }
     int live_indexes = 0;                      // guarded by s->bmu
+    int builds_done = 0;                       // opening builds finished (guarded by s->bmu)
+    static const int build_width = getenv("PMN_SCHED_BUILD_WIDTH") ? std::max(0, atoi(getenv("PMN_SCHED_BUILD_WIDTH"))) : 0;
     std::atomic<int> failed{0};                // some worker gave up: nobody may keep waiting for an index slot
     std::vector<int> first_refs;               // the first distinct references in processing order that have no index yet
     for (int k = 0; k < np && (int)first_refs.size() < MAX_LIVE_INDEXES; k++) {
@@ -207,10 +209,15 @@ static int sched_run(pmn_sched *s, int ng, const char *const *fasta, const size_
                 // at most MAX_LIVE_INDEXES indexes built by this run are alive at a time: pairs are taken in reference order, so the
                 // holders of the oldest ones finish without needing another; bounds the memory (8.25 B/base each) and keeps the
                 // number of index images the pool ever holds fixed, i.e. no allocation in later batches
-                { std::unique_lock<std::mutex> lk(s->bmu); s->bcv.wait(lk, [&] { return live_indexes < MAX_LIVE_INDEXES || failed.load(); }); if (failed.load()) return nullptr; live_indexes++; }
+                // PMN_SCHED_BUILD_WIDTH = n: at most n of the opening builds run at a time, in reference order (0 = all at once)
+                const auto it = std::find(first_refs.begin(), first_refs.end(), r);
+                const int pos = build_width > 0 && it != first_refs.end() ? (int)(it - first_refs.begin()) : -1;
+                { std::unique_lock<std::mutex> lk(s->bmu); s->bcv.wait(lk, [&] { return (live_indexes < MAX_LIVE_INDEXES && (pos < 0 || builds_done + build_width > pos)) || failed.load(); }); if (failed.load()) return nullptr; live_indexes++; }
                 BorrowedScratch b(s, c); OnStream on(c, use_prio ? pmn_ctx_prio_stream(c, level) : nullptr);
                 pmn_index *x = nullptr;
-                if (pmn_index_build(c, rs, &x)) { std::lock_guard<std::mutex> lk(s->bmu); live_indexes--; s->bcv.notify_all(); return nullptr; }
+                const int rc = pmn_index_build(c, rs, &x);
+                if (pos >= 0 || rc) { std::lock_guard<std::mutex> lk(s->bmu); if (pos >= 0) builds_done++; if (rc) live_indexes--; s->bcv.notify_all(); }
+                if (rc) return nullptr;
                 return (void *)x; });
         };
         // the first MAX_LIVE_INDEXES references of the batch are indexed side by side by the first workers, so that the batch
