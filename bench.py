@@ -416,7 +416,8 @@ def run_gpu(args):
             "extra_weak": weak,
             "gpu_launches": cnt_res["launches"], "launches_per_pair": launches_pair,
             "host_syncs_per_pair": cnt_res["syncs"] / max(1, npairs_rank * args.steps),
-            "step_wall_ms": {"resident": spread(cnt_res["walls"]), "e2e": spread(cnt_e2e["walls"]), "e2e_worker": spread(cnt_wrk["walls"])},
+            "step_wall_ms": {"resident": spread(cnt_res["walls"]), "e2e": spread(cnt_e2e["walls"]), "e2e_worker": spread(cnt_wrk["walls"]),
+                             "every_step": {"resident": cnt_res["walls"], "e2e": cnt_e2e["walls"], "e2e_worker": cnt_wrk["walls"]}},
             "device_allocations_in_timed_region": {"resident": cnt_res["allocs"], "e2e": cnt_e2e["allocs"]},
             "ms_per_step_by_rank": {"resident": cnt_res["ranks_ms"], "e2e": cnt_e2e["ranks_ms"]}, "host_cores": os.cpu_count(),
             "clocks": clocks, "device_memory_used_gb": round(mem_used_gb, 1),

@@ -97,8 +97,8 @@ struct ExShared {                       // everything the device code needs, pas
     int32_t *tsorted;                   // thread-per-job alignments in bin order (count = counters[10], warp cursor = counters[11])
     uint8_t *tscratch;                  // TPJ_SLOT_BYTES per resident warp of k_ex_wave1_tpj
     ExBack *back;                       // per cluster (wave 2), valid = 0 where none was computed
-    uint8_t *entered;                   // per cluster: some cluster's end job reached it (it will most likely be merged, not started)
-    uint8_t *targeted;                  // per cluster: some cluster's end job aims at it (k_ex_jobdesc); the others start alignments for certain
+    int32_t *aimers, *aimfail;          // per cluster: end jobs that aim at it (k_ex_jobdesc) / that did not reach it (k_ex_wave1_big)
+    const int4 *tgt;                    // per cluster: (target A, target B, target cluster) of its end job (k_ex_targets)
     int4 *dbg; unsigned dbg_cap;        // PMN_JOBLOG: two int4 per engine call (cursor = counters[15])
 };
 
@@ -814,6 +814,58 @@ __device__ int get_forward_target_cluster(const ExShared &X, int cp, int end, in
     return best;
 }
 
+// getForwardTargetCluster for every cluster at once: one warp per cluster, 32 candidates per step.  The sequential original
+// (get_forward_target_cluster above, still used by the stitcher) stops at the first "close enough" cluster and otherwise keeps the
+// first strict improvement of dist = 2*greater - lesser; a cluster in front of a rearrangement walks the whole rest of its
+// synteny, which made one thread per cluster the long pole of k_ex_jobdesc (70 us of a 5 Mbp pair).
+__global__ void __launch_bounds__(256) k_ex_targets(ExShared X, int4 *__restrict__ tgt)
+{
+    const int cp = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (cp >= X.nC) return;
+    const ExCluster c = X.cl[cp];
+    const ExSynteny S = X.syn[c.syn];
+    const int end = S.cfirst + S.nC;
+    const int last = c.mfirst + c.nm - 1;
+    const int64_t sA = (int64_t)X.mA[last] + X.mL[last] - 1, sB = (int64_t)X.mB[last] + X.mL[last] - 1;
+    int64_t targetA = S.lenA, targetB = S.lenB;
+    long long dist = targetA - sA < targetB - sB ? targetA - sA : targetB - sB;
+    int best = end;
+    for (int base = cp + 1; base < end; base += 32) {
+        const int ci = base + lane;
+        bool valid = false, close = false; long long score = 0; int64_t eA = 0, eB = 0;
+        if (ci < end) {
+            const ExCluster t = X.cl[ci];
+            if (t.dir == c.dir) {
+                eA = X.mA[t.mfirst]; eB = X.mB[t.mfirst];
+                const int tl = t.mfirst + t.nm - 1;
+                if ((eA < sA || eB < sB) && X.mA[tl] >= sA && X.mB[tl] >= sB)
+                    for (int k = t.mfirst; k <= tl && (eA < sA || eB < sB); k++) { eA = X.mA[k]; eB = X.mB[k]; }
+                if (eA >= sA && eB >= sB) {
+                    valid = true;
+                    int64_t greater, lesser;
+                    if (eA - sA > eB - sB) { greater = eA - sA; lesser = eB - sB; } else { lesser = eA - sA; greater = eB - sB; }
+                    close = greater < X.breaklen || lesser * PMN_GOOD_SCORE + (greater - lesser) * PMN_CONT_GAP_SCORE >= 0;
+                    score = (greater << 1) - lesser;
+                }
+            }
+        }
+        const unsigned cb = __ballot_sync(0xffffffffu, close);
+        const int F = cb ? __ffs((int)cb) - 1 : 32;
+        long long key = (valid && !close && lane < F) ? score * 32 + lane : LLONG_MAX;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const long long k2 = __shfl_xor_sync(0xffffffffu, key, o); if (k2 < key) key = k2; }
+        int src = -1;
+        if (key != LLONG_MAX && (key >> 5) < dist) { dist = key >> 5; src = (int)(key & 31); }
+        if (cb) src = F;
+        if (src >= 0) {
+            best = base + src;
+            targetA = __shfl_sync(0xffffffffu, eA, src); targetB = __shfl_sync(0xffffffffu, eB, src);
+        }
+        if (cb) break;
+    }
+    if (lane == 0) tgt[cp] = make_int4((int)targetA, (int)targetB, best, 0);
+}
+
 // the alignment-engine part of extendForward, from (eA, eB) towards (targetA, targetB)
 __device__ int forward_job(const Eng &E, const ExSynteny &S, int dirB, int64_t eA, int64_t eB, int64_t targetA, int64_t targetB, unsigned m_o, ExJob &out)
 {
@@ -908,12 +960,12 @@ __global__ void __launch_bounds__(256) k_ex_jobdesc(ExShared X, ExJobDesc *__res
             d.m_o = -1; d.tA = d.tB = 0; d.target = -1;
             descB[g] = d;                                       // the last match has no inner job
             if (X.do_extend) {
-                int64_t targetA = S.lenA, targetB = S.lenB;
                 const int end = S.cfirst + S.nC;
-                const int tc = get_forward_target_cluster(X, k, end, targetA, targetB);
-                d.tA = (int32_t)targetA; d.tB = (int32_t)targetB; d.target = tc;
+                const int4 t4 = X.tgt[k];                       // getForwardTargetCluster, one warp per cluster (k_ex_targets)
+                const int tc = t4.z;
+                d.tA = t4.x; d.tB = t4.y; d.target = tc;
                 d.m_o = PMN_FORWARD_ALIGN | (tc == end ? PMN_OPTIMAL_BIT : 0);
-                if (tc < end) X.targeted[tc] = 1;               // some cluster's end job aims at tc (see k_ex_wave1_big, heads)
+                if (tc < end) atomicAdd(X.aimers + tc, 1);      // one more end job aims at tc (see k_ex_wave1_big)
             }
             descA[k] = d;
         }
@@ -996,10 +1048,133 @@ __device__ __noinline__ void eng_small_full(const Eng &E, const ExShared &X, con
     __syncwarp();
 }
 
+// A forward alignment (not OPTIMAL) over a window of up to 100 x 100 bases with N + M <= breaklen, one WARP: what the
+// thread-per-job kernel does for such a window with one thread (k_ex_wave1_tpj: the full matrix is the engine's answer while no
+// cell falls 3*breaklen below the running high score, checked by the same sufficient condition) laid out as in
+// eng_forced_systolic: lane l owns the strip of columns 8l+1 .. 8l+8, handles row t - l at step t and hands the right edge of
+// its strip to lane l + 1 by one shuffle.  A 100 x 100 window is 113 steps of one row-strip each instead of 1313 row-strips of
+// one thread — the largest windows were the tail of the thread-per-job kernel (0.6 ms of a 5 Mbp pair, 9 % of the SMs busy) —
+// and from 64 x 64 on it is also fewer instructions (60 per step against 8.5 per row-strip and lane).  The traceback words
+// ([row][strip], 8 cells each) stay in the warp's score ring (row 7, the reversed deltas, is left out), the walk back runs on
+// shared memory.  Returns false when the condition fails: the caller runs the general engine.
+template <class Cfg>
+__device__ __noinline__ bool eng_mid_full(const Eng &E, const ExShared &X, const ExJobDesc &d, int N, int M, uint32_t *doff, int32_t *dcnt, int32_t *dasum)
+{
+    const int lane = E.lane;
+    int32_t *ring = eng_warp_smem<Cfg>();
+    int32_t *rev_s = ring + Cfg::REV_OFF;
+    const PackedView &Q = d.dir ? X.QR : X.QF;
+    const int64_t Apos0 = d.Abase + d.eA - 1, Bpos0 = d.Bbase + d.eB - 1;       // 0-based positions of window row 1 / column 1
+    const int strips = (M + 7) >> 3;
+    auto tbword = [&](int w) -> uint2 * { int off = w * 8; if (off >= Cfg::REV_OFF * 4) off += Cfg::REV_N * 4; return (uint2 *)((char *)ring + off); };
+    *doff = 0; *dcnt = 0; *dasum = 0;
+    const int j0 = lane * 8;
+    const bool have = lane < strips;
+    const unsigned qn = have ? tpj_query_nibbles(Q, Bpos0 + j0, M - j0) : 0x44444444u;
+    int uI[8], ug[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) { uI[c] = SYS_NEG; ug[c] = SYS_NEG; }
+    int prev_bmc = SYS_NEG;
+    int oD = SYS_NEG, oH = SYS_NEG, oC = SYS_NEG;           // right edge of the row this lane finished last: (D, max(I+1, M+2), cell maximum)
+    uint64_t aw = 0; uint32_t ax = 0;
+    int slack = INT32_MAX;
+    const int steps = N + strips;
+    __syncwarp();
+    for (int t = 0; t < steps; t++) {
+        int lD = __shfl_up_sync(0xffffffffu, oD, 1), hl = __shfl_up_sync(0xffffffffu, oH, 1), bmc = __shfl_up_sync(0xffffffffu, oC, 1);
+        const int i = t - lane;
+        const bool act = have && i >= 0 && i <= N;
+        if (lane == 0 && act) {
+            if (i == 0) { lD = SYS_NEG; hl = 2; bmc = 2; }                           // cell (0,0) = MAT 0
+            else { const int v = 4 * (PMN_OPEN_GAP_SCORE + PMN_CONT_GAP_SCORE * (i - 1)) + PMN_ST_INS; lD = SYS_NEG; hl = v; bmc = v; }
+        }
+        if (act) {
+            unsigned an = 8;
+            if (i >= 1) {
+                if (((i - 1) & 31) == 0) { aw = pmn_window64(X.R.w, Apos0 + i - 1); ax = X.R.has_x ? pmn_xwindow32(X.R.xm, Apos0 + i - 1) : 0u; }
+                an = (unsigned)(aw >> 62) | ((ax >> 31) << 3);
+                aw <<= 2; ax <<= 1;
+            }
+            const unsigned x = (an * 0x11111111u) ^ qn;
+            const int rowoff = -6 * (i + j0 + 8);
+            int dmc = prev_bmc;
+            prev_bmc = bmc;
+            unsigned t0 = 0, t1 = 0; int mc = 0;
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                const int sc = (x & (0xfu << (4 * c))) ? 4 * PMN_BAD_SCORE : 4 * PMN_GOOD_SCORE;
+                const int mD = __viaddmax_s32(lD, 4 * PMN_CONT_GAP_SCORE + PMN_ST_DEL, hl + 4 * PMN_OPEN_GAP_SCORE);
+                const int mI = __viaddmax_s32(uI[c], 4 * PMN_CONT_GAP_SCORE + PMN_ST_INS, ug[c] + 4 * PMN_OPEN_GAP_SCORE);
+                const int mM = dmc + sc;
+                dmc = __viaddmax_s32(uI[c], PMN_ST_INS, ug[c]);
+                const int vD = mD & ~3, vI = mI & ~3, vM2 = (mM & ~3) + PMN_ST_MAT;
+                hl = __viaddmax_s32(vI, PMN_ST_INS, vM2);
+                mc = max(hl, vD);
+                uI[c] = vI; ug[c] = max(vD, vM2);
+                lD = vD;
+                slack = __viaddmin_s32(mc, rowoff, slack);
+                const unsigned tbits = ((unsigned)mD & 3u) | (((unsigned)mI & 3u) << 2) | (((unsigned)mM & 3u) << 4);
+                if (c < 4) t0 |= tbits << (8 * c); else t1 |= tbits << (8 * (c - 4));
+            }
+            *tbword(i * strips + lane) = make_uint2(t0, t1);
+            oD = lD; oH = hl; oC = mc;
+        }
+    }
+    slack = __reduce_min_sync(0xffffffffu, slack);
+    if (slack < 3 - 4 * PMN_GOOD_SCORE * X.breaklen) return false;              // the same bound as k_ex_wave1_tpj
+    int ms_fin;
+    {   // the finish cell (N, M) sits in column (M-1) & 7 of lane (M-1) >> 3
+        const int c = (M - 1) & 7;
+        int mcf = 0;
+#pragma unroll
+        for (int cc = 0; cc < 8; cc++) if (cc == c) mcf = __viaddmax_s32(uI[cc], PMN_ST_INS, ug[cc]);
+        ms_fin = __shfl_sync(0xffffffffu, mcf, (M - 1) >> 3) & 3;
+    }
+    if (lane == 0) { atomicAdd(X.counters + 2, (unsigned long long)((N + 1) * (M + 1) - 1)); atomicAdd(X.counters + 3, 1ull); }
+    __syncwarp();
+    int nrev = 0;
+    if (lane == 0) {
+        int i = N, j = M, st = ms_fin, pending = 0, run = 0;
+        while (i > 0 || j > 0) {
+            unsigned b;
+            if (j == 0) b = (unsigned)(i == 1 ? PMN_ST_MAT : PMN_ST_INS) << 2;          // column 0: INS from above; cell (1,0) comes from (0,0) MAT
+            else {
+                const uint2 wv = *tbword(i * strips + ((j - 1) >> 3));
+                const int c = (j - 1) & 7;
+                b = ((c < 4 ? wv.x : wv.y) >> (8 * (c & 3))) & 0x3fu;
+            }
+            if (st == PMN_ST_MAT) { run++; st = (b >> 4) & 3; i--; j--; }
+            else {
+                if (pending) rev_s[nrev++] = pending * (run + 1);
+                run = 0;
+                if (st == PMN_ST_INS) { pending = 1; st = (b >> 2) & 3; i--; }
+                else { pending = -1; st = b & 3; j--; }
+            }
+        }
+        if (pending) rev_s[nrev++] = pending * (run + 1);
+    }
+    nrev = __shfl_sync(0xffffffffu, nrev, 0);
+    __syncwarp();
+    if (nrev > 0) {
+        unsigned long long at = 0;
+        if (lane == 0) at = atomicAdd(X.counters + 0, (unsigned long long)nrev);
+        at = __shfl_sync(0xffffffffu, at, 0);
+        if (at + (unsigned long long)nrev > X.pool_cap) { if (lane == 0) atomicOr(X.counters + 4, (unsigned long long)EX_ERR_POOL); return true; }
+        int asum = 0;
+        for (int k = lane; k < nrev; k += 32) { const int dv = rev_s[nrev - 1 - k]; X.pool[at + k] = dv; asum += dv > 0 ? dv : -dv - 1; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) asum += __shfl_xor_sync(0xffffffffu, asum, o);
+        *doff = (uint32_t)at; *dcnt = nrev; *dasum = asum;
+    }
+    __syncwarp();
+    return true;
+}
+
 // returns false when the alignment is too wide for this kernel's layout (never for CfgBig)
 template <class Cfg>
-__device__ __forceinline__ bool wave1_run(const Eng &E, const ExShared &X, const ExJobDesc &d)
+__device__ __forceinline__ bool wave1_run(const Eng &E, const ExShared &X, const ExJobDesc &d, int *reached_out = nullptr, bool allow_mid = true)
 {
+    if (reached_out) *reached_out = 1;
     {
         const int N = d.tA - d.eA + 1, M = d.tB - d.eB + 1;
         if (d.m_o == PMN_FORWARD_ALIGN && N >= 1 && M >= 1 && N <= 31 && M <= 31 && X.breaklen >= 134) {
@@ -1012,6 +1187,19 @@ __device__ __forceinline__ bool wave1_run(const Eng &E, const ExShared &X, const
             return true;
         }
     }
+    if (Cfg::MAXK >= 8 && allow_mid) {        // not for what the thread-per-job kernel handed back: the same condition failed there
+        const int N = d.tA - d.eA + 1, M = d.tB - d.eB + 1;
+        if (d.m_o == PMN_FORWARD_ALIGN && N >= 1 && M >= 1 && N <= TPJ_MAXDIM && M <= TPJ_MAXDIM && N + M <= X.breaklen) {
+            uint32_t doff; int32_t dcnt, dasum;
+            if (eng_mid_full<Cfg>(E, X, d, N, M, &doff, &dcnt, &dasum)) {
+                if (E.lane == 0) {
+                    ExJob r; r.endA = d.tA; r.endB = d.tB; r.dcnt = dcnt; r.doff = doff; r.reached = 1; r.valid = 1; r.asum = dasum; r.target = d.target;
+                    X.jobs[d.g] = r;
+                }
+                return true;
+            }
+        }
+    }
     int64_t targetA = d.tA, targetB = d.tB; unsigned m_o = (unsigned)d.m_o;
     int overflow = 0;
     if (targetA - d.eA + 1 > PMN_MAX_ALIGNMENT_LENGTH) { targetA = d.eA + PMN_MAX_ALIGNMENT_LENGTH - 1; overflow = 1; m_o |= PMN_OPTIMAL_BIT; }
@@ -1020,6 +1208,7 @@ __device__ __forceinline__ bool wave1_run(const Eng &E, const ExShared &X, const
     int reached = align_engine<Cfg>(E, d.Abase, d.eA, targetA, d.dir ? X.QR : X.QF, d.Bbase, d.eB, targetB, m_o, &doff, &dcnt, &dasum);
     if (reached < 0) return false;
     if (reached && overflow) reached = 0;
+    if (reached_out) *reached_out = reached;
     if (E.lane == 0) {
         ExJob r; r.endA = (int32_t)targetA; r.endB = (int32_t)targetB; r.dcnt = dcnt; r.doff = doff; r.reached = reached; r.valid = 1; r.asum = dasum; r.target = d.target;
         X.jobs[d.g] = r;
@@ -1027,8 +1216,12 @@ __device__ __forceinline__ bool wave1_run(const Eng &E, const ExShared &X, const
     return true;
 }
 
-// The backward extension of the first match of cluster k, ahead of the stitcher (see k_ex_wave2).
-__device__ __forceinline__ void back_job(const Eng &E, const ExShared &X, int k)
+// The backward extension of the first match of cluster k, ahead of the stitcher: every cluster that no end job reaches starts a
+// new alignment there (unless it turns out to be shadowed).  The search runs in the largest window extendBackward can ask
+// for (towards the sequence starts, OPTIMAL); the stitcher takes the result when its own window, bounded by the
+// target alignment, contains every cell this search evaluated (ext_i, ext_j) -- then the two runs are the same
+// cell for cell -- and runs the engine itself otherwise.
+__device__ __noinline__ void back_job(const Eng &E, const ExShared &X, int k)
 {
     const ExCluster c = X.cl[k];
     const ExSynteny S = X.syn[c.syn];
@@ -1063,8 +1256,10 @@ __global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32, 3) k_ex_wave1_big(ExS
     const int lane = E.lane;
     // pass 0 (runs beside the thread-per-job kernel): the heads, cluster ends + the windows k_ex_jobdesc found too large;
     // pass 1 (after it): the windows the thread-per-job kernel handed back.
-    // Heads: a cluster no end job aims at starts an alignment in the stitcher whatever wave 1 finds, so its backward extension
-    // (two engine runs, as long as the longest jobs of this pass) runs here, first, instead of in a wave of its own afterwards.
+    // Backward extensions (round 1: a wave of its own behind wave 1, 0.2-0.3 ms of every pair): a cluster no end job aims at
+    // (aimers == 0) starts an alignment whatever wave 1 finds, so its backward extension runs here, first — two engine runs, as
+    // long as the longest jobs of this pass.  A cluster that is aimed at starts one only when every end job aiming at it fails
+    // to reach it: the warp whose end job is the last of them to fail (aimfail == aimers) runs the backward extension at once.
     const unsigned long long nH = (pass == 0 && X.do_extend) ? (unsigned long long)X.nC : 0ull;
     const unsigned long long nA = nH, nO = X.counters[pass ? 12 : 7];
     const int32_t *list = pass ? X.overflow2 : X.overflow;
@@ -1073,10 +1268,21 @@ __global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32, 3) k_ex_wave1_big(ExS
         if (lane == 0) k = atomicAdd(X.counters + (pass ? 13 : 5), 1ull);
         k = __shfl_sync(0xffffffffu, k, 0);
         if (k >= nH + nA + nO) break;
-        if (k < nH) { if (!X.targeted[k]) { E.kid = 3; back_job(E, X, (int)k); E.kid = 1; } continue; }
+        if (k < nH) { if (X.aimers[k] == 0) { E.kid = 3; back_job(E, X, (int)k); E.kid = 1; } continue; }
         k -= nH;
-        const ExJobDesc d = k < nA ? X.descA[k] : X.descB[list[k - nA]];
-        if (d.m_o >= 0) wave1_run<CfgBig>(E, X, d);
+        if (k >= nA) { const ExJobDesc d = X.descB[list[k - nA]]; if (d.m_o >= 0) wave1_run<CfgBig>(E, X, d, nullptr, pass == 0); continue; }
+        const ExJobDesc d = X.descA[k];
+        if (d.m_o < 0) continue;
+        int reached = 1;
+        wave1_run<CfgBig>(E, X, d, &reached);
+        if (reached) continue;
+        const ExCluster c = X.cl[k];
+        const ExSynteny S = X.syn[c.syn];
+        if (d.target < 0 || d.target >= S.cfirst + S.nC) continue;
+        int last = 0;
+        if (lane == 0) last = atomicAdd(X.aimfail + d.target, 1) + 1 == X.aimers[d.target];
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) { E.kid = 3; back_job(E, X, d.target); E.kid = 1; }
     }
 }
 
@@ -1317,27 +1523,6 @@ __global__ void __launch_bounds__(256) k_ex_csum(ExShared X, ExCSum *__restrict_
     s.bulk_cnt = (int32_t)(X.dcnt_ex[l] - X.dcnt_ex[f]);
     s.bulk_P = c.nm > 1 ? range_last_P(X, f, l - 1, -1) : -1;
     out[k] = s;
-    const ExSynteny S = X.syn[c.syn];
-    if (j.valid && j.reached && j.target >= 0 && j.target < S.cfirst + S.nC) X.entered[j.target] = 1;
-}
-
-// Wave 2: the backward extension of every cluster that no end job reached (those start new alignments in the
-// stitcher unless they turn out to be shadowed).  The search runs in the largest window extendBackward can ask
-// for (towards the sequence starts, OPTIMAL); the stitcher takes the result when its own window, bounded by the
-// target alignment, contains every cell this search evaluated (ext_i, ext_j) -- then the two runs are the same
-// cell for cell -- and runs the engine itself otherwise.
-__global__ void __launch_bounds__(EX_WARPS_PER_BLOCK * 32, 3) k_ex_wave2(ExShared X)
-{
-    Eng E = make_eng(X, nullptr); E.kid = 3;
-    const int lane = E.lane;
-    for (;;) {
-        unsigned long long k = 0;
-        if (lane == 0) k = atomicAdd(X.counters + 14, 1ull);
-        k = __shfl_sync(0xffffffffu, k, 0);
-        if (k >= (unsigned long long)X.nC) break;
-        if (X.entered[k] || !X.targeted[k]) continue;       // merged, most likely / a head: done beside wave 1 (k_ex_wave1_big)
-        back_job(E, X, (int)k);
-    }
 }
 
 // ------------------------------------------------------------------------------------ E3: stitch
@@ -2097,7 +2282,7 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     const size_t arena_cap = S.arena_cap;
     const size_t ncap_al = (size_t)nm, ncap_nodes = 3 * (size_t)nm + 8 * (size_t)nS;
     const size_t npad = ((size_t)np + 63) / 64 * 64;
-    const size_t l_bytes = npad * 4 + 8 * (size_t)nS + 64 + 16 + sizeof(ExBack) * npad;      // fused, anyfail, entered, targeted, syn_nal (2 x nS), back
+    const size_t l_bytes = npad * 2 + 8 * npad + 8 * (size_t)nS + 64 + 16 + sizeof(ExBack) * npad;      // fused, anyfail, aimers, aimfail, syn_nal (2 x nS), back
     if (S.ex_i.ensure(sizeof(ExJob) * (size_t)nm) || S.ex_j.ensure(sizeof(ExAlign) * ncap_al) || S.ex_k.ensure(sizeof(ExNode) * ncap_nodes) ||
         S.ex_pool.ensure(4 * pool_cap) || S.ex_arena.ensure(arena_cap + 4096) || S.ex_scores.ensure(4 * (size_t)EX_ROWS * EX_WCAP * (size_t)nslots) ||
         S.ex_tb.ensure((size_t)EX_TBW * (size_t)nslots_tb + 4096) || S.ex_counters.ensure(256) || S.ex_l.ensure(l_bytes) ||
@@ -2114,12 +2299,12 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     X.gscore = S.ex_scores.as<int32_t>(); X.tbpriv = S.ex_tb.as<uint8_t>();
     X.counters = S.ex_counters.as<unsigned long long>();
     X.breaklen = o->breaklen; X.do_extend = o->do_extend; X.do_simplify = o->do_simplify;
-    { static const int cells = getenv("PMN_TPJ_CELLS") ? atoi(getenv("PMN_TPJ_CELLS")) : TPJ_MAXDIM * TPJ_MAXDIM; X.tpj_cells = cells; }
+    { static const int cells = getenv("PMN_TPJ_CELLS") ? atoi(getenv("PMN_TPJ_CELLS")) : 0; X.tpj_cells = cells > 0 ? cells : c->tpj_cells; }       // larger windows: one warp each (eng_mid_full)
     uint8_t *fused = S.ex_l.as<uint8_t>();
     uint8_t *anyfail = fused + npad;
-    X.entered = anyfail + npad;
-    X.targeted = X.entered + npad;
-    X.syn_nal = (int32_t *)(X.targeted + npad);
+    X.aimers = (int32_t *)(anyfail + npad);
+    X.aimfail = X.aimers + npad;
+    X.syn_nal = X.aimfail + npad;
     X.back = (ExBack *)(X.syn_nal + ((2 * (size_t)nS + 16 + 3) & ~(size_t)3));      // 16-byte aligned: the records are read with vector loads
     long long *pkey = S.ex_tbidx.as<long long>();                          // nm+1
     unsigned long long *markkey = (unsigned long long *)(pkey + (nm + 1));  // nm+1
@@ -2129,9 +2314,11 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     ExCSum *cs = S.cl_l.as<ExCSum>();      // the clustering scratch is free by now
     X.cs = cs;
     PMN_CUDA_OK(cudaMemsetAsync(markkey, 0, 8 * (size_t)(nm + 1), st));
-    if (S.ex_desc.ensure(sizeof(ExJobDesc) * (size_t)(np + nm + 1) + 8 * (size_t)(nm + 1))) return -3;
+    if (S.ex_desc.ensure(sizeof(ExJobDesc) * (size_t)(np + nm + 1) + 8 * (size_t)(nm + 2) + 16 * (size_t)np + 16)) return -3;
     ExJobDesc *descA = S.ex_desc.as<ExJobDesc>(), *descB = descA + np;
     X.descA = descA; X.descB = descB; X.overflow = (int32_t *)(descB + nm + 1); X.overflow2 = X.overflow + (nm + 1);
+    int4 *tgt = (int4 *)(((uintptr_t)(X.overflow2 + (nm + 1)) + 15) & ~(uintptr_t)15);
+    X.tgt = tgt;
     // thread-per-job windows: (bin, rank) per match, bin counters and starts, the sorted list, per-warp scratch
     const int blocks_tpj = c->sm_count * tpj_bps;
     const size_t tkey_bytes = 8 * (size_t)nm, tbin_bytes = 4 * (size_t)(2 * TPJ_BINS + 2);
@@ -2152,10 +2339,10 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     if (!c->smem_attr_set) {
         PMN_CUDA_OK(cudaFuncSetAttribute(k_ex_wave1_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PMN_CUDA_OK(cudaFuncSetAttribute(k_ex_stitch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PMN_CUDA_OK(cudaFuncSetAttribute(k_ex_wave2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         c->smem_attr_set = true;
     }
     int b1 = blocks1; { int64_t need = (nm + EX_WARPS_PER_BLOCK - 1) / EX_WARPS_PER_BLOCK; if (need < b1) b1 = (int)need; if (b1 < 1) b1 = 1; }
+    if (o->do_extend) { k_ex_targets<<<(unsigned)((np + 7) / 8), 256, 0, st>>>(X, tgt); launches++; }
     k_ex_jobdesc<<<gm, 256, 0, st>>>(X, descA, descB);
     PMN_CUDA_OK(cudaEventRecord(c->ev[8], st));
     // the warp-per-job kernel (cluster ends: few, long) runs beside the thread-per-job kernel on the context's second stream
@@ -2179,7 +2366,6 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
     pmn_scan<uint32_t, OpAddU32, false>(dcnt, dcnt_ex, nm + 1, S.scan_tmp.as<uint32_t>(), st);
     pmn_scan<long long, OpMaxI64x, true>(pkey, pkey, nm, S.scan_tmp.as<long long>(), st);
     k_ex_csum<<<gp, 256, 0, st>>>(X, cs);
-    if (o->do_extend) { k_ex_wave2<<<std::min<int>(blocks1, (int)((np + EX_WARPS_PER_BLOCK - 1) / EX_WARPS_PER_BLOCK)), EX_WARPS_PER_BLOCK * 32, smem, st>>>(X); launches++; }
     PMN_CUDA_OK(cudaEventRecord(c->ev[11], st));
     k_ex_stitch<<<blocks_st, EX_WARPS_PER_BLOCK * 32, smem, st>>>(X, fused);
     PMN_CUDA_OK(cudaEventRecord(c->ev[10], st));
@@ -2246,15 +2432,22 @@ int pmn_extend_impl(pmn_ctx *c, const pmn_index *ix, const pmn_seq *q, const pmn
         k_ex_errors<<<(unsigned)((nd + nal + 255) / 256), 256, 0, st>>>(X, al_syn, al_slot, nal, dstart, dflat, nd, sa_, sb_, errs);
         k_ex_rows<<<(unsigned)((nal + 255) / 256), 256, 0, st>>>(X, al_syn, al_slot, nal, errs, rows);
         launches += 9;
-        res->al_rows.resize((size_t)nal * 10);
-        res->al_deltas.resize((size_t)nd);
-        std::vector<uint32_t> ds((size_t)nal + 1);
-        PMN_D2H(c, res->al_rows.data(), rows, 80 * (size_t)nal);
-        if (nd) PMN_D2H(c, res->al_deltas.data(), dflat, 4 * (size_t)nd);
-        PMN_D2H(c, ds.data(), dstart, 4 * (size_t)(nal + 1));
+        // rows, deltas and offsets come back through the context's pinned staging buffer: three copies back to back and one
+        // wait (copies into pageable vectors are staged by the driver one after the other, 75 us of a 5 Mbp pair)
+        const size_t b_rows = 80 * (size_t)nal, b_del = 4 * (size_t)nd, b_off = 4 * (size_t)(nal + 1);
+        if (S.ensure_pinned(b_rows + b_del + b_off + 64)) return -3;         // hc is dead from here on
+        char *hp = (char *)S.pinned;
+        PMN_D2H(c, hp, rows, b_rows);
+        if (nd) PMN_D2H(c, hp + b_rows, dflat, b_del);
+        PMN_D2H(c, hp + b_rows + b_del, dstart, b_off);
         PMN_CUDA_OK(cudaStreamSynchronize(st));
         c->syncs++;
-        res->al_doff.assign(ds.begin(), ds.end());
+        res->al_rows.resize((size_t)nal * 10);
+        res->al_deltas.resize((size_t)nd);
+        memcpy(res->al_rows.data(), hp, b_rows);
+        if (nd) memcpy(res->al_deltas.data(), hp + b_rows, b_del);
+        const uint32_t *ds = (const uint32_t *)(hp + b_rows + b_del);
+        res->al_doff.assign(ds, ds + nal + 1);
     }
     PMN_CUDA_OK(cudaGetLastError());
     c->launches += launches;

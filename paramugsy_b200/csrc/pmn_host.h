@@ -92,6 +92,15 @@ struct pmn_ctx {
                                         // built by one worker is freed by whichever worker finishes its last pair)
     bool smem_attr_set = false;         // opt-in dynamic shared memory of the extension kernels (per device)
     std::vector<char> text_buf;         // grow-only staging of the .delta formatter (worst-case size, touched once)
+    // largest match -> next match window (cells) the thread-per-job kernel of the extension takes; larger ones are run by one warp
+    // each (eng_mid_full).  4096 is the shortest pair (the largest windows are the tail of the thread-per-job kernel: 0.57 -> 0.28 ms
+    // of a 5 Mbp pair) but 5 % more instructions per pair; a scheduler with many pairs in flight is bound by the instructions
+    // issued and asks for 10000 (pmn_sched.cu).  The results do not depend on it.
+    int tpj_cells = 4096;
+    // set by a scheduler around pmn_seq_from_fasta: called right before (phase 0) and right after (phase 1) the text of a genome
+    // is handed to the copy engine, so that the uploads of a batch reach the device in reference order (pmn_sched.cu)
+    void (*h2d_hook)(void *arg, int phase, cudaStream_t st) = nullptr;
+    void *h2d_hook_arg = nullptr;
 };
 
 // host<->device copies on the context's stream, counted for bench.py's e2e byte figures

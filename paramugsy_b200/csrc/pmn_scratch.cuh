@@ -41,7 +41,10 @@ struct Scratch {
     {
         if (bytes <= pinned_cap) return 0;
         if (pinned) cudaFreeHost(pinned);
-        size_t want = bytes + bytes / 4 + 4096;
+        // a power of two with as much again on top, 1 MB at least: results of the pairs a worker meets differ by tens of per cent,
+        // and every growth is a cudaFreeHost + cudaMallocHost that stalls the whole device
+        size_t want = (size_t)1 << 20;
+        while (want < 2 * bytes) want <<= 1;
         if (cudaMallocHost(&pinned, want) != cudaSuccess) { pinned = nullptr; pinned_cap = 0; return pmn_set_error(-3, "cudaMallocHost(%zu) failed", want); }
         pinned_cap = want;
         return 0;
