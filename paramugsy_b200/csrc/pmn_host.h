@@ -97,10 +97,6 @@ struct pmn_ctx {
     // of a 5 Mbp pair) but 5 % more instructions per pair; a scheduler with many pairs in flight is bound by the instructions
     // issued and asks for 10000 (pmn_sched.cu).  The results do not depend on it.
     int tpj_cells = 4096;
-    // set by a scheduler around pmn_seq_from_fasta: called right before (phase 0) and right after (phase 1) the text of a genome
-    // is handed to the copy engine, so that the uploads of a batch reach the device in reference order (pmn_sched.cu)
-    void (*h2d_hook)(void *arg, int phase, cudaStream_t st) = nullptr;
-    void *h2d_hook_arg = nullptr;
 };
 
 // host<->device copies on the context's stream, counted for bench.py's e2e byte figures

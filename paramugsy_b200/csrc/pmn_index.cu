@@ -141,9 +141,7 @@ int pmn_fasta_to_device(pmn_ctx *c, pmn_seq *s, const char *txt, size_t nb, cons
         S.ensure_pinned(8 * (size_t)(nrec + 2) + 64)) return -3;
     uint8_t *dtxt = S.k0.as<uint8_t>(); uint32_t *ev = S.v0.as<uint32_t>(), *keep = S.v1.as<uint32_t>(), *pos = S.k1.as<uint32_t>();
     int64_t *dhp = S.flags.as<int64_t>(); uint32_t *dout = (uint32_t *)(dhp + nrec + 1); uint32_t *anyx = dout + nrec + 2;
-    if (c->h2d_hook) c->h2d_hook(c->h2d_hook_arg, 0, st);
     PMN_H2D(c, dtxt, txt, nb);
-    if (c->h2d_hook) c->h2d_hook(c->h2d_hook_arg, 1, st);
     PMN_H2D(c, dhp, header_pos.data(), 8 * (size_t)nrec);
     PMN_CUDA_OK(cudaMemsetAsync(anyx, 0, 4, st));
     PMN_CUDA_OK(cudaMemsetAsync(S.codes.p, PMN_CODE_X, nb + 128, st));

@@ -49,40 +49,9 @@ struct pmn_sched {
     std::mutex bmu;
     std::condition_variable bcv;
     size_t total_mem = 0;               // device memory, read once (bounds the number of live indexes)
-    // uploads of a batch given as FASTA text: one event per genome (in upload order), the upload of genome k waits for the one
-    // before it, see sched_run
-    std::vector<cudaEvent_t> h2d_ev;
-    std::mutex hmu;
-    std::condition_variable hcv;
 };
 
 namespace {
-// one genome's turn in the upload order of a batch (pmn_ctx::h2d_hook)
-struct H2DTurn {
-    int *turn; pmn_sched *s; int rank; bool entered, passed;
-    static void hook(void *arg, int phase, cudaStream_t st)
-    {
-        H2DTurn *t = (H2DTurn *)arg;
-        if (phase == 0) {
-            { std::unique_lock<std::mutex> lk(t->s->hmu); t->s->hcv.wait(lk, [&] { return *t->turn >= t->rank; }); }
-            if (t->rank > 0) cudaStreamWaitEvent(st, t->s->h2d_ev[(size_t)t->rank - 1], 0);
-            t->entered = true;
-        } else {
-            cudaEventRecord(t->s->h2d_ev[(size_t)t->rank], st);
-            std::lock_guard<std::mutex> lk(t->s->hmu);
-            *t->turn = t->rank + 1; t->passed = true;
-            t->s->hcv.notify_all();
-        }
-    }
-    void give_up()
-    {
-        std::unique_lock<std::mutex> lk(s->hmu);
-        s->hcv.wait(lk, [&] { return *turn >= rank; });
-        if (*turn == rank) *turn = rank + 1;
-        passed = true;
-        s->hcv.notify_all();
-    }
-};
 struct BorrowedScratch {
     pmn_sched *s; pmn_ctx *c; Scratch *own;
     BorrowedScratch(pmn_sched *s_, pmn_ctx *c_) : s(s_), c(c_), own(c_->scratch)
@@ -126,7 +95,6 @@ extern "C" void pmn_sched_destroy(pmn_sched *s)
     if (!s) return;
     if (!s->ctx.empty()) cudaSetDevice(s->ctx[0]->device);
     for (Scratch *b : s->build_scratch) pmn_scratch_free(b);
-    for (cudaEvent_t e : s->h2d_ev) cudaEventDestroy(e);
     for (pmn_ctx *c : s->ctx) pmn_ctx_destroy(c);
     delete s;
 }
@@ -188,24 +156,6 @@ static int sched_run(pmn_sched *s, int ng, const char *const *fasta, const size_
         }
         if (const char *e = getenv("PMN_SCHED_LIVE_INDEXES")) MAX_LIVE_INDEXES = std::max(1, atoi(e));
     }
-    // upload order of the genomes given as text (see `pack` below): rank among the genomes some pair uses
-    std::vector<int> h2d_rank; int h2d_turn = 0;
-    static const bool h2d_order = !(getenv("PMN_SCHED_H2D_ORDER") && !strcmp(getenv("PMN_SCHED_H2D_ORDER"), "0"));
-    if (!resident && h2d_order) {
-        h2d_rank.assign((size_t)ng, -1);
-        int k = 0;
-        for (int g = 0; g < ng; g++) if (seqs[(size_t)g].users > 0 && seqs[(size_t)g].state == ST_NONE) h2d_rank[(size_t)g] = k++;
-        // A pack holds one of the scheduler's build scratch sets while it waits for its turn.  With no more genomes than sets, the
-        // packs of higher rank cannot hold all of them, so the one whose turn it is always gets a set; larger batches keep the
-        // unordered uploads.
-        if (k > (int)std::min<size_t>(s->ctx.size(), 8)) h2d_rank.clear();
-        cudaSetDevice(s->device);
-        while (!h2d_rank.empty() && (int)s->h2d_ev.size() < k) {
-            cudaEvent_t e = nullptr;
-            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); h2d_rank.clear(); break; }
-            s->h2d_ev.push_back(e);
-        }
-    }
     // few pairs: every pair's latency counts (thread-per-job windows up to 4096 cells, the rest one warp each); many pairs in
     // flight: the instructions issued count (pmn_ctx::tpj_cells)
     for (pmn_ctx *c : s->ctx) c->tpj_cells = np > 8 ? 10000 : 4096;
@@ -253,15 +203,7 @@ static int sched_run(pmn_sched *s, int ng, const char *const *fasta, const size_
         static const bool use_prio = !(getenv("PMN_SCHED_PRIORITIES") && !strcmp(getenv("PMN_SCHED_PRIORITIES"), "0"));
         auto pack = [&](int g) { return acquire(seqs, g, [&]() -> void * {
             BorrowedScratch b(s, c); OnStream on(c, use_prio ? pmn_ctx_prio_stream(c, 0) : nullptr);
-            // Uploads in genome order: eight 5 MB texts handed to the copy engines together share the link and all arrive at
-            // the end (0.8 ms for C2), while every pair of the batch waits for genome 0 and its index.  The upload of genome k
-            // waits (an event on its stream) for the upload of the genome before it; the host side takes turns only for the
-            // moment the copy is issued.
-            H2DTurn turn{ &h2d_turn, s, h2d_rank.empty() ? -1 : h2d_rank[(size_t)g], false, false };
-            if (turn.rank >= 0) { c->h2d_hook = &H2DTurn::hook; c->h2d_hook_arg = &turn; }
             pmn_seq *x = nullptr; const int rc = pmn_seq_from_fasta(c, fasta[g], bytes[g], &x);
-            c->h2d_hook = nullptr; c->h2d_hook_arg = nullptr;
-            if (turn.rank >= 0 && !turn.passed) turn.give_up();          // failed before its upload: the others must not wait for it
             return rc ? nullptr : (void *)x; }); };
         // genomes given as FASTA text: the workers pack them side by side first (H2D + parse + 2-bit pack per genome),
         // instead of every worker waiting for the reference of the first pairs and then packing its query alone

@@ -12,11 +12,17 @@ gs = synth.config_c2(n=n, count=8, inv_len=max(1000, n // 100))
 sched = lib.Scheduler(0, W); ctx = sched.context(0)
 seqs = [ctx.sequence(synth.fasta(*g)) for g in gs]; names = [g[0] for g in gs]
 pairs = [(i, j) for i in range(8) for j in range(i + 1, 8)]
+E2E = len(sys.argv) > 3 and sys.argv[3] == "e2e"       # FASTA text in pinned host memory -> .delta text (what bench.py's e2e arm times)
+pinned = [torch.frombuffer(bytearray(synth.fasta(*g)), dtype=torch.uint8).pin_memory() for g in gs] if E2E else []
+fasta_bytes = [(t.data_ptr(), t.numel()) for t in pinned]
+def step():
+    res = sched.align_fasta(fasta_bytes, pairs, names=names) if E2E else sched.align_seqs(seqs, pairs, names=names)
+    for r in res: r.close()
 for _ in range(3):
-    for r in sched.align_seqs(seqs, pairs, names=names): r.close()
+    step()
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-    for r in sched.align_seqs(seqs, pairs, names=names): r.close()
+    step()
     torch.cuda.synchronize()
 out = f"gpurun_out/trace_w{W}.json"
 prof.export_chrome_trace(out)
@@ -24,7 +30,7 @@ ev = json.load(open(out))["traceEvents"]
 k = [e for e in ev if e.get("cat") == "kernel"]
 rt = [e for e in ev if e.get("cat") in ("cuda_runtime", "cuda_driver")]
 mc = [e for e in ev if e.get("cat") in ("gpu_memcpy", "gpu_memset")]
-t0 = min(e["ts"] for e in k); t1 = max(e["ts"] + e["dur"] for e in k)
+t0 = min(e["ts"] for e in k + mc); t1 = max(e["ts"] + e["dur"] for e in k + mc)
 print(f"W={W}: {len(k)} kernels, {len(mc)} memcpy/memset, {len(rt)} runtime calls, span {(t1 - t0) / 1e3:.2f} ms")
 # union busy time
 iv = sorted((e["ts"], e["ts"] + e["dur"]) for e in k)
@@ -47,6 +53,12 @@ print(f"wide kernels (grid >= 100 blocks): {len(wide)}, union {union([(e['ts'], 
 for nm in ("k_ex_wave1", "k_seed", "k_ex_stitch", "k_cl_chains"):
     sel = [(e['ts'], e['ts'] + e['dur']) for e in k if e["name"].startswith(nm)]
     print(f"  union of {nm}: {union(sel) / 1e3:.2f} ms")
+if E2E:
+    big = sorted((e for e in mc if e.get("args", {}).get("bytes", 0) >= 1 << 20), key=lambda e: e["ts"])
+    print("copies of 1 MB and more (start ms, ms, MB, GB/s, stream):", [(round((e["ts"] - t0) / 1e3, 2), round(e["dur"] / 1e3, 2), round(e["args"]["bytes"] / 2**20, 1), round(e["args"]["bytes"] / e["dur"] / 1e3, 1), e["args"].get("stream")) for e in big])
+    fa = sorted((e for e in k if e["name"].startswith("k_pack") or e["name"].startswith("k_revcomp")), key=lambda e: e["ts"])
+    print("k_pack / k_revcomp ends (ms):", [round((e["ts"] + e["dur"] - t0) / 1e3, 2) for e in fa])
+    print("first copy or kernel at", round((min(e["ts"] for e in k + mc) - t0) / 1e3, 2), "ms relative to the first kernel")
 mallocs = [e for e in rt if e["name"] in ("cudaMalloc", "cudaFree", "cudaMallocHost", "cudaFreeHost")]
 print("allocation calls in the step:", [(e["name"], round(e["dur"] / 1e3, 2)) for e in mallocs])
 agg = collections.defaultdict(lambda: [0, 0.0])
