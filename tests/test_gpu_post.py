@@ -142,6 +142,22 @@ def test_front_ends_and_mirror(oracle, tmp_path):
     o2 = M.parse_argv(["-ref_seq", str(rp), "-query_seq", str(qp), "-maf_out", "c.maf", "-delta_out", "c.delta", "-out_dir", str(outd), "-tmp_dir", str(tmpd), "-colinear"])
     M.run_search(o2)
     assert (outd / "c.delta").read_bytes() == oracle.delta_filter(oracle.nucmer(ref, qry, str(rp), str(qp), fast_chain=1), 2)
+    # -delta_pp (lib/nucmer/mugsy_nucmer.ml:107-114): the filtered delta is piped through the post-processor into nucmer.pp.delta,
+    # which is what delta_out and the MAF come from; a program that does not exist is a Failure
+    o3 = M.parse_argv(["-ref_seq", str(rp), "-query_seq", str(qp), "-maf_out", "pp.maf", "-delta_out", "pp.delta", "-out_dir", str(outd), "-tmp_dir", str(tmpd),
+                       "-delta_pp", "head -c 100000000"])
+    M.run_search(o3)
+    assert (tmpd / "nucmer.pp.delta").read_bytes() == want == (outd / "pp.delta").read_bytes()
+    assert (outd / "pp.maf").read_bytes() == oracle.delta2maf(want, ref, qry)
+    o4 = M.parse_argv(["-ref_seq", str(rp), "-query_seq", str(qp), "-maf_out", "x.maf", "-delta_out", "x.delta", "-out_dir", str(outd), "-tmp_dir", str(tmpd),
+                       "-delta_pp", "no-such-delta-post-processor"])
+    with pytest.raises(M.Failure):
+        M.run_search(o4)
+    # main (lib/nucmer/mugsy_nucmer.ml:134-140): makes the directories, runs the search, removes tmp_dir
+    out2, tmp2 = tmp_path / "out2", tmp_path / "tmp2"
+    M.main(["-ref_seq", str(rp), "-query_seq", str(qp), "-maf_out", "m.maf", "-delta_out", "m.delta", "-out_dir", str(out2), "-tmp_dir", str(tmp2)])
+    assert (out2 / "m.delta").read_bytes() == want and (out2 / "m.maf").read_bytes() == oracle.delta2maf(want, ref, qry)
+    assert not tmp2.exists()
 
 
 def test_post_steps_inside_the_batch_call(oracle):

@@ -1,6 +1,6 @@
 #!/bin/bash
 # One GPU visit (run under gpurun): tools/gpu_visit.sh <tag> [steps...]
-#   steps: tests smoke bench bench_ref ncu_launches ncu_full  (default: tests smoke bench)
+#   steps: tests smoke bench bench_ref ncu_launches ncu_pair ncu_full sweep multi multic trace c4 configs stress stitchprof diag  (default: tests smoke bench)
 # Everything lands in gpurun_out/<tag>_*.  Each step has its own timeout, a failing step does not stop the others.
 tag=${1:-visit}; shift
 steps=${@:-tests smoke bench}
@@ -14,7 +14,7 @@ for s in $steps; do
     bench_ref) timeout 900 python bench.py --impl reference --steps 1 --warmup 1 > gpurun_out/${tag}_bench_ref.json 2> gpurun_out/${tag}_bench_ref.err; echo "ref rc=$?"; head -c 300 gpurun_out/${tag}_bench_ref.json; echo ;;
     ncu_launches) timeout 900 ncu --metrics gpu__time_duration.sum,sm__cycles_active.avg,smsp__inst_executed.sum --clock-control none --csv --log-file gpurun_out/${tag}_launches_bench.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/${tag}_ncu_launches.log 2>&1; echo "ncu launches rc=$?" ;;
     ncu_pair) timeout 900 ncu --metrics gpu__time_duration.sum,sm__cycles_active.avg,smsp__inst_executed.sum --clock-control none --csv --log-file gpurun_out/launches_pair.csv python tools/profile_pair.py 5000000 2 > gpurun_out/${tag}_ncu_pair.log 2>&1; echo "ncu pair rc=$?"; cp gpurun_out/launches_pair.csv gpurun_out/${tag}_launches_pair.csv ;;
-    ncu_full) timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:k_ex_wave1|k_ex_wave2|k_ex_stitch|k_seed$|k_cl_chains|pmn_rs_scatter|k_bucket_fill|k_skip_fill|k_present_fill" -c 24 -o gpurun_out/pair_full -f python tools/profile_pair.py 5000000 1 > gpurun_out/${tag}_ncu_full.log 2>&1; echo "ncu full rc=$?" ;;
+    ncu_full) timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:k_ex_wave1|k_ex_targets|k_ex_jobdesc|k_ex_stitch|k_seed$|k_cl_chains|pmn_rs_scatter|k_bucket_fill|k_skip_fill|k_present_fill" -c 24 -o gpurun_out/pair_full -f python tools/profile_pair.py 5000000 1 > gpurun_out/${tag}_ncu_full.log 2>&1; echo "ncu full rc=$?" ;;
     sweep)   # tools/sweep.txt: one run per line, "<name> [VAR=value ...] -- <bench.py arguments>"
              while read -r name rest; do
                [ -z "$name" ] && continue; case $name in \#*) continue;; esac
@@ -46,6 +46,11 @@ for f in sys.argv[1:]:
         print(f, "FAILED", e)
 P
              ;;
+    multic)  # GPUS=N: pmn_multi (one process, N real devices through the C ABI): C2 digests + timed steps, a 20 Mbp pair cut over the devices
+             N=${GPUS:-2}; timeout 600 python tools/multi_c_check.py $N 10 20000000 > gpurun_out/${tag}_multi_c_${N}gpu.json 2> gpurun_out/${tag}_multi_c_${N}gpu.err; echo "multi_c x$N rc=$?"; tail -1 gpurun_out/${tag}_multi_c_${N}gpu.json | cut -c1-900 ;;
+    trace)   timeout 300 python tools/trace_pair.py > gpurun_out/${tag}_trace_pair.txt 2>&1; head -3 gpurun_out/${tag}_trace_pair.txt | tail -1 | cut -c1-300
+             timeout 300 python tools/trace_pair.py 5000000 index > gpurun_out/${tag}_trace_index.txt 2>&1
+             timeout 300 python tools/trace_step.py 32 > gpurun_out/${tag}_trace_w32.log 2>&1; sed -n 3,4p gpurun_out/${tag}_trace_w32.log ;;
     c4)      timeout 900 python bench.py --config c4 --steps 6 --warmup 2 > gpurun_out/${tag}_c4_1gpu.json 2> gpurun_out/${tag}_c4_1gpu.err; echo "c4 rc=$?"; head -c 600 gpurun_out/${tag}_c4_1gpu.json; echo ;;
     configs) timeout 600 python tools/run_configs.py c5 > gpurun_out/${tag}_c5.json 2> gpurun_out/${tag}_c5.err; echo "c5 rc=$?"
              timeout 900 python tools/run_configs.py c3 > gpurun_out/${tag}_c3.json 2> gpurun_out/${tag}_c3.err; echo "c3 rc=$?"; tail -c 400 gpurun_out/${tag}_c3.json; echo ;;
