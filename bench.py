@@ -23,6 +23,7 @@ inversions each), all-vs-all = 28 (reference, query) pairs, the earlier genome b
 """
 import argparse
 import hashlib
+import gc
 import json
 import math
 import os
@@ -154,11 +155,16 @@ class Ranks:
         self.barrier()
         c0 = counters() if counters else {}; a0 = allocs() if allocs else 0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # no cyclic garbage collection inside the timed region (what timeit does): the path measured is a C library, and a
+        # full collection of this process (torch imported, every .delta of the parity pass alive) is tens of milliseconds —
+        # one such pause in a region of ten 12 ms steps is a fifth of the number
+        gc.collect(); gc.disable()
         e0.record()
         walls = []
         for _ in range(steps):
             t = time.perf_counter(); fn(); walls.append((time.perf_counter() - t) * 1e3)
         e1.record()
+        gc.enable()
         self.barrier()
         ms = e0.elapsed_time(e1)
         ranks_ms = [round(ms / steps, 3)]
