@@ -82,8 +82,8 @@ def sha(b):
 
 class ClockSampler:
     """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md)."""
-    # no power.draw: that query stalls the device for tens of milliseconds now and then (tools/outlier_probe.py: one e2e step of
-    # 150 took 35-39 ms instead of 13 / 19 with it, none of 300 without it) — a 10-step timed region with one such step is 10-30 % off
+    # no power.draw: in tools/outlier_probe.py the only long e2e steps (35-39 ms instead of 13 / 19, one in 150) came with it in the
+    # query; a 10-step timed region with one such step is 10-30 % off.  (It is not the only source: see DESIGN.md §6.)
     Q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
