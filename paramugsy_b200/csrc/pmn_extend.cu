@@ -13,11 +13,17 @@
 //       cluster list (match -> next match inside a cluster; last match -> target cluster),
 //       so all of them run at once: small match -> next match windows one THREAD per job
 //       (k_ex_wave1_tpj, full matrix in register strips), cluster ends and large windows one
-//       warp per job (k_ex_wave1_big, the banded engine), persistent warps pulling jobs
+//       warp per job (k_ex_wave1_big: the banded engine; windows up to 100 x 100 that are too
+//       large for a thread as a systolic full matrix, eng_mid_full), persistent warps pulling
+//       jobs.  The targets of the cluster-end jobs come from k_ex_targets (one warp per
+//       cluster).  The backward extension of every cluster that no end job reaches runs in the
+//       same kernel: first for the clusters nobody aims at, and by the warp whose end job is the
+//       last to fail for the others (aimers / aimfail).
 //   E3  STITCH, one warp per synteny: the sequential control flow of extendClusters
-//       (merging, shadow test, backward extension) consumes the wave-1 results; the few
-//       alignments that depend on earlier outcomes (backward searches, forced merges) run
-//       inline on the same warp with the same engine
+//       (merging, shadow test, backward extension) consumes the wave-1 results — runs of
+//       clusters that hand over to their successor 32 at a time, one node per cluster — and
+//       the few alignments that depend on earlier outcomes (backward searches the cap cut
+//       short, forced merges) run inline on the same warp with the same engine
 //   E4  flatten the delta lists, count errors (parseDelta), copy to the host
 //
 // The engine is an anti-diagonal DP: the cells of one anti-diagonal are striped over the 32
